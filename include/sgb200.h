@@ -1,0 +1,234 @@
+/*
+ * sgb200.h -- C ABI of libsgb200.so: the B200 (sm_100a) hot path behind SuperGradients' YOLO-NAS / ResNet
+ * training and inference modules.
+ *
+ * The reference (Deci-AI/super-gradients) has no FFI: every kernel on this path is reached through
+ * torch.nn / torchvision calls inside Python nn.Modules.  Each entry point below therefore cites the reference
+ * call site (file:line under src/super_gradients/) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - activations are NHWC bf16 (uint16_t storage) with an explicit channel pitch and channel offset, so a tensor
+ *     may be a channel slice of a wider NHWC buffer (concat-free CSP layers);
+ *   - functions never allocate, never synchronise; they enqueue on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative SGB_E_* code on error (no exceptions cross the boundary).
+ */
+#ifndef SGB200_H_
+#define SGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB_OK 0
+#define SGB_E_INVALID (-1)     /* bad shape / argument */
+#define SGB_E_UNSUPPORTED (-2) /* valid but not implemented for this configuration */
+#define SGB_E_CUDA (-3)        /* a CUDA runtime / driver call failed (see sgb_last_error) */
+#define SGB_E_ARCH (-4)        /* device is not sm_100 */
+
+#define SGB_ACT_NONE 0
+#define SGB_ACT_RELU 1
+#define SGB_ACT_SILU 2
+
+typedef uint16_t sgb_bf16; /* raw bfloat16 bits */
+
+/* Convolution problem, cuDNN-style names.  Weights are KRSC (out-ch, kh, kw, in-ch) bf16 for fprop/wgrad and
+ * CRSK for dgrad (sgb_weight_prepare makes both from the fp32 OIHW master copy). */
+typedef struct SgbConvDesc {
+  int32_t N, H, W, C; /* input batch, height, width, channels (C % 8 == 0) */
+  int32_t K, R, S;    /* output channels, filter height / width */
+  int32_t P, Q;       /* output height / width */
+  int32_t stride, pad;
+  int32_t x_pitch, x_off; /* channel pitch / offset of the buffer holding the input  (elements) */
+  int32_t y_pitch, y_off; /* channel pitch / offset of the buffer holding the output (elements) */
+  int32_t up2;            /* 1: ConvTranspose2d(k=2,s=2) mode -- see sgb_convt2x2_* */
+} SgbConvDesc;
+
+/* Fused epilogue of the forward implicit GEMM.  All pointers may be NULL. */
+typedef struct SgbEpilogue {
+  const float* scale;       /* [K]  y = acc*scale + shift   (inference: folded BN) */
+  const float* shift;       /* [K]  also used as plain bias when scale == NULL */
+  const sgb_bf16* residual; /* same geometry as y; added before the activation */
+  double* stats;            /* [stats_repl][2][K] running sums of y and y*y over all pixels (train-mode BN) */
+  int32_t stats_repl;       /* number of replicas of the stats buffer (power of two, >= 1) */
+  int32_t act;              /* SGB_ACT_* */
+  int32_t out_f32;          /* 1: y is float32 (parity tests of the accumulators); 0: bf16 */
+} SgbEpilogue;
+
+const char* sgb_last_error(void);
+int sgb_version(void);
+/* 0 if the current device is sm_100 and the library was built for it. */
+int sgb_check_device(void);
+
+/* ---- convolution family (rows C1-C5, C8, C10 of SURVEY.md section 8a) --------------------------------------
+ * replaces nn.Conv2d forward in modules/qarepvgg_block.py:184-204, modules/conv_bn_act_block.py:92-93,
+ * training/models/classification_models/resnet.py:53-84, dfl_heads.py:65-66, and their autograd backward
+ * (training/sg_trainer/sg_trainer.py:622). */
+int sgb_conv_fprop(const SgbConvDesc* d, const sgb_bf16* x, const sgb_bf16* w_krsc, void* y, const SgbEpilogue* ep,
+                   void* stream);
+/* dx = conv_transpose(dy, w).  accumulate != 0: dx += result (dx is read-modify-written). */
+int sgb_conv_dgrad(const SgbConvDesc* d, const sgb_bf16* dy, const sgb_bf16* w_crsk, sgb_bf16* dx, int accumulate,
+                   void* stream);
+/* dw_krsc (fp32, KRSC) += dy^T * im2col(x).  Split-K partial sums are reduced with fp32 atomics: the caller
+ * zeroes dw_krsc.  */
+int sgb_conv_wgrad(const SgbConvDesc* d, const sgb_bf16* x, const sgb_bf16* dy, float* dw_krsc, void* stream);
+/* fp32 OIHW master weights -> bf16 KRSC (+ optional CRSK), zero-padding C up to c_pad. `scale` (may be NULL) is
+ * a single device float multiplied into every weight; add_identity adds 1 to the centre tap of channel k==c. */
+int sgb_weight_prepare(const float* w_oihw, int K, int C, int R, int S, int c_pad, sgb_bf16* w_krsc, sgb_bf16* w_crsk,
+                       const float* scale, int add_identity, void* stream);
+/* fp32 KRSC (c_pad channels) gradient -> fp32 OIHW gradient; accumulate != 0 adds into g_oihw. */
+int sgb_wgrad_to_oihw(const float* dw_krsc, int K, int C, int R, int S, int c_pad, float* g_oihw, int accumulate,
+                      void* stream);
+/* ConvTranspose2d(kernel=2, stride=2) (modules/sampling.py:72-73): desc describes the EQUIVALENT 2x2/s2 convolution
+ * from the upsampled tensor (N,H,W,C) to the small tensor (N,P,Q,K); w is [K_small][2][2][C_up] bf16. */
+int sgb_convt2x2_fprop(const SgbConvDesc* d, const sgb_bf16* x_small, const sgb_bf16* w_up, const float* bias,
+                       sgb_bf16* y_up, void* stream);
+
+/* ---- layout ---------------------------------------------------------------------------------------------- */
+int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, sgb_bf16* y, int y_pitch, int y_off,
+                              void* stream);
+int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H, int W, int x_pitch, int x_off, float* y,
+                              void* stream);
+
+/* ---- BatchNorm (train) + residual + activation (row C9; nn.BatchNorm2d semantics, momentum / eps overridden by
+ * customizable_detector.py:97-104) -------------------------------------------------------------------------- */
+typedef struct SgbBnDesc {
+  int64_t M;                     /* pixels = N*H*W */
+  int32_t C;                     /* channels */
+  int32_t x_pitch, x_off;        /* pre-BN tensor */
+  int32_t y_pitch, y_off;        /* output tensor */
+  int32_t r_pitch, r_off;        /* residual tensor (if any) */
+  float eps, momentum;
+  int32_t act;
+  int32_t stats_repl;
+} SgbBnDesc;
+/* Reduces stats -> mean / rstd (saved for backward), updates running stats, writes y = act(bn(x) + residual). */
+int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, const sgb_bf16* residual, sgb_bf16* y, float* save_mean,
+                   float* save_rstd, void* stream);
+/* Inference-mode BN (running stats) + residual + activation. */
+int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const float* gamma, const float* beta,
+                     const float* running_mean, const float* running_var, const sgb_bf16* residual, sgb_bf16* y,
+                     void* stream);
+/* Backward, pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat with dz = dy * act'(y). */
+int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
+                          const float* save_mean, const float* save_rstd, double* sums, void* stream);
+/* Backward, pass 2: dx (pre-BN grad), dresidual (= dz, optional), dgamma / dbeta (+=). */
+int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
+                         const float* gamma, const float* save_mean, const float* save_rstd, const double* sums,
+                         sgb_bf16* dx, sgb_bf16* dresidual, float* dgamma, float* dbeta, void* stream);
+/* Per-channel sums of an NHWC bf16 tensor (used where the producer is not one of our GEMMs). */
+int sgb_channel_stats(const sgb_bf16* x, int64_t M, int C, int pitch, int off, double* stats, void* stream);
+
+/* ---- QARepVGG train-mode branch algebra (modules/qarepvgg_block.py:184-204) ---------------------------------
+ * y3 = conv3x3(x) (raw), u = conv1x1_{alpha*K1 + I}(x) (raw, identity folded into the 1x1 weights).
+ * z = s3*(y3 - mu3) + beta3 + u + alpha*b1 ;  out = act(post_bn(z)).
+ * moments: [stats_repl][5][C] doubles = sum y3, y3^2, u, u^2, y3*u (produced by sgb_qarep_moments).         */
+typedef struct SgbQarepDesc {
+  int64_t M;
+  int32_t C;
+  int32_t pitch3, off3, pitchu, offu, pitcho, offo;
+  float eps3, eps_post, momentum;
+  int32_t act;
+  int32_t use_post_bn;
+} SgbQarepDesc;
+int sgb_qarep_moments(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments, void* stream);
+/* coef out: [9][C] floats = mu3, rstd3, mu_u, rstd_z, a3 (coefficient of y3), au (of u), c0 (constant),
+ * mean(zhat*y3hat), s3 = gamma3*rstd3 */
+int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, const double* moments,
+                  const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
+                  const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out, float* coef,
+                  void* stream);
+/* pass 1: sums [3][C] = sum dzp, sum dzp*zhat, sum dzp*y3hat, dzp = dout*act'(out). */
+int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out, const sgb_bf16* y3,
+                         const sgb_bf16* u, const float* coef, double* sums, void* stream);
+/* pass 2: dy3, du (bf16), param grads (+=): dgamma3, dbeta3, dbias1a (grad of alpha*b1), dgamma_p, dbeta_p. */
+int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out, const sgb_bf16* y3,
+                        const sgb_bf16* u, const float* coef, const double* sums, const float* gamma3,
+                        const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du, float* dgamma3, float* dbeta3,
+                        float* dbias1a, float* dgamma_p, float* dbeta_p, void* stream);
+
+/* ---- pooling / elementwise (rows C6, C7, C8) --------------------------------------------------------------- */
+/* stride-`stride` max-pool k x k, pad k/2 (csp_darknet53.py:135-157 SPP; resnet.py maxpool 3/2/1). idx (int8,
+ * optional) records the arg-max tap for the backward pass. */
+int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, int x_pitch, int x_off, int k, int stride, int pad,
+                    sgb_bf16* y, int P, int Q, int y_pitch, int y_off, uint8_t* idx, void* stream);
+int sgb_maxpool_bwd(const sgb_bf16* dy, int N, int H, int W, int C, int k, int stride, int pad, int P, int Q,
+                    int dy_pitch, int dy_off, const uint8_t* idx, float* dx_f32, void* stream);
+/* y[slice] = a*x1 + b*x2 (x2 optional) over NHWC bf16 slices: concat copies, residual adds, grad accumulation */
+int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_bf16* x2, int p2, int o2, float b, sgb_bf16* y,
+              int py, int oy, int64_t M, int C, void* stream);
+int sgb_f32_to_bf16(const float* x, sgb_bf16* y, int64_t n, void* stream);
+/* global average pool NHWC bf16 -> [N, C] bf16 and its backward */
+int sgb_avgpool_fwd(const sgb_bf16* x, int N, int HW, int C, sgb_bf16* y, void* stream);
+int sgb_avgpool_bwd(const sgb_bf16* dy, int N, int HW, int C, sgb_bf16* dx, void* stream);
+
+/* ---- DFL head decode (row L0: dfl_heads.py:199-245, bbox_utils.py:9-29) --------------------------------------
+ * per level: reg [N, HW, reg_pitch] bf16 (4*(reg_max+1) logits), cls [N, HW, cls_pitch] bf16 -> writes rows
+ * [anchor_base, anchor_base + HW) of pred_bboxes [N, L, 4] f32 (xyxy, pixels), pred_scores [N, L, ncls] f32
+ * (sigmoid), and optionally the raw fp32 copies cls_logits [N, L, ncls], reg_distri [N, L, 4*(reg_max+1)]. */
+int sgb_dfl_decode(const sgb_bf16* reg, int reg_pitch, const sgb_bf16* cls, int cls_pitch, int N, int Hf, int Wf,
+                   int L, int anchor_base, int ncls, int reg_max, float stride, float cell_offset, float* pred_bboxes,
+                   float* pred_scores, float* cls_logits, float* reg_distri, void* stream);
+
+/* ---- PPYoloE / YOLO-NAS loss (rows L1-L6: training/losses/ppyolo_loss.py) ----------------------------------- */
+typedef struct SgbLossDesc {
+  int32_t B, L, ncls, reg_max; /* batch, anchors, classes, DFL bins - 1 */
+  int32_t n_max;               /* padded number of GT boxes per image */
+  int32_t topk;                /* TAL top-k (13) */
+  float alpha, beta;           /* TAL exponents (1, 6) */
+  float w_cls, w_iou, w_dfl;   /* 1.0, 2.5, 0.5 */
+  int32_t iou_type;            /* 0 = GIoU (PPYoloELoss), 1 = CIoU (YoloNASPoseLoss) */
+} SgbLossDesc;
+/* Task-aligned assigner (ppyolo_loss.py:454-561). gt_boxes [B, n_max, 4] xyxy pixels, gt_labels [B, n_max] int32,
+ * gt_valid [B, n_max] uint8.  Outputs: assigned_label [B, L] int32 (ncls = background), assigned_box [B, L, 4],
+ * assigned_score [B, L] f32 (the single non-zero entry of the reference's one-hot * metric row). */
+int sgb_tal_assign(const SgbLossDesc* d, const float* cls_logits, const float* reg_distri, const float* anchor_points,
+                   const float* stride_tensor, const float* gt_boxes, const int32_t* gt_labels, const uint8_t* gt_valid,
+                   int32_t* assigned_label, float* assigned_box, float* assigned_score, double* sums, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+int64_t sgb_tal_workspace_bytes(const SgbLossDesc* d);
+/* Varifocal + GIoU/CIoU + DFL loss, forward and backward in one launch (ppyolo_loss.py:944-1084).
+ * sums [4] doubles: sgb_tal_assign has already added sum(assigned_score) into sums[3] (the normaliser, clipped at 1);
+ * this call adds {cls_sum, iou_sum, dfl_sum} into sums[0..2] and writes the FINAL gradients of
+ * grad_scale * (w_cls*cls + w_iou*iou + w_dfl*dfl) / normaliser  w.r.t. the logits (grad_cls / grad_reg may be NULL). */
+int sgb_dfl_iou_loss_fwd_bwd(const SgbLossDesc* d, const float* cls_logits, const float* reg_distri,
+                             const float* anchor_points, const float* stride_tensor, const int32_t* assigned_label,
+                             const float* assigned_box, const float* assigned_score, double* sums, float grad_scale,
+                             float* grad_cls, float* grad_reg, void* stream);
+/* loss_out [4] = {cls, iou, dfl, total} (weighted, normalised) -- the reference's log_losses. */
+int sgb_loss_finalize(const SgbLossDesc* d, const double* sums, float* loss_out, void* stream);
+/* d(raw fp32 logits [N, L, gC]) -> bf16 NHWC head-output gradient of one level (rows anchor_base..+HW). */
+int sgb_head_grad_scatter(const float* grad, int gC, int N, int HW, int L, int anchor_base, sgb_bf16* dy, int pitch,
+                          void* stream);
+
+/* ---- batched NMS (rows N1-N5: pp_yolo_e/post_prediction_callback.py:42-98 + torchvision.ops.batched_nms) ---- */
+typedef struct SgbNmsDesc {
+  int32_t B, L, ncls;
+  float score_thr;
+  double iou_thr; /* compared in double, as torchvision's CPU kernel does */
+  int32_t top_k, max_out;
+  int32_t multi_label;    /* 1: every (anchor, class) above threshold is a candidate; 0: arg-max class only */
+  int32_t class_agnostic; /* 1: torchvision.ops.nms ; 0: batched_nms (coordinate-offset trick) */
+  int32_t thr_inclusive;  /* 1: score >= thr (pose callback / single-label), 0: score > thr (multi-label) */
+} SgbNmsDesc;
+int64_t sgb_nms_workspace_bytes(const SgbNmsDesc* d);
+/* boxes [B, L, 4] f32 xyxy, scores [B, L, ncls] f32. out [B, max_out, 6] f32 rows (x1,y1,x2,y2,conf,label) in the
+ * reference's order, out_idx [B, max_out] int32 = flat candidate index anchor*ncls + class, out_count [B] int32. */
+int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const float* scores, float* out, int32_t* out_idx,
+                    int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- optimizer over the flat parameter buffer (sg_trainer.py:634-644) --------------------------------------- */
+int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float wd, float grad_scale,
+                 int nesterov, void* stream);
+int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                   float wd, float bias1, float bias2, float grad_scale, void* stream);
+int sgb_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB200_H_ */

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libsgb200.so (sm_100a only) in-tree.  Usage: build.sh [extra nvcc flags]
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/../libsgb200.so"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE" --expt-relaxed-constexpr)
+mkdir -p "$HERE/obj"
+pids=()
+for f in "$HERE"/*.cu; do
+  o="$HERE/obj/$(basename "${f%.cu}").o"
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$ROOT/include/sgb200.h" -nt "$o" ]]; then
+    "$NVCC" "${FLAGS[@]}" "$@" -c "$f" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+"$NVCC" -shared -o "$OUT" "$HERE"/obj/*.o -lcudart
+echo "built $OUT"

@@ -1,0 +1,909 @@
+// Memory-bound companions of the convolution GEMMs: weight layout/cast, NCHW<->NHWC, train/infer BatchNorm with
+// fused residual + activation (forward and both backward passes), the QARepVGG branch algebra, pooling, axpby and
+// the flat-buffer optimizers.  All tensors are NHWC bf16 with channel pitch/offset; every kernel moves 16-byte
+// vectors (8 channels) per thread with consecutive threads on consecutive channel vectors (coalesced), per-channel
+// reductions go registers -> shared atomics -> one fp64 global atomic per channel per CTA.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+struct V8 {
+  float v[8];
+};
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  V8 o;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o.v[2 * i] = f.x;
+    o.v[2 * i + 1] = f.y;
+  }
+  return o;
+}
+__device__ __forceinline__ void st8(bf16* p, const V8& a) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+inline int grid_for(int64_t work, int per_cta = TPB, int max_ctas = 148 * 8) {
+  int64_t g = (work + per_cta - 1) / per_cta;
+  if (g > max_ctas) g = max_ctas;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------- weights / layout
+__global__ void weight_prepare_kernel(const float* __restrict__ w, int K, int C, int R, int S, int cp, bf16* krsc,
+                                      bf16* crsk, const float* scale, int add_identity) {
+  // krsc: [K][R][S][cp];  crsk: [cp rows? no: C rows][R][S][Kp]  (Kp = K rounded up to 8)
+  const int Kp = ((K + 7) / 8) * 8;
+  const float sc = scale ? *scale : 1.f;
+  const int64_t n1 = (int64_t)K * R * S * cp;
+  const int64_t n2 = crsk ? (int64_t)C * R * S * Kp : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      int c = i % cp;
+      int64_t t = i / cp;
+      int s = t % S; t /= S;
+      int r = t % R;
+      int k = t / R;
+      float v = 0.f;
+      if (c < C) {
+        v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
+        if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
+      }
+      krsc[i] = __float2bfloat16_rn(v);
+    } else {
+      int64_t j = i - n1;
+      int k = j % Kp;
+      int64_t t = j / Kp;
+      int s = t % S; t /= S;
+      int r = t % R;
+      int c = t / R;
+      float v = 0.f;
+      if (k < K) {
+        v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
+        if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
+      }
+      crsk[j] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+__global__ void wgrad_to_oihw_kernel(const float* __restrict__ dw, int K, int C, int R, int S, int cp, float* g,
+                                     int accumulate) {
+  const int64_t n = (int64_t)K * C * R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = i % S;
+    int64_t t = i / S;
+    int r = t % R; t /= R;
+    int c = t % C;
+    int k = t / C;
+    float v = dw[(((int64_t)k * R + r) * S + s) * cp + c];
+    g[i] = accumulate ? g[i] + v : v;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W, bf16* y, int pitch,
+                                    int off, int cpad) {
+  // one thread per (n, h, w, cvec) writes 8 channels; reads are strided by H*W but coalesced across w.
+  const int64_t hw = (int64_t)H * W;
+  const int cv = cpad / 8;
+  const int64_t total = (int64_t)N * cv * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pixel = i % hw;
+    int64_t t = i / hw;
+    int v = t % cv;
+    int n = t / cv;
+    V8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = v * 8 + e;
+      o.v[e] = c < C ? x[((int64_t)n * C + c) * hw + pixel] : 0.f;
+    }
+    st8(y + ((int64_t)n * hw + pixel) * pitch + off + v * 8, o);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, int H, int W, int pitch, int off,
+                                    float* y) {
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)N * C * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pixel = i % hw;
+    int64_t t = i / hw;
+    int c = t % C;
+    int n = t / C;
+    y[i] = __bfloat162float(x[((int64_t)n * hw + pixel) * pitch + off + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- channel reductions
+// Generic per-channel reduction skeleton.  F::NACC sums per channel;  F::eval(pix, c0, acc[NACC][8]) accumulates the
+// contribution of 8 consecutive channels of one pixel.
+template <class F>
+__global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C, double* out, int out_stride) {
+  constexpr int NACC = F::NACC;
+  extern __shared__ float sred[];  // [NACC][cvb*8]
+  const int cvs = C / 8;
+  const int cvb = cvs < TPB ? cvs : TPB;  // channel vectors per CTA pass
+  const int lanes = TPB / cvb;
+  const int t = threadIdx.x;
+  const int pl = t / cvb, cvi = t % cvb;
+  const int64_t pix_per_cta = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * pix_per_cta;
+  int64_t p1 = p0 + pix_per_cta;
+  if (p1 > M) p1 = M;
+  for (int cv0 = 0; cv0 < cvs; cv0 += cvb) {
+    for (int i = t; i < NACC * cvb * 8; i += TPB) sred[i] = 0.f;
+    __syncthreads();
+    const int cv = cv0 + cvi;
+    if (pl < lanes && cv < cvs) {
+      float acc[NACC][8];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+      for (int64_t pix = p0 + pl; pix < p1; pix += lanes) f.eval(pix, cv * 8, acc);
+#pragma unroll
+      for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sred[(a * cvb + cvi) * 8 + e], acc[a][e]);
+    }
+    __syncthreads();
+    for (int i = t; i < NACC * cvb * 8; i += TPB) {
+      int a = i / (cvb * 8), r = i % (cvb * 8);
+      int c = cv0 * 8 + r;
+      if (c < C) atomicAdd(&out[(int64_t)a * out_stride + c], (double)sred[i]);
+    }
+    __syncthreads();
+  }
+}
+
+template <class F>
+int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaStream_t st) {
+  int cvs = C / 8;
+  int cvb = cvs < TPB ? cvs : TPB;
+  size_t smem = (size_t)F::NACC * cvb * 8 * sizeof(float);
+  int64_t want = (M + 255) / 256;  // >= 256 pixels per CTA
+  int grid = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+  chan_reduce_kernel<F><<<grid, TPB, smem, st>>>(f, M, C, out, out_stride);
+  SGB_LAUNCH_CHECK("chan_reduce_kernel");
+  return SGB_OK;
+}
+
+struct StatsF {
+  static constexpr int NACC = 2;
+  const bf16* x;
+  int pitch, off;
+  __device__ void eval(int64_t pix, int c0, float (&acc)[2][8]) const {
+    V8 a = ld8(x + pix * pitch + off + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += a.v[e];
+      acc[1][e] += a.v[e] * a.v[e];
+    }
+  }
+};
+
+struct QarepMomF {
+  static constexpr int NACC = 5;
+  const bf16 *y3, *u;
+  int p3, o3, pu, ou;
+  __device__ void eval(int64_t pix, int c0, float (&acc)[5][8]) const {
+    V8 a = ld8(y3 + pix * p3 + o3 + c0), b = ld8(u + pix * pu + ou + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += a.v[e];
+      acc[1][e] += a.v[e] * a.v[e];
+      acc[2][e] += b.v[e];
+      acc[3][e] += b.v[e] * b.v[e];
+      acc[4][e] += a.v[e] * b.v[e];
+    }
+  }
+};
+
+struct BnBwdRedF {
+  static constexpr int NACC = 2;
+  const bf16 *dy, *x, *y;
+  const float *mean, *rstd;
+  int xp, xo, yp, yo, act;
+  __device__ void eval(int64_t pix, int c0, float (&acc)[2][8]) const {
+    V8 g = ld8(dy + pix * yp + yo + c0), xv = ld8(x + pix * xp + xo + c0), yv = ld8(y + pix * yp + yo + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = g.v[e];
+      if (act == SGB_ACT_RELU) dz = yv.v[e] > 0.f ? dz : 0.f;
+      float xh = (xv.v[e] - mean[c0 + e]) * rstd[c0 + e];
+      acc[0][e] += dz;
+      acc[1][e] += dz * xh;
+    }
+  }
+};
+
+struct QarepBwdRedF {
+  static constexpr int NACC = 3;
+  const bf16 *dout, *out, *y3, *u;
+  const float* coef;  // [8][C]
+  int C, p3, o3, pu, ou, po, oo, act, post;
+  __device__ void eval(int64_t pix, int c0, float (&acc)[3][8]) const {
+    V8 g = ld8(dout + pix * po + oo + c0), ov = ld8(out + pix * po + oo + c0);
+    V8 a = ld8(y3 + pix * p3 + o3 + c0), b = ld8(u + pix * pu + ou + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = c0 + e;
+      float dz = g.v[e];
+      if (act == SGB_ACT_RELU) dz = ov.v[e] > 0.f ? dz : 0.f;
+      float mu3 = coef[c], rstd3 = coef[C + c], muu = coef[2 * C + c], rstdz = coef[3 * C + c];
+      float s3 = coef[8 * C + c];  // gamma3 * rstd3
+      float y3h = (a.v[e] - mu3) * rstd3;
+      float zh = (s3 * (a.v[e] - mu3) + b.v[e] - muu) * rstdz;
+      acc[0][e] += dz;
+      acc[1][e] += post ? dz * zh : 0.f;
+      acc[2][e] += dz * y3h;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- BatchNorm forward
+struct BnCoef {
+  float scale, shift;
+};
+
+__global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(SgbBnDesc d, const bf16* __restrict__ x, const double* stats,
+                                                         const float* gamma, const float* beta, float* rmean,
+                                                         float* rvar, const bf16* __restrict__ res, bf16* y,
+                                                         float* save_mean, float* save_rstd) {
+  extern __shared__ float sc[];  // [2][C]
+  const int C = d.C;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    double s1 = 0, s2 = 0;
+    for (int r = 0; r < d.stats_repl; ++r) {
+      s1 += stats[(int64_t)r * 2 * C + c];
+      s2 += stats[(int64_t)r * 2 * C + C + c];
+    }
+    double mean = s1 / (double)d.M;
+    double var = s2 / (double)d.M - mean * mean;
+    if (var < 0) var = 0;
+    float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    sc[c] = g * rstd;
+    sc[C + c] = b - (float)mean * g * rstd;
+    if (blockIdx.x == 0) {
+      save_mean[c] = (float)mean;
+      save_rstd[c] = rstd;
+      if (rmean) {
+        double unb = d.M > 1 ? var * (double)d.M / (double)(d.M - 1) : var;
+        rmean[c] = (1.f - d.momentum) * rmean[c] + d.momentum * (float)mean;
+        rvar[c] = (1.f - d.momentum) * rvar[c] + d.momentum * (float)unb;
+      }
+    }
+  }
+  __syncthreads();
+  const int cvs = C / 8;
+  const int64_t total = d.M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 a = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
+    V8 r;
+    if (res) r = ld8(res + pix * d.r_pitch + d.r_off + cv * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = a.v[e] * sc[cv * 8 + e] + sc[C + cv * 8 + e];
+      if (res) v += r.v[e];
+      a.v[e] = apply_act(v, d.act);
+    }
+    st8(y + pix * d.y_pitch + d.y_off + cv * 8, a);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) bn_act_infer_kernel(SgbBnDesc d, const bf16* __restrict__ x, const float* gamma,
+                                                           const float* beta, const float* rmean, const float* rvar,
+                                                           const bf16* __restrict__ res, bf16* y) {
+  extern __shared__ float sc[];
+  const int C = d.C;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float rstd = rsqrtf(rvar[c] + d.eps);
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    sc[c] = g * rstd;
+    sc[C + c] = b - rmean[c] * g * rstd;
+  }
+  __syncthreads();
+  const int cvs = C / 8;
+  const int64_t total = d.M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 a = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
+    V8 r;
+    if (res) r = ld8(res + pix * d.r_pitch + d.r_off + cv * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = a.v[e] * sc[cv * 8 + e] + sc[C + cv * 8 + e];
+      if (res) v += r.v[e];
+      a.v[e] = apply_act(v, d.act);
+    }
+    st8(y + pix * d.y_pitch + d.y_off + cv * 8, a);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) bn_act_bwd_apply_kernel(SgbBnDesc d, const bf16* __restrict__ dy,
+                                                               const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                               const float* gamma, const float* mean,
+                                                               const float* rstd, const double* sums, bf16* dx,
+                                                               bf16* dres, float* dgamma, float* dbeta) {
+  extern __shared__ float sc[];  // [4][C]: mean, rstd, m0 (mean dz), m1 (mean dz*xhat) ; plus g*rstd
+  const int C = d.C;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float g = gamma ? gamma[c] : 1.f;
+    float m0 = (float)(sums[c] / (double)d.M), m1 = (float)(sums[C + c] / (double)d.M);
+    sc[c] = mean[c];
+    sc[C + c] = rstd[c];
+    sc[2 * C + c] = m0;
+    sc[3 * C + c] = m1;
+    sc[4 * C + c] = g * rstd[c];
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[c] += (float)sums[C + c];
+      if (dbeta) dbeta[c] += (float)sums[c];
+    }
+  }
+  __syncthreads();
+  const int cvs = C / 8;
+  const int64_t total = d.M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 g = ld8(dy + pix * d.y_pitch + d.y_off + cv * 8);
+    V8 xv = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
+    V8 yv = ld8(y + pix * d.y_pitch + d.y_off + cv * 8);
+    V8 o, dr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = cv * 8 + e;
+      float dz = g.v[e];
+      if (d.act == SGB_ACT_RELU) dz = yv.v[e] > 0.f ? dz : 0.f;
+      float xh = (xv.v[e] - sc[c]) * sc[C + c];
+      o.v[e] = sc[4 * C + c] * (dz - sc[2 * C + c] - xh * sc[3 * C + c]);
+      dr.v[e] = dz;
+    }
+    st8(dx + pix * d.x_pitch + d.x_off + cv * 8, o);
+    if (dres) st8(dres + pix * d.r_pitch + d.r_off + cv * 8, dr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- QARepVGG algebra
+__global__ void __launch_bounds__(TPB) qarep_fwd_kernel(SgbQarepDesc d, const bf16* __restrict__ y3,
+                                                        const bf16* __restrict__ u, const double* mom,
+                                                        const float* gamma3, const float* beta3, const float* ab,
+                                                        const float* gamma_p, const float* beta_p, float* rm3,
+                                                        float* rv3, float* rmp, float* rvp, bf16* out, float* coef) {
+  extern __shared__ float sc[];  // [3][C]: a3, au, c0
+  const int C = d.C;
+  const double M = (double)d.M;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    double S3 = mom[c], S33 = mom[C + c], Su = mom[2 * C + c], Suu = mom[3 * C + c], S3u = mom[4 * C + c];
+    double mu3 = S3 / M, var3 = S33 / M - mu3 * mu3;
+    if (var3 < 0) var3 = 0;
+    double muu = Su / M, varu = Suu / M - muu * muu, cov = S3u / M - mu3 * muu;
+    if (varu < 0) varu = 0;
+    double rstd3 = 1.0 / sqrt(var3 + (double)d.eps3);
+    double g3 = gamma3[c], b3 = beta3[c], abc = ab ? ab[c] : 0.0;
+    double s3 = g3 * rstd3;
+    double muz = b3 + muu + abc;
+    double varz = s3 * s3 * var3 + varu + 2.0 * s3 * cov;
+    if (varz < 0) varz = 0;
+    double a3, au, c0, rstdz = 1.0, czy = 0.0;
+    if (d.use_post_bn) {
+      rstdz = 1.0 / sqrt(varz + (double)d.eps_post);
+      double gp = gamma_p[c], bp = beta_p[c];
+      a3 = gp * rstdz * s3;
+      au = gp * rstdz;
+      c0 = gp * rstdz * (-s3 * mu3 - muu) + bp;
+      czy = (s3 * var3 + cov) * rstdz * rstd3;
+    } else {
+      a3 = s3;
+      au = 1.0;
+      c0 = b3 + abc - s3 * mu3;
+    }
+    sc[c] = (float)a3;
+    sc[C + c] = (float)au;
+    sc[2 * C + c] = (float)c0;
+    if (blockIdx.x == 0) {
+      coef[c] = (float)mu3;
+      coef[C + c] = (float)rstd3;
+      coef[2 * C + c] = (float)muu;
+      coef[3 * C + c] = (float)rstdz;
+      coef[4 * C + c] = (float)a3;
+      coef[5 * C + c] = (float)au;
+      coef[6 * C + c] = (float)c0;
+      coef[7 * C + c] = (float)czy;
+      coef[8 * C + c] = (float)s3;
+      double unb = d.M > 1 ? M / (M - 1.0) : 1.0;
+      if (rm3) {
+        rm3[c] = (1.f - d.momentum) * rm3[c] + d.momentum * (float)mu3;
+        rv3[c] = (1.f - d.momentum) * rv3[c] + d.momentum * (float)(var3 * unb);
+      }
+      if (d.use_post_bn && rmp) {
+        rmp[c] = (1.f - d.momentum) * rmp[c] + d.momentum * (float)muz;
+        rvp[c] = (1.f - d.momentum) * rvp[c] + d.momentum * (float)(varz * unb);
+      }
+    }
+  }
+  __syncthreads();
+  const int cvs = C / 8;
+  const int64_t total = d.M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + cv * 8), b = ld8(u + pix * d.pitchu + d.offu + cv * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = cv * 8 + e;
+      a.v[e] = apply_act(sc[c] * a.v[e] + sc[C + c] * b.v[e] + sc[2 * C + c], d.act);
+    }
+    st8(out + pix * d.pitcho + d.offo + cv * 8, a);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) qarep_bwd_apply_kernel(SgbQarepDesc d, const bf16* __restrict__ dout,
+                                                              const bf16* __restrict__ out,
+                                                              const bf16* __restrict__ y3, const bf16* __restrict__ u,
+                                                              const float* coef, const double* sums,
+                                                              const float* gamma3, const float* gamma_p, bf16* dy3,
+                                                              bf16* du, float* dgamma3, float* dbeta3, float* dab,
+                                                              float* dgamma_p, float* dbeta_p) {
+  extern __shared__ float sc[];  // [8][C]: mu3, rstd3, muu, rstdz, s3, g, m0, m1 ; q in [8]
+  const int C = d.C;
+  const double M = (double)d.M;
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float mu3 = coef[c], rstd3 = coef[C + c], muu = coef[2 * C + c], rstdz = coef[3 * C + c], czy = coef[7 * C + c];
+    float s3 = gamma3[c] * rstd3;
+    double T0 = sums[c], T1 = sums[C + c], T2 = sums[2 * C + c];
+    float m0 = (float)(T0 / M), m1 = (float)(T1 / M), m2 = (float)(T2 / M);
+    float g, q;
+    if (d.use_post_bn) {
+      g = gamma_p[c] * rstdz;
+      q = g * (m2 - m1 * czy);
+    } else {
+      g = 1.f;
+      q = m2;
+      m1 = 0.f;
+    }
+    sc[c] = mu3;
+    sc[C + c] = rstd3;
+    sc[2 * C + c] = muu;
+    sc[3 * C + c] = rstdz;
+    sc[4 * C + c] = s3;
+    sc[5 * C + c] = g;
+    sc[6 * C + c] = m0;
+    sc[7 * C + c] = m1;
+    sc[8 * C + c] = q;
+    if (blockIdx.x == 0) {
+      if (d.use_post_bn) {
+        if (dgamma_p) dgamma_p[c] += (float)T1;
+        if (dbeta_p) dbeta_p[c] += (float)T0;
+        if (dgamma3) dgamma3[c] += (float)(M * (double)q);
+        // dbeta3 and d(alpha*b1) are exactly zero: post_bn removes any per-channel constant.
+      } else {
+        if (dgamma3) dgamma3[c] += (float)T2;
+        if (dbeta3) dbeta3[c] += (float)T0;
+        if (dab) dab[c] += (float)T0;
+      }
+    }
+  }
+  __syncthreads();
+  const int cvs = C / 8;
+  const int64_t total = d.M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 g = ld8(dout + pix * d.pitcho + d.offo + cv * 8), ov = ld8(out + pix * d.pitcho + d.offo + cv * 8);
+    V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + cv * 8), b = ld8(u + pix * d.pitchu + d.offu + cv * 8);
+    V8 o3, ou;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int c = cv * 8 + e;
+      float dzp = g.v[e];
+      if (d.act == SGB_ACT_RELU) dzp = ov.v[e] > 0.f ? dzp : 0.f;
+      float mu3 = sc[c], rstd3 = sc[C + c], s3 = sc[4 * C + c];
+      float y3h = (a.v[e] - mu3) * rstd3;
+      float dz;
+      if (d.use_post_bn) {
+        float zh = (s3 * (a.v[e] - mu3) + b.v[e] - sc[2 * C + c]) * sc[3 * C + c];
+        dz = sc[5 * C + c] * (dzp - sc[6 * C + c] - zh * sc[7 * C + c]);
+        o3.v[e] = s3 * (dz - y3h * sc[8 * C + c]);
+      } else {
+        dz = dzp;
+        o3.v[e] = s3 * (dz - sc[6 * C + c] - y3h * sc[8 * C + c]);
+      }
+      ou.v[e] = dz;
+    }
+    st8(dy3 + pix * d.pitch3 + d.off3 + cv * 8, o3);
+    st8(du + pix * d.pitchu + d.offu + cv * 8, ou);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- pooling etc.
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int xp, int xo, int k,
+                                   int stride, int pad, bf16* y, int P, int Q, int yp, int yo, uint8_t* idx) {
+  const int cvs = C / 8;
+  const int64_t total = (int64_t)N * P * Q * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = i % cvs;
+    int64_t t = i / cvs;
+    int q = t % Q; t /= Q;
+    int p = t % P;
+    int n = t / P;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+    for (int r = 0; r < k; ++r) {
+      int h = p * stride - pad + r;
+      if ((unsigned)h >= (unsigned)H) continue;
+      for (int s = 0; s < k; ++s) {
+        int w = q * stride - pad + s;
+        if ((unsigned)w >= (unsigned)W) continue;
+        V8 a = ld8(x + (((int64_t)n * H + h) * W + w) * xp + xo + cv * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (a.v[e] > best[e]) { best[e] = a.v[e]; bi[e] = r * k + s; }
+      }
+    }
+    V8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o.v[e] = best[e];
+    int64_t opix = ((int64_t)n * P + p) * Q + q;
+    st8(y + opix * yp + yo + cv * 8, o);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + opix * C + cv * 8) = pk;
+    }
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, int N, int H, int W, int C, int k, int stride, int pad,
+                                   int P, int Q, int dyp, int dyo, const uint8_t* idx, float* dx) {
+  const int64_t total = (int64_t)N * P * Q * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C;
+    int64_t opix = i / C;
+    int64_t t = opix;
+    int q = t % Q; t /= Q;
+    int p = t % P;
+    int n = t / P;
+    int b = idx[opix * C + c];
+    int r = b / k, s = b - r * k;
+    int h = p * stride - pad + r, w = q * stride - pad + s;
+    float g = __bfloat162float(dy[opix * dyp + dyo + c]);
+    atomicAdd(dx + (((int64_t)n * H + h) * W + w) * C + c, g);
+  }
+}
+
+__global__ void axpby_kernel(const bf16* __restrict__ x1, int p1, int o1, float a, const bf16* __restrict__ x2, int p2,
+                             int o2, float b, bf16* y, int py, int oy, int64_t M, int C) {
+  const int cvs = C / 8;
+  const int64_t total = M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 u = ld8(x1 + pix * p1 + o1 + cv * 8);
+    if (x2) {
+      V8 v = ld8(x2 + pix * p2 + o2 + cv * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u.v[e] = a * u.v[e] + b * v.v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u.v[e] = a * u.v[e];
+    }
+    st8(y + pix * py + oy + cv * 8, u);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+__global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, int N, int HW, int C, bf16* y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int c = i % C, n = i / C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += __bfloat162float(x[((int64_t)n * HW + p) * C + c]);
+  y[i] = __float2bfloat16_rn(s / (float)HW);
+}
+__global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, int N, int HW, int C, bf16* dx) {
+  const int64_t total = (int64_t)N * HW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = i % C;
+    int n = i / ((int64_t)HW * C);
+    dx[i] = __float2bfloat16_rn(__bfloat162float(dy[n * C + c]) / (float)HW);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- optimizers
+__global__ void sgd_kernel(float* p, const float* g, float* mom, int64_t n, float lr, float mu, float wd, float gs,
+                           int nesterov) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gs + wd * p[i];
+    float d = gr;
+    if (mu != 0.f) {
+      float b = mu * mom[i] + gr;
+      mom[i] = b;
+      d = nesterov ? gr + mu * b : b;
+    }
+    p[i] -= lr * d;
+  }
+}
+__global__ void adamw_kernel(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                             float eps, float wd, float bc1, float bc2, float gs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gs;
+    float pi = p[i] * (1.f - lr * wd);
+    float mi = b1 * m[i] + (1.f - b1) * gr;
+    float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] = pi - (lr / bc1) * mi / denom;
+  }
+}
+__global__ void ema_kernel(float* e, const float* p, int64_t n, float d) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    e[i] = e[i] * d + (1.f - d) * p[i];
+}
+
+}  // namespace
+
+// ================================================================================================== C ABI
+extern "C" int sgb_weight_prepare(const float* w, int K, int C, int R, int S, int c_pad, sgb_bf16* krsc,
+                                  sgb_bf16* crsk, const float* scale, int add_identity, void* stream) {
+  SGB_REQUIRE(w && krsc, "null pointer");
+  SGB_REQUIRE(c_pad >= C && c_pad % 8 == 0, "c_pad must be >= C and a multiple of 8");
+  SGB_REQUIRE(!crsk || c_pad == C, "CRSK copy requires unpadded C");
+  int64_t n = (int64_t)K * R * S * c_pad + (crsk ? (int64_t)C * R * S * (((K + 7) / 8) * 8) : 0);
+  weight_prepare_kernel<<<grid_for(n), TPB, 0, (cudaStream_t)stream>>>(w, K, C, R, S, c_pad, (bf16*)krsc, (bf16*)crsk,
+                                                                       scale, add_identity);
+  SGB_LAUNCH_CHECK("weight_prepare_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_wgrad_to_oihw(const float* dw, int K, int C, int R, int S, int c_pad, float* g, int accumulate,
+                                 void* stream) {
+  SGB_REQUIRE(dw && g, "null pointer");
+  wgrad_to_oihw_kernel<<<grid_for((int64_t)K * C * R * S), TPB, 0, (cudaStream_t)stream>>>(dw, K, C, R, S, c_pad, g,
+                                                                                         accumulate);
+  SGB_LAUNCH_CHECK("wgrad_to_oihw_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, sgb_bf16* y, int y_pitch,
+                                         int y_off, void* stream) {
+  SGB_REQUIRE(x && y, "null pointer");
+  SGB_REQUIRE(y_pitch % 8 == 0 && y_off % 8 == 0, "pitch/offset multiples of 8");
+  int cpad = ((C + 7) / 8) * 8;
+  SGB_REQUIRE(y_pitch >= y_off + cpad, "slice exceeds pitch");
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)N * H * W * (cpad / 8)), TPB, 0, (cudaStream_t)stream>>>(
+      x, N, C, H, W, (bf16*)y, y_pitch, y_off, cpad);
+  SGB_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H, int W, int x_pitch, int x_off,
+                                         float* y, void* stream) {
+  SGB_REQUIRE(x && y, "null pointer");
+  nhwc_to_nchw_kernel<<<grid_for((int64_t)N * C * H * W), TPB, 0, (cudaStream_t)stream>>>((const bf16*)x, N, C, H, W,
+                                                                                        x_pitch, x_off, y);
+  SGB_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return SGB_OK;
+}
+
+static int check_bn(const SgbBnDesc* d) {
+  SGB_REQUIRE(d && d->M > 0 && d->C > 0, "bad desc");
+  SGB_REQUIRE(d->C % 8 == 0, "C must be a multiple of 8");
+  SGB_REQUIRE(d->x_pitch % 8 == 0 && d->x_off % 8 == 0 && d->y_pitch % 8 == 0 && d->y_off % 8 == 0,
+              "pitch/offset multiples of 8");
+  SGB_REQUIRE(d->C <= 4096, "C too large for the shared-memory coefficient cache");
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, const sgb_bf16* residual,
+                              sgb_bf16* y, float* save_mean, float* save_rstd, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(x && stats && y && save_mean && save_rstd, "null pointer");
+  SGB_REQUIRE(d->stats_repl >= 1, "stats_repl");
+  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
+  bn_act_fwd_kernel<<<grid, TPB, 2 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+      *d, (const bf16*)x, stats, gamma, beta, running_mean, running_var, (const bf16*)residual, (bf16*)y, save_mean,
+      save_rstd);
+  SGB_LAUNCH_CHECK("bn_act_fwd_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const float* gamma, const float* beta,
+                                const float* running_mean, const float* running_var, const sgb_bf16* residual,
+                                sgb_bf16* y, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(x && y && running_mean && running_var, "null pointer");
+  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
+  bn_act_infer_kernel<<<grid, TPB, 2 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+      *d, (const bf16*)x, gamma, beta, running_mean, running_var, (const bf16*)residual, (bf16*)y);
+  SGB_LAUNCH_CHECK("bn_act_infer_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
+                                     const float* save_mean, const float* save_rstd, double* sums, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(dy && x && y && save_mean && save_rstd && sums, "null pointer");
+  BnBwdRedF f{(const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean, save_rstd,
+              d->x_pitch,      d->x_off,       d->y_pitch,     d->y_off,  d->act};
+  return launch_chan_reduce(f, d->M, d->C, sums, d->C, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
+                                    const float* gamma, const float* save_mean, const float* save_rstd,
+                                    const double* sums, sgb_bf16* dx, sgb_bf16* dresidual, float* dgamma, float* dbeta,
+                                    void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(dy && x && y && save_mean && save_rstd && sums && dx, "null pointer");
+  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
+  bn_act_bwd_apply_kernel<<<grid, TPB, 5 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+      *d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, save_mean, save_rstd, sums, (bf16*)dx,
+      (bf16*)dresidual, dgamma, dbeta);
+  SGB_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_channel_stats(const sgb_bf16* x, int64_t M, int C, int pitch, int off, double* stats,
+                                 void* stream) {
+  SGB_REQUIRE(x && stats && M > 0 && C > 0 && C % 8 == 0 && pitch % 8 == 0 && off % 8 == 0, "bad args");
+  StatsF f{(const bf16*)x, pitch, off};
+  return launch_chan_reduce(f, M, C, stats, C, (cudaStream_t)stream);
+}
+
+static int check_qarep(const SgbQarepDesc* d) {
+  SGB_REQUIRE(d && d->M > 0 && d->C > 0 && d->C % 8 == 0 && d->C <= 2048, "bad desc");
+  SGB_REQUIRE(d->pitch3 % 8 == 0 && d->off3 % 8 == 0 && d->pitchu % 8 == 0 && d->offu % 8 == 0 &&
+                  d->pitcho % 8 == 0 && d->offo % 8 == 0,
+              "pitch/offset multiples of 8");
+  return SGB_OK;
+}
+
+extern "C" int sgb_qarep_moments(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments,
+                                 void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(y3 && u && moments, "null pointer");
+  QarepMomF f{(const bf16*)y3, (const bf16*)u, d->pitch3, d->off3, d->pitchu, d->offu};
+  return launch_chan_reduce(f, d->M, d->C, moments, d->C, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, const double* moments,
+                             const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
+                             const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out,
+                             float* coef, void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(y3 && u && moments && gamma3 && beta3 && out && coef, "null pointer");
+  SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
+  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
+  qarep_fwd_kernel<<<grid, TPB, 3 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+      *d, (const bf16*)y3, (const bf16*)u, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p,
+      (bf16*)out, coef);
+  SGB_LAUNCH_CHECK("qarep_fwd_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,
+                                    const sgb_bf16* y3, const sgb_bf16* u, const float* coef, double* sums,
+                                    void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(dout && out && y3 && u && coef && sums, "null pointer");
+  QarepBwdRedF f{(const bf16*)dout, (const bf16*)out, (const bf16*)y3, (const bf16*)u, coef,      d->C,
+                 d->pitch3,         d->off3,          d->pitchu,       d->offu,        d->pitcho, d->offo,
+                 d->act,            d->use_post_bn};
+  return launch_chan_reduce(f, d->M, d->C, sums, d->C, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,
+                                   const sgb_bf16* y3, const sgb_bf16* u, const float* coef, const double* sums,
+                                   const float* gamma3, const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du,
+                                   float* dgamma3, float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p,
+                                   void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(dout && out && y3 && u && coef && sums && gamma3 && dy3 && du, "null pointer");
+  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
+  qarep_bwd_apply_kernel<<<grid, TPB, 9 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+      *d, (const bf16*)dout, (const bf16*)out, (const bf16*)y3, (const bf16*)u, coef, sums, gamma3, gamma_p,
+      (bf16*)dy3, (bf16*)du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p);
+  SGB_LAUNCH_CHECK("qarep_bwd_apply_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, int x_pitch, int x_off, int k,
+                               int stride, int pad, sgb_bf16* y, int P, int Q, int y_pitch, int y_off, uint8_t* idx,
+                               void* stream) {
+  SGB_REQUIRE(x && y && C % 8 == 0 && x_pitch % 8 == 0 && x_off % 8 == 0 && y_pitch % 8 == 0 && y_off % 8 == 0,
+              "bad args");
+  SGB_REQUIRE(k * k <= 255, "kernel too large for uint8 arg-max");
+  SGB_REQUIRE(P == (H + 2 * pad - k) / stride + 1 && Q == (W + 2 * pad - k) / stride + 1, "P/Q inconsistent");
+  maxpool_fwd_kernel<<<grid_for((int64_t)N * P * Q * (C / 8)), TPB, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, N, H, W, C, x_pitch, x_off, k, stride, pad, (bf16*)y, P, Q, y_pitch, y_off, idx);
+  SGB_LAUNCH_CHECK("maxpool_fwd_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_maxpool_bwd(const sgb_bf16* dy, int N, int H, int W, int C, int k, int stride, int pad, int P,
+                               int Q, int dy_pitch, int dy_off, const uint8_t* idx, float* dx_f32, void* stream) {
+  SGB_REQUIRE(dy && idx && dx_f32, "null pointer");
+  maxpool_bwd_kernel<<<grid_for((int64_t)N * P * Q * C), TPB, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, N, H, W, C, k, stride, pad, P, Q, dy_pitch, dy_off, idx, dx_f32);
+  SGB_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_bf16* x2, int p2, int o2, float b,
+                         sgb_bf16* y, int py, int oy, int64_t M, int C, void* stream) {
+  SGB_REQUIRE(x1 && y && C % 8 == 0 && p1 % 8 == 0 && o1 % 8 == 0 && py % 8 == 0 && oy % 8 == 0, "bad args");
+  SGB_REQUIRE(!x2 || (p2 % 8 == 0 && o2 % 8 == 0), "bad args (x2)");
+  axpby_kernel<<<grid_for(M * (C / 8), TPB * 4), TPB, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x1, p1, o1, a, (const bf16*)x2, p2, o2, b, (bf16*)y, py, oy, M, C);
+  SGB_LAUNCH_CHECK("axpby_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_f32_to_bf16(const float* x, sgb_bf16* y, int64_t n, void* stream) {
+  SGB_REQUIRE(x && y, "null pointer");
+  f32_to_bf16_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n);
+  SGB_LAUNCH_CHECK("f32_to_bf16_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_avgpool_fwd(const sgb_bf16* x, int N, int HW, int C, sgb_bf16* y, void* stream) {
+  SGB_REQUIRE(x && y, "null pointer");
+  avgpool_fwd_kernel<<<ceil_div((int64_t)N * C, TPB), TPB, 0, (cudaStream_t)stream>>>((const bf16*)x, N, HW, C,
+                                                                                      (bf16*)y);
+  SGB_LAUNCH_CHECK("avgpool_fwd_kernel");
+  return SGB_OK;
+}
+extern "C" int sgb_avgpool_bwd(const sgb_bf16* dy, int N, int HW, int C, sgb_bf16* dx, void* stream) {
+  SGB_REQUIRE(dy && dx, "null pointer");
+  avgpool_bwd_kernel<<<grid_for((int64_t)N * HW * C), TPB, 0, (cudaStream_t)stream>>>((const bf16*)dy, N, HW, C,
+                                                                                     (bf16*)dx);
+  SGB_LAUNCH_CHECK("avgpool_bwd_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float wd,
+                            float grad_scale, int nesterov, void* stream) {
+  SGB_REQUIRE(p && g && (momentum == 0.f || mom), "null pointer");
+  sgd_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, wd, grad_scale,
+                                                                     nesterov);
+  SGB_LAUNCH_CHECK("sgd_kernel");
+  return SGB_OK;
+}
+extern "C" int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                              float eps, float wd, float bias1, float bias2, float grad_scale, void* stream) {
+  SGB_REQUIRE(p && g && m && v, "null pointer");
+  adamw_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bias1,
+                                                                       bias2, grad_scale);
+  SGB_LAUNCH_CHECK("adamw_kernel");
+  return SGB_OK;
+}
+extern "C" int sgb_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream) {
+  SGB_REQUIRE(ema && p, "null pointer");
+  ema_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(ema, p, n, decay);
+  SGB_LAUNCH_CHECK("ema_kernel");
+  return SGB_OK;
+}
