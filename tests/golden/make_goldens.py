@@ -1,0 +1,305 @@
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference (/root/reference) on CPU
+in fp32 through oracle/ref_shim.py.  Run once in the build container:
+
+    python tests/golden/make_goldens.py
+
+The reference tree does not exist on the GPU box, so the outputs (small .pt files) are committed.
+"""
+import copy
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+TINY_YOLO_NAS = {
+    "in_channels": 3,
+    "backbone": {
+        "NStageBackbone": {
+            "stem": {"YoloNASStem": {"out_channels": 16}},
+            "stages": [
+                {"YoloNASStage": {"out_channels": 32, "num_blocks": 1, "activation_type": "relu", "hidden_channels": 16, "concat_intermediates": False}},
+                {"YoloNASStage": {"out_channels": 48, "num_blocks": 2, "activation_type": "relu", "hidden_channels": 24, "concat_intermediates": False}},
+                {"YoloNASStage": {"out_channels": 64, "num_blocks": 1, "activation_type": "relu", "hidden_channels": 32, "concat_intermediates": True}},
+                {"YoloNASStage": {"out_channels": 96, "num_blocks": 1, "activation_type": "relu", "hidden_channels": 48, "concat_intermediates": False}},
+            ],
+            "context_module": {"SPP": {"output_channels": 96, "activation_type": "relu", "k": [5, 9, 13]}},
+            "out_layers": ["stage1", "stage2", "stage3", "context_module"],
+        }
+    },
+    "neck": {
+        "YoloNASPANNeckWithC2": {
+            "neck1": {"YoloNASUpStage": {"out_channels": 48, "num_blocks": 1, "hidden_channels": 24, "width_mult": 1, "depth_mult": 1, "activation_type": "relu", "reduce_channels": True}},
+            "neck2": {"YoloNASUpStage": {"out_channels": 32, "num_blocks": 1, "hidden_channels": 16, "width_mult": 1, "depth_mult": 1, "activation_type": "relu", "reduce_channels": True}},
+            "neck3": {"YoloNASDownStage": {"out_channels": 48, "num_blocks": 1, "hidden_channels": 24, "activation_type": "relu", "width_mult": 1, "depth_mult": 1}},
+            "neck4": {"YoloNASDownStage": {"out_channels": 64, "num_blocks": 1, "hidden_channels": 32, "activation_type": "relu", "width_mult": 1, "depth_mult": 1}},
+        }
+    },
+    "heads": {
+        "NDFLHeads": {
+            "num_classes": 4,
+            "reg_max": 16,
+            "heads_list": [
+                {"YoloNASDFLHead": {"inter_channels": 32, "width_mult": 0.5, "first_conv_group_size": 0, "stride": 8}},
+                {"YoloNASDFLHead": {"inter_channels": 48, "width_mult": 0.5, "first_conv_group_size": 0, "stride": 16}},
+                {"YoloNASDFLHead": {"inter_channels": 64, "width_mult": 0.5, "first_conv_group_size": 0, "stride": 32}},
+            ],
+        }
+    },
+    "bn_eps": 1e-3,
+    "bn_momentum": 0.03,
+    "inplace_act": True,
+}
+
+
+def randomize_bn(module, gen):
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.weight.shape, generator=gen) + 0.5
+            m.bias.data = torch.randn(m.bias.shape, generator=gen) * 0.1
+            m.running_mean.data = torch.randn(m.running_mean.shape, generator=gen) * 0.1
+            m.running_var.data = torch.rand(m.running_var.shape, generator=gen) + 0.5
+
+
+def sd_clone(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def golden_qarepvgg():
+    from super_gradients.modules import QARepVGGBlock
+
+    out = {}
+    for name, cin, cout, stride, res in [("s1_res", 16, 16, 1, True), ("s2", 8, 24, 2, False)]:
+        gen = torch.Generator().manual_seed(1)
+        torch.manual_seed(0)
+        blk = QARepVGGBlock(cin, cout, stride=stride, use_residual_connection=res)
+        randomize_bn(blk, gen)
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eps, m.momentum = 1e-3, 0.03
+        sd0 = sd_clone(blk)
+        x = torch.randn(2, cin, 12, 12, generator=gen, requires_grad=True)
+        blk.train()
+        y = blk(x)
+        gy = torch.randn(y.shape, generator=gen)
+        y.backward(gy)
+        grads = {k: p.grad.clone() for k, p in blk.named_parameters() if p.grad is not None}
+        sd1 = sd_clone(blk)  # running stats after one training forward
+        blk.eval()
+        with torch.no_grad():
+            y_eval = blk(x)
+            fused = copy.deepcopy(blk)
+            fused.partial_fusion()
+            y_partial = fused(x)
+            fused.full_fusion()
+            y_full = fused(x)
+        out[name] = dict(cin=cin, cout=cout, stride=stride, residual=res, sd0=sd0, sd1=sd1, x=x.detach(), y=y.detach(), gy=gy, gx=x.grad.clone(), grads=grads, y_eval=y_eval, y_partial=y_partial, y_full=y_full)
+    torch.save(out, os.path.join(HERE, "qarepvgg.pt"))
+
+
+def golden_conv_blocks():
+    from super_gradients.modules import Conv, ConvBNReLU
+    from super_gradients.training.models.classification_models.resnet import BasicResNetBlock, Bottleneck
+    from super_gradients.training.models.detection_models.csp_darknet53 import SPP
+
+    out = {}
+    gen = torch.Generator().manual_seed(2)
+    torch.manual_seed(0)
+    for name, mod, cin, hw in [
+        ("conv3x3_s2", Conv(16, 24, 3, 2, torch.nn.ReLU), 16, 12),
+        ("conv1x1", Conv(16, 8, 1, 1, torch.nn.ReLU), 16, 12),
+        ("convbnrelu", ConvBNReLU(8, 16, kernel_size=3, stride=1, padding=1, bias=False), 8, 12),
+        ("bottleneck_s2", Bottleneck(16, 8, stride=2, expansion=4), 16, 12),
+        ("bottleneck_id", Bottleneck(32, 8, stride=1, expansion=4), 32, 12),
+        ("basic_s2", BasicResNetBlock(16, 24, stride=2), 16, 12),
+        ("spp", SPP(16, 16, (5, 9, 13), torch.nn.ReLU), 16, 12),
+    ]:
+        randomize_bn(mod, gen)
+        sd0 = sd_clone(mod)
+        x = torch.randn(2, cin, hw, hw, generator=gen, requires_grad=True)
+        mod.train()
+        y = mod(x)
+        gy = torch.randn(y.shape, generator=gen)
+        y.backward(gy)
+        grads = {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+        sd1 = sd_clone(mod)
+        mod.eval()
+        with torch.no_grad():
+            y_eval = mod(x)
+        out[name] = dict(sd0=sd0, sd1=sd1, x=x.detach(), y=y.detach(), gy=gy, gx=x.grad.clone(), grads=grads, y_eval=y_eval)
+    torch.save(out, os.path.join(HERE, "conv_blocks.pt"))
+
+
+def golden_loss():
+    from super_gradients.training.losses.functional import bbox_ciou_loss
+    from super_gradients.training.losses.ppyolo_loss import GIoULoss, PPYoloELoss, TaskAlignedAssigner
+    from super_gradients.training.models.detection_models.pp_yolo_e.pp_yolo_head import generate_anchors_for_grid_cell
+
+    gen = torch.Generator().manual_seed(3)
+    B, C, reg_max = 3, 4, 16
+    feats = [torch.zeros(B, 1, 8, 8), torch.zeros(B, 1, 4, 4), torch.zeros(B, 1, 2, 2)]
+    anchors, anchor_points, nums, stride_tensor = generate_anchors_for_grid_cell(feats, (8, 16, 32), 5.0, 0.5)
+    L = sum(nums)
+    out = {}
+    for case, n_per_img in [("regular", [3, 2, 4]), ("ragged_with_empty", [5, 0, 1]), ("no_targets", [0, 0, 0])]:
+        cls_logits = (torch.randn(B, L, C, generator=gen) * 2.0).requires_grad_(True)
+        reg_distri = (torch.randn(B, L, 4 * (reg_max + 1), generator=gen) * 1.5).requires_grad_(True)
+        rows = []
+        for b, n in enumerate(n_per_img):
+            for _ in range(n):
+                cx, cy = (torch.rand(2, generator=gen) * 40 + 12).tolist()
+                w, h = (torch.rand(2, generator=gen) * 30 + 8).tolist()
+                rows.append([b, int(torch.randint(0, C, (1,), generator=gen)), cx, cy, w, h])
+        targets = torch.tensor(rows, dtype=torch.float32).reshape(-1, 6)
+        crit = PPYoloELoss(num_classes=C, use_static_assigner=False)
+        raw = (cls_logits, reg_distri, anchors, anchor_points, nums, stride_tensor)
+        loss, items = crit(raw, targets)
+        loss.backward()
+        # assignment of the same inputs (for the assigner kernel)
+        with torch.no_grad():
+            t = crit._get_targets_for_batched_assigner(targets, batch_size=B)
+            pts_s = anchor_points / stride_tensor
+            pred_bboxes, _, _ = crit._bbox_decode(pts_s, reg_distri)
+            al, ab, asc = TaskAlignedAssigner(topk=13, alpha=1.0, beta=6.0)(
+                pred_scores=cls_logits.sigmoid(), pred_bboxes=pred_bboxes * stride_tensor, anchor_points=anchor_points, num_anchors_list=nums,
+                gt_labels=t["gt_class"], gt_bboxes=t["gt_bbox"], pad_gt_mask=t["pad_gt_mask"], bg_index=C,
+            )  # fmt: skip
+        out[case] = dict(
+            cls_logits=cls_logits.detach(), reg_distri=reg_distri.detach(), targets=targets, loss=loss.detach(), items=items.detach(),
+            g_cls=cls_logits.grad.clone(), g_reg=reg_distri.grad.clone(), assigned_labels=al, assigned_bboxes=ab, assigned_scores=asc,
+            gt_class=t["gt_class"], gt_bbox=t["gt_bbox"], pad_gt_mask=t["pad_gt_mask"].float(),
+        )  # fmt: skip
+    out["anchors"], out["anchor_points"], out["nums"], out["stride_tensor"] = anchors, anchor_points, nums, stride_tensor
+    # box losses on random boxes
+    p = torch.rand(64, 4, generator=gen) * 10
+    p[:, 2:] += p[:, :2] + 0.5
+    g = torch.rand(64, 4, generator=gen) * 10
+    g[:, 2:] += g[:, :2] + 0.5
+    p.requires_grad_(True)
+    gl = GIoULoss()(p, g)
+    gl.sum().backward()
+    g_giou = p.grad.clone()
+    p.grad = None
+    cl = bbox_ciou_loss(p, g, eps=1e-10)
+    cl.sum().backward()
+    out["boxes"] = dict(p=p.detach(), g=g, giou=gl.detach(), ciou=cl.detach(), g_giou=g_giou, g_ciou=p.grad.clone())
+    torch.save(out, os.path.join(HERE, "loss.pt"))
+
+
+def golden_nms():
+    from super_gradients.training.models.detection_models.pp_yolo_e import PPYoloEPostPredictionCallback
+
+    gen = torch.Generator().manual_seed(4)
+    out = {}
+    for case, (B, L, C, thr, topk, maxp, multi, agn) in {
+        "multi_small": (2, 300, 4, 0.6, 1000, 300, True, False),
+        "multi_topk": (2, 600, 6, 0.3, 200, 50, True, False),
+        "multi_vanilla": (1, 2500, 3, 0.5, 1024, 300, True, False),
+        "single_label": (2, 500, 5, 0.7, 100, 300, False, False),
+        "class_agnostic": (2, 400, 4, 0.7, 1000, 300, True, True),
+        "nothing_passes": (2, 100, 3, 2.0, 1000, 300, True, False),
+    }.items():
+        xy = torch.rand(B, L, 2, generator=gen) * 200
+        wh = torch.rand(B, L, 2, generator=gen) * 60 + 4
+        boxes = torch.cat([xy, xy + wh], -1)
+        scores = torch.rand(B, L, C, generator=gen)
+        cb = PPYoloEPostPredictionCallback(score_threshold=thr, nms_threshold=0.65, nms_top_k=topk, max_predictions=maxp, multi_label_per_box=multi, class_agnostic_nms=agn)
+        res = cb(((boxes, scores), None))
+        out[case] = dict(boxes=boxes, scores=scores, params=dict(score_threshold=thr, nms_threshold=0.65, nms_top_k=topk, max_predictions=maxp, multi_label_per_box=multi, class_agnostic_nms=agn), result=[r.clone() for r in res])
+    torch.save(out, os.path.join(HERE, "nms.pt"))
+
+
+def golden_tiny_yolo_nas():
+    from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
+    from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNAS
+    from super_gradients.training.utils import HpmStruct
+
+    gen = torch.Generator().manual_seed(5)
+    torch.manual_seed(0)
+    ap = copy.deepcopy(TINY_YOLO_NAS)
+    m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    randomize_bn(m, gen)
+    sd0 = sd_clone(m)
+    x = torch.randn(2, 3, 64, 64, generator=gen)
+    targets = torch.tensor([[0, 1, 30.0, 28.0, 24.0, 20.0], [0, 3, 40.0, 44.0, 18.0, 30.0], [1, 0, 20.0, 36.0, 30.0, 22.0]])
+    m.train()
+    outs = m(x)
+    crit = PPYoloELoss(num_classes=4, use_static_assigner=False)
+    loss, items = crit(outs, targets)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    sd1 = sd_clone(m)
+    m.eval()
+    with torch.no_grad():
+        (eb, es), raw = m(x)
+    live = {k: v for k, v in sd0.items() if "rbr_reparam" not in k}  # dead placeholders are not needed to reproduce
+    running = {k: v for k, v in sd1.items() if "running_" in k}
+    gsum = {k: (float(g.double().sum()), float(g.double().norm())) for k, g in grads.items()}
+    keep = [k for k in grads if k.startswith("backbone.stem") or k.startswith("backbone.stage1.downsample") or k.startswith("heads.head1") or k.startswith("neck.neck2.upsample")]
+    torch.save(
+        dict(arch=TINY_YOLO_NAS, sd0=live, running1=running, x=x, targets=targets, train_pred_bboxes=outs[0][0].detach(), train_pred_scores=outs[0][1].detach(),
+             train_cls_logits=outs[1][0].detach(), train_reg_distri=outs[1][1].detach(), loss=loss.detach(), items=items.detach(),
+             grads={k: grads[k] for k in keep}, grad_sums=gsum, eval_pred_bboxes=eb, eval_pred_scores=es,
+             param_names=[k for k, _ in m.named_parameters()], state_keys=list(m.state_dict().keys())),
+        os.path.join(HERE, "tiny_yolo_nas.pt"),
+    )  # fmt: skip
+
+
+def golden_state_keys():
+    """state_dict keys + shapes of the full-size models (for checkpoint compatibility tests)."""
+    from super_gradients.training import models
+
+    out = {}
+    for name, nc in [("yolo_nas_s", 80), ("yolo_nas_m", 80), ("yolo_nas_l", 80), ("resnet18_cifar", 10), ("resnet18", 1000), ("resnet50", 1000)]:
+        torch.manual_seed(0)
+        m = models.get(name, num_classes=nc)
+        out[name] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        out[name + "/param_names"] = [k for k, _ in m.named_parameters()]
+        if name == "resnet18_cifar":
+            # seeded-init fingerprint: used to check that our constructor consumes the RNG identically
+            out[name + "/init_sums"] = {k: float(v.double().sum()) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+    torch.save(out, os.path.join(HERE, "state_keys.pt"))
+
+
+def golden_resnet_cifar_train():
+    """config 1: resnet18_cifar, synthetic CIFAR-shape data, bs 64, SGD lr 0.1 m 0.9 wd 1e-4, CE -- the reference's own
+    optimizer / loss classes driven step by step (per-step losses are the fixture)."""
+    from super_gradients.training import models
+    from super_gradients.training.losses.label_smoothing_cross_entropy_loss import CrossEntropyLoss
+
+    torch.manual_seed(0)
+    m = models.get("resnet18_cifar", num_classes=10)
+    g = torch.Generator().manual_seed(6)
+    X = torch.randn(256, 3, 32, 32, generator=g)
+    Y = torch.randint(0, 10, (256,), generator=g)
+    crit = CrossEntropyLoss()
+    decay, no_decay = [], []
+    for n, p in m.named_parameters():
+        (no_decay if (n.endswith(".bias") or "bn" in n or "shortcut.1" in n) else decay).append(p)
+    opt = torch.optim.SGD([{"params": decay, "weight_decay": 1e-4}, {"params": no_decay, "weight_decay": 0.0}], lr=0.1, momentum=0.9)
+    losses = []
+    m.train()
+    for step in range(4):
+        xb, yb = X[step * 64 : (step + 1) * 64], Y[step * 64 : (step + 1) * 64]
+        out = m(xb)
+        loss = crit(out, yb)
+        loss = loss[0] if isinstance(loss, tuple) else loss
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    torch.save(dict(losses=losses, X=X.half(), Y=Y), os.path.join(HERE, "resnet18_cifar_train.pt"))
+
+
+if __name__ == "__main__":
+    ref_shim.install()
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "tiny_yolo_nas", "state_keys", "resnet_cifar_train"]
+    for w in which:
+        print("generating", w, flush=True)
+        globals()["golden_" + w]()
+    print("done")
