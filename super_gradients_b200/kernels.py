@@ -1,0 +1,432 @@
+"""Thin torch-tensor front end of the C ABI (lib.py).  Every function here launches CUDA kernels from libsgb200.so on
+the current torch stream; torch is used only for device memory and streams.  No function has a non-CUDA fallback.
+
+Activation tensors are NCHW-shaped torch tensors in channels_last memory format (physically NHWC bf16).  A channel
+slice ``buf[:, a:b]`` of such a tensor is a valid operand: its channel pitch is ``buf.shape[1]``.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import ACT_NONE, ACT_RELU, ACT_SILU  # noqa: F401
+
+STATS_REPL = 8  # replicas of the per-channel sum buffers (spreads fp64 atomics)
+
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU}
+
+
+def act_code(act) -> int:
+    if isinstance(act, int):
+        return act
+    return _ACT[act]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda(t: torch.Tensor, name="tensor"):
+    if not t.is_cuda:
+        raise L.SgbError(f"{name} must live on a CUDA device: super_gradients_b200 has no CPU execution path")
+
+
+def nhwc_pitch(t: torch.Tensor) -> int:
+    """Channel pitch (elements) of an NHWC operand; raises if `t` is not laid out as (a channel slice of) NHWC."""
+    if t.dim() != 4:
+        raise L.SgbError(f"expected a 4-d activation tensor, got shape {tuple(t.shape)}")
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    if c > 1 and sc != 1:
+        raise L.SgbError(f"tensor with shape {tuple(t.shape)} strides {t.stride()} is not NHWC (channel stride != 1)")
+    if w > 1:
+        pitch = sw
+    elif h > 1:
+        pitch = sh
+    elif n > 1:
+        pitch = sn
+    else:
+        return ((c + 7) // 8) * 8  # a single pixel: any pitch describes it
+    ok = pitch >= c and (w == 1 or sw == pitch) and (h == 1 or sh == w * pitch) and (n == 1 or sn == h * w * pitch)
+    if not ok:
+        raise L.SgbError(f"tensor with shape {tuple(t.shape)} strides {t.stride()} is not NHWC")
+    return pitch
+
+
+def as_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Returns `t` itself if it is a valid NHWC bf16 operand, else a channels_last bf16 copy."""
+    require_cuda(t)
+    if t.dtype == torch.bfloat16:
+        try:
+            p = nhwc_pitch(t)
+            if p % 8 == 0 and t.data_ptr() % 16 == 0:
+                return t
+        except L.SgbError:
+            pass
+    return t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def empty_nhwc(n, c, h, w, device, c_alloc=None) -> torch.Tensor:
+    """bf16 NHWC tensor with logical channels c; storage pitch is c rounded up to 8 (padding channels are zero)."""
+    ca = c_alloc or ((c + 7) // 8) * 8
+    if ca == c:
+        return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=torch.channels_last)
+    buf = torch.zeros((n, ca, h, w), dtype=torch.bfloat16, device=device).contiguous(memory_format=torch.channels_last)
+    return buf[:, :c]
+
+
+def conv_desc(x: torch.Tensor, K: int, R: int, S: int, stride: int, pad: int, y: Optional[torch.Tensor] = None, P=None, Q=None) -> L.ConvDesc:
+    n, c, h, w = x.shape
+    P = (h + 2 * pad - R) // stride + 1 if P is None else P
+    Q = (w + 2 * pad - S) // stride + 1 if Q is None else Q
+    d = L.ConvDesc()
+    d.N, d.H, d.W, d.C = n, h, w, c
+    d.K, d.R, d.S, d.P, d.Q = K, R, S, P, Q
+    d.stride, d.pad = stride, pad
+    d.x_pitch, d.x_off = nhwc_pitch(x), 0
+    d.y_pitch, d.y_off = (nhwc_pitch(y), 0) if y is not None else (((K + 7) // 8) * 8, 0)
+    d.up2 = 0
+    return d
+
+
+def new_stats(C: int, device, nacc=2) -> torch.Tensor:
+    return torch.zeros((STATS_REPL, nacc, C), dtype=torch.float64, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ conv family
+def conv_fprop(x, w_krsc, K, R, S, stride, pad, *, scale=None, shift=None, residual=None, stats=None, act=ACT_NONE, out=None, out_f32=False):
+    """y = act(conv(x, w) * scale + shift + residual); optionally accumulates per-channel sum / sum-of-squares."""
+    require_cuda(x, "x")
+    n, c, h, w = x.shape
+    P = (h + 2 * pad - R) // stride + 1
+    Q = (w + 2 * pad - S) // stride + 1
+    if out is None:
+        if out_f32:
+            out = torch.empty((n, K, P, Q), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        else:
+            out = empty_nhwc(n, K, P, Q, x.device)
+    d = conv_desc(x, K, R, S, stride, pad, out, P, Q)
+    ep = L.Epilogue()
+    ep.scale = scale.data_ptr() if scale is not None else None
+    ep.shift = shift.data_ptr() if shift is not None else None
+    ep.residual = residual.data_ptr() if residual is not None else None
+    ep.stats = stats.data_ptr() if stats is not None else None
+    ep.stats_repl = stats.shape[0] if stats is not None else 1
+    ep.act = act_code(act)
+    ep.out_f32 = 1 if out_f32 else 0
+    if residual is not None and nhwc_pitch(residual) != d.y_pitch:
+        raise L.SgbError("residual must share the output's channel pitch")
+    L.call("sgb_conv_fprop", ctypes.byref(d), _ptr(x), _ptr(w_krsc), _ptr(out), ctypes.byref(ep), _stream())
+    return out
+
+
+def conv_dgrad(dy, w_crsk, x_shape, R, S, stride, pad, out=None, accumulate=False):
+    n, c, h, w = x_shape
+    K = dy.shape[1]
+    if out is None:
+        out = empty_nhwc(n, c, h, w, dy.device)
+    d = L.ConvDesc()
+    d.N, d.H, d.W, d.C = n, h, w, c
+    d.K, d.R, d.S, d.P, d.Q = K, R, S, dy.shape[2], dy.shape[3]
+    d.stride, d.pad = stride, pad
+    d.x_pitch, d.x_off = nhwc_pitch(out), 0
+    d.y_pitch, d.y_off = nhwc_pitch(dy), 0
+    L.call("sgb_conv_dgrad", ctypes.byref(d), _ptr(dy), _ptr(w_crsk), _ptr(out), 1 if accumulate else 0, _stream())
+    return out
+
+
+def conv_wgrad(x, dy, R, S, stride, pad, dw_krsc=None):
+    """Returns fp32 [K, R, S, C] (C = x.shape[1], i.e. including any channel padding of x)."""
+    n, c, h, w = x.shape
+    K = dy.shape[1]
+    if dw_krsc is None:
+        dw_krsc = torch.zeros((K, R, S, c), dtype=torch.float32, device=x.device)
+    d = conv_desc(x, K, R, S, stride, pad, dy, dy.shape[2], dy.shape[3])
+    L.call("sgb_conv_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw_krsc), _stream())
+    return dw_krsc
+
+
+def weight_prepare(w_oihw: torch.Tensor, c_pad=None, want_crsk=True, scale=None, add_identity=False):
+    """fp32 OIHW -> (bf16 KRSC [K,R,S,c_pad], bf16 CRSK [C,R,S,Kp] or None)."""
+    require_cuda(w_oihw, "weight")
+    K, C, R, S = w_oihw.shape
+    c_pad = c_pad or ((C + 7) // 8) * 8
+    w = w_oihw.detach().contiguous().float()
+    krsc = torch.empty((K, R, S, c_pad), dtype=torch.bfloat16, device=w.device)
+    crsk = None
+    if want_crsk and c_pad == C:
+        crsk = torch.empty((C, R, S, ((K + 7) // 8) * 8), dtype=torch.bfloat16, device=w.device)
+    L.call("sgb_weight_prepare", _ptr(w), K, C, R, S, c_pad, _ptr(krsc), _ptr(crsk), _ptr(scale), 1 if add_identity else 0, _stream())
+    return krsc, crsk
+
+
+def wgrad_to_oihw(dw_krsc: torch.Tensor, C: int) -> torch.Tensor:
+    K, R, S, cp = dw_krsc.shape
+    g = torch.empty((K, C, R, S), dtype=torch.float32, device=dw_krsc.device)
+    L.call("sgb_wgrad_to_oihw", _ptr(dw_krsc), K, C, R, S, cp, _ptr(g), 0, _stream())
+    return g
+
+
+def convt2x2_fprop(x_small, w_up, bias, C_up):
+    """ConvTranspose2d(k=2, s=2): x_small [N,K,P,Q] -> [N,C_up,2P,2Q]; w_up bf16 [(dh,dw,c_up)][K]."""
+    n, K, P, Q = x_small.shape
+    out = empty_nhwc(n, C_up, 2 * P, 2 * Q, x_small.device)
+    d = L.ConvDesc()
+    d.N, d.H, d.W, d.C = n, 2 * P, 2 * Q, C_up
+    d.K, d.R, d.S, d.P, d.Q = K, 2, 2, P, Q
+    d.stride, d.pad = 2, 0
+    d.x_pitch, d.x_off = nhwc_pitch(out), 0
+    d.y_pitch, d.y_off = nhwc_pitch(x_small), 0
+    L.call("sgb_convt2x2_fprop", ctypes.byref(d), _ptr(x_small), _ptr(w_up), _ptr(bias), _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, "x")
+    n, c, h, w = x.shape
+    x = x.contiguous().float()
+    out = torch.empty((n, ((c + 7) // 8) * 8, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    L.call("sgb_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, _ptr(out), out.shape[1], 0, _stream())
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.call("sgb_nhwc_bf16_to_nchw_f32", _ptr(x), n, c, h, w, nhwc_pitch(x), 0, _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL) -> L.BnDesc:
+    n, c, h, w = x.shape
+    d = L.BnDesc()
+    d.M, d.C = n * h * w, c
+    d.x_pitch, d.x_off = nhwc_pitch(x), 0
+    d.y_pitch, d.y_off = nhwc_pitch(y), 0
+    d.r_pitch, d.r_off = (nhwc_pitch(residual), 0) if residual is not None else (0, 0)
+    d.eps, d.momentum = eps, momentum
+    d.act = act_code(act)
+    d.stats_repl = stats_repl
+    return d
+
+
+def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None):
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, c, h, w, x.device)
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    d = bn_desc(x, y, eps, momentum, act, residual, stats.shape[0])
+    L.call("sgb_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _ptr(mean), _ptr(rstd), _stream())
+    return y, mean, rstd
+
+
+def bn_act_infer(x, gamma, beta, running_mean, running_var, eps, act, residual=None):
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, c, h, w, x.device)
+    d = bn_desc(x, y, eps, 0.0, act, residual, 1)
+    L.call("sgb_bn_act_infer", ctypes.byref(d), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _stream())
+    return y
+
+
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False):
+    """Returns (dx, dresidual or None, dgamma, dbeta)."""
+    n, c, h, w = x.shape
+    dy = as_nhwc(dy)
+    d = bn_desc(x, y, eps, 0.0, act, None, 1)
+    if nhwc_pitch(dy) != d.y_pitch:
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if nhwc_pitch(dy) != d.y_pitch:
+            raise L.SgbError("dy pitch mismatch")
+    sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
+    L.call("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
+    dx = torch.empty_like(x, memory_format=torch.channels_last) if nhwc_pitch(x) == c else torch.zeros_like(x)
+    d.x_pitch = nhwc_pitch(dx)
+    # x and dx must share a pitch for the kernel: re-describe x if it is a slice
+    if nhwc_pitch(x) != d.x_pitch:
+        x = x.contiguous(memory_format=torch.channels_last)
+    dres = None
+    if want_residual_grad:
+        dres = empty_nhwc(n, c, h, w, x.device)
+        d.r_pitch = nhwc_pitch(dres)
+    dgamma = torch.zeros(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(c, dtype=torch.float32, device=x.device)
+    L.call("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
+    return dx, dres, dgamma, dbeta
+
+
+def channel_stats(x) -> torch.Tensor:
+    n, c, h, w = x.shape
+    st = torch.zeros((1, 2, c), dtype=torch.float64, device=x.device)
+    L.call("sgb_channel_stats", _ptr(x), n * h * w, c, nhwc_pitch(x), 0, _ptr(st), _stream())
+    return st
+
+
+# ------------------------------------------------------------------------------------------------ QARepVGG algebra
+def qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn) -> L.QarepDesc:
+    n, c, h, w = y3.shape
+    d = L.QarepDesc()
+    d.M, d.C = n * h * w, c
+    d.pitch3, d.off3 = nhwc_pitch(y3), 0
+    d.pitchu, d.offu = nhwc_pitch(u), 0
+    d.pitcho, d.offo = nhwc_pitch(out), 0
+    d.eps3, d.eps_post, d.momentum = eps3, eps_post, momentum
+    d.act = act_code(act)
+    d.use_post_bn = 1 if use_post_bn else 0
+    return d
+
+
+def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp, eps3, eps_post, momentum, act, use_post_bn=True):
+    n, c, h, w = y3.shape
+    out = empty_nhwc(n, c, h, w, y3.device)
+    d = qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn)
+    mom = torch.zeros((5, c), dtype=torch.float64, device=y3.device)
+    L.call("sgb_qarep_moments", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _stream())
+    coef = torch.empty((9, c), dtype=torch.float32, device=y3.device)
+    L.call("sgb_qarep_fwd", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _ptr(gamma3), _ptr(beta3), _ptr(bias1a), _ptr(gamma_p), _ptr(beta_p), _ptr(rm3), _ptr(rv3), _ptr(rmp), _ptr(rvp), _ptr(out), _ptr(coef), _stream())
+    return out, coef
+
+
+def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True):
+    """Returns dy3, du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p."""
+    n, c, h, w = y3.shape
+    dout = as_nhwc(dout)
+    if nhwc_pitch(dout) != nhwc_pitch(out):
+        dout = dout.contiguous(memory_format=torch.channels_last)
+    d = qarep_desc(y3, u, out, eps3, eps_post, 0.0, act, use_post_bn)
+    sums = torch.zeros((3, c), dtype=torch.float64, device=y3.device)
+    L.call("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
+    dy3, du = torch.empty_like(y3), torch.empty_like(u)
+    z = lambda: torch.zeros(c, dtype=torch.float32, device=y3.device)  # noqa: E731
+    dg3, db3, dab, dgp, dbp = z(), z(), z(), z(), z()
+    L.call("sgb_qarep_bwd_apply", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
+    return dy3, du, dg3, db3, dab, dgp, dbp
+
+
+# ------------------------------------------------------------------------------------------------ pooling / misc
+def maxpool_fwd(x, k, stride, pad, want_idx=True, out=None):
+    n, c, h, w = x.shape
+    P, Q = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    if out is None:
+        out = empty_nhwc(n, c, P, Q, x.device)
+    idx = torch.empty((n, P, Q, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    L.call("sgb_maxpool_fwd", _ptr(x), n, h, w, c, nhwc_pitch(x), 0, k, stride, pad, _ptr(out), P, Q, nhwc_pitch(out), 0, _ptr(idx), _stream())
+    return out, idx
+
+
+def maxpool_bwd(dy, idx, x_shape, k, stride, pad):
+    n, c, h, w = x_shape
+    dy = as_nhwc(dy)
+    dx = torch.zeros((n, h, w, c), dtype=torch.float32, device=dy.device)
+    L.call("sgb_maxpool_bwd", _ptr(dy), n, h, w, c, k, stride, pad, dy.shape[2], dy.shape[3], nhwc_pitch(dy), 0, _ptr(idx), _ptr(dx), _stream())
+    return dx.permute(0, 3, 1, 2)  # NCHW-shaped view of NHWC fp32 storage
+
+
+def axpby(x1, a, x2=None, b=0.0, out=None):
+    n, c, h, w = x1.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x1.device)
+    L.call("sgb_axpby", _ptr(x1), nhwc_pitch(x1), 0, float(a), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, float(b), _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
+    return out
+
+
+def f32_to_bf16(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.call("sgb_f32_to_bf16", _ptr(x.contiguous()), _ptr(y), x.numel(), _stream())
+    return y
+
+
+def avgpool_fwd(x):
+    n, c, h, w = x.shape
+    if nhwc_pitch(x) != c:
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((n, c, 1, 1), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    L.call("sgb_avgpool_fwd", _ptr(x), n, h * w, c, _ptr(y), _stream())
+    return y
+
+
+def avgpool_bwd(dy, hw_shape):
+    n, c = dy.shape[0], dy.shape[1]
+    h, w = hw_shape
+    dyc = dy.reshape(n, c).contiguous()
+    dx = torch.empty((n, c, h, w), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+    L.call("sgb_avgpool_bwd", _ptr(dyc), n, h * w, c, _ptr(dx), _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ head / loss / nms
+def dfl_decode(reg, cls, L_total, anchor_base, ncls, reg_max, stride, cell_offset, pred_bboxes, pred_scores, cls_logits=None, reg_distri=None):
+    n, _, hf, wf = reg.shape
+    L.call("sgb_dfl_decode", _ptr(reg), nhwc_pitch(reg), _ptr(cls), nhwc_pitch(cls), n, hf, wf, L_total, anchor_base, ncls, reg_max, float(stride), float(cell_offset), _ptr(pred_bboxes), _ptr(pred_scores), _ptr(cls_logits), _ptr(reg_distri), _stream())
+
+
+def head_grad_scatter(grad, n, hw, L_total, anchor_base, dy):
+    gC = grad.shape[-1]
+    L.call("sgb_head_grad_scatter", _ptr(grad), gC, n, hw, L_total, anchor_base, _ptr(dy), nhwc_pitch(dy), _stream())
+
+
+def loss_desc(B, Lc, ncls, reg_max, n_max, topk=13, alpha=1.0, beta=6.0, w_cls=1.0, w_iou=2.5, w_dfl=0.5, iou_type=0) -> L.LossDesc:
+    d = L.LossDesc()
+    d.B, d.L, d.ncls, d.reg_max, d.n_max, d.topk = B, Lc, ncls, reg_max, n_max, topk
+    d.alpha, d.beta, d.w_cls, d.w_iou, d.w_dfl, d.iou_type = alpha, beta, w_cls, w_iou, w_dfl, iou_type
+    return d
+
+
+def tal_assign(d, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, sums):
+    dev = cls_logits.device
+    al = torch.empty((d.B, d.L), dtype=torch.int32, device=dev)
+    ab = torch.empty((d.B, d.L, 4), dtype=torch.float32, device=dev)
+    asc = torch.empty((d.B, d.L), dtype=torch.float32, device=dev)
+    nbytes = L.load().sgb_tal_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.call("sgb_tal_assign", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(gt_boxes), _ptr(gt_labels), _ptr(gt_valid), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), _ptr(ws), nbytes, _stream())
+    return al, ab, asc
+
+
+def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
+    gc = torch.empty_like(cls_logits) if want_grad else None
+    gr = torch.empty_like(reg_distri) if want_grad else None
+    L.call("sgb_dfl_iou_loss_fwd_bwd", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), float(grad_scale), _ptr(gc), _ptr(gr), _stream())
+    out = torch.empty(4, dtype=torch.float32, device=cls_logits.device)
+    L.call("sgb_loss_finalize", ctypes.byref(d), _ptr(sums), _ptr(out), _stream())
+    return out, gc, gr
+
+
+def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=True, class_agnostic=False, thr_inclusive=None):
+    """boxes [B,L,4] f32, scores [B,L,C] f32 -> (out [B,max_out,6], out_idx [B,max_out] int32, count [B] int32)."""
+    require_cuda(boxes, "boxes")
+    B, Lc, C = scores.shape
+    d = L.NmsDesc()
+    d.B, d.L, d.ncls = B, Lc, C
+    d.score_thr, d.iou_thr = float(score_thr), float(iou_thr)
+    d.top_k, d.max_out = int(top_k), int(max_out)
+    d.multi_label, d.class_agnostic = int(bool(multi_label)), int(bool(class_agnostic))
+    d.thr_inclusive = int(not multi_label) if thr_inclusive is None else int(bool(thr_inclusive))
+    boxes = boxes.contiguous().float()
+    scores = scores.contiguous().float()
+    out = torch.empty((B, max_out, 6), dtype=torch.float32, device=boxes.device)
+    oidx = torch.empty((B, max_out), dtype=torch.int32, device=boxes.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    nbytes = L.load().sgb_nms_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
+    L.call("sgb_batched_nms", ctypes.byref(d), _ptr(boxes), _ptr(scores), _ptr(out), _ptr(oidx), _ptr(cnt), _ptr(ws), nbytes, _stream())
+    return out, oidx, cnt
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+def sgd_step(p, g, mom, lr, momentum, wd, grad_scale=1.0, nesterov=False):
+    L.call("sgb_sgd_step", _ptr(p), _ptr(g), _ptr(mom), p.numel(), float(lr), float(momentum), float(wd), float(grad_scale), int(nesterov), _stream())
+
+
+def adamw_step(p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0):
+    L.call("sgb_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps), float(wd), float(1 - b1**step), float(1 - b2**step), float(grad_scale), _stream())
+
+
+def ema_update(ema, p, decay):
+    L.call("sgb_ema_update", _ptr(ema), _ptr(p), p.numel(), float(decay), _stream())
