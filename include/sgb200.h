@@ -161,6 +161,12 @@ int sgb_maxpool_bwd(const sgb_bf16* dy, int N, int H, int W, int C, int k, int s
 /* y[slice] = a*x1 + b*x2 (x2 optional) over NHWC bf16 slices: concat copies, residual adds, grad accumulation */
 int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_bf16* x2, int p2, int o2, float b, sgb_bf16* y,
               int py, int oy, int64_t M, int C, void* stream);
+/* y = (*a_dev)*x1 + x2 with the scalar read on the device (learnable residual weight, yolo_stages.py:61-63) and
+ * out[c] += sum_pixels a*b (fp64), used for d(alpha). */
+int sgb_scale_add(const sgb_bf16* x1, int p1, int o1, const float* a_dev, const sgb_bf16* x2, int p2, int o2, sgb_bf16* y,
+                  int py, int oy, int64_t M, int C, void* stream);
+int sgb_channel_dot(const sgb_bf16* a, int pa, int oa, const sgb_bf16* b, int pb, int ob, int64_t M, int C, double* out,
+                    void* stream);
 int sgb_f32_to_bf16(const float* x, sgb_bf16* y, int64_t n, void* stream);
 /* global average pool NHWC bf16 -> [N, C] bf16 and its backward */
 int sgb_avgpool_fwd(const sgb_bf16* x, int N, int HW, int C, sgb_bf16* y, void* stream);

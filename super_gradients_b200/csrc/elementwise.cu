@@ -610,6 +610,38 @@ __global__ void axpby_kernel(const bf16* __restrict__ x1, int p1, int o1, float 
   }
 }
 
+__global__ void scale_add_kernel(const bf16* __restrict__ x1, int p1, int o1, const float* a_dev,
+                                 const bf16* __restrict__ x2, int p2, int o2, bf16* y, int py, int oy, int64_t M, int C) {
+  const float a = *a_dev;
+  const int cvs = C / 8;
+  const int64_t total = M * cvs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = i % cvs;
+    int64_t pix = i / cvs;
+    V8 u = ld8(x1 + pix * p1 + o1 + cv * 8);
+    if (x2) {
+      V8 v = ld8(x2 + pix * p2 + o2 + cv * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u.v[e] = a * u.v[e] + v.v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u.v[e] = a * u.v[e];
+    }
+    st8(y + pix * py + oy + cv * 8, u);
+  }
+}
+
+struct DotF {
+  static constexpr int NACC = 1;
+  const bf16 *a, *b;
+  int pa, oa, pb, ob;
+  __device__ void eval(int64_t pix, int c0, float (&acc)[1][8]) const {
+    V8 u = ld8(a + pix * pa + oa + c0), v = ld8(b + pix * pb + ob + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] += u.v[e] * v.v[e];
+  }
+};
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
@@ -861,6 +893,23 @@ extern "C" int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_
       (const bf16*)x1, p1, o1, a, (const bf16*)x2, p2, o2, b, (bf16*)y, py, oy, M, C);
   SGB_LAUNCH_CHECK("axpby_kernel");
   return SGB_OK;
+}
+
+extern "C" int sgb_scale_add(const sgb_bf16* x1, int p1, int o1, const float* a_dev, const sgb_bf16* x2, int p2, int o2,
+                             sgb_bf16* y, int py, int oy, int64_t M, int C, void* stream) {
+  SGB_REQUIRE(x1 && y && a_dev && C % 8 == 0 && p1 % 8 == 0 && o1 % 8 == 0 && py % 8 == 0 && oy % 8 == 0, "bad args");
+  SGB_REQUIRE(!x2 || (p2 % 8 == 0 && o2 % 8 == 0), "bad args (x2)");
+  scale_add_kernel<<<grid_for(M * (C / 8), TPB * 4), TPB, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x1, p1, o1, a_dev, (const bf16*)x2, p2, o2, (bf16*)y, py, oy, M, C);
+  SGB_LAUNCH_CHECK("scale_add_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_channel_dot(const sgb_bf16* a, int pa, int oa, const sgb_bf16* b, int pb, int ob, int64_t M, int C,
+                               double* out, void* stream) {
+  SGB_REQUIRE(a && b && out && C % 8 == 0 && pa % 8 == 0 && oa % 8 == 0 && pb % 8 == 0 && ob % 8 == 0, "bad args");
+  DotF f{(const bf16*)a, (const bf16*)b, pa, oa, pb, ob};
+  return launch_chan_reduce(f, M, C, out, C, (cudaStream_t)stream);
 }
 
 extern "C" int sgb_f32_to_bf16(const float* x, sgb_bf16* y, int64_t n, void* stream) {

@@ -1,0 +1,391 @@
+"""Autograd glue: each torch.autograd.Function below is one fused hot-path block whose forward AND backward are
+libsgb200 kernels (kernels.py).  torch only owns memory, streams and the autograd tape.
+
+Activations are channels_last bf16 (NHWC); parameters stay fp32 (state-dict compatible with the reference) and are
+re-laid-out to bf16 KRSC / CRSK once per optimizer step (cached on the parameter's version counter).
+"""
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+
+__all__ = [
+    "to_nhwc",
+    "from_nhwc",
+    "conv_bn_act",
+    "conv_bias",
+    "qarepvgg_block",
+    "conv_transpose2x2",
+    "max_pool",
+    "concat",
+    "add",
+    "global_avg_pool",
+    "dfl_decode",
+]
+
+
+class WeightCache:
+    """bf16 KRSC / CRSK copies of an fp32 OIHW conv weight, refreshed when the parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.krsc = None
+        self.crsk = None
+
+    def get(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, add_identity=False, extra_key=None):
+        key = (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key)
+        if key != self.key:
+            self.krsc, self.crsk = K.weight_prepare(w, scale=scale, add_identity=add_identity)
+            self.key = key
+        return self.krsc, self.crsk
+
+
+def _chan_sum(dy: torch.Tensor) -> torch.Tensor:
+    """Per-channel sum over pixels of an NHWC bf16 tensor (bias gradients) -> fp32 [C]."""
+    n, c, h, w = dy.shape
+    pitch = K.nhwc_pitch(dy)
+    cp = ((c + 7) // 8) * 8
+    view = dy if cp == c else torch.as_strided(dy, (n, cp, h, w), (h * w * pitch, 1, w * pitch, pitch), dy.storage_offset())
+    return K.channel_stats(view)[0, 0, :c].float()
+
+
+# ------------------------------------------------------------------------------------------------------------ layout
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """fp32/bf16 NCHW image batch -> bf16 NHWC with channels zero-padded to a multiple of 8 (no gradient)."""
+    K.require_cuda(x, "input")
+    if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        return K.as_nhwc(x)
+    return K.nchw_f32_to_nhwc_bf16(x.detach())
+
+
+class _FromNhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.nhwc_bf16_to_nchw_f32(K.as_nhwc(x))
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.as_nhwc(g)
+
+
+def from_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """bf16 NHWC -> fp32 contiguous NCHW (differentiable)."""
+    return _FromNhwc.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------------------ conv + BN
+class _ConvBnAct(torch.autograd.Function):
+    """act(bn_train(conv(x)) + residual): GEMM with fused per-channel statistics, then one normalise+act pass."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, residual, cfg):
+        x = K.as_nhwc(x)
+        krsc, crsk = cfg.cache.get(w)
+        kout, _, r, s = w.shape
+        stats = K.new_stats(kout, x.device)
+        y_raw = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, stats=stats)
+        res = K.as_nhwc(residual) if residual is not None else None
+        out, mean, rstd = K.bn_act_fwd(y_raw, stats, gamma, beta, cfg.running_mean, cfg.running_var, cfg.eps, cfg.momentum, cfg.act, res)
+        if cfg.num_batches_tracked is not None:
+            cfg.num_batches_tracked += 1
+        ctx.save_for_backward(x, y_raw, out, gamma, mean, rstd)
+        ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_res = cfg, crsk, tuple(w.shape), residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y_raw, out, gamma, mean, rstd = ctx.saved_tensors
+        cfg = ctx.cfg
+        kout, cin, r, s = ctx.wshape
+        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad)
+        dw = K.wgrad_to_oihw(K.conv_wgrad(x, dy, r, s, cfg.stride, cfg.pad), cin)
+        return dx, dw, dgamma, dbeta, dres, None
+
+
+def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracked, *, stride, pad, eps, momentum, act, training, cache: WeightCache, residual=None):
+    """Conv2d(bias=False) -> BatchNorm2d -> (+ residual) -> activation.   reference: modules/conv_bn_act_block.py:92-93,
+    training/models/classification_models/resnet.py:53-84 (the residual form)."""
+    K.require_cuda(x, "x")
+    if training:
+        cfg = SimpleNamespace(stride=stride, pad=pad, eps=eps, momentum=momentum, act=act, cache=cache, running_mean=running_mean, running_var=running_var, num_batches_tracked=num_batches_tracked)
+        return _ConvBnAct.apply(x, w, gamma, beta, residual, cfg)
+    # inference: BN folded into the GEMM epilogue (one kernel)
+    with torch.no_grad():
+        x = K.as_nhwc(x)
+        krsc, _ = cache.get(w)
+        scale = gamma * torch.rsqrt(running_var + eps)
+        shift = beta - running_mean * scale
+        res = K.as_nhwc(residual) if residual is not None else None
+        kout, _, r, s = w.shape
+        return K.conv_fprop(x, krsc, kout, r, s, stride, pad, scale=scale, shift=shift, residual=res, act=act)
+
+
+class _ConvBias(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, cfg):
+        x = K.as_nhwc(x)
+        krsc, crsk = cfg.cache.get(w)
+        kout, _, r, s = w.shape
+        y = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, shift=b, act=cfg.act)
+        ctx.save_for_backward(x)
+        ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_bias = cfg, crsk, tuple(w.shape), b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        cfg = ctx.cfg
+        kout, cin, r, s = ctx.wshape
+        dy = K.as_nhwc(dy)
+        if K.nhwc_pitch(dy) % 8 != 0 or (kout % 8 != 0 and K.nhwc_pitch(dy) < ((kout + 7) // 8) * 8):
+            pad = K.empty_nhwc(dy.shape[0], kout, dy.shape[2], dy.shape[3], dy.device)
+            pad.copy_(dy)
+            dy = pad
+        dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad) if ctx.needs_input_grad[0] else None
+        dw = K.wgrad_to_oihw(K.conv_wgrad(x, dy, r, s, cfg.stride, cfg.pad), cin)
+        db = _chan_sum(dy) if ctx.has_bias else None
+        return dx, dw, db, None
+
+
+def conv_bias(x, w, b, *, stride, pad, cache: WeightCache, act=None):
+    """Plain Conv2d (+ bias), e.g. the cls/reg prediction convs (yolo_nas/dfl_heads.py:65-66) and nn.Linear as 1x1."""
+    K.require_cuda(x, "x")
+    cfg = SimpleNamespace(stride=stride, pad=pad, cache=cache, act=act)
+    return _ConvBias.apply(x, w, b, cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------ QARepVGG
+class _QARepVGG(torch.autograd.Function):
+    """Train-mode QARepVGG block (modules/qarepvgg_block.py:184-204) as
+        y3 = conv3x3(x);  u = conv1x1_{alpha*K1 + I}(x);  out = act(a3*y3 + au*u + c0)
+    where the per-channel coefficients fold bn(3x3 branch), the 1x1 bias, the identity and post_bn, and are derived
+    from five fused moments (sum y3, y3^2, u, u^2, y3*u).  Backward is one reduction pass + one apply pass, then
+    dgrad/wgrad of the two GEMMs (the identity and alpha ride inside the folded 1x1 weights)."""
+
+    @staticmethod
+    def forward(ctx, x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
+        x = K.as_nhwc(x)
+        kout = w3.shape[0]
+        k3, c3 = cfg.cache3.get(w3)
+        k1, c1 = cfg.cache1.get(w1, scale=alpha, add_identity=cfg.residual)
+        y3 = K.conv_fprop(x, k3, kout, 3, 3, cfg.stride, 1)
+        u = K.conv_fprop(x, k1, kout, 1, 1, cfg.stride, 0)
+        ab = None
+        if bias1 is not None:
+            ab = bias1 * alpha if alpha is not None else bias1
+        out, coef = K.qarep_fwd(y3, u, g3, b3, ab, gp, bp, cfg.rm3, cfg.rv3, cfg.rmp, cfg.rvp, cfg.eps, cfg.eps, cfg.momentum, cfg.act, cfg.use_post_bn)
+        for nbt in cfg.nbt:
+            if nbt is not None:
+                nbt += 1
+        ctx.save_for_backward(x, y3, u, out, coef, g3, gp if gp is not None else g3, w1, bias1 if bias1 is not None else g3, alpha if alpha is not None else g3)
+        ctx.cfg, ctx.c3, ctx.c1 = cfg, c3, c1
+        ctx.flags = (bias1 is not None, alpha is not None, gp is not None, w3.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y3, u, out, coef, g3, gp, w1, bias1, alpha = ctx.saved_tensors
+        cfg = ctx.cfg
+        has_bias, has_alpha, has_post, cin = ctx.flags
+        dy3, du, dg3, db3, dab, dgp, dbp = K.qarep_bwd(dout, out, y3, u, coef, g3, gp if has_post else None, cfg.eps, cfg.eps, cfg.act, cfg.use_post_bn)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1)
+            K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=dx, accumulate=True)
+        dw3 = K.wgrad_to_oihw(K.conv_wgrad(x, dy3, 3, 3, cfg.stride, 1), cin)
+        dw1f = K.wgrad_to_oihw(K.conv_wgrad(x, du, 1, 1, cfg.stride, 0), cin)  # grad of the folded alpha*K1 + I
+        dalpha = None
+        if has_alpha:
+            dalpha = (dw1f * w1).sum().reshape(1)
+            if has_bias:
+                dalpha = dalpha + (dab * bias1).sum().reshape(1)
+            dw1 = dw1f * alpha
+            dbias1 = dab * alpha if has_bias else None
+        else:
+            dw1 = dw1f
+            dbias1 = dab if has_bias else None
+        return dx, dw3, dg3, db3, dw1, dbias1, dalpha, (dgp if has_post else None), (dbp if has_post else None), None
+
+
+def qarepvgg_block(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
+    K.require_cuda(x, "x")
+    return _QARepVGG.apply(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------ ConvTranspose 2x2/s2
+class _ConvT2x2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, cache):
+        x = K.as_nhwc(x)
+        cin, cout = w.shape[0], w.shape[1]
+        key = (w.data_ptr(), w._version)
+        if cache.get("key") != key:
+            wd = w.detach()
+            cache["w_up"] = wd.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous().to(torch.bfloat16)  # [(dh,dw,co)][ci]
+            cache["w_dn"] = wd.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)  # [ci][dh][dw][co]
+            cache["key"] = key
+        y = K.convt2x2_fprop(x, cache["w_up"], b, cout)
+        ctx.save_for_backward(x)
+        ctx.w_dn, ctx.shape, ctx.has_bias = cache["w_dn"], (cin, cout), b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        cin, cout = ctx.shape
+        dy = K.as_nhwc(dy)
+        dx = K.conv_fprop(dy, ctx.w_dn, cin, 2, 2, 2, 0) if ctx.needs_input_grad[0] else None
+        dwk = K.conv_wgrad(dy, x, 2, 2, 2, 0)  # [ci][dh][dw][co]
+        dw = dwk.permute(0, 3, 1, 2).contiguous()
+        db = _chan_sum(dy) if ctx.has_bias else None
+        return dx, dw, db, None
+
+
+def conv_transpose2x2(x, w, b, cache: dict):
+    """nn.ConvTranspose2d(c, c, kernel_size=2, stride=2) (modules/sampling.py:72-73)."""
+    K.require_cuda(x, "x")
+    return _ConvT2x2.apply(x, w, b, cache)
+
+
+# ------------------------------------------------------------------------------------------------------------ pooling, glue
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        x = K.as_nhwc(x)
+        y, idx = K.maxpool_fwd(x, k, stride, pad, want_idx=x.requires_grad or torch.is_grad_enabled())
+        ctx.idx, ctx.geom = idx, (tuple(x.shape), k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, k, stride, pad = ctx.geom
+        dx32 = K.maxpool_bwd(dy, ctx.idx, shape, k, stride, pad)  # fp32, NHWC storage
+        return K.as_nhwc(dx32), None, None, None
+
+
+def max_pool(x, k, stride, pad):
+    return _MaxPool.apply(x, k, stride, pad)
+
+
+class _Concat(torch.autograd.Function):
+    """Channel concat into one NHWC buffer (each input is copied once by our axpby kernel); backward hands out views."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [K.as_nhwc(x) for x in xs]
+        n, _, h, w = xs[0].shape
+        cs = [x.shape[1] for x in xs]
+        out = K.empty_nhwc(n, sum(cs), h, w, xs[0].device)
+        off = 0
+        for x, c in zip(xs, cs):
+            K.axpby(x, 1.0, out=out[:, off : off + c])
+            off += c
+        ctx.cs = cs
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = K.as_nhwc(dy)
+        outs, off = [], 0
+        for c in ctx.cs:
+            outs.append(dy[:, off : off + c])
+            off += c
+        return tuple(outs)
+
+
+def concat(xs):
+    return _Concat.apply(*xs)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, a, b):
+        x1, x2 = K.as_nhwc(x1), K.as_nhwc(x2)
+        ctx.ab = (a, b)
+        return K.axpby(x1, a, x2, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b = ctx.ab
+        dy = K.as_nhwc(dy)
+        d1 = dy if a == 1.0 else K.axpby(dy, a)
+        d2 = dy if b == 1.0 else K.axpby(dy, b)
+        return d1, d2, None, None
+
+
+def add(x1, x2, a=1.0, b=1.0):
+    """a*x1 + b*x2 (residual connections)."""
+    return _Add.apply(x1, x2, float(a), float(b))
+
+
+class _GlobalAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = K.as_nhwc(x)
+        ctx.hw = (x.shape[2], x.shape[3])
+        return K.avgpool_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.avgpool_bwd(K.as_nhwc(dy), ctx.hw)
+
+
+def global_avg_pool(x):
+    return _GlobalAvgPool.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------------------ head decode
+class _DflDecode(torch.autograd.Function):
+    """NDFLHeads decode (yolo_nas/dfl_heads.py:199-245): per-level bf16 NHWC reg/cls maps -> fp32 [B, L, *] tensors."""
+
+    @staticmethod
+    def forward(ctx, cfg, *maps):
+        regs, clss = maps[0::2], maps[1::2]
+        regs = [K.as_nhwc(r) for r in regs]
+        clss = [K.as_nhwc(c) for c in clss]
+        B = regs[0].shape[0]
+        hws = [r.shape[2] * r.shape[3] for r in regs]
+        Ltot = sum(hws)
+        dev = regs[0].device
+        nb = cfg.reg_max + 1
+        pb = torch.empty((B, Ltot, 4), dtype=torch.float32, device=dev)
+        ps = torch.empty((B, Ltot, cfg.num_classes), dtype=torch.float32, device=dev)
+        cl = torch.empty((B, Ltot, cfg.num_classes), dtype=torch.float32, device=dev)
+        rd = torch.empty((B, Ltot, 4 * nb), dtype=torch.float32, device=dev)
+        base = 0
+        for r, c, s, hw in zip(regs, clss, cfg.strides, hws):
+            K.dfl_decode(r, c, Ltot, base, cfg.num_classes, cfg.reg_max, s, cfg.cell_offset, pb, ps, cl, rd)
+            base += hw
+        ctx.geom = (B, hws, Ltot, [tuple(r.shape) for r in regs], [tuple(c.shape) for c in clss])
+        ctx.mark_non_differentiable(pb, ps)
+        return pb, ps, cl, rd
+
+    @staticmethod
+    def backward(ctx, _gpb, _gps, gcl, grd):
+        B, hws, Ltot, rshapes, cshapes = ctx.geom
+        outs = [None]
+        base = 0
+        for hw, rs, cs in zip(hws, rshapes, cshapes):
+            dr = dc = None
+            if grd is not None:
+                dr = K.empty_nhwc(rs[0], rs[1], rs[2], rs[3], grd.device)
+                K.head_grad_scatter(grd.contiguous(), B, hw, Ltot, base, dr)
+            if gcl is not None:
+                dc = K.empty_nhwc(cs[0], cs[1], cs[2], cs[3], gcl.device)
+                K.head_grad_scatter(gcl.contiguous(), B, hw, Ltot, base, dc)
+            outs += [dr, dc]
+            base += hw
+        return tuple(outs)
+
+
+def dfl_decode(regs, clss, strides, num_classes, reg_max, cell_offset):
+    cfg = SimpleNamespace(strides=tuple(strides), num_classes=num_classes, reg_max=reg_max, cell_offset=cell_offset)
+    maps = []
+    for r, c in zip(regs, clss):
+        maps += [r, c]
+    return _DflDecode.apply(cfg, *maps)

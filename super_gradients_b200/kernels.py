@@ -68,7 +68,10 @@ def as_nhwc(t: torch.Tensor) -> torch.Tensor:
                 return t
         except L.SgbError:
             pass
-    return t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    n, c, h, w = t.shape
+    out = empty_nhwc(n, c, h, w, t.device)
+    out.copy_(t)
+    return out
 
 
 def empty_nhwc(n, c, h, w, device, c_alloc=None) -> torch.Tensor:
@@ -333,6 +336,23 @@ def axpby(x1, a, x2=None, b=0.0, out=None):
     if out is None:
         out = empty_nhwc(n, c, h, w, x1.device)
     L.call("sgb_axpby", _ptr(x1), nhwc_pitch(x1), 0, float(a), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, float(b), _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
+    return out
+
+
+def scale_add(x1, a_dev, x2=None, out=None):
+    """(*a_dev) * x1 + x2 with the scalar read on the device (no host sync)."""
+    n, c, h, w = x1.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x1.device)
+    L.call("sgb_scale_add", _ptr(x1), nhwc_pitch(x1), 0, _ptr(a_dev), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
+    return out
+
+
+def channel_dot(a, b) -> torch.Tensor:
+    """fp64 [C]: sum over pixels of a*b."""
+    n, c, h, w = a.shape
+    out = torch.zeros(c, dtype=torch.float64, device=a.device)
+    L.call("sgb_channel_dot", _ptr(a), nhwc_pitch(a), 0, _ptr(b), nhwc_pitch(b), 0, n * h * w, c, _ptr(out), _stream())
     return out
 
 

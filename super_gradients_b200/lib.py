@@ -128,6 +128,8 @@ _SIGNATURES = {
     "sgb_maxpool_fwd": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, _I, _I, _I, _I, P, P]),
     "sgb_maxpool_bwd": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, P, P]),
     "sgb_axpby": (c_int, [P, _I, _I, _F, P, _I, _I, _F, P, _I, _I, _L, _I, P]),
+    "sgb_scale_add": (c_int, [P, _I, _I, P, P, _I, _I, P, _I, _I, _L, _I, P]),
+    "sgb_channel_dot": (c_int, [P, _I, _I, P, _I, _I, _L, _I, P, P]),
     "sgb_f32_to_bf16": (c_int, [P, P, _L, P]),
     "sgb_avgpool_fwd": (c_int, [P, _I, _I, _I, P, P]),
     "sgb_avgpool_bwd": (c_int, [P, _I, _I, _I, P, P]),
