@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: images/sec of a YOLO-NAS-S 640x640 bf16 TRAINING step (config 2:
+synthetic COCO-shape data, 32 images per GPU, AdamW, PPYoloELoss with the task-aligned assigner), weak scaling.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec YOLO-NAS-S 640 bf16 train"
+TRAIN_GFLOP_PER_IMG = 101.6  # 3 x 2 x 16.939 GMAC (fprop + dgrad + wgrad of the train graph)
+IMG, BATCH, NCLS, NBOX = 640, 32, 80, 8
+
+
+def synth_batch(batch, seed, img=IMG):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 3, img, img, generator=g)
+    rows = []
+    for b in range(batch):
+        cxy = torch.rand(NBOX, 2, generator=g) * (img - 200) + 100
+        wh = torch.rand(NBOX, 2, generator=g) * 150 + 30
+        cls = torch.randint(0, NCLS, (NBOX, 1), generator=g).float()
+        rows.append(torch.cat([torch.full((NBOX, 1), float(b)), cls, cxy, wh], 1))
+    return x, torch.cat(rows)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# =============================================================================================== reference arm (CPU)
+def cpu_train_sample(batch, img, threads, steps=1, warmup=0):
+    """The reference's own arithmetic (oracle port, fp32 CPU: oracle/yolo_nas_oracle.py) for the same train step, on a
+    bounded sample.  Returns (images/sec, seconds per step)."""
+    import torch
+
+    import yaml
+
+    from oracle.yolo_nas_oracle import random_state, train_step
+
+    torch.set_num_threads(threads)
+    # nothing from the product package on this path: shapes come from the reference-generated fixture, the arch from yaml
+    table = torch.load(os.path.join(ROOT, "tests", "golden", "state_keys.pt"), weights_only=False)
+    state = random_state(table["yolo_nas_s"], seed=0)
+    live = [k for k in table["yolo_nas_s/param_names"] if "rbr_reparam" not in k]
+    arch = yaml.safe_load(open(os.path.join(ROOT, "super_gradients_b200", "recipes", "arch_params", "yolo_nas_s_arch_params.yaml")))
+    arch["bn_eps"], arch["bn_momentum"] = float(arch["bn_eps"]), float(arch["bn_momentum"])
+    x, t = synth_batch(batch, 123, img)
+    opt_state = {k: (torch.zeros_like(state[k]), torch.zeros_like(state[k])) for k in live}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _items, grads = train_step(arch, state, x, t, NCLS, live)
+        for k, g in grads.items():  # AdamW, as in the GPU arm
+            m1, m2 = opt_state[k]
+            m1.mul_(0.9).add_(g, alpha=0.1)
+            m2.mul_(0.999).addcmul_(g, g, value=0.001)
+            state[k].mul_(1 - 2e-4 * 1e-5).addcdiv_(m1 / (1 - 0.9 ** (it + 1)), (m2 / (1 - 0.999 ** (it + 1))).sqrt_().add_(1e-8), value=-2e-4)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return batch / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    batch, img = 4, IMG
+    ips, sec = cpu_train_sample(batch, img, cores, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "YOLO-NAS-S 640x640 train step (fwd + PPYoloELoss/TAL + bwd + AdamW), CPU", "per_step_batch": batch},
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": f"{batch} images x 640x640 per step, fp32, torch CPU threads={cores}"},
+        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+# =============================================================================================== our arm (GPU)
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from super_gradients_b200 import kernels as K
+    from super_gradients_b200 import lib
+    from super_gradients_b200.training import models
+    from super_gradients_b200.training.losses import PPYoloELoss, pad_targets_host
+    from super_gradients_b200.training.sg_trainer import TrainStep, setup_device
+
+    dev = setup_device()
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lib.call("sgb_check_device")
+    torch.manual_seed(0)
+    model = models.get("yolo_nas_s", num_classes=NCLS).to(dev).train()
+    crit = PPYoloELoss(num_classes=NCLS, use_static_assigner=False)
+    step = TrainStep(model, crit, "AdamW", {"weight_decay": 1e-5}, zero_wd_on_bias_and_bn=True, ema=True)
+    batch = args.batch
+
+    # ---- synthetic data: distinct batches so that consecutive steps do not re-read the same inputs from L2
+    nbuf = 4
+    host_x, host_t, dev_x, dev_t = [], [], [], []
+    for i in range(nbuf):
+        x, t = synth_batch(batch, 1000 * rank + i)
+        gb, gl, gv = pad_targets_host(t, batch, NBOX)
+        host_x.append(x.pin_memory())
+        host_t.append((gb.pin_memory(), gl.pin_memory(), gv.pin_memory()))
+        dev_x.append(x.to(dev))
+        dev_t.append((gb.to(dev), gl.to(dev), gv.to(dev)))
+
+    def lr_at(i):
+        return 2e-4
+
+    # ---- count our kernel launches of one eager step (the claim behind `gpu_launches`)
+    step.set_hyper_params(lr_at(0), 0.9997)
+    lib.LAUNCHES[0] = 0
+    step.run(dev_x[0], dev_t[0])
+    torch.cuda.synchronize()
+    launches_per_step = lib.LAUNCHES[0]
+
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            step.capture(dev_x[0], dev_t[0], warmup=2)
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr)
+            step.graph = None
+            use_graph = False
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (A) device-resident throughput: `value`
+    for i in range(args.warmup):
+        step.set_hyper_params(lr_at(i), 0.9997)
+        step.run(dev_x[i % nbuf], dev_t[i % nbuf])
+    sampler = ClockSampler(dev.index or 0)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step.set_hyper_params(lr_at(i), 0.9997)
+        loss, _ = step.run(dev_x[i % nbuf], dev_t[i % nbuf])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    final_loss = float(loss)
+    value = world * batch * args.steps / (ms / 1e3)
+
+    # ---- (B) end to end through the public step API with HOST (pinned) inputs: H2D of the batch + D2H of the loss
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty_like(dev_x[0]), tuple(torch.empty_like(t) for t in dev_t[0])) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            stage[s][0].copy_(host_x[i % nbuf], non_blocking=True)
+            for d, h in zip(stage[s][1], host_t[i % nbuf]):
+                d.copy_(h, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record()
+    loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    e2e_steps = args.steps
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prefetch(0)
+    f0.record()
+    for i in range(e2e_steps):
+        if i + 1 < e2e_steps:
+            prefetch(i + 1)
+        s = i % 2
+        torch.cuda.current_stream().wait_event(ready[s])
+        step.set_hyper_params(lr_at(i), 0.9997)
+        loss, items = step.run(stage[s][0], stage[s][1])
+        consumed[s].record()
+        loss_host.copy_(items, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+    f1.record()
+    barrier()
+    ms2 = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t)
+    e2e = world * batch * e2e_steps / (ms2 / 1e3)
+    h2d = host_x[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_t[0])
+
+    # ---- (C) roofline of the dominant kernel family (implicit-GEMM convolutions): CUDA events around every launch
+    roof = None
+    if rank == 0:
+        tf_peak, hbm_peak, which = peaks()
+        K.PROFILE.clear()
+        K.PROFILE_ON[0] = True
+        n_prof = 2
+        for i in range(n_prof):
+            step.set_hyper_params(lr_at(i), 0.9997)
+            step._step_eager(dev_x[i % nbuf], dev_t[i % nbuf])
+        torch.cuda.synchronize()
+        K.PROFILE_ON[0] = False
+        per = {}
+        for name, a, b in K.PROFILE:
+            per[name] = per.get(name, 0.0) + a.elapsed_time(b)
+        conv_ms = sum(v for k, v in per.items() if k.startswith("sgb_conv")) / n_prof
+        flops = TRAIN_GFLOP_PER_IMG * 1e9 * batch
+        achieved = flops / (conv_ms / 1e3) / 1e12
+        roof = {
+            "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+            "kernel": "igemm_conv_kernel + wgrad_kernel (all conv fprop/dgrad/wgrad launches of one step)", "peak_source": which,
+            "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms / args.steps),
+            "per_call_ms": {k: v / n_prof for k, v in sorted(per.items(), key=lambda kv: -kv[1])[:12]},
+        }  # fmt: skip
+
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cpu = None
+    if not args.skip_cpu_baseline and world == 1:
+        ips, sec = cpu_train_sample(2, IMG, cores, steps=1, warmup=0)
+        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": f"1 step of 2 images 640x640, fp32 oracle port (oracle/yolo_nas_oracle.py), {sec:.1f} s"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": "configs[1]: YOLO-NAS-S 640x640 synthetic COCO-shape train step (fwd + PPYoloELoss/TAL + bwd + AdamW + EMA)", "per_gpu_batch": batch,
+            "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graph": use_graph,
+            "l2": "4 distinct 157 MB input batches rotate (each > 126 MB L2); activations of a step (> 10 GB) never fit L2",
+        },
+        "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "ms_per_step": ms2 / e2e_steps},
+        "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
+        "conv_tflops_whole_step": TRAIN_GFLOP_PER_IMG * 1e9 * batch * world / (ms / args.steps / 1e3) / 1e12,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

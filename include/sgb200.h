@@ -228,11 +228,13 @@ int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const float* scores
                     int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- optimizer over the flat parameter buffer (sg_trainer.py:634-644) --------------------------------------- */
-int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float wd, float grad_scale,
-                 int nesterov, void* stream);
-int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-                   float wd, float bias1, float bias2, float grad_scale, void* stream);
-int sgb_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream);
+/* Hyper-parameters live in DEVICE memory (so a CUDA-graph-captured step follows the host-side LR schedule):
+ *   sgd   hp[5] = {lr, momentum, weight_decay, grad_scale, nesterov}
+ *   adamw hp[8] = {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}   (torch.optim semantics) */
+int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, const float* hp, void* stream);
+int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp, void* stream);
+/* ema = ema * (*decay) + (1 - *decay) * p   (training/utils/ema.py:126-142) */
+int sgb_ema_update(float* ema, const float* p, int64_t n, const float* decay, void* stream);
 
 #ifdef __cplusplus
 }

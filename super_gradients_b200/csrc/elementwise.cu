@@ -665,8 +665,12 @@ __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, int N, int HW, i
 }
 
 // ---------------------------------------------------------------------------------------------- optimizers
-__global__ void sgd_kernel(float* p, const float* g, float* mom, int64_t n, float lr, float mu, float wd, float gs,
-                           int nesterov) {
+// Hyper-parameters are read from DEVICE memory so that a CUDA-graph-captured step follows the host's LR schedule.
+// sgd   hp: [lr, momentum, weight_decay, grad_scale, nesterov]
+// adamw hp: [lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale]
+__global__ void sgd_kernel(float* p, const float* g, float* mom, int64_t n, const float* hp) {
+  const float lr = hp[0], mu = hp[1], wd = hp[2], gs = hp[3];
+  const bool nesterov = hp[4] != 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gr = g[i] * gs + wd * p[i];
     float d = gr;
@@ -678,8 +682,8 @@ __global__ void sgd_kernel(float* p, const float* g, float* mom, int64_t n, floa
     p[i] -= lr * d;
   }
 }
-__global__ void adamw_kernel(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-                             float eps, float wd, float bc1, float bc2, float gs) {
+__global__ void adamw_kernel(float* p, const float* g, float* m, float* v, int64_t n, const float* hp) {
+  const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], gs = hp[7];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gr = g[i] * gs;
     float pi = p[i] * (1.f - lr * wd);
@@ -691,7 +695,8 @@ __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, int64
     p[i] = pi - (lr / bc1) * mi / denom;
   }
 }
-__global__ void ema_kernel(float* e, const float* p, int64_t n, float d) {
+__global__ void ema_kernel(float* e, const float* p, int64_t n, const float* decay) {
+  const float d = *decay;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     e[i] = e[i] * d + (1.f - d) * p[i];
 }
@@ -934,24 +939,20 @@ extern "C" int sgb_avgpool_bwd(const sgb_bf16* dy, int N, int HW, int C, sgb_bf1
   return SGB_OK;
 }
 
-extern "C" int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float momentum, float wd,
-                            float grad_scale, int nesterov, void* stream) {
-  SGB_REQUIRE(p && g && (momentum == 0.f || mom), "null pointer");
-  sgd_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, wd, grad_scale,
-                                                                     nesterov);
+extern "C" int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, const float* hp, void* stream) {
+  SGB_REQUIRE(p && g && mom && hp, "null pointer");
+  sgd_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, mom, n, hp);
   SGB_LAUNCH_CHECK("sgd_kernel");
   return SGB_OK;
 }
-extern "C" int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
-                              float eps, float wd, float bias1, float bias2, float grad_scale, void* stream) {
-  SGB_REQUIRE(p && g && m && v, "null pointer");
-  adamw_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bias1,
-                                                                       bias2, grad_scale);
+extern "C" int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp, void* stream) {
+  SGB_REQUIRE(p && g && m && v && hp, "null pointer");
+  adamw_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hp);
   SGB_LAUNCH_CHECK("adamw_kernel");
   return SGB_OK;
 }
-extern "C" int sgb_ema_update(float* ema, const float* p, int64_t n, float decay, void* stream) {
-  SGB_REQUIRE(ema && p, "null pointer");
+extern "C" int sgb_ema_update(float* ema, const float* p, int64_t n, const float* decay, void* stream) {
+  SGB_REQUIRE(ema && p && decay, "null pointer");
   ema_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(ema, p, n, decay);
   SGB_LAUNCH_CHECK("ema_kernel");
   return SGB_OK;

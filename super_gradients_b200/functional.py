@@ -26,6 +26,15 @@ __all__ = [
 ]
 
 
+_WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    """Invalidates every WeightCache.  The Trainer calls this after each optimizer step: its kernels update the flat
+    parameter buffer through raw pointers, which does not advance torch's per-tensor version counters."""
+    _WEIGHT_EPOCH[0] += 1
+
+
 class WeightCache:
     """bf16 KRSC / CRSK copies of an fp32 OIHW conv weight, refreshed when the parameter changes."""
 
@@ -35,11 +44,32 @@ class WeightCache:
         self.crsk = None
 
     def get(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, add_identity=False, extra_key=None):
-        key = (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key)
+        key = (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key, _WEIGHT_EPOCH[0])
         if key != self.key:
-            self.krsc, self.crsk = K.weight_prepare(w, scale=scale, add_identity=add_identity)
+            self.krsc, self.crsk = K.weight_prepare(w, scale=scale, add_identity=add_identity, out=(self.krsc, self.crsk))
             self.key = key
         return self.krsc, self.crsk
+
+
+def _mg(p):
+    """Flat-buffer gradient slot of a parameter (training/flat_state.py) or None under plain autograd."""
+    return getattr(p, "main_grad", None) if p is not None else None
+
+
+def _deliver(slot, grad):
+    """Adds `grad` into the parameter's flat gradient slot (returns None to autograd) or hands it to autograd."""
+    if grad is None or slot is None:
+        return grad
+    slot.add_(grad.reshape(slot.shape))
+    return None
+
+
+def _wgrad(x, dy, r, s, stride, pad, cin, slot):
+    dw = K.conv_wgrad(x, dy, r, s, stride, pad)
+    if slot is not None:
+        K.wgrad_to_oihw(dw, cin, out=slot, accumulate=True)
+        return None
+    return K.wgrad_to_oihw(dw, cin)
 
 
 def _chan_sum(dy: torch.Tensor) -> torch.Tensor:
@@ -92,6 +122,7 @@ class _ConvBnAct(torch.autograd.Function):
             cfg.num_batches_tracked += 1
         ctx.save_for_backward(x, y_raw, out, gamma, mean, rstd)
         ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_res = cfg, crsk, tuple(w.shape), residual is not None
+        ctx.slots = (_mg(w), _mg(gamma), _mg(beta))
         return out
 
     @staticmethod
@@ -99,12 +130,13 @@ class _ConvBnAct(torch.autograd.Function):
         x, y_raw, out, gamma, mean, rstd = ctx.saved_tensors
         cfg = ctx.cfg
         kout, cin, r, s = ctx.wshape
-        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res)
+        sw, sg, sb = ctx.slots
+        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res, dgamma=sg, dbeta=sb)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad)
-        dw = K.wgrad_to_oihw(K.conv_wgrad(x, dy, r, s, cfg.stride, cfg.pad), cin)
-        return dx, dw, dgamma, dbeta, dres, None
+        dw = _wgrad(x, dy, r, s, cfg.stride, cfg.pad, cin, sw)
+        return dx, dw, (None if sg is not None else dgamma), (None if sb is not None else dbeta), dres, None
 
 
 def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracked, *, stride, pad, eps, momentum, act, training, cache: WeightCache, residual=None):
@@ -134,6 +166,7 @@ class _ConvBias(torch.autograd.Function):
         y = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, shift=b, act=cfg.act)
         ctx.save_for_backward(x)
         ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_bias = cfg, crsk, tuple(w.shape), b is not None
+        ctx.slots = (_mg(w), _mg(b))
         return y
 
     @staticmethod
@@ -142,13 +175,9 @@ class _ConvBias(torch.autograd.Function):
         cfg = ctx.cfg
         kout, cin, r, s = ctx.wshape
         dy = K.as_nhwc(dy)
-        if K.nhwc_pitch(dy) % 8 != 0 or (kout % 8 != 0 and K.nhwc_pitch(dy) < ((kout + 7) // 8) * 8):
-            pad = K.empty_nhwc(dy.shape[0], kout, dy.shape[2], dy.shape[3], dy.device)
-            pad.copy_(dy)
-            dy = pad
         dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad) if ctx.needs_input_grad[0] else None
-        dw = K.wgrad_to_oihw(K.conv_wgrad(x, dy, r, s, cfg.stride, cfg.pad), cin)
-        db = _chan_sum(dy) if ctx.has_bias else None
+        dw = _wgrad(x, dy, r, s, cfg.stride, cfg.pad, cin, ctx.slots[0])
+        db = _deliver(ctx.slots[1], _chan_sum(dy)) if ctx.has_bias else None
         return dx, dw, db, None
 
 
@@ -185,6 +214,7 @@ class _QARepVGG(torch.autograd.Function):
         ctx.save_for_backward(x, y3, u, out, coef, g3, gp if gp is not None else g3, w1, bias1 if bias1 is not None else g3, alpha if alpha is not None else g3)
         ctx.cfg, ctx.c3, ctx.c1 = cfg, c3, c1
         ctx.flags = (bias1 is not None, alpha is not None, gp is not None, w3.shape[1])
+        ctx.slots = (_mg(w3), _mg(g3), _mg(b3), _mg(w1), _mg(bias1), _mg(alpha), _mg(gp), _mg(bp))
         return out
 
     @staticmethod
@@ -192,24 +222,30 @@ class _QARepVGG(torch.autograd.Function):
         x, y3, u, out, coef, g3, gp, w1, bias1, alpha = ctx.saved_tensors
         cfg = ctx.cfg
         has_bias, has_alpha, has_post, cin = ctx.flags
-        dy3, du, dg3, db3, dab, dgp, dbp = K.qarep_bwd(dout, out, y3, u, coef, g3, gp if has_post else None, cfg.eps, cfg.eps, cfg.act, cfg.use_post_bn)
+        sw3, sg3, sb3, sw1, sbias, salpha, sgp, sbp = ctx.slots
+        direct_bias = sbias if not has_alpha else None  # d(alpha*b1) == d(b1) when alpha is the constant 1
+        dy3, du, dg3, db3, dab, dgp, dbp = K.qarep_bwd(
+            dout, out, y3, u, coef, g3, gp if has_post else None, cfg.eps, cfg.eps, cfg.act, cfg.use_post_bn, acc=(sg3, sb3, direct_bias, sgp, sbp)
+        )
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1)
             K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=dx, accumulate=True)
-        dw3 = K.wgrad_to_oihw(K.conv_wgrad(x, dy3, 3, 3, cfg.stride, 1), cin)
-        dw1f = K.wgrad_to_oihw(K.conv_wgrad(x, du, 1, 1, cfg.stride, 0), cin)  # grad of the folded alpha*K1 + I
+        dw3 = _wgrad(x, dy3, 3, 3, cfg.stride, 1, cin, sw3)
         dalpha = None
         if has_alpha:
+            dw1f = K.wgrad_to_oihw(K.conv_wgrad(x, du, 1, 1, cfg.stride, 0), cin)  # grad of the folded alpha*K1 + I
             dalpha = (dw1f * w1).sum().reshape(1)
             if has_bias:
                 dalpha = dalpha + (dab * bias1).sum().reshape(1)
-            dw1 = dw1f * alpha
-            dbias1 = dab * alpha if has_bias else None
+            dw1 = _deliver(sw1, dw1f * alpha)
+            dbias1 = _deliver(sbias, dab * alpha) if has_bias else None
+            dalpha = _deliver(salpha, dalpha)
         else:
-            dw1 = dw1f
-            dbias1 = dab if has_bias else None
-        return dx, dw3, dg3, db3, dw1, dbias1, dalpha, (dgp if has_post else None), (dbp if has_post else None), None
+            dw1 = _wgrad(x, du, 1, 1, cfg.stride, 0, cin, sw1)
+            dbias1 = (None if sbias is not None else dab) if has_bias else None
+        ret = lambda slot, v: None if slot is not None else v  # noqa: E731
+        return dx, dw3, ret(sg3, dg3), ret(sb3, db3), dw1, dbias1, dalpha, (ret(sgp, dgp) if has_post else None), (ret(sbp, dbp) if has_post else None), None
 
 
 def qarepvgg_block(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
@@ -223,7 +259,7 @@ class _ConvT2x2(torch.autograd.Function):
     def forward(ctx, x, w, b, cache):
         x = K.as_nhwc(x)
         cin, cout = w.shape[0], w.shape[1]
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, _WEIGHT_EPOCH[0])
         if cache.get("key") != key:
             wd = w.detach()
             cache["w_up"] = wd.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous().to(torch.bfloat16)  # [(dh,dw,co)][ci]
@@ -232,6 +268,7 @@ class _ConvT2x2(torch.autograd.Function):
         y = K.convt2x2_fprop(x, cache["w_up"], b, cout)
         ctx.save_for_backward(x)
         ctx.w_dn, ctx.shape, ctx.has_bias = cache["w_dn"], (cin, cout), b is not None
+        ctx.slots = (_mg(w), _mg(b))
         return y
 
     @staticmethod
@@ -241,8 +278,8 @@ class _ConvT2x2(torch.autograd.Function):
         dy = K.as_nhwc(dy)
         dx = K.conv_fprop(dy, ctx.w_dn, cin, 2, 2, 2, 0) if ctx.needs_input_grad[0] else None
         dwk = K.conv_wgrad(dy, x, 2, 2, 2, 0)  # [ci][dh][dw][co]
-        dw = dwk.permute(0, 3, 1, 2).contiguous()
-        db = _chan_sum(dy) if ctx.has_bias else None
+        dw = _deliver(ctx.slots[0], dwk.permute(0, 3, 1, 2))
+        db = _deliver(ctx.slots[1], _chan_sum(dy)) if ctx.has_bias else None
         return dx, dw, db, None
 
 

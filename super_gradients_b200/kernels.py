@@ -14,6 +14,20 @@ from .lib import ACT_NONE, ACT_RELU, ACT_SILU  # noqa: F401
 
 STATS_REPL = 8  # replicas of the per-channel sum buffers (spreads fp64 atomics)
 
+# Optional per-launch timing (bench.py roofline pass): (name, start_event, end_event) on the launching stream.
+PROFILE_ON = [False]
+PROFILE = []
+
+
+def _timed(name, *args):
+    if not PROFILE_ON[0]:
+        return L.call(name, *args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    L.call(name, *args)
+    b.record()
+    PROFILE.append((name, a, b))
+
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU}
 
 
@@ -124,7 +138,7 @@ def conv_fprop(x, w_krsc, K, R, S, stride, pad, *, scale=None, shift=None, resid
     ep.out_f32 = 1 if out_f32 else 0
     if residual is not None and nhwc_pitch(residual) != d.y_pitch:
         raise L.SgbError("residual must share the output's channel pitch")
-    L.call("sgb_conv_fprop", ctypes.byref(d), _ptr(x), _ptr(w_krsc), _ptr(out), ctypes.byref(ep), _stream())
+    _timed("sgb_conv_fprop", ctypes.byref(d), _ptr(x), _ptr(w_krsc), _ptr(out), ctypes.byref(ep), _stream())
     return out
 
 
@@ -139,7 +153,7 @@ def conv_dgrad(dy, w_crsk, x_shape, R, S, stride, pad, out=None, accumulate=Fals
     d.stride, d.pad = stride, pad
     d.x_pitch, d.x_off = nhwc_pitch(out), 0
     d.y_pitch, d.y_off = nhwc_pitch(dy), 0
-    L.call("sgb_conv_dgrad", ctypes.byref(d), _ptr(dy), _ptr(w_crsk), _ptr(out), 1 if accumulate else 0, _stream())
+    _timed("sgb_conv_dgrad", ctypes.byref(d), _ptr(dy), _ptr(w_crsk), _ptr(out), 1 if accumulate else 0, _stream())
     return out
 
 
@@ -150,28 +164,31 @@ def conv_wgrad(x, dy, R, S, stride, pad, dw_krsc=None):
     if dw_krsc is None:
         dw_krsc = torch.zeros((K, R, S, c), dtype=torch.float32, device=x.device)
     d = conv_desc(x, K, R, S, stride, pad, dy, dy.shape[2], dy.shape[3])
-    L.call("sgb_conv_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw_krsc), _stream())
+    _timed("sgb_conv_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw_krsc), _stream())
     return dw_krsc
 
 
-def weight_prepare(w_oihw: torch.Tensor, c_pad=None, want_crsk=True, scale=None, add_identity=False):
-    """fp32 OIHW -> (bf16 KRSC [K,R,S,c_pad], bf16 CRSK [C,R,S,Kp] or None)."""
+def weight_prepare(w_oihw: torch.Tensor, c_pad=None, want_crsk=True, scale=None, add_identity=False, out=None):
+    """fp32 OIHW -> (bf16 KRSC [K,R,S,c_pad], bf16 CRSK [C,R,S,Kp] or None); `out` reuses a previous result's storage."""
     require_cuda(w_oihw, "weight")
     K, C, R, S = w_oihw.shape
     c_pad = c_pad or ((C + 7) // 8) * 8
     w = w_oihw.detach().contiguous().float()
-    krsc = torch.empty((K, R, S, c_pad), dtype=torch.bfloat16, device=w.device)
-    crsk = None
-    if want_crsk and c_pad == C:
-        crsk = torch.empty((C, R, S, ((K + 7) // 8) * 8), dtype=torch.bfloat16, device=w.device)
-    L.call("sgb_weight_prepare", _ptr(w), K, C, R, S, c_pad, _ptr(krsc), _ptr(crsk), _ptr(scale), 1 if add_identity else 0, _stream())
+    if out is not None and out[0] is not None and tuple(out[0].shape) == (K, R, S, c_pad):
+        krsc, crsk = out
+    else:
+        krsc = torch.empty((K, R, S, c_pad), dtype=torch.bfloat16, device=w.device)
+        crsk = None
+        if want_crsk and c_pad == C:
+            crsk = torch.empty((C, R, S, ((K + 7) // 8) * 8), dtype=torch.bfloat16, device=w.device)
+    _timed("sgb_weight_prepare", _ptr(w), K, C, R, S, c_pad, _ptr(krsc), _ptr(crsk), _ptr(scale), 1 if add_identity else 0, _stream())
     return krsc, crsk
 
 
-def wgrad_to_oihw(dw_krsc: torch.Tensor, C: int) -> torch.Tensor:
+def wgrad_to_oihw(dw_krsc: torch.Tensor, C: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
     K, R, S, cp = dw_krsc.shape
-    g = torch.empty((K, C, R, S), dtype=torch.float32, device=dw_krsc.device)
-    L.call("sgb_wgrad_to_oihw", _ptr(dw_krsc), K, C, R, S, cp, _ptr(g), 0, _stream())
+    g = out if out is not None else torch.empty((K, C, R, S), dtype=torch.float32, device=dw_krsc.device)
+    _timed("sgb_wgrad_to_oihw", _ptr(dw_krsc), K, C, R, S, cp, _ptr(g), 1 if accumulate else 0, _stream())
     return g
 
 
@@ -185,7 +202,7 @@ def convt2x2_fprop(x_small, w_up, bias, C_up):
     d.stride, d.pad = 2, 0
     d.x_pitch, d.x_off = nhwc_pitch(out), 0
     d.y_pitch, d.y_off = nhwc_pitch(x_small), 0
-    L.call("sgb_convt2x2_fprop", ctypes.byref(d), _ptr(x_small), _ptr(w_up), _ptr(bias), _ptr(out), _stream())
+    _timed("sgb_convt2x2_fprop", ctypes.byref(d), _ptr(x_small), _ptr(w_up), _ptr(bias), _ptr(out), _stream())
     return out
 
 
@@ -195,7 +212,7 @@ def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     n, c, h, w = x.shape
     x = x.contiguous().float()
     out = torch.empty((n, ((c + 7) // 8) * 8, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-    L.call("sgb_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, _ptr(out), out.shape[1], 0, _stream())
+    _timed("sgb_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, _ptr(out), out.shape[1], 0, _stream())
     return out
 
 
@@ -226,7 +243,7 @@ def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, 
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     rstd = torch.empty(c, dtype=torch.float32, device=x.device)
     d = bn_desc(x, y, eps, momentum, act, residual, stats.shape[0])
-    L.call("sgb_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _ptr(mean), _ptr(rstd), _stream())
+    _timed("sgb_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _ptr(mean), _ptr(rstd), _stream())
     return y, mean, rstd
 
 
@@ -238,8 +255,8 @@ def bn_act_infer(x, gamma, beta, running_mean, running_var, eps, act, residual=N
     return y
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False):
-    """Returns (dx, dresidual or None, dgamma, dbeta)."""
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None):
+    """Returns (dx, dresidual or None, dgamma, dbeta); dgamma / dbeta are accumulated into when given."""
     n, c, h, w = x.shape
     dy = as_nhwc(dy)
     d = bn_desc(x, y, eps, 0.0, act, None, 1)
@@ -248,7 +265,7 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False):
         if nhwc_pitch(dy) != d.y_pitch:
             raise L.SgbError("dy pitch mismatch")
     sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
-    L.call("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
+    _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
     dx = torch.empty_like(x, memory_format=torch.channels_last) if nhwc_pitch(x) == c else torch.zeros_like(x)
     d.x_pitch = nhwc_pitch(dx)
     # x and dx must share a pitch for the kernel: re-describe x if it is a slice
@@ -258,16 +275,18 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False):
     if want_residual_grad:
         dres = empty_nhwc(n, c, h, w, x.device)
         d.r_pitch = nhwc_pitch(dres)
-    dgamma = torch.zeros(c, dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros(c, dtype=torch.float32, device=x.device)
-    L.call("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
+    if dgamma is None:
+        dgamma = torch.zeros(c, dtype=torch.float32, device=x.device)
+    if dbeta is None:
+        dbeta = torch.zeros(c, dtype=torch.float32, device=x.device)
+    _timed("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
     return dx, dres, dgamma, dbeta
 
 
 def channel_stats(x) -> torch.Tensor:
     n, c, h, w = x.shape
     st = torch.zeros((1, 2, c), dtype=torch.float64, device=x.device)
-    L.call("sgb_channel_stats", _ptr(x), n * h * w, c, nhwc_pitch(x), 0, _ptr(st), _stream())
+    _timed("sgb_channel_stats", _ptr(x), n * h * w, c, nhwc_pitch(x), 0, _ptr(st), _stream())
     return st
 
 
@@ -290,25 +309,27 @@ def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp,
     out = empty_nhwc(n, c, h, w, y3.device)
     d = qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn)
     mom = torch.zeros((5, c), dtype=torch.float64, device=y3.device)
-    L.call("sgb_qarep_moments", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _stream())
+    _timed("sgb_qarep_moments", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _stream())
     coef = torch.empty((9, c), dtype=torch.float32, device=y3.device)
-    L.call("sgb_qarep_fwd", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _ptr(gamma3), _ptr(beta3), _ptr(bias1a), _ptr(gamma_p), _ptr(beta_p), _ptr(rm3), _ptr(rv3), _ptr(rmp), _ptr(rvp), _ptr(out), _ptr(coef), _stream())
+    _timed("sgb_qarep_fwd", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _ptr(gamma3), _ptr(beta3), _ptr(bias1a), _ptr(gamma_p), _ptr(beta_p), _ptr(rm3), _ptr(rv3), _ptr(rmp), _ptr(rvp), _ptr(out), _ptr(coef), _stream())
     return out, coef
 
 
-def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True):
-    """Returns dy3, du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p."""
+def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None):
+    """Returns dy3, du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p.  `acc` optionally supplies existing fp32 tensors
+    (dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p) to accumulate into (None entries are allocated)."""
     n, c, h, w = y3.shape
     dout = as_nhwc(dout)
     if nhwc_pitch(dout) != nhwc_pitch(out):
         dout = dout.contiguous(memory_format=torch.channels_last)
     d = qarep_desc(y3, u, out, eps3, eps_post, 0.0, act, use_post_bn)
     sums = torch.zeros((3, c), dtype=torch.float64, device=y3.device)
-    L.call("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
+    _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
     dy3, du = torch.empty_like(y3), torch.empty_like(u)
     z = lambda: torch.zeros(c, dtype=torch.float32, device=y3.device)  # noqa: E731
-    dg3, db3, dab, dgp, dbp = z(), z(), z(), z(), z()
-    L.call("sgb_qarep_bwd_apply", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
+    acc = acc or (None,) * 5
+    dg3, db3, dab, dgp, dbp = [a if a is not None else z() for a in acc]
+    _timed("sgb_qarep_bwd_apply", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
     return dy3, du, dg3, db3, dab, dgp, dbp
 
 
@@ -319,7 +340,7 @@ def maxpool_fwd(x, k, stride, pad, want_idx=True, out=None):
     if out is None:
         out = empty_nhwc(n, c, P, Q, x.device)
     idx = torch.empty((n, P, Q, c), dtype=torch.uint8, device=x.device) if want_idx else None
-    L.call("sgb_maxpool_fwd", _ptr(x), n, h, w, c, nhwc_pitch(x), 0, k, stride, pad, _ptr(out), P, Q, nhwc_pitch(out), 0, _ptr(idx), _stream())
+    _timed("sgb_maxpool_fwd", _ptr(x), n, h, w, c, nhwc_pitch(x), 0, k, stride, pad, _ptr(out), P, Q, nhwc_pitch(out), 0, _ptr(idx), _stream())
     return out, idx
 
 
@@ -327,7 +348,7 @@ def maxpool_bwd(dy, idx, x_shape, k, stride, pad):
     n, c, h, w = x_shape
     dy = as_nhwc(dy)
     dx = torch.zeros((n, h, w, c), dtype=torch.float32, device=dy.device)
-    L.call("sgb_maxpool_bwd", _ptr(dy), n, h, w, c, k, stride, pad, dy.shape[2], dy.shape[3], nhwc_pitch(dy), 0, _ptr(idx), _ptr(dx), _stream())
+    _timed("sgb_maxpool_bwd", _ptr(dy), n, h, w, c, k, stride, pad, dy.shape[2], dy.shape[3], nhwc_pitch(dy), 0, _ptr(idx), _ptr(dx), _stream())
     return dx.permute(0, 3, 1, 2)  # NCHW-shaped view of NHWC fp32 storage
 
 
@@ -335,7 +356,7 @@ def axpby(x1, a, x2=None, b=0.0, out=None):
     n, c, h, w = x1.shape
     if out is None:
         out = empty_nhwc(n, c, h, w, x1.device)
-    L.call("sgb_axpby", _ptr(x1), nhwc_pitch(x1), 0, float(a), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, float(b), _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
+    _timed("sgb_axpby", _ptr(x1), nhwc_pitch(x1), 0, float(a), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, float(b), _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
     return out
 
 
@@ -344,7 +365,7 @@ def scale_add(x1, a_dev, x2=None, out=None):
     n, c, h, w = x1.shape
     if out is None:
         out = empty_nhwc(n, c, h, w, x1.device)
-    L.call("sgb_scale_add", _ptr(x1), nhwc_pitch(x1), 0, _ptr(a_dev), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
+    _timed("sgb_scale_add", _ptr(x1), nhwc_pitch(x1), 0, _ptr(a_dev), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
     return out
 
 
@@ -352,7 +373,7 @@ def channel_dot(a, b) -> torch.Tensor:
     """fp64 [C]: sum over pixels of a*b."""
     n, c, h, w = a.shape
     out = torch.zeros(c, dtype=torch.float64, device=a.device)
-    L.call("sgb_channel_dot", _ptr(a), nhwc_pitch(a), 0, _ptr(b), nhwc_pitch(b), 0, n * h * w, c, _ptr(out), _stream())
+    _timed("sgb_channel_dot", _ptr(a), nhwc_pitch(a), 0, _ptr(b), nhwc_pitch(b), 0, n * h * w, c, _ptr(out), _stream())
     return out
 
 
@@ -383,12 +404,12 @@ def avgpool_bwd(dy, hw_shape):
 # ------------------------------------------------------------------------------------------------ head / loss / nms
 def dfl_decode(reg, cls, L_total, anchor_base, ncls, reg_max, stride, cell_offset, pred_bboxes, pred_scores, cls_logits=None, reg_distri=None):
     n, _, hf, wf = reg.shape
-    L.call("sgb_dfl_decode", _ptr(reg), nhwc_pitch(reg), _ptr(cls), nhwc_pitch(cls), n, hf, wf, L_total, anchor_base, ncls, reg_max, float(stride), float(cell_offset), _ptr(pred_bboxes), _ptr(pred_scores), _ptr(cls_logits), _ptr(reg_distri), _stream())
+    _timed("sgb_dfl_decode", _ptr(reg), nhwc_pitch(reg), _ptr(cls), nhwc_pitch(cls), n, hf, wf, L_total, anchor_base, ncls, reg_max, float(stride), float(cell_offset), _ptr(pred_bboxes), _ptr(pred_scores), _ptr(cls_logits), _ptr(reg_distri), _stream())
 
 
 def head_grad_scatter(grad, n, hw, L_total, anchor_base, dy):
     gC = grad.shape[-1]
-    L.call("sgb_head_grad_scatter", _ptr(grad), gC, n, hw, L_total, anchor_base, _ptr(dy), nhwc_pitch(dy), _stream())
+    _timed("sgb_head_grad_scatter", _ptr(grad), gC, n, hw, L_total, anchor_base, _ptr(dy), nhwc_pitch(dy), _stream())
 
 
 def loss_desc(B, Lc, ncls, reg_max, n_max, topk=13, alpha=1.0, beta=6.0, w_cls=1.0, w_iou=2.5, w_dfl=0.5, iou_type=0) -> L.LossDesc:
@@ -405,14 +426,14 @@ def tal_assign(d, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes
     asc = torch.empty((d.B, d.L), dtype=torch.float32, device=dev)
     nbytes = L.load().sgb_tal_workspace_bytes(ctypes.byref(d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    L.call("sgb_tal_assign", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(gt_boxes), _ptr(gt_labels), _ptr(gt_valid), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), _ptr(ws), nbytes, _stream())
+    _timed("sgb_tal_assign", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(gt_boxes), _ptr(gt_labels), _ptr(gt_valid), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), _ptr(ws), nbytes, _stream())
     return al, ab, asc
 
 
 def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
     gc = torch.empty_like(cls_logits) if want_grad else None
     gr = torch.empty_like(reg_distri) if want_grad else None
-    L.call("sgb_dfl_iou_loss_fwd_bwd", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), float(grad_scale), _ptr(gc), _ptr(gr), _stream())
+    _timed("sgb_dfl_iou_loss_fwd_bwd", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), float(grad_scale), _ptr(gc), _ptr(gr), _stream())
     out = torch.empty(4, dtype=torch.float32, device=cls_logits.device)
     L.call("sgb_loss_finalize", ctypes.byref(d), _ptr(sums), _ptr(out), _stream())
     return out, gc, gr
@@ -440,13 +461,15 @@ def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=T
 
 
 # ------------------------------------------------------------------------------------------------ optimizer
-def sgd_step(p, g, mom, lr, momentum, wd, grad_scale=1.0, nesterov=False):
-    L.call("sgb_sgd_step", _ptr(p), _ptr(g), _ptr(mom), p.numel(), float(lr), float(momentum), float(wd), float(grad_scale), int(nesterov), _stream())
+def sgd_step(p, g, mom, hp):
+    """hp: device float32 [5] = lr, momentum, weight_decay, grad_scale, nesterov."""
+    _timed("sgb_sgd_step", _ptr(p), _ptr(g), _ptr(mom), p.numel(), _ptr(hp), _stream())
 
 
-def adamw_step(p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0):
-    L.call("sgb_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps), float(wd), float(1 - b1**step), float(1 - b2**step), float(grad_scale), _stream())
+def adamw_step(p, g, m, v, hp):
+    """hp: device float32 [8] = lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale."""
+    _timed("sgb_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hp), _stream())
 
 
-def ema_update(ema, p, decay):
-    L.call("sgb_ema_update", _ptr(ema), _ptr(p), p.numel(), float(decay), _stream())
+def ema_update(ema, p, decay_dev):
+    _timed("sgb_ema_update", _ptr(ema), _ptr(p), p.numel(), _ptr(decay_dev), _stream())

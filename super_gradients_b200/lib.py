@@ -141,12 +141,16 @@ _SIGNATURES = {
     "sgb_head_grad_scatter": (c_int, [P, _I, _I, _I, _I, _I, P, _I, P]),
     "sgb_nms_workspace_bytes": (c_int64, [POINTER(NmsDesc)]),
     "sgb_batched_nms": (c_int, [POINTER(NmsDesc), P, P, P, P, P, P, _L, P]),
-    "sgb_sgd_step": (c_int, [P, P, P, _L, _F, _F, _F, _F, _I, P]),
-    "sgb_adamw_step": (c_int, [P, P, P, P, _L, _F, _F, _F, _F, _F, _F, _F, _F, P]),
-    "sgb_ema_update": (c_int, [P, P, _L, _F, P]),
+    "sgb_sgd_step": (c_int, [P, P, P, _L, P, P]),
+    "sgb_adamw_step": (c_int, [P, P, P, P, _L, P, P]),
+    "sgb_ema_update": (c_int, [P, P, _L, P, P]),
 }
 
 _lib = None
+
+# kernels launched by one call of each entry point (default 1); LAUNCHES[0] accumulates them (bench.py: gpu_launches)
+LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
+LAUNCHES = [0]
 
 
 def exported_names():
@@ -178,6 +182,7 @@ def check(rc, what=""):
 def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
+    LAUNCHES[0] += LAUNCH_COUNT.get(name, 1)
     if rc != 0:
         msg = lib.sgb_last_error()
         raise SgbError(f"{name} failed with code {rc}: {msg.decode() if msg else ''}")

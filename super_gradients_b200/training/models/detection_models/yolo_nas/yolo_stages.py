@@ -49,6 +49,7 @@ class _ScaledAdd(torch.autograd.Function):
 
         x, y = K.as_nhwc(x), K.as_nhwc(y)
         ctx.save_for_backward(x, alpha)
+        ctx.slot = getattr(alpha, "main_grad", None)
         return K.scale_add(x, alpha, y)
 
     @staticmethod
@@ -58,6 +59,9 @@ class _ScaledAdd(torch.autograd.Function):
         x, alpha = ctx.saved_tensors
         dy = K.as_nhwc(dy)
         dalpha = K.channel_dot(dy, x).sum().float().reshape(1)
+        if ctx.slot is not None:
+            ctx.slot.add_(dalpha)
+            dalpha = None
         return K.scale_add(dy, alpha), dy, dalpha
 
 

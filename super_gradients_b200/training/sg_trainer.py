@@ -1,0 +1,385 @@
+"""Trainer with the reference's entry points -- Trainer(experiment_name, ckpt_root_dir).train(model, training_params,
+train_loader, valid_loader) / .test() -- driving the sm_100a hot path (reference: training/sg_trainer/sg_trainer.py).
+
+What is kept: the per-batch order of SURVEY.md Appendix B (H2D -> forward+loss -> backward -> optimizer -> EMA -> LR
+step), named training_params of the reference recipes (max_epochs, initial_lr, lr_mode, cosine_final_lr_ratio,
+lr_warmup_steps, optimizer, optimizer_params, zero_weight_decay_on_bias_and_bn, ema, ema_params, batch_accumulate,
+loss, save_model, ...), the checkpoint dictionary keys, rank-0-only checkpointing.
+What is different by design: one flat fp32 parameter / gradient buffer (training/flat_state.py), bf16 activations
+without a GradScaler, two optimizer launches per step, ONE flat NCCL all-reduce of live gradients per step under
+torchrun, and (optionally) the whole step captured in a CUDA graph.
+Out of scope: hydra recipes, dataset classes, loggers, metrics bookkeeping, QAT/PTQ, KD.
+"""
+import math
+import os
+import time
+from typing import Any, Callable, Dict, Mapping, Optional
+
+import torch
+from torch import nn
+
+from .. import functional as SF
+from .. import kernels as K
+from ..common.factories import LossesFactory
+from .flat_state import FlatState
+
+DEFAULT_TRAINING_PARAMS = {
+    "max_epochs": 1,
+    "initial_lr": 0.1,
+    "lr_mode": "cosine",  # cosine | constant | step
+    "cosine_final_lr_ratio": 0.01,
+    "lr_updates": [],
+    "lr_decay_factor": 0.1,
+    "lr_warmup_steps": 0,
+    "warmup_initial_lr": None,
+    "optimizer": "SGD",
+    "optimizer_params": {},
+    "zero_weight_decay_on_bias_and_bn": False,
+    "loss": None,
+    "criterion_params": {},
+    "ema": False,
+    "ema_params": {"decay": 0.9999, "decay_type": "constant"},
+    "batch_accumulate": 1,
+    "mixed_precision": True,  # informational: the compute path is always bf16 operands / fp32 accumulation
+    "save_model": True,
+    "save_ckpt_epoch_list": [],
+    "run_validation_freq": 1,
+    "max_train_batches": None,
+    "max_valid_batches": None,
+    "cuda_graph": False,
+    "seed": 42,
+    "silent_mode": True,
+    "sync_bn": False,
+    "phase_callbacks": [],
+}
+
+# defaults merged under user optimizer_params (reference: training/params.py:84-90)
+OPTIMIZER_DEFAULTS = {"SGD": {"weight_decay": 1e-4, "momentum": 0.9}, "Adam": {"weight_decay": 1e-4}, "AdamW": {"weight_decay": 1e-2}}
+
+
+def cosine_lr(step: float, total_steps: float, initial_lr: float, final_lr_ratio: float) -> float:
+    """CosineLRScheduler.compute_learning_rate (training/utils/callbacks/callbacks.py:506-511)."""
+    lr = 0.5 * initial_lr * (1.0 + math.cos(step / (total_steps + 1) * math.pi))
+    return lr * (1 - final_lr_ratio) + initial_lr * final_lr_ratio
+
+
+def ema_decay(decay_type: str, decay: float, step: int, total_steps: int, beta: float = 15.0) -> float:
+    """training/utils/ema_decay_schedules.py:22-51 (constant / threshold / exp)."""
+    if decay_type == "constant":
+        return decay
+    if decay_type == "threshold":
+        return min(decay, (1 + step) / (10 + step))
+    if decay_type == "exp":
+        return decay * (1 - math.exp(-beta * step / max(total_steps, 1)))
+    raise ValueError(f"unknown ema decay_type {decay_type}")
+
+
+def is_distributed() -> bool:
+    return torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+
+
+def setup_device(device: Optional[str] = None):
+    """torchrun-launched jobs (LOCAL_RANK set) are data parallel over NCCL, one process per GPU
+    (reference: training/utils/distributed_training_utils.py:173-311, env:// rendezvous)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("super_gradients_b200 needs a CUDA device (sm_100a); there is no CPU execution path")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local_rank))
+    return torch.device("cuda", local_rank)
+
+
+class TrainStep:
+    """One optimisation step over a FlatState: zero grads -> forward -> loss -> backward -> (all-reduce) -> optimizer
+    (-> EMA).  The object owns every per-step device buffer, so the step can be captured in a CUDA graph."""
+
+    def __init__(self, model: nn.Module, criterion: Callable, optimizer: str, optimizer_params: Mapping[str, Any], zero_wd_on_bias_and_bn: bool, ema: bool = False, batch_accumulate: int = 1):
+        self.model, self.criterion = model, criterion
+        self.flat = FlatState(model, zero_wd_on_bias_and_bn)
+        self.device = self.flat.params.device
+        self.opt_name = optimizer
+        op = {**OPTIMIZER_DEFAULTS.get(optimizer, {}), **dict(optimizer_params)}
+        self.op = op
+        f = self.flat
+        if optimizer == "SGD":
+            self.state = [torch.zeros_like(f.params)]
+            self.hp_host = torch.zeros((2, 5), dtype=torch.float32).pin_memory()
+        elif optimizer in ("AdamW", "Adam"):
+            if optimizer == "Adam":
+                raise NotImplementedError("Adam (L2-coupled) is not implemented; use AdamW or SGD")
+            self.state = [torch.zeros_like(f.params), torch.zeros_like(f.params)]
+            self.hp_host = torch.zeros((2, 8), dtype=torch.float32).pin_memory()
+        else:
+            raise NotImplementedError(f"optimizer {optimizer} has no fused kernel (SGD, AdamW are implemented)")
+        self.hp = torch.zeros_like(self.hp_host, device=self.device)
+        self.ema_on = ema
+        if ema:
+            self.ema_params = f.params.clone()
+            self.ema_buffers = f.buffers.clone()
+            self.ema_decay_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.ema_decay = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.world = torch.distributed.get_world_size() if is_distributed() else 1
+        self.accumulate = batch_accumulate
+        self.opt_steps = 0
+        self.graph = None
+        self.static_in = None
+        self.static_out = None
+
+    # -------------------------------------------------------------------------------------------- host-side schedule
+    def set_hyper_params(self, lr: float, ema_decay_value: Optional[float] = None):
+        """Writes this step's LR (and Adam bias corrections) to the device; must precede run()."""
+        t = self.opt_steps + 1
+        gs = 1.0 / (self.world * self.accumulate)
+        wd = float(self.op.get("weight_decay", 0.0))
+        if self.opt_name == "SGD":
+            mu, nes = float(self.op.get("momentum", 0.0)), float(bool(self.op.get("nesterov", False)))
+            self.hp_host[0] = torch.tensor([lr, mu, wd, gs, nes])
+            self.hp_host[1] = torch.tensor([lr, mu, 0.0, gs, nes])
+        else:
+            b1, b2 = self.op.get("betas", (0.9, 0.999))
+            eps = float(self.op.get("eps", 1e-8))
+            row = [lr, b1, b2, eps, wd, 1 - b1**t, 1 - b2**t, gs]
+            self.hp_host[0] = torch.tensor(row)
+            row[4] = 0.0
+            self.hp_host[1] = torch.tensor(row)
+        self.hp.copy_(self.hp_host, non_blocking=True)
+        if self.ema_on and ema_decay_value is not None:
+            self.ema_decay_host[0] = ema_decay_value
+            self.ema_decay.copy_(self.ema_decay_host, non_blocking=True)
+
+    # -------------------------------------------------------------------------------------------- device-side step
+    def forward_backward(self, inputs, targets):
+        outputs = self.model(inputs)
+        out = self.criterion(outputs, targets)
+        loss, items = out if isinstance(out, tuple) else (out, out.detach().reshape(1))
+        loss.backward()
+        # parameters whose gradient arrived through plain autograd (e.g. views created outside a fused Function)
+        for _, p in self.flat.order:
+            if p.grad is not None:
+                p.main_grad.add_(p.grad)
+                p.grad = None
+        return loss.detach(), items
+
+    def optimizer_step(self):
+        f = self.flat
+        if self.world > 1:
+            f.all_reduce_grads(self.world)
+        nd = f.n_decay
+        ranges = [(0, nd, 0), (nd, f.n_live, 1)]
+        for a, b, row in ranges:
+            if b <= a:
+                continue
+            if self.opt_name == "SGD":
+                K.sgd_step(f.params[a:b], f.grads[a:b], self.state[0][a:b], self.hp[row])
+            else:
+                K.adamw_step(f.params[a:b], f.grads[a:b], self.state[0][a:b], self.state[1][a:b], self.hp[row])
+        if self.ema_on:
+            K.ema_update(self.ema_params, f.params, self.ema_decay)
+            if f.n_buf:
+                K.ema_update(self.ema_buffers, f.buffers, self.ema_decay)
+        f.zero_grad()
+        SF.bump_weight_epoch()
+
+    def _step_eager(self, inputs, targets, do_optimizer_step=True):
+        loss, items = self.forward_backward(inputs, targets)
+        if do_optimizer_step:
+            self.optimizer_step()
+        return loss, items
+
+    def run(self, inputs, targets, do_optimizer_step=True):
+        """inputs / targets: device tensors (targets may be any structure the criterion accepts).  With a captured
+        graph the tensors are copied into the static buffers first."""
+        if self.graph is not None:
+            if not do_optimizer_step:
+                raise RuntimeError("gradient accumulation is not supported together with cuda_graph")
+            self._copy_static(self.static_in, (inputs, targets))
+            self.graph.replay()
+            loss, items = self.static_out
+        else:
+            loss, items = self._step_eager(inputs, targets, do_optimizer_step)
+        if do_optimizer_step:
+            self.opt_steps += 1
+        return loss, items
+
+    @staticmethod
+    def _copy_static(dst, src):
+        if torch.is_tensor(dst):
+            dst.copy_(src, non_blocking=True)
+        else:
+            for d, s in zip(dst, src):
+                TrainStep._copy_static(d, s)
+
+    def capture(self, inputs, targets, warmup: int = 3):
+        """Captures the whole step in a CUDA graph (static shapes: pad the targets to a fixed n_max).  The LR is read
+        from device memory, so set_hyper_params() keeps working between replays."""
+        clone = lambda t: t.clone() if torch.is_tensor(t) else type(t)(clone(u) for u in t)  # noqa: E731
+        self.static_in = (clone(inputs), clone(targets))
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_eager(*self.static_in)
+                self.opt_steps += 1
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        SF.bump_weight_epoch()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.static_out = self._step_eager(*self.static_in)
+        self.graph = g
+        return g
+
+    # -------------------------------------------------------------------------------------------- EMA swap (validation)
+    def swap_ema(self):
+        if not self.ema_on:
+            return
+        for a, b in ((self.flat.params, self.ema_params), (self.flat.buffers, self.ema_buffers)):
+            tmp = a.clone()
+            a.copy_(b)
+            b.copy_(tmp)
+        SF.bump_weight_epoch()
+
+
+class Trainer:
+    def __init__(self, experiment_name: str, device: Optional[str] = None, multi_gpu=None, ckpt_root_dir: Optional[str] = None):
+        self.experiment_name = experiment_name
+        self.ckpt_root_dir = ckpt_root_dir or os.path.join(os.getcwd(), "checkpoints")
+        self.checkpoints_dir_path = os.path.join(self.ckpt_root_dir, experiment_name)
+        self.device = setup_device(device)
+        self.net: Optional[nn.Module] = None
+        self.step: Optional[TrainStep] = None
+        self.history: Dict[str, list] = {"train_loss": [], "valid_loss": [], "lr": []}
+
+    @property
+    def ddp_silent_mode(self) -> bool:
+        return is_distributed() and torch.distributed.get_rank() != 0
+
+    # ------------------------------------------------------------------------------------------------ LR schedule
+    def _lr_at(self, tp, global_step: int, steps_per_epoch: int) -> float:
+        lr0 = float(tp["initial_lr"])
+        warm = int(tp["lr_warmup_steps"])
+        if warm > 0 and global_step < warm:
+            start = tp["warmup_initial_lr"] if tp["warmup_initial_lr"] is not None else lr0 / (warm + 1)
+            return float(start + (lr0 - start) * global_step / warm)  # linear_batch_step warm-up
+        mode = tp["lr_mode"]
+        total = steps_per_epoch * int(tp["max_epochs"])
+        if mode in ("cosine", "CosineLRScheduler"):
+            return cosine_lr(max(0, global_step - warm), total - warm, lr0, float(tp["cosine_final_lr_ratio"]))
+        if mode in ("step", "StepLRScheduler"):
+            epoch = global_step // max(steps_per_epoch, 1)
+            return lr0 * float(tp["lr_decay_factor"]) ** sum(1 for e in tp["lr_updates"] if epoch >= e)
+        if mode in (None, "constant", "none"):
+            return lr0
+        raise NotImplementedError(f"lr_mode {mode}")
+
+    # ------------------------------------------------------------------------------------------------ train
+    def train(self, model: nn.Module, training_params: Mapping[str, Any], train_loader, valid_loader=None, test_loaders=None, additional_configs_to_log=None):
+        tp = {**DEFAULT_TRAINING_PARAMS, **dict(training_params or {})}
+        if tp["sync_bn"]:
+            raise NotImplementedError("sync_bn needs per-layer collectives; the data-parallel path uses ONE gradient all-reduce (SURVEY.md D4)")
+        self.net = model.to(self.device)
+        torch.manual_seed(int(tp["seed"]) + (torch.distributed.get_rank() if is_distributed() else 0))
+        criterion = tp["loss"]
+        if isinstance(criterion, (str, Mapping)):
+            criterion = LossesFactory().get({criterion: tp["criterion_params"]} if isinstance(criterion, str) else criterion)
+        if criterion is None:
+            raise ValueError("training_params['loss'] is required")
+        if isinstance(criterion, nn.Module):
+            criterion = criterion.to(self.device)
+        self.criterion = criterion
+        self.step = TrainStep(self.net, criterion, tp["optimizer"], tp["optimizer_params"], bool(tp["zero_weight_decay_on_bias_and_bn"]), ema=bool(tp["ema"]), batch_accumulate=int(tp["batch_accumulate"]))
+        steps_per_epoch = len(train_loader) if tp["max_train_batches"] is None else min(len(train_loader), int(tp["max_train_batches"]))
+        total_steps = steps_per_epoch * int(tp["max_epochs"])
+        ema_p = {**DEFAULT_TRAINING_PARAMS["ema_params"], **dict(tp["ema_params"] or {})}
+        acc = int(tp["batch_accumulate"])
+        best = None
+        t0 = time.time()
+        for epoch in range(int(tp["max_epochs"])):
+            self.net.train()
+            if hasattr(getattr(train_loader, "sampler", None), "set_epoch"):
+                train_loader.sampler.set_epoch(epoch)
+            running, nb = None, 0
+            for batch_idx, batch in enumerate(train_loader):
+                if batch_idx >= steps_per_epoch:
+                    break
+                inputs, targets = batch[0], batch[1]
+                inputs = inputs.to(self.device, non_blocking=True)
+                if torch.is_tensor(targets) and not (hasattr(criterion, "forward") and type(criterion).__name__ == "PPYoloELoss"):
+                    targets = targets.to(self.device, non_blocking=True)
+                gstep = epoch * steps_per_epoch + batch_idx
+                lr = self._lr_at(tp, gstep, steps_per_epoch)
+                do_step = (batch_idx + 1 + steps_per_epoch * epoch) % acc == 0
+                self.step.set_hyper_params(lr, ema_decay(ema_p["decay_type"], float(ema_p["decay"]), self.step.opt_steps + 1, total_steps, float(ema_p.get("beta", 15))) if tp["ema"] else None)
+                if tp["cuda_graph"] and self.step.graph is None and torch.is_tensor(targets) and targets.is_cuda:
+                    self.step.capture(inputs, targets)
+                loss, _items = self.step.run(inputs, targets, do_step)
+                running = loss if running is None else running + loss
+                nb += 1
+                self.history["lr"].append(lr)
+            train_loss = float(running / max(nb, 1)) if running is not None else float("nan")
+            self.history["train_loss"].append(train_loss)
+            metrics = {"train_loss": train_loss}
+            if valid_loader is not None and (epoch + 1) % int(tp["run_validation_freq"]) == 0:
+                self.step.swap_ema()  # validate / checkpoint the EMA weights (sg_trainer.py:1566-1569)
+                metrics["valid_loss"] = self._validate(valid_loader, tp)
+                self.history["valid_loss"].append(metrics["valid_loss"])
+                self.step.swap_ema()
+            if tp["save_model"] and not self.ddp_silent_mode:
+                watch = metrics.get("valid_loss", train_loss)
+                is_best = best is None or watch < best
+                best = watch if is_best else best
+                self._save_checkpoint(epoch, metrics, tp, is_best)
+            if not tp["silent_mode"] and not self.ddp_silent_mode:
+                print(f"[{self.experiment_name}] epoch {epoch} " + " ".join(f"{k}={v:.5f}" for k, v in metrics.items()) + f" ({time.time() - t0:.1f}s)")
+        return self.history
+
+    @torch.no_grad()
+    def _validate(self, loader, tp) -> float:
+        self.net.eval()
+        tot, n = 0.0, 0
+        for i, batch in enumerate(loader):
+            if tp["max_valid_batches"] is not None and i >= int(tp["max_valid_batches"]):
+                break
+            inputs, targets = batch[0].to(self.device), batch[1]
+            if torch.is_tensor(targets) and type(self.criterion).__name__ != "PPYoloELoss":
+                targets = targets.to(self.device)
+            out = self.criterion(self.net(inputs), targets)
+            loss = out[0] if isinstance(out, tuple) else out
+            tot += float(loss)
+            n += 1
+        self.net.train()
+        return tot / max(n, 1)
+
+    test = _validate
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def _state_dict(self, use_ema=False):
+        if use_ema and self.step.ema_on:
+            self.step.swap_ema()
+            sd = {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+            self.step.swap_ema()
+            return sd
+        return {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+
+    def _save_checkpoint(self, epoch: int, metrics: dict, tp, is_best: bool):
+        """Same dictionary keys as the reference (sg_trainer.py:649-739): net, acc, epoch, metrics, optimizer_state_dict,
+        ema_net, ..."""
+        os.makedirs(self.checkpoints_dir_path, exist_ok=True)
+        state = {
+            "net": self._state_dict(False),
+            "acc": metrics.get("valid_loss", metrics.get("train_loss")),
+            "epoch": epoch,
+            "metrics": metrics,
+            "packages": {"torch": torch.__version__},
+            "optimizer_state_dict": {"name": self.step.opt_name, "flat_order": [n for n, _ in self.step.flat.order], "state": [s.cpu() for s in self.step.state], "opt_steps": self.step.opt_steps},
+            "scaler_state_dict": None,
+            "processing_params": None,
+        }
+        if self.step.ema_on:
+            state["ema_net"] = self._state_dict(True)
+        torch.save(state, os.path.join(self.checkpoints_dir_path, "ckpt_latest.pth"))
+        if is_best:
+            torch.save(state, os.path.join(self.checkpoints_dir_path, "ckpt_best.pth"))
+        if epoch in tp["save_ckpt_epoch_list"]:
+            torch.save(state, os.path.join(self.checkpoints_dir_path, f"ckpt_epoch_{epoch}.pth"))

@@ -1,0 +1,122 @@
+"""Host-side logic on CPU: registries / factories / arch params, state-dict compatibility with the reference, target
+padding, LR / EMA schedules, flat parameter buffers and the world-size-2 gradient all-reduce (gloo)."""
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_and_factory_contract():
+    from super_gradients_b200.common.factories import DetectionModulesFactory, UnknownTypeException
+    from super_gradients_b200.common.registry import ALL_DETECTION_MODULES, ARCHITECTURES, LOSSES, register_model
+    from super_gradients_b200.training import models  # noqa: F401  (populates the registries)
+
+    for name in ("yolo_nas_s", "yolo_nas_m", "yolo_nas_l", "resnet18", "resnet18_cifar", "resnet50"):
+        assert name in ARCHITECTURES
+    for name in ("NStageBackbone", "YoloNASStem", "YoloNASStage", "YoloNASUpStage", "YoloNASDownStage", "YoloNASPANNeckWithC2", "NDFLHeads", "YoloNASDFLHead", "SPP"):
+        assert name in ALL_DETECTION_MODULES
+    assert "PPYoloELoss" in LOSSES and "ppyoloe_loss" in LOSSES
+    with pytest.raises(Exception):  # re-registering a different class under an existing name raises (registry.py:36-41)
+        register_model("yolo_nas_s")(type("Other", (), {}))
+    f = DetectionModulesFactory()
+    assert f.insert_module_param("SPP", "in_channels", 8) == {"SPP": {"in_channels": 8}}
+    with pytest.raises(UnknownTypeException):
+        f.get({"NoSuchModule": {}})
+
+
+@pytest.mark.parametrize("name,nc", [("yolo_nas_s", 80), ("yolo_nas_m", 80), ("yolo_nas_l", 80), ("resnet18_cifar", 10), ("resnet18", 1000), ("resnet50", 1000)])
+def test_state_dict_keys_match_reference(golden, name, nc):
+    """Reference checkpoints must load unchanged: same keys, shapes and parameter order."""
+    from super_gradients_b200.training import models
+
+    g = golden("state_keys")
+    torch.manual_seed(0)
+    m = models.get(name, num_classes=nc)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == g[name]
+    assert [k for k, _ in m.named_parameters()] == g[name + "/param_names"]
+    if name == "resnet18_cifar":  # identical RNG consumption => identical seeded initialisation
+        for k, v in m.state_dict().items():
+            if v.dtype.is_floating_point:
+                assert abs(float(v.double().sum()) - g[name + "/init_sums"][k]) < 1e-9, k
+
+
+def test_yolo_nas_s_live_parameter_count():
+    from super_gradients_b200.training import models
+    from super_gradients_b200.training.flat_state import FlatState
+
+    m = models.get("yolo_nas_s", num_classes=80)
+    fs = FlatState(m, zero_wd_on_bias_and_bn=True)
+    total = sum(p.numel() for p in m.parameters())
+    assert total == 19_053_888
+    assert abs(fs.n_live - 12.88e6) < 0.01e6
+    # parameters are views of the flat buffer, decay group first
+    name, p = fs.order[0]
+    assert p.data_ptr() == fs.params.data_ptr() and p.main_grad.data_ptr() == fs.grads.data_ptr()
+    assert all(not n.endswith(".bias") for n, _ in fs.order[:10])
+    assert m.backbone.stem.conv.branch_3x3.bn.running_mean.data_ptr() >= fs.buffers.data_ptr()
+
+
+def test_pad_targets_matches_oracle():
+    from oracle import sg_oracle as O
+    from super_gradients_b200.training.losses import pad_targets_host
+
+    t = torch.tensor([[2, 1, 30.0, 28.0, 24.0, 20.0], [0, 3, 40.0, 44.0, 18.0, 30.0], [2, 0, 20.0, 36.0, 30.0, 22.0], [0, 2, 0.0, 0.0, 0.0, 0.0]])
+    gc, gb, pm = O.pad_targets(t, 3, n_max=4)
+    b, l, v = pad_targets_host(t, 3, 4)
+    torch.testing.assert_close(b, gb)
+    assert torch.equal(l.long(), gc.squeeze(-1)) and torch.equal(v.float(), pm.squeeze(-1))
+    b, l, v = pad_targets_host(torch.zeros(0, 6), 2, 1)
+    assert b.shape == (2, 1, 4) and int(v.sum()) == 0
+
+
+def test_schedules_match_reference_formulas():
+    from super_gradients_b200.training.sg_trainer import cosine_lr, ema_decay
+
+    # CosineLRScheduler.compute_learning_rate (callbacks.py:506-511)
+    for step, total, lr0, r in [(0, 100, 0.1, 0.01), (37, 100, 0.1, 0.01), (100, 100, 2e-4, 0.1)]:
+        ref = 0.5 * lr0 * (1.0 + math.cos(step / (total + 1) * math.pi))
+        ref = ref * (1 - r) + lr0 * r
+        assert abs(cosine_lr(step, total, lr0, r) - ref) < 1e-12
+    assert ema_decay("threshold", 0.9997, 5, 100) == min(0.9997, 6 / 15)
+    assert ema_decay("constant", 0.99, 5, 100) == 0.99
+    assert abs(ema_decay("exp", 0.9999, 50, 100, 15.0) - 0.9999 * (1 - math.exp(-7.5))) < 1e-12
+
+
+_DDP_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from super_gradients_b200.training.flat_state import FlatState
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 2, 1))
+fs = FlatState(net, zero_wd_on_bias_and_bn=True)
+x = torch.full((2, 3, 5, 5), float(rank + 1))
+net(x).sum().backward()
+for _, p in fs.order:           # plain-autograd gradients are folded into the flat buffer
+    p.main_grad.add_(p.grad); p.grad = None
+local = fs.grads.clone()
+fs.all_reduce_grads(world)      # ONE flat all-reduce of the live gradients
+gathered = [torch.zeros_like(local) for _ in range(world)]
+dist.all_gather(gathered, local)
+assert torch.allclose(fs.grads, sum(gathered)), "flat all-reduce mismatch"
+assert fs.n_decay == 4 * 3 * 9 + 2 * 4 and fs.n_live == fs.n_decay + 4 + 4 + 4 + 2
+print("rank", rank, "ok")
+"""
+
+
+def test_flat_gradient_allreduce_world2_gloo(tmp_path):
+    script = tmp_path / "ddp.py"
+    script.write_text(_DDP_SCRIPT)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29511", str(script), ROOT],
+        capture_output=True, text=True, timeout=240, env=env,
+    )  # fmt: skip
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

@@ -345,7 +345,7 @@ def test_optimizer_kernels():
     for _ in range(3):
         pr.grad = gr.clone()
         opt.step()
-        k.sgd_step(pg, gr.to(DEV), mg, 0.1, 0.9, 1e-4)
+        k.sgd_step(pg, gr.to(DEV), mg, torch.tensor([0.1, 0.9, 1e-4, 1.0, 0.0], device=DEV))
     torch.testing.assert_close(pg.cpu(), pr.detach(), rtol=1e-5, atol=1e-6)
     pr = p.clone().requires_grad_(True)
     opt = torch.optim.AdamW([pr], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
@@ -353,5 +353,5 @@ def test_optimizer_kernels():
     for step in range(1, 4):
         pr.grad = gr.clone()
         opt.step()
-        k.adamw_step(pg, gr.to(DEV), m, v, 2e-4, 0.9, 0.999, 1e-8, 1e-5, step)
+        k.adamw_step(pg, gr.to(DEV), m, v, torch.tensor([2e-4, 0.9, 0.999, 1e-8, 1e-5, 1 - 0.9**step, 1 - 0.999**step, 1.0], device=DEV))
     torch.testing.assert_close(pg.cpu(), pr.detach(), rtol=1e-5, atol=1e-6)

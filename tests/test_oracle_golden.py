@@ -145,3 +145,28 @@ def test_decode_matches_tiny_model_outputs(golden):
     torch.testing.assert_close(ps, g["train_pred_scores"], rtol=1e-5, atol=1e-6)
     loss, items = O.ppyoloe_loss(raw, g["targets"], 4)
     torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-6)
+
+
+def test_tiny_yolo_nas_whole_graph(golden):
+    """oracle/yolo_nas_oracle.py reproduces the reference's whole-model train outputs, loss and gradients."""
+    from oracle.yolo_nas_oracle import YoloNASOracle, train_step
+
+    g = golden("tiny_yolo_nas")
+    state = {k: v.clone() for k, v in g["sd0"].items()}
+    (pb, ps), raw = YoloNASOracle(g["arch"], {k: v.clone() for k, v in state.items()}, training=True).forward(g["x"])
+    torch.testing.assert_close(raw[0], g["train_cls_logits"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(raw[1], g["train_reg_distri"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(pb, g["train_pred_bboxes"], rtol=1e-4, atol=1e-3)
+    live = [k for k in g["param_names"] if "rbr_reparam" not in k]
+    loss, items, grads = train_step(g["arch"], state, g["x"], g["targets"], 4, live)
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-4, atol=1e-6)
+    for k, v in g["grads"].items():
+        torch.testing.assert_close(grads[k], v, rtol=2e-3, atol=1e-5)
+    for k, (s, n) in g["grad_sums"].items():
+        assert abs(float(grads[k].double().norm()) - n) <= 2e-3 * n + 1e-6, k
+    # running statistics after the training forward, then eval-mode outputs
+    for k, v in g["running1"].items():
+        torch.testing.assert_close(state[k], v, rtol=1e-4, atol=1e-6)
+    (eb, es), _ = YoloNASOracle(g["arch"], {**g["sd0"], **g["running1"]}, training=False).forward(g["x"])
+    torch.testing.assert_close(es, g["eval_pred_scores"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(eb, g["eval_pred_bboxes"], rtol=1e-4, atol=1e-3)
