@@ -198,6 +198,20 @@ def test_maxpool_axpby_avgpool():
     torch.testing.assert_close(ap.float().cpu().flatten(1), a.mean((2, 3)).bfloat16().float(), rtol=2**-7, atol=1e-3)
 
 
+def test_scale_add_and_channel_dot():
+    k = K()
+    g = torch.Generator().manual_seed(15)
+    a = torch.randn(2, 24, 7, 5, generator=g).bfloat16().float()
+    b = torch.randn(2, 24, 7, 5, generator=g).bfloat16().float()
+    alpha = torch.tensor([0.75], device=DEV)
+    out = k.scale_add(to_nhwc_bf16(a), alpha, to_nhwc_bf16(b))
+    torch.testing.assert_close(out.float().cpu(), (0.75 * a + b).bfloat16().float(), rtol=2**-7, atol=1e-3)
+    out = k.scale_add(to_nhwc_bf16(a, pitch=48, off=8), alpha)
+    torch.testing.assert_close(out.float().cpu(), (0.75 * a).bfloat16().float(), rtol=2**-7, atol=1e-3)
+    d = k.channel_dot(to_nhwc_bf16(a), to_nhwc_bf16(b, pitch=32, off=8))
+    torch.testing.assert_close(d.cpu(), (a.double() * b.double()).sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+
+
 def _loss_inputs(G, case):
     g = G[case]
     B = g["cls_logits"].shape[0]

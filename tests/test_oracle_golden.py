@@ -133,7 +133,7 @@ def test_decode_matches_tiny_model_outputs(golden):
     g = golden("tiny_yolo_nas")
     B = g["x"].shape[0]
     # rebuild per-level NCHW head outputs from the raw [B, L, *] tensors
-    shapes, strides = [(8, 8), (4, 4), (2, 2)], (8, 16, 32)
+    shapes, strides = [(16, 16), (8, 8), (4, 4)], (8, 16, 32)
     regs, clss, a0 = [], [], 0
     for h, w in shapes:
         n = h * w
