@@ -10,6 +10,7 @@
 //   src/super_gradients/modules/qarepvgg_block.py:184-204, modules/conv_bn_act_block.py:92-93,
 //   training/models/classification_models/resnet.py:26-84 (see include/sgb200.h).
 #include "common.cuh"
+#include "conv_sm100.h"
 
 namespace {
 
@@ -467,6 +468,20 @@ extern "C" int sgb_conv_fprop(const SgbConvDesc* d, const sgb_bf16* x, const sgb
                               const SgbEpilogue* ep, void* stream) {
   if (int rc = check_desc(d)) return rc;
   SGB_REQUIRE(x && w && y, "null pointer");
+  if (!(ep && ep->out_f32)) {
+    sm100::Problem q{};
+    q.a = x + d->x_off; q.N = d->N; q.H = d->H; q.W = d->W; q.C = d->C; q.a_pitch = d->x_pitch;
+    q.b = w; q.b_rows = d->K; q.b_cols = d->R * d->S * d->C; q.b_cols_per_tap = d->C;
+    q.R = d->R; q.S = d->S; q.stride = d->stride; q.pad = d->pad; q.P = d->P; q.Q = d->Q; q.flip = 0;
+    q.y = y; q.y_pitch = d->y_pitch; q.y_off = d->y_off;
+    if (ep) {
+      q.scale = ep->scale; q.shift = ep->shift; q.residual = ep->residual; q.stats = ep->stats;
+      q.stats_repl = ep->stats_repl > 0 ? ep->stats_repl : 1; q.act = ep->act;
+    } else {
+      q.stats_repl = 1;
+    }
+    if (d->pad == d->R / 2 && sm100::supported(q)) return sm100::launch(q, (cudaStream_t)stream);
+  }
   IGemmParams p{};
   p.A = reinterpret_cast<const bf16*>(x);
   p.B = reinterpret_cast<const bf16*>(w);
@@ -561,6 +576,17 @@ extern "C" int sgb_conv_dgrad(const SgbConvDesc* d, const sgb_bf16* dy, const sg
   const int s = d->stride;
   SGB_REQUIRE(s == 1 || s == 2, "dgrad supports stride 1 or 2");
   const int Kp = ((d->K + 7) / 8) * 8;  // channels gathered per tap (w_crsk rows are padded with zeros to Kp)
+  if (s == 1 && d->pad == d->R / 2 && d->K % 16 == 0) {
+    // dgrad of a stride-1 "same" convolution == convolution of dy with the spatially flipped CRSK filter
+    sm100::Problem q{};
+    q.a = dy + d->y_off; q.N = d->N; q.H = d->P; q.W = d->Q; q.C = d->K; q.a_pitch = d->y_pitch;
+    q.b = w_crsk; q.b_rows = d->C; q.b_cols = d->R * d->S * Kp; q.b_cols_per_tap = Kp;
+    q.R = d->R; q.S = d->S; q.stride = 1; q.pad = d->R - 1 - d->pad; q.P = d->H; q.Q = d->W; q.flip = 1;
+    q.y = dx; q.y_pitch = d->x_pitch; q.y_off = d->x_off;
+    q.residual = accumulate ? dx : nullptr;
+    q.stats_repl = 1;
+    if (sm100::supported(q)) return sm100::launch(q, (cudaStream_t)stream);
+  }
   IGemmParams p{};
   p.A = reinterpret_cast<const bf16*>(dy);
   p.B = reinterpret_cast<const bf16*>(w_crsk);

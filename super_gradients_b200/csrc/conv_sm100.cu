@@ -1,0 +1,513 @@
+// Blackwell-native implicit-GEMM convolution: tcgen05.mma (UMMA, M=128) with the accumulator in TMEM, the A operand
+// streamed by TMA *im2col* descriptors straight from the NHWC activation tensor, the B operand (KRSC / CRSK filters)
+// by tiled TMA, a persistent warp-specialised CTA per SM:
+//     warp 0      TMA producer            (one elected lane)
+//     warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//     warps 2..5  epilogue: tcgen05.ld -> (scale, shift, residual, activation) -> bf16 -> global,
+//                 plus the per-channel sum / sum-of-squares needed by train-mode BatchNorm (butterfly transpose-reduce)
+// Two TMEM accumulators are ping-ponged so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Serves: fprop of every 1x1 / 3x3, stride 1 / 2 convolution with C % 16 == 0 and K % 8 == 0, and dgrad of the
+// stride-1 ones (a convolution of dy with the spatially flipped CRSK filter).  Everything else (3-channel stems, 7x7,
+// strided dgrad, wgrad, ragged channel counts) stays on the generic kernels in conv_mma.cu.
+//
+// Reference arithmetic replaced: nn.Conv2d forward / input-gradient as used by modules/qarepvgg_block.py:184-204,
+// modules/conv_bn_act_block.py:92-93, training/models/classification_models/resnet.py:53-84.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "conv_sm100.h"
+
+namespace sm100 {
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr int MAX_STAGES = 8;
+
+struct Params {
+  int M;            // output pixels (GEMM rows)
+  int N;            // output channels (GEMM cols)
+  int C;            // channels per tap of the gathered tensor
+  int R, S;         // taps
+  int KC;           // channels per TMA box (16 / 32 / 64)
+  int BN;           // N tile (multiple of 16, <= 256)
+  int stages;
+  int P, Q;         // output spatial size (rows -> (n, p, q))
+  int stride, pad;  // traversal stride, lower padding of the gather
+  int flip;         // 1: B columns are visited with spatially flipped taps (dgrad)
+  int b_cols_per_tap;
+  long long y_pitch;  // elements
+  int y_off;
+  bf16* y;
+  const float* scale;
+  const float* shift;
+  const bf16* residual;
+  double* stats;
+  int stats_repl;
+  int act;
+  int tmem_cols;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of KC bf16, 8-row swizzle atoms.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int kc) {
+  const uint32_t layout = kc == 64 ? 2u : (kc == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+  const uint32_t sbo = (uint32_t)(8 * kc * 2) >> 4;             // bytes between 8-row groups, in 16 B units
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;          // leading byte offset (ignored for swizzled K-major), canonical value 1
+  d |= (uint64_t)(sbo & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// 32 rows x 16 columns held one row per lane -> column sums; lanes 2j, 2j+1 end with the sum of column col_of_lane().
+__device__ __forceinline__ float butterfly_colsum(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float send = b16 ? v[i] : v[i + 8];
+    float keep = b16 ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = b8 ? w8[i] : w8[i + 4];
+    float keep = b8 ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = b4 ? w4[i] : w4[i + 2];
+    float keep = b4 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float send = b2 ? w2[0] : w2[1];
+  float keep = b2 ? w2[1] : w2[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return r + __shfl_xor_sync(0xffffffffu, r, 1);
+}
+__device__ __forceinline__ int col_of_lane(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = p.BN * p.KC * 2;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  // control block after the stages
+  const uint32_t ctrl = smem_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return ctrl + 8u * s; };
+  auto empty_bar = [&](int s) { return ctrl + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return ctrl + 8u * (2 * MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return ctrl + 8u * (2 * MAX_STAGES + 2 + b); };
+  const uint32_t tmem_slot = ctrl + 8u * (2 * MAX_STAGES + 4);
+  float* s_stats = reinterpret_cast<float*>(smem_raw + (ctrl - smem_u32(smem_raw)) + 8u * (2 * MAX_STAGES + 4) + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.BN - 1) / p.BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int chunks = p.C / p.KC;
+  const int k_iters = p.R * p.S * chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) s_stats[i] = 0.f;
+  if (warp == 1) tcgen05_alloc(tmem_slot, p.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================================================================== TMA producer
+    if (elect_one()) {
+      int it = 0;
+      const int pq = p.P * p.Q;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int m0 = mt * BLOCK_M;
+        const int n_img = m0 / pq;
+        const int rem = m0 - n_img * pq;
+        const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+        const int w0 = q0 * p.stride - p.pad, h0 = p0 * p.stride - p.pad;
+        for (int tap = 0; tap < p.R * p.S; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          const int btap = p.flip ? (p.R * p.S - 1 - tap) : tap;
+          for (int ck = 0; ck < chunks; ++ck, ++it) {
+            const int stg = it % p.stages;
+            const uint32_t par = ((it / p.stages) & 1) ^ 1;
+            mbar_wait(empty_bar(stg), par);
+            const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
+            mbar_expect_tx(full_bar(stg), a_bytes + b_bytes);
+            tma_load_im2col_4d(sa, &map_a, full_bar(stg), ck * p.KC, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+            tma_load_2d(sb, &map_b, full_bar(stg), btap * p.b_cols_per_tap + ck * p.KC, nt * p.BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      const uint32_t apar = ((tcount >> 1) & 1) ^ 1;
+      mbar_wait(tempty_bar(ab), apar);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.BN);
+      for (int k = 0; k < k_iters; ++k, ++it) {
+        const int stg = it % p.stages;
+        const uint32_t par = (it / p.stages) & 1;
+        mbar_wait(full_bar(stg), par);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
+          const uint64_t da = make_smem_desc(sa, p.KC), db = make_smem_desc(sb, p.KC);
+          for (int j = 0; j < p.KC / 16; ++j) {
+            // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (k | j) != 0);
+          }
+          umma_commit(empty_bar(stg));
+          if (k == k_iters - 1) umma_commit(tfull_bar(ab));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================================== epilogue
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int ab = tcount & 1;
+      const uint32_t apar = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(ab), apar);
+      tcgen05_fence_after();
+      const int row = quarter * 32 + lane;
+      const long long m = (long long)mt * BLOCK_M + row;
+      const bool row_ok = m < p.M;
+      const int n0 = nt * p.BN;
+      bf16* yrow = p.y + m * p.y_pitch + p.y_off;
+      const bf16* rrow = p.residual ? p.residual + m * p.y_pitch + p.y_off : nullptr;
+      const int ncols = min(p.BN, p.N - n0);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * p.BN + c0), v);
+        const int nvalid = min(16, ncols - c0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = n0 + c0 + i;
+          float x = v[i];
+          if (i < nvalid) {
+            if (p.scale) x *= p.scale[col];
+            if (p.shift) x += p.shift[col];
+          }
+          v[i] = x;
+        }
+        if (rrow && row_ok) {
+          if (nvalid == 16) {
+            uint4 r0 = *reinterpret_cast<const uint4*>(rrow + n0 + c0), r1 = *reinterpret_cast<const uint4*>(rrow + n0 + c0 + 8);
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+              v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
+            }
+          } else {
+            for (int i = 0; i < nvalid; ++i) v[i] += __bfloat162float(rrow[n0 + c0 + i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = bf16_round(apply_act(v[i], p.act));
+        if (row_ok) {
+          if (nvalid == 16) {
+            uint4 o0, o1;
+            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+            }
+            *reinterpret_cast<uint4*>(yrow + n0 + c0) = o0;
+            *reinterpret_cast<uint4*>(yrow + n0 + c0 + 8) = o1;
+          } else {
+            for (int i = 0; i < nvalid; ++i) yrow[n0 + c0 + i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+        if (p.stats) {
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (!row_ok || i >= nvalid) v[i] = 0.f;
+            sq[i] = v[i] * v[i];
+          }
+          float s1 = butterfly_colsum(v, lane), s2 = butterfly_colsum(sq, lane);
+          const int c = c0 + col_of_lane(lane);
+          if ((lane & 1) == 0 && c < ncols) {
+            atomicAdd(&s_stats[n0 + c], s1);
+            atomicAdd(&s_stats[p.N + n0 + c], s2);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(ab));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) tcgen05_dealloc(tmem_base, p.tmem_cols);
+  if (p.stats) {
+    double* st = p.stats + (long long)(blockIdx.x & (p.stats_repl - 1)) * 2 * p.N;
+    for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS)
+      if (s_stats[i] != 0.f) atomicAdd(&st[i], (double)s_stats[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_tiled = nullptr;
+static EncodeIm2colFn g_im2col = nullptr;
+static int g_num_sms = 0;
+
+static int init_driver() {
+  if (g_tiled && g_im2col) return SGB_OK;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    sgb_set_error("cuTensorMapEncodeTiled entry point not found");
+    return SGB_E_CUDA;
+  }
+  g_tiled = (EncodeTiledFn)fn;
+  fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    sgb_set_error("cuTensorMapEncodeIm2col entry point not found");
+    return SGB_E_CUDA;
+  }
+  g_im2col = (EncodeIm2colFn)fn;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  return SGB_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+bool enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGB_DISABLE_SM100");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool supported(const Problem& q) {
+  if (!enabled()) return false;
+  if (q.C % 16 != 0 || q.b_rows % 8 != 0) return false;
+  if (!((q.R == 1 && q.S == 1) || (q.R == 3 && q.S == 3))) return false;
+  if (q.stride != 1 && q.stride != 2) return false;
+  if (q.a_pitch % 8 != 0 || q.y_pitch % 8 != 0 || q.y_off % 8 != 0) return false;
+  if (((uintptr_t)q.a & 15) || ((uintptr_t)q.b & 15) || ((uintptr_t)q.y & 15)) return false;
+  if ((long long)q.N * q.P * q.Q >= (1ll << 31)) return false;
+  if (q.b_rows > 4096) return false;  // shared-memory statistics buffer
+  return true;
+}
+
+int launch(const Problem& q, cudaStream_t st) {
+  if (int rc = init_driver()) return rc;
+  Params p{};
+  p.M = q.N * q.P * q.Q;
+  p.N = q.b_rows;
+  p.C = q.C;
+  p.R = q.R;
+  p.S = q.S;
+  p.KC = q.C % 64 == 0 ? 64 : (q.C % 32 == 0 ? 32 : 16);
+  // N tile: whole N when it fits one accumulator, else the divisor-friendly size with least padding
+  int bn;
+  if (p.N <= 256) {
+    bn = ((p.N + 15) / 16) * 16;
+  } else {
+    bn = 256;
+    int best_waste = ((p.N + 255) / 256) * 256 - p.N;
+    for (int cand = 240; cand >= 128; cand -= 16) {
+      int waste = ((p.N + cand - 1) / cand) * cand - p.N;
+      if (waste < best_waste) { best_waste = waste; bn = cand; }
+    }
+  }
+  p.BN = bn;
+  p.P = q.P; p.Q = q.Q; p.stride = q.stride; p.pad = q.pad; p.flip = q.flip;
+  p.b_cols_per_tap = q.b_cols_per_tap;
+  p.y = (bf16*)q.y; p.y_pitch = q.y_pitch; p.y_off = q.y_off;
+  p.scale = q.scale; p.shift = q.shift; p.residual = (const bf16*)q.residual;
+  p.stats = q.stats; p.stats_repl = q.stats_repl > 0 ? q.stats_repl : 1; p.act = q.act;
+  int tc = 32;
+  while (tc < 2 * bn) tc <<= 1;
+  p.tmem_cols = tc;
+  const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = bn * p.KC * 2;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + 2 * p.N * 4 + 64;
+  const uint32_t budget = 200 * 1024;
+  int stages = (int)((budget - ctrl_bytes - 1024) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) { sgb_set_error("conv_sm100: tile does not fit shared memory"); return SGB_E_UNSUPPORTED; }
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + ctrl_bytes;
+
+  alignas(64) CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+    cuuint64_t strides[3] = {(cuuint64_t)q.a_pitch * 2, (cuuint64_t)q.W * q.a_pitch * 2, (cuuint64_t)q.H * q.W * q.a_pitch * 2};
+    int lower[2] = {-q.pad, -q.pad};
+    int upper[2] = {q.pad - (q.S - 1), q.pad - (q.R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)q.stride, (cuuint32_t)q.stride, 1};
+    CUresult r = g_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.a), dims, strides, lower, upper,
+                          (cuuint32_t)p.KC, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KC),
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      sgb_set_error("cuTensorMapEncodeIm2col failed with %d (C=%d W=%d H=%d N=%d pitch=%d pad=%d upper=%d,%d stride=%d KC=%d)", (int)r,
+                    q.C, q.W, q.H, q.N, q.a_pitch, q.pad, upper[0], upper[1], q.stride, p.KC);
+      return SGB_E_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)q.b_cols, (cuuint64_t)q.b_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)q.b_cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.KC, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_tiled(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q.b), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      sgb_set_error("cuTensorMapEncodeTiled(B) failed with %d (cols=%d rows=%d KC=%d BN=%d)", (int)r, q.b_cols, q.b_rows, p.KC, bn);
+      return SGB_E_CUDA;
+    }
+  }
+  static bool attr = false;
+  if (!attr) {
+    if (int rc = sgb_cuda_check(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                                "cudaFuncSetAttribute(conv_umma_kernel)"))
+      return rc;
+    attr = true;
+  }
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + bn - 1) / bn;
+  int grid = m_tiles * n_tiles;
+  if (grid > g_num_sms) grid = g_num_sms;
+  conv_umma_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, p);
+  return sgb_cuda_check(cudaGetLastError(), "conv_umma_kernel");
+}
+
+}  // namespace sm100

@@ -1,0 +1,28 @@
+// Interface between the C-ABI dispatch (conv_mma.cu) and the tcgen05 / TMA implicit-GEMM kernel (conv_sm100.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sm100 {
+
+struct Problem {
+  // gathered tensor (NHWC bf16, channel slice): N x H x W x C with channel pitch a_pitch (elements)
+  const void* a;
+  int N, H, W, C, a_pitch;
+  // B matrix: b_rows = GEMM N (output channels of this GEMM), b_cols = taps * b_cols_per_tap, K-major bf16
+  const void* b;
+  int b_rows, b_cols, b_cols_per_tap;
+  int R, S, stride, pad, P, Q, flip;
+  void* y;
+  int y_pitch, y_off;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  double* stats;
+  int stats_repl, act;
+};
+
+bool enabled();
+bool supported(const Problem& q);
+int launch(const Problem& q, cudaStream_t st);
+
+}  // namespace sm100

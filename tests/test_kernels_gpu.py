@@ -56,6 +56,14 @@ CONV_CASES = [
     (4, 64, 10, 10, 68, 1, 1, 0),
     (2, 192, 5, 5, 80, 1, 1, 0),
     (2, 16, 6, 6, 16, 2, 2, 0),
+    # multi-tile persistent loops of the tcgen05 kernel (tiles > SM count, both TMEM accumulators in flight)
+    (16, 32, 48, 48, 32, 3, 1, 1),
+    (8, 64, 40, 40, 64, 3, 1, 1),
+    (6, 96, 40, 40, 96, 3, 1, 1),
+    (8, 48, 40, 40, 96, 3, 2, 1),
+    (4, 192, 20, 20, 384, 3, 2, 1),
+    (2, 384, 20, 20, 768, 1, 1, 0),
+    (6, 64, 31, 29, 128, 1, 1, 0),
 ]
 
 
