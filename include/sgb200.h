@@ -62,6 +62,9 @@ const char* sgb_last_error(void);
 int sgb_version(void);
 /* 0 if the current device is sm_100 and the library was built for it. */
 int sgb_check_device(void);
+/* Number of tcgen05/TMA convolution launches issued by this process so far (evidence that the Blackwell-native path,
+ * not the generic mma.sync kernel, served a call). */
+int64_t sgb_sm100_launches(void);
 
 /* ---- convolution family (rows C1-C5, C8, C10 of SURVEY.md section 8a) --------------------------------------
  * replaces nn.Conv2d forward in modules/qarepvgg_block.py:184-204, modules/conv_bn_act_block.py:92-93,

@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "conv_sm100.h"
 
 static thread_local char g_err[512] = "";
 
@@ -32,3 +33,5 @@ extern "C" int sgb_check_device(void) {
   }
   return SGB_OK;
 }
+
+extern "C" int64_t sgb_sm100_launches(void) { return (int64_t)sm100::launch_count(); }

@@ -50,6 +50,7 @@ struct Params {
   int stats_repl;
   int act;
   int tmem_cols;
+  int dbg;  // SGB_DEBUG_SKIP bit mask (perf experiments only): 1 no stores, 2 no stats, 4 no A loads
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -179,6 +180,7 @@ __device__ __forceinline__ int col_of_lane(int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+template <int NCH, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -241,8 +243,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t par = ((it / p.stages) & 1) ^ 1;
             mbar_wait(empty_bar(stg), par);
             const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
-            mbar_expect_tx(full_bar(stg), a_bytes + b_bytes);
-            tma_load_im2col_4d(sa, &map_a, full_bar(stg), ck * p.KC, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+            mbar_expect_tx(full_bar(stg), ((p.dbg & 4) ? 0u : a_bytes) + b_bytes);
+            if (!(p.dbg & 4)) tma_load_im2col_4d(sa, &map_a, full_bar(stg), ck * p.KC, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             tma_load_2d(sb, &map_b, full_bar(stg), btap * p.b_cols_per_tap + ck * p.KC, nt * p.BN);
           }
         }
@@ -279,84 +281,159 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // ===================================================================================== epilogue
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the ones this warp may read
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int row = quarter * 32 + lane;
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int ab = tcount & 1;
-      const uint32_t apar = (tcount >> 1) & 1;
-      mbar_wait(tfull_bar(ab), apar);
-      tcgen05_fence_after();
-      const int row = quarter * 32 + lane;
-      const long long m = (long long)mt * BLOCK_M + row;
-      const bool row_ok = m < p.M;
-      const int n0 = nt * p.BN;
-      bf16* yrow = p.y + m * p.y_pitch + p.y_off;
-      const bf16* rrow = p.residual ? p.residual + m * p.y_pitch + p.y_off : nullptr;
-      const int ncols = min(p.BN, p.N - n0);
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * p.BN + c0), v);
-        const int nvalid = min(16, ncols - c0);
+    if constexpr (NCH > 0) {
+      // ---- fast path: one N tile of NCH*16 columns, no scale / shift / residual / activation.  The per-channel
+      // statistics are accumulated per thread (row) in registers across ALL tiles of this CTA and reduced across the
+      // warp once at the end, so a tile costs ~3.5 instructions per element.
+      float a1[STATS ? NCH * 16 : 1], a2[STATS ? NCH * 16 : 1];
+      if constexpr (STATS) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = n0 + c0 + i;
-          float x = v[i];
-          if (i < nvalid) {
-            if (p.scale) x *= p.scale[col];
-            if (p.shift) x += p.shift[col];
+        for (int i = 0; i < NCH * 16; ++i) a1[i] = a2[i] = 0.f;
+      }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int ab = tcount & 1;
+        mbar_wait(tfull_bar(ab), (tcount >> 1) & 1);
+        tcgen05_fence_after();
+        const long long m = (long long)tile * BLOCK_M + row;
+        const bool row_ok = m < p.M;
+        bf16* yrow = p.y + m * p.y_pitch + p.y_off;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * (NCH * 16) + c * 16), v);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
           }
-          v[i] = x;
-        }
-        if (rrow && row_ok) {
-          if (nvalid == 16) {
-            uint4 r0 = *reinterpret_cast<const uint4*>(rrow + n0 + c0), r1 = *reinterpret_cast<const uint4*>(rrow + n0 + c0 + 8);
-            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
-              v[2 * i] += f0.x; v[2 * i + 1] += f0.y; v[8 + 2 * i] += f1.x; v[8 + 2 * i + 1] += f1.y;
+          if (row_ok) {
+            if (!(p.dbg & 1)) {
+              *reinterpret_cast<uint4*>(yrow + c * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(yrow + c * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-          } else {
-            for (int i = 0; i < nvalid; ++i) v[i] += __bfloat162float(rrow[n0 + c0 + i]);
-          }
-        }
+            if constexpr (STATS) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = bf16_round(apply_act(v[i], p.act));
-        if (row_ok) {
-          if (nvalid == 16) {
-            uint4 o0, o1;
-            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+              for (int i = 0; i < 8; ++i) {
+                const float lo = __uint_as_float(pk[i] << 16), hi = __uint_as_float(pk[i] & 0xffff0000u);
+                a1[c * 16 + 2 * i] += lo;
+                a2[c * 16 + 2 * i] = fmaf(lo, lo, a2[c * 16 + 2 * i]);
+                a1[c * 16 + 2 * i + 1] += hi;
+                a2[c * 16 + 2 * i + 1] = fmaf(hi, hi, a2[c * 16 + 2 * i + 1]);
+              }
             }
-            *reinterpret_cast<uint4*>(yrow + n0 + c0) = o0;
-            *reinterpret_cast<uint4*>(yrow + n0 + c0 + 8) = o1;
-          } else {
-            for (int i = 0; i < nvalid; ++i) yrow[n0 + c0 + i] = __float2bfloat16_rn(v[i]);
           }
         }
-        if (p.stats) {
-          float sq[16];
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(ab));
+      }
+      if constexpr (STATS) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float t1[16], t2[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            if (!row_ok || i >= nvalid) v[i] = 0.f;
-            sq[i] = v[i] * v[i];
+            t1[i] = a1[c * 16 + i];
+            t2[i] = a2[c * 16 + i];
           }
-          float s1 = butterfly_colsum(v, lane), s2 = butterfly_colsum(sq, lane);
-          const int c = c0 + col_of_lane(lane);
-          if ((lane & 1) == 0 && c < ncols) {
-            atomicAdd(&s_stats[n0 + c], s1);
-            atomicAdd(&s_stats[p.N + n0 + c], s2);
+          const float s1 = butterfly_colsum(t1, lane), s2 = butterfly_colsum(t2, lane);
+          if ((lane & 1) == 0) {
+            atomicAdd(&s_stats[c * 16 + col_of_lane(lane)], s1);
+            atomicAdd(&s_stats[p.N + c * 16 + col_of_lane(lane)], s2);
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(ab));
+    } else {
+      // ---- general path: ragged N, several N tiles, fused scale / shift / residual / activation
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int ab = tcount & 1;
+        mbar_wait(tfull_bar(ab), (tcount >> 1) & 1);
+        tcgen05_fence_after();
+        const long long m = (long long)mt * BLOCK_M + row;
+        const bool row_ok = m < p.M;
+        const int n0 = nt * p.BN;
+        bf16* yrow = p.y + m * p.y_pitch + p.y_off + n0;
+        const bf16* rrow = p.residual ? p.residual + m * p.y_pitch + p.y_off + n0 : nullptr;
+        const int ncols = min(p.BN, p.N - n0);
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_base + (uint32_t)(ab * p.BN + c0), v);
+          const bool full = c0 + 16 <= ncols;
+          if (p.scale) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (full || c0 + i < ncols) v[i] *= p.scale[n0 + c0 + i];
+          }
+          if (p.shift) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (full || c0 + i < ncols) v[i] += p.shift[n0 + c0 + i];
+          }
+          if (rrow && row_ok) {
+            if (full) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + c0), r1 = *reinterpret_cast<const uint4*>(rrow + c0 + 8);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[2 * i] += __uint_as_float(rr[i] << 16);
+                v[2 * i + 1] += __uint_as_float(rr[i] & 0xffff0000u);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < ncols) v[i] += __bfloat162float(rrow[c0 + i]);
+            }
+          }
+          if (p.act != SGB_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (row_ok && !(p.dbg & 1)) {
+            if (full) {
+              *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(yrow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (c0 + 2 * i < ncols) yrow[c0 + 2 * i] = __ushort_as_bfloat16((unsigned short)(pk[i] & 0xffffu));
+                if (c0 + 2 * i + 1 < ncols) yrow[c0 + 2 * i + 1] = __ushort_as_bfloat16((unsigned short)(pk[i] >> 16));
+              }
+            }
+          }
+          if (p.stats && !(p.dbg & 2)) {
+            float t1[16], t2[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok0 = row_ok && (full || c0 + 2 * i < ncols), ok1 = row_ok && (full || c0 + 2 * i + 1 < ncols);
+              const float lo = ok0 ? __uint_as_float(pk[i] << 16) : 0.f, hi = ok1 ? __uint_as_float(pk[i] & 0xffff0000u) : 0.f;
+              t1[2 * i] = lo;
+              t1[2 * i + 1] = hi;
+              t2[2 * i] = lo * lo;
+              t2[2 * i + 1] = hi * hi;
+            }
+            const float s1 = butterfly_colsum(t1, lane), s2 = butterfly_colsum(t2, lane);
+            const int c = c0 + col_of_lane(lane);
+            if ((lane & 1) == 0 && c < ncols) {
+              atomicAdd(&s_stats[n0 + c], s1);
+              atomicAdd(&s_stats[p.N + n0 + c], s2);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(ab));
+      }
     }
   }
   tcgen05_fence_before();
@@ -380,6 +457,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 static EncodeTiledFn g_tiled = nullptr;
 static EncodeIm2colFn g_im2col = nullptr;
 static int g_num_sms = 0;
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
 
 static int init_driver() {
   if (g_tiled && g_im2col) return SGB_OK;
@@ -454,6 +533,10 @@ int launch(const Problem& q, cudaStream_t st) {
   p.y = (bf16*)q.y; p.y_pitch = q.y_pitch; p.y_off = q.y_off;
   p.scale = q.scale; p.shift = q.shift; p.residual = (const bf16*)q.residual;
   p.stats = q.stats; p.stats_repl = q.stats_repl > 0 ? q.stats_repl : 1; p.act = q.act;
+  {
+    const char* e = getenv("SGB_DEBUG_SKIP");
+    p.dbg = e ? atoi(e) : 0;
+  }
   int tc = 32;
   while (tc < 2 * bn) tc <<= 1;
   p.tmem_cols = tc;
@@ -496,17 +579,36 @@ int launch(const Problem& q, cudaStream_t st) {
       return SGB_E_CUDA;
     }
   }
-  static bool attr = false;
-  if (!attr) {
-    if (int rc = sgb_cuda_check(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                                "cudaFuncSetAttribute(conv_umma_kernel)"))
-      return rc;
-    attr = true;
-  }
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + bn - 1) / bn;
   int grid = m_tiles * n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  conv_umma_kernel<<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, p);
+  const bool plain = !p.scale && !p.shift && !p.residual && p.act == SGB_ACT_NONE && n_tiles == 1 && p.N == bn && !(p.dbg & 2);
+  const int nch = plain ? bn / 16 : 0;
+  int rc = SGB_OK;
+#define SGB_LAUNCH_UMMA(NCH_, ST_)                                                                                   \
+  do {                                                                                                               \
+    static bool attr_ = false;                                                                                       \
+    if (!attr_) {                                                                                                    \
+      rc = sgb_cuda_check(cudaFuncSetAttribute(conv_umma_kernel<NCH_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               227 * 1024),                                                          \
+                          "cudaFuncSetAttribute(conv_umma_kernel)");                                                 \
+      attr_ = true;                                                                                                  \
+    }                                                                                                                \
+    if (rc == SGB_OK) conv_umma_kernel<NCH_, ST_><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, p);                  \
+  } while (0)
+  const bool stats = p.stats != nullptr;
+  if (nch == 2 && stats) SGB_LAUNCH_UMMA(2, true);
+  else if (nch == 2) SGB_LAUNCH_UMMA(2, false);
+  else if (nch == 3 && stats) SGB_LAUNCH_UMMA(3, true);
+  else if (nch == 3) SGB_LAUNCH_UMMA(3, false);
+  else if (nch == 4 && stats) SGB_LAUNCH_UMMA(4, true);
+  else if (nch == 4) SGB_LAUNCH_UMMA(4, false);
+  else if (nch == 6 && stats) SGB_LAUNCH_UMMA(6, true);
+  else if (nch == 6) SGB_LAUNCH_UMMA(6, false);
+  else SGB_LAUNCH_UMMA(0, false);
+#undef SGB_LAUNCH_UMMA
+  if (rc != SGB_OK) return rc;
+  ++g_launches;
   return sgb_cuda_check(cudaGetLastError(), "conv_umma_kernel");
 }
 

@@ -24,5 +24,6 @@ struct Problem {
 bool enabled();
 bool supported(const Problem& q);
 int launch(const Problem& q, cudaStream_t st);
+long long launch_count();
 
 }  // namespace sm100

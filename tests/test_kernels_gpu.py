@@ -83,7 +83,12 @@ def test_conv_fprop_dgrad_wgrad(case):
     assert rel_err(y32.cpu(), ref) < 5e-5
     # bf16 output: correctly rounded (<= 1 bf16 ulp of the oracle)
     stats = k.new_stats(kk, DEV)
+    from super_gradients_b200 import lib
+
+    n_sm100 = lib.load().sgb_sm100_launches()
     y = k.conv_fprop(xg, krsc, kk, r, r, stride, pad, stats=stats)
+    if c % 16 == 0 and kk % 8 == 0 and r in (1, 3) and pad == r // 2:
+        assert lib.load().sgb_sm100_launches() == n_sm100 + 1, "the tcgen05/TMA kernel should have served this shape"
     yc = y.float().cpu()
     assert ((yc - ref).abs() <= ref.abs() * 2**-7 + 1e-5).all()
     # fused per-channel statistics of the stored tensor
