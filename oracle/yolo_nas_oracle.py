@@ -49,7 +49,7 @@ class YoloNASOracle:
             else:
                 y = self._conv(self._conv(cur, bp + "cv1.", 3, 1), bp + "cv2.", 3, 1)
             alpha = self.p.get(bp + "alpha", 1.0)
-            outs.append(alpha * cur + y)
+            outs.append(O.q(alpha * cur + y))
         x1s = outs if concat_intermediates else [outs[-1]]
         x2 = self._conv(x, prefix + "conv2.", 1, 1)
         return self._conv(torch.cat((*x1s, x2), 1), prefix + "conv3.", 1, 1)
@@ -78,7 +78,7 @@ class YoloNASOracle:
         s2 = self._conv(s2, prefix + "reduce_skip2.", 1, 1)
         s2 = self._conv(s2, prefix + "downsample.", 3, 2)
         x_inter = self._conv(x, prefix + "conv.", 1, 1)
-        up = F.conv_transpose2d(x_inter, self.p[prefix + "upsample.weight"], self.p[prefix + "upsample.bias"], stride=2)
+        up = O.q(F.conv_transpose2d(x_inter, O.qw(self.p[prefix + "upsample.weight"]), self.p[prefix + "upsample.bias"], stride=2))
         x = self._conv(torch.cat([up, s1, s2], 1), prefix + "reduce_after_concat.", 1, 1)
         nb = a["num_blocks"]
         nb = max(round(nb * a.get("depth_mult", 1)), 1) if nb > 1 else nb
@@ -108,13 +108,13 @@ class YoloNASOracle:
             x = O.conv_bn_act(f, self.p, pre + "stem.seq.", 1, 0, "relu", self.training, self.eps, self.mom)
             c = O.conv_bn_act(x, self.p, pre + "cls_convs.0.seq.", 1, 1, "relu", self.training, self.eps, self.mom)
             r = O.conv_bn_act(x, self.p, pre + "reg_convs.0.seq.", 1, 1, "relu", self.training, self.eps, self.mom)
-            clss.append(F.conv2d(c, self.p[pre + "cls_pred.weight"], self.p[pre + "cls_pred.bias"]))
-            regs.append(F.conv2d(r, self.p[pre + "reg_pred.weight"], self.p[pre + "reg_pred.bias"]))
+            clss.append(O.q(F.conv2d(c, O.qw(self.p[pre + "cls_pred.weight"]), self.p[pre + "cls_pred.bias"])))
+            regs.append(O.q(F.conv2d(r, O.qw(self.p[pre + "reg_pred.weight"]), self.p[pre + "reg_pred.bias"])))
             strides.append(h["YoloNASDFLHead"]["stride"])
         return O.ndfl_decode(regs, clss, strides, reg_max=hd.get("reg_max", 16))
 
     def forward(self, x):
-        return self.heads(self.neck(self.backbone(x)))
+        return self.heads(self.neck(self.backbone(O.q(x))))
 
 
 def train_step(arch: dict, state: Dict[str, torch.Tensor], x: torch.Tensor, targets: torch.Tensor, num_classes: int, live: List[str]):

@@ -636,6 +636,15 @@ extern "C" int sgb_conv_wgrad(const SgbConvDesc* d, const sgb_bf16* x, const sgb
   SGB_REQUIRE(x && dy && dw, "null pointer");
   SGB_REQUIRE(d->y_pitch % 8 == 0 && d->y_off % 8 == 0, "dy pitch/offset must be multiples of 8");
   SGB_REQUIRE(d->K % 8 == 0 || d->y_pitch - d->y_off >= ((d->K + 7) / 8) * 8, "dy channels must be padded to 8");
+  {
+    sm100::WgradProblem q{};
+    q.x = x + d->x_off; q.dy = dy + d->y_off;
+    q.N = d->N; q.H = d->H; q.W = d->W; q.C = d->C; q.x_pitch = d->x_pitch;
+    q.K = d->K; q.y_pitch = d->y_pitch;
+    q.R = d->R; q.S = d->S; q.stride = d->stride; q.pad = d->pad; q.P = d->P; q.Q = d->Q;
+    q.dw = dw;
+    if (sm100::wgrad_supported(q)) return sm100::wgrad_launch(q, (cudaStream_t)stream);
+  }
   WgradParams p{};
   p.X = reinterpret_cast<const bf16*>(x);
   p.DY = reinterpret_cast<const bf16*>(dy);

@@ -447,6 +447,163 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad kernel
+// dW[ko][(r,s,c)] += sum_pix dy[pix][ko] * x[pix @ (r,s)][c]       (fp32 atomics over pixel splits)
+// GEMM view: M = out-channels (TMEM lanes), N = in-channels of one tap (TMEM columns, one column range per tap),
+// K = pixels.  Both operands are "MN-major": a TMA box of [PIX pixels][channels] IS the canonical MN-major swizzled
+// layout (each K index is one swizzled row), so dy and the im2col'd x stream straight from NHWC memory with no
+// transpose.  One CTA = (64 x 128 out-channels) x (group of taps) x (c tile) x (pixel range).
+struct WParams {
+  int K, C;            // out / in channels
+  int R, S, stride, pad, P, Q;
+  int npix;            // N*P*Q
+  int CB;              // in-channels per im2col box (32 or 64)
+  int c_tile;          // in-channels handled by one CTA
+  int tpg;             // taps per CTA (tap group)
+  int n_groups, n_ctiles, n_ktiles;
+  int pix_per_cta;     // multiple of WPIX
+  int stages;
+  int cpad;            // channel count of the KRSC output rows (x channels incl. padding)
+  float* dw;
+  int tmem_cols;
+};
+constexpr int WPIX = 64;  // pixels (GEMM K) per pipeline stage
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, int row_bytes, uint32_t lbo_bytes) {
+  // MN-major canonical layout: rows of row_bytes (= swizzle span: 128 / 64 / 32), 8-row groups along K
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  const uint32_t sbo = (uint32_t)(8 * row_bytes) >> 4;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(sbo & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 2 * WPIX * 128;                       // two 64-channel blocks of dy
+  const uint32_t b_box = WPIX * p.CB * 2;                        // one im2col box
+  const int boxes_per_tap = p.c_tile / p.CB;
+  const uint32_t b_bytes = (uint32_t)(p.tpg * boxes_per_tap) * b_box;
+  const uint32_t stage_bytes = a_bytes + b_bytes;                // multiples of 1024 by construction
+  const uint32_t ctrl = smem_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return ctrl + 8u * s; };
+  auto empty_bar = [&](int s) { return ctrl + 8u * (MAX_STAGES + s); };
+  const uint32_t done_bar = ctrl + 8u * (2 * MAX_STAGES);
+  const uint32_t tmem_slot = ctrl + 8u * (2 * MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // decode the CTA's work item
+  int w = blockIdx.x;
+  const int ktile = w % p.n_ktiles; w /= p.n_ktiles;
+  const int ctile = w % p.n_ctiles; w /= p.n_ctiles;
+  const int group = w % p.n_groups; w /= p.n_groups;
+  const int split = w;
+  const int tap0 = group * p.tpg;
+  const int ntaps = min(p.tpg, p.R * p.S - tap0);
+  const int pix0 = split * p.pix_per_cta;
+  const int pix1 = min(pix0 + p.pix_per_cta, p.npix);
+  const int n_iters = (pix1 - pix0 + WPIX - 1) / WPIX;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tcgen05_alloc(tmem_slot, p.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (n_iters > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const int pq = p.P * p.Q;
+        for (int it = 0; it < n_iters; ++it) {
+          const int stg = it % p.stages;
+          mbar_wait(empty_bar(stg), ((it / p.stages) & 1) ^ 1);
+          const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
+          mbar_expect_tx(full_bar(stg), a_bytes + (uint32_t)(ntaps * boxes_per_tap) * b_box);
+          const int pix = pix0 + it * WPIX;
+          tma_load_2d(sa, &map_dy, full_bar(stg), ktile * 128, pix);
+          tma_load_2d(sa + WPIX * 128, &map_dy, full_bar(stg), ktile * 128 + 64, pix);
+          const int n_img = pix / pq;
+          const int rem = pix - n_img * pq;
+          const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
+          const int w0 = q0 * p.stride - p.pad, h0 = p0 * p.stride - p.pad;
+          for (int t = 0; t < ntaps; ++t) {
+            const int tap = tap0 + t, r = tap / p.S, s = tap - r * p.S;
+            for (int bx = 0; bx < boxes_per_tap; ++bx)
+              tma_load_im2col_4d(sb + (uint32_t)(t * boxes_per_tap + bx) * b_box, &map_x, full_bar(stg),
+                                 ctile * p.c_tile + bx * p.CB, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // A and B are MN-major: a_major (bit 15) and b_major (bit 16) set; M = 128, N = CB
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.CB >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const int b_row_bytes = p.CB * 2;
+      for (int it = 0; it < n_iters; ++it) {
+        const int stg = it % p.stages;
+        mbar_wait(full_bar(stg), (it / p.stages) & 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
+          for (int t = 0; t < ntaps; ++t)
+            for (int bx = 0; bx < boxes_per_tap; ++bx) {
+              const uint32_t sbox = sb + (uint32_t)(t * boxes_per_tap + bx) * b_box;
+              const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.c_tile + bx * p.CB);
+#pragma unroll
+              for (int j = 0; j < WPIX / 16; ++j) {
+                const uint64_t da = make_smem_desc_mn(sa + j * 16 * 128, 128, WPIX * 128);
+                const uint64_t db = make_smem_desc_mn(sbox + j * 16 * b_row_bytes, b_row_bytes, 0);
+                umma_bf16(d_tmem, da, db, idesc, (it | j) != 0);
+              }
+            }
+          umma_commit(empty_bar(stg));
+          if (it == n_iters - 1) umma_commit(done_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int quarter = warp & 3;
+      mbar_wait(done_bar, 0);
+      tcgen05_fence_after();
+      const int ko = ktile * 128 + quarter * 32 + lane;
+      const int row_len = p.R * p.S * p.cpad;
+      float* drow = p.dw + (long long)ko * row_len;
+      for (int t = 0; t < ntaps; ++t) {
+        const int tap = tap0 + t;
+        for (int c0 = 0; c0 < p.c_tile; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.c_tile + c0), v);
+          if (ko < p.K) {
+            float* dst = drow + tap * p.cpad + ctile * p.c_tile + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) tcgen05_dealloc(tmem_base, p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -610,6 +767,93 @@ int launch(const Problem& q, cudaStream_t st) {
   if (rc != SGB_OK) return rc;
   ++g_launches;
   return sgb_cuda_check(cudaGetLastError(), "conv_umma_kernel");
+}
+
+bool wgrad_supported(const WgradProblem& q) {
+  if (!enabled()) return false;
+  if (q.C % 32 != 0 || q.K % 8 != 0) return false;
+  if (!((q.R == 1 && q.S == 1) || (q.R == 3 && q.S == 3))) return false;
+  if (q.pad != q.R / 2 || (q.stride != 1 && q.stride != 2)) return false;
+  if (q.x_pitch % 8 != 0 || q.y_pitch % 8 != 0) return false;
+  if (((uintptr_t)q.x & 15) || ((uintptr_t)q.dy & 15)) return false;
+  if ((long long)q.N * q.P * q.Q >= (1ll << 31)) return false;
+  return true;
+}
+
+int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
+  if (int rc = init_driver()) return rc;
+  WParams p{};
+  p.K = q.K; p.C = q.C; p.R = q.R; p.S = q.S; p.stride = q.stride; p.pad = q.pad; p.P = q.P; p.Q = q.Q;
+  p.npix = q.N * q.P * q.Q;
+  p.CB = q.C % 64 == 0 ? 64 : 32;
+  p.c_tile = q.C <= 512 ? q.C : 256;
+  if (q.C % p.c_tile != 0) p.c_tile = p.CB;
+  const int taps = q.R * q.S;
+  int tpg = 512 / p.c_tile;
+  if (tpg < 1) tpg = 1;
+  if (tpg > taps) tpg = taps;
+  p.n_groups = (taps + tpg - 1) / tpg;
+  p.tpg = (taps + p.n_groups - 1) / p.n_groups;
+  p.n_ctiles = q.C / p.c_tile;
+  p.n_ktiles = (q.K + 127) / 128;
+  p.cpad = q.C;
+  p.dw = q.dw;
+  int tc = 32;
+  while (tc < p.tpg * p.c_tile) tc <<= 1;
+  p.tmem_cols = tc;
+  const uint32_t a_bytes = 2 * WPIX * 128;
+  const uint32_t b_bytes = (uint32_t)p.tpg * (p.c_tile / p.CB) * WPIX * p.CB * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 2) + 64;
+  int stages = (int)((200 * 1024 - ctrl_bytes - 1024) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return SGB_E_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + ctrl_bytes;
+  // pixel splits: fill ~2 waves of SMs, keep at least 8 pipeline iterations per CTA
+  const int base_ctas = p.n_ktiles * p.n_ctiles * p.n_groups;
+  const int total_iters = (p.npix + WPIX - 1) / WPIX;
+  int splits = (2 * g_num_sms + base_ctas - 1) / base_ctas;
+  if (splits > total_iters / 8) splits = total_iters / 8;
+  if (splits < 1) splits = 1;
+  int iters_per = (total_iters + splits - 1) / splits;
+  p.pix_per_cta = iters_per * WPIX;
+  splits = (p.npix + p.pix_per_cta - 1) / p.pix_per_cta;
+
+  alignas(64) CUtensorMap map_dy, map_x;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)q.K, (cuuint64_t)p.npix};
+    cuuint64_t strides[1] = {(cuuint64_t)q.y_pitch * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)WPIX};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_tiled(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q.dy), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sgb_set_error("cuTensorMapEncodeTiled(dy) failed with %d", (int)r); return SGB_E_CUDA; }
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+    cuuint64_t strides[3] = {(cuuint64_t)q.x_pitch * 2, (cuuint64_t)q.W * q.x_pitch * 2, (cuuint64_t)q.H * q.W * q.x_pitch * 2};
+    int lower[2] = {-q.pad, -q.pad};
+    int upper[2] = {q.pad - (q.S - 1), q.pad - (q.R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)q.stride, (cuuint32_t)q.stride, 1};
+    CUresult r = g_im2col(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.x), dims, strides, lower, upper,
+                          (cuuint32_t)p.CB, (cuuint32_t)WPIX, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sgb_set_error("cuTensorMapEncodeIm2col(x, wgrad) failed with %d", (int)r); return SGB_E_CUDA; }
+  }
+  static bool attr = false;
+  if (!attr) {
+    if (int rc = sgb_cuda_check(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                                "cudaFuncSetAttribute(wgrad_umma_kernel)"))
+      return rc;
+    attr = true;
+  }
+  const int grid = base_ctas * splits;
+  wgrad_umma_kernel<<<grid, NUM_THREADS, smem, st>>>(map_dy, map_x, p);
+  ++g_launches;
+  return sgb_cuda_check(cudaGetLastError(), "wgrad_umma_kernel");
 }
 
 }  // namespace sm100

@@ -21,7 +21,18 @@ struct Problem {
   int stats_repl, act;
 };
 
+struct WgradProblem {
+  const void* x;   // NHWC bf16 slice, N x H x W x C
+  const void* dy;  // NHWC bf16 slice, N x P x Q x K
+  int N, H, W, C, x_pitch;
+  int K, y_pitch;
+  int R, S, stride, pad, P, Q;
+  float* dw;       // fp32 [K][R][S][C], accumulated into
+};
+
 bool enabled();
+bool wgrad_supported(const WgradProblem& q);
+int wgrad_launch(const WgradProblem& q, cudaStream_t st);
 bool supported(const Problem& q);
 int launch(const Problem& q, cudaStream_t st);
 long long launch_count();

@@ -64,6 +64,10 @@ CONV_CASES = [
     (4, 192, 20, 20, 384, 3, 2, 1),
     (2, 384, 20, 20, 768, 1, 1, 0),
     (6, 64, 31, 29, 128, 1, 1, 0),
+    (4, 16, 16, 16, 16, 3, 1, 1),
+    (4, 32, 16, 16, 32, 3, 1, 1),
+    (4, 16, 16, 16, 16, 1, 1, 0),
+    (2, 64, 24, 24, 64, 3, 1, 1),
 ]
 
 

