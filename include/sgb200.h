@@ -91,7 +91,8 @@ int sgb_convt2x2_fprop(const SgbConvDesc* d, const sgb_bf16* x_small, const sgb_
                        sgb_bf16* y_up, void* stream);
 
 /* ---- layout ---------------------------------------------------------------------------------------------- */
-int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, sgb_bf16* y, int y_pitch, int y_off,
+/* fp32 NCHW -> bf16 NHWC; channels [C, c_out) of the destination are written as zeros (c_out % 8 == 0). */
+int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, sgb_bf16* y, int y_pitch, int y_off, int c_out,
                               void* stream);
 int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H, int W, int x_pitch, int x_off, float* y,
                               void* stream);

@@ -587,6 +587,38 @@ extern "C" int sgb_conv_dgrad(const SgbConvDesc* d, const sgb_bf16* dy, const sg
     q.stats_repl = 1;
     if (sm100::supported(q)) return sm100::launch(q, (cudaStream_t)stream);
   }
+  if (s == 2 && d->K % 16 == 0 && d->R == 3 && d->S == 3 && d->pad == 1 && d->C % 8 == 0 && d->H % 2 == 0 &&
+      d->W % 2 == 0 && d->H == 2 * d->P && d->W == 2 * d->Q && sm100::enabled()) {
+    // stride-2 dgrad = 4 output-parity classes, each an exact stride-1 gather of dy with a subset of the taps
+    bool all_ok = true;
+    for (int cls = 0; cls < 4 && all_ok; ++cls) {
+      const int ph = cls >> 1, pw = cls & 1;
+      sm100::Problem q{};
+      q.a = dy + d->y_off; q.N = d->N; q.H = d->P; q.W = d->Q; q.C = d->K; q.a_pitch = d->y_pitch;
+      q.b = w_crsk; q.b_rows = d->C; q.b_cols = d->R * d->S * Kp; q.b_cols_per_tap = Kp;
+      q.R = d->R; q.S = d->S; q.stride = 1; q.pad = 0; q.P = d->P; q.Q = d->Q; q.flip = 0;
+      q.y = dx; q.y_pitch = d->x_pitch; q.y_off = d->x_off;
+      q.residual = accumulate ? dx : nullptr;
+      q.stats_repl = 1;
+      q.out_mode = 1; q.o_mul = 2; q.oh_add = ph; q.ow_add = pw; q.outH = d->H; q.outW = d->W;
+      // taps r with (h + pad - r) even, h = 2j + ph:  ho = j + (ph + pad - r) / 2
+      int nt = 0;
+      for (int r = 0; r < d->R; ++r) {
+        if (((ph + d->pad - r) & 1) != 0) continue;
+        for (int sx = 0; sx < d->S; ++sx) {
+          if (((pw + d->pad - sx) & 1) != 0) continue;
+          q.tap_dh[nt] = (ph + d->pad - r) / 2;
+          q.tap_dw[nt] = (pw + d->pad - sx) / 2;
+          q.tap_b[nt] = r * d->S + sx;
+          ++nt;
+        }
+      }
+      q.ntaps = nt;
+      if (!sm100::supported(q)) { all_ok = false; break; }  // identical for the 4 classes: fails before any launch
+      if (int rc = sm100::launch(q, (cudaStream_t)stream)) return rc;
+    }
+    if (all_ok) return SGB_OK;
+  }
   IGemmParams p{};
   p.A = reinterpret_cast<const bf16*>(dy);
   p.B = reinterpret_cast<const bf16*>(w_crsk);

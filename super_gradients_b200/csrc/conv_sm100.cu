@@ -40,6 +40,11 @@ struct Params {
   int stride, pad;  // traversal stride, lower padding of the gather
   int flip;         // 1: B columns are visited with spatially flipped taps (dgrad)
   int b_cols_per_tap;
+  int ntaps;                  // taps visited (R*S for fprop / stride-1 dgrad; a subset for a stride-2 dgrad parity class)
+  signed char tap_dh[9], tap_dw[9], tap_b[9];  // im2col offsets of each tap and its column block in the B matrix
+  // output row m -> address.  out_mode 0: rows are consecutive NHWC pixels.  out_mode 1: row m = (n, j, i) over a
+  // (P x Q) grid is written to pixel (n, j*o_mul + oh_add, i*o_mul + ow_add) of an (outH x outW) image.
+  int out_mode, o_mul, oh_add, ow_add, outH, outW;
   long long y_pitch;  // elements
   int y_off;
   bf16* y;
@@ -179,6 +184,15 @@ __device__ __forceinline__ int col_of_lane(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+__device__ __forceinline__ long long out_row(const Params& p, long long m) {
+  if (p.out_mode == 0) return m;
+  const int pq = p.P * p.Q;
+  const int n = (int)(m / pq);
+  const int rem = (int)(m - (long long)n * pq);
+  const int j = rem / p.Q, i = rem - j * p.Q;
+  return ((long long)n * p.outH + j * p.o_mul + p.oh_add) * p.outW + i * p.o_mul + p.ow_add;
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int NCH, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -200,7 +214,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.BN - 1) / p.BN;
   const int total_tiles = m_tiles * n_tiles;
   const int chunks = p.C / p.KC;
-  const int k_iters = p.R * p.S * chunks;
+  const int k_iters = p.ntaps * chunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -235,9 +249,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int rem = m0 - n_img * pq;
         const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
         const int w0 = q0 * p.stride - p.pad, h0 = p0 * p.stride - p.pad;
-        for (int tap = 0; tap < p.R * p.S; ++tap) {
-          const int r = tap / p.S, s = tap - r * p.S;
-          const int btap = p.flip ? (p.R * p.S - 1 - tap) : tap;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int r = p.tap_dh[tap], s = p.tap_dw[tap];
+          const int btap = p.tap_b[tap];
           for (int ck = 0; ck < chunks; ++ck, ++it) {
             const int stg = it % p.stages;
             const uint32_t par = ((it / p.stages) & 1) ^ 1;
@@ -299,7 +313,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tcgen05_fence_after();
         const long long m = (long long)tile * BLOCK_M + row;
         const bool row_ok = m < p.M;
-        bf16* yrow = p.y + m * p.y_pitch + p.y_off;
+        bf16* yrow = p.y + out_row(p, m) * p.y_pitch + p.y_off;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           float v[16];
@@ -357,8 +371,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const long long m = (long long)mt * BLOCK_M + row;
         const bool row_ok = m < p.M;
         const int n0 = nt * p.BN;
-        bf16* yrow = p.y + m * p.y_pitch + p.y_off + n0;
-        const bf16* rrow = p.residual ? p.residual + m * p.y_pitch + p.y_off + n0 : nullptr;
+        const long long orow = out_row(p, m);
+        bf16* yrow = p.y + orow * p.y_pitch + p.y_off + n0;
+        const bf16* rrow = p.residual ? p.residual + orow * p.y_pitch + p.y_off + n0 : nullptr;
         const int ncols = min(p.BN, p.N - n0);
         for (int c0 = 0; c0 < ncols; c0 += 16) {
           float v[16];
@@ -686,6 +701,18 @@ int launch(const Problem& q, cudaStream_t st) {
   }
   p.BN = bn;
   p.P = q.P; p.Q = q.Q; p.stride = q.stride; p.pad = q.pad; p.flip = q.flip;
+  if (q.ntaps > 0) {
+    p.ntaps = q.ntaps;
+    for (int t = 0; t < q.ntaps; ++t) { p.tap_dh[t] = (signed char)q.tap_dh[t]; p.tap_dw[t] = (signed char)q.tap_dw[t]; p.tap_b[t] = (signed char)q.tap_b[t]; }
+  } else {
+    p.ntaps = q.R * q.S;
+    for (int t = 0; t < p.ntaps; ++t) {
+      p.tap_dh[t] = (signed char)(t / q.S);
+      p.tap_dw[t] = (signed char)(t % q.S);
+      p.tap_b[t] = (signed char)(q.flip ? (p.ntaps - 1 - t) : t);
+    }
+  }
+  p.out_mode = q.out_mode; p.o_mul = q.o_mul; p.oh_add = q.oh_add; p.ow_add = q.ow_add; p.outH = q.outH; p.outW = q.outW;
   p.b_cols_per_tap = q.b_cols_per_tap;
   p.y = (bf16*)q.y; p.y_pitch = q.y_pitch; p.y_off = q.y_off;
   p.scale = q.scale; p.shift = q.shift; p.residual = (const bf16*)q.residual;
@@ -713,6 +740,11 @@ int launch(const Problem& q, cudaStream_t st) {
     cuuint64_t strides[3] = {(cuuint64_t)q.a_pitch * 2, (cuuint64_t)q.W * q.a_pitch * 2, (cuuint64_t)q.H * q.W * q.a_pitch * 2};
     int lower[2] = {-q.pad, -q.pad};
     int upper[2] = {q.pad - (q.S - 1), q.pad - (q.R - 1)};
+    if (q.ntaps > 0) {  // explicit tap table (stride-2 dgrad class): base pixel = output-class pixel, no padding
+      lower[0] = lower[1] = 0;
+      upper[0] = q.Q - q.W;
+      upper[1] = q.P - q.H;
+    }
     cuuint32_t estr[4] = {1, (cuuint32_t)q.stride, (cuuint32_t)q.stride, 1};
     CUresult r = g_im2col(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.a), dims, strides, lower, upper,
                           (cuuint32_t)p.KC, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.KC),
@@ -740,6 +772,7 @@ int launch(const Problem& q, cudaStream_t st) {
   int grid = m_tiles * n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
   const bool plain = !p.scale && !p.shift && !p.residual && p.act == SGB_ACT_NONE && n_tiles == 1 && p.N == bn && !(p.dbg & 2);
+  if (p.ntaps > 9) return SGB_E_UNSUPPORTED;
   const int nch = plain ? bn / 16 : 0;
   int rc = SGB_OK;
 #define SGB_LAUNCH_UMMA(NCH_, ST_)                                                                                   \
@@ -771,7 +804,7 @@ int launch(const Problem& q, cudaStream_t st) {
 
 bool wgrad_supported(const WgradProblem& q) {
   if (!enabled()) return false;
-  if (q.C % 32 != 0 || q.K % 8 != 0) return false;
+  if (q.C % 16 != 0 || q.K % 8 != 0) return false;
   if (!((q.R == 1 && q.S == 1) || (q.R == 3 && q.S == 3))) return false;
   if (q.pad != q.R / 2 || (q.stride != 1 && q.stride != 2)) return false;
   if (q.x_pitch % 8 != 0 || q.y_pitch % 8 != 0) return false;
@@ -785,7 +818,7 @@ int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
   WParams p{};
   p.K = q.K; p.C = q.C; p.R = q.R; p.S = q.S; p.stride = q.stride; p.pad = q.pad; p.P = q.P; p.Q = q.Q;
   p.npix = q.N * q.P * q.Q;
-  p.CB = q.C % 64 == 0 ? 64 : 32;
+  p.CB = q.C % 64 == 0 ? 64 : (q.C % 32 == 0 ? 32 : 16);
   p.c_tile = q.C <= 512 ? q.C : 256;
   if (q.C % p.c_tile != 0) p.c_tile = p.CB;
   const int taps = q.R * q.S;
@@ -839,7 +872,7 @@ int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
     cuuint32_t estr[4] = {1, (cuuint32_t)q.stride, (cuuint32_t)q.stride, 1};
     CUresult r = g_im2col(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.x), dims, strides, lower, upper,
                           (cuuint32_t)p.CB, (cuuint32_t)WPIX, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          swizzle_for(p.CB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sgb_set_error("cuTensorMapEncodeIm2col(x, wgrad) failed with %d", (int)r); return SGB_E_CUDA; }
   }

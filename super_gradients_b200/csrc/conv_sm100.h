@@ -12,6 +12,11 @@ struct Problem {
   const void* b;
   int b_rows, b_cols, b_cols_per_tap;
   int R, S, stride, pad, P, Q, flip;
+  // optional explicit tap table (ntaps > 0): im2col offsets (dh, dw) and B column block of each tap
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_b[9];
+  // strided output rows (see conv_sm100.cu: Params::out_mode)
+  int out_mode, o_mul, oh_add, ow_add, outH, outW;
   void* y;
   int y_pitch, y_off;
   const float* scale;

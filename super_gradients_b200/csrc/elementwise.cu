@@ -726,10 +726,11 @@ extern "C" int sgb_wgrad_to_oihw(const float* dw, int K, int C, int R, int S, in
 }
 
 extern "C" int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, sgb_bf16* y, int y_pitch,
-                                         int y_off, void* stream) {
+                                         int y_off, int c_out, void* stream) {
   SGB_REQUIRE(x && y, "null pointer");
   SGB_REQUIRE(y_pitch % 8 == 0 && y_off % 8 == 0, "pitch/offset multiples of 8");
-  int cpad = ((C + 7) / 8) * 8;
+  SGB_REQUIRE(c_out >= C && c_out % 8 == 0, "c_out must be >= C and a multiple of 8");
+  int cpad = c_out;  // channels [C, c_out) are written as zeros
   SGB_REQUIRE(y_pitch >= y_off + cpad, "slice exceeds pitch");
   nchw_to_nhwc_kernel<<<grid_for((int64_t)N * H * W * (cpad / 8)), TPB, 0, (cudaStream_t)stream>>>(
       x, N, C, H, W, (bf16*)y, y_pitch, y_off, cpad);

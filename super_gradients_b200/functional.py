@@ -43,10 +43,11 @@ class WeightCache:
         self.krsc = None
         self.crsk = None
 
-    def get(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, add_identity=False, extra_key=None):
-        key = (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key, _WEIGHT_EPOCH[0])
+    def get(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, add_identity=False, extra_key=None, c_pad=None):
+        """c_pad: channel count of the activation the filter is applied to (>= w.shape[1]; the extra channels are zero)."""
+        key = (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key, c_pad, _WEIGHT_EPOCH[0])
         if key != self.key:
-            self.krsc, self.crsk = K.weight_prepare(w, scale=scale, add_identity=add_identity, out=(self.krsc, self.crsk))
+            self.krsc, self.crsk = K.weight_prepare(w, c_pad=c_pad, scale=scale, add_identity=add_identity, out=(self.krsc, self.crsk))
             self.key = key
         return self.krsc, self.crsk
 
@@ -87,7 +88,7 @@ def to_nhwc(x: torch.Tensor) -> torch.Tensor:
     K.require_cuda(x, "input")
     if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
         return K.as_nhwc(x)
-    return K.nchw_f32_to_nhwc_bf16(x.detach())
+    return K.nchw_f32_to_nhwc_bf16(x.detach(), c_align=16)
 
 
 class _FromNhwc(torch.autograd.Function):
@@ -112,7 +113,7 @@ class _ConvBnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, residual, cfg):
         x = K.as_nhwc(x)
-        krsc, crsk = cfg.cache.get(w)
+        krsc, crsk = cfg.cache.get(w, c_pad=x.shape[1])
         kout, _, r, s = w.shape
         stats = K.new_stats(kout, x.device)
         y_raw = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, stats=stats)
@@ -149,7 +150,7 @@ def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracke
     # inference: BN folded into the GEMM epilogue (one kernel)
     with torch.no_grad():
         x = K.as_nhwc(x)
-        krsc, _ = cache.get(w)
+        krsc, _ = cache.get(w, c_pad=x.shape[1])
         scale = gamma * torch.rsqrt(running_var + eps)
         shift = beta - running_mean * scale
         res = K.as_nhwc(residual) if residual is not None else None
@@ -161,7 +162,7 @@ class _ConvBias(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, cfg):
         x = K.as_nhwc(x)
-        krsc, crsk = cfg.cache.get(w)
+        krsc, crsk = cfg.cache.get(w, c_pad=x.shape[1])
         kout, _, r, s = w.shape
         y = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, shift=b, act=cfg.act)
         ctx.save_for_backward(x)
@@ -200,8 +201,8 @@ class _QARepVGG(torch.autograd.Function):
     def forward(ctx, x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
         x = K.as_nhwc(x)
         kout = w3.shape[0]
-        k3, c3 = cfg.cache3.get(w3)
-        k1, c1 = cfg.cache1.get(w1, scale=alpha, add_identity=cfg.residual)
+        k3, c3 = cfg.cache3.get(w3, c_pad=x.shape[1])
+        k1, c1 = cfg.cache1.get(w1, scale=alpha, add_identity=cfg.residual, c_pad=x.shape[1])
         y3 = K.conv_fprop(x, k3, kout, 3, 3, cfg.stride, 1)
         u = K.conv_fprop(x, k1, kout, 1, 1, cfg.stride, 0)
         ab = None

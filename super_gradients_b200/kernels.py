@@ -207,12 +207,14 @@ def convt2x2_fprop(x_small, w_up, bias, C_up):
 
 
 # ------------------------------------------------------------------------------------------------ layout
-def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor, c_align: int = 8) -> torch.Tensor:
+    """c_align: channel count of the result is C rounded up to a multiple of it (16 lets a 3-channel image use the
+    tcgen05 path, whose K-chunk is 16 channels)."""
     require_cuda(x, "x")
     n, c, h, w = x.shape
     x = x.contiguous().float()
-    out = torch.empty((n, ((c + 7) // 8) * 8, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-    _timed("sgb_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, _ptr(out), out.shape[1], 0, _stream())
+    out = torch.empty((n, ((c + c_align - 1) // c_align) * c_align, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    _timed("sgb_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, _ptr(out), out.shape[1], 0, out.shape[1], _stream())
     return out
 
 

@@ -112,7 +112,7 @@ class QARepVGGBlock(nn.Module):
     def _forward_single_conv(self, x, weight, bias, extra_key=None):
         """act(post_bn_eval(conv3x3(x, weight) + bias)) in one GEMM launch."""
         x = K.as_nhwc(x)
-        krsc, _ = self._cache_eq.get(weight, extra_key=extra_key)
+        krsc, _ = self._cache_eq.get(weight, extra_key=extra_key, c_pad=x.shape[1])
         if self.use_post_bn and not self.fully_fused:
             pbn = self.post_bn
             if self.training:

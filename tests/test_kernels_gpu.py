@@ -68,6 +68,8 @@ CONV_CASES = [
     (4, 32, 16, 16, 32, 3, 1, 1),
     (4, 16, 16, 16, 16, 1, 1, 0),
     (2, 64, 24, 24, 64, 3, 1, 1),
+    (2, 16, 32, 32, 48, 3, 2, 1),
+    (3, 32, 24, 24, 64, 3, 2, 1),
 ]
 
 
