@@ -117,13 +117,15 @@ int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, c
 int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const float* gamma, const float* beta,
                      const float* running_mean, const float* running_var, const sgb_bf16* residual, sgb_bf16* y,
                      void* stream);
-/* Backward, pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat with dz = dy * act'(y). */
-int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
-                          const float* save_mean, const float* save_rstd, double* sums, void* stream);
+/* Backward, pass 1: sums[0][c] = sum dz, sums[1][c] = sum dz * xhat with dz = dy * act'(pre-activation).
+ * y (the forward output) is only needed when a residual was added; pass NULL otherwise and the activation mask is
+ * recomputed from x, gamma, beta (one tensor read less). */
+int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y, const float* gamma,
+                          const float* beta, const float* save_mean, const float* save_rstd, double* sums, void* stream);
 /* Backward, pass 2: dx (pre-BN grad), dresidual (= dz, optional), dgamma / dbeta (+=). */
 int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
-                         const float* gamma, const float* save_mean, const float* save_rstd, const double* sums,
-                         sgb_bf16* dx, sgb_bf16* dresidual, float* dgamma, float* dbeta, void* stream);
+                         const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
+                         const double* sums, sgb_bf16* dx, sgb_bf16* dresidual, float* dgamma, float* dbeta, void* stream);
 /* Per-channel sums of an NHWC bf16 tensor (used where the producer is not one of our GEMMs). */
 int sgb_channel_stats(const sgb_bf16* x, int64_t M, int C, int pitch, int off, double* stats, void* stream);
 
@@ -146,7 +148,8 @@ int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, 
                   const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
                   const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out, float* coef,
                   void* stream);
-/* pass 1: sums [3][C] = sum dzp, sum dzp*zhat, sum dzp*y3hat, dzp = dout*act'(out). */
+/* pass 1: sums [3][C] = sum dzp, sum dzp*zhat, sum dzp*y3hat, dzp = dout*act'(pre).  `out` is unused (may be NULL):
+ * the activation mask is recomputed from y3, u and the saved coefficients. */
 int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out, const sgb_bf16* y3,
                          const sgb_bf16* u, const float* coef, double* sums, void* stream);
 /* pass 2: dy3, du (bf16), param grads (+=): dgamma3, dbeta3, dbias1a (grad of alpha*b1), dgamma_p, dbeta_p. */

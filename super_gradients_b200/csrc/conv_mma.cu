@@ -619,6 +619,30 @@ extern "C" int sgb_conv_dgrad(const SgbConvDesc* d, const sgb_bf16* dy, const sg
     }
     if (all_ok) return SGB_OK;
   }
+  if (s == 2 && d->K % 16 == 0 && d->R == 1 && d->S == 1 && d->pad == 0 && d->C % 8 == 0 && d->H == 2 * d->P &&
+      d->W == 2 * d->Q && sm100::enabled()) {
+    // 1x1 stride-2 dgrad: only the even/even input pixels receive a gradient.  With accumulate the other three parity
+    // classes are untouched; otherwise they are zero-filled first.
+    sm100::Problem q{};
+    q.a = dy + d->y_off; q.N = d->N; q.H = d->P; q.W = d->Q; q.C = d->K; q.a_pitch = d->y_pitch;
+    q.b = w_crsk; q.b_rows = d->C; q.b_cols = Kp; q.b_cols_per_tap = Kp;
+    q.R = 1; q.S = 1; q.stride = 1; q.pad = 0; q.P = d->P; q.Q = d->Q; q.flip = 0;
+    q.y = dx; q.y_pitch = d->x_pitch; q.y_off = d->x_off;
+    q.residual = accumulate ? dx : nullptr;
+    q.stats_repl = 1;
+    q.out_mode = 1; q.o_mul = 2; q.oh_add = 0; q.ow_add = 0; q.outH = d->H; q.outW = d->W;
+    q.ntaps = 1; q.tap_dh[0] = 0; q.tap_dw[0] = 0; q.tap_b[0] = 0;
+    if (sm100::supported(q)) {
+      if (!accumulate) {
+        if (d->x_pitch == d->C && d->x_off == 0) {
+          cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->C * sizeof(sgb_bf16), (cudaStream_t)stream);
+          return sm100::launch(q, (cudaStream_t)stream);
+        }
+      } else {
+        return sm100::launch(q, (cudaStream_t)stream);
+      }
+    }
+  }
   IGemmParams p{};
   p.A = reinterpret_cast<const bf16*>(dy);
   p.B = reinterpret_cast<const bf16*>(w_crsk);

@@ -212,16 +212,20 @@ struct QarepMomF {
 
 struct BnBwdRedF {
   static constexpr int NACC = 2;
-  const bf16 *dy, *x, *y;
-  const float *mean, *rstd;
+  const bf16 *dy, *x, *y;  // y == nullptr: the ReLU mask is recomputed from x (no residual), saving one tensor read
+  const float *mean, *rstd, *gamma, *beta;
   int xp, xo, yp, yo, act;
   __device__ void eval(int64_t pix, int c0, float (&acc)[2][8]) const {
-    V8 g = ld8(dy + pix * yp + yo + c0), xv = ld8(x + pix * xp + xo + c0), yv = ld8(y + pix * yp + yo + c0);
+    V8 g = ld8(dy + pix * yp + yo + c0), xv = ld8(x + pix * xp + xo + c0), yv;
+    if (y) yv = ld8(y + pix * yp + yo + c0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = g.v[e];
-      if (act == SGB_ACT_RELU) dz = yv.v[e] > 0.f ? dz : 0.f;
       float xh = (xv.v[e] - mean[c0 + e]) * rstd[c0 + e];
+      if (act == SGB_ACT_RELU) {
+        float pre = y ? yv.v[e] : xh * (gamma ? gamma[c0 + e] : 1.f) + (beta ? beta[c0 + e] : 0.f);
+        dz = pre > 0.f ? dz : 0.f;
+      }
       acc[0][e] += dz;
       acc[1][e] += dz * xh;
     }
@@ -234,13 +238,14 @@ struct QarepBwdRedF {
   const float* coef;  // [8][C]
   int C, p3, o3, pu, ou, po, oo, act, post;
   __device__ void eval(int64_t pix, int c0, float (&acc)[3][8]) const {
-    V8 g = ld8(dout + pix * po + oo + c0), ov = ld8(out + pix * po + oo + c0);
+    V8 g = ld8(dout + pix * po + oo + c0);
     V8 a = ld8(y3 + pix * p3 + o3 + c0), b = ld8(u + pix * pu + ou + c0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int c = c0 + e;
       float dz = g.v[e];
-      if (act == SGB_ACT_RELU) dz = ov.v[e] > 0.f ? dz : 0.f;
+      // ReLU mask recomputed from the saved coefficients: out = act(a3*y3 + au*u + c0)
+      if (act == SGB_ACT_RELU) dz = (coef[4 * C + c] * a.v[e] + coef[5 * C + c] * b.v[e] + coef[6 * C + c]) > 0.f ? dz : 0.f;
       float mu3 = coef[c], rstd3 = coef[C + c], muu = coef[2 * C + c], rstdz = coef[3 * C + c];
       float s3 = coef[8 * C + c];  // gamma3 * rstd3
       float y3h = (a.v[e] - mu3) * rstd3;
@@ -337,10 +342,11 @@ __global__ void __launch_bounds__(TPB) bn_act_infer_kernel(SgbBnDesc d, const bf
 
 __global__ void __launch_bounds__(TPB) bn_act_bwd_apply_kernel(SgbBnDesc d, const bf16* __restrict__ dy,
                                                                const bf16* __restrict__ x, const bf16* __restrict__ y,
-                                                               const float* gamma, const float* mean,
-                                                               const float* rstd, const double* sums, bf16* dx,
-                                                               bf16* dres, float* dgamma, float* dbeta) {
-  extern __shared__ float sc[];  // [4][C]: mean, rstd, m0 (mean dz), m1 (mean dz*xhat) ; plus g*rstd
+                                                               const float* gamma, const float* beta,
+                                                               const float* mean, const float* rstd,
+                                                               const double* sums, bf16* dx, bf16* dres, float* dgamma,
+                                                               float* dbeta) {
+  extern __shared__ float sc[];  // [7][C]: mean, rstd, m0 (mean dz), m1 (mean dz*xhat), g*rstd, g, beta
   const int C = d.C;
   for (int c = threadIdx.x; c < C; c += TPB) {
     float g = gamma ? gamma[c] : 1.f;
@@ -350,6 +356,8 @@ __global__ void __launch_bounds__(TPB) bn_act_bwd_apply_kernel(SgbBnDesc d, cons
     sc[2 * C + c] = m0;
     sc[3 * C + c] = m1;
     sc[4 * C + c] = g * rstd[c];
+    sc[5 * C + c] = g;
+    sc[6 * C + c] = beta ? beta[c] : 0.f;
     if (blockIdx.x == 0) {
       if (dgamma) dgamma[c] += (float)sums[C + c];
       if (dbeta) dbeta[c] += (float)sums[c];
@@ -363,14 +371,18 @@ __global__ void __launch_bounds__(TPB) bn_act_bwd_apply_kernel(SgbBnDesc d, cons
     int64_t pix = i / cvs;
     V8 g = ld8(dy + pix * d.y_pitch + d.y_off + cv * 8);
     V8 xv = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
-    V8 yv = ld8(y + pix * d.y_pitch + d.y_off + cv * 8);
+    V8 yv;
+    if (y) yv = ld8(y + pix * d.y_pitch + d.y_off + cv * 8);
     V8 o, dr;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int c = cv * 8 + e;
       float dz = g.v[e];
-      if (d.act == SGB_ACT_RELU) dz = yv.v[e] > 0.f ? dz : 0.f;
       float xh = (xv.v[e] - sc[c]) * sc[C + c];
+      if (d.act == SGB_ACT_RELU) {
+        float pre = y ? yv.v[e] : xh * sc[5 * C + c] + sc[6 * C + c];
+        dz = pre > 0.f ? dz : 0.f;
+      }
       o.v[e] = sc[4 * C + c] * (dz - sc[2 * C + c] - xh * sc[3 * C + c]);
       dr.v[e] = dz;
     }
@@ -486,6 +498,9 @@ __global__ void __launch_bounds__(TPB) qarep_bwd_apply_kernel(SgbQarepDesc d, co
     sc[6 * C + c] = m0;
     sc[7 * C + c] = m1;
     sc[8 * C + c] = q;
+    sc[9 * C + c] = coef[4 * C + c];
+    sc[10 * C + c] = coef[5 * C + c];
+    sc[11 * C + c] = coef[6 * C + c];
     if (blockIdx.x == 0) {
       if (d.use_post_bn) {
         if (dgamma_p) dgamma_p[c] += (float)T1;
@@ -505,14 +520,14 @@ __global__ void __launch_bounds__(TPB) qarep_bwd_apply_kernel(SgbQarepDesc d, co
   for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
     int cv = i % cvs;
     int64_t pix = i / cvs;
-    V8 g = ld8(dout + pix * d.pitcho + d.offo + cv * 8), ov = ld8(out + pix * d.pitcho + d.offo + cv * 8);
+    V8 g = ld8(dout + pix * d.pitcho + d.offo + cv * 8);
     V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + cv * 8), b = ld8(u + pix * d.pitchu + d.offu + cv * 8);
     V8 o3, ou;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int c = cv * 8 + e;
       float dzp = g.v[e];
-      if (d.act == SGB_ACT_RELU) dzp = ov.v[e] > 0.f ? dzp : 0.f;
+      if (d.act == SGB_ACT_RELU) dzp = (sc[9 * C + c] * a.v[e] + sc[10 * C + c] * b.v[e] + sc[11 * C + c]) > 0.f ? dzp : 0.f;
       float mu3 = sc[c], rstd3 = sc[C + c], s3 = sc[4 * C + c];
       float y3h = (a.v[e] - mu3) * rstd3;
       float dz;
@@ -783,23 +798,24 @@ extern "C" int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const flo
 }
 
 extern "C" int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
-                                     const float* save_mean, const float* save_rstd, double* sums, void* stream) {
+                                     const float* gamma, const float* beta, const float* save_mean,
+                                     const float* save_rstd, double* sums, void* stream) {
   if (int rc = check_bn(d)) return rc;
-  SGB_REQUIRE(dy && x && y && save_mean && save_rstd && sums, "null pointer");
-  BnBwdRedF f{(const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean, save_rstd,
-              d->x_pitch,      d->x_off,       d->y_pitch,     d->y_off,  d->act};
+  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums, "null pointer");
+  BnBwdRedF f{(const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean,  save_rstd, gamma, beta,
+              d->x_pitch,      d->x_off,       d->y_pitch,     d->y_off,   d->act};
   return launch_chan_reduce(f, d->M, d->C, sums, d->C, (cudaStream_t)stream);
 }
 
 extern "C" int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
-                                    const float* gamma, const float* save_mean, const float* save_rstd,
-                                    const double* sums, sgb_bf16* dx, sgb_bf16* dresidual, float* dgamma, float* dbeta,
-                                    void* stream) {
+                                    const float* gamma, const float* beta, const float* save_mean,
+                                    const float* save_rstd, const double* sums, sgb_bf16* dx, sgb_bf16* dresidual,
+                                    float* dgamma, float* dbeta, void* stream) {
   if (int rc = check_bn(d)) return rc;
-  SGB_REQUIRE(dy && x && y && save_mean && save_rstd && sums && dx, "null pointer");
+  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums && dx, "null pointer");
   int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  bn_act_bwd_apply_kernel<<<grid, TPB, 5 * d->C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, save_mean, save_rstd, sums, (bf16*)dx,
+  bn_act_bwd_apply_kernel<<<grid, TPB, 7 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+      *d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, beta, save_mean, save_rstd, sums, (bf16*)dx,
       (bf16*)dresidual, dgamma, dbeta);
   SGB_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return SGB_OK;
@@ -847,7 +863,7 @@ extern "C" int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout,
                                     const sgb_bf16* y3, const sgb_bf16* u, const float* coef, double* sums,
                                     void* stream) {
   if (int rc = check_qarep(d)) return rc;
-  SGB_REQUIRE(dout && out && y3 && u && coef && sums, "null pointer");
+  SGB_REQUIRE(dout && y3 && u && coef && sums, "null pointer");
   QarepBwdRedF f{(const bf16*)dout, (const bf16*)out, (const bf16*)y3, (const bf16*)u, coef,      d->C,
                  d->pitch3,         d->off3,          d->pitchu,       d->offu,        d->pitcho, d->offo,
                  d->act,            d->use_post_bn};
@@ -860,9 +876,9 @@ extern "C" int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, 
                                    float* dgamma3, float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p,
                                    void* stream) {
   if (int rc = check_qarep(d)) return rc;
-  SGB_REQUIRE(dout && out && y3 && u && coef && sums && gamma3 && dy3 && du, "null pointer");
+  SGB_REQUIRE(dout && y3 && u && coef && sums && gamma3 && dy3 && du, "null pointer");
   int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  qarep_bwd_apply_kernel<<<grid, TPB, 9 * d->C * sizeof(float), (cudaStream_t)stream>>>(
+  qarep_bwd_apply_kernel<<<grid, TPB, 12 * d->C * sizeof(float), (cudaStream_t)stream>>>(
       *d, (const bf16*)dout, (const bf16*)out, (const bf16*)y3, (const bf16*)u, coef, sums, gamma3, gamma_p,
       (bf16*)dy3, (bf16*)du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p);
   SGB_LAUNCH_CHECK("qarep_bwd_apply_kernel");

@@ -121,18 +121,18 @@ class _ConvBnAct(torch.autograd.Function):
         out, mean, rstd = K.bn_act_fwd(y_raw, stats, gamma, beta, cfg.running_mean, cfg.running_var, cfg.eps, cfg.momentum, cfg.act, res)
         if cfg.num_batches_tracked is not None:
             cfg.num_batches_tracked += 1
-        ctx.save_for_backward(x, y_raw, out, gamma, mean, rstd)
+        ctx.save_for_backward(x, y_raw, out, gamma, mean, rstd, beta)
         ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_res = cfg, crsk, tuple(w.shape), residual is not None
         ctx.slots = (_mg(w), _mg(gamma), _mg(beta))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y_raw, out, gamma, mean, rstd = ctx.saved_tensors
+        x, y_raw, out, gamma, mean, rstd, beta = ctx.saved_tensors
         cfg = ctx.cfg
         kout, cin, r, s = ctx.wshape
         sw, sg, sb = ctx.slots
-        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res, dgamma=sg, dbeta=sb)
+        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res, dgamma=sg, dbeta=sb, beta=beta)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad)

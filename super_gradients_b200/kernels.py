@@ -257,7 +257,7 @@ def bn_act_infer(x, gamma, beta, running_mean, running_var, eps, act, residual=N
     return y
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None):
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None):
     """Returns (dx, dresidual or None, dgamma, dbeta); dgamma / dbeta are accumulated into when given."""
     n, c, h, w = x.shape
     dy = as_nhwc(dy)
@@ -267,7 +267,9 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
         if nhwc_pitch(dy) != d.y_pitch:
             raise L.SgbError("dy pitch mismatch")
     sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
-    _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
+    # the forward output is only read when a residual entered the activation; otherwise the mask is recomputed from x
+    y_arg = y if (want_residual_grad or beta is None) else None
+    _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
     dx = torch.empty_like(x, memory_format=torch.channels_last) if nhwc_pitch(x) == c else torch.zeros_like(x)
     d.x_pitch = nhwc_pitch(dx)
     # x and dx must share a pitch for the kernel: re-describe x if it is a slice
@@ -281,7 +283,7 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
         dgamma = torch.zeros(c, dtype=torch.float32, device=x.device)
     if dbeta is None:
         dbeta = torch.zeros(c, dtype=torch.float32, device=x.device)
-    _timed("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
+    _timed("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
     return dx, dres, dgamma, dbeta
 
 

@@ -119,8 +119,8 @@ _SIGNATURES = {
     "sgb_nhwc_bf16_to_nchw_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, P, P]),
     "sgb_bn_act_fwd": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P]),
     "sgb_bn_act_infer": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P]),
-    "sgb_bn_act_bwd_reduce": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P]),
-    "sgb_bn_act_bwd_apply": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P, P]),
+    "sgb_bn_act_bwd_reduce": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P]),
+    "sgb_bn_act_bwd_apply": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "sgb_channel_stats": (c_int, [P, _L, _I, _I, _I, P, P]),
     "sgb_qarep_moments": (c_int, [POINTER(QarepDesc), P, P, P, P]),
     "sgb_qarep_fwd": (c_int, [POINTER(QarepDesc)] + [P] * 15),

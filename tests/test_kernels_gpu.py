@@ -188,7 +188,8 @@ def test_bn_act_fwd_bwd(act, with_res):
     assert ((y.float().cpu() - ref.detach()).abs() <= ref.detach().abs() * 2**-7 + 2e-3).all()
     torch.testing.assert_close(rmg.cpu(), rm, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rvg.cpu(), rv, rtol=1e-4, atol=1e-5)
-    dx, dres, dgamma, dbeta = k.bn_act_bwd(to_nhwc_bf16(dy), xg, y, gamma.detach().to(DEV), mean, rstd, eps, act, want_residual_grad=with_res)
+    # without a residual the activation mask is recomputed from x / gamma / beta instead of reading y
+    dx, dres, dgamma, dbeta = k.bn_act_bwd(to_nhwc_bf16(dy), xg, y, gamma.detach().to(DEV), mean, rstd, eps, act, want_residual_grad=with_res, beta=beta.detach().to(DEV))
     assert rel_err(dx.float().cpu(), x.grad) < 2e-2
     assert rel_err(dgamma.cpu(), gamma.grad) < 5e-3
     assert rel_err(dbeta.cpu(), beta.grad) < 5e-3
