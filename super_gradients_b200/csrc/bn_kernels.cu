@@ -1,0 +1,561 @@
+// Train / inference BatchNorm (+ residual + activation) and the QARepVGG branch algebra: forward apply, backward
+// reduction and backward apply passes over NHWC bf16 tensors.
+//
+// All kernels share one thread mapping: a thread owns ONE 8-channel vector (16 bytes) and walks over pixels, so the
+// per-channel coefficients (scale / shift / means / ...) are loaded from shared memory into registers ONCE per thread
+// and the inner loop is pure 16-byte loads, FMAs and 16-byte stores; consecutive threads hold consecutive channel
+// vectors of the same pixel (coalesced).  Per-channel coefficients are derived in every CTA's prologue from the fp64
+// sums produced by the GEMM epilogues / reduction passes (block 0 also writes the side effects: saved statistics,
+// running statistics, parameter gradients).
+//
+// Reference: nn.BatchNorm2d as used by modules/conv_bn_act_block.py:92-93, modules/qarepvgg_block.py:190-204,
+// training/models/classification_models/resnet.py:53-84 and its autograd backward.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+struct V8 {
+  float v[8];
+};
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  V8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o.v[2 * i] = __uint_as_float(w[i] << 16);
+    o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return o;
+}
+__device__ __forceinline__ void st8(bf16* p, const V8& a) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+// Op interface:
+//   static constexpr int NCOEF, NACC;           (NACC == 0: pure map)
+//   __device__ void prologue(float* sc) const;  all threads of the CTA; fills sc[NCOEF][C]
+//   __device__ void apply(int64_t pix, int c0, const float (&r)[NCOEF][8], float (&acc)[NACC or 1][8]) const;
+//   double* out; int out_stride;                (only when NACC > 0)
+template <class Op>
+__global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M, const int C) {
+  constexpr int NCOEF = Op::NCOEF, NACC = Op::NACC;
+  extern __shared__ float sc[];  // [NCOEF][C] (+ [NACC][cvb*8] reduction scratch)
+  op.prologue(sc);
+  __syncthreads();
+  const int cvs = C / 8;
+  const int cvb = cvs < TPB ? cvs : TPB;
+  const int lanes = TPB / cvb;
+  const int t = threadIdx.x, pl = t / cvb, cvi = t % cvb;
+  const int64_t per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per;
+  const int64_t p1 = (p0 + per < M) ? p0 + per : M;
+  float* sred = sc + NCOEF * C;
+  for (int cv0 = 0; cv0 < cvs; cv0 += cvb) {
+    if (NACC > 0) {
+      for (int i = t; i < NACC * cvb * 8; i += TPB) sred[i] = 0.f;
+      __syncthreads();
+    }
+    const int cv = cv0 + cvi;
+    if (pl < lanes && cv < cvs) {
+      float r[NCOEF > 0 ? NCOEF : 1][8];
+#pragma unroll
+      for (int k = 0; k < NCOEF; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[k][e] = sc[k * C + cv * 8 + e];
+      float acc[NACC > 0 ? NACC : 1][8];
+#pragma unroll
+      for (int a = 0; a < (NACC > 0 ? NACC : 1); ++a)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+      for (int64_t pix = p0 + pl; pix < p1; pix += lanes) op.apply(pix, cv * 8, r, acc);
+      if (NACC > 0) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) atomicAdd(&sred[(a * cvb + cvi) * 8 + e], acc[a][e]);
+      }
+    }
+    if (NACC > 0) {
+      __syncthreads();
+      for (int i = t; i < NACC * cvb * 8; i += TPB) {
+        const int a = i / (cvb * 8), rr = i % (cvb * 8);
+        const int c = cv0 * 8 + rr;
+        if (c < C) atomicAdd(&op.out[(int64_t)a * op.out_stride + c], (double)sred[i]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <class Op>
+int launch_chan(const Op& op, int64_t M, int C, cudaStream_t st, const char* what) {
+  const int cvs = C / 8;
+  const int cvb = cvs < TPB ? cvs : TPB;
+  const size_t smem = ((size_t)Op::NCOEF * C + (size_t)Op::NACC * cvb * 8) * sizeof(float);
+  int64_t want = (M + 127) / 128;
+  const int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(chan_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  chan_kernel<Op><<<grid, TPB, smem, st>>>(op, M, C);
+  return sgb_cuda_check(cudaGetLastError(), what);
+}
+
+// ============================================================================================== BatchNorm forward
+struct BnFwdOp {
+  static constexpr int NCOEF = 2, NACC = 0;
+  SgbBnDesc d;
+  const bf16 *x, *res;
+  bf16* y;
+  const double* stats;
+  const float *gamma, *beta;
+  float *rmean, *rvar, *save_mean, *save_rstd;
+  double* out = nullptr;
+  int out_stride = 0;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      double s1 = 0, s2 = 0;
+      for (int r = 0; r < d.stats_repl; ++r) {
+        s1 += stats[(int64_t)r * 2 * C + c];
+        s2 += stats[(int64_t)r * 2 * C + C + c];
+      }
+      const double mean = s1 / (double)d.M;
+      double var = s2 / (double)d.M - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+      const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+      sc[c] = g * rstd;
+      sc[C + c] = b - (float)mean * g * rstd;
+      if (blockIdx.x == 0) {
+        save_mean[c] = (float)mean;
+        save_rstd[c] = rstd;
+        if (rmean) {
+          const double unb = d.M > 1 ? var * (double)d.M / (double)(d.M - 1) : var;
+          rmean[c] = (1.f - d.momentum) * rmean[c] + d.momentum * (float)mean;
+          rvar[c] = (1.f - d.momentum) * rvar[c] + d.momentum * (float)unb;
+        }
+      }
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[2][8], float (&)[1][8]) const {
+    V8 a = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    if (res) {
+      const V8 rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + rr.v[e], d.act);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]), d.act);
+    }
+    st8(y + pix * d.y_pitch + d.y_off + c0, a);
+  }
+};
+
+struct BnInferOp {
+  static constexpr int NCOEF = 2, NACC = 0;
+  SgbBnDesc d;
+  const bf16 *x, *res;
+  bf16* y;
+  const float *gamma, *beta, *rmean, *rvar;
+  double* out = nullptr;
+  int out_stride = 0;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      const float rstd = rsqrtf(rvar[c] + d.eps);
+      const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+      sc[c] = g * rstd;
+      sc[C + c] = b - rmean[c] * g * rstd;
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[2][8], float (&)[1][8]) const {
+    V8 a = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    if (res) {
+      const V8 rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + rr.v[e], d.act);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]), d.act);
+    }
+    st8(y + pix * d.y_pitch + d.y_off + c0, a);
+  }
+};
+
+// ============================================================================================== BatchNorm backward
+// coefficient rows: 0 mean, 1 rstd, 2 scale (= gamma * rstd), 3 shift (= beta - mean * scale)
+struct BnBwdRedOp {
+  static constexpr int NCOEF = 4, NACC = 2;
+  SgbBnDesc d;
+  const bf16 *dy, *x, *y;  // y == nullptr: activation mask recomputed from x (no residual)
+  const float *mean, *rstd, *gamma, *beta;
+  double* out;
+  int out_stride;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+      sc[c] = mean[c];
+      sc[C + c] = rstd[c];
+      sc[2 * C + c] = g * rstd[c];
+      sc[3 * C + c] = b - mean[c] * g * rstd[c];
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[4][8], float (&acc)[2][8]) const {
+    const V8 g = ld8(dy + pix * d.y_pitch + d.y_off + c0), xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    V8 yv;
+    if (y) yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = g.v[e];
+      if (d.act == SGB_ACT_RELU) {
+        const float pre = y ? yv.v[e] : fmaf(xv.v[e], r[2][e], r[3][e]);  // same FMA as the forward pass
+        dz = pre > 0.f ? dz : 0.f;
+      }
+      acc[0][e] += dz;
+      acc[1][e] = fmaf(dz, (xv.v[e] - r[0][e]) * r[1][e], acc[1][e]);
+    }
+  }
+};
+
+// coefficient rows: 0 mean, 1 rstd, 2 scale, 3 shift, 4 m0 (mean dz), 5 m1 (mean dz*xhat)
+struct BnBwdApplyOp {
+  static constexpr int NCOEF = 6, NACC = 0;
+  SgbBnDesc d;
+  const bf16 *dy, *x, *y;
+  const float *gamma, *beta, *mean, *rstd;
+  const double* sums;
+  bf16 *dx, *dres;
+  float *dgamma, *dbeta;
+  double* out = nullptr;
+  int out_stride = 0;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+      sc[c] = mean[c];
+      sc[C + c] = rstd[c];
+      sc[2 * C + c] = g * rstd[c];
+      sc[3 * C + c] = b - mean[c] * g * rstd[c];
+      sc[4 * C + c] = (float)(sums[c] / (double)d.M);
+      sc[5 * C + c] = (float)(sums[C + c] / (double)d.M);
+      if (blockIdx.x == 0) {
+        if (dgamma) dgamma[c] += (float)sums[C + c];
+        if (dbeta) dbeta[c] += (float)sums[c];
+      }
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[6][8], float (&)[1][8]) const {
+    const V8 g = ld8(dy + pix * d.y_pitch + d.y_off + c0), xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    V8 yv;
+    if (y) yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
+    V8 o, dr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = g.v[e];
+      if (d.act == SGB_ACT_RELU) {
+        const float pre = y ? yv.v[e] : fmaf(xv.v[e], r[2][e], r[3][e]);
+        dz = pre > 0.f ? dz : 0.f;
+      }
+      const float xh = (xv.v[e] - r[0][e]) * r[1][e];
+      o.v[e] = r[2][e] * (dz - r[4][e] - xh * r[5][e]);
+      dr.v[e] = dz;
+    }
+    st8(dx + pix * d.x_pitch + d.x_off + c0, o);
+    if (dres) st8(dres + pix * d.r_pitch + d.r_off + c0, dr);
+  }
+};
+
+// ============================================================================================== QARepVGG algebra
+// y3 = conv3x3(x) (raw), u = conv1x1_{alpha*K1 + I}(x) (raw);  z = s3*(y3 - mu3) + beta3 + u + alpha*b1;
+// out = act(post_bn(z)) = act(a3*y3 + au*u + c0).  See include/sgb200.h for the coefficient / moment layout.
+struct QarepFwdOp {
+  static constexpr int NCOEF = 3, NACC = 0;
+  SgbQarepDesc d;
+  const bf16 *y3, *u;
+  bf16* outp;
+  const double* mom;
+  const float *gamma3, *beta3, *ab, *gamma_p, *beta_p;
+  float *rm3, *rv3, *rmp, *rvp, *coef;
+  double* out = nullptr;
+  int out_stride = 0;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    const double M = (double)d.M;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      const double S3 = mom[c], S33 = mom[C + c], Su = mom[2 * C + c], Suu = mom[3 * C + c], S3u = mom[4 * C + c];
+      const double mu3 = S3 / M;
+      double var3 = S33 / M - mu3 * mu3;
+      if (var3 < 0) var3 = 0;
+      const double muu = Su / M;
+      double varu = Suu / M - muu * muu;
+      if (varu < 0) varu = 0;
+      const double cov = S3u / M - mu3 * muu;
+      const double rstd3 = 1.0 / sqrt(var3 + (double)d.eps3);
+      const double g3 = gamma3[c], b3 = beta3[c], abc = ab ? ab[c] : 0.0;
+      const double s3 = g3 * rstd3;
+      const double muz = b3 + muu + abc;
+      double varz = s3 * s3 * var3 + varu + 2.0 * s3 * cov;
+      if (varz < 0) varz = 0;
+      double a3, au, c0, rstdz = 1.0, czy = 0.0;
+      if (d.use_post_bn) {
+        rstdz = 1.0 / sqrt(varz + (double)d.eps_post);
+        const double gp = gamma_p[c], bp = beta_p[c];
+        a3 = gp * rstdz * s3;
+        au = gp * rstdz;
+        c0 = gp * rstdz * (-s3 * mu3 - muu) + bp;
+        czy = (s3 * var3 + cov) * rstdz * rstd3;
+      } else {
+        a3 = s3;
+        au = 1.0;
+        c0 = b3 + abc - s3 * mu3;
+      }
+      sc[c] = (float)a3;
+      sc[C + c] = (float)au;
+      sc[2 * C + c] = (float)c0;
+      if (blockIdx.x == 0) {
+        coef[c] = (float)mu3;
+        coef[C + c] = (float)rstd3;
+        coef[2 * C + c] = (float)muu;
+        coef[3 * C + c] = (float)rstdz;
+        coef[4 * C + c] = (float)a3;
+        coef[5 * C + c] = (float)au;
+        coef[6 * C + c] = (float)c0;
+        coef[7 * C + c] = (float)czy;
+        coef[8 * C + c] = (float)s3;
+        const double unb = d.M > 1 ? M / (M - 1.0) : 1.0;
+        if (rm3) {
+          rm3[c] = (1.f - d.momentum) * rm3[c] + d.momentum * (float)mu3;
+          rv3[c] = (1.f - d.momentum) * rv3[c] + d.momentum * (float)(var3 * unb);
+        }
+        if (d.use_post_bn && rmp) {
+          rmp[c] = (1.f - d.momentum) * rmp[c] + d.momentum * (float)muz;
+          rvp[c] = (1.f - d.momentum) * rvp[c] + d.momentum * (float)(varz * unb);
+        }
+      }
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[3][8], float (&)[1][8]) const {
+    V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
+    const V8 b = ld8(u + pix * d.pitchu + d.offu + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(r[0][e], a.v[e], fmaf(r[1][e], b.v[e], r[2][e])), d.act);
+    st8(outp + pix * d.pitcho + d.offo + c0, a);
+  }
+};
+
+// coefficient rows: 0 mu3, 1 rstd3, 2 mu_u, 3 rstd_z, 4 a3, 5 au, 6 c0, 7 s3
+struct QarepBwdRedOp {
+  static constexpr int NCOEF = 8, NACC = 3;
+  SgbQarepDesc d;
+  const bf16 *dout, *y3, *u;
+  const float* coef;  // [9][C] written by the forward
+  double* out;
+  int out_stride;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      sc[c] = coef[c];
+      sc[C + c] = coef[C + c];
+      sc[2 * C + c] = coef[2 * C + c];
+      sc[3 * C + c] = coef[3 * C + c];
+      sc[4 * C + c] = coef[4 * C + c];
+      sc[5 * C + c] = coef[5 * C + c];
+      sc[6 * C + c] = coef[6 * C + c];
+      sc[7 * C + c] = coef[8 * C + c];
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[8][8], float (&acc)[3][8]) const {
+    const V8 g = ld8(dout + pix * d.pitcho + d.offo + c0);
+    const V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + c0), b = ld8(u + pix * d.pitchu + d.offu + c0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dz = g.v[e];
+      if (d.act == SGB_ACT_RELU) dz = fmaf(r[4][e], a.v[e], fmaf(r[5][e], b.v[e], r[6][e])) > 0.f ? dz : 0.f;
+      const float y3c = a.v[e] - r[0][e];
+      acc[0][e] += dz;
+      if (d.use_post_bn) acc[1][e] = fmaf(dz, (fmaf(r[7][e], y3c, b.v[e] - r[2][e])) * r[3][e], acc[1][e]);
+      acc[2][e] = fmaf(dz, y3c * r[1][e], acc[2][e]);
+    }
+  }
+};
+
+// coefficient rows: 0 mu3, 1 rstd3, 2 mu_u, 3 rstd_z, 4 a3, 5 au, 6 c0, 7 s3, 8 g (= gamma_p*rstd_z or 1), 9 m0, 10 m1, 11 q
+struct QarepBwdApplyOp {
+  static constexpr int NCOEF = 12, NACC = 0;
+  SgbQarepDesc d;
+  const bf16 *dout, *y3, *u;
+  const float* coef;
+  const double* sums;
+  const float *gamma3, *gamma_p;
+  bf16 *dy3, *du;
+  float *dgamma3, *dbeta3, *dab, *dgamma_p, *dbeta_p;
+  double* out = nullptr;
+  int out_stride = 0;
+  __device__ void prologue(float* sc) const {
+    const int C = d.C;
+    const double M = (double)d.M;
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      const float rstdz = coef[3 * C + c], czy = coef[7 * C + c];
+      const double T0 = sums[c], T1 = sums[C + c], T2 = sums[2 * C + c];
+      const float m0 = (float)(T0 / M), m2 = (float)(T2 / M);
+      float m1 = (float)(T1 / M), g, q;
+      if (d.use_post_bn) {
+        g = gamma_p[c] * rstdz;
+        q = g * (m2 - m1 * czy);
+      } else {
+        g = 1.f;
+        q = m2;
+        m1 = 0.f;
+      }
+      sc[c] = coef[c];
+      sc[C + c] = coef[C + c];
+      sc[2 * C + c] = coef[2 * C + c];
+      sc[3 * C + c] = rstdz;
+      sc[4 * C + c] = coef[4 * C + c];
+      sc[5 * C + c] = coef[5 * C + c];
+      sc[6 * C + c] = coef[6 * C + c];
+      sc[7 * C + c] = coef[8 * C + c];
+      sc[8 * C + c] = g;
+      sc[9 * C + c] = m0;
+      sc[10 * C + c] = m1;
+      sc[11 * C + c] = q;
+      if (blockIdx.x == 0) {
+        if (d.use_post_bn) {
+          if (dgamma_p) dgamma_p[c] += (float)T1;
+          if (dbeta_p) dbeta_p[c] += (float)T0;
+          if (dgamma3) dgamma3[c] += (float)(M * (double)q);
+          // dbeta3 and d(alpha*b1) are exactly zero: post_bn removes any per-channel constant.
+        } else {
+          if (dgamma3) dgamma3[c] += (float)T2;
+          if (dbeta3) dbeta3[c] += (float)T0;
+          if (dab) dab[c] += (float)T0;
+        }
+      }
+    }
+  }
+  __device__ void apply(int64_t pix, int c0, const float (&r)[12][8], float (&)[1][8]) const {
+    const V8 g = ld8(dout + pix * d.pitcho + d.offo + c0);
+    const V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + c0), b = ld8(u + pix * d.pitchu + d.offu + c0);
+    V8 o3, ou;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float dzp = g.v[e];
+      if (d.act == SGB_ACT_RELU) dzp = fmaf(r[4][e], a.v[e], fmaf(r[5][e], b.v[e], r[6][e])) > 0.f ? dzp : 0.f;
+      const float y3c = a.v[e] - r[0][e];
+      const float y3h = y3c * r[1][e];
+      float dz;
+      if (d.use_post_bn) {
+        const float zh = fmaf(r[7][e], y3c, b.v[e] - r[2][e]) * r[3][e];
+        dz = r[8][e] * (dzp - r[9][e] - zh * r[10][e]);
+        o3.v[e] = r[7][e] * (dz - y3h * r[11][e]);
+      } else {
+        dz = dzp;
+        o3.v[e] = r[7][e] * (dz - r[9][e] - y3h * r[11][e]);
+      }
+      ou.v[e] = dz;
+    }
+    st8(dy3 + pix * d.pitch3 + d.off3 + c0, o3);
+    st8(du + pix * d.pitchu + d.offu + c0, ou);
+  }
+};
+
+int check_bn(const SgbBnDesc* d) {
+  SGB_REQUIRE(d && d->M > 0 && d->C > 0, "bad desc");
+  SGB_REQUIRE(d->C % 8 == 0, "C must be a multiple of 8");
+  SGB_REQUIRE(d->x_pitch % 8 == 0 && d->x_off % 8 == 0 && d->y_pitch % 8 == 0 && d->y_off % 8 == 0,
+              "pitch/offset multiples of 8");
+  SGB_REQUIRE(d->C <= 4096, "C too large for the shared-memory coefficient cache");
+  return SGB_OK;
+}
+int check_qarep(const SgbQarepDesc* d) {
+  SGB_REQUIRE(d && d->M > 0 && d->C > 0 && d->C % 8 == 0 && d->C <= 2048, "bad desc");
+  SGB_REQUIRE(d->pitch3 % 8 == 0 && d->off3 % 8 == 0 && d->pitchu % 8 == 0 && d->offu % 8 == 0 &&
+                  d->pitcho % 8 == 0 && d->offo % 8 == 0,
+              "pitch/offset multiples of 8");
+  return SGB_OK;
+}
+
+}  // namespace
+
+extern "C" int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, const sgb_bf16* residual,
+                              sgb_bf16* y, float* save_mean, float* save_rstd, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(x && stats && y && save_mean && save_rstd, "null pointer");
+  SGB_REQUIRE(d->stats_repl >= 1, "stats_repl");
+  BnFwdOp op{*d, (const bf16*)x, (const bf16*)residual, (bf16*)y, stats, gamma, beta, running_mean, running_var, save_mean, save_rstd};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_fwd");
+}
+
+extern "C" int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const float* gamma, const float* beta,
+                                const float* running_mean, const float* running_var, const sgb_bf16* residual,
+                                sgb_bf16* y, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(x && y && running_mean && running_var, "null pointer");
+  BnInferOp op{*d, (const bf16*)x, (const bf16*)residual, (bf16*)y, gamma, beta, running_mean, running_var};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_infer");
+}
+
+extern "C" int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
+                                     const float* gamma, const float* beta, const float* save_mean,
+                                     const float* save_rstd, double* sums, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums, "null pointer");
+  BnBwdRedOp op{*d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean, save_rstd, gamma, beta, sums, d->C};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_bwd_reduce");
+}
+
+extern "C" int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
+                                    const float* gamma, const float* beta, const float* save_mean,
+                                    const float* save_rstd, const double* sums, sgb_bf16* dx, sgb_bf16* dresidual,
+                                    float* dgamma, float* dbeta, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums && dx, "null pointer");
+  BnBwdApplyOp op{*d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, beta, save_mean, save_rstd, sums, (bf16*)dx, (bf16*)dresidual, dgamma, dbeta};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_bwd_apply");
+}
+
+extern "C" int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, const double* moments,
+                             const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
+                             const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out,
+                             float* coef, void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(y3 && u && moments && gamma3 && beta3 && out && coef, "null pointer");
+  SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
+  QarepFwdOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd");
+}
+
+extern "C" int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,
+                                    const sgb_bf16* y3, const sgb_bf16* u, const float* coef, double* sums,
+                                    void* stream) {
+  (void)out;
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(dout && y3 && u && coef && sums, "null pointer");
+  QarepBwdRedOp op{*d, (const bf16*)dout, (const bf16*)y3, (const bf16*)u, coef, sums, d->C};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_bwd_reduce");
+}
+
+extern "C" int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,
+                                   const sgb_bf16* y3, const sgb_bf16* u, const float* coef, const double* sums,
+                                   const float* gamma3, const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du,
+                                   float* dgamma3, float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p,
+                                   void* stream) {
+  (void)out;
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(dout && y3 && u && coef && sums && gamma3 && dy3 && du, "null pointer");
+  SGB_REQUIRE(!d->use_post_bn || gamma_p, "gamma_p missing");
+  QarepBwdApplyOp op{*d, (const bf16*)dout, (const bf16*)y3, (const bf16*)u, coef, sums, gamma3, gamma_p, (bf16*)dy3, (bf16*)du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p};
+  return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_bwd_apply");
+}

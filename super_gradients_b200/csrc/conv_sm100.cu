@@ -481,6 +481,7 @@ struct WParams {
   int cpad;            // channel count of the KRSC output rows (x channels incl. padding)
   float* dw;
   int tmem_cols;
+  int dbg;  // SGB_DEBUG_SKIP (perf experiments): 1 no atomics, 4 no x loads, 8 no dy loads
 };
 constexpr int WPIX = 64;  // pixels (GEMM K) per pipeline stage
 
@@ -549,17 +550,25 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           const int stg = it % p.stages;
           mbar_wait(empty_bar(stg), ((it / p.stages) & 1) ^ 1);
           const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
-          mbar_expect_tx(full_bar(stg), a_bytes + (uint32_t)(ntaps * boxes_per_tap) * b_box);
+          mbar_expect_tx(full_bar(stg), ((p.dbg & 8) ? 0u : a_bytes) + ((p.dbg & 4) ? 0u : (uint32_t)(ntaps * boxes_per_tap) * b_box) +
+                                            ((p.dbg & 12) == 12 ? 16u : 0u));
           const int pix = pix0 + it * WPIX;
-          tma_load_2d(sa, &map_dy, full_bar(stg), ktile * 128, pix);
-          tma_load_2d(sa + WPIX * 128, &map_dy, full_bar(stg), ktile * 128 + 64, pix);
+          if (!(p.dbg & 8)) {
+            tma_load_2d(sa, &map_dy, full_bar(stg), ktile * 128, pix);
+            tma_load_2d(sa + WPIX * 128, &map_dy, full_bar(stg), ktile * 128 + 64, pix);
+          }
+          if ((p.dbg & 12) == 12) {  // keep the barrier protocol alive with a 16-byte dummy transfer
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];" ::"r"(sa),
+                         "l"(p.dw), "r"(full_bar(stg))
+                         : "memory");
+          }
           const int n_img = pix / pq;
           const int rem = pix - n_img * pq;
           const int p0 = rem / p.Q, q0 = rem - p0 * p.Q;
           const int w0 = q0 * p.stride - p.pad, h0 = p0 * p.stride - p.pad;
           for (int t = 0; t < ntaps; ++t) {
             const int tap = tap0 + t, r = tap / p.S, s = tap - r * p.S;
-            for (int bx = 0; bx < boxes_per_tap; ++bx)
+            for (int bx = 0; bx < boxes_per_tap && !(p.dbg & 4); ++bx)
               tma_load_im2col_4d(sb + (uint32_t)(t * boxes_per_tap + bx) * b_box, &map_x, full_bar(stg),
                                  ctile * p.c_tile + bx * p.CB, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
           }
@@ -604,10 +613,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         for (int c0 = 0; c0 < p.c_tile; c0 += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.c_tile + c0), v);
-          if (ko < p.K) {
-            float* dst = drow + tap * p.cpad + ctile * p.c_tile + c0;
+          if (ko < p.K && !(p.dbg & 1)) {
+            float* dst = drow + tap * p.cpad + ctile * p.c_tile + c0;  // 64-byte aligned: cpad, c_tile, c0 are multiples of 16
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+            for (int i = 0; i < 16; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
+                           "f"(v[i + 3])
+                           : "memory");
           }
         }
       }
@@ -831,6 +843,10 @@ int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
   p.n_ktiles = (q.K + 127) / 128;
   p.cpad = q.C;
   p.dw = q.dw;
+  {
+    const char* e = getenv("SGB_DEBUG_SKIP");
+    p.dbg = e ? atoi(e) : 0;
+  }
   int tc = 32;
   while (tc < p.tpg * p.c_tile) tc <<= 1;
   p.tmem_cols = tc;

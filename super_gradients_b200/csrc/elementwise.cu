@@ -210,342 +210,6 @@ struct QarepMomF {
   }
 };
 
-struct BnBwdRedF {
-  static constexpr int NACC = 2;
-  const bf16 *dy, *x, *y;  // y == nullptr: the ReLU mask is recomputed from x (no residual), saving one tensor read
-  const float *mean, *rstd, *gamma, *beta;
-  int xp, xo, yp, yo, act;
-  __device__ void eval(int64_t pix, int c0, float (&acc)[2][8]) const {
-    V8 g = ld8(dy + pix * yp + yo + c0), xv = ld8(x + pix * xp + xo + c0), yv;
-    if (y) yv = ld8(y + pix * yp + yo + c0);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float dz = g.v[e];
-      float xh = (xv.v[e] - mean[c0 + e]) * rstd[c0 + e];
-      if (act == SGB_ACT_RELU) {
-        float pre = y ? yv.v[e] : xh * (gamma ? gamma[c0 + e] : 1.f) + (beta ? beta[c0 + e] : 0.f);
-        dz = pre > 0.f ? dz : 0.f;
-      }
-      acc[0][e] += dz;
-      acc[1][e] += dz * xh;
-    }
-  }
-};
-
-struct QarepBwdRedF {
-  static constexpr int NACC = 3;
-  const bf16 *dout, *out, *y3, *u;
-  const float* coef;  // [8][C]
-  int C, p3, o3, pu, ou, po, oo, act, post;
-  __device__ void eval(int64_t pix, int c0, float (&acc)[3][8]) const {
-    V8 g = ld8(dout + pix * po + oo + c0);
-    V8 a = ld8(y3 + pix * p3 + o3 + c0), b = ld8(u + pix * pu + ou + c0);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int c = c0 + e;
-      float dz = g.v[e];
-      // ReLU mask recomputed from the saved coefficients: out = act(a3*y3 + au*u + c0)
-      if (act == SGB_ACT_RELU) dz = (coef[4 * C + c] * a.v[e] + coef[5 * C + c] * b.v[e] + coef[6 * C + c]) > 0.f ? dz : 0.f;
-      float mu3 = coef[c], rstd3 = coef[C + c], muu = coef[2 * C + c], rstdz = coef[3 * C + c];
-      float s3 = coef[8 * C + c];  // gamma3 * rstd3
-      float y3h = (a.v[e] - mu3) * rstd3;
-      float zh = (s3 * (a.v[e] - mu3) + b.v[e] - muu) * rstdz;
-      acc[0][e] += dz;
-      acc[1][e] += post ? dz * zh : 0.f;
-      acc[2][e] += dz * y3h;
-    }
-  }
-};
-
-// ---------------------------------------------------------------------------------------------- BatchNorm forward
-struct BnCoef {
-  float scale, shift;
-};
-
-__global__ void __launch_bounds__(TPB) bn_act_fwd_kernel(SgbBnDesc d, const bf16* __restrict__ x, const double* stats,
-                                                         const float* gamma, const float* beta, float* rmean,
-                                                         float* rvar, const bf16* __restrict__ res, bf16* y,
-                                                         float* save_mean, float* save_rstd) {
-  extern __shared__ float sc[];  // [2][C]
-  const int C = d.C;
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    double s1 = 0, s2 = 0;
-    for (int r = 0; r < d.stats_repl; ++r) {
-      s1 += stats[(int64_t)r * 2 * C + c];
-      s2 += stats[(int64_t)r * 2 * C + C + c];
-    }
-    double mean = s1 / (double)d.M;
-    double var = s2 / (double)d.M - mean * mean;
-    if (var < 0) var = 0;
-    float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
-    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-    sc[c] = g * rstd;
-    sc[C + c] = b - (float)mean * g * rstd;
-    if (blockIdx.x == 0) {
-      save_mean[c] = (float)mean;
-      save_rstd[c] = rstd;
-      if (rmean) {
-        double unb = d.M > 1 ? var * (double)d.M / (double)(d.M - 1) : var;
-        rmean[c] = (1.f - d.momentum) * rmean[c] + d.momentum * (float)mean;
-        rvar[c] = (1.f - d.momentum) * rvar[c] + d.momentum * (float)unb;
-      }
-    }
-  }
-  __syncthreads();
-  const int cvs = C / 8;
-  const int64_t total = d.M * cvs;
-  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
-    int cv = i % cvs;
-    int64_t pix = i / cvs;
-    V8 a = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
-    V8 r;
-    if (res) r = ld8(res + pix * d.r_pitch + d.r_off + cv * 8);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = a.v[e] * sc[cv * 8 + e] + sc[C + cv * 8 + e];
-      if (res) v += r.v[e];
-      a.v[e] = apply_act(v, d.act);
-    }
-    st8(y + pix * d.y_pitch + d.y_off + cv * 8, a);
-  }
-}
-
-__global__ void __launch_bounds__(TPB) bn_act_infer_kernel(SgbBnDesc d, const bf16* __restrict__ x, const float* gamma,
-                                                           const float* beta, const float* rmean, const float* rvar,
-                                                           const bf16* __restrict__ res, bf16* y) {
-  extern __shared__ float sc[];
-  const int C = d.C;
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    float rstd = rsqrtf(rvar[c] + d.eps);
-    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-    sc[c] = g * rstd;
-    sc[C + c] = b - rmean[c] * g * rstd;
-  }
-  __syncthreads();
-  const int cvs = C / 8;
-  const int64_t total = d.M * cvs;
-  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
-    int cv = i % cvs;
-    int64_t pix = i / cvs;
-    V8 a = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
-    V8 r;
-    if (res) r = ld8(res + pix * d.r_pitch + d.r_off + cv * 8);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = a.v[e] * sc[cv * 8 + e] + sc[C + cv * 8 + e];
-      if (res) v += r.v[e];
-      a.v[e] = apply_act(v, d.act);
-    }
-    st8(y + pix * d.y_pitch + d.y_off + cv * 8, a);
-  }
-}
-
-__global__ void __launch_bounds__(TPB) bn_act_bwd_apply_kernel(SgbBnDesc d, const bf16* __restrict__ dy,
-                                                               const bf16* __restrict__ x, const bf16* __restrict__ y,
-                                                               const float* gamma, const float* beta,
-                                                               const float* mean, const float* rstd,
-                                                               const double* sums, bf16* dx, bf16* dres, float* dgamma,
-                                                               float* dbeta) {
-  extern __shared__ float sc[];  // [7][C]: mean, rstd, m0 (mean dz), m1 (mean dz*xhat), g*rstd, g, beta
-  const int C = d.C;
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    float g = gamma ? gamma[c] : 1.f;
-    float m0 = (float)(sums[c] / (double)d.M), m1 = (float)(sums[C + c] / (double)d.M);
-    sc[c] = mean[c];
-    sc[C + c] = rstd[c];
-    sc[2 * C + c] = m0;
-    sc[3 * C + c] = m1;
-    sc[4 * C + c] = g * rstd[c];
-    sc[5 * C + c] = g;
-    sc[6 * C + c] = beta ? beta[c] : 0.f;
-    if (blockIdx.x == 0) {
-      if (dgamma) dgamma[c] += (float)sums[C + c];
-      if (dbeta) dbeta[c] += (float)sums[c];
-    }
-  }
-  __syncthreads();
-  const int cvs = C / 8;
-  const int64_t total = d.M * cvs;
-  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
-    int cv = i % cvs;
-    int64_t pix = i / cvs;
-    V8 g = ld8(dy + pix * d.y_pitch + d.y_off + cv * 8);
-    V8 xv = ld8(x + pix * d.x_pitch + d.x_off + cv * 8);
-    V8 yv;
-    if (y) yv = ld8(y + pix * d.y_pitch + d.y_off + cv * 8);
-    V8 o, dr;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int c = cv * 8 + e;
-      float dz = g.v[e];
-      float xh = (xv.v[e] - sc[c]) * sc[C + c];
-      if (d.act == SGB_ACT_RELU) {
-        float pre = y ? yv.v[e] : xh * sc[5 * C + c] + sc[6 * C + c];
-        dz = pre > 0.f ? dz : 0.f;
-      }
-      o.v[e] = sc[4 * C + c] * (dz - sc[2 * C + c] - xh * sc[3 * C + c]);
-      dr.v[e] = dz;
-    }
-    st8(dx + pix * d.x_pitch + d.x_off + cv * 8, o);
-    if (dres) st8(dres + pix * d.r_pitch + d.r_off + cv * 8, dr);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------- QARepVGG algebra
-__global__ void __launch_bounds__(TPB) qarep_fwd_kernel(SgbQarepDesc d, const bf16* __restrict__ y3,
-                                                        const bf16* __restrict__ u, const double* mom,
-                                                        const float* gamma3, const float* beta3, const float* ab,
-                                                        const float* gamma_p, const float* beta_p, float* rm3,
-                                                        float* rv3, float* rmp, float* rvp, bf16* out, float* coef) {
-  extern __shared__ float sc[];  // [3][C]: a3, au, c0
-  const int C = d.C;
-  const double M = (double)d.M;
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    double S3 = mom[c], S33 = mom[C + c], Su = mom[2 * C + c], Suu = mom[3 * C + c], S3u = mom[4 * C + c];
-    double mu3 = S3 / M, var3 = S33 / M - mu3 * mu3;
-    if (var3 < 0) var3 = 0;
-    double muu = Su / M, varu = Suu / M - muu * muu, cov = S3u / M - mu3 * muu;
-    if (varu < 0) varu = 0;
-    double rstd3 = 1.0 / sqrt(var3 + (double)d.eps3);
-    double g3 = gamma3[c], b3 = beta3[c], abc = ab ? ab[c] : 0.0;
-    double s3 = g3 * rstd3;
-    double muz = b3 + muu + abc;
-    double varz = s3 * s3 * var3 + varu + 2.0 * s3 * cov;
-    if (varz < 0) varz = 0;
-    double a3, au, c0, rstdz = 1.0, czy = 0.0;
-    if (d.use_post_bn) {
-      rstdz = 1.0 / sqrt(varz + (double)d.eps_post);
-      double gp = gamma_p[c], bp = beta_p[c];
-      a3 = gp * rstdz * s3;
-      au = gp * rstdz;
-      c0 = gp * rstdz * (-s3 * mu3 - muu) + bp;
-      czy = (s3 * var3 + cov) * rstdz * rstd3;
-    } else {
-      a3 = s3;
-      au = 1.0;
-      c0 = b3 + abc - s3 * mu3;
-    }
-    sc[c] = (float)a3;
-    sc[C + c] = (float)au;
-    sc[2 * C + c] = (float)c0;
-    if (blockIdx.x == 0) {
-      coef[c] = (float)mu3;
-      coef[C + c] = (float)rstd3;
-      coef[2 * C + c] = (float)muu;
-      coef[3 * C + c] = (float)rstdz;
-      coef[4 * C + c] = (float)a3;
-      coef[5 * C + c] = (float)au;
-      coef[6 * C + c] = (float)c0;
-      coef[7 * C + c] = (float)czy;
-      coef[8 * C + c] = (float)s3;
-      double unb = d.M > 1 ? M / (M - 1.0) : 1.0;
-      if (rm3) {
-        rm3[c] = (1.f - d.momentum) * rm3[c] + d.momentum * (float)mu3;
-        rv3[c] = (1.f - d.momentum) * rv3[c] + d.momentum * (float)(var3 * unb);
-      }
-      if (d.use_post_bn && rmp) {
-        rmp[c] = (1.f - d.momentum) * rmp[c] + d.momentum * (float)muz;
-        rvp[c] = (1.f - d.momentum) * rvp[c] + d.momentum * (float)(varz * unb);
-      }
-    }
-  }
-  __syncthreads();
-  const int cvs = C / 8;
-  const int64_t total = d.M * cvs;
-  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
-    int cv = i % cvs;
-    int64_t pix = i / cvs;
-    V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + cv * 8), b = ld8(u + pix * d.pitchu + d.offu + cv * 8);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int c = cv * 8 + e;
-      a.v[e] = apply_act(sc[c] * a.v[e] + sc[C + c] * b.v[e] + sc[2 * C + c], d.act);
-    }
-    st8(out + pix * d.pitcho + d.offo + cv * 8, a);
-  }
-}
-
-__global__ void __launch_bounds__(TPB) qarep_bwd_apply_kernel(SgbQarepDesc d, const bf16* __restrict__ dout,
-                                                              const bf16* __restrict__ out,
-                                                              const bf16* __restrict__ y3, const bf16* __restrict__ u,
-                                                              const float* coef, const double* sums,
-                                                              const float* gamma3, const float* gamma_p, bf16* dy3,
-                                                              bf16* du, float* dgamma3, float* dbeta3, float* dab,
-                                                              float* dgamma_p, float* dbeta_p) {
-  extern __shared__ float sc[];  // [8][C]: mu3, rstd3, muu, rstdz, s3, g, m0, m1 ; q in [8]
-  const int C = d.C;
-  const double M = (double)d.M;
-  for (int c = threadIdx.x; c < C; c += TPB) {
-    float mu3 = coef[c], rstd3 = coef[C + c], muu = coef[2 * C + c], rstdz = coef[3 * C + c], czy = coef[7 * C + c];
-    float s3 = gamma3[c] * rstd3;
-    double T0 = sums[c], T1 = sums[C + c], T2 = sums[2 * C + c];
-    float m0 = (float)(T0 / M), m1 = (float)(T1 / M), m2 = (float)(T2 / M);
-    float g, q;
-    if (d.use_post_bn) {
-      g = gamma_p[c] * rstdz;
-      q = g * (m2 - m1 * czy);
-    } else {
-      g = 1.f;
-      q = m2;
-      m1 = 0.f;
-    }
-    sc[c] = mu3;
-    sc[C + c] = rstd3;
-    sc[2 * C + c] = muu;
-    sc[3 * C + c] = rstdz;
-    sc[4 * C + c] = s3;
-    sc[5 * C + c] = g;
-    sc[6 * C + c] = m0;
-    sc[7 * C + c] = m1;
-    sc[8 * C + c] = q;
-    sc[9 * C + c] = coef[4 * C + c];
-    sc[10 * C + c] = coef[5 * C + c];
-    sc[11 * C + c] = coef[6 * C + c];
-    if (blockIdx.x == 0) {
-      if (d.use_post_bn) {
-        if (dgamma_p) dgamma_p[c] += (float)T1;
-        if (dbeta_p) dbeta_p[c] += (float)T0;
-        if (dgamma3) dgamma3[c] += (float)(M * (double)q);
-        // dbeta3 and d(alpha*b1) are exactly zero: post_bn removes any per-channel constant.
-      } else {
-        if (dgamma3) dgamma3[c] += (float)T2;
-        if (dbeta3) dbeta3[c] += (float)T0;
-        if (dab) dab[c] += (float)T0;
-      }
-    }
-  }
-  __syncthreads();
-  const int cvs = C / 8;
-  const int64_t total = d.M * cvs;
-  for (int64_t i = blockIdx.x * (int64_t)TPB + threadIdx.x; i < total; i += (int64_t)gridDim.x * TPB) {
-    int cv = i % cvs;
-    int64_t pix = i / cvs;
-    V8 g = ld8(dout + pix * d.pitcho + d.offo + cv * 8);
-    V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + cv * 8), b = ld8(u + pix * d.pitchu + d.offu + cv * 8);
-    V8 o3, ou;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int c = cv * 8 + e;
-      float dzp = g.v[e];
-      if (d.act == SGB_ACT_RELU) dzp = (sc[9 * C + c] * a.v[e] + sc[10 * C + c] * b.v[e] + sc[11 * C + c]) > 0.f ? dzp : 0.f;
-      float mu3 = sc[c], rstd3 = sc[C + c], s3 = sc[4 * C + c];
-      float y3h = (a.v[e] - mu3) * rstd3;
-      float dz;
-      if (d.use_post_bn) {
-        float zh = (s3 * (a.v[e] - mu3) + b.v[e] - sc[2 * C + c]) * sc[3 * C + c];
-        dz = sc[5 * C + c] * (dzp - sc[6 * C + c] - zh * sc[7 * C + c]);
-        o3.v[e] = s3 * (dz - y3h * sc[8 * C + c]);
-      } else {
-        dz = dzp;
-        o3.v[e] = s3 * (dz - sc[6 * C + c] - y3h * sc[8 * C + c]);
-      }
-      ou.v[e] = dz;
-    }
-    st8(dy3 + pix * d.pitch3 + d.off3 + cv * 8, o3);
-    st8(du + pix * d.pitchu + d.offu + cv * 8, ou);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------- pooling etc.
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int xp, int xo, int k,
                                    int stride, int pad, bf16* y, int P, int Q, int yp, int yo, uint8_t* idx) {
@@ -762,65 +426,6 @@ extern "C" int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H,
   return SGB_OK;
 }
 
-static int check_bn(const SgbBnDesc* d) {
-  SGB_REQUIRE(d && d->M > 0 && d->C > 0, "bad desc");
-  SGB_REQUIRE(d->C % 8 == 0, "C must be a multiple of 8");
-  SGB_REQUIRE(d->x_pitch % 8 == 0 && d->x_off % 8 == 0 && d->y_pitch % 8 == 0 && d->y_off % 8 == 0,
-              "pitch/offset multiples of 8");
-  SGB_REQUIRE(d->C <= 4096, "C too large for the shared-memory coefficient cache");
-  return SGB_OK;
-}
-
-extern "C" int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, const float* gamma,
-                              const float* beta, float* running_mean, float* running_var, const sgb_bf16* residual,
-                              sgb_bf16* y, float* save_mean, float* save_rstd, void* stream) {
-  if (int rc = check_bn(d)) return rc;
-  SGB_REQUIRE(x && stats && y && save_mean && save_rstd, "null pointer");
-  SGB_REQUIRE(d->stats_repl >= 1, "stats_repl");
-  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  bn_act_fwd_kernel<<<grid, TPB, 2 * d->C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const bf16*)x, stats, gamma, beta, running_mean, running_var, (const bf16*)residual, (bf16*)y, save_mean,
-      save_rstd);
-  SGB_LAUNCH_CHECK("bn_act_fwd_kernel");
-  return SGB_OK;
-}
-
-extern "C" int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const float* gamma, const float* beta,
-                                const float* running_mean, const float* running_var, const sgb_bf16* residual,
-                                sgb_bf16* y, void* stream) {
-  if (int rc = check_bn(d)) return rc;
-  SGB_REQUIRE(x && y && running_mean && running_var, "null pointer");
-  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  bn_act_infer_kernel<<<grid, TPB, 2 * d->C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const bf16*)x, gamma, beta, running_mean, running_var, (const bf16*)residual, (bf16*)y);
-  SGB_LAUNCH_CHECK("bn_act_infer_kernel");
-  return SGB_OK;
-}
-
-extern "C" int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
-                                     const float* gamma, const float* beta, const float* save_mean,
-                                     const float* save_rstd, double* sums, void* stream) {
-  if (int rc = check_bn(d)) return rc;
-  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums, "null pointer");
-  BnBwdRedF f{(const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean,  save_rstd, gamma, beta,
-              d->x_pitch,      d->x_off,       d->y_pitch,     d->y_off,   d->act};
-  return launch_chan_reduce(f, d->M, d->C, sums, d->C, (cudaStream_t)stream);
-}
-
-extern "C" int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y,
-                                    const float* gamma, const float* beta, const float* save_mean,
-                                    const float* save_rstd, const double* sums, sgb_bf16* dx, sgb_bf16* dresidual,
-                                    float* dgamma, float* dbeta, void* stream) {
-  if (int rc = check_bn(d)) return rc;
-  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums && dx, "null pointer");
-  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  bn_act_bwd_apply_kernel<<<grid, TPB, 7 * d->C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, beta, save_mean, save_rstd, sums, (bf16*)dx,
-      (bf16*)dresidual, dgamma, dbeta);
-  SGB_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
-  return SGB_OK;
-}
-
 extern "C" int sgb_channel_stats(const sgb_bf16* x, int64_t M, int C, int pitch, int off, double* stats,
                                  void* stream) {
   SGB_REQUIRE(x && stats && M > 0 && C > 0 && C % 8 == 0 && pitch % 8 == 0 && off % 8 == 0, "bad args");
@@ -828,61 +433,12 @@ extern "C" int sgb_channel_stats(const sgb_bf16* x, int64_t M, int C, int pitch,
   return launch_chan_reduce(f, M, C, stats, C, (cudaStream_t)stream);
 }
 
-static int check_qarep(const SgbQarepDesc* d) {
-  SGB_REQUIRE(d && d->M > 0 && d->C > 0 && d->C % 8 == 0 && d->C <= 2048, "bad desc");
-  SGB_REQUIRE(d->pitch3 % 8 == 0 && d->off3 % 8 == 0 && d->pitchu % 8 == 0 && d->offu % 8 == 0 &&
-                  d->pitcho % 8 == 0 && d->offo % 8 == 0,
-              "pitch/offset multiples of 8");
-  return SGB_OK;
-}
-
 extern "C" int sgb_qarep_moments(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments,
                                  void* stream) {
-  if (int rc = check_qarep(d)) return rc;
-  SGB_REQUIRE(y3 && u && moments, "null pointer");
+  SGB_REQUIRE(d && d->M > 0 && d->C > 0 && d->C % 8 == 0 && y3 && u && moments, "bad args");
+  SGB_REQUIRE(d->pitch3 % 8 == 0 && d->off3 % 8 == 0 && d->pitchu % 8 == 0 && d->offu % 8 == 0, "pitch/offset multiples of 8");
   QarepMomF f{(const bf16*)y3, (const bf16*)u, d->pitch3, d->off3, d->pitchu, d->offu};
   return launch_chan_reduce(f, d->M, d->C, moments, d->C, (cudaStream_t)stream);
-}
-
-extern "C" int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, const double* moments,
-                             const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
-                             const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out,
-                             float* coef, void* stream) {
-  if (int rc = check_qarep(d)) return rc;
-  SGB_REQUIRE(y3 && u && moments && gamma3 && beta3 && out && coef, "null pointer");
-  SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
-  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  qarep_fwd_kernel<<<grid, TPB, 3 * d->C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const bf16*)y3, (const bf16*)u, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p,
-      (bf16*)out, coef);
-  SGB_LAUNCH_CHECK("qarep_fwd_kernel");
-  return SGB_OK;
-}
-
-extern "C" int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,
-                                    const sgb_bf16* y3, const sgb_bf16* u, const float* coef, double* sums,
-                                    void* stream) {
-  if (int rc = check_qarep(d)) return rc;
-  SGB_REQUIRE(dout && y3 && u && coef && sums, "null pointer");
-  QarepBwdRedF f{(const bf16*)dout, (const bf16*)out, (const bf16*)y3, (const bf16*)u, coef,      d->C,
-                 d->pitch3,         d->off3,          d->pitchu,       d->offu,        d->pitcho, d->offo,
-                 d->act,            d->use_post_bn};
-  return launch_chan_reduce(f, d->M, d->C, sums, d->C, (cudaStream_t)stream);
-}
-
-extern "C" int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,
-                                   const sgb_bf16* y3, const sgb_bf16* u, const float* coef, const double* sums,
-                                   const float* gamma3, const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du,
-                                   float* dgamma3, float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p,
-                                   void* stream) {
-  if (int rc = check_qarep(d)) return rc;
-  SGB_REQUIRE(dout && y3 && u && coef && sums && gamma3 && dy3 && du, "null pointer");
-  int grid = grid_for(d->M * (d->C / 8), TPB * 4);
-  qarep_bwd_apply_kernel<<<grid, TPB, 12 * d->C * sizeof(float), (cudaStream_t)stream>>>(
-      *d, (const bf16*)dout, (const bf16*)out, (const bf16*)y3, (const bf16*)u, coef, sums, gamma3, gamma_p,
-      (bf16*)dy3, (bf16*)du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p);
-  SGB_LAUNCH_CHECK("qarep_bwd_apply_kernel");
-  return SGB_OK;
 }
 
 extern "C" int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, int x_pitch, int x_off, int k,

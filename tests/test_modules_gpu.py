@@ -186,7 +186,9 @@ def test_tiny_yolo_nas_train_step_and_eval(golden):
     # bf16 activations are amplified by the train-mode BatchNorms of the deep 4x4 / 8x8 maps
     # (tests/test_oracle_golden.py::test_bf16_emulation_sensitivity measures that spread).
     assert l2rel(raw[0], rawe[0]) < 1.5e-2 and l2rel(raw[1], rawe[1]) < 0.13
-    assert l2rel(ps, pse) < 3e-2 and l2rel(pb, pbe) < 2e-2
+    # scores = sigmoid(logit) with logits around the -4.6 prior bias: d(sigmoid)/sigmoid = (1 - sigmoid) * d(logit), so the
+    # RELATIVE score error is the ABSOLUTE logit error, i.e. 1.5e-2 * rms(logit) ~ 7e-2 at the logit tolerance above.
+    assert l2rel(ps, pse) < 7e-2 and l2rel(pb, pbe) < 2e-2
     assert abs(float(loss) - float(losse)) <= 5e-2 * abs(float(losse))
     errs = sorted((l2rel(params[k].grad, pe[k].grad), k) for k in live if pe[k].grad is not None and pe[k].grad.norm() > 1e-6)
     assert errs[len(errs) // 2][0] < 0.15, errs[len(errs) // 2]
