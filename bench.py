@@ -274,7 +274,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         K.PROFILE_ON[0] = False
         per = {}
-        for name, a, b in K.PROFILE:
+        for name, a, b, _tag in K.PROFILE:
             per[name] = per.get(name, 0.0) + a.elapsed_time(b)
         conv_ms = sum(v for k, v in per.items() if k.startswith("sgb_conv")) / n_prof
         flops = TRAIN_GFLOP_PER_IMG * 1e9 * batch

@@ -284,7 +284,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint64_t da = make_smem_desc(sa, p.KC), db = make_smem_desc(sb, p.KC);
           for (int j = 0; j < p.KC / 16; ++j) {
             // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (k | j) != 0);
+            if (!(p.dbg & 8)) umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (k | j) != 0);
           }
           umma_commit(empty_bar(stg));
           if (k == k_iters - 1) umma_commit(tfull_bar(ab));
@@ -736,12 +736,53 @@ int launch(const Problem& q, cudaStream_t st) {
   int tc = 32;
   while (tc < 2 * bn) tc <<= 1;
   p.tmem_cols = tc;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + bn - 1) / bn;
+  const bool plain = !p.scale && !p.shift && !p.residual && p.act == SGB_ACT_NONE && n_tiles == 1 && p.N == bn && !(p.dbg & 2);
+  if (p.ntaps > 9) return SGB_E_UNSUPPORTED;
+  const int nch = plain ? bn / 16 : 0;
+  const bool stats = p.stats != nullptr;
+  // kernel variant + its register footprint (decides how many CTAs can share an SM)
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
+  struct Variant { KernelFn fn; int regs; bool ready; };
+  static Variant variants[9] = {
+      {conv_umma_kernel<0, false>, 0, false}, {conv_umma_kernel<2, false>, 0, false}, {conv_umma_kernel<2, true>, 0, false},
+      {conv_umma_kernel<3, false>, 0, false}, {conv_umma_kernel<3, true>, 0, false},  {conv_umma_kernel<4, false>, 0, false},
+      {conv_umma_kernel<4, true>, 0, false},  {conv_umma_kernel<6, false>, 0, false}, {conv_umma_kernel<6, true>, 0, false}};
+  int vi = 0;
+  if (nch == 2) vi = stats ? 2 : 1;
+  else if (nch == 3) vi = stats ? 4 : 3;
+  else if (nch == 4) vi = stats ? 6 : 5;
+  else if (nch == 6) vi = stats ? 8 : 7;
+  Variant& var = variants[vi];
+  if (!var.ready) {
+    if (int rc = sgb_cuda_check(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                                "cudaFuncSetAttribute(conv_umma_kernel)"))
+      return rc;
+    cudaFuncAttributes fa{};
+    if (int rc = sgb_cuda_check(cudaFuncGetAttributes(&fa, var.fn), "cudaFuncGetAttributes(conv_umma_kernel)")) return rc;
+    var.regs = fa.numRegs;
+    var.ready = true;
+  }
+  // A CTA's pipeline is latency-bound when its k-iterations are small (few channels per tap): co-resident CTAs overlap
+  // each other's TMA / MMA / epilogue chains.  Limits: TMEM columns (512 per SM), registers (64K per SM), shared memory.
   const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = bn * p.KC * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
   const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + 2 * p.N * 4 + 64;
-  const uint32_t budget = 200 * 1024;
-  int stages = (int)((budget - ctrl_bytes - 1024) / stage_bytes);
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  int ctas_per_sm = 3;
+  {
+    const char* e = getenv("SGB_CTAS_PER_SM");
+    if (e) ctas_per_sm = atoi(e);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int regs_alloc = ((var.regs + 7) / 8) * 8 * NUM_THREADS;
+  while (ctas_per_sm > 1 && (ctas_per_sm * tc > 512 || ctas_per_sm * regs_alloc > 65536)) --ctas_per_sm;
+  int stages = 0;
+  for (;; --ctas_per_sm) {
+    const uint32_t budget = (ctas_per_sm == 1 ? 200u : 224u / ctas_per_sm - 2u) * 1024u;
+    stages = budget > ctrl_bytes + 1024 ? (int)((budget - ctrl_bytes - 1024) / stage_bytes) : 0;
+    if (stages > 8) stages = 8;
+    if (stages >= 4 || ctas_per_sm == 1) break;
+  }
   if (stages < 2) { sgb_set_error("conv_sm100: tile does not fit shared memory"); return SGB_E_UNSUPPORTED; }
   p.stages = stages;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + ctrl_bytes;
@@ -780,36 +821,9 @@ int launch(const Problem& q, cudaStream_t st) {
       return SGB_E_CUDA;
     }
   }
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + bn - 1) / bn;
   int grid = m_tiles * n_tiles;
-  if (grid > g_num_sms) grid = g_num_sms;
-  const bool plain = !p.scale && !p.shift && !p.residual && p.act == SGB_ACT_NONE && n_tiles == 1 && p.N == bn && !(p.dbg & 2);
-  if (p.ntaps > 9) return SGB_E_UNSUPPORTED;
-  const int nch = plain ? bn / 16 : 0;
-  int rc = SGB_OK;
-#define SGB_LAUNCH_UMMA(NCH_, ST_)                                                                                   \
-  do {                                                                                                               \
-    static bool attr_ = false;                                                                                       \
-    if (!attr_) {                                                                                                    \
-      rc = sgb_cuda_check(cudaFuncSetAttribute(conv_umma_kernel<NCH_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               227 * 1024),                                                          \
-                          "cudaFuncSetAttribute(conv_umma_kernel)");                                                 \
-      attr_ = true;                                                                                                  \
-    }                                                                                                                \
-    if (rc == SGB_OK) conv_umma_kernel<NCH_, ST_><<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, p);                  \
-  } while (0)
-  const bool stats = p.stats != nullptr;
-  if (nch == 2 && stats) SGB_LAUNCH_UMMA(2, true);
-  else if (nch == 2) SGB_LAUNCH_UMMA(2, false);
-  else if (nch == 3 && stats) SGB_LAUNCH_UMMA(3, true);
-  else if (nch == 3) SGB_LAUNCH_UMMA(3, false);
-  else if (nch == 4 && stats) SGB_LAUNCH_UMMA(4, true);
-  else if (nch == 4) SGB_LAUNCH_UMMA(4, false);
-  else if (nch == 6 && stats) SGB_LAUNCH_UMMA(6, true);
-  else if (nch == 6) SGB_LAUNCH_UMMA(6, false);
-  else SGB_LAUNCH_UMMA(0, false);
-#undef SGB_LAUNCH_UMMA
-  if (rc != SGB_OK) return rc;
+  if (grid > g_num_sms * ctas_per_sm) grid = g_num_sms * ctas_per_sm;
+  var.fn<<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, p);
   ++g_launches;
   return sgb_cuda_check(cudaGetLastError(), "conv_umma_kernel");
 }

@@ -26,7 +26,9 @@ def _timed(name, *args):
     a.record()
     L.call(name, *args)
     b.record()
-    PROFILE.append((name, a, b))
+    d = args[0]._obj if args and hasattr(args[0], "_obj") else None  # ctypes.byref(desc)
+    tag = tuple(getattr(d, f) for f in ("N", "H", "W", "C", "K", "R", "stride") if hasattr(d, f)) if d is not None else ()
+    PROFILE.append((name, a, b, tag))
 
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU}
 

@@ -45,6 +45,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     print(f"sm100 enabled: {os.environ.get('SGB_DISABLE_SM100', '0') != '1'}  mode={which}")
     shapes = SHAPES[: int(os.environ.get('NSHAPES', len(SHAPES)))]
+    if os.environ.get("SHAPES"):
+        shapes = [tuple(int(v) for v in t.split(",")) for t in os.environ["SHAPES"].split(";")]
     for n, c, h, w, k, r, s in shapes:
         pad = r // 2
         x = torch.randn(n, c, h, w, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
@@ -57,7 +59,7 @@ def main():
         bytes_ = 2.0 * (x.numel() + y.numel())
         n0 = lib.load().sgb_sm100_launches()
         if which == "fprop":
-            us = bench(lambda: K.conv_fprop(x, krsc, k, r, r, s, pad, stats=stats, out=y), flush)
+            us = bench(lambda: K.conv_fprop(x, krsc, k, r, r, s, pad, stats=None if os.environ.get('NOSTATS') else stats, out=y), flush)
         elif which == "dgrad":
             dx = torch.empty_like(x)
             us = bench(lambda: K.conv_dgrad(y, crsk, x.shape, r, r, s, pad, out=dx), flush)
