@@ -65,6 +65,12 @@ int sgb_check_device(void);
 /* Number of tcgen05/TMA convolution launches issued by this process so far (evidence that the Blackwell-native path,
  * not the generic mma.sync kernel, served a call). */
 int64_t sgb_sm100_launches(void);
+/* ... of which served by the halo-tile 3x3 kernel (conv_halo_sm100.cu). */
+int64_t sgb_sm100_halo_launches(void);
+
+/* Developer hook: copies the 12 x 512 SM-clock stamps recorded by CTA 0 of the last tcgen05 convolution launched with
+ * SGB_DEBUG_SKIP & 16 into host_out (int64[6144]); used by tools/ to study the TMA / MMA pipeline, never by the product. */
+int sgb_debug_read_trace(int64_t* host_out);
 
 /* ---- convolution family (rows C1-C5, C8, C10 of SURVEY.md section 8a) --------------------------------------
  * replaces nn.Conv2d forward in modules/qarepvgg_block.py:184-204, modules/conv_bn_act_block.py:92-93,

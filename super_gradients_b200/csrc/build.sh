@@ -10,7 +10,9 @@ mkdir -p "$HERE/obj"
 pids=()
 for f in "$HERE"/*.cu; do
   o="$HERE/obj/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$ROOT/include/sgb200.h" -nt "$o" ]]; then
+  stale=0
+  for h in "$HERE"/*.cuh "$HERE"/*.h "$ROOT/include/sgb200.h"; do [[ "$h" -nt "$o" ]] && stale=1; done
+  if [[ ! -f "$o" || "$f" -nt "$o" || $stale -eq 1 ]]; then
     "$NVCC" "${FLAGS[@]}" "$@" -c "$f" -o "$o" &
     pids+=($!)
   fi

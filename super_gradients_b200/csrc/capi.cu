@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "conv_sm100.h"
+#include "sm100_host.h"
 
 static thread_local char g_err[512] = "";
 
@@ -35,3 +36,9 @@ extern "C" int sgb_check_device(void) {
 }
 
 extern "C" int64_t sgb_sm100_launches(void) { return (int64_t)sm100::launch_count(); }
+extern "C" int64_t sgb_sm100_halo_launches(void) { return (int64_t)sm100::halo_launch_count(); }
+
+extern "C" int sgb_debug_read_trace(int64_t* host_out) {
+  if (!host_out) return SGB_E_INVALID;
+  return sm100::read_trace(reinterpret_cast<long long*>(host_out));
+}

@@ -20,6 +20,8 @@
 
 #include "common.cuh"
 #include "conv_sm100.h"
+#include "sm100_host.h"
+#include "sm100_ptx.cuh"
 
 namespace sm100 {
 
@@ -58,132 +60,6 @@ struct Params {
   int dbg;  // SGB_DEBUG_SKIP bit mask (perf experiments only): 1 no stores, 2 no stats, 4 no A loads
 };
 
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
-                                                   int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
-      "{%7, %8};" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of KC bf16, 8-row swizzle atoms.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int kc) {
-  const uint32_t layout = kc == 64 ? 2u : (kc == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
-  const uint32_t sbo = (uint32_t)(8 * kc * 2) >> 4;             // bytes between 8-row groups, in 16 B units
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)1 << 16;          // leading byte offset (ignored for swizzled K-major), canonical value 1
-  d |= (uint64_t)(sbo & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-
-// 32 rows x 16 columns held one row per lane -> column sums; lanes 2j, 2j+1 end with the sum of column col_of_lane().
-__device__ __forceinline__ float butterfly_colsum(const float (&v)[16], int lane) {
-  float w8[8], w4[4], w2[2];
-  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float send = b16 ? v[i] : v[i + 8];
-    float keep = b16 ? v[i + 8] : v[i];
-    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float send = b8 ? w8[i] : w8[i + 4];
-    float keep = b8 ? w8[i + 4] : w8[i];
-    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float send = b4 ? w4[i] : w4[i + 2];
-    float keep = b4 ? w4[i + 2] : w4[i];
-    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  float send = b2 ? w2[0] : w2[1];
-  float keep = b2 ? w2[1] : w2[0];
-  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  return r + __shfl_xor_sync(0xffffffffu, r, 1);
-}
-__device__ __forceinline__ int col_of_lane(int lane) {
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
 __device__ __forceinline__ long long out_row(const Params& p, long long m) {
   if (p.out_mode == 0) return m;
   const int pq = p.P * p.Q;
@@ -192,6 +68,10 @@ __device__ __forceinline__ long long out_row(const Params& p, long long m) {
   const int j = rem / p.Q, i = rem - j * p.Q;
   return ((long long)n * p.outH + j * p.o_mul + p.oh_add) * p.outW + i * p.o_mul + p.ow_add;
 }
+
+// SGB_DEBUG_SKIP & 16: CTA 0 records SM clock stamps of its first 512 k-iterations (perf experiments only):
+// [0] producer passed the empty wait, [1] producer issued its TMA, [2] MMA warp passed the full wait, [3] MMA committed
+__device__ long long g_trace[12][512];
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int NCH, bool STATS>
@@ -240,7 +120,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // ===================================================================================== TMA producer
     if (elect_one()) {
-      int it = 0;
+      int it = 0, stg = 0;
+      uint32_t par = 1;  // parity awaited on the empty barriers: the first pass through the ring is free
       const int pq = p.P * p.Q;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
@@ -253,13 +134,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int r = p.tap_dh[tap], s = p.tap_dw[tap];
           const int btap = p.tap_b[tap];
           for (int ck = 0; ck < chunks; ++ck, ++it) {
-            const int stg = it % p.stages;
-            const uint32_t par = ((it / p.stages) & 1) ^ 1;
             mbar_wait(empty_bar(stg), par);
+            const bool tr = (p.dbg & 16) && blockIdx.x == 0 && it < 512;
+            if (tr) g_trace[0][it] = clock64();
             const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
             mbar_expect_tx(full_bar(stg), ((p.dbg & 4) ? 0u : a_bytes) + b_bytes);
+            if (tr) g_trace[4][it] = clock64();
             if (!(p.dbg & 4)) tma_load_im2col_4d(sa, &map_a, full_bar(stg), ck * p.KC, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+            if (tr) g_trace[5][it] = clock64();
             tma_load_2d(sb, &map_b, full_bar(stg), btap * p.b_cols_per_tap + ck * p.KC, nt * p.BN);
+            if (tr) g_trace[1][it] = clock64();
+            if (++stg == p.stages) {
+              stg = 0;
+              par ^= 1;
+            }
           }
         }
       }
@@ -267,7 +155,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 1) {
     // ===================================================================================== MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-    int it = 0, tcount = 0;
+    int it = 0, tcount = 0, stg = 0;
+    uint32_t par = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
       const uint32_t apar = ((tcount >> 1) & 1) ^ 1;
@@ -275,21 +164,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.BN);
       for (int k = 0; k < k_iters; ++k, ++it) {
-        const int stg = it % p.stages;
-        const uint32_t par = (it / p.stages) & 1;
+        const bool tr0 = (p.dbg & 16) && blockIdx.x == 0 && it < 512 && lane == 0;
+        if (tr0) g_trace[7][it] = clock64();
         mbar_wait(full_bar(stg), par);
+        if (tr0) g_trace[8][it] = clock64();
         tcgen05_fence_after();
+        if (tr0) g_trace[9][it] = clock64();
         if (elect_one()) {
+          const bool tr = (p.dbg & 16) && blockIdx.x == 0 && it < 512;
+          if (tr) g_trace[2][it] = clock64();
           const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
           const uint64_t da = make_smem_desc(sa, p.KC), db = make_smem_desc(sb, p.KC);
           for (int j = 0; j < p.KC / 16; ++j) {
             // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
             if (!(p.dbg & 8)) umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (k | j) != 0);
           }
+          if (tr) g_trace[10][it] = clock64();
           umma_commit(empty_bar(stg));
           if (k == k_iters - 1) umma_commit(tfull_bar(ab));
+          if (tr) g_trace[3][it] = clock64();
         }
         __syncwarp();
+        if (tr0) g_trace[11][it] = clock64();
+        if (++stg == p.stages) {
+          stg = 0;
+          par ^= 1;
+        }
       }
     }
   } else {
@@ -546,9 +446,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     if (warp == 0) {
       if (elect_one()) {
         const int pq = p.P * p.Q;
+        int stg = 0;
+        uint32_t par = 1;
         for (int it = 0; it < n_iters; ++it) {
-          const int stg = it % p.stages;
-          mbar_wait(empty_bar(stg), ((it / p.stages) & 1) ^ 1);
+          mbar_wait(empty_bar(stg), par);
           const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
           mbar_expect_tx(full_bar(stg), ((p.dbg & 8) ? 0u : a_bytes) + ((p.dbg & 4) ? 0u : (uint32_t)(ntaps * boxes_per_tap) * b_box) +
                                             ((p.dbg & 12) == 12 ? 16u : 0u));
@@ -572,6 +473,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
               tma_load_im2col_4d(sb + (uint32_t)(t * boxes_per_tap + bx) * b_box, &map_x, full_bar(stg),
                                  ctile * p.c_tile + bx * p.CB, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
           }
+          if (++stg == p.stages) {
+            stg = 0;
+            par ^= 1;
+          }
         }
       }
     } else if (warp == 1) {
@@ -579,9 +484,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.CB >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const int b_row_bytes = p.CB * 2;
+      int stg = 0;
+      uint32_t par = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int stg = it % p.stages;
-        mbar_wait(full_bar(stg), (it / p.stages) & 1);
+        mbar_wait(full_bar(stg), par);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
@@ -600,6 +506,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           if (it == n_iters - 1) umma_commit(done_bar);
         }
         __syncwarp();
+        if (++stg == p.stages) {
+          stg = 0;
+          par ^= 1;
+        }
       }
     } else {
       const int quarter = warp & 3;
@@ -632,19 +542,16 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_tiled = nullptr;
-static EncodeIm2colFn g_im2col = nullptr;
-static int g_num_sms = 0;
-static long long g_launches = 0;
+EncodeTiledFn g_tiled = nullptr;
+EncodeIm2colFn g_im2col = nullptr;
+int g_num_sms = 0;
+long long g_launches = 0;
 long long launch_count() { return g_launches; }
+int read_trace(long long* host_out) {
+  return sgb_cuda_check(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 12 * 512), "cudaMemcpyFromSymbol(g_trace)");
+}
 
-static int init_driver() {
+int init_driver() {
   if (g_tiled && g_im2col) return SGB_OK;
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
@@ -665,8 +572,19 @@ static int init_driver() {
   return SGB_OK;
 }
 
-static CUtensorMapSwizzle swizzle_for(int kc) {
+CUtensorMapSwizzle swizzle_for(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+long long* trace_buffer() {
+  void* ptr = nullptr;
+  cudaGetSymbolAddress(&ptr, g_trace);
+  return reinterpret_cast<long long*>(ptr);
+}
+
+int debug_skip_mask() {
+  const char* e = getenv("SGB_DEBUG_SKIP");
+  return e ? atoi(e) : 0;
 }
 
 bool enabled() {
@@ -691,6 +609,7 @@ bool supported(const Problem& q) {
 }
 
 int launch(const Problem& q, cudaStream_t st) {
+  if (halo_supported(q)) return halo_launch(q, st);
   if (int rc = init_driver()) return rc;
   Params p{};
   p.M = q.N * q.P * q.Q;

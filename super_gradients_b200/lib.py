@@ -109,6 +109,8 @@ _SIGNATURES = {
     "sgb_version": (c_int, []),
     "sgb_check_device": (c_int, []),
     "sgb_sm100_launches": (c_int64, []),
+    "sgb_sm100_halo_launches": (c_int64, []),
+    "sgb_debug_read_trace": (c_int, [P]),
     "sgb_conv_fprop": (c_int, [POINTER(ConvDesc), P, P, P, POINTER(Epilogue), P]),
     "sgb_conv_dgrad": (c_int, [POINTER(ConvDesc), P, P, P, _I, P]),
     "sgb_conv_wgrad": (c_int, [POINTER(ConvDesc), P, P, P, P]),
@@ -150,7 +152,7 @@ _SIGNATURES = {
 _lib = None
 
 # kernels launched by one call of each entry point (default 1); LAUNCHES[0] accumulates them (bench.py: gpu_launches)
-LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_sm100_launches": 0, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
+LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_sm100_launches": 0, "sgb_sm100_halo_launches": 0, "sgb_debug_read_trace": 0, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
 LAUNCHES = [0]
 
 

@@ -70,6 +70,12 @@ CONV_CASES = [
     (2, 64, 24, 24, 64, 3, 1, 1),
     (2, 16, 32, 32, 48, 3, 2, 1),
     (3, 32, 24, 24, 64, 3, 2, 1),
+    # halo-tile 3x3 kernel: every channel-chunk variant, ragged image edges, tiles > CTAs
+    (2, 48, 20, 20, 48, 3, 1, 1),
+    (2, 192, 20, 20, 192, 3, 1, 1),
+    (3, 32, 13, 37, 32, 3, 1, 1),
+    (2, 128, 19, 16, 128, 3, 1, 1),
+    (40, 32, 64, 64, 32, 3, 1, 1),
 ]
 
 
@@ -96,7 +102,13 @@ def test_conv_fprop_dgrad_wgrad(case):
     if c % 16 == 0 and kk % 8 == 0 and r in (1, 3) and pad == r // 2:
         assert lib.load().sgb_sm100_launches() == n_sm100 + 1, "the tcgen05/TMA kernel should have served this shape"
     yc = y.float().cpu()
-    assert ((yc - ref).abs() <= ref.abs() * 2**-7 + 1e-5).all()
+    # absolute floor: fp32 accumulation noise of a c*r*r-term sum whose result cancels to ~0
+    assert ((yc - ref).abs() <= ref.abs() * 2**-7 + 2e-7 * c * r * r).all()
+    if r == 3 and stride == 1 and pad == 1 and c in (32, 48, 64, 96, 128) and kk % 8 == 0 and kk <= 256:
+        n_halo = lib.load().sgb_sm100_halo_launches()
+        y_plain = k.conv_fprop(xg, krsc, kk, r, r, stride, pad)
+        assert lib.load().sgb_sm100_halo_launches() == n_halo + 1, "the halo-tile kernel should have served this shape"
+        assert torch.equal(y_plain, y)
     # fused per-channel statistics of the stored tensor
     st = stats.sum(0).cpu()
     torch.testing.assert_close(st[0], yc.double().sum((0, 2, 3)), rtol=1e-6, atol=1e-4)

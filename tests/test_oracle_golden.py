@@ -174,19 +174,38 @@ def test_tiny_yolo_nas_whole_graph(golden):
 
 def test_bf16_emulation_sensitivity(golden):
     """Justifies the whole-graph GPU tolerances: two bf16 emulations of the SAME graph that differ only in the
-    accumulation precision of the sums (fp32 vs fp64) already diverge by ~0.7 % (cls), ~6 % (reg), ~0.6 % (boxes)."""
+    accumulation precision of the sums (fp32 vs fp64) already diverge by ~0.7 % (cls), ~6 % (reg), ~0.6 % (boxes) in the
+    forward outputs, and -- because the task-aligned assigner is a discrete top-k over those outputs and the deep maps are
+    4x4 with train-mode BatchNorm -- by a MEDIAN of ~50 % in the per-parameter gradients (norms agree, directions do not).
+    The whole-graph gradient comparison of tests/test_modules_gpu.py is therefore only a sanity bound; gradient parity is
+    carried by the per-block tests (tight tolerances against this oracle) and the kernel tests."""
     from oracle.yolo_nas_oracle import YoloNASOracle
 
     g = golden("tiny_yolo_nas")
-    rel = lambda a, b: float((a - b).norm() / b.norm())  # noqa: E731
-    with O.bf16_emulation():
-        (pb, _), raw = YoloNASOracle(g["arch"], {k: v.clone() for k, v in g["sd0"].items()}, True).forward(g["x"])
-        sd64 = {k: (v.double() if v.dtype.is_floating_point else v.clone()) for k, v in g["sd0"].items()}
-        keep = O._r
-        O._r = lambda t: t.bfloat16().to(t.dtype)
-        try:
-            (pb2, _), raw2 = YoloNASOracle(g["arch"], sd64, True).forward(g["x"].double())
-        finally:
-            O._r = keep
-    spread = dict(cls=rel(raw2[0].float(), raw[0]), reg=rel(raw2[1].float(), raw[1]), boxes=rel(pb2.float(), pb))
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))  # noqa: E731
+    live = [k for k in g["param_names"] if "rbr_reparam" not in k]
+
+    def run(dt):
+        with O.bf16_emulation():
+            pe = {k: (v.detach().clone().to(dt) if v.dtype.is_floating_point else v.clone()) for k, v in g["sd0"].items()}
+            for k in live:
+                pe[k].requires_grad_(True)
+            keep = O._r
+            if dt == torch.float64:
+                O._r = lambda t: t.bfloat16().to(t.dtype)
+            try:
+                (pb, _), raw = YoloNASOracle(g["arch"], pe, True).forward(g["x"].to(dt))
+                loss, _ = O.ppyoloe_loss(raw, g["targets"], 4)
+                loss.backward()
+            finally:
+                O._r = keep
+        return pe, pb, raw
+
+    p32, pb, raw = run(torch.float32)
+    p64, pb2, raw2 = run(torch.float64)
+    spread = dict(cls=rel(raw2[0], raw[0]), reg=rel(raw2[1], raw[1]), boxes=rel(pb2, pb))
     assert 1e-3 < spread["cls"] < 7.5e-3 and 1e-2 < spread["reg"] < 6.5e-2 and spread["boxes"] < 1e-2, spread
+    errs = sorted(rel(p64[k].grad, p32[k].grad) for k in live if p32[k].grad is not None and p32[k].grad.norm() > 1e-6)
+    norm_ratio = sorted(abs(float(torch.log(p64[k].grad.float().norm() / p32[k].grad.norm()))) for k in live if p32[k].grad is not None and p32[k].grad.norm() > 1e-6)
+    assert 0.3 < errs[len(errs) // 2] < 0.65, errs[len(errs) // 2]      # measured 0.51
+    assert norm_ratio[len(norm_ratio) // 2] < 0.1, norm_ratio[len(norm_ratio) // 2]
