@@ -355,6 +355,162 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad from halo tiles
+// dW[k][dh][dw][c] += sum over the 16 x 16 tile of dy[pix][k] * x[pix + (dh-1, dw-1)][c]       (3x3, stride 1, pad 1)
+// GEMM view per filter row dh: M = out-channels (TMEM lanes), N = (dw, c) (TMEM columns), K = the 16 pixels of one tile row.
+//   * A = the dy tile [16][16][K] exactly as TMA lands it: MN-major, one MMA per tile row r.  Out-channel atoms that do not
+//     exist (K < 128) alias atom 0 (LBO = 0); the duplicated accumulator rows are never read.
+//   * B = the x halo tile [18][18][c]: the pixels (r + dh, 0..15) are 16 consecutive rows of the tile, and the three
+//     horizontal taps dw = 0, 1, 2 are the SAME rows shifted by one pixel -- expressed as three overlapping N atoms with
+//     LBO = one pixel.  One MMA therefore covers a whole filter row for KCB channels: 3 x fewer MMAs than per-tap issue and
+//     one activation load per tile instead of nine.
+// A CTA owns (128 out-channels) x (Cs = KCB * CHB in-channels) x (a contiguous range of tiles) and keeps all nine taps of
+// its slice in TMEM (9 * Cs fp32 columns) across its tiles; one round of fp32 reductions to global memory at the end.
+struct WHaloParams {
+  int N, H, W;
+  int K, C, cpad;
+  int tiles_h, tiles_w, total_tiles, tiles_per_cta;
+  int n_mblocks, n_slices;
+  int stages;
+  int a_atoms;            // 64- or 32-channel dy boxes loaded per stage (1 or 2)
+  int row_a;              // bytes per pixel row of a dy atom (64 or 128)
+  uint32_t a_lbo_bytes;   // 0: every M atom aliases atom 0
+  uint32_t stage_bytes, a_bytes;
+  float* dw;
+  int tmem_cols;
+  int dbg;
+};
+
+template <int KCB, int CHB>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WHaloParams p) {
+  constexpr int ROWB = KCB * 2;
+  constexpr uint32_t B_REGION = ((uint32_t)(HALO_PX * ROWB) + 1023u) & ~1023u;
+  constexpr int NB = 3 * KCB;  // GEMM N of one MMA: three horizontal taps
+  constexpr int WG_MAX_STAGES = 8;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ctrl = smem_base + (uint32_t)p.stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return ctrl + 8u * s; };
+  auto empty_bar = [&](int s) { return ctrl + 8u * (WG_MAX_STAGES + s); };
+  const uint32_t done_bar = ctrl + 8u * (2 * WG_MAX_STAGES);
+  const uint32_t tmem_slot = ctrl + 8u * (2 * WG_MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int wi = blockIdx.x;
+  const int mblock = wi % p.n_mblocks; wi /= p.n_mblocks;
+  const int slice = wi % p.n_slices; wi /= p.n_slices;
+  const int t0 = wi * p.tiles_per_cta;
+  const int t1 = min(t0 + p.tiles_per_cta, p.total_tiles);
+  const int n_tiles = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_MAX_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tcgen05_alloc(tmem_slot, p.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (n_tiles > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const int tiles_per_img = p.tiles_h * p.tiles_w;
+        int stg = 0;
+        uint32_t par = 1;
+        const uint32_t tx = (uint32_t)p.a_atoms * 256u * (uint32_t)p.row_a + (uint32_t)(CHB * HALO_PX * ROWB);
+        for (int tile = t0; tile < t1; ++tile) {
+          const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+          const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+          const int h0 = th * TILE_H, w0 = tw * TILE_W;
+          mbar_wait(empty_bar(stg), par);
+          mbar_expect_tx(full_bar(stg), tx);
+          const uint32_t sa = smem_base + (uint32_t)stg * p.stage_bytes, sb = sa + p.a_bytes;
+          for (int a = 0; a < p.a_atoms; ++a)
+            tma_load_tiled_4d(sa + (uint32_t)a * 256u * (uint32_t)p.row_a, &map_dy, full_bar(stg), mblock * 128 + a * (p.row_a / 2), w0, h0, n);
+#pragma unroll
+          for (int ck = 0; ck < CHB; ++ck)
+            tma_load_tiled_4d(sb + ck * B_REGION, &map_x, full_bar(stg), slice * (KCB * CHB) + ck * KCB, w0 - 1, h0 - 1, n);
+          if (++stg == p.stages) {
+            stg = 0;
+            par ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      // A and B MN-major (bits 15, 16); M = 128, N = NB
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t row_a = (uint32_t)p.row_a;
+      const uint64_t a_layout = row_a == 128 ? 2u : 4u;
+      const uint64_t a_hi = ((uint64_t)((p.a_lbo_bytes >> 4) & 0x3fff) << 16) | ((uint64_t)(((8 * row_a) >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46) | (a_layout << 61);
+      constexpr uint64_t b_layout = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+      constexpr uint64_t b_hi = ((uint64_t)((ROWB >> 4) & 0x3fff) << 16) | ((uint64_t)(((8 * ROWB) >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46) | (b_layout << 61);
+      int stg = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < n_tiles; ++it) {
+        mbar_wait(full_bar(stg), par);
+        tcgen05_fence_after();
+        const uint32_t sa = (smem_base + (uint32_t)stg * p.stage_bytes) >> 4, sb = sa + (p.a_bytes >> 4);
+#pragma unroll 1
+        for (int r = 0; r < TILE_H; ++r) {
+          const uint64_t da = a_hi | (uint64_t)((sa + (uint32_t)r * ((16u * row_a) >> 4)) & 0x3fff);
+#pragma unroll
+          for (int dh = 0; dh < 3; ++dh) {
+#pragma unroll
+            for (int ck = 0; ck < CHB; ++ck) {
+              const uint64_t db = b_hi | (uint64_t)((sb + ck * (B_REGION >> 4) + (uint32_t)(r + dh) * ((HALO_W * ROWB) >> 4)) & 0x3fff);
+              if (!(p.dbg & 8)) umma_bf16_if(leader, tmem_base + (uint32_t)((dh * CHB + ck) * NB), da, db, idesc, (it | r) != 0);
+            }
+          }
+        }
+        umma_commit_if(leader, empty_bar(stg));
+        if (it == n_tiles - 1) umma_commit_if(leader, done_bar);
+        if (++stg == p.stages) {
+          stg = 0;
+          par ^= 1;
+        }
+      }
+    } else {
+      const int quarter = warp & 3;
+      mbar_wait(done_bar, 0);
+      tcgen05_fence_after();
+      const int ko = mblock * 128 + quarter * 32 + lane;
+      float* drow = p.dw + (long long)ko * 9 * p.cpad + slice * (KCB * CHB);
+#pragma unroll 1
+      for (int dh = 0; dh < 3; ++dh)
+#pragma unroll 1
+        for (int ck = 0; ck < CHB; ++ck)
+#pragma unroll 1
+          for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+            for (int c0 = 0; c0 < KCB; c0 += 16) {
+              float v[16];
+              tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((dh * CHB + ck) * NB + dw * KCB + c0), v);
+              if (ko < p.K && !(p.dbg & 1)) {
+                float* dst = drow + (dh * 3 + dw) * p.cpad + ck * KCB + c0;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "f"(v[k]), "f"(v[k + 1]), "f"(v[k + 2]), "f"(v[k + 3])
+                               : "memory");
+              }
+            }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) tcgen05_dealloc(tmem_base, p.tmem_cols);
+}
+
 typedef void (*HaloFn)(const CUtensorMap, const CUtensorMap, const HaloParams);
 struct HaloVariant {
   int kc, chunks, snch;
@@ -528,6 +684,117 @@ int halo_launch(const Problem& q, cudaStream_t st) {
   ++g_launches;
   ++g_halo_launches;
   return sgb_cuda_check(cudaGetLastError(), "conv3x3_halo_kernel");
+}
+
+// ---- wgrad
+namespace {
+typedef void (*WHaloFn)(const CUtensorMap, const CUtensorMap, const WHaloParams);
+struct WHaloPlan {
+  WHaloFn fn;
+  int kcb, chb, cs;
+  WHaloParams p;
+  size_t smem;
+  int grid;
+};
+
+bool make_wplan(const WgradProblem& q, WHaloPlan& pl) {
+  if (!halo_enabled()) return false;
+  {
+    const char* e = getenv("SGB_DISABLE_HALO_WGRAD");
+    if (e && e[0] == '1') return false;
+  }
+  if (q.R != 3 || q.S != 3 || q.stride != 1 || q.pad != 1 || q.P != q.H || q.Q != q.W) return false;
+  if (q.C % 16 != 0 || q.K % 8 != 0) return false;
+  if (q.x_pitch % 8 != 0 || q.y_pitch % 8 != 0) return false;
+  if (((uintptr_t)q.x & 15) || ((uintptr_t)q.dy & 15) || ((uintptr_t)q.dw & 15)) return false;
+  if (q.C % 32 == 0) { pl.kcb = 32; pl.chb = 1; pl.fn = wgrad3x3_halo_kernel<32, 1>; }
+  else if (q.C % 48 == 0) { pl.kcb = 16; pl.chb = 3; pl.fn = wgrad3x3_halo_kernel<16, 3>; }
+  else { pl.kcb = 16; pl.chb = 1; pl.fn = wgrad3x3_halo_kernel<16, 1>; }
+  pl.cs = pl.kcb * pl.chb;
+  WHaloParams& p = pl.p;
+  p = WHaloParams{};
+  p.N = q.N; p.H = q.H; p.W = q.W; p.K = q.K; p.C = q.C; p.cpad = q.C;
+  p.tiles_h = (q.H + TILE_H - 1) / TILE_H;
+  p.tiles_w = (q.W + TILE_W - 1) / TILE_W;
+  const long long total = (long long)q.N * p.tiles_h * p.tiles_w;
+  if (total >= (1ll << 31)) return false;
+  p.total_tiles = (int)total;
+  p.n_mblocks = (q.K + 127) / 128;
+  p.n_slices = q.C / pl.cs;
+  const int kb = q.K < 128 ? q.K : 128;  // widest M block
+  if (kb <= 32) { p.row_a = 64; p.a_atoms = 1; p.a_lbo_bytes = 0; }
+  else if (kb <= 64) { p.row_a = 128; p.a_atoms = 1; p.a_lbo_bytes = 0; }
+  else { p.row_a = 128; p.a_atoms = 2; p.a_lbo_bytes = 256u * 128u; }
+  p.a_bytes = (uint32_t)p.a_atoms * 256u * (uint32_t)p.row_a;  // multiples of 16 KB
+  const uint32_t b_bytes = (uint32_t)pl.chb * (((uint32_t)(HALO_PX * pl.kcb * 2) + 1023u) & ~1023u);
+  p.stage_bytes = p.a_bytes + b_bytes;
+  const uint32_t ctrl_bytes = 8 * (2 * 8 + 1) + 16 + 64;
+  int stages = (int)((226u * 1024u - 1024u - ctrl_bytes) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return false;
+  p.stages = stages;
+  int tc = 32;
+  while (tc < 9 * pl.cs) tc <<= 1;
+  if (tc > 512) return false;
+  p.tmem_cols = tc;
+  p.dw = q.dw;
+  p.dbg = debug_skip_mask();
+  pl.smem = 1024 + (size_t)stages * p.stage_bytes + ctrl_bytes;
+  const int base = p.n_mblocks * p.n_slices;
+  int splits = g_num_sms > 0 ? g_num_sms / base : 1;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  pl.grid = base * splits;
+  return true;
+}
+}  // namespace
+
+bool wgrad_halo_supported(const WgradProblem& q) {
+  if (init_driver() != SGB_OK) return false;
+  WHaloPlan pl{};
+  return make_wplan(q, pl);
+}
+
+int wgrad_halo_launch(const WgradProblem& q, cudaStream_t st) {
+  if (int rc = init_driver()) return rc;
+  WHaloPlan pl{};
+  if (!make_wplan(q, pl)) return SGB_E_UNSUPPORTED;
+  static bool attr[3] = {false, false, false};
+  const int vi = pl.kcb == 32 ? 0 : (pl.chb == 3 ? 1 : 2);
+  if (!attr[vi]) {
+    if (int rc = sgb_cuda_check(cudaFuncSetAttribute(pl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                                "cudaFuncSetAttribute(wgrad3x3_halo_kernel)"))
+      return rc;
+    attr[vi] = true;
+  }
+  const WHaloParams& p = pl.p;
+  alignas(64) CUtensorMap map_dy, map_x;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)q.K, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+    cuuint64_t strides[3] = {(cuuint64_t)q.y_pitch * 2, (cuuint64_t)q.W * q.y_pitch * 2, (cuuint64_t)q.H * q.W * q.y_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)(p.row_a / 2), (cuuint32_t)TILE_W, (cuuint32_t)TILE_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_tiled(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.dy), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(p.row_a / 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sgb_set_error("cuTensorMapEncodeTiled(halo wgrad dy) failed with %d", (int)r); return SGB_E_CUDA; }
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+    cuuint64_t strides[3] = {(cuuint64_t)q.x_pitch * 2, (cuuint64_t)q.W * q.x_pitch * 2, (cuuint64_t)q.H * q.W * q.x_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)pl.kcb, (cuuint32_t)HALO_W, (cuuint32_t)HALO_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_tiled(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pl.kcb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sgb_set_error("cuTensorMapEncodeTiled(halo wgrad x) failed with %d", (int)r); return SGB_E_CUDA; }
+  }
+  pl.fn<<<pl.grid, HALO_THREADS, pl.smem, st>>>(map_dy, map_x, p);
+  ++g_launches;
+  ++g_halo_launches;
+  return sgb_cuda_check(cudaGetLastError(), "wgrad3x3_halo_kernel");
 }
 
 }  // namespace sm100

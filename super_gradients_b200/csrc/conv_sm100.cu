@@ -759,6 +759,7 @@ bool wgrad_supported(const WgradProblem& q) {
 }
 
 int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
+  if (wgrad_halo_supported(q)) return wgrad_halo_launch(q, st);
   if (int rc = init_driver()) return rc;
   WParams p{};
   p.K = q.K; p.C = q.C; p.R = q.R; p.S = q.S; p.stride = q.stride; p.pad = q.pad; p.P = q.P; p.Q = q.Q;

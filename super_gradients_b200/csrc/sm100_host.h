@@ -25,5 +25,8 @@ struct Problem;
 bool halo_supported(const Problem& q);      // conv_halo_sm100.cu: 3x3 stride-1 convolutions read from one halo tile
 int halo_launch(const Problem& q, cudaStream_t st);
 long long halo_launch_count();
+struct WgradProblem;
+bool wgrad_halo_supported(const WgradProblem& q);  // 3x3 stride-1 weight gradient from halo tiles
+int wgrad_halo_launch(const WgradProblem& q, cudaStream_t st);
 
 }  // namespace sm100

@@ -64,7 +64,7 @@ probe(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtenso
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(64) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -72,7 +72,7 @@ probe(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtenso
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
-  const int s_rows = c.mode == 0 ? 16 : 128;
+  const int s_rows = (c.mode == 0 || c.mode == 3) ? 16 : 128;
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar0, 256 * c.row_bytes + s_rows * c.s_row_bytes);
     tma_load_2d(g, &map_g, bar0, 0, 0);
@@ -85,10 +85,22 @@ probe(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtenso
       da = desc(g + c.off_rows * c.row_bytes + c.kstep * 32, c.row_bytes, c.sbo_rows * c.row_bytes, c.base_mode);
       db = desc(s + c.kstep * 32, c.s_row_bytes, 8 * c.s_row_bytes, 0);
       idesc |= (uint32_t)(16 >> 3) << 17;
-    } else {
+    } else if (c.mode == 1) {
       da = desc(s, c.s_row_bytes, 8 * c.s_row_bytes, 0);
       db = desc(g + c.off_rows * c.row_bytes, c.row_bytes, 8 * c.row_bytes, c.base_mode);
       idesc |= (1u << 16) | ((uint32_t)((c.row_bytes / 2) >> 3) << 17);
+    } else if (c.mode == 2) {
+      // B MN-major, N = 3 atoms that OVERLAP: atom i starts one row (pixel) after atom i-1 (LBO = row_bytes)
+      da = desc(s, c.s_row_bytes, 8 * c.s_row_bytes, 0);
+      db = desc(g + c.off_rows * c.row_bytes, c.row_bytes, 8 * c.row_bytes, 0);
+      db = (db & ~((uint64_t)0x3fff << 16)) | ((uint64_t)((c.row_bytes >> 4) & 0x3fff) << 16);
+      idesc |= (1u << 16) | ((uint32_t)((3 * c.row_bytes / 2) >> 3) << 17);
+    } else {
+      // A MN-major, M = 128 made of 128 / atom aliases of ONE atom (LBO = 0): rows m and m % atom are equal
+      da = desc(g + c.off_rows * c.row_bytes, c.row_bytes, 8 * c.row_bytes, 0);
+      da = da & ~((uint64_t)0x3fff << 16);
+      db = desc(s, c.s_row_bytes, 8 * c.s_row_bytes, 0);  // B K-major: 16 rows (N) x 16 k
+      idesc |= (1u << 15) | ((uint32_t)(16 >> 3) << 17);
     }
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
                  "l"(da), "l"(db), "r"(idesc), "r"(0)
@@ -98,7 +110,7 @@ probe(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtenso
   __syncwarp();
   mbar_wait(bar1, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int ncols = c.mode == 0 ? 16 : c.row_bytes / 2;
+  const int ncols = (c.mode == 0 || c.mode == 3) ? 16 : (c.mode == 1 ? c.row_bytes / 2 : 3 * c.row_bytes / 2);
   for (int c0 = 0; c0 < ncols; c0 += 16) {
     uint32_t r[16];
     asm volatile(
@@ -107,11 +119,11 @@ probe(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtenso
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(tmem + ((uint32_t)(warp * 32) << 16) + c0));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    for (int i = 0; i < 16; ++i) out[(warp * 32 + lane) * 64 + c0 + i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) out[(warp * 32 + lane) * 256 + c0 + i] = __uint_as_float(r[i]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -143,14 +155,14 @@ int main() {
   g_tiled = (EncodeTiledFn)fn;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   float* d_out;
-  cudaMalloc(&d_out, 128 * 64 * 4);
-  std::vector<float> h_out(128 * 64);
+  cudaMalloc(&d_out, 128 * 256 * 4);
+  std::vector<float> h_out(128 * 256);
   srand(1);
   int n_fail = 0, n_run = 0;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 4; ++mode)
     for (int row_bytes : {128, 64, 32}) {
       const int cols = row_bytes / 2;
-      const int s_row_bytes = mode == 0 ? row_bytes : 64, s_cols = s_row_bytes / 2, s_rows = mode == 0 ? 16 : 128;
+      const int s_row_bytes = mode == 0 ? row_bytes : 64, s_cols = s_row_bytes / 2, s_rows = (mode == 0 || mode == 3) ? 16 : 128;
       std::vector<float> G(256 * cols), S(s_rows * s_cols);
       std::vector<__nv_bfloat16> Gb(G.size()), Sb(S.size());
       for (size_t i = 0; i < G.size(); ++i) { G[i] = (float)(rand() % 7 - 3); Gb[i] = __float2bfloat16(G[i]); }
@@ -163,32 +175,36 @@ int main() {
       CUtensorMap mg = make_map(dG, cols, 256, row_bytes), ms = make_map(dS, s_cols, s_rows, s_row_bytes);
       const int offs[] = {0, 1, 2, 3, 5, 7, 8, 9, 10, 11, 12, 20, 21, 22};
       for (int sbo_rows : {8, 10, 18}) {
-        if (mode == 1 && sbo_rows != 8) continue;
+        if (mode >= 1 && sbo_rows != 8) continue;
         for (int off : offs)
           for (int kstep = 0; kstep < (mode == 0 ? cols / 16 : 1); kstep += (cols / 16 > 1 ? cols / 16 - 1 : 1))
             for (int base_mode = 0; base_mode < 2; ++base_mode) {
               if (mode == 0 && off + 15 * sbo_rows + 8 > 256) continue;
               Cfg c{mode, row_bytes, off, sbo_rows, kstep, base_mode, s_row_bytes};
-              cudaMemset(d_out, 0xff, 128 * 64 * 4);
+              cudaMemset(d_out, 0xff, 128 * 256 * 4);
               probe<<<1, 128, 64 * 1024>>>(mg, ms, c, d_out);
               cudaError_t e = cudaDeviceSynchronize();
               if (e != cudaSuccess) {
                 printf("CUDA error %s at mode=%d rb=%d off=%d sbo=%d k=%d base=%d\n", cudaGetErrorString(e), mode, row_bytes, off, sbo_rows, kstep, base_mode);
                 return 3;
               }
-              cudaMemcpy(h_out.data(), d_out, 128 * 64 * 4, cudaMemcpyDeviceToHost);
+              cudaMemcpy(h_out.data(), d_out, 128 * 256 * 4, cudaMemcpyDeviceToHost);
               int bad = 0;
-              const int ncols = mode == 0 ? 16 : cols;
+              const int ncols = (mode == 0 || mode == 3) ? 16 : (mode == 1 ? cols : 3 * cols);
               for (int i = 0; i < 128; ++i)
                 for (int n = 0; n < ncols; ++n) {
                   float ref = 0;
                   if (mode == 0) {
                     const int row = off + (i / 8) * sbo_rows + i % 8;
                     for (int k = 0; k < 16; ++k) ref += G[row * cols + kstep * 16 + k] * S[n * s_cols + kstep * 16 + k];
-                  } else {
+                  } else if (mode == 1) {
                     for (int k = 0; k < 16; ++k) ref += S[i * s_cols + k] * G[(off + k) * cols + n];
+                  } else if (mode == 2) {
+                    for (int k = 0; k < 16; ++k) ref += S[i * s_cols + k] * G[(off + k + n / cols) * cols + n % cols];
+                  } else {
+                    for (int k = 0; k < 16; ++k) ref += G[(off + k) * cols + i % cols] * S[n * s_cols + k];
                   }
-                  if (ref != h_out[i * 64 + n]) ++bad;
+                  if (ref != h_out[i * 256 + n]) ++bad;
                 }
               ++n_run;
               if (bad) ++n_fail;
