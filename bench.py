@@ -203,12 +203,17 @@ def run_ours(args):
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("SGB_PROFILER_RANGE") == "1"  # `ncu --profile-from-start off`: capture exactly the timed steps
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         step.set_hyper_params(lr_at(i), 0.9997)
         loss, _ = step.run(dev_x[i % nbuf], dev_t[i % nbuf])
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     if world > 1:

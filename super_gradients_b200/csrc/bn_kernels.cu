@@ -41,7 +41,10 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
 // Op interface:
 //   static constexpr int NCOEF, NACC;           (NACC == 0: pure map)
 //   __device__ void prologue(float* sc) const;  all threads of the CTA; fills sc[NCOEF][C]
-//   __device__ void apply(int64_t pix, int c0, const float (&r)[NCOEF][8], float (&acc)[NACC or 1][8]) const;
+//   struct In;  static constexpr int UNROLL;    the 16-byte vectors of one pixel / pixels batched per thread
+//   __device__ In load(int64_t pix, int c0) const;
+//   __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[NCOEF][8], float (&acc)[NACC or 1][8]) const;
+//   (all loads of a batch are issued before the first store, so UNROLL pixels x |In| vectors are in flight per thread)
 //   double* out; int out_stride;                (only when NACC > 0)
 template <class Op>
 __global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M, const int C) {
@@ -56,40 +59,50 @@ __global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M,
   const int64_t per = (M + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = blockIdx.x * per;
   const int64_t p1 = (p0 + per < M) ? p0 + per : M;
-  float* sred = sc + NCOEF * C;
+  float* sred = sc + NCOEF * C;  // [TPB][NACC * 8]: every thread's partial sums, tree-summed without atomics
   for (int cv0 = 0; cv0 < cvs; cv0 += cvb) {
-    if (NACC > 0) {
-      for (int i = t; i < NACC * cvb * 8; i += TPB) sred[i] = 0.f;
-      __syncthreads();
-    }
     const int cv = cv0 + cvi;
-    if (pl < lanes && cv < cvs) {
+    const bool active = pl < lanes && cv < cvs;
+    float acc[NACC > 0 ? NACC : 1][8];
+#pragma unroll
+    for (int a = 0; a < (NACC > 0 ? NACC : 1); ++a)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+    if (active) {
       float r[NCOEF > 0 ? NCOEF : 1][8];
 #pragma unroll
       for (int k = 0; k < NCOEF; ++k)
 #pragma unroll
         for (int e = 0; e < 8; ++e) r[k][e] = sc[k * C + cv * 8 + e];
-      float acc[NACC > 0 ? NACC : 1][8];
+      constexpr int U = Op::UNROLL;
+      int64_t pix = p0 + pl;
+      for (; pix + (int64_t)(U - 1) * lanes < p1; pix += (int64_t)U * lanes) {
+        typename Op::In in[U];
 #pragma unroll
-      for (int a = 0; a < (NACC > 0 ? NACC : 1); ++a)
+        for (int k = 0; k < U; ++k) in[k] = op.load(pix + (int64_t)k * lanes, cv * 8);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
-      for (int64_t pix = p0 + pl; pix < p1; pix += lanes) op.apply(pix, cv * 8, r, acc);
-      if (NACC > 0) {
+        for (int k = 0; k < U; ++k) op.finish(pix + (int64_t)k * lanes, cv * 8, in[k], r, acc);
+      }
+      for (; pix < p1; pix += lanes) op.finish(pix, cv * 8, op.load(pix, cv * 8), r, acc);
+    }
+    if (NACC > 0) {
+      // thread t = pl * cvb + cvi stores its NACC*8 sums at [pl][cvi][a][e]; output j = (cvi, a, e) then sums over pl
+      __syncthreads();
+      if (pl < lanes) {
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) atomicAdd(&sred[(a * cvb + cvi) * 8 + e], acc[a][e]);
-      }
-    }
-    if (NACC > 0) {
-      __syncthreads();
-      for (int i = t; i < NACC * cvb * 8; i += TPB) {
-        const int a = i / (cvb * 8), rr = i % (cvb * 8);
-        const int c = cv0 * 8 + rr;
-        if (c < C) atomicAdd(&op.out[(int64_t)a * op.out_stride + c], (double)sred[i]);
+          for (int e = 0; e < 8; ++e) sred[(pl * cvb + cvi) * (NACC * 8 + 1) + a * 8 + e] = acc[a][e];  // +1: conflict-free
       }
       __syncthreads();
+      const int nout = cvb * NACC * 8;
+      for (int j = t; j < nout; j += TPB) {
+        float sum = 0.f;
+        const int ci = j / (NACC * 8), a = (j / 8) % NACC, e = j % 8;
+        for (int q = 0; q < lanes; ++q) sum += sred[(q * cvb + ci) * (NACC * 8 + 1) + a * 8 + e];
+        const int c = (cv0 + ci) * 8 + e;
+        if (c < C) atomicAdd(&op.out[(int64_t)a * op.out_stride + c], (double)sum);
+      }
     }
   }
 }
@@ -98,9 +111,9 @@ template <class Op>
 int launch_chan(const Op& op, int64_t M, int C, cudaStream_t st, const char* what) {
   const int cvs = C / 8;
   const int cvb = cvs < TPB ? cvs : TPB;
-  const size_t smem = ((size_t)Op::NCOEF * C + (size_t)Op::NACC * cvb * 8) * sizeof(float);
-  int64_t want = (M + 127) / 128;
-  const int grid = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  const size_t smem = ((size_t)Op::NCOEF * C + (size_t)(Op::NACC * 8 + 1) * TPB) * sizeof(float);
+  int64_t want = (M + 255) / 256;
+  const int grid = (int)(want < 1 ? 1 : (want > 148 * 6 ? 148 * 6 : want));
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     cudaFuncSetAttribute(chan_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -147,12 +160,21 @@ struct BnFwdOp {
       }
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[2][8], float (&)[1][8]) const {
-    V8 a = ld8(x + pix * d.x_pitch + d.x_off + c0);
+  static constexpr int UNROLL = 4;
+  struct In {
+    V8 a, rr;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.a = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    if (res) in.rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
+    return in;
+  }
+  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[2][8], float (&)[1][8]) const {
+    V8 a = in.a;
     if (res) {
-      const V8 rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + rr.v[e], d.act);
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + in.rr.v[e], d.act);
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]), d.act);
@@ -178,12 +200,21 @@ struct BnInferOp {
       sc[C + c] = b - rmean[c] * g * rstd;
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[2][8], float (&)[1][8]) const {
-    V8 a = ld8(x + pix * d.x_pitch + d.x_off + c0);
+  static constexpr int UNROLL = 4;
+  struct In {
+    V8 a, rr;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.a = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    if (res) in.rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
+    return in;
+  }
+  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[2][8], float (&)[1][8]) const {
+    V8 a = in.a;
     if (res) {
-      const V8 rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + rr.v[e], d.act);
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + in.rr.v[e], d.act);
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]), d.act);
@@ -211,10 +242,19 @@ struct BnBwdRedOp {
       sc[3 * C + c] = b - mean[c] * g * rstd[c];
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[4][8], float (&acc)[2][8]) const {
-    const V8 g = ld8(dy + pix * d.y_pitch + d.y_off + c0), xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
-    V8 yv;
-    if (y) yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
+  static constexpr int UNROLL = 4;
+  struct In {
+    V8 g, xv, yv;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.g = ld8(dy + pix * d.y_pitch + d.y_off + c0);
+    in.xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    if (y) in.yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
+    return in;
+  }
+  __device__ void finish(int64_t, int, const In& in, const float (&r)[4][8], float (&acc)[2][8]) const {
+    const V8 &g = in.g, &xv = in.xv, &yv = in.yv;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = g.v[e];
@@ -255,10 +295,19 @@ struct BnBwdApplyOp {
       }
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[6][8], float (&)[1][8]) const {
-    const V8 g = ld8(dy + pix * d.y_pitch + d.y_off + c0), xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
-    V8 yv;
-    if (y) yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
+  static constexpr int UNROLL = 2;
+  struct In {
+    V8 g, xv, yv;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.g = ld8(dy + pix * d.y_pitch + d.y_off + c0);
+    in.xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
+    if (y) in.yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
+    return in;
+  }
+  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[6][8], float (&)[1][8]) const {
+    const V8 &g = in.g, &xv = in.xv, &yv = in.yv;
     V8 o, dr;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -345,9 +394,19 @@ struct QarepFwdOp {
       }
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[3][8], float (&)[1][8]) const {
-    V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
-    const V8 b = ld8(u + pix * d.pitchu + d.offu + c0);
+  static constexpr int UNROLL = 4;
+  struct In {
+    V8 a, b;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
+    in.b = ld8(u + pix * d.pitchu + d.offu + c0);
+    return in;
+  }
+  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[3][8], float (&)[1][8]) const {
+    V8 a = in.a;
+    const V8& b = in.b;
 #pragma unroll
     for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(r[0][e], a.v[e], fmaf(r[1][e], b.v[e], r[2][e])), d.act);
     st8(outp + pix * d.pitcho + d.offo + c0, a);
@@ -375,9 +434,19 @@ struct QarepBwdRedOp {
       sc[7 * C + c] = coef[8 * C + c];
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[8][8], float (&acc)[3][8]) const {
-    const V8 g = ld8(dout + pix * d.pitcho + d.offo + c0);
-    const V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + c0), b = ld8(u + pix * d.pitchu + d.offu + c0);
+  static constexpr int UNROLL = 4;
+  struct In {
+    V8 g, a, b;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.g = ld8(dout + pix * d.pitcho + d.offo + c0);
+    in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
+    in.b = ld8(u + pix * d.pitchu + d.offu + c0);
+    return in;
+  }
+  __device__ void finish(int64_t, int, const In& in, const float (&r)[8][8], float (&acc)[3][8]) const {
+    const V8 &g = in.g, &a = in.a, &b = in.b;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = g.v[e];
@@ -444,9 +513,19 @@ struct QarepBwdApplyOp {
       }
     }
   }
-  __device__ void apply(int64_t pix, int c0, const float (&r)[12][8], float (&)[1][8]) const {
-    const V8 g = ld8(dout + pix * d.pitcho + d.offo + c0);
-    const V8 a = ld8(y3 + pix * d.pitch3 + d.off3 + c0), b = ld8(u + pix * d.pitchu + d.offu + c0);
+  static constexpr int UNROLL = 2;
+  struct In {
+    V8 g, a, b;
+  };
+  __device__ In load(int64_t pix, int c0) const {
+    In in;
+    in.g = ld8(dout + pix * d.pitcho + d.offo + c0);
+    in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
+    in.b = ld8(u + pix * d.pitchu + d.offu + c0);
+    return in;
+  }
+  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[12][8], float (&)[1][8]) const {
+    const V8 &g = in.g, &a = in.a, &b = in.b;
     V8 o3, ou;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {

@@ -131,7 +131,7 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, in
 template <class F>
 __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C, double* out, int out_stride) {
   constexpr int NACC = F::NACC;
-  extern __shared__ float sred[];  // [NACC][cvb*8]
+  extern __shared__ float sred[];  // [TPB][NACC*8]
   const int cvs = C / 8;
   const int cvb = cvs < TPB ? cvs : TPB;  // channel vectors per CTA pass
   const int lanes = TPB / cvb;
@@ -142,28 +142,33 @@ __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C,
   int64_t p1 = p0 + pix_per_cta;
   if (p1 > M) p1 = M;
   for (int cv0 = 0; cv0 < cvs; cv0 += cvb) {
-    for (int i = t; i < NACC * cvb * 8; i += TPB) sred[i] = 0.f;
-    __syncthreads();
     const int cv = cv0 + cvi;
+    float acc[NACC][8];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
     if (pl < lanes && cv < cvs) {
-      float acc[NACC][8];
-#pragma unroll
-      for (int a = 0; a < NACC; ++a)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+#pragma unroll 4
       for (int64_t pix = p0 + pl; pix < p1; pix += lanes) f.eval(pix, cv * 8, acc);
+    }
+    // every thread parks its NACC*8 partial sums at [pl][cvi][a][e]; output j = (cvi, a, e) sums over pl (no atomics)
+    __syncthreads();
+    if (pl < lanes) {
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&sred[(a * cvb + cvi) * 8 + e], acc[a][e]);
+        for (int e = 0; e < 8; ++e) sred[(pl * cvb + cvi) * (NACC * 8 + 1) + a * 8 + e] = acc[a][e];  // +1: conflict-free
     }
     __syncthreads();
-    for (int i = t; i < NACC * cvb * 8; i += TPB) {
-      int a = i / (cvb * 8), r = i % (cvb * 8);
-      int c = cv0 * 8 + r;
-      if (c < C) atomicAdd(&out[(int64_t)a * out_stride + c], (double)sred[i]);
+    const int nout = cvb * NACC * 8;
+    for (int j = t; j < nout; j += TPB) {
+      float sum = 0.f;
+      const int ci = j / (NACC * 8), a = (j / 8) % NACC, e = j % 8;
+      for (int q = 0; q < lanes; ++q) sum += sred[(q * cvb + ci) * (NACC * 8 + 1) + a * 8 + e];
+      const int c = (cv0 + ci) * 8 + e;
+      if (c < C) atomicAdd(&out[(int64_t)a * out_stride + c], (double)sum);
     }
-    __syncthreads();
   }
 }
 
@@ -171,9 +176,9 @@ template <class F>
 int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaStream_t st) {
   int cvs = C / 8;
   int cvb = cvs < TPB ? cvs : TPB;
-  size_t smem = (size_t)F::NACC * cvb * 8 * sizeof(float);
+  size_t smem = (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
   int64_t want = (M + 255) / 256;  // >= 256 pixels per CTA
-  int grid = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+  int grid = (int)(want < 1 ? 1 : (want > 148 * 6 ? 148 * 6 : want));
   chan_reduce_kernel<F><<<grid, TPB, smem, st>>>(f, M, C, out, out_stride);
   SGB_LAUNCH_CHECK("chan_reduce_kernel");
   return SGB_OK;
