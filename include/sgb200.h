@@ -91,6 +91,26 @@ int sgb_weight_prepare(const float* w_oihw, int K, int C, int R, int S, int c_pa
 /* fp32 KRSC (c_pad channels) gradient -> fp32 OIHW gradient; accumulate != 0 adds into g_oihw. */
 int sgb_wgrad_to_oihw(const float* dw_krsc, int K, int C, int R, int S, int c_pad, float* g_oihw, int accumulate,
                       void* stream);
+/* Batched forms of the two calls above for a whole network: the item tables live in DEVICE memory, `start` is the
+ * exclusive prefix sum of the per-item element counts (KRSC + CRSK elements / OIHW elements) and `total` their sum.
+ * One launch replaces the per-layer weight casts of a step (reference: the fp32 -> bf16 autocast copies implied by
+ * training/sg_trainer/sg_trainer.py:622-644) and the per-layer gradient layout changes. */
+typedef struct SgbWeightItem {
+  const float* w;     /* fp32 OIHW */
+  const float* scale; /* device scalar or NULL */
+  sgb_bf16* krsc;
+  sgb_bf16* crsk;     /* or NULL */
+  int32_t K, C, R, S, c_pad, add_identity;
+  int64_t start;
+} SgbWeightItem;
+typedef struct SgbWgradItem {
+  const float* dw; /* fp32 KRSC with c_pad channels */
+  float* g;        /* fp32 OIHW */
+  int32_t K, C, R, S, c_pad, accumulate;
+  int64_t start;
+} SgbWgradItem;
+int sgb_weight_prepare_batch(const SgbWeightItem* items_dev, int n_items, int64_t total, void* stream);
+int sgb_wgrad_to_oihw_batch(const SgbWgradItem* items_dev, int n_items, int64_t total, void* stream);
 /* ConvTranspose2d(kernel=2, stride=2) (modules/sampling.py:72-73): desc describes the EQUIVALENT 2x2/s2 convolution
  * from the upsampled tensor (N,H,W,C) to the small tensor (N,P,Q,K); w is [K_small][2][2][C_up] bf16. */
 int sgb_convt2x2_fprop(const SgbConvDesc* d, const sgb_bf16* x_small, const sgb_bf16* w_up, const float* bias,

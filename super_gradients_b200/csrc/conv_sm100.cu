@@ -154,7 +154,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================================================================== MMA issuer
+    // The warp stays converged (descriptors live in uniform registers); only the elected lane's instructions issue.
+    const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    const uint64_t desc_hi = make_smem_desc(0, p.KC);
+    const uint32_t ksteps = (uint32_t)p.KC / 16;
     int it = 0, tcount = 0, stg = 0;
     uint32_t par = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -165,27 +169,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.BN);
       for (int k = 0; k < k_iters; ++k, ++it) {
         const bool tr0 = (p.dbg & 16) && blockIdx.x == 0 && it < 512 && lane == 0;
-        if (tr0) g_trace[7][it] = clock64();
         mbar_wait(full_bar(stg), par);
-        if (tr0) g_trace[8][it] = clock64();
+        if (tr0) g_trace[2][it] = clock64();
         tcgen05_fence_after();
-        if (tr0) g_trace[9][it] = clock64();
-        if (elect_one()) {
-          const bool tr = (p.dbg & 16) && blockIdx.x == 0 && it < 512;
-          if (tr) g_trace[2][it] = clock64();
-          const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
-          const uint64_t da = make_smem_desc(sa, p.KC), db = make_smem_desc(sb, p.KC);
-          for (int j = 0; j < p.KC / 16; ++j) {
-            // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if (!(p.dbg & 8)) umma_bf16(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (k | j) != 0);
-          }
-          if (tr) g_trace[10][it] = clock64();
-          umma_commit(empty_bar(stg));
-          if (k == k_iters - 1) umma_commit(tfull_bar(ab));
-          if (tr) g_trace[3][it] = clock64();
+        const uint32_t sa = (smem_base + stg * stage_bytes) >> 4, sb = sa + (a_bytes >> 4);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+          // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
+          const uint64_t da = desc_hi | (uint64_t)((sa + 2 * j) & 0x3fff), db = desc_hi | (uint64_t)((sb + 2 * j) & 0x3fff);
+          if (!(p.dbg & 8)) umma_bf16_if((j < ksteps) ? leader : 0u, d_tmem, da, db, idesc, (k | (int)j) != 0);
         }
-        __syncwarp();
-        if (tr0) g_trace[11][it] = clock64();
+        umma_commit_if(leader, empty_bar(stg));
+        if (k == k_iters - 1) umma_commit_if(leader, tfull_bar(ab));
+        if (tr0) g_trace[3][it] = clock64();
         if (++stg == p.stages) {
           stg = 0;
           par ^= 1;
@@ -481,31 +477,30 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       }
     } else if (warp == 1) {
       // A and B are MN-major: a_major (bit 15) and b_major (bit 16) set; M = 128, N = CB
+      const uint32_t leader = elect_one() ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.CB >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const int b_row_bytes = p.CB * 2;
+      const uint64_t a_hi = make_smem_desc_mn(0, 128, WPIX * 128), b_hi = make_smem_desc_mn(0, b_row_bytes, 0);
       int stg = 0;
       uint32_t par = 0;
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(full_bar(stg), par);
         tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
-          for (int t = 0; t < ntaps; ++t)
-            for (int bx = 0; bx < boxes_per_tap; ++bx) {
-              const uint32_t sbox = sb + (uint32_t)(t * boxes_per_tap + bx) * b_box;
-              const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.c_tile + bx * p.CB);
+        const uint32_t sa = (smem_base + stg * stage_bytes) >> 4, sb = sa + (a_bytes >> 4);
+        for (int t = 0; t < ntaps; ++t)
+          for (int bx = 0; bx < boxes_per_tap; ++bx) {
+            const uint32_t sbox = sb + (((uint32_t)(t * boxes_per_tap + bx) * b_box) >> 4);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.c_tile + bx * p.CB);
 #pragma unroll
-              for (int j = 0; j < WPIX / 16; ++j) {
-                const uint64_t da = make_smem_desc_mn(sa + j * 16 * 128, 128, WPIX * 128);
-                const uint64_t db = make_smem_desc_mn(sbox + j * 16 * b_row_bytes, b_row_bytes, 0);
-                umma_bf16(d_tmem, da, db, idesc, (it | j) != 0);
-              }
+            for (int j = 0; j < WPIX / 16; ++j) {
+              const uint64_t da = a_hi | (uint64_t)((sa + ((j * 16 * 128) >> 4)) & 0x3fff);
+              const uint64_t db = b_hi | (uint64_t)((sbox + (uint32_t)((j * 16 * b_row_bytes) >> 4)) & 0x3fff);
+              umma_bf16_if(leader, d_tmem, da, db, idesc, (it | j) != 0);
             }
-          umma_commit(empty_bar(stg));
-          if (it == n_iters - 1) umma_commit(done_bar);
-        }
-        __syncwarp();
+          }
+        umma_commit_if(leader, empty_bar(stg));
+        if (it == n_iters - 1) umma_commit_if(leader, done_bar);
         if (++stg == p.stages) {
           stg = 0;
           par ^= 1;

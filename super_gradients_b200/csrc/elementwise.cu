@@ -40,54 +40,93 @@ inline int grid_for(int64_t work, int per_cta = TPB, int max_ctas = 148 * 8) {
 }
 
 // ---------------------------------------------------------------------------------------------- weights / layout
+// element i of the concatenated [K][R][S][cp] (KRSC) ++ [C][R][S][Kp] (CRSK) bf16 copies of one fp32 OIHW filter
+__device__ __forceinline__ void weight_prepare_elem(const float* __restrict__ w, int K, int C, int R, int S, int cp, bf16* krsc,
+                                                    bf16* crsk, float sc, int add_identity, int64_t i) {
+  const int Kp = ((K + 7) / 8) * 8;
+  const int64_t n1 = (int64_t)K * R * S * cp;
+  if (i < n1) {
+    int c = i % cp;
+    int64_t t = i / cp;
+    int s = t % S; t /= S;
+    int r = t % R;
+    int k = t / R;
+    float v = 0.f;
+    if (c < C) {
+      v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
+      if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
+    }
+    krsc[i] = __float2bfloat16_rn(v);
+  } else {
+    int64_t j = i - n1;
+    int k = j % Kp;
+    int64_t t = j / Kp;
+    int s = t % S; t /= S;
+    int r = t % R;
+    int c = t / R;
+    float v = 0.f;
+    if (k < K) {
+      v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
+      if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
+    }
+    crsk[j] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void weight_prepare_kernel(const float* __restrict__ w, int K, int C, int R, int S, int cp, bf16* krsc,
                                       bf16* crsk, const float* scale, int add_identity) {
-  // krsc: [K][R][S][cp];  crsk: [cp rows? no: C rows][R][S][Kp]  (Kp = K rounded up to 8)
   const int Kp = ((K + 7) / 8) * 8;
   const float sc = scale ? *scale : 1.f;
   const int64_t n1 = (int64_t)K * R * S * cp;
   const int64_t n2 = crsk ? (int64_t)C * R * S * Kp : 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i < n1) {
-      int c = i % cp;
-      int64_t t = i / cp;
-      int s = t % S; t /= S;
-      int r = t % R;
-      int k = t / R;
-      float v = 0.f;
-      if (c < C) {
-        v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
-        if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
-      }
-      krsc[i] = __float2bfloat16_rn(v);
-    } else {
-      int64_t j = i - n1;
-      int k = j % Kp;
-      int64_t t = j / Kp;
-      int s = t % S; t /= S;
-      int r = t % R;
-      int c = t / R;
-      float v = 0.f;
-      if (k < K) {
-        v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
-        if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
-      }
-      crsk[j] = __float2bfloat16_rn(v);
-    }
-  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x)
+    weight_prepare_elem(w, K, C, R, S, cp, krsc, crsk, sc, add_identity, i);
+}
+
+// element i of the fp32 OIHW gradient gathered from the fp32 KRSC accumulation buffer
+__device__ __forceinline__ void wgrad_to_oihw_elem(const float* __restrict__ dw, int C, int R, int S, int cp, float* g,
+                                                   int accumulate, int64_t i) {
+  int s = i % S;
+  int64_t t = i / S;
+  int r = t % R; t /= R;
+  int c = t % C;
+  int k = t / C;
+  float v = dw[(((int64_t)k * R + r) * S + s) * cp + c];
+  g[i] = accumulate ? g[i] + v : v;
 }
 
 __global__ void wgrad_to_oihw_kernel(const float* __restrict__ dw, int K, int C, int R, int S, int cp, float* g,
                                      int accumulate) {
   const int64_t n = (int64_t)K * C * R * S;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int s = i % S;
-    int64_t t = i / S;
-    int r = t % R; t /= R;
-    int c = t % C;
-    int k = t / C;
-    float v = dw[(((int64_t)k * R + r) * S + s) * cp + c];
-    g[i] = accumulate ? g[i] + v : v;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    wgrad_to_oihw_elem(dw, C, R, S, cp, g, accumulate, i);
+}
+
+// Batched forms: ONE launch serves every convolution of the network.  The items live in device memory; `start` is the
+// exclusive prefix sum of the per-item element counts, so a thread finds its item with a binary search.
+template <class Item>
+__device__ __forceinline__ int find_item(const Item* items, int n, int64_t i) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].start <= i) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void weight_prepare_batch_kernel(const SgbWeightItem* __restrict__ items, int n, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const SgbWeightItem it = items[find_item(items, n, i)];
+    weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f,
+                        it.add_identity, i - it.start);
+  }
+}
+
+__global__ void wgrad_to_oihw_batch_kernel(const SgbWgradItem* __restrict__ items, int n, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const SgbWgradItem it = items[find_item(items, n, i)];
+    wgrad_to_oihw_elem(it.dw, it.C, it.R, it.S, it.c_pad, it.g, it.accumulate, i - it.start);
   }
 }
 
@@ -406,6 +445,20 @@ extern "C" int sgb_wgrad_to_oihw(const float* dw, int K, int C, int R, int S, in
   wgrad_to_oihw_kernel<<<grid_for((int64_t)K * C * R * S), TPB, 0, (cudaStream_t)stream>>>(dw, K, C, R, S, c_pad, g,
                                                                                          accumulate);
   SGB_LAUNCH_CHECK("wgrad_to_oihw_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_weight_prepare_batch(const SgbWeightItem* items_dev, int n_items, int64_t total, void* stream) {
+  SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
+  weight_prepare_batch_kernel<<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(items_dev, n_items, total);
+  SGB_LAUNCH_CHECK("weight_prepare_batch_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_wgrad_to_oihw_batch(const SgbWgradItem* items_dev, int n_items, int64_t total, void* stream) {
+  SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
+  wgrad_to_oihw_batch_kernel<<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(items_dev, n_items, total);
+  SGB_LAUNCH_CHECK("wgrad_to_oihw_batch_kernel");
   return SGB_OK;
 }
 

@@ -4,6 +4,7 @@ libsgb200 kernels (kernels.py).  torch only owns memory, streams and the autogra
 Activations are channels_last bf16 (NHWC); parameters stay fp32 (state-dict compatible with the reference) and are
 re-laid-out to bf16 KRSC / CRSK once per optimizer step (cached on the parameter's version counter).
 """
+import weakref
 from types import SimpleNamespace
 from typing import Optional
 
@@ -27,12 +28,36 @@ __all__ = [
 
 
 _WEIGHT_EPOCH = [0]
+_NBT_DEFERRED = [False]  # True inside a TrainStep: it bumps every num_batches_tracked buffer with one foreach add
 
 
 def bump_weight_epoch():
     """Invalidates every WeightCache.  The Trainer calls this after each optimizer step: its kernels update the flat
     parameter buffer through raw pointers, which does not advance torch's per-tensor version counters."""
     _WEIGHT_EPOCH[0] += 1
+
+
+class StepContext:
+    """Per-TrainStep state of the batched plumbing: the filter caches its model touched, the device work tables of the
+    batched filter re-layout / gradient layout change (kept alive here because a captured CUDA graph reads them) and the
+    weight gradients waiting for the batched conversion."""
+
+    def __init__(self):
+        self.caches = {}          # id(cache) -> WeightCache
+        self.weight_table = None  # (device items, n, total)
+        self.weight_key = None
+        self.pending = []         # (dw fp32 KRSC, C, slot)
+        self.wgrad_table = None
+        self.wgrad_key = None
+
+
+_CTX = [None]  # the StepContext of the TrainStep that is executing (None: per-layer launches everywhere)
+
+
+def set_step_context(ctx: Optional["StepContext"]):
+    _CTX[0] = ctx
+    if ctx is not None:
+        ctx.pending.clear()
 
 
 class WeightCache:
@@ -42,14 +67,56 @@ class WeightCache:
         self.key = None
         self.krsc = None
         self.crsk = None
+        self.args = None  # (w, scale, add_identity, extra_key, c_pad) of the last prepare
+
+    @staticmethod
+    def _key(w, scale, add_identity, extra_key, c_pad):
+        return (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key, c_pad, _WEIGHT_EPOCH[0])
 
     def get(self, w: torch.Tensor, scale: Optional[torch.Tensor] = None, add_identity=False, extra_key=None, c_pad=None):
         """c_pad: channel count of the activation the filter is applied to (>= w.shape[1]; the extra channels are zero)."""
-        key = (w.data_ptr(), w._version, None if scale is None else (scale.data_ptr(), scale._version), add_identity, extra_key, c_pad, _WEIGHT_EPOCH[0])
+        key = self._key(w, scale, add_identity, extra_key, c_pad)
         if key != self.key:
             self.krsc, self.crsk = K.weight_prepare(w, c_pad=c_pad, scale=scale, add_identity=add_identity, out=(self.krsc, self.crsk))
             self.key = key
+            self.args = (w, scale, add_identity, extra_key, c_pad)
+        if _CTX[0] is not None:
+            _CTX[0].caches.setdefault(id(self), self)
         return self.krsc, self.crsk
+
+
+def refresh_weight_caches(ctx: StepContext, device) -> int:
+    """Re-prepares every filter the context's model uses with ONE batched launch (instead of one launch per layer on
+    first use) and marks those caches current.  Called by the train step after the optimizer moved the weights."""
+    live = [c for c in ctx.caches.values() if c.args is not None and c.krsc is not None]
+    live = [c for c in live if c.args[0].is_cuda and c.args[0].dtype == torch.float32 and c.args[0].is_contiguous()]
+    if not live:
+        return 0
+    ident = tuple((c.args[0].data_ptr(), c.krsc.data_ptr(), None if c.crsk is None else c.crsk.data_ptr(), None if c.args[1] is None else c.args[1].data_ptr(), c.args[2], c.args[4]) for c in live)
+    if ctx.weight_key != ident:
+        entries = [(c.args[0], c.args[1], c.krsc, c.crsk, c.krsc.shape[3], c.args[2]) for c in live]
+        ctx.weight_table = K.weight_prepare_batch(entries, device)
+        ctx.weight_key = ident
+    table, n, total = ctx.weight_table
+    K.run_weight_prepare_batch(table, n, total)
+    for c in live:
+        c.key = WeightCache._key(*c.args)
+    return n
+
+
+def flush_wgrads(ctx: StepContext, device) -> int:
+    """Converts every deferred fp32 KRSC weight gradient of this step into its OIHW gradient slot with one launch."""
+    pend = ctx.pending
+    if not pend:
+        return 0
+    ident = tuple((dw.data_ptr(), g.data_ptr(), c) for dw, c, g in pend)
+    if ctx.wgrad_key != ident:
+        ctx.wgrad_table = K.wgrad_to_oihw_batch_table([(dw, c, g, True) for dw, c, g in pend], device)
+        ctx.wgrad_key = ident
+    table, n, total = ctx.wgrad_table
+    K.run_wgrad_to_oihw_batch(table, n, total)
+    pend.clear()
+    return n
 
 
 def _mg(p):
@@ -67,6 +134,9 @@ def _deliver(slot, grad):
 
 def _wgrad(x, dy, r, s, stride, pad, cin, slot):
     dw = K.conv_wgrad(x, dy, r, s, stride, pad)
+    if slot is not None and _CTX[0] is not None:
+        _CTX[0].pending.append((dw, cin, slot))  # dw (step arena or a plain tensor) stays referenced until flush_wgrads()
+        return None
     if slot is not None:
         K.wgrad_to_oihw(dw, cin, out=slot, accumulate=True)
         return None
@@ -119,7 +189,7 @@ class _ConvBnAct(torch.autograd.Function):
         y_raw = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, stats=stats)
         res = K.as_nhwc(residual) if residual is not None else None
         out, mean, rstd = K.bn_act_fwd(y_raw, stats, gamma, beta, cfg.running_mean, cfg.running_var, cfg.eps, cfg.momentum, cfg.act, res)
-        if cfg.num_batches_tracked is not None:
+        if cfg.num_batches_tracked is not None and not _NBT_DEFERRED[0]:
             cfg.num_batches_tracked += 1
         ctx.save_for_backward(x, y_raw, out, gamma, mean, rstd, beta)
         ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_res = cfg, crsk, tuple(w.shape), residual is not None
@@ -209,9 +279,10 @@ class _QARepVGG(torch.autograd.Function):
         if bias1 is not None:
             ab = bias1 * alpha if alpha is not None else bias1
         out, coef = K.qarep_fwd(y3, u, g3, b3, ab, gp, bp, cfg.rm3, cfg.rv3, cfg.rmp, cfg.rvp, cfg.eps, cfg.eps, cfg.momentum, cfg.act, cfg.use_post_bn)
-        for nbt in cfg.nbt:
-            if nbt is not None:
-                nbt += 1
+        if not _NBT_DEFERRED[0]:
+            for nbt in cfg.nbt:
+                if nbt is not None:
+                    nbt += 1
         ctx.save_for_backward(x, y3, u, out, coef, g3, gp if gp is not None else g3, w1, bias1 if bias1 is not None else g3, alpha if alpha is not None else g3)
         ctx.cfg, ctx.c3, ctx.c1 = cfg, c3, c1
         ctx.flags = (bias1 is not None, alpha is not None, gp is not None, w3.shape[1])

@@ -30,6 +30,62 @@ def _timed(name, *args):
     tag = tuple(getattr(d, f) for f in ("N", "H", "W", "C", "K", "R", "stride") if hasattr(d, f)) if d is not None else ()
     PROFILE.append((name, a, b, tag))
 
+class StepArena:
+    """Zero-initialised scratch of ONE training step (BatchNorm / moment accumulators, fp32 weight-gradient buffers).
+
+    Outside a step (`active` False) `zeros()` is plain torch.zeros.  training/sg_trainer.TrainStep brackets every step with
+    begin_step() / end_step(): the first bracketed step only measures the demand, later steps sub-allocate from one buffer
+    that a single memset clears, instead of one fill kernel per tensor (~360 launches per YOLO-NAS-S step).  Tensors
+    handed out never outlive the step that requested them."""
+
+    ALIGN = 256
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.need = 0
+        self.active = False
+
+    def begin_step(self, device):
+        if self.buf is None and self.need > 0:
+            self.buf = torch.empty(int(self.need * 1.25) + (1 << 20), dtype=torch.uint8, device=device)
+            self.high = self.buf.numel()
+        if self.buf is not None:
+            self.buf[: min(self.high, self.buf.numel())].zero_()
+            self.high = 0
+        self.off = 0
+        self.need = 0
+        self.active = True
+
+    def end_step(self):
+        self.active = False
+        if self.buf is not None:
+            self.high = self.off
+
+    def zeros(self, shape, dtype, device):
+        if not self.active:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        span = (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.need += span
+        if self.buf is None or self.off + span > self.buf.numel() or self.buf.device != torch.device(device):
+            return torch.zeros(shape, dtype=dtype, device=device)
+        out = self.buf[self.off : self.off + nbytes].view(dtype).view(shape)
+        self.off += span
+        return out
+
+
+NO_ARENA = StepArena()  # never activated: zeros() is torch.zeros
+ARENA = NO_ARENA        # the arena of the TrainStep that is executing (training/sg_trainer.py swaps it in and out)
+
+
+def zeros(shape, dtype, device):
+    return ARENA.zeros(tuple(shape) if not isinstance(shape, int) else (shape,), dtype, device)
+
+
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU}
 
 
@@ -114,7 +170,7 @@ def conv_desc(x: torch.Tensor, K: int, R: int, S: int, stride: int, pad: int, y:
 
 
 def new_stats(C: int, device, nacc=2) -> torch.Tensor:
-    return torch.zeros((STATS_REPL, nacc, C), dtype=torch.float64, device=device)
+    return zeros((STATS_REPL, nacc, C), torch.float64, device)
 
 
 # ------------------------------------------------------------------------------------------------ conv family
@@ -164,7 +220,7 @@ def conv_wgrad(x, dy, R, S, stride, pad, dw_krsc=None):
     n, c, h, w = x.shape
     K = dy.shape[1]
     if dw_krsc is None:
-        dw_krsc = torch.zeros((K, R, S, c), dtype=torch.float32, device=x.device)
+        dw_krsc = zeros((K, R, S, c), torch.float32, x.device)
     d = conv_desc(x, K, R, S, stride, pad, dy, dy.shape[2], dy.shape[3])
     _timed("sgb_conv_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw_krsc), _stream())
     return dw_krsc
@@ -192,6 +248,48 @@ def wgrad_to_oihw(dw_krsc: torch.Tensor, C: int, out: Optional[torch.Tensor] = N
     g = out if out is not None else torch.empty((K, C, R, S), dtype=torch.float32, device=dw_krsc.device)
     _timed("sgb_wgrad_to_oihw", _ptr(dw_krsc), K, C, R, S, cp, _ptr(g), 1 if accumulate else 0, _stream())
     return g
+
+
+def _item_table(items) -> torch.Tensor:
+    """ctypes item structs -> device byte tensor (the batched kernels read their work list from device memory)."""
+    arr = (type(items[0]) * len(items))(*items)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host
+
+
+def weight_prepare_batch(entries, device) -> torch.Tensor:
+    """entries: (w fp32 OIHW, scale or None, krsc, crsk or None, c_pad, add_identity).  Returns the device item table
+    to pass to run_weight_prepare_batch (build once, replay every step)."""
+    items, start = [], 0
+    for w, scale, krsc, crsk, c_pad, add_identity in entries:
+        Kk, C, R, S = w.shape
+        it = L.WeightItem()
+        it.w, it.scale, it.krsc, it.crsk = w.data_ptr(), (scale.data_ptr() if scale is not None else None), krsc.data_ptr(), (crsk.data_ptr() if crsk is not None else None)
+        it.K, it.C, it.R, it.S, it.c_pad, it.add_identity, it.start = Kk, C, R, S, c_pad, 1 if add_identity else 0, start
+        start += krsc.numel() + (crsk.numel() if crsk is not None else 0)
+        items.append(it)
+    return _item_table(items).to(device), len(items), start
+
+
+def run_weight_prepare_batch(table, n, total):
+    _timed("sgb_weight_prepare_batch", _ptr(table), n, total, _stream())
+
+
+def wgrad_to_oihw_batch_table(entries, device):
+    """entries: (dw fp32 KRSC, C, slot fp32 OIHW, accumulate)."""
+    items, start = [], 0
+    for dw, C, g, accumulate in entries:
+        Kk, R, S, cp = dw.shape
+        it = L.WgradItem()
+        it.dw, it.g = dw.data_ptr(), g.data_ptr()
+        it.K, it.C, it.R, it.S, it.c_pad, it.accumulate, it.start = Kk, C, R, S, cp, 1 if accumulate else 0, start
+        start += Kk * C * R * S
+        items.append(it)
+    return _item_table(items).to(device), len(items), start
+
+
+def run_wgrad_to_oihw_batch(table, n, total):
+    _timed("sgb_wgrad_to_oihw_batch", _ptr(table), n, total, _stream())
 
 
 def convt2x2_fprop(x_small, w_up, bias, C_up):
@@ -268,7 +366,7 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
         dy = dy.contiguous(memory_format=torch.channels_last)
         if nhwc_pitch(dy) != d.y_pitch:
             raise L.SgbError("dy pitch mismatch")
-    sums = torch.zeros((2, c), dtype=torch.float64, device=x.device)
+    sums = zeros((2, c), torch.float64, x.device)
     # the forward output is only read when a residual entered the activation; otherwise the mask is recomputed from x
     y_arg = y if (want_residual_grad or beta is None) else None
     _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
@@ -282,16 +380,16 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
         dres = empty_nhwc(n, c, h, w, x.device)
         d.r_pitch = nhwc_pitch(dres)
     if dgamma is None:
-        dgamma = torch.zeros(c, dtype=torch.float32, device=x.device)
+        dgamma = zeros((c,), torch.float32, x.device)
     if dbeta is None:
-        dbeta = torch.zeros(c, dtype=torch.float32, device=x.device)
+        dbeta = zeros((c,), torch.float32, x.device)
     _timed("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
     return dx, dres, dgamma, dbeta
 
 
 def channel_stats(x) -> torch.Tensor:
     n, c, h, w = x.shape
-    st = torch.zeros((1, 2, c), dtype=torch.float64, device=x.device)
+    st = zeros((1, 2, c), torch.float64, x.device)
     _timed("sgb_channel_stats", _ptr(x), n * h * w, c, nhwc_pitch(x), 0, _ptr(st), _stream())
     return st
 
@@ -314,7 +412,7 @@ def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp,
     n, c, h, w = y3.shape
     out = empty_nhwc(n, c, h, w, y3.device)
     d = qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn)
-    mom = torch.zeros((5, c), dtype=torch.float64, device=y3.device)
+    mom = zeros((5, c), torch.float64, y3.device)
     _timed("sgb_qarep_moments", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _stream())
     coef = torch.empty((9, c), dtype=torch.float32, device=y3.device)
     _timed("sgb_qarep_fwd", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _ptr(gamma3), _ptr(beta3), _ptr(bias1a), _ptr(gamma_p), _ptr(beta_p), _ptr(rm3), _ptr(rv3), _ptr(rmp), _ptr(rvp), _ptr(out), _ptr(coef), _stream())
@@ -329,10 +427,10 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
     if nhwc_pitch(dout) != nhwc_pitch(out):
         dout = dout.contiguous(memory_format=torch.channels_last)
     d = qarep_desc(y3, u, out, eps3, eps_post, 0.0, act, use_post_bn)
-    sums = torch.zeros((3, c), dtype=torch.float64, device=y3.device)
+    sums = zeros((3, c), torch.float64, y3.device)
     _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
     dy3, du = torch.empty_like(y3), torch.empty_like(u)
-    z = lambda: torch.zeros(c, dtype=torch.float32, device=y3.device)  # noqa: E731
+    z = lambda: zeros((c,), torch.float32, y3.device)  # noqa: E731
     acc = acc or (None,) * 5
     dg3, db3, dab, dgp, dbp = [a if a is not None else z() for a in acc]
     _timed("sgb_qarep_bwd_apply", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
@@ -378,7 +476,7 @@ def scale_add(x1, a_dev, x2=None, out=None):
 def channel_dot(a, b) -> torch.Tensor:
     """fp64 [C]: sum over pixels of a*b."""
     n, c, h, w = a.shape
-    out = torch.zeros(c, dtype=torch.float64, device=a.device)
+    out = zeros((c,), torch.float64, a.device)
     _timed("sgb_channel_dot", _ptr(a), nhwc_pitch(a), 0, _ptr(b), nhwc_pitch(b), 0, n * h * w, c, _ptr(out), _stream())
     return out
 

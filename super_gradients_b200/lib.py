@@ -33,6 +33,14 @@ class Epilogue(Structure):
     ]
 
 
+class WeightItem(Structure):  # SgbWeightItem
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("krsc", c_void_p), ("crsk", c_void_p)] + [(n, c_int32) for n in ("K", "C", "R", "S", "c_pad", "add_identity")] + [("start", c_int64)]
+
+
+class WgradItem(Structure):  # SgbWgradItem
+    _fields_ = [("dw", c_void_p), ("g", c_void_p)] + [(n, c_int32) for n in ("K", "C", "R", "S", "c_pad", "accumulate")] + [("start", c_int64)]
+
+
 class BnDesc(Structure):
     _fields_ = [
         ("M", c_int64),
@@ -116,6 +124,8 @@ _SIGNATURES = {
     "sgb_conv_wgrad": (c_int, [POINTER(ConvDesc), P, P, P, P]),
     "sgb_weight_prepare": (c_int, [P, _I, _I, _I, _I, _I, P, P, P, _I, P]),
     "sgb_wgrad_to_oihw": (c_int, [P, _I, _I, _I, _I, _I, P, _I, P]),
+    "sgb_weight_prepare_batch": (c_int, [P, _I, c_int64, P]),
+    "sgb_wgrad_to_oihw_batch": (c_int, [P, _I, c_int64, P]),
     "sgb_convt2x2_fprop": (c_int, [POINTER(ConvDesc), P, P, P, P, P]),
     "sgb_nchw_f32_to_nhwc_bf16": (c_int, [P, _I, _I, _I, _I, P, _I, _I, _I, P]),
     "sgb_nhwc_bf16_to_nchw_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, P, P]),

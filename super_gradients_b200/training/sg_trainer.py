@@ -125,6 +125,11 @@ class TrainStep:
         self.graph = None
         self.static_in = None
         self.static_out = None
+        self._filters_stale = False
+        self.batched_plumbing = True
+        self.arena = K.StepArena()   # zero-initialised scratch of one step (owned here: a captured graph replays its addresses)
+        self.ctx = SF.StepContext()  # filter caches + batched work tables of this model
+        self._nbt = [b for n, b in model.named_buffers() if n.endswith("num_batches_tracked")]
 
     # -------------------------------------------------------------------------------------------- host-side schedule
     def set_hyper_params(self, lr: float, ema_decay_value: Optional[float] = None):
@@ -150,11 +155,45 @@ class TrainStep:
 
     # -------------------------------------------------------------------------------------------- device-side step
     def forward_backward(self, inputs, targets):
+        # per-step plumbing that would otherwise cost one tiny launch per layer: one memset for every zero-initialised
+        # scratch tensor (K.ARENA), one batched bf16 re-layout of all filters, one batched KRSC -> OIHW gradient pass and
+        # one foreach add for the num_batches_tracked counters
+        if not self.batched_plumbing:
+            return self._forward_backward_plain(inputs, targets)
+        self.arena.begin_step(self.device)
+        K.ARENA = self.arena
+        SF.set_step_context(self.ctx)
+        SF._NBT_DEFERRED[0] = True
+        try:
+            if self._filters_stale:
+                if SF.refresh_weight_caches(self.ctx, self.device):
+                    self._filters_stale = False
+            outputs = self.model(inputs)
+            out = self.criterion(outputs, targets)
+            loss, items = out if isinstance(out, tuple) else (out, out.detach().reshape(1))
+            loss.backward()
+            SF.flush_wgrads(self.ctx, self.device)
+            if self._nbt:
+                torch._foreach_add_(self._nbt, 1)
+        finally:
+            SF._NBT_DEFERRED[0] = False
+            SF.set_step_context(None)
+            self.arena.end_step()
+            K.ARENA = K.NO_ARENA
+        # parameters whose gradient arrived through plain autograd (e.g. views created outside a fused Function)
+        for _, p in self.flat.order:
+            if p.grad is not None:
+                p.main_grad.add_(p.grad)
+                p.grad = None
+        return loss.detach(), items
+
+    def _forward_backward_plain(self, inputs, targets):
+        """The same step with every per-layer launch in place (batched_plumbing = False): the reference behaviour the
+        batched path is tested against."""
         outputs = self.model(inputs)
         out = self.criterion(outputs, targets)
         loss, items = out if isinstance(out, tuple) else (out, out.detach().reshape(1))
         loss.backward()
-        # parameters whose gradient arrived through plain autograd (e.g. views created outside a fused Function)
         for _, p in self.flat.order:
             if p.grad is not None:
                 p.main_grad.add_(p.grad)
@@ -180,6 +219,7 @@ class TrainStep:
                 K.ema_update(self.ema_buffers, f.buffers, self.ema_decay)
         f.zero_grad()
         SF.bump_weight_epoch()
+        self._filters_stale = True
 
     def _step_eager(self, inputs, targets, do_optimizer_step=True):
         loss, items = self.forward_backward(inputs, targets)
@@ -214,6 +254,7 @@ class TrainStep:
         """Captures the whole step in a CUDA graph (static shapes: pad the targets to a fixed n_max).  The LR is read
         from device memory, so set_hyper_params() keeps working between replays."""
         clone = lambda t: t.clone() if torch.is_tensor(t) else type(t)(clone(u) for u in t)  # noqa: E731
+        warmup = max(warmup, 2)  # step 1 sizes the zero arena, step 2 builds the batched work tables the graph replays
         self.static_in = (clone(inputs), clone(targets))
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
