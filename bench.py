@@ -19,6 +19,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec YOLO-NAS-S 640 bf16 train"
+# dram__bytes_read.sum + dram__bytes_write.sum of the conv family over ONE step, from the ncu launch list of this command
+# (profiles/r1_launches_graph_step.txt: 18.936 GB read + 2.052 GB written at per-GPU batch 32); None for other batches
+NCU_CONV_DRAM_BYTES_PER_STEP = {32: 20.988e9}
 TRAIN_GFLOP_PER_IMG = 101.6  # 3 x 2 x 16.939 GMAC (fprop + dgrad + wgrad of the train graph)
 IMG, BATCH, NCLS, NBOX = 640, 32, 80, 8
 
@@ -185,10 +188,15 @@ def run_ours(args):
         try:
             step.capture(dev_x[0], dev_t[0], warmup=2)
         except Exception as e:  # noqa: BLE001
-            if rank == 0:
-                print(f"[bench] CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr)
+            print(f"[bench] rank {rank}: CUDA graph capture failed ({e!r}); running eagerly", file=sys.stderr)
             step.graph = None
             use_graph = False
+        if world > 1:  # all ranks replay the graph or none does
+            ok = torch.tensor([1 if use_graph else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                step.graph = None
+                use_graph = False
 
     def barrier():
         if world > 1:
@@ -266,28 +274,38 @@ def run_ours(args):
     e2e = world * batch * e2e_steps / (ms2 / 1e3)
     h2d = host_x[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_t[0])
 
-    # ---- (C) roofline of the dominant kernel family (implicit-GEMM convolutions): CUDA events around every launch
+    # ---- (C) roofline of the dominant kernel family (implicit-GEMM convolutions): CUDA events around every launch.
+    # EVERY rank runs these eager steps (they contain the gradient all-reduce); only rank 0 reports.
     roof = None
+    K.PROFILE.clear()
+    K.PROFILE_ON[0] = True
+    n_prof = 2
+    for i in range(n_prof):
+        step.set_hyper_params(lr_at(i), 0.9997)
+        step._step_eager(dev_x[i % nbuf], dev_t[i % nbuf])
+    torch.cuda.synchronize()
+    K.PROFILE_ON[0] = False
+    barrier()
     if rank == 0:
         tf_peak, hbm_peak, which = peaks()
-        K.PROFILE.clear()
-        K.PROFILE_ON[0] = True
-        n_prof = 2
-        for i in range(n_prof):
-            step.set_hyper_params(lr_at(i), 0.9997)
-            step._step_eager(dev_x[i % nbuf], dev_t[i % nbuf])
-        torch.cuda.synchronize()
-        K.PROFILE_ON[0] = False
-        per = {}
-        for name, a, b, _tag in K.PROFILE:
+        per, conv_bytes = {}, 0.0
+        for name, a, b, tag in K.PROFILE:
             per[name] = per.get(name, 0.0) + a.elapsed_time(b)
+            if name.startswith("sgb_conv_") and len(tag) == 7:  # activations in + out of the call (filters are noise)
+                N_, H_, W_, C_, K_, _R, s_ = tag
+                conv_bytes += 2.0 * N_ * (H_ * W_ * C_ + ((H_ + s_ - 1) // s_) * ((W_ + s_ - 1) // s_) * K_)
         conv_ms = sum(v for k, v in per.items() if k.startswith("sgb_conv")) / n_prof
+        conv_bytes /= n_prof
         flops = TRAIN_GFLOP_PER_IMG * 1e9 * batch
         achieved = flops / (conv_ms / 1e3) / 1e12
         roof = {
-            "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
-            "kernel": "igemm_conv_kernel + wgrad_kernel (all conv fprop/dgrad/wgrad launches of one step)", "peak_source": which,
-            "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms / args.steps),
+            "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+            "traffic": NCU_CONV_DRAM_BYTES_PER_STEP.get(batch),
+            "kernel": "conv family of one step = one 'launch': conv3x3_halo_kernel + wgrad3x3_halo_kernel (3x3 stride 1), conv_umma_kernel + wgrad_umma_kernel (1x1, stride 2)",
+            "peak_source": which, "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms / args.steps),
+            "algorithmic_flops_per_step": flops, "algorithmic_activation_bytes_per_step": conv_bytes,
+            "hbm_view": {"achieved_GBps": conv_bytes / (conv_ms / 1e3) / 1e9, "peak_GBps": hbm_peak, "frac": conv_bytes / (conv_ms / 1e3) / 1e9 / hbm_peak,
+                         "note": "these layers have 32..192 channels: the family is HBM / shared-memory-operand bound, not tensor bound (DESIGN.md section 5)"},
             "per_call_ms": {k: v / n_prof for k, v in sorted(per.items(), key=lambda kv: -kv[1])[:12]},
         }  # fmt: skip
 

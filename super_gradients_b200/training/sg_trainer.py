@@ -10,6 +10,7 @@ without a GradScaler, two optimizer launches per step, ONE flat NCCL all-reduce 
 torchrun, and (optionally) the whole step captured in a CUDA graph.
 Out of scope: hydra recipes, dataset classes, loggers, metrics bookkeeping, QAT/PTQ, KD.
 """
+import datetime
 import math
 import os
 import time
@@ -86,7 +87,8 @@ def setup_device(device: Optional[str] = None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initialized():
-        torch.distributed.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local_rank))
+        # a finite timeout turns a lost rank / mismatched collective into an error instead of an endless wait
+        torch.distributed.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=4))
     return torch.device("cuda", local_rank)
 
 
@@ -266,7 +268,10 @@ class TrainStep:
         torch.cuda.synchronize()
         SF.bump_weight_epoch()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # with NCCL in the step other threads of the process (the process-group watchdog) touch CUDA during capture:
+        # thread-local capture mode keeps those calls from invalidating the capture
+        mode = "thread_local" if self.world > 1 else "global"
+        with torch.cuda.graph(g, capture_error_mode=mode):
             self.static_out = self._step_eager(*self.static_in)
         self.graph = g
         return g
