@@ -305,7 +305,7 @@ def run_ours(args):
             "peak_source": which, "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms / args.steps),
             "algorithmic_flops_per_step": flops, "algorithmic_activation_bytes_per_step": conv_bytes,
             "hbm_view": {"achieved_GBps": conv_bytes / (conv_ms / 1e3) / 1e9, "peak_GBps": hbm_peak, "frac": conv_bytes / (conv_ms / 1e3) / 1e9 / hbm_peak,
-                         "note": "these layers have 32..192 channels: the family is HBM / shared-memory-operand bound, not tensor bound (DESIGN.md section 5)"},
+                         "note": "these layers have 32..192 channels: the family is HBM / shared-memory-operand bound, not tensor bound (DESIGN.md section 3)"},
             "per_call_ms": {k: v / n_prof for k, v in sorted(per.items(), key=lambda kv: -kv[1])[:12]},
         }  # fmt: skip
 
