@@ -191,6 +191,32 @@ def golden_loss():
     torch.save(out, os.path.join(HERE, "loss.pt"))
 
 
+def golden_pose_nms():
+    """YoloNASPosePostPredictionCallback of the unmodified reference on seeded decoded pose outputs."""
+    from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_post_prediction_callback import YoloNASPosePostPredictionCallback
+
+    gen = torch.Generator().manual_seed(9)
+    out = {}
+    for case, (B, L, J, thr, pre, post) in {
+        "regular": (2, 400, 17, 0.5, 1000, 100),
+        "topk": (1, 900, 17, 0.2, 300, 50),
+        "few_joints": (2, 300, 5, 0.6, 1000, 300),
+        "nothing_passes": (1, 100, 17, 2.0, 1000, 100),
+    }.items():
+        xy = torch.rand(B, L, 2, generator=gen) * 300
+        wh = torch.rand(B, L, 2, generator=gen) * 80 + 6
+        boxes = torch.cat([xy, xy + wh], -1)
+        conf = torch.rand(B, L, 1, generator=gen)
+        coords = torch.rand(B, L, J, 2, generator=gen) * 400
+        jscores = torch.rand(B, L, J, generator=gen)
+        cb = YoloNASPosePostPredictionCallback(pose_confidence_threshold=thr, nms_iou_threshold=0.6, pre_nms_max_predictions=pre, post_nms_max_predictions=post)
+        res = cb(((boxes, conf, coords, jscores), None))
+        out[case] = dict(boxes=boxes, conf=conf, coords=coords, jscores=jscores,
+                         params=dict(pose_confidence_threshold=thr, nms_iou_threshold=0.6, pre_nms_max_predictions=pre, post_nms_max_predictions=post),
+                         result=[(r.poses.clone(), r.scores.clone(), r.bboxes_xyxy.clone()) for r in res])
+    torch.save(out, os.path.join(HERE, "pose_nms.pt"))
+
+
 def golden_nms():
     from super_gradients.training.models.detection_models.pp_yolo_e import PPYoloEPostPredictionCallback
 
@@ -300,7 +326,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "tiny_yolo_nas", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "tiny_yolo_nas", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

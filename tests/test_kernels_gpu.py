@@ -362,6 +362,35 @@ def test_nms_bit_exact_vs_oracle_and_reference_golden(golden, case):
         np.testing.assert_array_equal(_canon(out[b, : cnt[b]]), _canon(rr))
 
 
+@pytest.mark.parametrize("case", ["regular", "topk", "few_joints", "nothing_passes"])
+def test_pose_post_prediction_callback_vs_oracle_and_reference_golden(golden, case):
+    """Row N2: YoloNASPosePostPredictionCallback on the batched NMS kernel (single score, class-agnostic, >= threshold)."""
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPosePostPredictionCallback
+
+    g = golden("pose_nms")[case]
+    p = g["params"]
+    ref, ref_idx = O.yolo_nas_pose_postprocess(g["boxes"], g["conf"], g["coords"], g["jscores"], **p)
+    cb = YoloNASPosePostPredictionCallback(**p)
+    dev = [g[k].to(DEV) for k in ("boxes", "conf", "coords", "jscores")]
+    rows, poses, idx, cnt = cb.forward_batched((tuple(dev), None))
+    preds = cb((tuple(dev), None))
+    assert len(preds) == len(ref)
+    for b, ((rposes, rscores, rboxes), kept) in enumerate(zip(ref, ref_idx)):
+        n = int(cnt[b])
+        assert n == kept.shape[0]
+        np.testing.assert_array_equal(idx[b, :n].cpu().numpy(), kept)  # the same anchors in the same order
+        np.testing.assert_array_equal(preds[b].scores.cpu().numpy(), rscores)
+        np.testing.assert_array_equal(preds[b].bboxes_xyxy.cpu().numpy(), rboxes)
+        np.testing.assert_array_equal(preds[b].poses.cpu().numpy(), rposes)
+        # and the unmodified reference callback's own output
+        gp, gs, gb = g["result"][b]
+        np.testing.assert_array_equal(preds[b].poses.cpu().numpy(), gp.numpy())
+        np.testing.assert_array_equal(preds[b].scores.cpu().numpy(), gs.numpy())
+        np.testing.assert_array_equal(preds[b].bboxes_xyxy.cpu().numpy(), gb.numpy())
+    with pytest.raises(ValueError):
+        YoloNASPosePostPredictionCallback(0.5, 0.6, pre_nms_max_predictions=10, post_nms_max_predictions=20)
+
+
 def test_nms_config2_shape():
     """B=32, 8400 anchors, 80 classes, thr 0.25 / top-k 1000 / IoU 0.7 / max 300."""
     k = K()

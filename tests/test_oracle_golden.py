@@ -209,3 +209,21 @@ def test_bf16_emulation_sensitivity(golden):
     norm_ratio = sorted(abs(float(torch.log(p64[k].grad.float().norm() / p32[k].grad.norm()))) for k in live if p32[k].grad is not None and p32[k].grad.norm() > 1e-6)
     assert 0.3 < errs[len(errs) // 2] < 0.65, errs[len(errs) // 2]      # measured 0.51
     assert norm_ratio[len(norm_ratio) // 2] < 0.1, norm_ratio[len(norm_ratio) // 2]
+
+
+@pytest.mark.parametrize("case", ["regular", "topk", "few_joints", "nothing_passes"])
+def test_pose_postprocess_oracle_matches_reference(golden, case):
+    """oracle.yolo_nas_pose_postprocess == the unmodified YoloNASPosePostPredictionCallback (row N2): same instances in
+    the same order (scores are continuous random numbers: no exact ties), bit-identical boxes / scores / poses."""
+    g = golden("pose_nms")[case]
+    res, idx = O.yolo_nas_pose_postprocess(g["boxes"], g["conf"], g["coords"], g["jscores"], **g["params"])
+    assert len(res) == len(g["result"])
+    for (poses, scores, boxes), kept, (rp, rs, rb) in zip(res, idx, g["result"]):
+        np.testing.assert_array_equal(scores, rs.numpy())
+        np.testing.assert_array_equal(boxes, rb.numpy())
+        np.testing.assert_array_equal(poses, rp.numpy())
+        assert poses.shape[0] == kept.shape[0] <= g["params"]["post_nms_max_predictions"]
+    if case == "topk":
+        assert any(int((c.reshape(-1) >= g["params"]["pose_confidence_threshold"]).sum()) > g["params"]["pre_nms_max_predictions"] for c in g["conf"])
+    if case == "nothing_passes":
+        assert all(r[0].shape[0] == 0 for r in res)
