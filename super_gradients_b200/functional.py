@@ -109,14 +109,24 @@ def flush_wgrads(ctx: StepContext, device) -> int:
     pend = ctx.pending
     if not pend:
         return 0
+    # a weight used twice in one step (shared filters) has two pending buffers for ONE gradient slot: the batched kernel
+    # would race on it, so every contribution after the first goes through the per-layer kernel (stream-ordered)
+    seen, first, rest = set(), [], []
+    for item in pend:
+        (rest if item[2].data_ptr() in seen else first).append(item)
+        seen.add(item[2].data_ptr())
+    if rest:
+        pend[:] = first
     ident = tuple((dw.data_ptr(), g.data_ptr(), c) for dw, c, g in pend)
     if ctx.wgrad_key != ident:
         ctx.wgrad_table = K.wgrad_to_oihw_batch_table([(dw, c, g, True) for dw, c, g in pend], device)
         ctx.wgrad_key = ident
     table, n, total = ctx.wgrad_table
     K.run_wgrad_to_oihw_batch(table, n, total)
+    for dw, c, g in rest:
+        K.wgrad_to_oihw(dw, c, out=g, accumulate=True)
     pend.clear()
-    return n
+    return n + len(rest)
 
 
 def _mg(p):
