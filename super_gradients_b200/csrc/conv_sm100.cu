@@ -1,18 +1,21 @@
-// Blackwell-native implicit-GEMM convolution: tcgen05.mma (UMMA, M=128) with the accumulator in TMEM, the A operand
-// streamed by TMA *im2col* descriptors straight from the NHWC activation tensor, the B operand (KRSC / CRSK filters)
-// by tiled TMA, a persistent warp-specialised CTA per SM:
+// Blackwell-native implicit-GEMM convolution, TMA-im2col engine: tcgen05.mma (UMMA, M=128) with the accumulator in TMEM,
+// the A operand streamed by TMA *im2col* descriptors straight from the NHWC activation tensor, the B operand (KRSC / CRSK
+// filters) by tiled TMA, persistent warp-specialised CTAs (1-3 co-resident per SM):
 //     warp 0      TMA producer            (one elected lane)
-//     warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//     warp 1      TMEM allocator + MMA issuer (the warp stays converged; the elected lane's tcgen05.mma / commit issue)
 //     warps 2..5  epilogue: tcgen05.ld -> (scale, shift, residual, activation) -> bf16 -> global,
 //                 plus the per-channel sum / sum-of-squares needed by train-mode BatchNorm (butterfly transpose-reduce)
 // Two TMEM accumulators are ping-ponged so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Serves: fprop of every 1x1 / 3x3, stride 1 / 2 convolution with C % 16 == 0 and K % 8 == 0, and dgrad of the
-// stride-1 ones (a convolution of dy with the spatially flipped CRSK filter).  Everything else (3-channel stems, 7x7,
-// strided dgrad, wgrad, ragged channel counts) stays on the generic kernels in conv_mma.cu.
+// Serves what the halo-tile engine (conv_halo_sm100.cu: every 3x3 stride-1 convolution with C in {32..128}) does not:
+// 1x1 convolutions, stride-2 3x3 (fprop; dgrad as s^2 output-parity classes through the explicit tap table), C >= 192,
+// fused scale / shift / residual / activation epilogues, and the weight gradients of those shapes (wgrad_umma_kernel,
+// MN-major operands).  launch() / wgrad_launch() try the halo engine first.  3-channel stems that are not padded to
+// 16 channels, 7x7, ragged channel counts and fp32 outputs stay on the mma.sync kernels of conv_mma.cu.
 //
-// Reference arithmetic replaced: nn.Conv2d forward / input-gradient as used by modules/qarepvgg_block.py:184-204,
-// modules/conv_bn_act_block.py:92-93, training/models/classification_models/resnet.py:53-84.
+// Reference arithmetic replaced: nn.Conv2d forward / input-gradient / weight-gradient as used by
+// modules/qarepvgg_block.py:184-204, modules/conv_bn_act_block.py:92-93,
+// training/models/classification_models/resnet.py:53-84.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -27,7 +30,6 @@ namespace sm100 {
 
 constexpr int BLOCK_M = 128;
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
 constexpr int MAX_STAGES = 8;
 
 struct Params {
