@@ -217,6 +217,66 @@ def golden_pose_nms():
     torch.save(out, os.path.join(HERE, "pose_nms.pt"))
 
 
+def golden_pose():
+    """Rows L7 / L8: YoloNASPoseNDFLHeads decode (through a real yolo_nas_pose_n model at 96x96) and YoloNASPoseLoss value +
+    gradients on seeded raw predictions / targets, all from the unmodified reference."""
+    from super_gradients.training import models
+    from super_gradients.training.losses.yolo_nas_pose_loss import YoloNASPoseLoss
+
+    out = {}
+    torch.manual_seed(21)
+    m = models.get("yolo_nas_pose_n", num_classes=17).train()
+    heads = m.heads
+    cap = {}
+    for i in (1, 2, 3):
+        getattr(heads, f"head{i}").register_forward_hook(lambda mod, inp, o, i=i: cap.__setitem__(i, tuple(t.detach().clone() for t in o)))
+    x = torch.randn(2, 3, 96, 96)
+    with torch.no_grad():
+        decoded, raw = m(x)
+    out["decode"] = dict(
+        levels=[cap[i] for i in (1, 2, 3)],  # (reg_distri, cls_logit, pose_regression, pose_logits) per level
+        strides=tuple(int(s) for s in heads.fpn_strides), reg_max=int(heads.reg_max), cell_offset=float(heads.grid_cell_offset), cell_scale=float(heads.grid_cell_scale),
+        pose_offset_multiplier=float(heads.pose_offset_multiplier), compensate=bool(heads.compensate_grid_cell_offset),
+        decoded=tuple(t.clone() for t in decoded), raw=tuple(t.clone() if torch.is_tensor(t) else t for t in raw),
+    )
+    # ---- loss on seeded raw predictions (anchors of a 96x96 image, strides 8/16/32 -> L = 144 + 36 + 9)
+    from super_gradients.training.models.detection_models.pp_yolo_e.pp_yolo_head import generate_anchors_for_grid_cell
+
+    gen = torch.Generator().manual_seed(22)
+    B, J = 3, 17
+    feats = [torch.zeros(B, 1, 96 // s, 96 // s) for s in (8, 16, 32)]
+    anchors, anchor_points, nums, stride_tensor = generate_anchors_for_grid_cell(feats, (8, 16, 32), 5.0, 0.5)
+    L = anchor_points.shape[0]
+    sigmas = [0.026, 0.025, 0.025, 0.035, 0.035, 0.079, 0.079, 0.072, 0.072, 0.062, 0.062, 0.107, 0.107, 0.087, 0.087, 0.089, 0.089]
+    boxes, joints, crowd = [], [], []
+    for b, n in enumerate((3, 0, 2)):  # an image without targets in the middle
+        for k in range(n):
+            cx, cy = (torch.rand(2, generator=gen) * 40 + 28).tolist()
+            w, h = (torch.rand(2, generator=gen) * 36 + 20).tolist()
+            boxes.append([b, cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+            jxy = torch.stack([torch.rand(J, generator=gen) * w + cx - w / 2, torch.rand(J, generator=gen) * h + cy - h / 2], -1)
+            vis = (torch.rand(J, generator=gen) > 0.3).float() * (1 + (torch.rand(J, generator=gen) > 0.5).float())
+            joints.append(torch.cat([torch.full((J, 1), float(b)), jxy, vis[:, None]], -1))
+            crowd.append([b, 1.0 if (b == 0 and k == 2) else 0.0])
+    targets = (torch.tensor(boxes), torch.stack(joints), torch.tensor(crowd))
+    variants = {
+        "default": dict(),
+        "oks_rescale_bce_giou": dict(classification_loss_type="bce", regression_iou_loss_type="giou", assigner_multiply_by_pose_oks=True, rescale_pose_loss_with_assigned_score=True, pose_classification_loss_type="focal"),
+    }
+    for name, kw in variants.items():
+        cls_logits = (torch.randn(B, L, 1, generator=gen) * 1.5 - 1.0).requires_grad_(True)
+        reg_distri = torch.randn(B, L, 68, generator=gen).requires_grad_(True)
+        pose_coords = (anchor_points.unsqueeze(0).unsqueeze(2) + torch.randn(B, L, J, 2, generator=gen) * 12).requires_grad_(True)
+        pose_logits = torch.randn(B, L, J, generator=gen).requires_grad_(True)
+        raw = (cls_logits, reg_distri, pose_coords, pose_logits, anchors, anchor_points, nums, stride_tensor)
+        crit = YoloNASPoseLoss(oks_sigmas=sigmas, **kw)
+        loss, items = crit((None, raw), targets)
+        loss.backward()
+        out["loss_" + name] = dict(kw=kw, sigmas=sigmas, targets=targets, raw=tuple(t.detach().clone() if torch.is_tensor(t) else t for t in raw), loss=loss.detach(), items=items.clone(),
+                                   grads=tuple(t.grad.clone() for t in (cls_logits, reg_distri, pose_coords, pose_logits)))
+    torch.save(out, os.path.join(HERE, "pose.pt"))
+
+
 def golden_nms():
     from super_gradients.training.models.detection_models.pp_yolo_e import PPYoloEPostPredictionCallback
 
@@ -326,7 +386,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "tiny_yolo_nas", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "pose", "tiny_yolo_nas", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

@@ -227,3 +227,38 @@ def test_pose_postprocess_oracle_matches_reference(golden, case):
         assert any(int((c.reshape(-1) >= g["params"]["pose_confidence_threshold"]).sum()) > g["params"]["pre_nms_max_predictions"] for c in g["conf"])
     if case == "nothing_passes":
         assert all(r[0].shape[0] == 0 for r in res)
+
+
+def test_pose_decode_oracle_matches_reference(golden):
+    """Row L8: oracle.pose_ndfl_decode == YoloNASPoseNDFLHeads.forward of the unmodified reference (per-level head outputs
+    captured from a real yolo_nas_pose_n forward)."""
+    g = golden("pose")["decode"]
+    lv = g["levels"]
+    decoded, raw = O.pose_ndfl_decode([t[0] for t in lv], [t[1] for t in lv], [t[2] for t in lv], [t[3] for t in lv], g["strides"], g["reg_max"],
+                                      g["cell_offset"], g["cell_scale"], g["pose_offset_multiplier"], g["compensate"])  # fmt: skip
+    for mine, ref in zip(decoded, g["decoded"]):
+        torch.testing.assert_close(mine, ref, rtol=1e-5, atol=1e-4)
+    for i in (0, 1, 2, 3, 4, 5, 7):
+        torch.testing.assert_close(raw[i], g["raw"][i], rtol=1e-5, atol=1e-4)
+    assert list(raw[6]) == list(g["raw"][6])
+
+
+@pytest.mark.parametrize("case", ["default", "oks_rescale_bce_giou"])
+def test_pose_loss_oracle_matches_reference(golden, case):
+    """Row L7: oracle.yolo_nas_pose_loss (assigner with crowd handling / optional OKS weighting, focal or BCE classification,
+    CIoU or GIoU, DFL, keypoint OKS regression + visibility classification) == YoloNASPoseLoss: value, components, gradients."""
+    g = golden("pose")["loss_" + case]
+    raw = list(g["raw"])
+    leaves = [raw[i].clone().requires_grad_(True) for i in range(4)]
+    kw = dict(g["kw"])
+    loss, items = O.yolo_nas_pose_loss(
+        tuple(leaves) + tuple(raw[4:]), g["targets"], g["sigmas"], classification_loss_type=kw.get("classification_loss_type", "focal"),
+        regression_iou_loss_type=kw.get("regression_iou_loss_type", "ciou"), pose_classification_loss_type=kw.get("pose_classification_loss_type", "bce"),
+        assigner_multiply_by_pose_oks=kw.get("assigner_multiply_by_pose_oks", False), rescale_pose_loss_with_assigned_score=kw.get("rescale_pose_loss_with_assigned_score", False),
+    )  # fmt: skip
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(items, g["items"], rtol=1e-5, atol=1e-6)
+    assert float(items[3]) > 0 and float(items[4]) > 0  # the keypoint terms are live in the fixture
+    loss.backward()
+    for leaf, ref in zip(leaves, g["grads"]):
+        torch.testing.assert_close(leaf.grad, ref, rtol=1e-4, atol=1e-7)
