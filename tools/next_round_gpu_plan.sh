@@ -1,0 +1,31 @@
+#!/usr/bin/env bash
+# First GPU calls of the next round, cheapest / most informative first (each line is one `gpurun` payload; wrap in `timeout`).
+#   1. bash tools/next_round_gpu_plan.sh verify      -> every GPU test incl. the ones written after round 1's budget ran out
+#   2. bash tools/next_round_gpu_plan.sh repro       -> the interleaved-model anomaly under compute-sanitizer
+#   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
+#   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
+set -uo pipefail
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+case "${1:-verify}" in
+  verify)
+    timeout 500 python -m pytest tests -m gpu -q --tb=short --timeout 300 2>&1 | tail -25
+    timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+    timeout 300 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_verify.json 2> gpurun_out/bench_verify.err
+    tail -2 gpurun_out/bench_verify.err; cut -c1-400 gpurun_out/bench_verify.json ;;
+  repro)
+    STEPS=4 timeout 120 python tools/repro_interleaved.py 2>&1 | tail -6
+    for tool in memcheck initcheck; do
+      echo "== compute-sanitizer $tool"
+      STEPS=3 timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/repro_interleaved.py > gpurun_out/sanitizer_$tool.log 2>&1
+      grep -E "ERROR SUMMARY|Invalid|Uninitialized|at 0x|by thread" gpurun_out/sanitizer_$tool.log | head -30
+    done ;;
+  twogpu)
+    timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
+      bench.py --gpus 2 --steps 8 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
+    echo "rc=$?"; tail -5 gpurun_out/bench_2gpu.err; cut -c1-500 gpurun_out/bench_2gpu.json ;;
+  profile)
+    SGB_PROFILER_RANGE=1 timeout 700 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+      --clock-control none --csv --log-file gpurun_out/launches_next.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/ncu_next.log 2>&1
+    timeout 200 python tools/layer_profile.py > gpurun_out/layers_next.txt 2>&1; head -40 gpurun_out/layers_next.txt ;;
+esac
