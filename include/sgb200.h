@@ -213,6 +213,17 @@ int sgb_dfl_decode(const sgb_bf16* reg, int reg_pitch, const sgb_bf16* cls, int 
                    int L, int anchor_base, int ncls, int reg_max, float stride, float cell_offset, float* pred_bboxes,
                    float* pred_scores, float* cls_logits, float* reg_distri, void* stream);
 
+/* Keypoint decode of one level (row L8: pose_estimation_models/yolo_nas_pose/yolo_nas_pose_ndfl_heads.py:186-199):
+ * pose [N, HW, pose_pitch] bf16 (channel 2j = x offset, 2j+1 = y offset of joint j), logit [N, HW, logit_pitch] bf16 (joint j
+ * at channel logit_off + j) -> rows [anchor_base, anchor_base + HW) of pose_coords [N, L, J, 2] f32
+ * = (offset * offset_multiplier + grid centre - (compensate ? cell_offset : 0)) * stride, pose_scores [N, L, J] f32
+ * (sigmoid) and optionally the raw pose_logits [N, L, J].  Boxes and the person score of the same head go through
+ * sgb_dfl_decode with ncls = 1 (channel 0 of the class head). */
+int sgb_pose_keypoint_decode(const sgb_bf16* pose, int pose_pitch, const sgb_bf16* logit, int logit_pitch, int logit_off, int N,
+                             int Hf, int Wf, int L, int anchor_base, int J, float stride, float cell_offset,
+                             float offset_multiplier, int compensate_grid_cell_offset, float* pose_coords, float* pose_scores,
+                             float* pose_logits, void* stream);
+
 /* ---- PPYoloE / YOLO-NAS loss (rows L1-L6: training/losses/ppyolo_loss.py) ----------------------------------- */
 typedef struct SgbLossDesc {
   int32_t B, L, ncls, reg_max; /* batch, anchors, classes, DFL bins - 1 */

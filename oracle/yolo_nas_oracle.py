@@ -100,7 +100,36 @@ class YoloNASOracle:
         p5 = self._down_stage("neck.neck4.", nk["neck4"]["YoloNASDownStage"], [p4, n1i])
         return p3, p4, p5
 
+    def pose_heads(self, feats):
+        """YoloNASPoseNDFLHeads over YoloNASPoseDFLHead levels (pose_estimation_models/yolo_nas_pose/
+        yolo_nas_pose_dfl_head.py:131-167, yolo_nas_pose_ndfl_heads.py:126-206); separate stems, joint logits in the class head."""
+        hd = self.arch["heads"]["YoloNASPoseNDFLHeads"]
+        J = hd["num_classes"]
+        regs, clss, prs, pls, strides = [], [], [], [], []
+        cba = lambda t, pre, k: O.conv_bn_act(t, self.p, pre, 1, k // 2, "relu", self.training, self.eps, self.mom)  # noqa: E731
+        for i, (f, h) in enumerate(zip(feats, hd["heads_list"])):
+            a = h["YoloNASPoseDFLHead"]
+            assert not a["shared_stem"] and a["pose_conf_in_class_head"] and not a["pose_block_use_repvgg"] and a["first_conv_group_size"] == 0
+            pre = f"heads.head{i + 1}."
+            pose_f = cba(f, pre + "pose_stem.seq.", 1)
+            bbox_f = cba(f, pre + "bbox_stem.seq.", 1)
+            c = cba(bbox_f, pre + "cls_convs.0.seq.", 3)
+            r = cba(bbox_f, pre + "reg_convs.0.seq.", 3)
+            for b in range(a["pose_regression_blocks"]):
+                pose_f = cba(pose_f, pre + f"pose_convs.{b}.seq.", 3)
+            cls_out = O.q(F.conv2d(c, O.qw(self.p[pre + "cls_pred.weight"]), self.p[pre + "cls_pred.bias"]))
+            regs.append(O.q(F.conv2d(r, O.qw(self.p[pre + "reg_pred.weight"]), self.p[pre + "reg_pred.bias"])))
+            pose_out = O.q(F.conv2d(pose_f, O.qw(self.p[pre + "pose_pred.weight"]), self.p[pre + "pose_pred.bias"]))
+            clss.append(cls_out[:, 0:1])
+            pls.append(cls_out[:, 1:])
+            prs.append(pose_out.reshape(pose_out.shape[0], J, 2, pose_out.shape[2], pose_out.shape[3]))
+            strides.append(a["stride"])
+        return O.pose_ndfl_decode(regs, clss, prs, pls, strides, reg_max=hd.get("reg_max", 16), pose_offset_multiplier=hd.get("pose_offset_multiplier", 1.0),
+                                  compensate_grid_cell_offset=hd.get("compensate_grid_cell_offset", True))  # fmt: skip
+
     def heads(self, feats):
+        if "YoloNASPoseNDFLHeads" in self.arch["heads"]:
+            return self.pose_heads(feats)
         hd = self.arch["heads"]["NDFLHeads"]
         regs, clss, strides = [], [], []
         for i, (f, h) in enumerate(zip(feats, hd["heads_list"])):

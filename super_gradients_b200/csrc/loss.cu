@@ -62,6 +62,33 @@ __global__ void dfl_decode_kernel(const bf16* __restrict__ reg, int reg_pitch, c
   }
 }
 
+// Keypoint decode of one pyramid level (row L8: yolo_nas_pose_ndfl_heads.py:186-199): per anchor and joint
+//   xy = (offset * multiplier + anchor_point_in_stride_units - compensation) * stride,  score = sigmoid(logit).
+// pose: [N, HW, pose_pitch] bf16 with channel 2*j + {0: x, 1: y};  logit: [N, HW, logit_pitch] bf16, joint j at channel
+// logit_off + j (the reference keeps the joint logits in the class head: channels 1..J of cls_pred).
+__global__ void pose_keypoint_decode_kernel(const bf16* __restrict__ pose, int pose_pitch, const bf16* __restrict__ logit,
+                                            int logit_pitch, int logit_off, int N, int Hf, int Wf, int L, int abase, int J,
+                                            float stride, float cell_off, float mult, float comp, float* coords,
+                                            float* scores, float* logits_out) {
+  const int HW = Hf * Wf;
+  const int64_t total = (int64_t)N * HW * J;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = i % J;
+    const int64_t a = i / J;
+    const int hw = a % HW;
+    const int n = a / HW;
+    const int64_t row = (int64_t)n * L + abase + hw;
+    const bf16* pz = pose + ((int64_t)n * HW + hw) * pose_pitch + 2 * j;
+    const float ax = (float)(hw % Wf) + cell_off, ay = (float)(hw / Wf) + cell_off;
+    const float ox = __bfloat162float(pz[0]), oy = __bfloat162float(pz[1]);
+    coords[(row * J + j) * 2 + 0] = (ox * mult + (ax - comp)) * stride;
+    coords[(row * J + j) * 2 + 1] = (oy * mult + (ay - comp)) * stride;
+    const float x = __bfloat162float(logit[((int64_t)n * HW + hw) * logit_pitch + logit_off + j]);
+    if (logits_out) logits_out[row * J + j] = x;
+    scores[row * J + j] = 1.f / (1.f + expf(-x));
+  }
+}
+
 // gradient of the raw fp32 copies back into the per-level bf16 NHWC head outputs
 __global__ void head_grad_scatter_kernel(const float* __restrict__ g, int gC, int N, int HW, int L, int abase,
                                          bf16* dy, int pitch, int cpad) {
@@ -519,6 +546,23 @@ extern "C" int sgb_dfl_decode(const sgb_bf16* reg, int reg_pitch, const sgb_bf16
                                                             Hf, Wf, L, anchor_base, ncls, reg_max, stride, cell_offset,
                                                             pred_bboxes, pred_scores, cls_logits, reg_distri);
   SGB_LAUNCH_CHECK("dfl_decode_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_pose_keypoint_decode(const sgb_bf16* pose, int pose_pitch, const sgb_bf16* logit, int logit_pitch,
+                                        int logit_off, int N, int Hf, int Wf, int L, int anchor_base, int J, float stride,
+                                        float cell_offset, float offset_multiplier, int compensate_grid_cell_offset,
+                                        float* pose_coords, float* pose_scores, float* pose_logits, void* stream) {
+  SGB_REQUIRE(pose && logit && pose_coords && pose_scores, "null pointer");
+  SGB_REQUIRE(N > 0 && Hf > 0 && Wf > 0 && J > 0, "bad shape");
+  SGB_REQUIRE(pose_pitch >= 2 * J && logit_pitch >= logit_off + J && logit_off >= 0, "channel range exceeds pitch");
+  SGB_REQUIRE(anchor_base >= 0 && anchor_base + Hf * Wf <= L, "anchor range");
+  int64_t total = (int64_t)N * Hf * Wf * J;
+  int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  pose_keypoint_decode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)pose, pose_pitch, (const bf16*)logit, logit_pitch, logit_off, N, Hf, Wf, L, anchor_base, J, stride, cell_offset,
+      offset_multiplier, compensate_grid_cell_offset ? cell_offset : 0.f, pose_coords, pose_scores, pose_logits);
+  SGB_LAUNCH_CHECK("pose_keypoint_decode_kernel");
   return SGB_OK;
 }
 

@@ -24,6 +24,7 @@ __all__ = [
     "add",
     "global_avg_pool",
     "dfl_decode",
+    "pose_decode",
 ]
 
 
@@ -500,6 +501,32 @@ class _DflDecode(torch.autograd.Function):
             outs += [dr, dc]
             base += hw
         return tuple(outs)
+
+
+@torch.no_grad()
+def pose_decode(regs, clss, poses, strides, num_joints, reg_max, cell_offset, pose_offset_multiplier=1.0, compensate_grid_cell_offset=True):
+    """YoloNASPoseNDFLHeads decode (yolo_nas_pose_ndfl_heads.py:126-206), inference / evaluation path (no autograd):
+    per-level bf16 NHWC maps reg [B, 4*(reg_max+1), H, W], cls [B, 1 + J, H, W] (channel 0 person logit, 1..J joint logits),
+    pose [B, 2J, H, W] -> fp32 pred_bboxes [B, L, 4], pred_scores [B, L, 1], pose_coords [B, L, J, 2], pose_scores [B, L, J]
+    and the raw cls_logits [B, L, 1], reg_distri [B, L, 4*(reg_max+1)], pose_logits [B, L, J]."""
+    regs, clss, poses = [K.as_nhwc(t) for t in regs], [K.as_nhwc(t) for t in clss], [K.as_nhwc(t) for t in poses]
+    B, dev, J = regs[0].shape[0], regs[0].device, num_joints
+    hws = [r.shape[2] * r.shape[3] for r in regs]
+    Ltot = sum(hws)
+    nb = reg_max + 1
+    pb = torch.empty((B, Ltot, 4), dtype=torch.float32, device=dev)
+    ps = torch.empty((B, Ltot, 1), dtype=torch.float32, device=dev)
+    cl = torch.empty((B, Ltot, 1), dtype=torch.float32, device=dev)
+    rd = torch.empty((B, Ltot, 4 * nb), dtype=torch.float32, device=dev)
+    pc = torch.empty((B, Ltot, J, 2), dtype=torch.float32, device=dev)
+    pj = torch.empty((B, Ltot, J), dtype=torch.float32, device=dev)
+    pl = torch.empty((B, Ltot, J), dtype=torch.float32, device=dev)
+    base = 0
+    for r, c, p, s, hw in zip(regs, clss, poses, strides, hws):
+        K.dfl_decode(r, c, Ltot, base, 1, reg_max, s, cell_offset, pb, ps, cl, rd)  # class head channel 0 = person logit
+        K.pose_keypoint_decode(p, c, 1, Ltot, base, J, s, cell_offset, pose_offset_multiplier, compensate_grid_cell_offset, pc, pj, pl)
+        base += hw
+    return pb, ps, pc, pj, cl, rd, pl
 
 
 def dfl_decode(regs, clss, strides, num_classes, reg_max, cell_offset):

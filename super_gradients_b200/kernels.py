@@ -511,6 +511,13 @@ def dfl_decode(reg, cls, L_total, anchor_base, ncls, reg_max, stride, cell_offse
     _timed("sgb_dfl_decode", _ptr(reg), nhwc_pitch(reg), _ptr(cls), nhwc_pitch(cls), n, hf, wf, L_total, anchor_base, ncls, reg_max, float(stride), float(cell_offset), _ptr(pred_bboxes), _ptr(pred_scores), _ptr(cls_logits), _ptr(reg_distri), _stream())
 
 
+def pose_keypoint_decode(pose, logit, logit_off, L_total, anchor_base, J, stride, cell_offset, offset_multiplier, compensate, pose_coords, pose_scores, pose_logits=None):
+    """pose [N, 2J, H, W] / logit [N, >= logit_off + J, H, W] bf16 NHWC maps of one level -> rows of the fp32 [N, L, *] outputs."""
+    n, _, hf, wf = pose.shape
+    _timed("sgb_pose_keypoint_decode", _ptr(pose), nhwc_pitch(pose), _ptr(logit), nhwc_pitch(logit), int(logit_off), n, hf, wf, L_total, anchor_base, J, float(stride), float(cell_offset),
+           float(offset_multiplier), 1 if compensate else 0, _ptr(pose_coords), _ptr(pose_scores), _ptr(pose_logits), _stream())  # fmt: skip
+
+
 def head_grad_scatter(grad, n, hw, L_total, anchor_base, dy):
     gC = grad.shape[-1]
     _timed("sgb_head_grad_scatter", _ptr(grad), gC, n, hw, L_total, anchor_base, _ptr(dy), nhwc_pitch(dy), _stream())

@@ -147,6 +147,7 @@ _SIGNATURES = {
     "sgb_avgpool_fwd": (c_int, [P, _I, _I, _I, P, P]),
     "sgb_avgpool_bwd": (c_int, [P, _I, _I, _I, P, P]),
     "sgb_dfl_decode": (c_int, [P, _I, P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, P, P, P, P, P]),
+    "sgb_pose_keypoint_decode": (c_int, [P, _I, P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, P, P, P, P]),
     "sgb_tal_assign": (c_int, [POINTER(LossDesc)] + [P] * 12 + [_L, P]),
     "sgb_tal_workspace_bytes": (c_int64, [POINTER(LossDesc)]),
     "sgb_dfl_iou_loss_fwd_bwd": (c_int, [POINTER(LossDesc)] + [P] * 8 + [_F, P, P, P]),

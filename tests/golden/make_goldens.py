@@ -338,12 +338,51 @@ def golden_tiny_yolo_nas():
     )  # fmt: skip
 
 
+def tiny_pose_arch():
+    """TINY_YOLO_NAS backbone + neck with small YoloNASPoseDFLHeads (5 joints; separate stems, joint logits in the class head
+    -- the configuration of every shipped YOLO-NAS-POSE variant)."""
+    ap = copy.deepcopy(TINY_YOLO_NAS)
+    mk = lambda b, p, r, s: {"YoloNASPoseDFLHead": {"bbox_inter_channels": b, "pose_inter_channels": p, "pose_regression_blocks": r, "shared_stem": False, "width_mult": 0.5,
+                                                     "pose_conf_in_class_head": True, "pose_block_use_repvgg": False, "first_conv_group_size": 0, "stride": s}}  # noqa: E731
+    ap["heads"] = {"YoloNASPoseNDFLHeads": {"num_classes": 5, "reg_max": 16, "pose_offset_multiplier": 1.0, "compensate_grid_cell_offset": True, "inference_mode": False,
+                                            "heads_list": [mk(32, 32, 2, 8), mk(48, 64, 2, 16), mk(64, 64, 3, 32)]}}
+    return ap
+
+
+def golden_tiny_yolo_nas_pose():
+    """Row L8 end to end: eval-mode forward of a tiny YOLO-NAS-POSE built from the reference classes (random weights and
+    BatchNorm running statistics), decoded + raw outputs, and the post-prediction callback on them."""
+    from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_post_prediction_callback import YoloNASPosePostPredictionCallback
+    from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_variants import YoloNASPose
+
+    gen = torch.Generator().manual_seed(15)
+    torch.manual_seed(3)
+    arch = tiny_pose_arch()
+    ap = copy.deepcopy(arch)
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    randomize_bn(m, gen)
+    sd0 = sd_clone(m)
+    x = torch.randn(2, 3, 96, 96, generator=gen)
+    m.eval()
+    with torch.no_grad():
+        decoded, raw = m(x)
+    cb = YoloNASPosePostPredictionCallback(pose_confidence_threshold=0.01, nms_iou_threshold=0.6, pre_nms_max_predictions=100, post_nms_max_predictions=20)
+    preds = cb((decoded, raw))
+    live = {k: v for k, v in sd0.items() if "rbr_reparam" not in k}
+    torch.save(dict(arch=arch, sd0=live, x=x, decoded=tuple(t.clone() for t in decoded), raw=tuple(t.clone() if torch.is_tensor(t) else t for t in raw),
+                    cb=dict(pose_confidence_threshold=0.01, nms_iou_threshold=0.6, pre_nms_max_predictions=100, post_nms_max_predictions=20),
+                    preds=[(r.poses.clone(), r.scores.clone(), r.bboxes_xyxy.clone()) for r in preds],
+                    param_names=[k for k, _ in m.named_parameters()], state_keys=list(m.state_dict().keys())),
+               os.path.join(HERE, "tiny_yolo_nas_pose.pt"))  # fmt: skip
+
+
 def golden_state_keys():
     """state_dict keys + shapes of the full-size models (for checkpoint compatibility tests)."""
     from super_gradients.training import models
 
     out = {}
-    for name, nc in [("yolo_nas_s", 80), ("yolo_nas_m", 80), ("yolo_nas_l", 80), ("resnet18_cifar", 10), ("resnet18", 1000), ("resnet50", 1000)]:
+    for name, nc in [("yolo_nas_s", 80), ("yolo_nas_m", 80), ("yolo_nas_l", 80), ("resnet18_cifar", 10), ("resnet18", 1000), ("resnet50", 1000),
+                     ("yolo_nas_pose_n", 17), ("yolo_nas_pose_s", 17), ("yolo_nas_pose_m", 17), ("yolo_nas_pose_l", 17)]:
         torch.manual_seed(0)
         m = models.get(name, num_classes=nc)
         out[name] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
@@ -386,7 +425,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "pose", "tiny_yolo_nas", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

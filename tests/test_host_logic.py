@@ -29,7 +29,8 @@ def test_registry_and_factory_contract():
         f.get({"NoSuchModule": {}})
 
 
-@pytest.mark.parametrize("name,nc", [("yolo_nas_s", 80), ("yolo_nas_m", 80), ("yolo_nas_l", 80), ("resnet18_cifar", 10), ("resnet18", 1000), ("resnet50", 1000)])
+@pytest.mark.parametrize("name,nc", [("yolo_nas_s", 80), ("yolo_nas_m", 80), ("yolo_nas_l", 80), ("resnet18_cifar", 10), ("resnet18", 1000), ("resnet50", 1000),
+                                     ("yolo_nas_pose_n", 17), ("yolo_nas_pose_s", 17), ("yolo_nas_pose_m", 17), ("yolo_nas_pose_l", 17)])  # fmt: skip
 def test_state_dict_keys_match_reference(golden, name, nc):
     """Reference checkpoints must load unchanged: same keys, shapes and parameter order."""
     from super_gradients_b200.training import models
@@ -154,3 +155,23 @@ def test_step_arena_hands_out_zeroed_non_overlapping_scratch():
         assert not (base <= huge.data_ptr() < base + a.buf.numel())
         a.end_step()
         assert a.high == a.off
+
+
+def test_tiny_yolo_nas_pose_mirror_has_reference_state_dict(golden):
+    """The YoloNASPose mirror built from the fixture's arch has the reference model's state-dict keys, shapes and parameter
+    order, and loads the reference state dict (dead rbr_reparam placeholders aside)."""
+    import copy
+
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPose
+
+    g = golden("tiny_yolo_nas_pose")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    assert list(m.state_dict().keys()) == g["state_keys"]
+    assert [k for k, _ in m.named_parameters()] == g["param_names"]
+    missing, unexpected = m.load_state_dict(g["sd0"], strict=False)
+    assert not unexpected and all("rbr_reparam" in k for k in missing)
+    for k, v in g["sd0"].items():
+        assert tuple(m.state_dict()[k].shape) == tuple(v.shape), k
+    with pytest.raises(Exception):  # no CPU execution path: the product raises instead of falling back
+        m.eval()(g["x"])

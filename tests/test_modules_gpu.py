@@ -13,6 +13,7 @@ Two comparisons per module:
 """
 import copy
 
+import numpy as np
 import pytest
 import torch
 
@@ -281,3 +282,47 @@ def test_resnet18_cifar_training_matches_reference_trajectory(golden):
         losses.append(float(loss))
     assert abs(losses[0] - g["losses"][0]) < 2e-2 * g["losses"][0]
     assert abs(losses[1] - g["losses"][1]) < 0.1 * g["losses"][1]
+
+
+def test_tiny_yolo_nas_pose_eval_and_predict(golden):
+    """Row L8 end to end on the GPU: eval-mode YoloNASPose (reference arch + state dict) -> decoded boxes / person scores /
+    keypoints / joint scores and raw head outputs against the whole-graph oracle in bf16-emulation mode (tight) and the fp32
+    outputs of the unmodified reference (loose); then the post-prediction callback on the product's own outputs against the
+    oracle post-processing of the same tensors (exact)."""
+    from oracle import sg_oracle as O
+    from oracle.yolo_nas_oracle import YoloNASOracle
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPose, YoloNASPosePostPredictionCallback
+
+    g = golden("tiny_yolo_nas_pose")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    assert list(m.state_dict().keys()) == g["state_keys"]
+    load_sd(m, g["sd0"])
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        decoded, raw = m(g["x"].to(DEV))
+    with O.bf16_emulation():
+        dec_e, raw_e = YoloNASOracle(g["arch"], {k: v.clone() for k, v in g["sd0"].items()}, training=False).forward(g["x"])
+    names = ("boxes", "scores", "pose_coords", "pose_scores")
+    for name, a, b in zip(names, decoded, dec_e):
+        assert tuple(a.shape) == tuple(b.shape), name
+        assert l2rel(a, b) < 3e-2, (name, l2rel(a, b))
+    for i in (0, 1, 3):  # person logits, box distributions, joint logits
+        assert l2rel(raw[i], raw_e[i]) < 3e-2, (i, l2rel(raw[i], raw_e[i]))
+    for i in (4, 5, 7):  # anchors, anchor points, strides are exact
+        torch.testing.assert_close(raw[i].cpu(), raw_e[i])
+    assert list(raw[6]) == list(raw_e[6])
+    for name, a, b in zip(names, decoded, g["decoded"]):  # fp32 reference, loose
+        assert l2rel(a, b) < 0.1, (name, l2rel(a, b))
+    # post-prediction callback on the product's own decoded tensors: exact against the oracle on the same numbers
+    cb = YoloNASPosePostPredictionCallback(**g["cb"])
+    preds = cb((decoded, raw))
+    ref, _ = O.yolo_nas_pose_postprocess(*(t.cpu() for t in decoded), **g["cb"])
+    assert len(preds) == len(ref) and sum(r[0].shape[0] for r in ref) > 0
+    for pr, (rposes, rscores, rboxes) in zip(preds, ref):
+        np.testing.assert_array_equal(pr.scores.cpu().numpy(), rscores)
+        np.testing.assert_array_equal(pr.bboxes_xyxy.cpu().numpy(), rboxes)
+        np.testing.assert_array_equal(pr.poses.cpu().numpy(), rposes)
+    # the model-level predict() wraps exactly that
+    out = m.predict(g["x"].to(DEV), conf=g["cb"]["pose_confidence_threshold"], iou=g["cb"]["nms_iou_threshold"], pre_nms_max_predictions=100, post_nms_max_predictions=20)
+    assert [int(o.scores.shape[0]) for o in out] == [r[0].shape[0] for r in ref]

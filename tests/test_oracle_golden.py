@@ -262,3 +262,22 @@ def test_pose_loss_oracle_matches_reference(golden, case):
     loss.backward()
     for leaf, ref in zip(leaves, g["grads"]):
         torch.testing.assert_close(leaf.grad, ref, rtol=1e-4, atol=1e-7)
+
+
+def test_tiny_yolo_nas_pose_oracle_matches_reference(golden):
+    """Whole-graph oracle with the pose heads (eval mode, fp32) == the reference YoloNASPose built from the same arch and
+    state dict: decoded boxes / scores / keypoints, raw head outputs, and the post-prediction callback's instances."""
+    from oracle.yolo_nas_oracle import YoloNASOracle
+
+    g = golden("tiny_yolo_nas_pose")
+    decoded, raw = YoloNASOracle(g["arch"], {k: v.clone() for k, v in g["sd0"].items()}, training=False).forward(g["x"])
+    for mine, ref in zip(decoded, g["decoded"]):
+        torch.testing.assert_close(mine, ref, rtol=1e-4, atol=1e-3)
+    for i in (0, 1, 2, 3, 5, 7):
+        torch.testing.assert_close(raw[i], g["raw"][i], rtol=1e-4, atol=1e-3)
+    res, _ = O.yolo_nas_pose_postprocess(*g["decoded"], **g["cb"])
+    assert len(res) == len(g["preds"]) and sum(r[0].shape[0] for r in res) > 0
+    for (poses, scores, boxes), (rp, rs, rb) in zip(res, g["preds"]):
+        np.testing.assert_array_equal(poses, rp.numpy())
+        np.testing.assert_array_equal(scores, rs.numpy())
+        np.testing.assert_array_equal(boxes, rb.numpy())
