@@ -262,6 +262,9 @@ def golden_pose():
     variants = {
         "default": dict(),
         "oks_rescale_bce_giou": dict(classification_loss_type="bce", regression_iou_loss_type="giou", assigner_multiply_by_pose_oks=True, rescale_pose_loss_with_assigned_score=True, pose_classification_loss_type="focal"),
+        # recipes/training_hyperparams/coco2017_yolo_nas_pose_train_params.yaml:23-34
+        "recipe": dict(classification_loss_weight=1.0, classification_loss_type="focal", regression_iou_loss_type="ciou", iou_loss_weight=2.5, dfl_loss_weight=0.01, pose_cls_loss_weight=1.0,
+                       pose_reg_loss_weight=34.0, pose_classification_loss_type="focal", rescale_pose_loss_with_assigned_score=True, assigner_multiply_by_pose_oks=True),
     }
     for name, kw in variants.items():
         cls_logits = (torch.randn(B, L, 1, generator=gen) * 1.5 - 1.0).requires_grad_(True)

@@ -243,7 +243,7 @@ def test_pose_decode_oracle_matches_reference(golden):
     assert list(raw[6]) == list(g["raw"][6])
 
 
-@pytest.mark.parametrize("case", ["default", "oks_rescale_bce_giou"])
+@pytest.mark.parametrize("case", ["default", "oks_rescale_bce_giou", "recipe"])
 def test_pose_loss_oracle_matches_reference(golden, case):
     """Row L7: oracle.yolo_nas_pose_loss (assigner with crowd handling / optional OKS weighting, focal or BCE classification,
     CIoU or GIoU, DFL, keypoint OKS regression + visibility classification) == YoloNASPoseLoss: value, components, gradients."""
@@ -255,6 +255,8 @@ def test_pose_loss_oracle_matches_reference(golden, case):
         tuple(leaves) + tuple(raw[4:]), g["targets"], g["sigmas"], classification_loss_type=kw.get("classification_loss_type", "focal"),
         regression_iou_loss_type=kw.get("regression_iou_loss_type", "ciou"), pose_classification_loss_type=kw.get("pose_classification_loss_type", "bce"),
         assigner_multiply_by_pose_oks=kw.get("assigner_multiply_by_pose_oks", False), rescale_pose_loss_with_assigned_score=kw.get("rescale_pose_loss_with_assigned_score", False),
+        w_cls=kw.get("classification_loss_weight", 1.0), w_iou=kw.get("iou_loss_weight", 2.5), w_dfl=kw.get("dfl_loss_weight", 0.5), w_pose_cls=kw.get("pose_cls_loss_weight", 1.0),
+        w_pose_reg=kw.get("pose_reg_loss_weight", 1.0),
     )  # fmt: skip
     torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(items, g["items"], rtol=1e-5, atol=1e-6)
