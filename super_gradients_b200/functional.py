@@ -90,7 +90,8 @@ def refresh_weight_caches(ctx: StepContext, device) -> int:
     """Re-prepares every filter the context's model uses with ONE batched launch (instead of one launch per layer on
     first use) and marks those caches current.  Called by the train step after the optimizer moved the weights."""
     live = [c for c in ctx.caches.values() if c.args is not None and c.krsc is not None]
-    live = [c for c in live if c.args[0].is_cuda and c.args[0].dtype == torch.float32 and c.args[0].is_contiguous()]
+    dev = torch.device(device)
+    live = [c for c in live if c.args[0].device == dev and c.args[0].dtype == torch.float32 and c.args[0].is_contiguous()]
     if not live:
         return 0
     ident = tuple((c.args[0].data_ptr(), c.krsc.data_ptr(), None if c.crsk is None else c.crsk.data_ptr(), None if c.args[1] is None else c.args[1].data_ptr(), c.args[2], c.args[4]) for c in live)

@@ -1,10 +1,15 @@
-"""Test infrastructure: a CPU stand-in for the INFERENCE subset of super_gradients_b200.kernels (fp32 torch math, bf16
-storage at the same points as the CUDA kernels).  It replaces the kernel wrappers, not the product: with it installed the
+"""Test infrastructure: a CPU stand-in for super_gradients_b200.kernels (fp32 torch math, bf16 storage at the same points
+as the CUDA kernels): `install()` covers the inference subset, `install_training()` adds the backward / BatchNorm /
+QARepVGG / loss / optimizer wrappers so that a whole TrainStep runs.  It replaces the kernel wrappers, not the product: with it installed the
 Python glue above kernels.py (functional.py, the module mirrors, head decoding, post-prediction callbacks, predict()) runs
 on a machine without a GPU, so wiring mistakes (argument order, channel slices, anchor bases, head plumbing) are caught
 by the CPU suite.  It says nothing about the CUDA kernels themselves -- those are covered by the `-m gpu` parity tests.
 
-Only tests may import this module.  Anything outside the subset raises NotImplementedError.
+The training stand-ins are written from the layer definitions (torch autograd on the textbook formulation), not from the
+CUDA kernels' algebra; they exist to exercise the step plumbing (flat state, step arena, deferred weight gradients,
+batched work tables, filter caches) deterministically.
+
+Only tests may import this module.  Anything outside the installed subset raises NotImplementedError.
 """
 import torch
 import torch.nn.functional as F
@@ -100,11 +105,11 @@ def bn_act_infer(x, gamma, beta, running_mean, running_var, eps, act, residual=N
 
 
 def maxpool_fwd(x, k, stride, pad, want_idx=True, out=None):
-    y = F.max_pool2d(x.float(), k, stride, pad)
+    y, idx = F.max_pool2d(x.float(), k, stride, pad, return_indices=True)
     if out is None:
         out = K.empty_nhwc(x.shape[0], x.shape[1], y.shape[2], y.shape[3], x.device)
     out.copy_(_bf16(y))
-    return out, None
+    return out, (idx if want_idx else None)
 
 
 def axpby(x1, a, x2=None, b=0.0, out=None):
@@ -172,6 +177,274 @@ def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=T
     return out, oidx, cnt
 
 
+# ---------------------------------------------------------------------------------------------------- training subset
+def conv_dgrad(dy, w_crsk, x_shape, R, S, stride, pad, out=None, accumulate=False):
+    n, c, h, w = x_shape
+    Kk = dy.shape[1]
+    wt = w_crsk[..., :Kk].permute(3, 0, 1, 2).float()  # CRSK -> OIHW
+    dx = torch.nn.grad.conv2d_input((n, wt.shape[1], h, w), wt, dy.float(), stride=stride, padding=pad)
+    if out is None:
+        out = K.empty_nhwc(n, c, h, w, dy.device)
+        accumulate = False
+    out[:, : wt.shape[1]].copy_(_bf16(out[:, : wt.shape[1]].float() + dx if accumulate else dx))
+    return out
+
+
+def conv_wgrad(x, dy, R, S, stride, pad, dw_krsc=None):
+    n, c, h, w = x.shape
+    Kk = dy.shape[1]
+    if dw_krsc is None:
+        dw_krsc = K.zeros((Kk, R, S, c), torch.float32, x.device)  # through the step arena, like the CUDA wrapper
+    g = torch.nn.grad.conv2d_weight(x.float(), (Kk, c, R, S), dy.float(), stride=stride, padding=pad)
+    dw_krsc += g.permute(0, 2, 3, 1)
+    return dw_krsc
+
+
+def wgrad_to_oihw(dw_krsc, C, out=None, accumulate=False):
+    g = dw_krsc[..., :C].permute(0, 3, 1, 2)
+    if out is None:
+        return g.contiguous()
+    out.copy_(out + g if accumulate else g)
+    return out
+
+
+def weight_prepare_batch(entries, device):
+    return list(entries), len(entries), sum(e[2].numel() + (e[3].numel() if e[3] is not None else 0) for e in entries)
+
+
+def run_weight_prepare_batch(table, n, total):
+    assert len(table) == n
+    for w, scale, krsc, crsk, c_pad, add_identity in table:
+        k2, c2 = weight_prepare(w, c_pad=c_pad, want_crsk=crsk is not None, scale=scale, add_identity=add_identity)
+        krsc.copy_(k2)
+        if crsk is not None:
+            crsk.copy_(c2)
+
+
+def wgrad_to_oihw_batch_table(entries, device):
+    return list(entries), len(entries), sum(e[2].numel() for e in entries)
+
+
+def run_wgrad_to_oihw_batch(table, n, total):
+    assert len(table) == n
+    for dw, C, g, accumulate in table:
+        wgrad_to_oihw(dw, C, out=g, accumulate=accumulate)
+
+
+def _cv(t):
+    return t.float().view(1, -1, 1, 1)
+
+
+def _update_running(rm, rv, mean, var_biased, M, momentum):
+    if rm is not None:
+        rm.mul_(1 - momentum).add_(momentum * mean)
+        rv.mul_(1 - momentum).add_(momentum * var_biased * (M / max(M - 1, 1)))
+
+
+def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None):
+    n, c, h, w = x.shape
+    M = n * h * w
+    tot = stats.sum(0)  # [2, C] fp64
+    mean = tot[0] / M
+    var = (tot[1] / M - mean * mean).clamp_min(0)
+    rstd = torch.rsqrt(var + eps)
+    y = (x.float() - _cv(mean)) * _cv(rstd) * _cv(gamma) + _cv(beta)
+    if residual is not None:
+        y = y + residual.float()
+    out = K.empty_nhwc(n, c, h, w, x.device)
+    out.copy_(_bf16(_act(y, act)))
+    _update_running(running_mean, running_var, mean.float(), var.float(), M, momentum)
+    return out, mean.float(), rstd.float()
+
+
+def _mask(dout, out, act):
+    code = K.act_code(act)
+    if code == K.ACT_RELU:
+        return dout.float() * (out.float() > 0)
+    if code == K.ACT_NONE:
+        return dout.float()
+    raise NotImplementedError("CPU stand-in: only relu / identity activations have a backward")
+
+
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None):
+    n, c, h, w = x.shape
+    M = n * h * w
+    dz = _mask(dy, y, act)
+    xh = (x.float() - _cv(mean)) * _cv(rstd)
+    sb = dz.sum((0, 2, 3))
+    sg = (dz * xh).sum((0, 2, 3))
+    dx32 = _cv(gamma.float() * rstd) * (dz - _cv(sb / M) - xh * _cv(sg / M))
+    dx = K.empty_nhwc(n, c, h, w, x.device)
+    dx.copy_(_bf16(dx32))
+    dres = None
+    if want_residual_grad:
+        dres = K.empty_nhwc(n, c, h, w, x.device)
+        dres.copy_(_bf16(dz))
+    dgamma = K.zeros((c,), torch.float32, x.device) if dgamma is None else dgamma
+    dbeta = K.zeros((c,), torch.float32, x.device) if dbeta is None else dbeta
+    dgamma += sg
+    dbeta += sb
+    return dx, dres, dgamma, dbeta
+
+
+def channel_stats(x):
+    st = K.zeros((1, 2, x.shape[1]), torch.float64, x.device)
+    s = x.double()
+    st[0, 0] += s.sum((0, 2, 3))
+    st[0, 1] += (s * s).sum((0, 2, 3))
+    return st
+
+
+def channel_dot(a, b):
+    out = K.zeros((a.shape[1],), torch.float64, a.device)
+    out += (a.double() * b.double()).sum((0, 2, 3))
+    return out
+
+
+def _bn_batch(t, gamma, beta, eps):
+    mean = t.mean((0, 2, 3), keepdim=True)
+    var = t.var((0, 2, 3), unbiased=False, keepdim=True)
+    out = (t - mean) * torch.rsqrt(var + eps)
+    if gamma is not None:
+        out = out * gamma.view(1, -1, 1, 1)
+    if beta is not None:
+        out = out + beta.view(1, -1, 1, 1)
+    return out, mean.flatten(), var.flatten()
+
+
+def _qarep_pre(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, eps3, eps_post, use_post_bn):
+    """Pre-activation of the train-mode block: bn3(y3) + u + alpha*bias1 [-> post_bn]  (qarepvgg_block.py:184-204)."""
+    b3, m3, v3 = _bn_batch(y3, gamma3, beta3, eps3)
+    z = b3 + u
+    if bias1a is not None:
+        z = z + bias1a.view(1, -1, 1, 1)
+    if not use_post_bn:
+        return z, (m3, v3, None, None)
+    zp, mz, vz = _bn_batch(z, gamma_p, beta_p, eps_post)
+    return zp, (m3, v3, mz, vz)
+
+
+def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp, eps3, eps_post, momentum, act, use_post_bn=True):
+    n, c, h, w = y3.shape
+    M = n * h * w
+    f = lambda t: None if t is None else t.detach().float()  # noqa: E731
+    pre, (m3, v3, mz, vz) = _qarep_pre(y3.float(), u.float(), f(gamma3), f(beta3), f(bias1a), f(gamma_p), f(beta_p), eps3, eps_post, use_post_bn)
+    out = K.empty_nhwc(n, c, h, w, y3.device)
+    out.copy_(_bf16(_act(pre, act)))
+    _update_running(rm3, rv3, m3, v3, M, momentum)
+    if use_post_bn:
+        _update_running(rmp, rvp, mz, vz, M, momentum)
+    return out, torch.zeros((9, c), dtype=torch.float32)  # the coefficient table is private to the CUDA kernels
+
+
+def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None):
+    n, c, h, w = y3.shape
+    dpre = _mask(dout, out, act)
+    leaf = lambda t: t.detach().float().clone().requires_grad_(True)  # noqa: E731
+    y3l, ul, g3l = leaf(y3), leaf(u), leaf(gamma3)
+    b3l, abl = torch.zeros(c, requires_grad=True), torch.zeros(c, requires_grad=True)  # additive constants: only their gradients matter
+    gpl = leaf(gamma_p) if use_post_bn else None
+    bpl = torch.zeros(c, requires_grad=True) if use_post_bn else None
+    with torch.enable_grad():
+        pre, _ = _qarep_pre(y3l, ul, g3l, b3l, abl, gpl, bpl, eps3, eps_post, use_post_bn)
+        wrt = [y3l, ul, g3l, b3l, abl] + ([gpl, bpl] if use_post_bn else [])
+        grads = torch.autograd.grad(pre, wrt, dpre, allow_unused=True)
+    gy3, gu, gg3, gb3, gab = grads[:5]
+    ggp, gbp = (grads[5], grads[6]) if use_post_bn else (None, None)
+    dy3, du = torch.empty_like(y3), torch.empty_like(u)
+    dy3.copy_(_bf16(gy3))
+    du.copy_(_bf16(gu))
+    acc = acc or (None,) * 5
+    outs = []
+    for slot, g in zip(acc, (gg3, gb3, gab, ggp, gbp)):
+        t = slot if slot is not None else K.zeros((c,), torch.float32, y3.device)
+        if g is not None:
+            t += g
+        outs.append(t)
+    return (dy3, du, *outs)
+
+
+def maxpool_bwd(dy, idx, x_shape, k, stride, pad):
+    n, c, h, w = x_shape
+    dx = torch.zeros((n, c, h * w), dtype=torch.float32)
+    dx.scatter_add_(2, idx.reshape(n, c, -1), dy.float().reshape(n, c, -1))
+    return dx.view(n, c, h, w)
+
+
+def head_grad_scatter(grad, n, hw, L_total, anchor_base, dy):
+    _, gC, hf, wf = dy.shape
+    dy.copy_(_bf16(grad[:, anchor_base : anchor_base + hw, :gC].reshape(n, hf, wf, gC).permute(0, 3, 1, 2)))
+
+
+def tal_assign(d, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, sums):
+    st = stride_tensor.view(-1, 1)
+    pred = O.bbox_decode(anchor_points / st, reg_distri.detach()) * st
+    lab, box, score = O.tal_assign(cls_logits.detach().sigmoid(), pred, anchor_points, gt_labels.long().unsqueeze(-1), gt_boxes.float(), gt_valid.float().unsqueeze(-1),
+                                   bg_index=d.ncls, topk=d.topk, alpha=d.alpha, beta=d.beta)  # fmt: skip
+    sums[3] += score.sum().double()
+    return lab.int(), box, score.sum(-1)
+
+
+def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
+    C, reg_max = d.ncls, d.reg_max
+    st = stride_tensor.view(-1, 1)
+    cl, rd = cls_logits.detach().clone().requires_grad_(True), reg_distri.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        lab = al.long()
+        onehot = F.one_hot(lab, C + 1)[..., :C].float()
+        cls_sum = O.varifocal_loss(cl, onehot * asc.unsqueeze(-1), onehot)
+        pts_s = anchor_points / st
+        pred = O.bbox_decode(pts_s, rd)
+        pos = lab != C
+        if bool(pos.any()):
+            wgt = asc[pos].unsqueeze(-1)
+            pb, gb = pred[pos], (ab / st)[pos]
+            iou_sum = ((O.giou_loss if d.iou_type == 0 else O.ciou_loss)(pb, gb) * wgt).sum()
+            pts = pts_s.unsqueeze(0).expand(lab.shape[0], -1, 2)[pos]
+            ltrb = torch.cat([pts - gb[:, :2], gb[:, 2:] - pts], -1).clip(0, reg_max - 0.01)
+            dfl_sum = (O.df_loss(rd[pos].reshape(-1, 4, reg_max + 1), ltrb) * wgt).sum()
+        else:
+            iou_sum, dfl_sum = rd.sum() * 0.0, rd.sum() * 0.0
+        sums[0] += cls_sum.detach().double()
+        sums[1] += iou_sum.detach().double()
+        sums[2] += dfl_sum.detach().double()
+        nrm = float(sums[3].clamp_min(1.0))
+        total = (d.w_cls * cls_sum + d.w_iou * iou_sum + d.w_dfl * dfl_sum) / nrm
+        gc = gr = None
+        if want_grad:
+            gc, gr = torch.autograd.grad(total * grad_scale, [cl, rd])
+    items = torch.stack([d.w_cls * sums[0] / nrm, d.w_iou * sums[1] / nrm, d.w_dfl * sums[2] / nrm, total.detach().double()]).float()
+    return items, gc, gr
+
+
+def sgd_step(p, g, mom, hp):
+    lr, mu, wd, gs, nesterov = [float(v) for v in hp]
+    gg = g * gs + wd * p
+    mom.mul_(mu).add_(gg)
+    p.sub_(lr * (gg + mu * mom if nesterov else mom))
+
+
+def adamw_step(p, g, m, v, hp):
+    lr, b1, b2, eps, wd, bc1, bc2, gs = [float(x) for x in hp]
+    gg = g * gs
+    p.mul_(1 - lr * wd)
+    m.mul_(b1).add_((1 - b1) * gg)
+    v.mul_(b2).add_((1 - b2) * gg * gg)
+    p.sub_((lr / bc1) * m / ((v / bc2).sqrt() + eps))
+
+
+def ema_update(ema, p, decay_dev):
+    dcy = float(decay_dev.reshape(-1)[0])
+    ema.mul_(dcy).add_((1 - dcy) * p)
+
+
+_TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgrad_to_oihw, weight_prepare_batch=weight_prepare_batch,
+                 run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch,
+                 bn_act_fwd=bn_act_fwd, bn_act_bwd=bn_act_bwd, channel_stats=channel_stats, channel_dot=channel_dot, qarep_fwd=qarep_fwd, qarep_bwd=qarep_bwd,
+                 maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,
+                 adamw_step=adamw_step, ema_update=ema_update)  # fmt: skip
+
+
 _SUBSET = dict(conv_fprop=conv_fprop, weight_prepare=weight_prepare, convt2x2_fprop=convt2x2_fprop, nchw_f32_to_nhwc_bf16=nchw_f32_to_nhwc_bf16,
                nhwc_bf16_to_nchw_f32=nhwc_bf16_to_nchw_f32, bn_act_infer=bn_act_infer, maxpool_fwd=maxpool_fwd, axpby=axpby, scale_add=scale_add,
                dfl_decode=dfl_decode, pose_keypoint_decode=pose_keypoint_decode, batched_nms=batched_nms)  # fmt: skip
@@ -187,3 +460,11 @@ def install(monkeypatch):
     monkeypatch.setattr(L, "call", refuse)
     for name, fn in _SUBSET.items():
         monkeypatch.setattr(K, name, fn)
+
+
+def install_training(monkeypatch):
+    """install() plus the training subset; host-pinned staging buffers become plain host tensors."""
+    install(monkeypatch)
+    for name, fn in _TRAINING.items():
+        monkeypatch.setattr(K, name, fn)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
