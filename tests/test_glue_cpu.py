@@ -2,6 +2,9 @@
 module wiring, head decoding, post-prediction callbacks and predict() of the detection and pose models against the
 whole-graph oracle.  The CUDA kernels themselves are NOT exercised here (see the `-m gpu` tests)."""
 import copy
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -187,3 +190,74 @@ def test_train_step_stand_in_tracks_the_whole_graph_oracle(golden, monkeypatch):
     assert abs(float(loss) - float(g["loss"])) < 5e-2 * abs(float(g["loss"]))
     for k in ("heads.head1.cls_pred.bias", "heads.head1.reg_pred.bias", "heads.head1.cls_pred.weight"):
         assert l2rel(st.flat.grad_of(k), g["grads"][k].reshape(-1)) < 0.15, (k, l2rel(st.flat.grad_of(k), g["grads"][k].reshape(-1)))
+
+
+_DP_SCRIPT = r"""
+import copy, os, sys, torch, torch.distributed as dist
+root = sys.argv[1]
+sys.path[:0] = [root, os.path.join(root, "tests")]
+from _pytest.monkeypatch import MonkeyPatch
+import cpu_backend
+from super_gradients_b200.training.losses import PPYoloELoss, pad_targets_host
+from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+from super_gradients_b200.training.sg_trainer import TrainStep
+
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+mp = MonkeyPatch()
+cpu_backend.install_training(mp)
+g = torch.load(os.path.join(root, "tests", "golden", "tiny_yolo_nas.pt"), weights_only=False)
+ap = copy.deepcopy(g["arch"])
+m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+m.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+m.train()
+crit = PPYoloELoss(num_classes=4, use_static_assigner=False, sync_normaliser=(sys.argv[2] == "sync"))
+st = TrainStep(m, crit, "SGD", {"weight_decay": 1e-5, "momentum": 0.9}, zero_wd_on_bias_and_bn=True, ema=True)
+assert st.world == world == 2
+x = g["x"] if rank == 0 else torch.flip(g["x"], dims=[0]) * 0.9      # each rank its own shard of the global batch
+tg = g["targets"].clone()
+if rank == 1:
+    tg[:, 0] = (g["x"].shape[0] - 1) - tg[:, 0]
+t = pad_targets_host(tg, x.shape[0], 16)
+lr, wd = 1e-2, 1e-5
+for step in range(3):
+    p0, mom0 = st.flat.params.clone(), st.state[0].clone()
+    st.set_hyper_params(lr, 0.99)
+    loss, _ = st.forward_backward(x, t)
+    local = st.flat.grads.clone()
+    both = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(both, local)
+    assert not torch.equal(both[0], both[1]), "the two ranks must see different data"
+    st.optimizer_step()            # ONE flat all-reduce (SUM), the 1/world average rides in the optimizer's grad_scale
+    st.opt_steps += 1
+    mean = (both[0] + both[1]) / world
+    nd = st.flat.n_decay
+    gg = mean.clone()
+    gg[:nd] += wd * p0[:nd]
+    mom = 0.9 * mom0 + gg
+    torch.testing.assert_close(st.flat.params, p0 - lr * mom, rtol=1e-6, atol=1e-8)
+    mine = [torch.zeros_like(st.flat.params) for _ in range(world)]
+    dist.all_gather(mine, st.flat.params)
+    assert torch.equal(mine[0], mine[1]), "replicas diverged"
+    ema = [torch.zeros_like(st.ema_params) for _ in range(world)]
+    dist.all_gather(ema, st.ema_params)
+    assert torch.equal(ema[0], ema[1])
+print("rank", rank, "ok", float(loss))
+"""
+
+
+@pytest.mark.parametrize("normaliser", ["local", "sync"])
+def test_data_parallel_train_step_world2_gloo(tmp_path, normaliser):
+    """The N>1 path of the training step on two CPU ranks (gloo): per-rank shards, one flat SUM all-reduce of the live
+    gradients, the average applied through the optimizer's grad_scale, replicas (and their EMA) bit-identical afterwards;
+    `sync` also exercises the loss normaliser's all-reduce."""
+    script = tmp_path / "dp.py"
+    script.write_text(_DP_SCRIPT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = "29533" if normaliser == "local" else "29534"
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", port, str(script), root, normaliser],
+        capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"),
+    )  # fmt: skip
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == 2
