@@ -255,6 +255,41 @@ int sgb_loss_finalize(const SgbLossDesc* d, const double* sums, float* loss_out,
 int sgb_head_grad_scatter(const float* grad, int gC, int N, int HW, int L, int anchor_base, sgb_bf16* dy, int pitch,
                           void* stream);
 
+/* ---- YoloNASPoseLoss (row L7: training/losses/yolo_nas_pose_loss.py:45-683) --------------------------------- */
+typedef struct SgbPoseLossDesc {
+  int32_t B, L, J, reg_max;                         /* batch, anchors, joints, DFL bins - 1 */
+  int32_t n_max;                                    /* padded number of GT instances per image */
+  int32_t topk;                                     /* assigner top-k (13) */
+  float alpha, beta;                                /* assigner exponents (1, 6) */
+  float w_cls, w_iou, w_dfl, w_pose_cls, w_pose_reg; /* 1.0, 2.5, 0.5, 1.0, 1.0 */
+  int32_t iou_type;                                 /* 0 = GIoU, 1 = CIoU (default) */
+  int32_t cls_type;                                 /* person classification: 0 = focal (default), 1 = BCE */
+  int32_t pose_cls_type;                            /* joint visibility: 0 = BCE (default), 1 = focal */
+  int32_t multiply_by_oks;                          /* assigner_multiply_by_pose_oks */
+  int32_t rescale_with_score;                       /* rescale_pose_loss_with_assigned_score */
+} SgbPoseLossDesc;
+int64_t sgb_pose_tal_workspace_bytes(const SgbPoseLossDesc* d);
+/* YoloNASPoseTaskAlignedAssigner (:77-244).  cls_logits [B, L] (one class), reg_distri [B, L, 4*(reg_max+1)], pose_coords
+ * [B, L, J, 2] decoded pixels, anchor_points [L, 2], stride_tensor [L]; gt_boxes [B, n_max, 4] xyxy pixels, gt_poses
+ * [B, n_max, J, 3] (x, y, visibility), gt_crowd / gt_valid [B, n_max] uint8, sigmas [J].  Outputs: assigned_gt [B, L]
+ * int32 = index of the assigned NON-CROWD instance or -1, assigned_score [B, L] f32 (0 for background and crowd).
+ * Adds sum(assigned_score) into sums[3] and the number of positive anchors into sums[6] (sums: 8 doubles, zeroed by the
+ * caller). */
+int sgb_pose_tal_assign(const SgbPoseLossDesc* d, const float* cls_logits, const float* reg_distri, const float* pose_coords,
+                        const float* anchor_points, const float* stride_tensor, const float* gt_boxes, const float* gt_poses,
+                        const uint8_t* gt_crowd, const uint8_t* gt_valid, const float* sigmas, int32_t* assigned_gt,
+                        float* assigned_score, double* sums, void* workspace, int64_t workspace_bytes, void* stream);
+/* YoloNASPoseLoss.forward (:404-494) after the assignment, forward and backward in one launch: adds {cls, iou, dfl} into
+ * sums[0..2] and {pose_cls, pose_reg} into sums[4..5], and writes the FINAL gradients of grad_scale * total loss w.r.t.
+ * cls_logits [B, L], reg_distri, pose_coords [B, L, J, 2] and pose_logits [B, L, J] (any grad pointer may be NULL). */
+int sgb_pose_loss_fwd_bwd(const SgbPoseLossDesc* d, const float* cls_logits, const float* reg_distri, const float* pose_coords,
+                          const float* pose_logits, const float* anchor_points, const float* stride_tensor,
+                          const float* gt_boxes, const float* gt_poses, const float* sigmas, const int32_t* assigned_gt,
+                          const float* assigned_score, double* sums, float grad_scale, float* grad_cls, float* grad_reg,
+                          float* grad_pose, float* grad_pose_logits, void* stream);
+/* loss_out [6] = {cls, iou, dfl, pose_cls, pose_reg, total} (weighted, normalised) -- the reference's log_losses. */
+int sgb_pose_loss_finalize(const SgbPoseLossDesc* d, const double* sums, float* loss_out, void* stream);
+
 /* ---- batched NMS (rows N1-N5: pp_yolo_e/post_prediction_callback.py:42-98 + torchvision.ops.batched_nms) ---- */
 typedef struct SgbNmsDesc {
   int32_t B, L, ncls;

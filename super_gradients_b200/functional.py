@@ -504,29 +504,81 @@ class _DflDecode(torch.autograd.Function):
         return tuple(outs)
 
 
-@torch.no_grad()
+class _PoseDecode(torch.autograd.Function):
+    """YoloNASPoseNDFLHeads decode (yolo_nas_pose_ndfl_heads.py:126-206): per-level bf16 NHWC maps reg [B, 4*(reg_max+1), H, W],
+    cls [B, 1 + J, H, W] (channel 0 person logit, 1..J joint logits), pose [B, 2J, H, W] -> the fp32 [B, L, *] tensors.
+    Backward scatters the gradients of the raw outputs (cls_logits, reg_distri, pose_coords, pose_logits) back into the
+    per-level maps; d(pose_coords)/d(offset) = pose_offset_multiplier * stride."""
+
+    @staticmethod
+    def forward(ctx, cfg, *maps):
+        regs, clss, poses = [[K.as_nhwc(t) for t in maps[k::3]] for k in range(3)]
+        B, dev, J = regs[0].shape[0], regs[0].device, cfg.num_joints
+        hws = [r.shape[2] * r.shape[3] for r in regs]
+        Ltot = sum(hws)
+        nb = cfg.reg_max + 1
+        pb = torch.empty((B, Ltot, 4), dtype=torch.float32, device=dev)
+        ps = torch.empty((B, Ltot, 1), dtype=torch.float32, device=dev)
+        cl = torch.empty((B, Ltot, 1), dtype=torch.float32, device=dev)
+        rd = torch.empty((B, Ltot, 4 * nb), dtype=torch.float32, device=dev)
+        pc = torch.empty((B, Ltot, J, 2), dtype=torch.float32, device=dev)
+        pj = torch.empty((B, Ltot, J), dtype=torch.float32, device=dev)
+        pl = torch.empty((B, Ltot, J), dtype=torch.float32, device=dev)
+        base = 0
+        for r, c, p, s, hw in zip(regs, clss, poses, cfg.strides, hws):
+            K.dfl_decode(r, c, Ltot, base, 1, cfg.reg_max, s, cfg.cell_offset, pb, ps, cl, rd)  # class head channel 0 = person logit
+            K.pose_keypoint_decode(p, c, 1, Ltot, base, J, s, cfg.cell_offset, cfg.pose_offset_multiplier, cfg.compensate, pc, pj, pl)
+            base += hw
+        ctx.cfg = cfg
+        ctx.geom = (B, hws, Ltot, [tuple(t.shape) for t in regs], [tuple(t.shape) for t in clss], [tuple(t.shape) for t in poses])
+        ctx.mark_non_differentiable(pb, ps, pj)
+        return pb, ps, pc, pj, cl, rd, pl
+
+    @staticmethod
+    def backward(ctx, _gpb, _gps, gpc, _gpj, gcl, grd, gpl):
+        cfg = ctx.cfg
+        B, hws, Ltot, rshapes, cshapes, pshapes = ctx.geom
+        J = cfg.num_joints
+        some = next(g for g in (gpc, gcl, grd, gpl) if g is not None)
+        g_cls = g_pose = None
+        if gcl is not None or gpl is not None:  # one [B, L, 1 + J] gradient for the class head: person logit, then joint logits
+            zc = gcl if gcl is not None else torch.zeros((B, Ltot, 1), dtype=torch.float32, device=some.device)
+            zl = gpl if gpl is not None else torch.zeros((B, Ltot, J), dtype=torch.float32, device=some.device)
+            g_cls = torch.cat([zc.reshape(B, Ltot, 1), zl], -1).contiguous()
+        if gpc is not None:
+            g_pose = gpc.reshape(B, Ltot, 2 * J).clone()
+            base = 0
+            for s, hw in zip(cfg.strides, hws):
+                g_pose[:, base : base + hw] *= float(cfg.pose_offset_multiplier) * float(s)
+                base += hw
+        outs = [None]
+        base = 0
+        for hw, rs, cs, psh in zip(hws, rshapes, cshapes, pshapes):
+            dr = dc = dp = None
+            if grd is not None:
+                dr = K.empty_nhwc(rs[0], rs[1], rs[2], rs[3], some.device)
+                K.head_grad_scatter(grd.contiguous(), B, hw, Ltot, base, dr)
+            if g_cls is not None:
+                dc = K.empty_nhwc(cs[0], cs[1], cs[2], cs[3], some.device)
+                K.head_grad_scatter(g_cls, B, hw, Ltot, base, dc)
+            if g_pose is not None:
+                dp = K.empty_nhwc(psh[0], psh[1], psh[2], psh[3], some.device)
+                K.head_grad_scatter(g_pose, B, hw, Ltot, base, dp)
+            outs += [dr, dc, dp]
+            base += hw
+        return tuple(outs)
+
+
 def pose_decode(regs, clss, poses, strides, num_joints, reg_max, cell_offset, pose_offset_multiplier=1.0, compensate_grid_cell_offset=True):
-    """YoloNASPoseNDFLHeads decode (yolo_nas_pose_ndfl_heads.py:126-206), inference / evaluation path (no autograd):
-    per-level bf16 NHWC maps reg [B, 4*(reg_max+1), H, W], cls [B, 1 + J, H, W] (channel 0 person logit, 1..J joint logits),
-    pose [B, 2J, H, W] -> fp32 pred_bboxes [B, L, 4], pred_scores [B, L, 1], pose_coords [B, L, J, 2], pose_scores [B, L, J]
-    and the raw cls_logits [B, L, 1], reg_distri [B, L, 4*(reg_max+1)], pose_logits [B, L, J]."""
-    regs, clss, poses = [K.as_nhwc(t) for t in regs], [K.as_nhwc(t) for t in clss], [K.as_nhwc(t) for t in poses]
-    B, dev, J = regs[0].shape[0], regs[0].device, num_joints
-    hws = [r.shape[2] * r.shape[3] for r in regs]
-    Ltot = sum(hws)
-    nb = reg_max + 1
-    pb = torch.empty((B, Ltot, 4), dtype=torch.float32, device=dev)
-    ps = torch.empty((B, Ltot, 1), dtype=torch.float32, device=dev)
-    cl = torch.empty((B, Ltot, 1), dtype=torch.float32, device=dev)
-    rd = torch.empty((B, Ltot, 4 * nb), dtype=torch.float32, device=dev)
-    pc = torch.empty((B, Ltot, J, 2), dtype=torch.float32, device=dev)
-    pj = torch.empty((B, Ltot, J), dtype=torch.float32, device=dev)
-    pl = torch.empty((B, Ltot, J), dtype=torch.float32, device=dev)
-    base = 0
-    for r, c, p, s, hw in zip(regs, clss, poses, strides, hws):
-        K.dfl_decode(r, c, Ltot, base, 1, reg_max, s, cell_offset, pb, ps, cl, rd)  # class head channel 0 = person logit
-        K.pose_keypoint_decode(p, c, 1, Ltot, base, J, s, cell_offset, pose_offset_multiplier, compensate_grid_cell_offset, pc, pj, pl)
-        base += hw
+    """-> pred_bboxes [B, L, 4], pred_scores [B, L, 1], pose_coords [B, L, J, 2] (pixels), pose_scores [B, L, J] and the raw
+    cls_logits [B, L, 1], reg_distri [B, L, 4*(reg_max+1)], pose_logits [B, L, J]; differentiable w.r.t. the maps through
+    pose_coords and the three raw tensors."""
+    cfg = SimpleNamespace(strides=tuple(strides), num_joints=num_joints, reg_max=reg_max, cell_offset=cell_offset, pose_offset_multiplier=pose_offset_multiplier,
+                          compensate=compensate_grid_cell_offset)  # fmt: skip
+    maps = []
+    for r, c, p in zip(regs, clss, poses):
+        maps += [r, c, p]
+    pb, ps, pc, pj, cl, rd, pl = _PoseDecode.apply(cfg, *maps)
     return pb, ps, pc, pj, cl, rd, pl
 
 

@@ -550,6 +550,40 @@ def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab
     return out, gc, gr
 
 
+def pose_loss_desc(B, Lc, J, reg_max, n_max, topk=13, alpha=1.0, beta=6.0, w_cls=1.0, w_iou=2.5, w_dfl=0.5, w_pose_cls=1.0, w_pose_reg=1.0, iou_type=1, cls_type=0,
+                   pose_cls_type=0, multiply_by_oks=False, rescale_with_score=False) -> L.PoseLossDesc:  # fmt: skip
+    """iou_type 0 giou / 1 ciou; cls_type 0 focal / 1 bce; pose_cls_type 0 bce / 1 focal."""
+    d = L.PoseLossDesc()
+    d.B, d.L, d.J, d.reg_max, d.n_max, d.topk = B, Lc, J, reg_max, n_max, topk
+    d.alpha, d.beta, d.w_cls, d.w_iou, d.w_dfl, d.w_pose_cls, d.w_pose_reg = alpha, beta, w_cls, w_iou, w_dfl, w_pose_cls, w_pose_reg
+    d.iou_type, d.cls_type, d.pose_cls_type = iou_type, cls_type, pose_cls_type
+    d.multiply_by_oks, d.rescale_with_score = int(bool(multiply_by_oks)), int(bool(rescale_with_score))
+    return d
+
+
+def pose_tal_assign(d, cls_logits, reg_distri, pose_coords, anchor_points, stride_tensor, gt_boxes, gt_poses, gt_crowd, gt_valid, sigmas, sums):
+    """-> (assigned_gt [B, L] int32: index of the assigned non-crowd instance or -1, assigned_score [B, L] f32); adds the
+    normaliser into sums[3] and the number of positives into sums[6] (sums: 8 zeroed doubles)."""
+    dev = cls_logits.device
+    agt = torch.empty((d.B, d.L), dtype=torch.int32, device=dev)
+    asc = torch.empty((d.B, d.L), dtype=torch.float32, device=dev)
+    nbytes = L.load().sgb_pose_tal_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _timed("sgb_pose_tal_assign", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(pose_coords), _ptr(anchor_points), _ptr(stride_tensor), _ptr(gt_boxes), _ptr(gt_poses),
+           _ptr(gt_crowd), _ptr(gt_valid), _ptr(sigmas), _ptr(agt), _ptr(asc), _ptr(sums), _ptr(ws), nbytes, _stream())  # fmt: skip
+    return agt, asc
+
+
+def pose_loss(d, cls_logits, reg_distri, pose_coords, pose_logits, anchor_points, stride_tensor, gt_boxes, gt_poses, sigmas, agt, asc, sums, grad_scale=1.0, want_grad=True):
+    """-> (items [6] = cls, iou, dfl, pose_cls, pose_reg, total; grad_cls, grad_reg, grad_pose_coords, grad_pose_logits)."""
+    gc, gr, gp, gl = (torch.empty_like(t) if want_grad else None for t in (cls_logits, reg_distri, pose_coords, pose_logits))
+    _timed("sgb_pose_loss_fwd_bwd", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(pose_coords), _ptr(pose_logits), _ptr(anchor_points), _ptr(stride_tensor), _ptr(gt_boxes),
+           _ptr(gt_poses), _ptr(sigmas), _ptr(agt), _ptr(asc), _ptr(sums), float(grad_scale), _ptr(gc), _ptr(gr), _ptr(gp), _ptr(gl), _stream())  # fmt: skip
+    out = torch.empty(6, dtype=torch.float32, device=cls_logits.device)
+    L.call("sgb_pose_loss_finalize", ctypes.byref(d), _ptr(sums), _ptr(out), _stream())
+    return out, gc, gr, gp, gl
+
+
 def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=True, class_agnostic=False, thr_inclusive=None):
     """boxes [B,L,4] f32, scores [B,L,C] f32 -> (out [B,max_out,6], out_idx [B,max_out] int32, count [B] int32)."""
     require_cuda(boxes, "boxes")

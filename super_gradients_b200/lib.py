@@ -76,6 +76,14 @@ class QarepDesc(Structure):
     ]
 
 
+class PoseLossDesc(Structure):  # SgbPoseLossDesc
+    _fields_ = (
+        [(n, c_int32) for n in ("B", "L", "J", "reg_max", "n_max", "topk")]
+        + [(n, c_float) for n in ("alpha", "beta", "w_cls", "w_iou", "w_dfl", "w_pose_cls", "w_pose_reg")]
+        + [(n, c_int32) for n in ("iou_type", "cls_type", "pose_cls_type", "multiply_by_oks", "rescale_with_score")]
+    )
+
+
 class LossDesc(Structure):
     _fields_ = [
         ("B", c_int32),
@@ -152,6 +160,10 @@ _SIGNATURES = {
     "sgb_tal_workspace_bytes": (c_int64, [POINTER(LossDesc)]),
     "sgb_dfl_iou_loss_fwd_bwd": (c_int, [POINTER(LossDesc)] + [P] * 8 + [_F, P, P, P]),
     "sgb_loss_finalize": (c_int, [POINTER(LossDesc), P, P, P]),
+    "sgb_pose_tal_workspace_bytes": (c_int64, [POINTER(PoseLossDesc)]),
+    "sgb_pose_tal_assign": (c_int, [POINTER(PoseLossDesc)] + [P] * 14 + [_L, P]),
+    "sgb_pose_loss_fwd_bwd": (c_int, [POINTER(PoseLossDesc)] + [P] * 12 + [_F] + [P] * 5),
+    "sgb_pose_loss_finalize": (c_int, [POINTER(PoseLossDesc), P, P, P]),
     "sgb_head_grad_scatter": (c_int, [P, _I, _I, _I, _I, _I, P, _I, P]),
     "sgb_nms_workspace_bytes": (c_int64, [POINTER(NmsDesc)]),
     "sgb_batched_nms": (c_int, [POINTER(NmsDesc), P, P, P, P, P, P, _L, P]),
@@ -163,7 +175,7 @@ _SIGNATURES = {
 _lib = None
 
 # kernels launched by one call of each entry point (default 1); LAUNCHES[0] accumulates them (bench.py: gpu_launches)
-LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_sm100_launches": 0, "sgb_sm100_halo_launches": 0, "sgb_debug_read_trace": 0, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
+LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_pose_tal_assign": 4, "sgb_sm100_launches": 0, "sgb_sm100_halo_launches": 0, "sgb_debug_read_trace": 0, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
 LAUNCHES = [0]
 
 

@@ -1,7 +1,7 @@
 """YoloNASPoseNDFLHeads (reference: pose_estimation_models/yolo_nas_pose/yolo_nas_pose_ndfl_heads.py:23-242): runs the
 per-level heads and decodes boxes (DFL softmax integral), person score, keypoints and joint scores with two launches per
-level (sgb_dfl_decode, sgb_pose_keypoint_decode) into the reference's [B, L, *] tensors.  Inference / evaluation path; the
-training path (YoloNASPoseLoss, row L7) has a pinned CPU restatement under tests but no kernels yet and raises."""
+level (sgb_dfl_decode, sgb_pose_keypoint_decode) into the reference's [B, L, *] tensors; in training the raw outputs carry
+gradients back into the per-level maps (functional._PoseDecode) for YoloNASPoseLoss (training/losses/yolo_nas_pose_loss.py)."""
 from typing import List, Optional, Tuple
 
 import torch
@@ -64,8 +64,6 @@ class YoloNASPoseNDFLHeads(BaseDetectionModule):
         """Returns decoded (pred_bboxes [B, L, 4], pred_scores [B, L, 1], pred_pose_coords [B, L, J, 2], pred_pose_scores
         [B, L, J]) in inference_mode, else (decoded, raw) with raw = (cls_logits, reg_distri, pose_coords, pose_logits,
         anchors, anchor_points, num_anchors_list, stride_tensor) like the reference."""
-        if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
-            raise NotImplementedError("YOLO-NAS-POSE training (YoloNASPoseLoss, SURVEY.md row L7) is not implemented yet: run the model under torch.no_grad() / eval")
         feats = feats[: self.num_heads]
         regs, clss, poses = [], [], []
         for i, feat in enumerate(feats):
@@ -78,7 +76,7 @@ class YoloNASPoseNDFLHeads(BaseDetectionModule):
             poses.append(pose)
         pb, ps, pc, pj, cl, rd, pl = SF.pose_decode(regs, clss, poses, self.fpn_strides, self.num_classes, self.reg_max, self.grid_cell_offset, self.pose_offset_multiplier,
                                                     self.compensate_grid_cell_offset)  # fmt: skip
-        decoded = pb, ps, pc, pj
+        decoded = pb, ps, pc.detach(), pj  # the reference decodes from detached clones (:201-202)
         if self.inference_mode:
             return decoded
         shapes = [(f.shape[2], f.shape[3]) for f in feats]

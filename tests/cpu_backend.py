@@ -438,11 +438,49 @@ def ema_update(ema, p, decay_dev):
     ema.mul_(dcy).add_((1 - dcy) * p)
 
 
+# ---- pose loss: the product's own kernel arithmetic (csrc/pose_loss_math.cuh) compiled for the host
+_POSE_HOST = {}
+
+
+def _pose_host():
+    if "h" not in _POSE_HOST:
+        import tempfile
+
+        import host_pose_loss
+
+        _POSE_HOST["dir"] = tempfile.mkdtemp(prefix="sgb_pose_host_")
+        _POSE_HOST["h"] = host_pose_loss.build(_POSE_HOST["dir"])
+    return _POSE_HOST["h"]
+
+
+def pose_tal_assign(d, cls_logits, reg_distri, pose_coords, anchor_points, stride_tensor, gt_boxes, gt_poses, gt_crowd, gt_valid, sigmas, sums):
+    import host_pose_loss
+
+    dummy = torch.zeros((d.B, d.L, d.J))
+    r = host_pose_loss.run(_pose_host(), d, cls_logits, reg_distri, pose_coords, dummy, anchor_points, stride_tensor, gt_boxes, gt_poses, gt_crowd, gt_valid, sigmas)
+    sums[3] += r["sums"][3]
+    sums[6] += r["sums"][6]
+    _POSE_HOST["targets"] = (gt_crowd, gt_valid)
+    return r["assigned_gt"], r["assigned_score"]
+
+
+def pose_loss(d, cls_logits, reg_distri, pose_coords, pose_logits, anchor_points, stride_tensor, gt_boxes, gt_poses, sigmas, agt, asc, sums, grad_scale=1.0, want_grad=True):
+    import host_pose_loss
+
+    gt_crowd, gt_valid = _POSE_HOST["targets"]  # the host driver redoes the assignment (same inputs -> same result)
+    r = host_pose_loss.run(_pose_host(), d, cls_logits, reg_distri, pose_coords, pose_logits, anchor_points, stride_tensor, gt_boxes, gt_poses, gt_crowd, gt_valid, sigmas, grad_scale)
+    assert torch.equal(r["assigned_gt"], agt) and torch.equal(r["assigned_score"], asc)
+    for k in (0, 1, 2, 4, 5):
+        sums[k] += r["sums"][k]
+    gc, gr, gp, gl = r["grads"]
+    return r["items"], gc.reshape(cls_logits.shape), gr, gp, gl
+
+
 _TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgrad_to_oihw, weight_prepare_batch=weight_prepare_batch,
                  run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch,
                  bn_act_fwd=bn_act_fwd, bn_act_bwd=bn_act_bwd, channel_stats=channel_stats, channel_dot=channel_dot, qarep_fwd=qarep_fwd, qarep_bwd=qarep_bwd,
                  maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,
-                 adamw_step=adamw_step, ema_update=ema_update)  # fmt: skip
+                 adamw_step=adamw_step, ema_update=ema_update, pose_tal_assign=pose_tal_assign, pose_loss=pose_loss)  # fmt: skip
 
 
 _SUBSET = dict(conv_fprop=conv_fprop, weight_prepare=weight_prepare, convt2x2_fprop=convt2x2_fprop, nchw_f32_to_nhwc_bf16=nchw_f32_to_nhwc_bf16,

@@ -379,6 +379,50 @@ def golden_tiny_yolo_nas_pose():
                os.path.join(HERE, "tiny_yolo_nas_pose.pt"))  # fmt: skip
 
 
+def golden_tiny_yolo_nas_pose_train():
+    """Row L7 end to end: train-mode forward of the SAME tiny YOLO-NAS-POSE (weights of tiny_yolo_nas_pose.pt), the
+    reference YoloNASPoseLoss in the shipped COCO recipe configuration, backward: loss, components, raw head outputs,
+    updated BatchNorm statistics, gradient sums of every parameter and full gradients of the layers next to the loss."""
+    from super_gradients.training.losses.yolo_nas_pose_loss import YoloNASPoseLoss
+    from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_variants import YoloNASPose
+
+    gen = torch.Generator().manual_seed(15)
+    torch.manual_seed(3)
+    ap = copy.deepcopy(tiny_pose_arch())
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    randomize_bn(m, gen)
+    sd0 = sd_clone(m)
+    prev = torch.load(os.path.join(HERE, "tiny_yolo_nas_pose.pt"), weights_only=False)["sd0"]
+    assert all(torch.equal(sd0[k], v) for k, v in prev.items()), "must start from the weights of tiny_yolo_nas_pose.pt"
+    g2 = torch.Generator().manual_seed(21)
+    x = torch.randn(4, 3, 128, 128, generator=g2)
+    J = 5
+    rows = [(0, 20.0, 24.0, 84.0, 100.0, 0), (0, 60.0, 30.0, 120.0, 90.0, 0), (1, 10.0, 40.0, 70.0, 120.0, 1), (2, 30.0, 20.0, 110.0, 110.0, 0), (3, 48.0, 50.0, 100.0, 118.0, 0)]
+    boxes = torch.tensor([[r[0], r[1], r[2], r[3], r[4]] for r in rows])
+    crowd = torch.tensor([[float(r[0]), float(r[5])] for r in rows])
+    joints = []
+    for r in rows:
+        xy = torch.rand(J, 2, generator=g2) * torch.tensor([r[3] - r[1], r[4] - r[2]]) + torch.tensor([r[1], r[2]])
+        vis = torch.tensor([2.0, 1.0, 0.0, 2.0, 1.0]).roll(int(r[1]) % J)
+        joints.append(torch.cat([torch.full((J, 1), float(r[0])), xy, vis[:, None]], 1))
+    targets = (boxes, torch.stack(joints), crowd)
+    sigmas = [0.026, 0.035, 0.079, 0.072, 0.062]
+    kw = dict(classification_loss_weight=1.0, classification_loss_type="focal", regression_iou_loss_type="ciou", iou_loss_weight=2.5, dfl_loss_weight=0.01,
+              pose_cls_loss_weight=1.0, pose_reg_loss_weight=34.0, pose_classification_loss_type="focal", rescale_pose_loss_with_assigned_score=True,
+              assigner_multiply_by_pose_oks=True)  # fmt: skip
+    m.train()
+    outs = m(x)
+    loss, items = YoloNASPoseLoss(oks_sigmas=sigmas, **kw)(outs, targets)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    running = {k: v for k, v in sd_clone(m).items() if "running_" in k}
+    gsum = {k: (float(g.double().sum()), float(g.double().norm())) for k, g in grads.items()}
+    keep = [k for k in grads if k.startswith("heads.head1") and ("_pred" in k or "pose_convs.1" in k)]
+    torch.save(dict(x=x, targets=targets, sigmas=sigmas, kw=kw, loss=loss.detach(), items=items.detach(), raw=tuple(t.detach().clone() for t in outs[1][:4]),
+                    running1=running, grads={k: grads[k] for k in keep}, grad_sums=gsum),
+               os.path.join(HERE, "tiny_yolo_nas_pose_train.pt"))  # fmt: skip
+
+
 def golden_state_keys():
     """state_dict keys + shapes of the full-size models (for checkpoint compatibility tests)."""
     from super_gradients.training import models
@@ -428,7 +472,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

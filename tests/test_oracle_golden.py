@@ -283,3 +283,45 @@ def test_tiny_yolo_nas_pose_oracle_matches_reference(golden):
         np.testing.assert_array_equal(poses, rp.numpy())
         np.testing.assert_array_equal(scores, rs.numpy())
         np.testing.assert_array_equal(boxes, rb.numpy())
+
+
+_POSE_KW = dict(classification_loss_weight="w_cls", iou_loss_weight="w_iou", dfl_loss_weight="w_dfl", pose_cls_loss_weight="w_pose_cls", pose_reg_loss_weight="w_pose_reg",
+                bbox_assigner_topk="topk", bbox_assigned_alpha="alpha", bbox_assigned_beta="beta")  # fmt: skip
+
+
+def pose_oracle_train_step(arch, sd0, x, targets, sigmas, kw):
+    """Whole-graph oracle, train mode: forward, YoloNASPoseLoss restatement, backward.  Returns (loss, items, raw, params)."""
+    from oracle.yolo_nas_oracle import YoloNASOracle
+
+    p = {k: v.clone() for k, v in sd0.items()}
+    for k, v in p.items():
+        if v.dtype.is_floating_point and "running_" not in k:
+            v.requires_grad_(True)
+    _decoded, raw = YoloNASOracle(arch, p, training=True).forward(x)
+    loss, items = O.yolo_nas_pose_loss(raw, targets, sigmas, **{_POSE_KW.get(k, k): v for k, v in kw.items()})
+    loss.backward()
+    return loss.detach(), items, raw, p
+
+
+def test_tiny_yolo_nas_pose_train_oracle_matches_reference(golden):
+    """Row L7 end to end in fp32: train-mode whole-graph oracle + pose-loss restatement == the unmodified reference on the
+    same tiny model (loss, components, raw head outputs, updated BatchNorm statistics, every parameter's gradient)."""
+    g0, g = golden("tiny_yolo_nas_pose"), golden("tiny_yolo_nas_pose_train")
+    loss, items, raw, p = pose_oracle_train_step(g0["arch"], g0["sd0"], g["x"], g["targets"], g["sigmas"], g["kw"])
+    torch.testing.assert_close(items, g["items"], rtol=2e-4, atol=1e-6)
+    for mine, ref in zip(raw[:4], g["raw"]):
+        torch.testing.assert_close(mine.detach(), ref, rtol=1e-4, atol=2e-3)
+    for k, v in g["running1"].items():
+        torch.testing.assert_close(p[k], v, rtol=1e-4, atol=1e-5)
+    for k, ref in g["grads"].items():
+        torch.testing.assert_close(p[k].grad, ref, rtol=2e-3, atol=2e-6 + 1e-3 * float(ref.abs().max()))
+    live = [k for k in g["grad_sums"] if k in p]
+    assert len(live) == len(g["grad_sums"])
+    zero_ref = {k for k, v in g["grad_sums"].items() if tuple(v) == (0.0, 0.0)}
+    zero_mine = {k for k in live if p[k].grad is None or float(p[k].grad.abs().sum()) == 0.0}
+    assert zero_mine == zero_ref
+    for k in live:
+        if k not in zero_ref:
+            # (biases in front of a train-mode BatchNorm have an identically zero gradient: both sides hold fp32 noise ~1e-6)
+            n_ref = g["grad_sums"][k][1]
+            assert abs(float(p[k].grad.double().norm()) - n_ref) <= 5e-3 * n_ref + 2e-5, k

@@ -1,0 +1,111 @@
+"""Row L7 on the GPU (file name sorts last on purpose: these kernels were written after round 1's GPU budget was spent, so a
+surprise here must not hide the verified suites under `pytest -x`): the CUDA pose-loss kernels against the reference's
+recorded loss / components / gradients and against the oracle on seeded random cases, the assigner against the host build of
+the same arithmetic, and the tiny YOLO-NAS-POSE train step against the whole-graph oracle."""
+import copy
+import shutil
+
+import pytest
+import torch
+
+from oracle import sg_oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.4)")]
+DEV = "cuda"
+
+
+def l2rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def _module_forward_backward(kw, sigmas, raw, targets):
+    from super_gradients_b200.training.losses import YoloNASPoseLoss
+
+    crit = YoloNASPoseLoss(oks_sigmas=sigmas, **kw).to(DEV)
+    leaves = [t.detach().clone().to(DEV).requires_grad_(True) for t in raw[:4]]
+    rest = [t.to(DEV) if torch.is_tensor(t) else t for t in raw[4:]]
+    loss, items = crit((None, (*leaves, *rest)), targets)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), items.cpu(), [t.grad.cpu() for t in leaves]
+
+
+@pytest.mark.parametrize("case", ["loss_default", "loss_oks_rescale_bce_giou", "loss_recipe"])
+def test_pose_loss_kernels_match_the_reference(golden, case):
+    g = golden("pose")[case]
+    loss, items, grads = _module_forward_backward(g["kw"], g["sigmas"], g["raw"], g["targets"])
+    torch.testing.assert_close(items, g["items"], rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(loss, g["loss"], rtol=2e-4, atol=1e-6)
+    for name, a, b in zip(("cls_logits", "reg_distri", "pose_coords", "pose_logits"), grads, g["grads"]):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-7 + 1e-4 * float(b.abs().max()), msg=lambda m, name=name: f"{name}: {m}")
+
+
+@pytest.mark.parametrize("kw_i", range(4))
+@pytest.mark.parametrize("seed,n_inst", [(0, (3, 0, 2)), (1, (1, 4, 1)), (2, (0, 0, 5)), (5, (0, 0, 0))])
+def test_pose_loss_kernels_match_the_oracle(kw_i, seed, n_inst):
+    from test_pose_loss_host import KWS, _oracle, _random_case
+
+    raw, targets, sigmas = _random_case(seed, n_inst=n_inst)
+    loss, items, grads = _module_forward_backward(KWS[kw_i], sigmas, raw, targets)
+    loss_e, items_e, grads_e = _oracle(raw, targets, sigmas, KWS[kw_i])
+    torch.testing.assert_close(items, items_e, rtol=3e-4, atol=1e-6)
+    for name, a, b in zip(("cls_logits", "reg_distri", "pose_coords", "pose_logits"), grads, grads_e):
+        torch.testing.assert_close(a, b, rtol=3e-3, atol=3e-7 + 1e-4 * float(b.abs().max()), msg=lambda m, name=name: f"{name}: {m}")
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+@pytest.mark.parametrize("oks", [False, True])
+def test_pose_assigner_matches_the_host_build_of_the_same_arithmetic(tmp_path, oks):
+    """Larger case (3 levels of a 160x160 input, 12 instances per image): assigned instance per anchor identical, scores equal
+    to fp32 rounding, normaliser and positive count equal."""
+    import host_pose_loss
+    from test_pose_loss_host import _random_case
+
+    from super_gradients_b200 import kernels as K
+    from super_gradients_b200.training.losses import pad_pose_targets_host
+
+    raw, targets, sigmas = _random_case(11, B=4, J=17, reg_max=16, sizes=((20, 20), (10, 10), (5, 5)), strides=(8, 16, 32), n_inst=(12, 3, 0, 7), crowd_every=4)
+    cl, rd, pc, pl, _a, ap, _n, st = raw
+    B, L, J = cl.shape[0], cl.shape[1], pl.shape[-1]
+    gb, gp, gc, gv = pad_pose_targets_host(targets, B, 16)
+    d = K.pose_loss_desc(B, L, J, 16, 16, multiply_by_oks=oks, rescale_with_score=oks)
+    ref = host_pose_loss.run(host_pose_loss.build(str(tmp_path)), d, cl, rd, pc, pl, ap, st, gb, gp, gc, gv, torch.tensor(sigmas))
+    dev = lambda t: t.contiguous().to(DEV)  # noqa: E731
+    sums = torch.zeros(8, dtype=torch.float64, device=DEV)
+    agt, asc = K.pose_tal_assign(d, dev(cl.reshape(B, L)), dev(rd), dev(pc), dev(ap), dev(st.reshape(-1)), dev(gb), dev(gp), dev(gc), dev(gv), dev(torch.tensor(sigmas)), sums)
+    torch.cuda.synchronize()
+    assert int((ref["assigned_gt"] >= 0).sum()) > 20
+    assert torch.equal(agt.cpu(), ref["assigned_gt"])
+    torch.testing.assert_close(asc.cpu(), ref["assigned_score"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(sums.cpu()[[3, 6]], ref["sums"][[3, 6]], rtol=1e-5, atol=1e-7)
+
+
+def test_tiny_yolo_nas_pose_train_step(golden):
+    """The CPU glue test's GPU twin: train-mode forward, YoloNASPoseLoss (recipe configuration), backward."""
+    from test_oracle_golden import pose_oracle_train_step
+
+    from super_gradients_b200.training.losses import YoloNASPoseLoss
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPose
+
+    g0, g = golden("tiny_yolo_nas_pose"), golden("tiny_yolo_nas_pose_train")
+    ap = copy.deepcopy(g0["arch"])
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    m.load_state_dict({k: v.clone() for k, v in g0["sd0"].items()}, strict=False)
+    m = m.to(DEV).train()
+    outs = m(g["x"].to(DEV))
+    loss, items = YoloNASPoseLoss(oks_sigmas=g["sigmas"], **g["kw"]).to(DEV)(outs, g["targets"])
+    loss.backward()
+    torch.cuda.synchronize()
+    with O.bf16_emulation():
+        loss_e, items_e, raw_e, pe = pose_oracle_train_step(g0["arch"], g0["sd0"], g["x"], g["targets"], g["sigmas"], g["kw"])
+    for i, tol in ((0, 2e-2), (1, 0.13), (2, 2e-2), (3, 5e-2)):
+        assert l2rel(outs[1][i], raw_e[i]) < tol, (i, l2rel(outs[1][i], raw_e[i]))
+    assert l2rel(items, items_e) < 0.15, (items, items_e)  # iou^6 * oks scores of a random model: see tests/test_glue_cpu.py
+    params = dict(m.named_parameters())
+    zero_ref = {k for k, v in g["grad_sums"].items() if tuple(v) == (0.0, 0.0)}
+    for k in g["grad_sums"]:
+        assert params[k].grad is not None, k
+        assert (float(params[k].grad.abs().sum()) == 0.0) == (k in zero_ref), k
+    for k in ("heads.head1.cls_pred.bias", "heads.head1.pose_pred.bias", "heads.head1.reg_pred.bias"):
+        assert l2rel(params[k].grad, pe[k].grad) < 0.3, (k, l2rel(params[k].grad, pe[k].grad))
