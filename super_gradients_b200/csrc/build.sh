@@ -4,12 +4,13 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-OUT="$HERE/../libsgb200.so"
+OUT="${SGB_OUT:-$HERE/../libsgb200.so}"   # SGB_OUT / SGB_OBJ: build a variant (e.g. -DSGB_DETERMINISTIC_STATS) next to the default library
+OBJ="${SGB_OBJ:-$HERE/obj}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE" --expt-relaxed-constexpr)
-mkdir -p "$HERE/obj"
+mkdir -p "$OBJ"
 pids=()
 for f in "$HERE"/*.cu; do
-  o="$HERE/obj/$(basename "${f%.cu}").o"
+  o="$OBJ/$(basename "${f%.cu}").o"
   stale=0
   for h in "$HERE"/*.cuh "$HERE"/*.h "$ROOT/include/sgb200.h"; do [[ "$h" -nt "$o" ]] && stale=1; done
   if [[ ! -f "$o" || "$f" -nt "$o" || $stale -eq 1 ]]; then
@@ -18,5 +19,5 @@ for f in "$HERE"/*.cu; do
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/obj/*.o -lcudart
+"$NVCC" -shared -o "$OUT" "$OBJ"/*.o -lcudart
 echo "built $OUT"

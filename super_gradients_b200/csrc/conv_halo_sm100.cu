@@ -117,7 +117,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (SNCH > 0)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += HALO_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < SGB_STATS_SLOTS * 2 * p.BN; i += HALO_THREADS) s_stats[i] = 0.f;
   if (warp == 1) tcgen05_alloc(tmem_slot, p.tmem_cols);
   tcgen05_fence_before();
   __syncthreads();
@@ -335,8 +335,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const float s1 = butterfly_colsum(t1, lane), s2 = butterfly_colsum(t2, lane);
         const int col = c16 * 16 + col_of_lane(lane);
         if ((lane & 1) == 0 && col < p.K) {
+#if SGB_STATS_SLOTS == 1
           atomicAdd(&s_stats[col], s1);
           atomicAdd(&s_stats[p.BN + col], s2);
+#else
+          float* mine = s_stats + quarter * 2 * p.BN;  // one (even lane, column) pair per warp: plain stores
+          mine[col] = s1;
+          mine[p.BN + col] = s2;
+#endif
         }
       }
     }
@@ -349,8 +355,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // stats layout in global memory: [repl][2][K]
     double* st = p.stats + (long long)(blockIdx.x & (p.stats_repl - 1)) * 2 * p.K;
     for (int k = threadIdx.x; k < p.K; k += HALO_THREADS) {
+#if SGB_STATS_SLOTS == 1
       if (s_stats[k] != 0.f) atomicAdd(&st[k], (double)s_stats[k]);
       if (s_stats[p.BN + k] != 0.f) atomicAdd(&st[p.K + k], (double)s_stats[p.BN + k]);
+#else
+      float v1 = s_stats[k], v2 = s_stats[p.BN + k];
+#pragma unroll
+      for (int q = 1; q < SGB_STATS_SLOTS; ++q) {  // fixed order
+        v1 += s_stats[q * 2 * p.BN + k];
+        v2 += s_stats[q * 2 * p.BN + p.BN + k];
+      }
+      if (v1 != 0.f) atomicAdd(&st[k], (double)v1);
+      if (v2 != 0.f) atomicAdd(&st[p.K + k], (double)v2);
+#endif
     }
   }
 }
@@ -574,7 +591,7 @@ bool make_plan(const Problem& q, HaloPlan& pl) {
   const int rowb = var->kc * 2, chunks = var->chunks;
   pl.a_bytes = (uint32_t)chunks * ((HALO_PX * rowb + 1023u) & ~1023u);
   pl.b_tile_bytes = ((uint32_t)(pl.bn * rowb) + 1023u) & ~1023u;
-  pl.ctrl_bytes = 8 * (2 * MAX_A_STAGES + 4 + 2 * MAX_B_TILES) + 16 + 2 * pl.bn * 4 + 64;
+  pl.ctrl_bytes = 8 * (2 * MAX_A_STAGES + 4 + 2 * MAX_B_TILES) + 16 + SGB_STATS_SLOTS * 2 * pl.bn * 4 + 64;
   const int regs_alloc = ((var->regs + 7) / 8) * 8 * HALO_THREADS;
   const int max_ctas_regs = 65536 / regs_alloc > 0 ? 65536 / regs_alloc : 1;
   auto tmem_cols = [&](int bufs) {

@@ -111,7 +111,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < SGB_STATS_SLOTS * 2 * p.N; i += NUM_THREADS) s_stats[i] = 0.f;
   if (warp == 1) tcgen05_alloc(tmem_slot, p.tmem_cols);
   tcgen05_fence_before();
   __syncthreads();
@@ -254,8 +254,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           const float s1 = butterfly_colsum(t1, lane), s2 = butterfly_colsum(t2, lane);
           if ((lane & 1) == 0) {
+#if SGB_STATS_SLOTS == 1
             atomicAdd(&s_stats[c * 16 + col_of_lane(lane)], s1);
             atomicAdd(&s_stats[p.N + c * 16 + col_of_lane(lane)], s2);
+#else
+            float* mine = s_stats + quarter * 2 * p.N;  // this warp's slot: each (even lane, column) is written by one lane
+            mine[c * 16 + col_of_lane(lane)] += s1;
+            mine[p.N + c * 16 + col_of_lane(lane)] += s2;
+#endif
           }
         }
       }
@@ -338,8 +344,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const float s1 = butterfly_colsum(t1, lane), s2 = butterfly_colsum(t2, lane);
             const int c = c0 + col_of_lane(lane);
             if ((lane & 1) == 0 && c < ncols) {
+#if SGB_STATS_SLOTS == 1
               atomicAdd(&s_stats[n0 + c], s1);
               atomicAdd(&s_stats[p.N + n0 + c], s2);
+#else
+              float* mine = s_stats + quarter * 2 * p.N;  // tiles are visited in a fixed order by this warp
+              mine[n0 + c] += s1;
+              mine[p.N + n0 + c] += s2;
+#endif
             }
           }
         }
@@ -355,8 +367,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1) tcgen05_dealloc(tmem_base, p.tmem_cols);
   if (p.stats) {
     double* st = p.stats + (long long)(blockIdx.x & (p.stats_repl - 1)) * 2 * p.N;
-    for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS)
-      if (s_stats[i] != 0.f) atomicAdd(&st[i], (double)s_stats[i]);
+    for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) {
+      float v = s_stats[i];
+#if SGB_STATS_SLOTS > 1
+#pragma unroll
+      for (int q = 1; q < SGB_STATS_SLOTS; ++q) v += s_stats[q * 2 * p.N + i];  // fixed order
+#endif
+      if (v != 0.f) atomicAdd(&st[i], (double)v);
+    }
   }
 }
 
@@ -683,7 +701,7 @@ int launch(const Problem& q, cudaStream_t st) {
   // each other's TMA / MMA / epilogue chains.  Limits: TMEM columns (512 per SM), registers (64K per SM), shared memory.
   const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = bn * p.KC * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + 2 * p.N * 4 + 64;
+  const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + SGB_STATS_SLOTS * 2 * p.N * 4 + 64;
   int ctas_per_sm = 3;
   {
     const char* e = getenv("SGB_CTAS_PER_SM");

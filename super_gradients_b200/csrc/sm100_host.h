@@ -1,6 +1,17 @@
 // Host-side state shared by the tcgen05 / TMA translation units: the driver's tensor-map encoders (resolved through
 // cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda), the SM count and the launch counter.
 #pragma once
+
+// Per-CTA BatchNorm-statistics partials in shared memory.  Default (1 slot): the four epilogue warps add their fp32 partials
+// with shared-memory atomics -- their arrival order is not fixed, so the partial (and with it mean / rstd, in the last fp32
+// bit) can differ between two runs of the same problem.  -DSGB_DETERMINISTIC_STATS gives every epilogue warp its own slot
+// and sums the four slots in a fixed order (bit-reproducible per CTA; costs 3x the statistics' shared memory).
+#ifdef SGB_DETERMINISTIC_STATS
+#define SGB_STATS_SLOTS 4
+#else
+#define SGB_STATS_SLOTS 1
+#endif
+
 #include <cuda.h>
 
 namespace sm100 {

@@ -2,6 +2,8 @@
 # First GPU calls of the next round, cheapest / most informative first (each line is one `gpurun` payload; wrap in `timeout`).
 #   1. bash tools/next_round_gpu_plan.sh verify      -> every GPU test incl. the ones written after round 1's budget ran out
 #   2. bash tools/next_round_gpu_plan.sh repro       -> the interleaved-model anomaly under compute-sanitizer
+#   2b. bash tools/next_round_gpu_plan.sh determinism -> same scenario on the -DSGB_DETERMINISTIC_STATS build (prebuilt HERE by
+#       `SGB_OUT=$PWD/super_gradients_b200/libsgb200_det.so SGB_OBJ=$PWD/super_gradients_b200/csrc/obj_det bash super_gradients_b200/csrc/build.sh -DSGB_DETERMINISTIC_STATS`)
 #   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
 #   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
 set -uo pipefail
@@ -22,6 +24,12 @@ case "${1:-verify}" in
       STEPS=3 timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/repro_interleaved.py > gpurun_out/sanitizer_$tool.log 2>&1
       grep -E "ERROR SUMMARY|Invalid|Uninitialized|at 0x|by thread" gpurun_out/sanitizer_$tool.log | head -30
     done ;;
+  determinism)
+    echo "== default build"; STEPS=6 timeout 120 python tools/repro_interleaved.py 2>&1 | tail -8
+    echo "== deterministic per-warp statistics slots"
+    SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so STEPS=6 timeout 120 python tools/repro_interleaved.py 2>&1 | tail -8
+    SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -m gpu -q --tb=short 2>&1 | tail -5
+    SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so timeout 300 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline 2>/dev/null | cut -c1-300 ;;
   twogpu)
     timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus 2 --steps 8 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err

@@ -35,6 +35,38 @@ def make(g, batched):
     return m, st
 
 
+def trace_forward(m, x):
+    """One no-grad forward with a hook on every module: [(qualified name, output clone)] in execution order."""
+    rec, hooks = [], []
+
+    def mk(name):
+        def hook(_mod, _inp, out):
+            if torch.is_tensor(out):
+                rec.append((name, out.detach().clone()))
+        return hook
+
+    for name, mod in m.named_modules():
+        if name:
+            hooks.append(mod.register_forward_hook(mk(name)))
+    with torch.no_grad():
+        m(x)
+    for h in hooks:
+        h.remove()
+    return rec
+
+
+def first_divergence(ma, mb, x):
+    """Runs both models (identical parameters) once and reports the first module, in execution order, whose outputs differ."""
+    ra, rb = trace_forward(ma, x), trace_forward(mb, x)
+    for (na, ta), (nb, tb) in zip(ra, rb):
+        assert na == nb
+        if ta.shape != tb.shape or not torch.equal(ta, tb):
+            d = (ta.float() - tb.float()).abs()
+            mod = dict(ma.named_modules())[na]
+            return f"first differing module: {na} ({type(mod).__name__}) out {tuple(ta.shape)} max|d|={float(d.max()):.3e} at {int(d.argmax())} n_diff={int((d > 0).sum())}"
+    return "all module outputs identical"
+
+
 def main():
     g = torch.load(os.path.join(ROOT, "tests", "golden", "tiny_yolo_nas.pt"), weights_only=False)
     x = g["x"].cuda()
@@ -55,6 +87,8 @@ def main():
             with torch.no_grad():
                 (_pb, _ps), raw = m(x)
             outs.append(raw[0].clone())
+        if rel(outs[0], outs[1]) > 0 and os.environ.get("LOCALISE", "1") == "1":
+            print("   ", first_divergence(ma, mb, x), flush=True)
         la, _ = sa.forward_backward(x, t)
         lb, _ = sb.forward_backward(x, t)
         print(f"step {i}: forward cls a-b {rel(outs[0], outs[1]):.3e}  a-a {rel(outs[0], outs[2]):.3e}  b-b {rel(outs[1], outs[3]):.3e}   "
