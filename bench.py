@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec YOLO-NAS-S 640 bf16 train"
+WORKLOAD = "configs[1]: YOLO-NAS-S 640x640 synthetic COCO-shape train step (fwd + PPYoloELoss/TAL + bwd + AdamW + EMA)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the conv family over ONE step, from the ncu launch list of this command
 # (profiles/r1_launches_graph_step.txt: 18.936 GB read + 2.052 GB written at per-GPU batch 32); None for other batches
 NCU_CONV_DRAM_BYTES_PER_STEP = {32: 20.988e9}
@@ -132,6 +133,7 @@ def cpu_train_sample(batch, img, threads, max_steps=3, budget_s=90.0):
     arch["bn_eps"], arch["bn_momentum"] = float(arch["bn_eps"]), float(arch["bn_momentum"])
     x, t = synth_batch(batch, 123, img)
     opt_state = {k: (torch.zeros_like(state[k]), torch.zeros_like(state[k])) for k in live}
+    ema = {k: state[k].detach().clone() for k in live}
     times, start = [], time.perf_counter()
     for it in range(max_steps):
         t0 = time.perf_counter()
@@ -141,6 +143,7 @@ def cpu_train_sample(batch, img, threads, max_steps=3, budget_s=90.0):
             m1.mul_(0.9).add_(g, alpha=0.1)
             m2.mul_(0.999).addcmul_(g, g, value=0.001)
             state[k].mul_(1 - 2e-4 * 1e-5).addcdiv_(m1 / (1 - 0.9 ** (it + 1)), (m2 / (1 - 0.999 ** (it + 1))).sqrt_().add_(1e-8), value=-2e-4)
+            ema[k].mul_(0.9997).add_(state[k].detach(), alpha=1 - 0.9997)  # EMA, as in the GPU arm
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - start + times[-1] > budget_s:  # another step would overrun the budget
             break
@@ -160,7 +163,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "YOLO-NAS-S 640x640 train step (fwd + PPYoloELoss/TAL + bwd + AdamW), CPU", "per_step_batch": batch},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH, "parallelism": "cpu", "cuda_graph": False,
+                   "sample": f"each timed step is a bounded sample of the workload: {batch} of the {BATCH} images of a step, fp32 CPU (oracle port)"},
         "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port",
                          "sample": f"{n} timed step(s) of {batch} images x 640x640, fp32 oracle port, torch CPU threads={threads} (fastest of a sweep up to the host's {cores})"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -349,7 +353,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": "configs[1]: YOLO-NAS-S 640x640 synthetic COCO-shape train step (fwd + PPYoloELoss/TAL + bwd + AdamW + EMA)", "per_gpu_batch": batch,
+            "workload": WORKLOAD, "per_gpu_batch": batch,
             "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graph": use_graph,
             "l2": "4 distinct 157 MB input batches rotate (each > 126 MB L2); activations of a step (> 10 GB) never fit L2",
         },
