@@ -302,3 +302,79 @@ def test_tiny_yolo_nas_pose_train_step_glue(golden, monkeypatch):
         assert l2rel(params[k].grad, pe[k].grad) < 0.25, (k, l2rel(params[k].grad, pe[k].grad))
     norms = sorted(abs(float(torch.log(params[k].grad.norm() / pe[k].grad.norm()))) for k in g["grad_sums"] if k not in zero_ref and g["grad_sums"][k][1] > 1e-4)
     assert norms[len(norms) // 2] < 0.1, norms[len(norms) // 2]
+
+
+def test_trainer_train_end_to_end(golden, monkeypatch, tmp_path):
+    """The reference-facing entry point itself, Trainer(...).train(model, training_params, train_loader, valid_loader), on the CPU
+    stand-in: LR warm-up + cosine schedule reaches the optimizer, EMA decay schedule, validation on the EMA weights with the
+    raw weights restored afterwards, rank-0 checkpoints with the reference's keys that load back into a fresh model."""
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.losses import PPYoloELoss
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.sg_trainer import Trainer, cosine_lr
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("tiny_yolo_nas")
+
+    def build():
+        ap = copy.deepcopy(g["arch"])
+        m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+        m.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+        return m
+
+    gen = torch.Generator().manual_seed(0)
+    loader = [(g["x"] + 0.05 * i * torch.randn(g["x"].shape, generator=gen), g["targets"]) for i in range(3)]
+    seen_lr = []
+    orig = sg_trainer.TrainStep.set_hyper_params
+    monkeypatch.setattr(sg_trainer.TrainStep, "set_hyper_params", lambda self, lr, d=None: (seen_lr.append((lr, d)), orig(self, lr, d))[1])
+    tp = dict(max_epochs=2, initial_lr=2e-3, lr_mode="cosine", cosine_final_lr_ratio=0.1, lr_warmup_steps=2, optimizer="SGD", optimizer_params={"momentum": 0.9, "weight_decay": 1e-5},
+              zero_weight_decay_on_bias_and_bn=True, ema=True, ema_params={"decay": 0.99, "decay_type": "threshold"}, loss=PPYoloELoss(num_classes=4, use_static_assigner=False),
+              save_model=True, save_ckpt_epoch_list=[1])  # fmt: skip
+    model = build()
+    trainer = Trainer("glue", ckpt_root_dir=str(tmp_path))
+    hist = trainer.train(model, tp, loader, valid_loader=loader[:1])
+    assert len(hist["train_loss"]) == 2 and len(hist["valid_loss"]) == 2 and len(hist["lr"]) == 6
+    assert all(np.isfinite(v) for v in hist["train_loss"] + hist["valid_loss"])
+    # the schedule: 2 linear warm-up steps from lr0 / 3, then cosine over the remaining 4 of 6 steps down to 0.1 * lr0
+    want = [2e-3 / 3 + (2e-3 - 2e-3 / 3) * s / 2 for s in range(2)] + [cosine_lr(s, 4, 2e-3, 0.1) for s in range(4)]
+    np.testing.assert_allclose([lr for lr, _ in seen_lr], want, rtol=1e-12)
+    np.testing.assert_allclose([d for _, d in seen_lr], [min(0.99, (1 + t) / (10 + t)) for t in range(1, 7)], rtol=1e-12)
+    assert trainer.step.opt_steps == 6 and not np.allclose(hist["train_loss"][0], hist["train_loss"][1])
+    ck = torch.load(tmp_path / "glue" / "ckpt_latest.pth", weights_only=False)
+    assert {"net", "acc", "epoch", "metrics", "optimizer_state_dict", "scaler_state_dict", "processing_params", "ema_net"} <= set(ck) and ck["epoch"] == 1
+    assert (tmp_path / "glue" / "ckpt_best.pth").exists() and (tmp_path / "glue" / "ckpt_epoch_1.pth").exists()
+    assert list(ck["net"].keys()) == g["state_keys"] == list(ck["ema_net"].keys())
+    # the live model holds the RAW weights again after validation; the checkpoint's ema_net differs from them
+    torch.testing.assert_close(ck["net"]["heads.head1.cls_pred.weight"], model.state_dict()["heads.head1.cls_pred.weight"])
+    assert not torch.equal(ck["net"]["heads.head1.cls_pred.weight"], ck["ema_net"]["heads.head1.cls_pred.weight"])
+    fresh = build()
+    fresh.load_state_dict(ck["ema_net"])  # strict
+    fresh.eval()
+    model.eval()
+    trainer.step.swap_ema()
+    with torch.no_grad():
+        (b1, s1), _ = fresh(g["x"])
+        (b2, s2), _ = model(g["x"])
+    assert torch.equal(s1, s2) and torch.equal(b1, b2)  # checkpoint -> fresh model reproduces the EMA model bit for bit
+
+
+def test_trainer_train_pose_model(golden, monkeypatch, tmp_path):
+    """Trainer.train() with YoloNASPose + YoloNASPoseLoss built through the losses registry (flat (boxes, joints, crowd)
+    targets stay on the host and are padded per step): two optimisation steps change the weights, losses stay finite."""
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPose
+    from super_gradients_b200.training.sg_trainer import Trainer
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g0, g = golden("tiny_yolo_nas_pose"), golden("tiny_yolo_nas_pose_train")
+    ap = copy.deepcopy(g0["arch"])
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    m.load_state_dict({k: v.clone() for k, v in g0["sd0"].items()}, strict=False)
+    before = m.heads.head1.pose_pred.weight.detach().clone()
+    tp = dict(max_epochs=1, initial_lr=1e-3, lr_mode="constant", optimizer="AdamW", optimizer_params={"weight_decay": 1e-5}, zero_weight_decay_on_bias_and_bn=True, ema=False,
+              loss="YoloNASPoseLoss", criterion_params=dict(oks_sigmas=g["sigmas"], **g["kw"]), save_model=False)  # fmt: skip
+    hist = Trainer("pose", ckpt_root_dir=str(tmp_path)).train(m, tp, [(g["x"], g["targets"]), (g["x"] * 0.9, g["targets"])])
+    assert len(hist["train_loss"]) == 1 and np.isfinite(hist["train_loss"][0]) and hist["train_loss"][0] > 0
+    assert not torch.equal(before, m.heads.head1.pose_pred.weight.detach())
