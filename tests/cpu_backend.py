@@ -160,15 +160,16 @@ def pose_keypoint_decode(pose, logit, logit_off, L_total, anchor_base, J, stride
 
 
 def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=True, class_agnostic=False, thr_inclusive=None):
-    """Same contract as the CUDA wrapper, implemented with the oracle's post-processing (incl. its tie rule)."""
+    """Same contract as the CUDA wrapper, implemented with the oracle's post-processing (incl. its tie rule): multi-label
+    candidates pass with score > thr, single-label with >= thr (the two modes the product's callbacks use)."""
     B, Lc, C = scores.shape
     inclusive = (not multi_label) if thr_inclusive is None else bool(thr_inclusive)
-    if multi_label or not inclusive:
-        raise NotImplementedError("CPU stand-in: only the single-label inclusive mode is implemented")
+    if inclusive == bool(multi_label):
+        raise NotImplementedError("CPU stand-in: multi-label is exclusive (>), single-label inclusive (>=)")
     out = torch.zeros((B, max_out, 6))
     oidx = torch.full((B, max_out), -1, dtype=torch.int32)
     cnt = torch.zeros((B,), dtype=torch.int32)
-    rows, idx = O.ppyoloe_postprocess(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label_per_box=False, class_agnostic_nms=class_agnostic)
+    rows, idx = O.ppyoloe_postprocess(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label_per_box=bool(multi_label), class_agnostic_nms=class_agnostic)
     for b, (r, i) in enumerate(zip(rows, idx)):
         n = r.shape[0]
         cnt[b] = n

@@ -378,3 +378,28 @@ def test_trainer_train_pose_model(golden, monkeypatch, tmp_path):
     hist = Trainer("pose", ckpt_root_dir=str(tmp_path)).train(m, tp, [(g["x"], g["targets"]), (g["x"] * 0.9, g["targets"])])
     assert len(hist["train_loss"]) == 1 and np.isfinite(hist["train_loss"][0]) and hist["train_loss"][0] > 0
     assert not torch.equal(before, m.heads.head1.pose_pred.weight.detach())
+
+
+def test_yolo_nas_predict_glue(golden, monkeypatch):
+    """model.predict() of the detection mirror (eval switch, batching, PPYoloEPostPredictionCallback defaults and overrides) ==
+    the oracle post-processing of the model's own decoded outputs."""
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+
+    cpu_backend.install(monkeypatch)
+    g = golden("tiny_yolo_nas")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    _load(m, {**g["sd0"], **g["running1"]})
+    m.train()
+    with torch.no_grad():
+        m.eval()
+        (boxes, scores), _ = m(g["x"])
+        m.train()
+    for kw in (dict(conf=0.008, iou=0.6), dict(conf=0.008, iou=0.5, multi_label_per_box=False, class_agnostic_nms=True, max_predictions=7)):
+        out = m.predict(g["x"], batch_size=3, **kw)  # 4 images in batches of 3 + 1
+        assert m.training  # predict() restores the mode
+        ref, _ = O.ppyoloe_postprocess(boxes, scores, kw["conf"], kw["iou"], 1024, kw.get("max_predictions", 300), multi_label_per_box=kw.get("multi_label_per_box", True),
+                                       class_agnostic_nms=kw.get("class_agnostic_nms", False))  # fmt: skip
+        assert len(out) == 4 and sum(r.shape[0] for r in ref) > 0
+        for mine, r in zip(out, ref):
+            np.testing.assert_array_equal(mine.numpy(), r)
