@@ -439,6 +439,19 @@ def ema_update(ema, p, decay_dev):
     ema.mul_(dcy).add_((1 - dcy) * p)
 
 
+def avgpool_fwd(x):
+    y = torch.empty((x.shape[0], x.shape[1], 1, 1), dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y.copy_(_bf16(x.float().mean((2, 3), keepdim=True)))
+    return y
+
+
+def avgpool_bwd(dy, hw_shape):
+    h, w = hw_shape
+    dx = torch.empty((dy.shape[0], dy.shape[1], h, w), dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dx.copy_(_bf16((dy.float() / (h * w)).expand(-1, -1, h, w)))
+    return dx
+
+
 # ---- pose loss: the product's own kernel arithmetic (csrc/pose_loss_math.cuh) compiled for the host
 _POSE_HOST = {}
 
@@ -481,7 +494,7 @@ _TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgr
                  run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch,
                  bn_act_fwd=bn_act_fwd, bn_act_bwd=bn_act_bwd, channel_stats=channel_stats, channel_dot=channel_dot, qarep_fwd=qarep_fwd, qarep_bwd=qarep_bwd,
                  maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,
-                 adamw_step=adamw_step, ema_update=ema_update, pose_tal_assign=pose_tal_assign, pose_loss=pose_loss)  # fmt: skip
+                 adamw_step=adamw_step, ema_update=ema_update, pose_tal_assign=pose_tal_assign, pose_loss=pose_loss, avgpool_fwd=avgpool_fwd, avgpool_bwd=avgpool_bwd)  # fmt: skip
 
 
 _SUBSET = dict(conv_fprop=conv_fprop, weight_prepare=weight_prepare, convt2x2_fprop=convt2x2_fprop, nchw_f32_to_nhwc_bf16=nchw_f32_to_nhwc_bf16,

@@ -403,3 +403,37 @@ def test_yolo_nas_predict_glue(golden, monkeypatch):
         assert len(out) == 4 and sum(r.shape[0] for r in ref) > 0
         for mine, r in zip(out, ref):
             np.testing.assert_array_equal(mine.numpy(), r)
+
+
+def test_trainer_train_resnet18_cifar_follows_the_reference_trajectory(golden, monkeypatch, tmp_path):
+    """config[0] (the reference's own CPU-runnable case) through Trainer.train(): seeded resnet18_cifar from models.get, the
+    fixture's four batches of 64, SGD(0.1, momentum 0.9, wd 1e-4 off for bias / BN) + CrossEntropyLoss from the registry.
+    The per-step losses follow the unmodified reference's (bf16 activations here, fp32 there)."""
+    from super_gradients_b200.training import models, sg_trainer
+    from super_gradients_b200.training.losses import CrossEntropyLoss
+    from super_gradients_b200.training.sg_trainer import Trainer
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("resnet18_cifar_train")
+    torch.manual_seed(0)
+    m = models.get("resnet18_cifar", num_classes=10)
+    gen = torch.Generator().manual_seed(6)
+    X = torch.randn(256, 3, 32, 32, generator=gen)
+    Y = torch.randint(0, 10, (256,), generator=gen)
+    losses = []
+
+    class Recording(CrossEntropyLoss):
+        def forward(self, input, target):
+            loss, item = super().forward(input, target)
+            losses.append(float(loss.detach()))
+            return loss, item
+
+    tp = dict(max_epochs=1, initial_lr=0.1, lr_mode="constant", optimizer="SGD", optimizer_params={"momentum": 0.9, "weight_decay": 1e-4}, zero_weight_decay_on_bias_and_bn=True,
+              loss=Recording(), save_model=False)  # fmt: skip
+    Trainer("cifar", ckpt_root_dir=str(tmp_path)).train(m, tp, [(X[i * 64 : (i + 1) * 64], Y[i * 64 : (i + 1) * 64]) for i in range(4)])
+    ref = [float(v) for v in g["losses"][:4]]
+    assert len(losses) == 4
+    assert abs(losses[0] - ref[0]) < 2e-2 * ref[0], (losses, ref)
+    for mine, r in zip(losses[1:], ref[1:]):
+        assert abs(mine - r) < 0.12 * r, (losses, ref)
