@@ -160,21 +160,36 @@ def pose_keypoint_decode(pose, logit, logit_off, L_total, anchor_base, J, stride
 
 
 def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=True, class_agnostic=False, thr_inclusive=None):
-    """Same contract as the CUDA wrapper, implemented with the oracle's post-processing (incl. its tie rule): multi-label
-    candidates pass with score > thr, single-label with >= thr (the two modes the product's callbacks use)."""
+    """Same contract as the CUDA wrapper (rows [B, max_out, 6], flat candidate index anchor * C + class, count), written
+    directly from the callbacks' definition: candidates (multi-label: every (anchor, class) in nonzero order; single-label:
+    best class per anchor) passing the threshold (> or >=), top-k by (score desc, position asc), torchvision-style NMS."""
+    import numpy as np
+
     B, Lc, C = scores.shape
     inclusive = (not multi_label) if thr_inclusive is None else bool(thr_inclusive)
-    if inclusive == bool(multi_label):
-        raise NotImplementedError("CPU stand-in: multi-label is exclusive (>), single-label inclusive (>=)")
     out = torch.zeros((B, max_out, 6))
     oidx = torch.full((B, max_out), -1, dtype=torch.int32)
     cnt = torch.zeros((B,), dtype=torch.int32)
-    rows, idx = O.ppyoloe_postprocess(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label_per_box=bool(multi_label), class_agnostic_nms=class_agnostic)
-    for b, (r, i) in enumerate(zip(rows, idx)):
-        n = r.shape[0]
+    for b in range(B):
+        bb, ss = boxes[b].float(), scores[b].float()
+        if multi_label:
+            i, j = ((ss >= score_thr) if inclusive else (ss > score_thr)).nonzero(as_tuple=False).T
+            conf = ss[i, j]
+        else:
+            cmax, cidx = ss.max(1)
+            m = (cmax >= score_thr) if inclusive else (cmax > score_thr)
+            i, j, conf = m.nonzero().flatten(), cidx[m], cmax[m]
+        if conf.shape[0] > top_k:
+            order = torch.from_numpy(np.lexsort((np.arange(conf.shape[0]), -conf.numpy()))[:top_k].copy())
+            i, j, conf = i[order], j[order], conf[order]
+        bx = bb[i].numpy()
+        keep = O.nms_numpy(bx, conf.numpy(), iou_thr) if class_agnostic else O.batched_nms_numpy(bx, conf.numpy(), j.numpy(), iou_thr)
+        keep = keep[:max_out]
+        n = len(keep)
         cnt[b] = n
-        out[b, :n] = torch.from_numpy(r)
-        oidx[b, :n] = torch.from_numpy(i).int()
+        if n:
+            out[b, :n] = torch.from_numpy(np.concatenate([bx[keep], conf.numpy()[keep, None], j.numpy()[keep, None].astype(np.float32)], 1))
+            oidx[b, :n] = torch.from_numpy((i.numpy()[keep] * C + j.numpy()[keep]).astype(np.int32))
     return out, oidx, cnt
 
 

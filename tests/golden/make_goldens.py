@@ -303,6 +303,36 @@ def golden_nms():
     torch.save(out, os.path.join(HERE, "nms.pt"))
 
 
+def golden_yolox_nms():
+    """Row N3: the reference's non_max_suppression / YoloXPostPredictionCallback on synthetic YoloX-format predictions."""
+    from super_gradients.training.models.detection_models.yolo_base import YoloXPostPredictionCallback
+    from super_gradients.training.utils.detection_utils import non_max_suppression
+
+    gen = torch.Generator().manual_seed(9)
+    out = {}
+    for case, (B, A, C, conf, multi, withc, agn) in {
+        "multi_conf": (2, 400, 4, 0.35, True, True, False),
+        "multi_raw": (2, 300, 3, 0.6, True, False, False),
+        "single": (2, 500, 5, 0.45, False, True, False),
+        "agnostic": (1, 400, 4, 0.4, True, True, True),
+        "one_empty_image": (2, 200, 3, 0.5, True, True, False),
+        "nothing_passes": (2, 100, 3, 1.5, True, True, False),
+    }.items():
+        cxy = torch.rand(B, A, 2, generator=gen) * 200 + 20
+        wh = torch.rand(B, A, 2, generator=gen) * 60 + 4
+        obj = torch.rand(B, A, 1, generator=gen)
+        cls = torch.rand(B, A, C, generator=gen)
+        if case == "one_empty_image":
+            obj[1] *= 0.4  # below the objectness filter everywhere
+        pred = torch.cat([cxy, wh, obj, cls], -1)
+        kw = dict(conf_thres=conf, iou_thres=0.6, multi_label_per_box=multi, with_confidence=withc, class_agnostic_nms=agn)
+        res = non_max_suppression(pred.clone(), **kw)
+        cb = YoloXPostPredictionCallback(conf=conf, iou=0.6, max_predictions=15, with_confidence=withc, class_agnostic_nms=agn, multi_label_per_box=multi)
+        res_cb = cb((pred.clone(), None))
+        out[case] = dict(pred=pred, kw=kw, result=[None if r is None else r.clone() for r in res], callback=[None if r is None else r.clone() for r in res_cb])
+    torch.save(out, os.path.join(HERE, "yolox_nms.pt"))
+
+
 def golden_tiny_yolo_nas():
     from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
     from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNAS
@@ -472,7 +502,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

@@ -437,3 +437,28 @@ def test_trainer_train_resnet18_cifar_follows_the_reference_trajectory(golden, m
     assert abs(losses[0] - ref[0]) < 2e-2 * ref[0], (losses, ref)
     for mine, r in zip(losses[1:], ref[1:]):
         assert abs(mine - r) < 0.12 * r, (losses, ref)
+
+
+@pytest.mark.parametrize("case", ["multi_conf", "multi_raw", "single", "agnostic", "one_empty_image", "nothing_passes"])
+def test_yolox_non_max_suppression_glue(golden, monkeypatch, case):
+    """Row N3 wiring (objectness filter folded into the scores, cxcywh -> xyxy, thresholds, None for empty images, the
+    callback's truncation) on the stand-in NMS == the unmodified reference's rows."""
+    from super_gradients_b200.lib import SgbError
+    from super_gradients_b200.training.models.detection_models.yolo_base import YoloXPostPredictionCallback
+    from super_gradients_b200.training.utils.detection_utils import non_max_suppression
+
+    cpu_backend.install(monkeypatch)
+    g = golden("yolox_nms")[case]
+    res = non_max_suppression(g["pred"].clone(), **g["kw"])
+    kw = g["kw"]
+    cb = YoloXPostPredictionCallback(conf=kw["conf_thres"], iou=kw["iou_thres"], max_predictions=15, with_confidence=kw["with_confidence"], class_agnostic_nms=kw["class_agnostic_nms"],
+                                     multi_label_per_box=kw["multi_label_per_box"])  # fmt: skip
+    res_cb = cb((g["pred"].clone(), None))
+    for mine, ref in list(zip(res, g["result"])) + list(zip(res_cb, g["callback"])):
+        assert (mine is None) == (ref is None)
+        if ref is not None:
+            np.testing.assert_array_equal(mine.numpy(), ref.numpy())
+    if case == "multi_raw":  # more candidates than the kernel's shared-memory IoU matrix holds: a loud error, not a truncation
+        big = torch.cat([g["pred"]] * 8, 1)
+        with pytest.raises(SgbError, match="candidates"):
+            non_max_suppression(big, **{**kw, "conf_thres": 0.2})

@@ -325,3 +325,15 @@ def test_tiny_yolo_nas_pose_train_oracle_matches_reference(golden):
             # (biases in front of a train-mode BatchNorm have an identically zero gradient: both sides hold fp32 noise ~1e-6)
             n_ref = g["grad_sums"][k][1]
             assert abs(float(p[k].grad.double().norm()) - n_ref) <= 5e-3 * n_ref + 2e-5, k
+
+
+@pytest.mark.parametrize("case", ["multi_conf", "multi_raw", "single", "agnostic", "one_empty_image", "nothing_passes"])
+def test_yolox_nms_oracle_matches_reference(golden, case):
+    """Row N3: the YoloX-format non_max_suppression restatement == the unmodified reference (rows, order, None for empty)."""
+    g = golden("yolox_nms")[case]
+    res = O.yolox_non_max_suppression(g["pred"], **g["kw"])
+    assert len(res) == len(g["result"])
+    for mine, ref in zip(res, g["result"]):
+        assert (mine is None) == (ref is None)
+        if ref is not None:
+            np.testing.assert_array_equal(mine, ref.numpy())

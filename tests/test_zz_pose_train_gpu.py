@@ -109,3 +109,23 @@ def test_tiny_yolo_nas_pose_train_step(golden):
         assert (float(params[k].grad.abs().sum()) == 0.0) == (k in zero_ref), k
     for k in ("heads.head1.cls_pred.bias", "heads.head1.pose_pred.bias", "heads.head1.reg_pred.bias"):
         assert l2rel(params[k].grad, pe[k].grad) < 0.3, (k, l2rel(params[k].grad, pe[k].grad))
+
+
+@pytest.mark.parametrize("case", ["multi_conf", "multi_raw", "single", "agnostic", "one_empty_image", "nothing_passes"])
+def test_yolox_non_max_suppression_vs_reference_golden(golden, case):
+    """Row N3 on the batched NMS kernel (single-label with an exclusive threshold is a mode the other callbacks do not use)."""
+    import numpy as np
+
+    from super_gradients_b200.training.models.detection_models.yolo_base import YoloXPostPredictionCallback
+    from super_gradients_b200.training.utils.detection_utils import non_max_suppression
+
+    g = golden("yolox_nms")[case]
+    kw = g["kw"]
+    res = non_max_suppression(g["pred"].to(DEV), **kw)
+    cb = YoloXPostPredictionCallback(conf=kw["conf_thres"], iou=kw["iou_thres"], max_predictions=15, with_confidence=kw["with_confidence"], class_agnostic_nms=kw["class_agnostic_nms"],
+                                     multi_label_per_box=kw["multi_label_per_box"])  # fmt: skip
+    res_cb = cb((g["pred"].to(DEV), None))
+    for mine, ref in list(zip(res, g["result"])) + list(zip(res_cb, g["callback"])):
+        assert (mine is None) == (ref is None)
+        if ref is not None:
+            np.testing.assert_array_equal(mine.cpu().numpy(), ref.numpy())
