@@ -462,3 +462,23 @@ def test_yolox_non_max_suppression_glue(golden, monkeypatch, case):
         big = torch.cat([g["pred"]] * 8, 1)
         with pytest.raises(SgbError, match="candidates"):
             non_max_suppression(big, **{**kw, "conf_thres": 0.2})
+
+
+def test_ppyoloe_loss_is_agnostic_to_the_head_output_form(golden, monkeypatch):
+    """Row L0b: PPYOLOEHead's train mode returns the raw 6-tuple alone, NDFLHeads / eval mode return (decoded, raw); the loss
+    accepts both (ppyolo_loss.py:959-964) and gives the same value and gradients."""
+    from super_gradients_b200.training.losses import PPYoloELoss
+
+    cpu_backend.install_training(monkeypatch)
+    g = golden("tiny_yolo_nas")
+    anchors, anchor_points, nums, strides = O.anchors_for_levels([(16, 16), (8, 8), (4, 4)], (8, 16, 32))
+    res = []
+    for wrap in (False, True):
+        cl, rd = g["train_cls_logits"].clone().requires_grad_(True), g["train_reg_distri"].clone().requires_grad_(True)
+        raw = (cl, rd, anchors, anchor_points, nums, strides)
+        loss, items = PPYoloELoss(num_classes=4, use_static_assigner=False)(((g["train_pred_bboxes"], g["train_pred_scores"]), raw) if wrap else raw, g["targets"])
+        loss.backward()
+        res.append((loss.detach(), items, cl.grad, rd.grad))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    torch.testing.assert_close(res[0][1], g["items"], rtol=1e-4, atol=1e-6)  # and it is the reference's value on the reference's own logits
