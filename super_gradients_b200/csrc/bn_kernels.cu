@@ -48,6 +48,8 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
 //   double* out; int out_stride;                (only when NACC > 0)
 template <class Op>
 __global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M, const int C) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   constexpr int NCOEF = Op::NCOEF, NACC = Op::NACC;
   extern __shared__ float sc[];  // [NCOEF][C] (+ [NACC][cvb*8] reduction scratch)
   op.prologue(sc);
@@ -119,7 +121,7 @@ int launch_chan(const Op& op, int64_t M, int C, cudaStream_t st, const char* wha
     cudaFuncSetAttribute(chan_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr = true;
   }
-  chan_kernel<Op><<<grid, TPB, smem, st>>>(op, M, C);
+  SGB_LAUNCH(chan_kernel<Op>, grid, TPB, smem, st, op, M, C);
   return sgb_cuda_check(cudaGetLastError(), what);
 }
 

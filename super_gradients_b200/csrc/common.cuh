@@ -76,3 +76,32 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch (experiment, -DSGB_PDL; the default build compiles these to nothing and launches with <<<>>>).
+// A kernel first tells the runtime that its dependents may be scheduled (SGB_GRID_DEP_LAUNCH), does whatever does not touch
+// global memory (barrier init, TMEM allocation, shared-memory clears), then SGB_GRID_DEP_WAIT blocks until every prerequisite
+// grid has completed and its writes are visible.  The launch side marks the kernel as programmatically serialised, so its CTAs
+// may become resident while the previous kernel drains; stream capture turns that into programmatic graph edges.
+#ifdef SGB_PDL
+#define SGB_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define SGB_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <class... KArgs, class... Args>
+static inline void sgb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // a failure surfaces through cudaGetLastError() at the call site
+}
+#define SGB_LAUNCH(kernel, grid, block, smem, st, ...) sgb_launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
+#else
+#define SGB_GRID_DEP_LAUNCH() ((void)0)
+#define SGB_GRID_DEP_WAIT() ((void)0)
+#define SGB_LAUNCH(kernel, grid, block, smem, st, ...) kernel<<<grid, block, smem, st>>>(__VA_ARGS__)
+#endif

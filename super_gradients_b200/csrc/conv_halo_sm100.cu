@@ -85,6 +85,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int KSTEPS = KC / 16;
   constexpr uint32_t A_REGION = ((uint32_t)(HALO_PX * ROWB) + 1023u) & ~1023u;
   constexpr uint32_t A_BYTES = CHUNKS * A_REGION;
+  SGB_GRID_DEP_LAUNCH();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base, b_base = smem_base + (uint32_t)p.a_stages * A_BYTES;
@@ -122,6 +123,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  SGB_GRID_DEP_WAIT();  // everything above touches only shared memory / TMEM
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -405,6 +407,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
   constexpr uint32_t B_REGION = ((uint32_t)(HALO_PX * ROWB) + 1023u) & ~1023u;
   constexpr int NB = 3 * KCB;  // GEMM N of one MMA: three horizontal taps
   constexpr int WG_MAX_STAGES = 8;
+  SGB_GRID_DEP_LAUNCH();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ctrl = smem_base + (uint32_t)p.stages * p.stage_bytes;
@@ -434,6 +437,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  SGB_GRID_DEP_WAIT();  // everything above touches only shared memory / TMEM
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -697,7 +701,7 @@ int halo_launch(const Problem& q, cudaStream_t st) {
   }
   int grid = p.total_tiles;
   if (grid > g_num_sms * ctas) grid = g_num_sms * ctas;
-  var->fn<<<grid, HALO_THREADS, smem, st>>>(map_a, map_b, p);
+  SGB_LAUNCH(var->fn, grid, HALO_THREADS, smem, st, map_a, map_b, p);
   ++g_launches;
   ++g_halo_launches;
   return sgb_cuda_check(cudaGetLastError(), "conv3x3_halo_kernel");
@@ -808,7 +812,7 @@ int wgrad_halo_launch(const WgradProblem& q, cudaStream_t st) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sgb_set_error("cuTensorMapEncodeTiled(halo wgrad x) failed with %d", (int)r); return SGB_E_CUDA; }
   }
-  pl.fn<<<pl.grid, HALO_THREADS, pl.smem, st>>>(map_dy, map_x, p);
+  SGB_LAUNCH(pl.fn, pl.grid, HALO_THREADS, pl.smem, st, map_dy, map_x, p);
   ++g_launches;
   ++g_halo_launches;
   return sgb_cuda_check(cudaGetLastError(), "wgrad3x3_halo_kernel");

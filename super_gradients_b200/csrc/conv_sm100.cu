@@ -79,6 +79,7 @@ __device__ long long g_trace[12][512];
 template <int NCH, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  SGB_GRID_DEP_LAUNCH();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = p.BN * p.KC * 2;
@@ -116,6 +117,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  SGB_GRID_DEP_WAIT();  // everything above touches only shared memory / TMEM
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -416,6 +418,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, int ro
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WParams p) {
+  SGB_GRID_DEP_LAUNCH();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = 2 * WPIX * 128;                       // two 64-channel blocks of dy
@@ -455,6 +458,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  SGB_GRID_DEP_WAIT();  // everything above touches only shared memory / TMEM
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -757,7 +761,7 @@ int launch(const Problem& q, cudaStream_t st) {
   }
   int grid = m_tiles * n_tiles;
   if (grid > g_num_sms * ctas_per_sm) grid = g_num_sms * ctas_per_sm;
-  var.fn<<<grid, NUM_THREADS, smem, st>>>(map_a, map_b, p);
+  SGB_LAUNCH(var.fn, grid, NUM_THREADS, smem, st, map_a, map_b, p);
   ++g_launches;
   return sgb_cuda_check(cudaGetLastError(), "conv_umma_kernel");
 }
@@ -849,7 +853,7 @@ int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
     attr = true;
   }
   const int grid = base_ctas * splits;
-  wgrad_umma_kernel<<<grid, NUM_THREADS, smem, st>>>(map_dy, map_x, p);
+  SGB_LAUNCH(wgrad_umma_kernel, grid, NUM_THREADS, smem, st, map_dy, map_x, p);
   ++g_launches;
   return sgb_cuda_check(cudaGetLastError(), "wgrad_umma_kernel");
 }

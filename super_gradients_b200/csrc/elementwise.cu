@@ -116,6 +116,8 @@ __device__ __forceinline__ int find_item(const Item* items, int n, int64_t i) {
 }
 
 __global__ void weight_prepare_batch_kernel(const SgbWeightItem* __restrict__ items, int n, int64_t total) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const SgbWeightItem it = items[find_item(items, n, i)];
     weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f,
@@ -124,6 +126,8 @@ __global__ void weight_prepare_batch_kernel(const SgbWeightItem* __restrict__ it
 }
 
 __global__ void wgrad_to_oihw_batch_kernel(const SgbWgradItem* __restrict__ items, int n, int64_t total) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const SgbWgradItem it = items[find_item(items, n, i)];
     wgrad_to_oihw_elem(it.dw, it.C, it.R, it.S, it.c_pad, it.g, it.accumulate, i - it.start);
@@ -132,6 +136,8 @@ __global__ void wgrad_to_oihw_batch_kernel(const SgbWgradItem* __restrict__ item
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W, bf16* y, int pitch,
                                     int off, int cpad) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   // one thread per (n, h, w, cvec) writes 8 channels; reads are strided by H*W but coalesced across w.
   const int64_t hw = (int64_t)H * W;
   const int cv = cpad / 8;
@@ -153,6 +159,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, i
 
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, int H, int W, int pitch, int off,
                                     float* y) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const int64_t hw = (int64_t)H * W;
   const int64_t total = (int64_t)N * C * hw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -169,6 +177,8 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, in
 // contribution of 8 consecutive channels of one pixel.
 template <class F>
 __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C, double* out, int out_stride) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   constexpr int NACC = F::NACC;
   extern __shared__ float sred[];  // [TPB][NACC*8]
   const int cvs = C / 8;
@@ -218,7 +228,7 @@ int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaS
   size_t smem = (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
   int64_t want = (M + 255) / 256;  // >= 256 pixels per CTA
   int grid = (int)(want < 1 ? 1 : (want > 148 * 6 ? 148 * 6 : want));
-  chan_reduce_kernel<F><<<grid, TPB, smem, st>>>(f, M, C, out, out_stride);
+  SGB_LAUNCH(chan_reduce_kernel<F>, grid, TPB, smem, st, f, M, C, out, out_stride);
   SGB_LAUNCH_CHECK("chan_reduce_kernel");
   return SGB_OK;
 }
@@ -257,6 +267,8 @@ struct QarepMomF {
 // ---------------------------------------------------------------------------------------------- pooling etc.
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int xp, int xo, int k,
                                    int stride, int pad, bf16* y, int P, int Q, int yp, int yo, uint8_t* idx) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const int cvs = C / 8;
   const int64_t total = (int64_t)N * P * Q * cvs;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -297,6 +309,8 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int
 
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, int N, int H, int W, int C, int k, int stride, int pad,
                                    int P, int Q, int dyp, int dyo, const uint8_t* idx, float* dx) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const int64_t total = (int64_t)N * P * Q * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = i % C;
@@ -315,6 +329,8 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, int N, int H, in
 
 __global__ void axpby_kernel(const bf16* __restrict__ x1, int p1, int o1, float a, const bf16* __restrict__ x2, int p2,
                              int o2, float b, bf16* y, int py, int oy, int64_t M, int C) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const int cvs = C / 8;
   const int64_t total = M * cvs;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -335,6 +351,8 @@ __global__ void axpby_kernel(const bf16* __restrict__ x1, int p1, int o1, float 
 
 __global__ void scale_add_kernel(const bf16* __restrict__ x1, int p1, int o1, const float* a_dev,
                                  const bf16* __restrict__ x2, int p2, int o2, bf16* y, int py, int oy, int64_t M, int C) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const float a = *a_dev;
   const int cvs = C / 8;
   const int64_t total = M * cvs;
@@ -392,6 +410,8 @@ __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, int N, int HW, i
 // sgd   hp: [lr, momentum, weight_decay, grad_scale, nesterov]
 // adamw hp: [lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale]
 __global__ void sgd_kernel(float* p, const float* g, float* mom, int64_t n, const float* hp) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const float lr = hp[0], mu = hp[1], wd = hp[2], gs = hp[3];
   const bool nesterov = hp[4] != 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -406,6 +426,8 @@ __global__ void sgd_kernel(float* p, const float* g, float* mom, int64_t n, cons
   }
 }
 __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, int64_t n, const float* hp) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], gs = hp[7];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gr = g[i] * gs;
@@ -419,6 +441,8 @@ __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, int64
   }
 }
 __global__ void ema_kernel(float* e, const float* p, int64_t n, const float* decay) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
   const float d = *decay;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     e[i] = e[i] * d + (1.f - d) * p[i];
@@ -450,14 +474,14 @@ extern "C" int sgb_wgrad_to_oihw(const float* dw, int K, int C, int R, int S, in
 
 extern "C" int sgb_weight_prepare_batch(const SgbWeightItem* items_dev, int n_items, int64_t total, void* stream) {
   SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
-  weight_prepare_batch_kernel<<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(items_dev, n_items, total);
+  SGB_LAUNCH(weight_prepare_batch_kernel, grid_for(total), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
   SGB_LAUNCH_CHECK("weight_prepare_batch_kernel");
   return SGB_OK;
 }
 
 extern "C" int sgb_wgrad_to_oihw_batch(const SgbWgradItem* items_dev, int n_items, int64_t total, void* stream) {
   SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
-  wgrad_to_oihw_batch_kernel<<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(items_dev, n_items, total);
+  SGB_LAUNCH(wgrad_to_oihw_batch_kernel, grid_for(total), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
   SGB_LAUNCH_CHECK("wgrad_to_oihw_batch_kernel");
   return SGB_OK;
 }
@@ -469,8 +493,7 @@ extern "C" int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, in
   SGB_REQUIRE(c_out >= C && c_out % 8 == 0, "c_out must be >= C and a multiple of 8");
   int cpad = c_out;  // channels [C, c_out) are written as zeros
   SGB_REQUIRE(y_pitch >= y_off + cpad, "slice exceeds pitch");
-  nchw_to_nhwc_kernel<<<grid_for((int64_t)N * H * W * (cpad / 8)), TPB, 0, (cudaStream_t)stream>>>(
-      x, N, C, H, W, (bf16*)y, y_pitch, y_off, cpad);
+  SGB_LAUNCH(nchw_to_nhwc_kernel, grid_for((int64_t)N * H * W * (cpad / 8)), TPB, 0, (cudaStream_t)stream,  x, N, C, H, W, (bf16*)y, y_pitch, y_off, cpad);
   SGB_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return SGB_OK;
 }
@@ -478,8 +501,7 @@ extern "C" int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, in
 extern "C" int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H, int W, int x_pitch, int x_off,
                                          float* y, void* stream) {
   SGB_REQUIRE(x && y, "null pointer");
-  nhwc_to_nchw_kernel<<<grid_for((int64_t)N * C * H * W), TPB, 0, (cudaStream_t)stream>>>((const bf16*)x, N, C, H, W,
-                                                                                        x_pitch, x_off, y);
+  SGB_LAUNCH(nhwc_to_nchw_kernel, grid_for((int64_t)N * C * H * W), TPB, 0, (cudaStream_t)stream, (const bf16*)x, N, C, H, W, x_pitch, x_off, y);
   SGB_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return SGB_OK;
 }
@@ -506,8 +528,7 @@ extern "C" int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, in
               "bad args");
   SGB_REQUIRE(k * k <= 255, "kernel too large for uint8 arg-max");
   SGB_REQUIRE(P == (H + 2 * pad - k) / stride + 1 && Q == (W + 2 * pad - k) / stride + 1, "P/Q inconsistent");
-  maxpool_fwd_kernel<<<grid_for((int64_t)N * P * Q * (C / 8)), TPB, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, N, H, W, C, x_pitch, x_off, k, stride, pad, (bf16*)y, P, Q, y_pitch, y_off, idx);
+  SGB_LAUNCH(maxpool_fwd_kernel, grid_for((int64_t)N * P * Q * (C / 8)), TPB, 0, (cudaStream_t)stream,  (const bf16*)x, N, H, W, C, x_pitch, x_off, k, stride, pad, (bf16*)y, P, Q, y_pitch, y_off, idx);
   SGB_LAUNCH_CHECK("maxpool_fwd_kernel");
   return SGB_OK;
 }
@@ -515,8 +536,7 @@ extern "C" int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, in
 extern "C" int sgb_maxpool_bwd(const sgb_bf16* dy, int N, int H, int W, int C, int k, int stride, int pad, int P,
                                int Q, int dy_pitch, int dy_off, const uint8_t* idx, float* dx_f32, void* stream) {
   SGB_REQUIRE(dy && idx && dx_f32, "null pointer");
-  maxpool_bwd_kernel<<<grid_for((int64_t)N * P * Q * C), TPB, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, N, H, W, C, k, stride, pad, P, Q, dy_pitch, dy_off, idx, dx_f32);
+  SGB_LAUNCH(maxpool_bwd_kernel, grid_for((int64_t)N * P * Q * C), TPB, 0, (cudaStream_t)stream,  (const bf16*)dy, N, H, W, C, k, stride, pad, P, Q, dy_pitch, dy_off, idx, dx_f32);
   SGB_LAUNCH_CHECK("maxpool_bwd_kernel");
   return SGB_OK;
 }
@@ -525,8 +545,7 @@ extern "C" int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_
                          sgb_bf16* y, int py, int oy, int64_t M, int C, void* stream) {
   SGB_REQUIRE(x1 && y && C % 8 == 0 && p1 % 8 == 0 && o1 % 8 == 0 && py % 8 == 0 && oy % 8 == 0, "bad args");
   SGB_REQUIRE(!x2 || (p2 % 8 == 0 && o2 % 8 == 0), "bad args (x2)");
-  axpby_kernel<<<grid_for(M * (C / 8), TPB * 4), TPB, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x1, p1, o1, a, (const bf16*)x2, p2, o2, b, (bf16*)y, py, oy, M, C);
+  SGB_LAUNCH(axpby_kernel, grid_for(M * (C / 8), TPB * 4), TPB, 0, (cudaStream_t)stream,  (const bf16*)x1, p1, o1, a, (const bf16*)x2, p2, o2, b, (bf16*)y, py, oy, M, C);
   SGB_LAUNCH_CHECK("axpby_kernel");
   return SGB_OK;
 }
@@ -535,8 +554,7 @@ extern "C" int sgb_scale_add(const sgb_bf16* x1, int p1, int o1, const float* a_
                              sgb_bf16* y, int py, int oy, int64_t M, int C, void* stream) {
   SGB_REQUIRE(x1 && y && a_dev && C % 8 == 0 && p1 % 8 == 0 && o1 % 8 == 0 && py % 8 == 0 && oy % 8 == 0, "bad args");
   SGB_REQUIRE(!x2 || (p2 % 8 == 0 && o2 % 8 == 0), "bad args (x2)");
-  scale_add_kernel<<<grid_for(M * (C / 8), TPB * 4), TPB, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x1, p1, o1, a_dev, (const bf16*)x2, p2, o2, (bf16*)y, py, oy, M, C);
+  SGB_LAUNCH(scale_add_kernel, grid_for(M * (C / 8), TPB * 4), TPB, 0, (cudaStream_t)stream,  (const bf16*)x1, p1, o1, a_dev, (const bf16*)x2, p2, o2, (bf16*)y, py, oy, M, C);
   SGB_LAUNCH_CHECK("scale_add_kernel");
   return SGB_OK;
 }
@@ -572,19 +590,19 @@ extern "C" int sgb_avgpool_bwd(const sgb_bf16* dy, int N, int HW, int C, sgb_bf1
 
 extern "C" int sgb_sgd_step(float* p, const float* g, float* mom, int64_t n, const float* hp, void* stream) {
   SGB_REQUIRE(p && g && mom && hp, "null pointer");
-  sgd_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, mom, n, hp);
+  SGB_LAUNCH(sgd_kernel, grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream, p, g, mom, n, hp);
   SGB_LAUNCH_CHECK("sgd_kernel");
   return SGB_OK;
 }
 extern "C" int sgb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp, void* stream) {
   SGB_REQUIRE(p && g && m && v && hp, "null pointer");
-  adamw_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hp);
+  SGB_LAUNCH(adamw_kernel, grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream, p, g, m, v, n, hp);
   SGB_LAUNCH_CHECK("adamw_kernel");
   return SGB_OK;
 }
 extern "C" int sgb_ema_update(float* ema, const float* p, int64_t n, const float* decay, void* stream) {
   SGB_REQUIRE(ema && p && decay, "null pointer");
-  ema_kernel<<<grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream>>>(ema, p, n, decay);
+  SGB_LAUNCH(ema_kernel, grid_for(n, TPB * 4), TPB, 0, (cudaStream_t)stream, ema, p, n, decay);
   SGB_LAUNCH_CHECK("ema_kernel");
   return SGB_OK;
 }

@@ -284,7 +284,7 @@ def test_resnet18_cifar_training_matches_reference_trajectory(golden):
     assert abs(losses[1] - g["losses"][1]) < 0.1 * g["losses"][1]
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.4)")
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.5)")
 def test_tiny_yolo_nas_pose_eval_and_predict(golden):
     """Row L8 end to end on the GPU: eval-mode YoloNASPose (reference arch + state dict) -> decoded boxes / person scores /
     keypoints / joint scores and raw head outputs against the whole-graph oracle in bf16-emulation mode (tight) and the fp32

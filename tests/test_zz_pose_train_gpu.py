@@ -10,7 +10,7 @@ import torch
 
 from oracle import sg_oracle as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.4)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.5)")]
 DEV = "cuda"
 
 

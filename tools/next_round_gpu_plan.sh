@@ -4,6 +4,8 @@
 #   2. bash tools/next_round_gpu_plan.sh repro       -> the interleaved-model anomaly under compute-sanitizer
 #   2b. bash tools/next_round_gpu_plan.sh determinism -> same scenario on the -DSGB_DETERMINISTIC_STATS build (prebuilt HERE by
 #       `SGB_OUT=$PWD/super_gradients_b200/libsgb200_det.so SGB_OBJ=$PWD/super_gradients_b200/csrc/obj_det bash super_gradients_b200/csrc/build.sh -DSGB_DETERMINISTIC_STATS`)
+#   2c. bash tools/next_round_gpu_plan.sh pdl -> programmatic dependent launch build (-DSGB_PDL, prebuilt HERE the same way into
+#       super_gradients_b200/libsgb200_pdl.so): kernel / module / trainer suites, then default vs PDL bench back to back
 #   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
 #   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
 set -uo pipefail
@@ -30,6 +32,11 @@ case "${1:-verify}" in
     SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so STEPS=6 timeout 120 python tools/repro_interleaved.py 2>&1 | tail -8
     SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -m gpu -q --tb=short 2>&1 | tail -5
     SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so timeout 300 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline 2>/dev/null | cut -c1-300 ;;
+  pdl)
+    SGB200_LIB=$PWD/super_gradients_b200/libsgb200_pdl.so timeout 500 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py tests/test_trainer_gpu.py -m gpu -q --tb=short -x 2>&1 | tail -6
+    for lib in libsgb200.so libsgb200_pdl.so; do
+      echo "== $lib"; SGB200_LIB=$PWD/super_gradients_b200/$lib timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/bench_$lib.err | cut -c1-260
+    done ;;
   twogpu)
     timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus 2 --steps 8 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
