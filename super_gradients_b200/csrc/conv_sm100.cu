@@ -203,6 +203,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // statistics are accumulated per thread (row) in registers across ALL tiles of this CTA and reduced across the
       // warp once at the end, so a tile costs ~3.5 instructions per element.
       float a1[STATS ? NCH * 16 : 1], a2[STATS ? NCH * 16 : 1];
+#ifdef SGB_UMMA_WIDE_STORE
+      const bool wide_store = (p.y_pitch % 16 == 0) && (p.y_off % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 31) == 0);
+#endif
       if constexpr (STATS) {
 #pragma unroll
         for (int i = 0; i < NCH * 16; ++i) a1[i] = a2[i] = 0.f;
@@ -226,8 +229,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           if (row_ok) {
             if (!(p.dbg & 1)) {
-              *reinterpret_cast<uint4*>(yrow + c * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(yrow + c * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#ifdef SGB_UMMA_WIDE_STORE  // experiment: one 256-bit store per 16 channels (as the halo kernels do) when the row is 32-byte aligned
+              if (wide_store) {
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + c * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                             "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                             : "memory");
+              } else
+#endif
+              {
+                *reinterpret_cast<uint4*>(yrow + c * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(yrow + c * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
             }
             if constexpr (STATS) {
 #pragma unroll
