@@ -10,6 +10,8 @@
 #       im2col kernels' fast epilogue) / _exp (all flags) benched back to back
 #   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
 #   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
+# NOTE: the experiment libraries (libsgb200_{det,pdl,wide,exp}.so) are listed in .gpurunignore so that routine calls stay small:
+# comment those lines out before `determinism`, `pdl` or `variants`.
 set -uo pipefail
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
