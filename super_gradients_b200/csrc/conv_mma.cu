@@ -182,7 +182,11 @@ __global__ void __launch_bounds__(THREADS) igemm_conv_kernel(const __grid_consta
   float* sstat = reinterpret_cast<float*>(smem_raw);  // [2][BN]
   const bool do_stats = p.stats != nullptr;
   if (do_stats) {
+#ifdef SGB_DETERMINISTIC_STATS  // one slot per warp row (sm100_host.h explains the experiment)
+    for (int i = tid; i < WARPS_M * 2 * BN; i += THREADS) sstat[i] = 0.f;
+#else
     for (int i = tid; i < 2 * BN; i += THREADS) sstat[i] = 0.f;
+#endif
     __syncthreads();
   }
   float cs1[NT][2], cs2[NT][2];
@@ -256,8 +260,13 @@ __global__ void __launch_bounds__(THREADS) igemm_conv_kernel(const __grid_consta
         }
         if (lane < 4) {
           int c = wn * WTN + nt * 8 + 2 * lane + e;
+#ifdef SGB_DETERMINISTIC_STATS
+          sstat[wm * 2 * BN + c] = a;  // (wm, column) is owned by exactly one lane of one warp
+          sstat[wm * 2 * BN + BN + c] = b;
+#else
           atomicAdd(&sstat[c], a);
           atomicAdd(&sstat[BN + c], b);
+#endif
         }
       }
     __syncthreads();
@@ -266,8 +275,19 @@ __global__ void __launch_bounds__(THREADS) igemm_conv_kernel(const __grid_consta
     for (int c = tid; c < BN; c += THREADS) {
       int col = n0 + c;
       if (col < p.Ngemm) {
+#ifdef SGB_DETERMINISTIC_STATS
+        float v1 = sstat[c], v2 = sstat[BN + c];
+#pragma unroll
+        for (int q = 1; q < WARPS_M; ++q) {  // fixed order
+          v1 += sstat[q * 2 * BN + c];
+          v2 += sstat[q * 2 * BN + BN + c];
+        }
+        atomicAdd(&st[col], (double)v1);
+        atomicAdd(&st[p.Ngemm + col], (double)v2);
+#else
         atomicAdd(&st[col], (double)sstat[c]);
         atomicAdd(&st[p.Ngemm + col], (double)sstat[BN + c]);
+#endif
       }
     }
   }
