@@ -12,7 +12,7 @@ pids=()
 for f in "$HERE"/*.cu; do
   o="$OBJ/$(basename "${f%.cu}").o"
   stale=0
-  for h in "$HERE"/*.cuh "$HERE"/*.h "$ROOT/include/sgb200.h"; do [[ "$h" -nt "$o" ]] && stale=1; done
+  for h in "$HERE"/*.cuh "$HERE"/*.h "$HERE"/*.inc "$ROOT/include/sgb200.h"; do [[ "$h" -nt "$o" ]] && stale=1; done
   if [[ ! -f "$o" || "$f" -nt "$o" || $stale -eq 1 ]]; then
     "$NVCC" "${FLAGS[@]}" "$@" -c "$f" -o "$o" &
     pids+=($!)

@@ -8,6 +8,8 @@
 #       super_gradients_b200/libsgb200_pdl.so): kernel / module / trainer suites, then default vs PDL bench back to back
 #   2d. bash tools/next_round_gpu_plan.sh variants -> default / _det / _pdl / _wide (-DSGB_UMMA_WIDE_STORE: 256-bit stores in the
 #       im2col kernels' fast epilogue) / _exp (all flags) benched back to back
+#       _1x1 (-DSGB_HALO_1X1: 1x1 stride-1 convolutions on the halo kernel's pipeline with a plain 16 x 16 tile; run
+#       `SGB200_LIB=.../libsgb200_1x1.so pytest tests/test_kernels_gpu.py -m gpu -k conv` first)
 #   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
 #   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
 # NOTE: the experiment libraries (libsgb200_{det,pdl,wide,exp}.so) are listed in .gpurunignore so that routine calls stay small:
@@ -37,7 +39,7 @@ case "${1:-verify}" in
     SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -m gpu -q --tb=short 2>&1 | tail -5
     SGB200_LIB=$PWD/super_gradients_b200/libsgb200_det.so timeout 300 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline 2>/dev/null | cut -c1-300 ;;
   variants)  # every prepared experiment, one bench each (each library is a full build with one -D flag; exp = all of them)
-    for v in "" _det _pdl _wide _exp; do
+    for v in "" _det _pdl _wide _1x1 _exp; do
       lib=$PWD/super_gradients_b200/libsgb200$v.so; [[ -f $lib ]] || { echo "missing $lib (see the header of this script)"; continue; }
       printf "%-22s" "libsgb200$v.so"; SGB200_LIB=$lib timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/bench_variant$v.err | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('%.1f img/s  %.3f ms/step  e2e %.1f' % (d['value'], d['ms_per_step'], d['e2e']['value']))"
     done ;;
