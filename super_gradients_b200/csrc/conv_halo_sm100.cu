@@ -291,7 +291,10 @@ HaloVariant* find_variant(int C, int bn, bool stats) {
 #define SGB_TILE1(KC_, CH_) \
   {KC_, CH_, 0, conv1x1_tile_kernel<KC_, CH_, 0>, 0, false}, {KC_, CH_, (KC_ * CH_) / 16, conv1x1_tile_kernel<KC_, CH_, (KC_ * CH_) / 16>, 0, false}
 HaloVariant g_variants_1x1[] = {SGB_TILE1(32, 1), SGB_TILE1(16, 3), SGB_TILE1(64, 1), SGB_TILE1(32, 3),
-                                {64, 2, 0, conv1x1_tile_kernel<64, 2, 0>, 0, false}, {64, 3, 0, conv1x1_tile_kernel<64, 3, 0>, 0, false}};
+                                {64, 2, 0, conv1x1_tile_kernel<64, 2, 0>, 0, false}, {64, 3, 0, conv1x1_tile_kernel<64, 3, 0>, 0, false},
+                                // ConvBNAct 1x1 layers of the CSP stages change the channel count: statistics for K != C
+                                {32, 3, 2, conv1x1_tile_kernel<32, 3, 2>, 0, false}, {64, 1, 6, conv1x1_tile_kernel<64, 1, 6>, 0, false},
+                                {64, 3, 4, conv1x1_tile_kernel<64, 3, 4>, 0, false}, {32, 3, 3, conv1x1_tile_kernel<32, 3, 3>, 0, false}};
 #undef SGB_TILE1
 HaloVariant* find_variant_1x1(int C, int bn, bool stats) {
   for (HaloVariant& v : g_variants_1x1)

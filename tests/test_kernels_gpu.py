@@ -83,6 +83,9 @@ CONV_CASES = [
     (3, 48, 13, 37, 48, 1, 1, 0),
     (2, 128, 19, 16, 64, 1, 1, 0),
     (40, 32, 64, 64, 32, 1, 1, 0),
+    (4, 96, 40, 40, 32, 1, 1, 0),
+    (4, 64, 24, 24, 96, 1, 1, 0),
+    (2, 192, 20, 20, 64, 1, 1, 0),
 ]
 
 
