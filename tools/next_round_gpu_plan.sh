@@ -55,5 +55,11 @@ case "${1:-verify}" in
   profile)
     SGB_PROFILER_RANGE=1 timeout 700 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
       --clock-control none --csv --log-file gpurun_out/launches_next.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/ncu_next.log 2>&1
-    timeout 200 python tools/layer_profile.py > gpurun_out/layers_next.txt 2>&1; head -40 gpurun_out/layers_next.txt ;;
+    timeout 200 python tools/layer_profile.py > gpurun_out/layers_next.txt 2>&1; head -40 gpurun_out/layers_next.txt
+    # what limits the streaming BN / QARepVGG passes (2.3-3.3 TB/s of 6.6) and the im2col kernel on 1x1 layers: one full capture each
+    for kn in "chan_kernel" "conv_umma_kernel" "wgrad_umma_kernel"; do
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kn --launch-skip 12 --launch-count 2 -o gpurun_out/full_$kn -f \
+        python bench.py --steps 1 --warmup 1 --no-graph --skip-cpu-baseline > gpurun_out/ncu_full_$kn.log 2>&1
+      ncu -i gpurun_out/full_$kn.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py 2>/dev/null | head -30
+    done ;;
 esac
