@@ -306,6 +306,24 @@ int64_t sgb_nms_workspace_bytes(const SgbNmsDesc* d);
 int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const float* scores, float* out, int32_t* out_idx,
                     int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- fused predict() pre-processing (training/processing/processing.py:205-590, pipelines.py:192-216) ---- */
+typedef struct SgbPreprocDesc {
+  int32_t src_h, src_w, src_c; /* uint8 H x W x C source image (C <= 4) */
+  int32_t src_pitch;           /* bytes per source row */
+  int32_t dst_h, dst_w;        /* size after the rescale step (== src_h, src_w: no resize) */
+  int32_t out_h, out_w;        /* padded canvas = the model's input size */
+  int32_t pad_top, pad_left;   /* where the resized image sits on the canvas */
+  int32_t out_pitch;           /* channel pitch (elements) of the bf16 NHWC output slot; channels >= src_c are written as 0 */
+  int32_t reverse_channels;    /* ReverseImageChannels: output channel c reads source channel src_c - 1 - c */
+  int32_t normalize;           /* NormalizeImage: (v - mean[c]) / std[c] after the standardisation */
+  float pad_value;             /* Detection*Padding pad_value, in uint8 units (114) */
+  double max_value;            /* StandardizeImage: v / max_value; <= 0 skips it */
+  float mean[4], std[4];
+} SgbPreprocDesc;
+/* src: device uint8 image; out: device bf16 [out_h, out_w, out_pitch] (one image slot of an NHWC batch).  Bit-exact with
+ * cv2.resize(INTER_LINEAR) + numpy padding / scaling of the reference pipeline followed by a round-to-nearest bf16 store. */
+int sgb_preprocess_u8(const SgbPreprocDesc* d, const uint8_t* src, sgb_bf16* out, void* stream);
+
 /* ---- optimizer over the flat parameter buffer (sg_trainer.py:634-644) --------------------------------------- */
 /* Hyper-parameters live in DEVICE memory (so a CUDA-graph-captured step follows the host-side LR schedule):
  *   sgd   hp[5] = {lr, momentum, weight_decay, grad_scale, nesterov}

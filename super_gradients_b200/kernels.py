@@ -325,6 +325,34 @@ def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def preprocess_u8(src, out_slot, dst_hw, pad_tl, pad_value=114.0, max_value=255.0, reverse_channels=False, mean=None, std=None):
+    """Fused predict() pre-processing of ONE image.  src: uint8 [H, W, C] (C <= 4) on the device; out_slot: bf16 NHWC view
+    [1 or -, c_pad, out_h, out_w] of the batch tensor (one image), channels >= C are zeroed.  dst_hw: size after the rescale
+    step; pad_tl: (top, left) position of the resized image on the canvas."""
+    require_cuda(src, "image")
+    if src.dtype != torch.uint8 or src.dim() != 3 or not src.is_contiguous():
+        raise L.SgbError("image must be a contiguous uint8 [H, W, C] tensor")
+    slot = out_slot if out_slot.dim() == 4 else out_slot.unsqueeze(0)
+    d = L.PreprocDesc()
+    d.src_h, d.src_w, d.src_c = src.shape
+    d.src_pitch = src.shape[1] * src.shape[2]
+    d.dst_h, d.dst_w = int(dst_hw[0]), int(dst_hw[1])
+    d.out_h, d.out_w = slot.shape[2], slot.shape[3]
+    d.pad_top, d.pad_left = int(pad_tl[0]), int(pad_tl[1])
+    d.out_pitch = nhwc_pitch(slot)
+    d.reverse_channels = 1 if reverse_channels else 0
+    d.pad_value = float(pad_value)
+    d.max_value = float(max_value) if max_value else 0.0
+    d.normalize = 1 if mean is not None else 0
+    for i in range(4):
+        d.mean[i] = float(mean[i]) if mean is not None and i < len(mean) else 0.0
+        d.std[i] = float(std[i]) if std is not None and i < len(std) else 1.0
+    if slot.shape[0] != 1 or slot.shape[1] != d.out_pitch:
+        raise L.SgbError("out_slot must be one image of a dense NHWC batch (all its channels)")
+    _timed("sgb_preprocess_u8", ctypes.byref(d), _ptr(src), _ptr(slot), _stream())
+    return out_slot
+
+
 # ------------------------------------------------------------------------------------------------ batch norm
 def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL) -> L.BnDesc:
     n, c, h, w = x.shape

@@ -84,6 +84,13 @@ class PoseLossDesc(Structure):  # SgbPoseLossDesc
     )
 
 
+class PreprocDesc(Structure):  # SgbPreprocDesc
+    _fields_ = (
+        [(n, c_int32) for n in ("src_h", "src_w", "src_c", "src_pitch", "dst_h", "dst_w", "out_h", "out_w", "pad_top", "pad_left", "out_pitch", "reverse_channels", "normalize")]
+        + [("pad_value", c_float), ("max_value", c_double), ("mean", c_float * 4), ("std", c_float * 4)]
+    )
+
+
 class LossDesc(Structure):
     _fields_ = [
         ("B", c_int32),
@@ -160,6 +167,7 @@ _SIGNATURES = {
     "sgb_tal_workspace_bytes": (c_int64, [POINTER(LossDesc)]),
     "sgb_dfl_iou_loss_fwd_bwd": (c_int, [POINTER(LossDesc)] + [P] * 8 + [_F, P, P, P]),
     "sgb_loss_finalize": (c_int, [POINTER(LossDesc), P, P, P]),
+    "sgb_preprocess_u8": (c_int, [POINTER(PreprocDesc), P, P, P]),
     "sgb_pose_tal_workspace_bytes": (c_int64, [POINTER(PoseLossDesc)]),
     "sgb_pose_tal_assign": (c_int, [POINTER(PoseLossDesc)] + [P] * 14 + [_L, P]),
     "sgb_pose_loss_fwd_bwd": (c_int, [POINTER(PoseLossDesc)] + [P] * 12 + [_F] + [P] * 5),

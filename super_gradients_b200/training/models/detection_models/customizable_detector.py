@@ -86,10 +86,15 @@ class CustomizableDetector(SgModule):
             self._default_class_agnostic_nms = bool(class_agnostic_nms)
 
     @torch.no_grad()
-    def predict(self, images: torch.Tensor, iou=None, conf=None, batch_size: int = 32, fuse_model: bool = True, nms_top_k=None, max_predictions=None, multi_label_per_box=None, class_agnostic_nms=None):
-        """Tensor-input predict(): images [B, C, H, W] already pre-processed (the reference's per-image numpy
-        pre/post-processing in training/pipelines/pipelines.py is host-side and out of scope).
+    def predict(self, images, iou=None, conf=None, batch_size: int = 32, fuse_model: bool = True, nms_top_k=None, max_predictions=None, multi_label_per_box=None, class_agnostic_nms=None):
+        """images: either a pre-processed tensor [B, C, H, W], or raw images -- one uint8 H x W x C array or a list of them (any
+        sizes) -- which go through the model's image processor (set_dataset_processing_params; default: the YOLO-NAS COCO chain)
+        as ONE fused GPU launch per image (training/processing/processing.py) and whose boxes come back in original-image pixels,
+        like the reference's Pipeline (training/pipelines/pipelines.py:192-216).
         Returns a list (one per image) of [Ni, 6] tensors (x1, y1, x2, y2, confidence, class)."""
+        if not torch.is_tensor(images):
+            return self._predict_raw_images(images, dict(iou=iou, conf=conf, nms_top_k=nms_top_k, max_predictions=max_predictions, multi_label_per_box=multi_label_per_box,
+                                                         class_agnostic_nms=class_agnostic_nms), batch_size)  # fmt: skip
         cb = self.get_post_prediction_callback(
             conf=self._default_nms_conf if conf is None else conf,
             iou=self._default_nms_iou if iou is None else iou,
@@ -104,4 +109,19 @@ class CustomizableDetector(SgModule):
         for i in range(0, images.shape[0], batch_size):
             out += cb(self(images[i : i + batch_size]))
         self.train(was_training)
+        return out
+
+    def _predict_raw_images(self, images, kw, batch_size):
+        from ...processing import default_yolo_nas_coco_processing_params
+
+        import numpy as np
+
+        images = [images] if isinstance(images, np.ndarray) else list(images)
+        processor = self._image_processor or default_yolo_nas_coco_processing_params()["image_processor"]
+        device = next(self.parameters()).device
+        out = []
+        for i in range(0, len(images), batch_size):
+            batch, geos = processor.preprocess_batch(images[i : i + batch_size], device)
+            rows = self.predict(batch, batch_size=batch_size, **kw)
+            out += [processor.postprocess_boxes(r, g) for r, g in zip(rows, geos)]
         return out

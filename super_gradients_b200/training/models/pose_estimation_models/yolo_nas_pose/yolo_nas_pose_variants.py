@@ -41,8 +41,26 @@ class YoloNASPose(CustomizableDetector):
     @torch.no_grad()
     def predict(self, images: torch.Tensor, iou: Optional[float] = None, conf: Optional[float] = None, pre_nms_max_predictions: Optional[int] = None,
                 post_nms_max_predictions: Optional[int] = None, batch_size: int = 32, fuse_model: bool = True) -> List[PoseEstimationPredictions]:  # fmt: skip
-        """Tensor-input predict(): images [B, C, H, W] already pre-processed (the reference's per-image numpy pipeline,
-        training/pipelines/pipelines.py, is host-side and out of scope).  One PoseEstimationPredictions per image."""
+        """images: a pre-processed tensor [B, C, H, W], or raw images (one uint8 H x W x C array or a list of them, any sizes) that
+        go through the model's image processor (default: the YOLO-NAS-POSE COCO chain) as one fused GPU launch per image, with
+        poses and boxes returned in original-image pixels.  One PoseEstimationPredictions per image."""
+        if not torch.is_tensor(images):
+            import numpy as np
+
+            from ....processing import default_yolo_nas_pose_coco_processing_params
+
+            raw = [images] if isinstance(images, np.ndarray) else list(images)
+            processor = self._image_processor or default_yolo_nas_pose_coco_processing_params()["image_processor"]
+            device = next(self.parameters()).device
+            out: List[PoseEstimationPredictions] = []
+            for i in range(0, len(raw), batch_size):
+                batch, geos = processor.preprocess_batch(raw[i : i + batch_size], device)
+                preds = self.predict(batch, iou=iou, conf=conf, pre_nms_max_predictions=pre_nms_max_predictions, post_nms_max_predictions=post_nms_max_predictions, batch_size=batch_size)
+                for pr, g in zip(preds, geos):
+                    poses = pr.poses.clone()
+                    poses[..., :2] = processor.postprocess_keypoints(pr.poses[..., :2], g)
+                    out.append(PoseEstimationPredictions(poses=poses, scores=pr.scores, bboxes_xyxy=processor.postprocess_boxes(pr.bboxes_xyxy, g)))
+            return out
         cb = self.get_post_prediction_callback(
             conf=conf or self._default_nms_conf or 0.5, iou=iou or self._default_nms_iou or 0.7,
             pre_nms_max_predictions=pre_nms_max_predictions or self._default_pre_nms_max_predictions or 300,

@@ -512,9 +512,16 @@ _TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgr
                  adamw_step=adamw_step, ema_update=ema_update, pose_tal_assign=pose_tal_assign, pose_loss=pose_loss, avgpool_fwd=avgpool_fwd, avgpool_bwd=avgpool_bwd)  # fmt: skip
 
 
+def preprocess_u8(*args, **kwargs):
+    """The product's own pre-processing arithmetic (csrc/preprocess_math.cuh) compiled for the host."""
+    import host_preprocess
+
+    return host_preprocess.preprocess_u8(*args, **kwargs)
+
+
 _SUBSET = dict(conv_fprop=conv_fprop, weight_prepare=weight_prepare, convt2x2_fprop=convt2x2_fprop, nchw_f32_to_nhwc_bf16=nchw_f32_to_nhwc_bf16,
                nhwc_bf16_to_nchw_f32=nhwc_bf16_to_nchw_f32, bn_act_infer=bn_act_infer, maxpool_fwd=maxpool_fwd, axpby=axpby, scale_add=scale_add,
-               dfl_decode=dfl_decode, pose_keypoint_decode=pose_keypoint_decode, batched_nms=batched_nms)  # fmt: skip
+               dfl_decode=dfl_decode, pose_keypoint_decode=pose_keypoint_decode, batched_nms=batched_nms, preprocess_u8=preprocess_u8)  # fmt: skip
 
 
 def install(monkeypatch):

@@ -333,6 +333,54 @@ def golden_yolox_nms():
     torch.save(out, os.path.join(HERE, "yolox_nms.pt"))
 
 
+def golden_processing():
+    """Row (f)-N3: the reference's own ComposeProcessing chains (cv2 + numpy) on random uint8 images, and their box post-processing."""
+    import numpy as np
+    from super_gradients.training.processing import processing as P
+    from super_gradients.training.utils.predict import DetectionPrediction, PoseEstimationPrediction
+
+    import hashlib
+
+    rng = np.random.RandomState(12)  # legacy stream: frozen across numpy versions, so the tests regenerate the images instead of storing them
+    chains = {
+        "yolo_nas_default": (lambda: [P.DetectionLongestMaxSizeRescale(output_shape=(636, 636)), P.DetectionCenterPadding(output_shape=(640, 640), pad_value=114),
+                                      P.StandardizeImage(max_value=255.0), P.ImagePermute(permutation=(2, 0, 1))],
+                             dict(rescale=(636, 636), keep_aspect=True, pad_shape=(640, 640), pad_value=114, center=True)),
+        "pose_default": (lambda: [P.ReverseImageChannels(), P.KeypointsLongestMaxSizeRescale(output_shape=(640, 640)), P.KeypointsBottomRightPadding(output_shape=(640, 640), pad_value=127),
+                                  P.StandardizeImage(max_value=255.0), P.ImagePermute(permutation=(2, 0, 1))],
+                         dict(rescale=(640, 640), keep_aspect=True, pad_shape=(640, 640), pad_value=127, center=False, reverse=True)),
+        "stretch_normalize": (lambda: [P.DetectionRescale(output_shape=(96, 160)), P.StandardizeImage(max_value=255.0), P.NormalizeImage(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]),
+                                       P.ImagePermute(permutation=(2, 0, 1))],
+                              dict(rescale=(96, 160), keep_aspect=False, mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])),
+    }  # fmt: skip
+    out = {}
+    for name, (mk, kw) in chains.items():
+        cases = []
+        for (h, w) in [(427, 640), (640, 480), (333, 500), (1080, 1920), (64, 48), (640, 640)]:
+            seed = int(rng.randint(0, 2**31 - 1))
+            img = np.random.RandomState(seed).randint(0, 256, (h, w, 3)).astype(np.uint8)
+            cp = P.ComposeProcessing(mk())
+            pre, metas = cp.preprocess_image(img)
+            boxes = np.concatenate([rng.uniform(0, pre.shape[2] / 2, (5, 1)), rng.uniform(0, pre.shape[1] / 2, (5, 1)),
+                                    rng.uniform(0, pre.shape[2], (5, 1)), rng.uniform(0, pre.shape[1], (5, 1))], 1).astype(np.float32)
+            poses = np.concatenate([rng.uniform(0, pre.shape[2], (5, 4, 1)), rng.uniform(0, pre.shape[1], (5, 4, 1)), rng.uniform(0, 1, (5, 4, 1))], -1).astype(np.float32)
+            if name == "pose_default":
+                pred = PoseEstimationPrediction(poses=poses.copy(), scores=np.ones(5, np.float32), bboxes_xyxy=boxes.copy(), edge_links=np.zeros((0, 2), int), edge_colors=np.zeros((0, 3), int),
+                                                keypoint_colors=np.zeros((4, 3), int), image_shape=pre.shape[1:])
+            else:
+                pred = DetectionPrediction(bboxes=boxes.copy(), bbox_format="xyxy", confidence=np.ones(5, np.float32), labels=np.zeros(5, np.float32), image_shape=pre.shape[1:])
+            post = cp.postprocess_predictions(pred, metas)
+            pre_bf16 = torch.from_numpy(np.ascontiguousarray(pre)).to(torch.bfloat16)  # what the model mirrors consume (round to nearest)
+            case = dict(image_seed=seed, image_shape=(h, w), pre_shape=tuple(pre.shape), pre_sha256=hashlib.sha256(pre_bf16.view(torch.int16).numpy().tobytes()).hexdigest(),
+                        pre_sample=pre_bf16[:, ::37, ::41].clone(), pre_sum=float(pre_bf16.double().sum()),
+                        boxes=torch.from_numpy(boxes), boxes_post=torch.from_numpy(np.asarray(post.bboxes_xyxy, dtype=np.float32)))
+            if name == "pose_default":
+                case.update(poses=torch.from_numpy(poses), poses_post=torch.from_numpy(np.asarray(post.poses, dtype=np.float32)))
+            cases.append(case)
+        out[name] = dict(kw=kw, cases=cases)
+    torch.save(out, os.path.join(HERE, "processing.pt"))
+
+
 def golden_tiny_yolo_nas():
     from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
     from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNAS
@@ -502,7 +550,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

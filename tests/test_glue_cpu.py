@@ -482,3 +482,63 @@ def test_ppyoloe_loss_is_agnostic_to_the_head_output_form(golden, monkeypatch):
     for a, b in zip(*res):
         assert torch.equal(a, b)
     torch.testing.assert_close(res[0][1], g["items"], rtol=1e-4, atol=1e-6)  # and it is the reference's value on the reference's own logits
+
+
+def test_predict_on_raw_images_matches_the_reference_pipeline_steps(golden, monkeypatch):
+    """predict() on raw uint8 images of different sizes: fused pre-processing (host build of the kernel arithmetic) -> model ->
+    NMS -> boxes in original-image pixels == the oracle's chain (the reference's Pipeline steps) around the same model."""
+    from super_gradients_b200.training import processing as P
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+
+    cpu_backend.install(monkeypatch)
+    g = golden("tiny_yolo_nas")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    _load(m, {**g["sd0"], **g["running1"]})
+    m.set_dataset_processing_params(image_processor=P.ComposeProcessing([P.DetectionLongestMaxSizeRescale((120, 120)), P.DetectionCenterPadding((128, 128), pad_value=114),
+                                                                         P.StandardizeImage(255.0), P.ImagePermute((2, 0, 1))]), conf=0.008, iou=0.6)  # fmt: skip
+    rng = np.random.RandomState(4)
+    images = [rng.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in ((90, 150), (200, 160), (128, 128))]
+    out = m.predict(images, batch_size=2)
+    assert len(out) == 3
+    kw = dict(rescale=(120, 120), keep_aspect=True, pad_shape=(128, 128), pad_value=114, center=True)
+    pres, metas = zip(*(O.preprocess_image(im, **kw) for im in images))
+    x = torch.from_numpy(np.stack(pres))
+    with torch.no_grad():
+        (boxes, scores), _ = m(x)
+    ref, _ = O.ppyoloe_postprocess(boxes, scores, 0.008, 0.6, 1024, 300)
+    assert sum(r.shape[0] for r in ref) > 0
+    for mine, r, meta in zip(out, ref, metas):
+        np.testing.assert_array_equal(mine.numpy(), O.postprocess_boxes(r, meta))
+
+
+def test_pose_predict_on_raw_images(golden, monkeypatch):
+    """YoloNASPose.predict() on raw images: BGR->RGB + aspect-preserving rescale + bottom-right padding fused on the way in, poses
+    and boxes mapped back to original pixels on the way out == the oracle chain around the same model."""
+    from super_gradients_b200.training import processing as P
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPose
+
+    cpu_backend.install(monkeypatch)
+    g = golden("tiny_yolo_nas_pose")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    _load(m, g["sd0"])
+    m.set_dataset_processing_params(image_processor=P.ComposeProcessing([P.ReverseImageChannels(), P.KeypointsLongestMaxSizeRescale((96, 96)), P.KeypointsBottomRightPadding((96, 96), pad_value=127),
+                                                                         P.StandardizeImage(255.0), P.ImagePermute((2, 0, 1))]))  # fmt: skip
+    rng = np.random.RandomState(8)
+    images = [rng.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in ((60, 120), (150, 100))]
+    cbkw = g["cb"]
+    out = m.predict(images, conf=cbkw["pose_confidence_threshold"], iou=cbkw["nms_iou_threshold"], pre_nms_max_predictions=100, post_nms_max_predictions=20)
+    kw = dict(rescale=(96, 96), keep_aspect=True, pad_shape=(96, 96), pad_value=127, center=False, reverse=True)
+    pres, metas = zip(*(O.preprocess_image(im, **kw) for im in images))
+    with torch.no_grad():
+        decoded, _ = m(torch.from_numpy(np.stack(pres)))
+    ref, _ = O.yolo_nas_pose_postprocess(*decoded, **cbkw)
+    assert sum(r[0].shape[0] for r in ref) > 0
+    for pr, (rposes, rscores, rboxes), meta in zip(out, ref, metas):
+        np.testing.assert_array_equal(pr.scores.numpy(), rscores)
+        np.testing.assert_array_equal(pr.bboxes_xyxy.numpy(), O.postprocess_boxes(rboxes, meta))
+        exp = rposes.copy()
+        exp[..., 0] = (exp[..., 0] - meta["pad_left"]) * np.float32(1 / meta["scale_w"])
+        exp[..., 1] = (exp[..., 1] - meta["pad_top"]) * np.float32(1 / meta["scale_h"])
+        np.testing.assert_array_equal(pr.poses.numpy(), exp)

@@ -129,3 +129,39 @@ def test_yolox_non_max_suppression_vs_reference_golden(golden, case):
         assert (mine is None) == (ref is None)
         if ref is not None:
             np.testing.assert_array_equal(mine.cpu().numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("chain", ["yolo_nas_default", "pose_default", "stretch_normalize"])
+def test_fused_preprocessing_kernel_matches_reference(golden, chain):
+    """Row (f)-N3 on the GPU: the fused pre-processing launch reproduces the reference's cv2 + numpy chain bit for bit (sha256 of
+    the bf16 model input), images of six sizes incl. 1080p; box / keypoint post-processing exact."""
+    from test_processing_host import _image, _product_chain, _sha
+
+    g = golden("processing")[chain]
+    cp = _product_chain(chain)
+    for case in g["cases"]:
+        batch, geos = cp.preprocess_batch([_image(case)], DEV)
+        torch.cuda.synchronize()
+        assert float(batch[:, 3:].abs().max()) == 0.0
+        t = batch[0, :3].contiguous().cpu()
+        torch.testing.assert_close(t[:, ::37, ::41].float(), case["pre_sample"].float(), rtol=0, atol=0)
+        assert _sha(t) == case["pre_sha256"], case["image_shape"]
+        torch.testing.assert_close(cp.postprocess_boxes(case["boxes"].to(DEV), geos[0]).cpu(), case["boxes_post"], rtol=0, atol=0)
+        if "poses" in case:
+            torch.testing.assert_close(cp.postprocess_keypoints(case["poses"].to(DEV), geos[0]).cpu(), case["poses_post"], rtol=0, atol=0)
+
+
+def test_predict_on_raw_images_gpu(golden):
+    import numpy as np
+
+    from super_gradients_b200.training import models
+
+    torch.manual_seed(0)
+    m = models.get("yolo_nas_s", num_classes=80).to(DEV)
+    rng = np.random.RandomState(1)
+    images = [rng.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in ((427, 640), (640, 480), (300, 500))]
+    out = m.predict(images, conf=0.01, iou=0.7)
+    assert len(out) == 3 and all(o.shape[1] == 6 for o in out)
+    for o, im in zip(out, images):
+        if o.shape[0]:
+            assert float(o[:, :4].min()) > -0.35 * max(im.shape[:2]) and float(o[:, [0, 2]].max()) < 1.35 * im.shape[1]
