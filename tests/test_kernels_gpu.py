@@ -76,16 +76,6 @@ CONV_CASES = [
     (3, 32, 13, 37, 32, 3, 1, 1),
     (2, 128, 19, 16, 128, 3, 1, 1),
     (40, 32, 64, 64, 32, 3, 1, 1),
-    # 1x1 stride 1 on the channel counts of the halo variants (served by the im2col kernel; by the 16 x 16-tile kernel in the
-    # -DSGB_HALO_1X1 experiment build): ragged edges, statistics with K == C, tiles > CTAs
-    (8, 32, 40, 40, 32, 1, 1, 0),
-    (4, 96, 40, 40, 96, 1, 1, 0),
-    (3, 48, 13, 37, 48, 1, 1, 0),
-    (2, 128, 19, 16, 64, 1, 1, 0),
-    (40, 32, 64, 64, 32, 1, 1, 0),
-    (4, 96, 40, 40, 32, 1, 1, 0),
-    (4, 64, 24, 24, 96, 1, 1, 0),
-    (2, 192, 20, 20, 64, 1, 1, 0),
 ]
 
 

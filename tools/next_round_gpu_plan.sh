@@ -9,7 +9,7 @@
 #   2d. bash tools/next_round_gpu_plan.sh variants -> default / _det / _pdl / _wide (-DSGB_UMMA_WIDE_STORE: 256-bit stores in the
 #       im2col kernels' fast epilogue) / _exp (all flags) benched back to back
 #       _1x1 (-DSGB_HALO_1X1: 1x1 stride-1 convolutions on the halo kernel's pipeline with a plain 16 x 16 tile; run
-#       `SGB200_LIB=.../libsgb200_1x1.so pytest tests/test_kernels_gpu.py -m gpu -k conv` first)
+#       `SGB200_LIB=.../libsgb200_1x1.so pytest tests/test_kernels_gpu.py tests/test_zz_pose_train_gpu.py -m gpu --runxfail -k conv` first)
 #   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
 #   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
 # NOTE: the experiment libraries (libsgb200_{det,pdl,wide,exp}.so) are listed in .gpurunignore so that routine calls stay small:
