@@ -238,27 +238,45 @@ def run_ours(args):
     for i in range(args.warmup):
         step.set_hyper_params(lr_at(i), 0.9997)
         step.run(dev_x[i % nbuf], dev_t[i % nbuf])
-    sampler = ClockSampler(dev.index or 0)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof_range = os.environ.get("SGB_PROFILER_RANGE") == "1"  # `ncu --profile-from-start off`: capture exactly the timed steps
-    if prof_range:
-        torch.cuda.profiler.start()
-    e0.record()
-    for i in range(args.steps):
-        step.set_hyper_params(lr_at(i), 0.9997)
-        loss, _ = step.run(dev_x[i % nbuf], dev_t[i % nbuf])
-    e1.record()
-    barrier()
-    if prof_range:
-        torch.cuda.profiler.stop()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+
+    def timed_region():
+        """K steps between barriers, CUDA events, max over ranks; nvidia-smi clocks / throttle reasons sampled meanwhile."""
+        sampler = ClockSampler(dev.index or 0)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if prof_range:
+            torch.cuda.profiler.start()
+        e0.record()
+        loss = None
+        for i in range(args.steps):
+            step.set_hyper_params(lr_at(i), 0.9997)
+            loss, _ = step.run(dev_x[i % nbuf], dev_t[i % nbuf])
+        e1.record()
+        barrier()
+        if prof_range:
+            torch.cuda.profiler.stop()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, clocks, loss
+
+    ms, clocks, loss = timed_region()
+    # a thermally / hardware-throttled region, or clocks pinned far below max without a reason, is measured once more (every
+    # rank follows rank 0's verdict: the region contains collectives)
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
+    pinned = bool(clocks.get("sm_mhz")) and bool(clocks.get("sm_max_mhz")) and clocks["sm_mhz"] < 0.5 * clocks["sm_max_mhz"] and not clocks.get("reasons")
+    redo = torch.tensor([1 if (bad or pinned) else 0], device=dev)
     if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+        dist.broadcast(redo, src=0)
+    if int(redo) == 1 and not prof_range:
+        first = clocks
+        ms, clocks, loss = timed_region()
+        clocks["remeasured_after"] = {"reasons": first.get("reasons"), "sm_mhz": first.get("sm_mhz")}
     final_loss = float(loss)
     value = world * batch * args.steps / (ms / 1e3)
 

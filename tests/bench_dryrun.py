@@ -123,5 +123,25 @@ mp.setattr(torch.cuda, "synchronize", lambda *a: None)
 mp.setattr(torch.cuda.profiler, "start", lambda: None)
 mp.setattr(torch.cuda.profiler, "stop", lambda: None)
 
+if os.environ.get("SGB_DRYRUN_THROTTLE") == "1":
+
+    class ThrottledOnce:
+        """Reports a hardware slowdown for the first timed region on rank 0 only (the other ranks see clean clocks)."""
+
+        calls = 0
+
+        def __init__(self, index):
+            pass
+
+        def start(self):
+            pass
+
+        def stop(self):
+            ThrottledOnce.calls += 1
+            hot = ThrottledOnce.calls == 1 and os.environ.get("RANK", "0") == "0"
+            return {"sm_mhz": 1500.0, "sm_max_mhz": 1965.0, "reasons": ["hw_slowdown"] if hot else [], "samples": 3}
+
+    mp.setattr(bench, "ClockSampler", ThrottledOnce)
+
 bench.main()
 print(f"rank {os.environ.get('RANK', '0')} finished", file=sys.stderr, flush=True)

@@ -12,10 +12,10 @@ KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
         "clocks", "roofline", "cpu_baseline"}  # fmt: skip
 
 
-def _run(nproc, port, *flags, timeout=900):
+def _run(nproc, port, *flags, timeout=900, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "bench_dryrun.py"), ROOT, "--gpus", str(nproc), "--steps", "2", "--warmup", "1", "--batch", "2", "--skip-cpu-baseline", *flags]  # fmt: skip
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, OMP_NUM_THREADS="4"))
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, OMP_NUM_THREADS="4", **(env or {})))
 
 
 @pytest.mark.parametrize("flags", [(), ("--no-graph",)], ids=["graph", "eager"])
@@ -38,3 +38,13 @@ def test_bench_single_rank_control_flow():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][0])
     assert KEYS <= set(line) and line["n_gpus"] == 1 and line["config"]["cuda_graph"] is True and line["value"] > 0
+
+
+def test_bench_remeasures_a_throttled_region_on_every_rank():
+    """Rank 0 alone sees hw_slowdown in the first timed region: its verdict is broadcast, BOTH ranks run the region again (it contains
+    the gradient all-reduce), and the line records why."""
+    out = _run(2, 29544, "--no-graph", env={"SGB_DRYRUN_THROTTLE": "1"})
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stderr.count("finished") == 2
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][0])
+    assert line["clocks"]["reasons"] == [] and line["clocks"]["remeasured_after"]["reasons"] == ["hw_slowdown"]
