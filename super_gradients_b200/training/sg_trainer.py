@@ -360,7 +360,7 @@ class Trainer:
                 if tp["cuda_graph"] and self.step.graph is None and torch.is_tensor(targets) and targets.is_cuda:
                     self.step.capture(inputs, targets)
                 loss, _items = self.step.run(inputs, targets, do_step)
-                running = loss if running is None else running + loss
+                running = loss.clone() if running is None else running + loss  # clone: with a captured graph `loss` is the static output buffer
                 nb += 1
                 self.history["lr"].append(lr)
             train_loss = float(running / max(nb, 1)) if running is not None else float("nan")
