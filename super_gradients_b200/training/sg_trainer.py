@@ -96,6 +96,8 @@ class TrainStep:
     """One optimisation step over a FlatState: zero grads -> forward -> loss -> backward -> (all-reduce) -> optimizer
     (-> EMA).  The object owns every per-step device buffer, so the step can be captured in a CUDA graph."""
 
+    STAGING_SLOTS = 8  # pinned host slots of the per-step hyper-parameters (how far the host may run ahead of the device)
+
     def __init__(self, model: nn.Module, criterion: Callable, optimizer: str, optimizer_params: Mapping[str, Any], zero_wd_on_bias_and_bn: bool, ema: bool = False, batch_accumulate: int = 1):
         self.model, self.criterion = model, criterion
         self.flat = FlatState(model, zero_wd_on_bias_and_bn)
@@ -106,20 +108,21 @@ class TrainStep:
         f = self.flat
         if optimizer == "SGD":
             self.state = [torch.zeros_like(f.params)]
-            self.hp_host = torch.zeros((2, 5), dtype=torch.float32).pin_memory()
+            self.hp_host = torch.zeros((self.STAGING_SLOTS, 2, 5), dtype=torch.float32).pin_memory()
         elif optimizer in ("AdamW", "Adam"):
             if optimizer == "Adam":
                 raise NotImplementedError("Adam (L2-coupled) is not implemented; use AdamW or SGD")
             self.state = [torch.zeros_like(f.params), torch.zeros_like(f.params)]
-            self.hp_host = torch.zeros((2, 8), dtype=torch.float32).pin_memory()
+            self.hp_host = torch.zeros((self.STAGING_SLOTS, 2, 8), dtype=torch.float32).pin_memory()
         else:
             raise NotImplementedError(f"optimizer {optimizer} has no fused kernel (SGD, AdamW are implemented)")
-        self.hp = torch.zeros_like(self.hp_host, device=self.device)
+        self.hp = torch.zeros_like(self.hp_host[0], device=self.device)
+        self._slot, self._slot_events = 0, [None] * self.STAGING_SLOTS
         self.ema_on = ema
         if ema:
             self.ema_params = f.params.clone()
             self.ema_buffers = f.buffers.clone()
-            self.ema_decay_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.ema_decay_host = torch.zeros((self.STAGING_SLOTS, 1), dtype=torch.float32).pin_memory()
             self.ema_decay = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.world = torch.distributed.get_world_size() if is_distributed() else 1
         self.accumulate = batch_accumulate
@@ -139,21 +142,32 @@ class TrainStep:
         t = self.opt_steps + 1
         gs = 1.0 / (self.world * self.accumulate)
         wd = float(self.op.get("weight_decay", 0.0))
+        # The host may run many steps ahead of the device (graph replays are enqueued without a sync): every call stages its
+        # values in its own pinned slot, and a slot is only rewritten after the copy that read it has executed.
+        k = self._slot
+        self._slot = (k + 1) % self.STAGING_SLOTS
+        if self._slot_events[k] is not None:
+            self._slot_events[k].synchronize()
+        hp_host = self.hp_host[k]
         if self.opt_name == "SGD":
             mu, nes = float(self.op.get("momentum", 0.0)), float(bool(self.op.get("nesterov", False)))
-            self.hp_host[0] = torch.tensor([lr, mu, wd, gs, nes])
-            self.hp_host[1] = torch.tensor([lr, mu, 0.0, gs, nes])
+            hp_host[0] = torch.tensor([lr, mu, wd, gs, nes])
+            hp_host[1] = torch.tensor([lr, mu, 0.0, gs, nes])
         else:
             b1, b2 = self.op.get("betas", (0.9, 0.999))
             eps = float(self.op.get("eps", 1e-8))
             row = [lr, b1, b2, eps, wd, 1 - b1**t, 1 - b2**t, gs]
-            self.hp_host[0] = torch.tensor(row)
+            hp_host[0] = torch.tensor(row)
             row[4] = 0.0
-            self.hp_host[1] = torch.tensor(row)
-        self.hp.copy_(self.hp_host, non_blocking=True)
+            hp_host[1] = torch.tensor(row)
+        self.hp.copy_(hp_host, non_blocking=True)
         if self.ema_on and ema_decay_value is not None:
-            self.ema_decay_host[0] = ema_decay_value
-            self.ema_decay.copy_(self.ema_decay_host, non_blocking=True)
+            self.ema_decay_host[k, 0] = ema_decay_value
+            self.ema_decay.copy_(self.ema_decay_host[k], non_blocking=True)
+        if self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            self._slot_events[k] = ev
 
     # -------------------------------------------------------------------------------------------- device-side step
     def forward_backward(self, inputs, targets):
