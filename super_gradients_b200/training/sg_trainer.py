@@ -52,6 +52,10 @@ DEFAULT_TRAINING_PARAMS = {
     "silent_mode": True,
     "sync_bn": False,
     "phase_callbacks": [],
+    "resume": False,  # continue from <ckpt_root_dir>/<experiment_name>/<ckpt_name> (reference: sg_trainer.py:1877-1935)
+    "resume_path": None,  # ... or from an explicit checkpoint file
+    "ckpt_name": "ckpt_latest.pth",
+    "resume_strict_load": True,
 }
 
 # defaults merged under user optimizer_params (reference: training/params.py:84-90)
@@ -338,6 +342,11 @@ class Trainer:
         tp = {**DEFAULT_TRAINING_PARAMS, **dict(training_params or {})}
         if tp["sync_bn"]:
             raise NotImplementedError("sync_bn needs per-layer collectives; the data-parallel path uses ONE gradient all-reduce (SURVEY.md D4)")
+        ckpt = None
+        if tp["resume"] or tp["resume_path"]:
+            path = tp["resume_path"] or os.path.join(self.checkpoints_dir_path, tp["ckpt_name"])
+            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+            model.load_state_dict(ckpt["net"], strict=bool(tp["resume_strict_load"]))
         self.net = model.to(self.device)
         torch.manual_seed(int(tp["seed"]) + (torch.distributed.get_rank() if is_distributed() else 0))
         criterion = tp["loss"]
@@ -354,8 +363,13 @@ class Trainer:
         ema_p = {**DEFAULT_TRAINING_PARAMS["ema_params"], **dict(tp["ema_params"] or {})}
         acc = int(tp["batch_accumulate"])
         best = None
+        start_epoch = 0
+        if ckpt is not None:
+            start_epoch = int(ckpt.get("epoch", -1)) + 1
+            best = ckpt.get("acc")
+            self._restore_training_state(ckpt)
         t0 = time.time()
-        for epoch in range(int(tp["max_epochs"])):
+        for epoch in range(start_epoch, int(tp["max_epochs"])):
             self.net.train()
             if hasattr(getattr(train_loader, "sampler", None), "set_epoch"):
                 train_loader.sampler.set_epoch(epoch)
@@ -421,6 +435,28 @@ class Trainer:
             self.step.swap_ema()
             return sd
         return {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+
+    def _restore_training_state(self, ckpt: Mapping[str, Any]):
+        """Optimizer moments, step counter and EMA weights of a checkpoint written by _save_checkpoint (the network weights were
+        loaded into the model before the flat buffers were built)."""
+        st = self.step
+        osd = ckpt.get("optimizer_state_dict") or {}
+        if osd:
+            if osd.get("name") != st.opt_name or list(osd.get("flat_order", [])) != [n for n, _ in st.flat.order]:
+                raise ValueError("the checkpoint's optimizer state does not belong to this model / optimizer")
+            for mine, saved in zip(st.state, osd["state"]):
+                mine.copy_(saved.to(mine.device))
+            st.opt_steps = int(osd.get("opt_steps", 0))
+        if st.ema_on and ckpt.get("ema_net") is not None:
+            ema = ckpt["ema_net"]
+            with torch.no_grad():
+                for name, (off, k) in st.flat.offsets.items():
+                    st.ema_params[off : off + k].copy_(ema[name].reshape(-1).to(st.ema_params.device))
+                off = 0
+                for name in st.flat.buffer_names:
+                    k = ema[name].numel()
+                    st.ema_buffers[off : off + k].copy_(ema[name].reshape(-1).to(st.ema_buffers.device))
+                    off += k
 
     def _save_checkpoint(self, epoch: int, metrics: dict, tp, is_best: bool):
         """Same dictionary keys as the reference (sg_trainer.py:649-739): net, acc, epoch, metrics, optimizer_state_dict,

@@ -542,3 +542,57 @@ def test_pose_predict_on_raw_images(golden, monkeypatch):
         exp[..., 0] = (exp[..., 0] - meta["pad_left"]) * np.float32(1 / meta["scale_w"])
         exp[..., 1] = (exp[..., 1] - meta["pad_top"]) * np.float32(1 / meta["scale_h"])
         np.testing.assert_array_equal(pr.poses.numpy(), exp)
+
+
+def test_trainer_resume_continues_bit_exactly(golden, monkeypatch, tmp_path):
+    """training_params.resume: network weights, optimizer moments, step counter (LR / EMA schedules) and EMA weights come back from
+    ckpt_latest.pth -- one epoch + a resumed second epoch ends exactly where two uninterrupted epochs end."""
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.losses import PPYoloELoss
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.sg_trainer import Trainer
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("tiny_yolo_nas")
+
+    def build():
+        ap = copy.deepcopy(g["arch"])
+        m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+        m.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+        return m
+
+    loader = [(g["x"] * (1 + 0.1 * i), g["targets"]) for i in range(2)]
+    tp = lambda **kw: dict(max_epochs=2, initial_lr=2e-3, lr_mode="cosine", cosine_final_lr_ratio=0.1, lr_warmup_steps=1, optimizer="AdamW", optimizer_params={"weight_decay": 1e-5},  # noqa: E731
+                           zero_weight_decay_on_bias_and_bn=True, ema=True, ema_params={"decay": 0.9, "decay_type": "threshold"}, loss=PPYoloELoss(num_classes=4, use_static_assigner=False), **kw)  # fmt: skip
+    straight = Trainer("straight", ckpt_root_dir=str(tmp_path))
+    m_ref = build()
+    straight.train(m_ref, tp(), loader)
+    ck_dir = tmp_path / "resumed"
+    # epoch 0 of the 2-epoch recipe, interrupted by an exception raised from the loader at the start of epoch 1
+    class Interrupt(Exception):
+        pass
+
+    class OneEpochLoader(list):
+        passes = 0
+
+        def __iter__(self):
+            OneEpochLoader.passes += 1
+            if OneEpochLoader.passes > 1:
+                raise Interrupt()
+            return super().__iter__()
+
+    broken = Trainer("resumed", ckpt_root_dir=str(tmp_path))
+    with pytest.raises(Interrupt):
+        broken.train(build(), tp(), OneEpochLoader(loader))
+    assert (ck_dir / "ckpt_latest.pth").exists()
+    resumed = Trainer("resumed", ckpt_root_dir=str(tmp_path))
+    m_res = build()
+    hist = resumed.train(m_res, tp(resume=True), loader)
+    assert len(hist["train_loss"]) == 1 and resumed.step.opt_steps == straight.step.opt_steps == 4
+    assert torch.equal(resumed.step.flat.params, straight.step.flat.params)
+    assert torch.equal(resumed.step.ema_params, straight.step.ema_params) and torch.equal(resumed.step.flat.buffers, straight.step.flat.buffers)
+    for a, b in zip(resumed.step.state, straight.step.state):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError, match="optimizer"):
+        Trainer("resumed", ckpt_root_dir=str(tmp_path)).train(build(), {**tp(resume=True), "optimizer": "SGD", "optimizer_params": {}}, loader)
