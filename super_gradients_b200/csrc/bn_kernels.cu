@@ -115,7 +115,7 @@ int launch_chan(const Op& op, int64_t M, int C, cudaStream_t st, const char* wha
   const int cvb = cvs < TPB ? cvs : TPB;
   const size_t smem = ((size_t)Op::NCOEF * C + (size_t)(Op::NACC * 8 + 1) * TPB) * sizeof(float);
   int64_t want = (M + 255) / 256;
-  const int grid = (int)(want < 1 ? 1 : (want > 148 * 6 ? 148 * 6 : want));
+  const int grid = (int)(want < 1 ? 1 : (want > sgb_chan_grid_cap() ? sgb_chan_grid_cap() : want));
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     cudaFuncSetAttribute(chan_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "sgb200.h"
 
@@ -76,6 +77,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// CTA cap of the streaming per-channel kernels: 148 SMs x SGB_CHAN_CTAS_PER_SM (default 6; the environment variable is a tuning hook)
+static inline int sgb_chan_grid_cap() {
+  static int cap = 0;
+  if (cap == 0) {
+    const char* e = getenv("SGB_CHAN_CTAS_PER_SM");
+    const int per_sm = (e && atoi(e) > 0) ? atoi(e) : 6;
+    cap = 148 * per_sm;
+  }
+  return cap;
+}
 
 // Programmatic dependent launch (experiment, -DSGB_PDL; the default build compiles these to nothing and launches with <<<>>>).
 // A kernel first tells the runtime that its dependents may be scheduled (SGB_GRID_DEP_LAUNCH), does whatever does not touch

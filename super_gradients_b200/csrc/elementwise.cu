@@ -227,7 +227,7 @@ int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaS
   int cvb = cvs < TPB ? cvs : TPB;
   size_t smem = (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
   int64_t want = (M + 255) / 256;  // >= 256 pixels per CTA
-  int grid = (int)(want < 1 ? 1 : (want > 148 * 6 ? 148 * 6 : want));
+  int grid = (int)(want < 1 ? 1 : (want > sgb_chan_grid_cap() ? sgb_chan_grid_cap() : want));
   SGB_LAUNCH(chan_reduce_kernel<F>, grid, TPB, smem, st, f, M, C, out, out_stride);
   SGB_LAUNCH_CHECK("chan_reduce_kernel");
   return SGB_OK;
