@@ -107,8 +107,13 @@ static inline void sgb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static int enabled = -1;  // SGB_PDL=0 in the environment launches the same build with plain stream serialisation (A/B in one library)
+  if (enabled < 0) {
+    const char* e = getenv("SGB_PDL");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = enabled ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // a failure surfaces through cudaGetLastError() at the call site
 }
 #define SGB_LAUNCH(kernel, grid, block, smem, st, ...) sgb_launch_pdl(kernel, dim3(grid), dim3(block), smem, st, __VA_ARGS__)
