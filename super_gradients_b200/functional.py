@@ -64,11 +64,12 @@ def set_step_context(ctx: Optional["StepContext"]):
 class WeightCache:
     """bf16 KRSC / CRSK copies of an fp32 OIHW conv weight, refreshed when the parameter changes."""
 
-    def __init__(self):
+    def __init__(self, batched: bool = True):
         self.key = None
         self.krsc = None
         self.crsk = None
         self.args = None  # (w, scale, add_identity, extra_key, c_pad) of the last prepare
+        self.batched = batched  # False: never part of a TrainStep's batched refresh (its source is staged during the forward)
 
     @staticmethod
     def _key(w, scale, add_identity, extra_key, c_pad):
@@ -81,7 +82,7 @@ class WeightCache:
             self.krsc, self.crsk = K.weight_prepare(w, c_pad=c_pad, scale=scale, add_identity=add_identity, out=(self.krsc, self.crsk))
             self.key = key
             self.args = (w, scale, add_identity, extra_key, c_pad)
-        if _CTX[0] is not None:
+        if _CTX[0] is not None and self.batched:
             _CTX[0].caches.setdefault(id(self), self)
         return self.krsc, self.crsk
 
@@ -129,6 +130,43 @@ def flush_wgrads(ctx: StepContext, device) -> int:
         K.wgrad_to_oihw(dw, c, out=g, accumulate=True)
     pend.clear()
     return n + len(rest)
+
+
+# Experiment (off unless SGB_QAREP_FOLD=1): a stride-1 QARepVGG block runs its 1x1 branch as the centre tap of ONE 3x3 convolution
+# with 2K output channels (rows [0, K) = the 3x3 filters, rows [K, 2K) = alpha * K1 + I embedded at the centre), so y3 and u come
+# out of one halo-kernel launch that reads x once, dgrad consumes [dy3 | du] in one launch (no accumulate pass) and wgrad produces
+# both gradients in one launch (for K <= 64 inside the M = 128 padding the 3x3 weight gradient already pays for).  Only verified
+# kernels are involved; tools/next_round_gpu_plan.sh benches it.
+QAREP_FOLD = [__import__("os").environ.get("SGB_QAREP_FOLD") == "1"]
+_FOLD_CHANNELS = (32, 48, 64, 96, 128, 192)  # channel counts the halo-tile kernels are instantiated for
+
+
+def qarep_fold_supported(cin: int, x_channels: int, kout: int, stride: int) -> bool:
+    return stride == 1 and cin == x_channels and cin in _FOLD_CHANNELS and 2 * kout in _FOLD_CHANNELS
+
+
+class FoldedWeightCache:
+    """fp32 OIHW [2K, C, 3, 3] staging of (K3 ; centre(alpha * K1 + I)) + its bf16 KRSC / CRSK copies, refreshed when a source changes."""
+
+    def __init__(self):
+        self.key = None
+        self.stage = None
+        self.inner = WeightCache(batched=False)
+
+    def get(self, w3, w1, alpha, add_identity, c_pad):
+        key = (WeightCache._key(w3, None, False, None, c_pad), WeightCache._key(w1, alpha, add_identity, None, c_pad))
+        if key != self.key:
+            kout, cin = w3.shape[0], w3.shape[1]
+            with torch.no_grad():
+                if self.stage is None or tuple(self.stage.shape) != (2 * kout, cin, 3, 3) or self.stage.device != w3.device:
+                    self.stage = torch.zeros((2 * kout, cin, 3, 3), dtype=torch.float32, device=w3.device)
+                self.stage[:kout].copy_(w3.detach())
+                centre = w1.detach()[:, :, 0, 0] * alpha.detach() if alpha is not None else w1.detach()[:, :, 0, 0].clone()
+                if add_identity:
+                    centre.diagonal().add_(1.0)
+                self.stage[kout:, :, 1, 1].copy_(centre)
+            self.key = key
+        return self.inner.get(self.stage, c_pad=c_pad, extra_key=key)
 
 
 def _mg(p):
@@ -283,10 +321,16 @@ class _QARepVGG(torch.autograd.Function):
     def forward(ctx, x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
         x = K.as_nhwc(x)
         kout = w3.shape[0]
-        k3, c3 = cfg.cache3.get(w3, c_pad=x.shape[1])
-        k1, c1 = cfg.cache1.get(w1, scale=alpha, add_identity=cfg.residual, c_pad=x.shape[1])
-        y3 = K.conv_fprop(x, k3, kout, 3, 3, cfg.stride, 1)
-        u = K.conv_fprop(x, k1, kout, 1, 1, cfg.stride, 0)
+        fold = QAREP_FOLD[0] and getattr(cfg, "cache_fold", None) is not None and qarep_fold_supported(w3.shape[1], x.shape[1], kout, cfg.stride)
+        if fold:
+            kf, cf = cfg.cache_fold.get(w3, w1, alpha, cfg.residual, x.shape[1])
+            ycat = K.conv_fprop(x, kf, 2 * kout, 3, 3, 1, 1)
+            y3, u, c3, c1 = ycat[:, :kout], ycat[:, kout:], cf, None
+        else:
+            k3, c3 = cfg.cache3.get(w3, c_pad=x.shape[1])
+            k1, c1 = cfg.cache1.get(w1, scale=alpha, add_identity=cfg.residual, c_pad=x.shape[1])
+            y3 = K.conv_fprop(x, k3, kout, 3, 3, cfg.stride, 1)
+            u = K.conv_fprop(x, k1, kout, 1, 1, cfg.stride, 0)
         ab = None
         if bias1 is not None:
             ab = bias1 * alpha if alpha is not None else bias1
@@ -296,7 +340,7 @@ class _QARepVGG(torch.autograd.Function):
                 if nbt is not None:
                     nbt += 1
         ctx.save_for_backward(x, y3, u, out, coef, g3, gp if gp is not None else g3, w1, bias1 if bias1 is not None else g3, alpha if alpha is not None else g3)
-        ctx.cfg, ctx.c3, ctx.c1 = cfg, c3, c1
+        ctx.cfg, ctx.c3, ctx.c1, ctx.fold = cfg, c3, c1, fold
         ctx.flags = (bias1 is not None, alpha is not None, gp is not None, w3.shape[1])
         ctx.slots = (_mg(w3), _mg(g3), _mg(b3), _mg(w1), _mg(bias1), _mg(alpha), _mg(gp), _mg(bp))
         return out
@@ -308,17 +352,38 @@ class _QARepVGG(torch.autograd.Function):
         has_bias, has_alpha, has_post, cin = ctx.flags
         sw3, sg3, sb3, sw1, sbias, salpha, sgp, sbp = ctx.slots
         direct_bias = sbias if not has_alpha else None  # d(alpha*b1) == d(b1) when alpha is the constant 1
+        dcat = None
+        if ctx.fold:  # [dy3 | du] in one buffer: one dgrad and one wgrad launch consume it
+            n, kout, h, w = y3.shape
+            dcat = K.empty_nhwc(n, 2 * kout, h, w, y3.device)
         dy3, du, dg3, db3, dab, dgp, dbp = K.qarep_bwd(
-            dout, out, y3, u, coef, g3, gp if has_post else None, cfg.eps, cfg.eps, cfg.act, cfg.use_post_bn, acc=(sg3, sb3, direct_bias, sgp, sbp)
-        )
+            dout, out, y3, u, coef, g3, gp if has_post else None, cfg.eps, cfg.eps, cfg.act, cfg.use_post_bn, acc=(sg3, sb3, direct_bias, sgp, sbp),
+            out_grads=(dcat[:, :kout], dcat[:, kout:]) if dcat is not None else None,
+        )  # fmt: skip
         dx = None
-        if ctx.needs_input_grad[0]:
-            dx = K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1)
-            K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=dx, accumulate=True)
-        dw3 = _wgrad(x, dy3, 3, 3, cfg.stride, 1, cin, sw3)
+        dw1f = None
+        if dcat is not None:
+            if ctx.needs_input_grad[0]:
+                dx = K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1)
+            dwf = K.conv_wgrad(x, dcat, 3, 3, 1, 1)  # fp32 [2K, 3, 3, C]: rows [0, K) = dW3, rows [K, 2K) centre tap = d(alpha * K1 + I)
+            if sw3 is not None and _CTX[0] is not None:
+                _CTX[0].pending.append((dwf[:kout], cin, sw3))
+                dw3 = None
+            elif sw3 is not None:
+                K.wgrad_to_oihw(dwf[:kout], cin, out=sw3, accumulate=True)
+                dw3 = None
+            else:
+                dw3 = K.wgrad_to_oihw(dwf[:kout], cin)
+            dw1f = dwf[kout:, 1, 1, :cin].reshape(kout, cin, 1, 1).contiguous()
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1)
+                K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=dx, accumulate=True)
+            dw3 = _wgrad(x, dy3, 3, 3, cfg.stride, 1, cin, sw3)
         dalpha = None
         if has_alpha:
-            dw1f = K.wgrad_to_oihw(K.conv_wgrad(x, du, 1, 1, cfg.stride, 0), cin)  # grad of the folded alpha*K1 + I
+            if dw1f is None:
+                dw1f = K.wgrad_to_oihw(K.conv_wgrad(x, du, 1, 1, cfg.stride, 0), cin)  # grad of the folded alpha*K1 + I
             dalpha = (dw1f * w1).sum().reshape(1)
             if has_bias:
                 dalpha = dalpha + (dab * bias1).sum().reshape(1)
@@ -326,7 +391,7 @@ class _QARepVGG(torch.autograd.Function):
             dbias1 = _deliver(sbias, dab * alpha) if has_bias else None
             dalpha = _deliver(salpha, dalpha)
         else:
-            dw1 = _wgrad(x, du, 1, 1, cfg.stride, 0, cin, sw1)
+            dw1 = _deliver(sw1, dw1f) if dw1f is not None else _wgrad(x, du, 1, 1, cfg.stride, 0, cin, sw1)
             dbias1 = (None if sbias is not None else dab) if has_bias else None
         ret = lambda slot, v: None if slot is not None else v  # noqa: E731
         return dx, dw3, ret(sg3, dg3), ret(sb3, db3), dw1, dbias1, dalpha, (ret(sgp, dgp) if has_post else None), (ret(sbp, dbp) if has_post else None), None

@@ -447,9 +447,11 @@ def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp,
     return out, coef
 
 
-def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None):
+def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None, out_grads=None):
     """Returns dy3, du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p.  `acc` optionally supplies existing fp32 tensors
-    (dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p) to accumulate into (None entries are allocated)."""
+    (dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p) to accumulate into (None entries are allocated).  The kernel writes dy3 / du
+    with the channel pitch of y3 / u: `out_grads` = (dy3, du) buffers of those pitches (e.g. channel slices of one tensor when
+    y3 / u are slices); by default dense tensors are allocated, which requires dense y3 / u."""
     n, c, h, w = y3.shape
     dout = as_nhwc(dout)
     if nhwc_pitch(dout) != nhwc_pitch(out):
@@ -457,7 +459,12 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
     d = qarep_desc(y3, u, out, eps3, eps_post, 0.0, act, use_post_bn)
     sums = zeros((3, c), torch.float64, y3.device)
     _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
-    dy3, du = torch.empty_like(y3), torch.empty_like(u)
+    if out_grads is not None:
+        dy3, du = out_grads
+    else:
+        dy3, du = empty_nhwc(n, c, h, w, y3.device), empty_nhwc(n, c, h, w, y3.device)
+    if nhwc_pitch(dy3) != nhwc_pitch(y3) or nhwc_pitch(du) != nhwc_pitch(u):
+        raise L.SgbError("qarep_bwd: dy3 / du must have the channel pitch of y3 / u")
     z = lambda: zeros((c,), torch.float32, y3.device)  # noqa: E731
     acc = acc or (None,) * 5
     dg3, db3, dab, dgp, dbp = [a if a is not None else z() for a in acc]

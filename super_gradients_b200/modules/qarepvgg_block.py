@@ -77,6 +77,7 @@ class QARepVGGBlock(nn.Module):
         self.partially_fused = False
         self.fully_fused = False
         self._cache3, self._cache1, self._cache_eq = SF.WeightCache(), SF.WeightCache(), SF.WeightCache()
+        self._cache_fold = SF.FoldedWeightCache()
         self._eq = None
         if not build_residual_branches:
             self.fuse_block_residual_branches()
@@ -93,7 +94,7 @@ class QARepVGGBlock(nn.Module):
             pbn = self.post_bn if self.use_post_bn else None
             cfg = SimpleNamespace(
                 stride=self.stride, residual=self.identity is not None, act=self._act_code, eps=bn3.eps, momentum=0.1 if bn3.momentum is None else bn3.momentum,
-                use_post_bn=self.use_post_bn, cache3=self._cache3, cache1=self._cache1, rm3=bn3.running_mean, rv3=bn3.running_var,
+                use_post_bn=self.use_post_bn, cache3=self._cache3, cache1=self._cache1, cache_fold=self._cache_fold, rm3=bn3.running_mean, rv3=bn3.running_var,
                 rmp=pbn.running_mean if pbn is not None else None, rvp=pbn.running_var if pbn is not None else None,
                 nbt=(bn3.num_batches_tracked, pbn.num_batches_tracked if pbn is not None else None),
             )  # fmt: skip

@@ -353,7 +353,7 @@ def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp,
     return out, torch.zeros((9, c), dtype=torch.float32)  # the coefficient table is private to the CUDA kernels
 
 
-def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None):
+def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None, out_grads=None):
     n, c, h, w = y3.shape
     dpre = _mask(dout, out, act)
     leaf = lambda t: t.detach().float().clone().requires_grad_(True)  # noqa: E731
@@ -367,7 +367,7 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
         grads = torch.autograd.grad(pre, wrt, dpre, allow_unused=True)
     gy3, gu, gg3, gb3, gab = grads[:5]
     ggp, gbp = (grads[5], grads[6]) if use_post_bn else (None, None)
-    dy3, du = torch.empty_like(y3), torch.empty_like(u)
+    dy3, du = out_grads if out_grads is not None else (K.empty_nhwc(n, c, h, w, y3.device), K.empty_nhwc(n, c, h, w, y3.device))
     dy3.copy_(_bf16(gy3))
     du.copy_(_bf16(gu))
     acc = acc or (None,) * 5

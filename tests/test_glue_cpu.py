@@ -596,3 +596,45 @@ def test_trainer_resume_continues_bit_exactly(golden, monkeypatch, tmp_path):
         assert torch.equal(a, b)
     with pytest.raises(ValueError, match="optimizer"):
         Trainer("resumed", ckpt_root_dir=str(tmp_path)).train(build(), {**tp(resume=True), "optimizer": "SGD", "optimizer_params": {}}, loader)
+
+
+def test_folded_qarepvgg_path_is_the_same_block(golden, monkeypatch):
+    """SGB_QAREP_FOLD experiment (the 1x1 branch as the centre tap of one 2K-channel 3x3 convolution): forward output, input
+    gradient and every parameter gradient of a QARepVGG block agree with the two-convolution path, for a block with and without
+    the identity / alpha, and a whole TrainStep of the tiny model stays on the unfolded trajectory."""
+    from super_gradients_b200 import functional as SF
+    from super_gradients_b200.modules import QARepVGGBlock
+
+    cpu_backend.install_training(monkeypatch)
+
+    def run(fold, cin, cout, use_alpha, seed=0):
+        monkeypatch.setattr(SF, "QAREP_FOLD", [fold])
+        torch.manual_seed(seed)
+        blk = QARepVGGBlock(cin, cout, stride=1, use_alpha=use_alpha, use_residual_connection=cin == cout).train()
+        with torch.no_grad():
+            for p in blk.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        x = torch.randn(2, cin, 12, 12).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = blk(x)
+        (y.float() * torch.linspace(-1, 1, y.numel()).reshape(y.shape)).sum().backward()
+        return y.detach().float(), x.grad.float(), {k: p.grad.clone() for k, p in blk.named_parameters() if p.grad is not None}
+
+    for cin, cout, use_alpha in ((32, 32, True), (48, 48, False), (64, 32, True)):
+        y0, dx0, g0 = run(False, cin, cout, use_alpha)
+        y1, dx1, g1 = run(True, cin, cout, use_alpha)
+        assert l2rel(y1, y0) < 4e-3 and l2rel(dx1, dx0) < 8e-3, (cin, cout, l2rel(y1, y0), l2rel(dx1, dx0))  # bf16 rounding of two GEMM orders
+        assert set(g0) == set(g1)
+        for k in g0:
+            assert l2rel(g1[k], g0[k]) < 2e-2, (cin, cout, k, l2rel(g1[k], g0[k]))
+    # a channel count without halo-kernel variants keeps the two-convolution path even with the switch on
+    monkeypatch.setattr(SF, "QAREP_FOLD", [True])
+    assert not SF.qarep_fold_supported(40, 40, 40, 1) and not SF.qarep_fold_supported(32, 32, 32, 2) and SF.qarep_fold_supported(96, 96, 96, 1)
+    g = golden("tiny_yolo_nas")
+    x, t = g["x"], _padded_targets(g)
+    res = {}
+    for fold in (False, True):
+        monkeypatch.setattr(SF, "QAREP_FOLD", [fold])
+        _, st = _train_step(g, monkeypatch)
+        res[fold] = _run(st, x, t, 2)
+    assert abs(res[True][0][0] - res[False][0][0]) < 2e-2 * abs(res[False][0][0])
+    assert l2rel(res[True][1][3], res[False][1][3]) < 1e-3  # parameters after two steps

@@ -179,3 +179,31 @@ def test_conv_1x1_fprop_dgrad_wgrad(case):
     from test_kernels_gpu import test_conv_fprop_dgrad_wgrad as conv_case
 
     conv_case(case)
+
+
+@pytest.mark.parametrize("cin,cout,use_alpha", [(32, 32, True), (48, 48, False), (64, 32, True), (96, 96, True)])
+def test_folded_qarepvgg_block_matches_the_two_convolution_path(monkeypatch, cin, cout, use_alpha):
+    """SGB_QAREP_FOLD experiment on the real kernels: one 2K-channel 3x3 convolution (+ one dgrad, one wgrad) instead of the 3x3 and
+    1x1 pairs -- same block output (the y3 half bit-identical), input gradient and parameter gradients."""
+    from super_gradients_b200 import functional as SF
+    from super_gradients_b200.modules import QARepVGGBlock
+
+    def run(fold):
+        monkeypatch.setattr(SF, "QAREP_FOLD", [fold])
+        torch.manual_seed(0)
+        blk = QARepVGGBlock(cin, cout, stride=1, use_alpha=use_alpha, use_residual_connection=cin == cout).to(DEV).train()
+        with torch.no_grad():
+            for p in blk.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        x = torch.randn(4, cin, 40, 40, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = blk(x)
+        (y.float() * torch.linspace(-1, 1, y.numel(), device=DEV).reshape(y.shape)).sum().backward()
+        torch.cuda.synchronize()
+        return y.detach().float().cpu(), x.grad.float().cpu(), {k: p.grad.clone().cpu() for k, p in blk.named_parameters() if p.grad is not None}
+
+    y0, dx0, g0 = run(False)
+    y1, dx1, g1 = run(True)
+    assert l2rel(y1, y0) < 4e-3 and l2rel(dx1, dx0) < 8e-3, (l2rel(y1, y0), l2rel(dx1, dx0))
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert l2rel(g1[k], g0[k]) < 2e-2, (k, l2rel(g1[k], g0[k]))
