@@ -50,12 +50,17 @@ def main(path, skip):
                 kwargs["golden"] = golden
             if "tmp_path" in sig:
                 kwargs["tmp_path"] = pathlib.Path(tempfile.mkdtemp())
+            local_mp = MonkeyPatch()
+            if "monkeypatch" in sig:
+                kwargs["monkeypatch"] = local_mp
             try:
                 fn(**kwargs)
                 ok += 1
             except Exception as e:  # noqa: BLE001
                 bad += 1
                 print("FAIL", name, combo, type(e).__name__, str(e)[:300])
+            finally:
+                local_mp.undo()
     print(f"{ok} passed, {bad} failed")
     return bad
 
