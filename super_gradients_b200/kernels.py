@@ -461,10 +461,10 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
     _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
     if out_grads is not None:
         dy3, du = out_grads
+        if nhwc_pitch(dy3) != nhwc_pitch(y3) or nhwc_pitch(du) != nhwc_pitch(u):
+            raise L.SgbError("qarep_bwd: dy3 / du must have the channel pitch of y3 / u")
     else:
-        dy3, du = empty_nhwc(n, c, h, w, y3.device), empty_nhwc(n, c, h, w, y3.device)
-    if nhwc_pitch(dy3) != nhwc_pitch(y3) or nhwc_pitch(du) != nhwc_pitch(u):
-        raise L.SgbError("qarep_bwd: dy3 / du must have the channel pitch of y3 / u")
+        dy3, du = torch.empty_like(y3), torch.empty_like(u)
     z = lambda: zeros((c,), torch.float32, y3.device)  # noqa: E731
     acc = acc or (None,) * 5
     dg3, db3, dab, dgp, dbp = [a if a is not None else z() for a in acc]
