@@ -638,3 +638,24 @@ def test_folded_qarepvgg_path_is_the_same_block(golden, monkeypatch):
         res[fold] = _run(st, x, t, 2)
     assert abs(res[True][0][0] - res[False][0][0]) < 2e-2 * abs(res[False][0][0])
     assert l2rel(res[True][1][3], res[False][1][3]) < 1e-3  # parameters after two steps
+
+
+@pytest.mark.parametrize("name,shape", [("resnet50", (2, 3, 64, 64)), ("resnet18", (2, 3, 64, 64))])
+def test_resnet_imagenet_variants_wire_up(monkeypatch, name, shape):
+    """configs[3] family (Bottleneck / BasicBlock ImageNet ResNets) through models.get(): forward + backward run on the stand-in,
+    logits have the right shape, every parameter receives a finite gradient, eval mode is deterministic."""
+    from super_gradients_b200.training import models
+
+    cpu_backend.install_training(monkeypatch)
+    torch.manual_seed(0)
+    m = models.get(name, num_classes=7).train()
+    x = torch.randn(*shape)
+    logits = m(x)
+    assert tuple(logits.shape) == (shape[0], 7) and logits.dtype == torch.float32
+    torch.nn.functional.cross_entropy(logits, torch.tensor([1, 4])).backward()
+    missing = [k for k, p in m.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not missing, missing[:5]
+    m.eval()
+    with torch.no_grad():
+        a, b = m(x), m(x)
+    assert torch.equal(a, b)
