@@ -255,7 +255,7 @@ int sgb_loss_finalize(const SgbLossDesc* d, const double* sums, float* loss_out,
 int sgb_head_grad_scatter(const float* grad, int gC, int N, int HW, int L, int anchor_base, sgb_bf16* dy, int pitch,
                           void* stream);
 
-/* ---- YoloNASPoseLoss (row L7: training/losses/yolo_nas_pose_loss.py:45-683) --------------------------------- */
+/* ---- YoloNASPoseLoss (row L7: training/losses/yolo_nas_pose_loss.py:45-682) --------------------------------- */
 typedef struct SgbPoseLossDesc {
   int32_t B, L, J, reg_max;                         /* batch, anchors, joints, DFL bins - 1 */
   int32_t n_max;                                    /* padded number of GT instances per image */

@@ -4,7 +4,7 @@
 //
 // Reference: src/super_gradients/training/losses/yolo_nas_pose_loss.py
 //   batch_pose_oks :45-74, YoloNASPoseTaskAlignedAssigner.forward :77-244, YoloNASPoseLoss.forward :404-494,
-//   _keypoint_loss :514-564, _bbox_loss :574-639, _df_loss :496-512, _focal_loss :663-683;
+//   _keypoint_loss :514-564, _bbox_loss :574-639, _df_loss :496-512, _focal_loss :663-682;
 //   GIoU: training/losses/ppyolo_loss.py:564-638, CIoU: training/losses/functional.py:82-133.
 #pragma once
 #include <math.h>
