@@ -1,4 +1,4 @@
-"""width_multiplier / autopad (reference: modules/utils.py:65-80)."""
+"""width_multiplier / autopad (reference: modules/utils.py:63-74)."""
 import math
 
 

@@ -1,5 +1,5 @@
 """ResNet / CifarResNet with the reference's constructors and state-dict keys
-(training/models/classification_models/resnet.py:26-380).  Every conv-bn(-add)-relu group is one fused call:
+(training/models/classification_models/resnet.py:26-379).  Every conv-bn(-add)-relu group is one fused call:
 GEMM with fused batch statistics + one normalise/add/ReLU pass (training) or a single GEMM (inference)."""
 from typing import Dict
 

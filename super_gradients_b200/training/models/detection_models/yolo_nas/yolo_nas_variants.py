@@ -1,4 +1,4 @@
-"""YoloNAS S / M / L (reference: training/models/detection_models/yolo_nas/yolo_nas_variants.py:75-222) and the
+"""YoloNAS S / M / L (reference: training/models/detection_models/yolo_nas/yolo_nas_variants.py:75-212) and the
 export-time pre-NMS top-k decoding module (:24-72)."""
 import copy
 from typing import Any, Optional, Tuple
