@@ -2,7 +2,7 @@
 """Runs the bodies of `-m gpu` test functions on the CPU stand-in of the kernel wrappers (tests/cpu_backend.py) with DEV = "cpu":
 it cannot say anything about the kernels, but it executes the TEST code (fixture keys, shapes, helper names, tolerances against the
 host build of the kernel arithmetic), so a test written without hardware does not waste its first GPU call on a typo.
-Usage: python tools/dryrun_gpu_tests.py tests/test_zz_pose_train_gpu.py [name-substring-to-skip ...]"""
+Usage: python tests/diagnostics/dryrun_gpu_tests.py tests/test_zz_pose_train_gpu.py [name-substring-to-skip ...]"""
 import importlib
 import inspect
 import itertools
@@ -11,7 +11,7 @@ import pathlib
 import sys
 import tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import torch  # noqa: E402
 from _pytest.monkeypatch import MonkeyPatch  # noqa: E402
