@@ -48,6 +48,11 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(d, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(d, f)
+    # developer tools stay oracle-free too (anything that needs the checker lives under tests/)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
 
 
 def test_ctypes_structs_match_the_c_header(tmp_path):
