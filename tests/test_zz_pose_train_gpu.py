@@ -207,3 +207,34 @@ def test_folded_qarepvgg_block_matches_the_two_convolution_path(monkeypatch, cin
     assert set(g0) == set(g1)
     for k in g0:
         assert l2rel(g1[k], g0[k]) < 2e-2, (k, l2rel(g1[k], g0[k]))
+
+
+# (C, H, K, R, stride) of YOLO-NAS-S 640 x 640 layers at the benchmark's batch of 32: full-size parity through
+# a size-independent property.  For any x, w, dy:  <conv(x, w), dy> = <x, dgrad(dy, w)> = <w, wgrad(x, dy)>  (the three kernels are
+# adjoints of one bilinear map), so the three dot products tie fprop, dgrad and wgrad together without an oracle of that size.
+FULL_SIZE_LAYERS = [(48, 320, 96, 3, 2), (32, 160, 32, 3, 1), (96, 160, 96, 1, 1), (96, 160, 32, 1, 1), (64, 80, 64, 3, 1), (192, 80, 192, 1, 1), (96, 40, 96, 3, 1),
+                    (192, 80, 384, 3, 2), (768, 20, 768, 1, 1)]  # fmt: skip
+
+
+@pytest.mark.parametrize("layer", FULL_SIZE_LAYERS)
+def test_conv_adjoint_identity_at_benchmark_size(layer):
+    from super_gradients_b200 import kernels as K
+
+    c, h, kout, r, stride = layer
+    n, pad = 32, r // 2
+    g = torch.Generator().manual_seed(c * 1000 + h + kout)
+    x = K.empty_nhwc(n, c, h, h, DEV)
+    x.copy_(torch.randn(n, c, h, h, generator=g).to(DEV))
+    w = (torch.randn(kout, c, r, r, generator=g) * (c * r * r) ** -0.5).bfloat16().float().to(DEV)
+    krsc, crsk = K.weight_prepare(w)
+    y = K.conv_fprop(x, krsc, kout, r, r, stride, pad)
+    dy = K.empty_nhwc(*y.shape, DEV)
+    dy.copy_(y.float() + 0.5 * torch.randn(y.shape, generator=g).to(DEV))  # correlated with y: the dot products are large and positive
+    dx = K.conv_dgrad(dy, crsk, tuple(x.shape), r, r, stride, pad)
+    dw = K.wgrad_to_oihw(K.conv_wgrad(x, dy, r, r, stride, pad), c)
+    torch.cuda.synchronize()
+    s_fprop = float((y.double() * dy.double()).sum())
+    s_dgrad = float((x.double() * dx.double()).sum())
+    s_wgrad = float((w.double() * dw.double()).sum())
+    assert s_wgrad > 0
+    assert abs(s_fprop - s_wgrad) < 1e-3 * s_wgrad and abs(s_dgrad - s_wgrad) < 1e-3 * s_wgrad, (s_fprop, s_dgrad, s_wgrad)
