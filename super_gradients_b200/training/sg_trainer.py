@@ -96,6 +96,18 @@ def setup_device(device: Optional[str] = None):
     return torch.device("cuda", local_rank)
 
 
+class _SplitReplay:
+    """replay() = graph A, an eagerly issued collective, graph B (TrainStep.capture under data parallelism)."""
+
+    def __init__(self, first, between, second):
+        self.first, self.between, self.second = first, between, second
+
+    def replay(self):
+        self.first.replay()
+        self.between()
+        self.second.replay()
+
+
 class TrainStep:
     """One optimisation step over a FlatState: zero grads -> forward -> loss -> backward -> (all-reduce) -> optimizer
     (-> EMA).  The object owns every per-step device buffer, so the step can be captured in a CUDA graph."""
@@ -221,9 +233,13 @@ class TrainStep:
         return loss.detach(), items
 
     def optimizer_step(self):
-        f = self.flat
         if self.world > 1:
-            f.all_reduce_grads(self.world)
+            self.flat.all_reduce_grads(self.world)
+        self._apply_update()
+
+    def _apply_update(self):
+        """Optimizer + EMA over the (already reduced) flat gradients; no collective in here."""
+        f = self.flat
         nd = f.n_decay
         ranges = [(0, nd, 0), (nd, f.n_live, 1)]
         for a, b, row in ranges:
@@ -285,14 +301,28 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         SF.bump_weight_epoch()
+        if self.world > 1 and os.environ.get("SGB_NCCL_IN_GRAPH") != "1":
+            # Data parallel: TWO graphs around an eagerly issued all-reduce (forward + backward | NCCL | optimizer + EMA).  Capturing
+            # the collective inside the graph saves one launch but depends on NCCL's capture support and on nothing else in the
+            # process touching CUDA meanwhile; the split costs ~one extra graph launch per step and is as robust as the 1-GPU capture.
+            g1, self.static_out = self._capture_region(lambda: self.forward_backward(*self.static_in))
+            g2, _ = self._capture_region(self._apply_update, pool=g1.pool())
+            self.graph = _SplitReplay(g1, lambda: self.flat.all_reduce_grads(self.world), g2)
+        else:
+            self.graph, self.static_out = self._capture_region(lambda: self._step_eager(*self.static_in))
+        return self.graph
+
+    def _capture_region(self, fn, pool=None):
+        """Records fn() into a CUDA graph; returns (graph, fn's outputs = the graph's static output tensors)."""
         g = torch.cuda.CUDAGraph()
-        # with NCCL in the step other threads of the process (the process-group watchdog) touch CUDA during capture:
-        # thread-local capture mode keeps those calls from invalidating the capture
-        mode = "thread_local" if self.world > 1 else "global"
-        with torch.cuda.graph(g, capture_error_mode=mode):
-            self.static_out = self._step_eager(*self.static_in)
-        self.graph = g
-        return g
+        # with NCCL in the process other threads (the process-group watchdog) touch CUDA during capture: thread-local capture mode
+        # keeps those calls from invalidating it
+        kw = {"capture_error_mode": "thread_local" if self.world > 1 else "global"}
+        if pool is not None:
+            kw["pool"] = pool
+        with torch.cuda.graph(g, **kw):
+            out = fn()
+        return g, out
 
     # -------------------------------------------------------------------------------------------- EMA swap (validation)
     def swap_ema(self):

@@ -60,26 +60,23 @@ def setup_device(device=None):
     return torch.device("cpu")
 
 
-def fake_capture(self, inputs, targets, warmup=3):
-    """Same host-side protocol as TrainStep.capture (warm-up steps, static buffers, weight-epoch bump); the 'graph' replays
-    the eager step into the static outputs.  Like a real capture, recording executes nothing (no collective)."""
-    clone = lambda t: t.clone() if torch.is_tensor(t) else type(t)(clone(u) for u in t)  # noqa: E731
-    self.static_in = (clone(inputs), clone(targets))
-    for _ in range(max(warmup, 2)):
-        self._step_eager(*self.static_in)
-        self.opt_steps += 1
-    SF.bump_weight_epoch()
-    self.static_out = (torch.zeros(()), torch.zeros(4))
-    step = self
+def fake_capture_region(self, fn, pool=None):
+    """Stand-in for TrainStep._capture_region: like a real capture it executes nothing now; replay() runs fn() and copies its
+    outputs into the static output tensors handed back here.  TrainStep.capture's own logic (warm-up, one graph or the
+    data-parallel split around the all-reduce) runs unmodified on top of it."""
+    template = (torch.zeros(()), torch.zeros(4))
 
     class FakeGraph:
         def replay(self):
-            loss, items = step._step_eager(*step.static_in)
-            step.static_out[0].copy_(loss)
-            step.static_out[1].copy_(items)
+            out = fn()
+            if out is not None:
+                template[0].copy_(out[0])
+                template[1].copy_(out[1])
 
-    self.graph = FakeGraph()
-    return self.graph
+        def pool(self):
+            return None
+
+    return FakeGraph(), template
 
 
 def synth_batch(batch, seed, img=64):
@@ -113,7 +110,7 @@ mp.setattr(L, "call", lambda name, *a: 0 if name == "sgb_check_device" else refu
 for n in ("conv_fprop", "conv_dgrad", "conv_wgrad"):
     mp.setattr(K, n, profiled("sgb_" + n, getattr(K, n)))
 mp.setattr(sg_trainer, "setup_device", setup_device)
-mp.setattr(sg_trainer.TrainStep, "capture", fake_capture)
+mp.setattr(sg_trainer.TrainStep, "_capture_region", fake_capture_region)
 mp.setattr(bench, "synth_batch", synth_batch)
 mp.setattr(torch.cuda, "Event", FakeEvent)
 mp.setattr(torch.cuda, "Stream", FakeStream)
