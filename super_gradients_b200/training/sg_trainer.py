@@ -301,13 +301,14 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         SF.bump_weight_epoch()
-        if self.world > 1 and os.environ.get("SGB_NCCL_IN_GRAPH") != "1":
+        split = (self.world > 1 and os.environ.get("SGB_NCCL_IN_GRAPH") != "1") or os.environ.get("SGB_SPLIT_GRAPH") == "1"
+        if split:
             # Data parallel: TWO graphs around an eagerly issued all-reduce (forward + backward | NCCL | optimizer + EMA).  Capturing
             # the collective inside the graph saves one launch but depends on NCCL's capture support and on nothing else in the
             # process touching CUDA meanwhile; the split costs ~one extra graph launch per step and is as robust as the 1-GPU capture.
             g1, self.static_out = self._capture_region(lambda: self.forward_backward(*self.static_in))
             g2, _ = self._capture_region(self._apply_update, pool=g1.pool())
-            self.graph = _SplitReplay(g1, lambda: self.flat.all_reduce_grads(self.world), g2)
+            self.graph = _SplitReplay(g1, (lambda: self.flat.all_reduce_grads(self.world)) if self.world > 1 else (lambda: None), g2)
         else:
             self.graph, self.static_out = self._capture_region(lambda: self._step_eager(*self.static_in))
         return self.graph

@@ -238,3 +238,28 @@ def test_conv_adjoint_identity_at_benchmark_size(layer):
     s_wgrad = float((w.double() * dw.double()).sum())
     assert s_wgrad > 0
     assert abs(s_fprop - s_wgrad) < 1e-3 * s_wgrad and abs(s_dgrad - s_wgrad) < 1e-3 * s_wgrad, (s_fprop, s_dgrad, s_wgrad)
+
+
+def test_split_graph_replay_matches_eager(golden, monkeypatch):
+    """The data-parallel capture mechanics (two graphs around the eagerly issued collective) forced on one GPU (SGB_SPLIT_GRAPH=1):
+    replays follow the eager twin like the single-graph capture does (tests/test_trainer_gpu.py)."""
+    from test_trainer_gpu import _step, _targets, rel
+
+    monkeypatch.setenv("SGB_SPLIT_GRAPH", "1")
+    g = golden("tiny_yolo_nas")
+    x, t = g["x"].to(DEV), _targets(g)
+    _, _, sa = _step(g)
+    _, _, sb = _step(g)
+    sb.set_hyper_params(1e-3, 0.99)
+    sb.capture(x, t, warmup=2)
+    assert type(sb.graph).__name__ == "_SplitReplay"
+    for _ in range(2):
+        sa.set_hyper_params(1e-3, 0.99)
+        sa.run(x, t)
+    for i in range(3):
+        sa.set_hyper_params(1e-3, 0.99)
+        sb.set_hyper_params(1e-3, 0.99)
+        la, _ = sa.run(x, t)
+        lb, _ = sb.run(x, t)
+        assert abs(float(la) - float(lb)) <= 2e-2 * abs(float(la)), (i, float(la), float(lb))
+    assert rel(sb.flat.params, sa.flat.params) < 1e-3
