@@ -44,7 +44,9 @@ case "${1:-verify}" in
       printf "%-22s" "libsgb200$v.so"; SGB200_LIB=$lib timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/bench_variant$v.err | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('%.1f img/s  %.3f ms/step  e2e %.1f' % (d['value'], d['ms_per_step'], d['e2e']['value']))"
     done
     # Python-level experiment on the default library: QARepVGG 1x1 branch folded into the 3x3 convolution (functional.QAREP_FOLD)
-    printf "%-22s" "SGB_QAREP_FOLD=1"; SGB_QAREP_FOLD=1 timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/bench_variant_fold.err | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('%.1f img/s  %.3f ms/step  e2e %.1f  launches/step %d' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step']))" ;;
+    printf "%-22s" "SGB_QAREP_FOLD=1"; SGB_QAREP_FOLD=1 timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/bench_variant_fold.err | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('%.1f img/s  %.3f ms/step  e2e %.1f  launches/step %d' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step']))"
+    # cost of the data-parallel capture layout (two graphs around an eager collective) measured on one GPU
+    printf "%-22s" "SGB_SPLIT_GRAPH=1"; SGB_SPLIT_GRAPH=1 timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/bench_variant_split.err | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('%.1f img/s  %.3f ms/step' % (d['value'], d['ms_per_step']))" ;;
   pdl)
     SGB200_LIB=$PWD/super_gradients_b200/libsgb200_pdl.so timeout 500 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py tests/test_trainer_gpu.py -m gpu -q --tb=short -x 2>&1 | tail -6
     for lib in libsgb200.so libsgb200_pdl.so; do
