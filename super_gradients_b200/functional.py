@@ -381,7 +381,16 @@ class _QARepVGG(torch.autograd.Function):
                 K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=dx, accumulate=True)
             dw3 = _wgrad(x, dy3, 3, 3, cfg.stride, 1, cin, sw3)
         dalpha = None
-        if has_alpha:
+        if has_alpha and dcat is not None and sw1 is not None and salpha is not None and (sbias is not None or not has_bias):
+            # fold path with flat gradient slots: the same quantities with one launch each (dot / addcmul_) instead of mul + sum + add
+            dalpha_v = torch.dot(dw1f.reshape(-1), w1.reshape(-1))
+            if has_bias:
+                dalpha_v = dalpha_v + torch.dot(dab, bias1)
+                sbias.addcmul_(dab, alpha)
+            sw1.addcmul_(dw1f, alpha)
+            salpha.add_(dalpha_v)
+            dw1 = dbias1 = dalpha = None
+        elif has_alpha:
             if dw1f is None:
                 dw1f = K.wgrad_to_oihw(K.conv_wgrad(x, du, 1, 1, cfg.stride, 0), cin)  # grad of the folded alpha*K1 + I
             dalpha = (dw1f * w1).sum().reshape(1)
