@@ -371,8 +371,8 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------ train
     def train(self, model: nn.Module, training_params: Mapping[str, Any], train_loader, valid_loader=None, test_loaders=None, additional_configs_to_log=None):
         tp = {**DEFAULT_TRAINING_PARAMS, **dict(training_params or {})}
-        if tp["sync_bn"]:
-            raise NotImplementedError("sync_bn needs per-layer collectives; the data-parallel path uses ONE gradient all-reduce (SURVEY.md D4)")
+        if tp["sync_bn"] and is_distributed():  # on one GPU SyncBatchNorm is plain BatchNorm (the shipped YOLO-NAS recipe sets sync_bn: True)
+            raise NotImplementedError("sync_bn needs per-layer collectives; the data-parallel path uses ONE gradient all-reduce (SURVEY.md D4): set sync_bn=False")
         ckpt = None
         if tp["resume"] or tp["resume_path"]:
             path = tp["resume_path"] or os.path.join(self.checkpoints_dir_path, tp["ckpt_name"])

@@ -659,3 +659,29 @@ def test_resnet_imagenet_variants_wire_up(monkeypatch, name, shape):
     with torch.no_grad():
         a, b = m(x), m(x)
     assert torch.equal(a, b)
+
+
+def test_trainer_accepts_the_shipped_yolo_nas_recipe_dict(golden, monkeypatch, tmp_path):
+    """The training hyper-parameters of the reference's coco2017_yolo_nas_train_params.yaml (recipes/training_hyperparams), as the
+    dict hydra would hand to Trainer.train(): registry-built loss with criterion_params, LinearBatchLRWarmup + CosineLRScheduler, AdamW,
+    threshold EMA, sync_bn: True (a no-op on one device), metric bookkeeping keys that this mirror ignores."""
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.sg_trainer import Trainer
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("tiny_yolo_nas")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    m.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+    recipe = dict(max_epochs=2, warmup_mode="LinearBatchLRWarmup", warmup_initial_lr=1e-6, lr_warmup_steps=3, lr_warmup_epochs=0, initial_lr=2e-4, lr_mode="CosineLRScheduler",
+                  cosine_final_lr_ratio=0.1, zero_weight_decay_on_bias_and_bn=True, batch_accumulate=1, save_ckpt_epoch_list=[100, 200, 250], loss="PPYoloELoss",
+                  criterion_params={"use_static_assigner": False, "num_classes": 4}, optimizer="AdamW", optimizer_params={"weight_decay": 0.00001}, ema=True,
+                  ema_params={"decay": 0.9997, "decay_type": "threshold"}, mixed_precision=False, sync_bn=True, valid_metrics_list=[], pre_prediction_callback=None,
+                  metric_to_watch="mAP@0.50:0.95", greater_metric_to_watch_is_better=True)  # fmt: skip
+    tr = Trainer("recipe", ckpt_root_dir=str(tmp_path))
+    hist = tr.train(m, recipe, [(g["x"], g["targets"])] * 2, valid_loader=[(g["x"], g["targets"])])
+    assert len(hist["train_loss"]) == 2 and all(np.isfinite(hist["train_loss"])) and len(hist["valid_loss"]) == 2
+    np.testing.assert_allclose(hist["lr"][:3], [1e-6 + (2e-4 - 1e-6) * s / 3 for s in range(3)], rtol=1e-12)  # linear batch warm-up from warmup_initial_lr
+    assert hist["lr"][3] <= 2e-4 and tr.step.opt_name == "AdamW" and tr.step.ema_on
