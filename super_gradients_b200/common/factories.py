@@ -13,22 +13,34 @@ class UnknownTypeException(Exception):
         super().__init__(f"Unknown object type: {unknown_type} in configuration. valid types are: {sorted(choices)}")
 
 
+def _fuzzy(name) -> str:
+    """Registry names are matched without sensitivity to case, underscores and punctuation when there is no exact hit
+    (training/utils/utils.py:255-261): the shipped recipes write `yolo_nas_pose_loss` for the class registered as `YoloNASPoseLoss`."""
+    import re
+
+    return re.sub(r"[^\w|\/]", "", str(name)).replace("_", "").lower()
+
+
 class BaseFactory:
     def __init__(self, type_dict: Dict[str, type]):
         self.type_dict = type_dict
 
+    def _resolve(self, name):
+        if name in self.type_dict:
+            return self.type_dict[name]
+        loose = {_fuzzy(k): v for k, v in self.type_dict.items()}
+        if _fuzzy(name) in loose:
+            return loose[_fuzzy(name)]
+        raise UnknownTypeException(name, self.type_dict.keys())
+
     def get(self, conf: Union[str, dict]):
         if isinstance(conf, str):
-            if conf not in self.type_dict:
-                raise UnknownTypeException(conf, self.type_dict.keys())
-            return self.type_dict[conf]()
+            return self._resolve(conf)()
         if isinstance(conf, Mapping):
             if len(conf) != 1:
                 raise RuntimeError(f"Malformed object definition: expected a type name or a single-entry dict {{type_name: {{params}}}}, received: {conf}")
             (_type, _params), = conf.items()
-            if _type not in self.type_dict:
-                raise UnknownTypeException(_type, self.type_dict.keys())
-            return self.type_dict[_type](**_params)
+            return self._resolve(_type)(**_params)
         return conf
 
 

@@ -373,8 +373,9 @@ def test_trainer_train_pose_model(golden, monkeypatch, tmp_path):
     m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
     m.load_state_dict({k: v.clone() for k, v in g0["sd0"].items()}, strict=False)
     before = m.heads.head1.pose_pred.weight.detach().clone()
+    # `yolo_nas_pose_loss` is how the shipped coco2017_yolo_nas_pose_train_params.yaml names the loss (fuzzy registry match)
     tp = dict(max_epochs=1, initial_lr=1e-3, lr_mode="constant", optimizer="AdamW", optimizer_params={"weight_decay": 1e-5}, zero_weight_decay_on_bias_and_bn=True, ema=False,
-              loss="YoloNASPoseLoss", criterion_params=dict(oks_sigmas=g["sigmas"], **g["kw"]), save_model=False)  # fmt: skip
+              loss="yolo_nas_pose_loss", criterion_params=dict(oks_sigmas=g["sigmas"], **g["kw"]), save_model=False)  # fmt: skip
     hist = Trainer("pose", ckpt_root_dir=str(tmp_path)).train(m, tp, [(g["x"], g["targets"]), (g["x"] * 0.9, g["targets"])])
     assert len(hist["train_loss"]) == 1 and np.isfinite(hist["train_loss"][0]) and hist["train_loss"][0] > 0
     assert not torch.equal(before, m.heads.head1.pose_pred.weight.detach())
