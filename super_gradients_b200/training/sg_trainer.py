@@ -31,7 +31,10 @@ DEFAULT_TRAINING_PARAMS = {
     "cosine_final_lr_ratio": 0.01,
     "lr_updates": [],
     "lr_decay_factor": 0.1,
-    "lr_warmup_steps": 0,
+    "lr_warmup_steps": 0,  # LinearBatchLRWarmup
+    "lr_warmup_epochs": 0,  # LinearEpochLRWarmup (and the epoch the schedulers start at)
+    "lr_cooldown_epochs": 0,
+    "warmup_mode": None,  # None: batch warm-up when lr_warmup_steps > 0, else epoch warm-up
     "warmup_initial_lr": None,
     "optimizer": "SGD",
     "optimizer_params": {},
@@ -66,6 +69,51 @@ def cosine_lr(step: float, total_steps: float, initial_lr: float, final_lr_ratio
     """CosineLRScheduler.compute_learning_rate (training/utils/callbacks/callbacks.py:506-511)."""
     lr = 0.5 * initial_lr * (1.0 + math.cos(step / (total_steps + 1) * math.pi))
     return lr * (1 - final_lr_ratio) + initial_lr * final_lr_ratio
+
+
+def lr_schedule(tp: Mapping[str, Any], steps_per_epoch: int) -> list:
+    """The learning rate the reference's callbacks leave in the optimizer at every optimisation step of a run, reproduced by
+    replaying their order inside Trainer._train_epoch (training/utils/callbacks/callbacks.py; sg_trainer.py:499-600):
+      epoch start  -> LinearEpochLRWarmup (:275-314), while lr_warmup_epochs >= epoch;
+      batch start  -> LinearBatchLRWarmup (:317-380): linspace(warmup_initial_lr, initial_lr, min(lr_warmup_steps, len(loader)))[step];
+      (the optimizer step uses the rate at this point)
+      batch step   -> CosineLRScheduler (:489-512), i.e. its value takes effect from the NEXT step;
+      epoch end    -> StepLRScheduler (:395-425), i.e. a milestone e takes effect from epoch e + 1."""
+    lr0 = float(tp["initial_lr"])
+    spe = max(int(steps_per_epoch), 1)
+    max_epochs = int(tp["max_epochs"])
+    warm_epochs = int(tp.get("lr_warmup_epochs") or 0)
+    warm_steps = int(tp.get("lr_warmup_steps") or 0)
+    cool = int(tp.get("lr_cooldown_epochs") or 0)
+    mode_w = tp.get("warmup_mode")
+    batch_warmup = warm_steps > 0 and (mode_w is None or "batch" in str(getattr(mode_w, "__name__", mode_w)).lower())
+    epoch_warmup = not batch_warmup and warm_epochs > 0
+    mode = tp.get("lr_mode")
+    if mode not in (None, "constant", "none", "cosine", "CosineLRScheduler", "step", "StepLRScheduler"):
+        raise NotImplementedError(f"lr_mode {mode}")
+    n_batch = min(warm_steps, spe) if batch_warmup else 0
+    w0 = tp.get("warmup_initial_lr")
+    batch_start = float(w0) if w0 is not None else lr0 / (n_batch + 1)
+    epoch_start = float(w0) if w0 is not None else lr0 / (warm_epochs + 1)
+    ratio = float(tp.get("cosine_final_lr_ratio", 0.01))
+    lr, out = lr0, []
+    for epoch in range(max_epochs):
+        if epoch_warmup and warm_epochs >= epoch:
+            lr = epoch_start + epoch * (lr0 - epoch_start) / warm_epochs
+        for b in range(spe):
+            g = epoch * spe + b
+            if g < n_batch:
+                lr = batch_start + (lr0 - batch_start) * g / (n_batch - 1) if n_batch > 1 else batch_start
+            out.append(float(lr))
+            if mode in ("cosine", "CosineLRScheduler"):
+                enabled = (g >= warm_steps) if warm_steps > 0 else (warm_epochs <= epoch < max_epochs - cool)
+                if enabled:
+                    cur = max(0, spe * (epoch - warm_epochs) + b - warm_steps)
+                    total = spe * (max_epochs - warm_epochs - cool) - warm_steps
+                    lr = cosine_lr(cur, total, lr0, ratio)
+        if mode in ("step", "StepLRScheduler") and warm_epochs <= epoch:
+            lr = lr0 * float(tp["lr_decay_factor"]) ** sum(1 for e in tp["lr_updates"] if e <= epoch)
+    return out or [lr0]
 
 
 def ema_decay(decay_type: str, decay: float, step: int, total_steps: int, beta: float = 15.0) -> float:
@@ -352,21 +400,12 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------------ LR schedule
     def _lr_at(self, tp, global_step: int, steps_per_epoch: int) -> float:
-        lr0 = float(tp["initial_lr"])
-        warm = int(tp["lr_warmup_steps"])
-        if warm > 0 and global_step < warm:
-            start = tp["warmup_initial_lr"] if tp["warmup_initial_lr"] is not None else lr0 / (warm + 1)
-            return float(start + (lr0 - start) * global_step / warm)  # linear_batch_step warm-up
-        mode = tp["lr_mode"]
-        total = steps_per_epoch * int(tp["max_epochs"])
-        if mode in ("cosine", "CosineLRScheduler"):
-            return cosine_lr(max(0, global_step - warm), total - warm, lr0, float(tp["cosine_final_lr_ratio"]))
-        if mode in ("step", "StepLRScheduler"):
-            epoch = global_step // max(steps_per_epoch, 1)
-            return lr0 * float(tp["lr_decay_factor"]) ** sum(1 for e in tp["lr_updates"] if epoch >= e)
-        if mode in (None, "constant", "none"):
-            return lr0
-        raise NotImplementedError(f"lr_mode {mode}")
+        """Learning rate in the optimizer at one optimisation step (see lr_schedule)."""
+        key = (id(tp), int(steps_per_epoch))
+        if getattr(self, "_lr_table_key", None) != key:
+            self._lr_table = lr_schedule(tp, steps_per_epoch)
+            self._lr_table_key = key
+        return self._lr_table[min(int(global_step), len(self._lr_table) - 1)]
 
     # ------------------------------------------------------------------------------------------------ train
     def train(self, model: nn.Module, training_params: Mapping[str, Any], train_loader, valid_loader=None, test_loaders=None, additional_configs_to_log=None):

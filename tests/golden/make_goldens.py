@@ -381,6 +381,59 @@ def golden_processing():
     torch.save(out, os.path.join(HERE, "processing.pt"))
 
 
+def golden_lr_schedules():
+    """LR actually in the optimizer at every optimisation step, produced by the reference's own warm-up / scheduler callbacks driven in
+    the order of Trainer._train_epoch (epoch-start callbacks, per batch: batch-start callbacks -> optimizer step -> TRAIN_BATCH_STEP
+    callbacks, then epoch-end callbacks)."""
+    from super_gradients.common.registry.registry import LR_SCHEDULERS_CLS_DICT, LR_WARMUP_CLS_DICT
+    from super_gradients.training.utils import HpmStruct
+    from super_gradients.training.utils.callbacks import Phase, PhaseContext
+
+    base = dict(lr_mode=None, lr_warmup_epochs=0, lr_warmup_steps=0, lr_cooldown_epochs=0, warmup_initial_lr=None, warmup_mode="LinearEpochLRWarmup", cosine_final_lr_ratio=0.01,
+                lr_updates=[], lr_decay_factor=0.1, step_lr_update_freq=None, max_epochs=6, initial_lr=0.1)
+    cases = {
+        "yolo_nas_recipe": dict(warmup_mode="LinearBatchLRWarmup", warmup_initial_lr=1e-6, lr_warmup_steps=1000, initial_lr=2e-4, lr_mode="CosineLRScheduler", cosine_final_lr_ratio=0.1, max_epochs=4),
+        "pose_recipe_like": dict(warmup_mode="LinearBatchLRWarmup", warmup_initial_lr=1e-6, lr_warmup_steps=3, lr_warmup_epochs=2, initial_lr=2e-3, lr_mode="cosine", cosine_final_lr_ratio=0.05),
+        "resnet50_like": dict(lr_warmup_epochs=2, lr_mode="CosineLRScheduler", initial_lr=0.1),
+        "cifar_like": dict(lr_mode="StepLRScheduler", lr_updates=[2, 4], lr_decay_factor=0.1, initial_lr=0.1),
+        "epoch_warmup_given_start_step": dict(lr_warmup_epochs=3, warmup_initial_lr=0.01, lr_mode="step", lr_updates=[4], lr_decay_factor=0.5, initial_lr=0.2),
+        "cosine_cooldown": dict(lr_mode="cosine", lr_cooldown_epochs=2, initial_lr=0.05, cosine_final_lr_ratio=0.1),
+    }
+    out = {}
+    loader_len = 5
+    for name, kw in cases.items():
+        tp = HpmStruct(**{**base, **kw})
+        net = torch.nn.Linear(2, 2)
+        opt = torch.optim.SGD([{"params": net.parameters(), "name": "default"}], lr=tp.initial_lr)
+        common = dict(train_loader_len=loader_len, net=net, training_params=tp, update_param_groups=False, **tp.to_dict())
+        cbs = []
+        if tp.lr_mode is not None:
+            cbs.append(LR_SCHEDULERS_CLS_DICT[tp.lr_mode](**common))
+        cbs.append(LR_WARMUP_CLS_DICT[tp.warmup_mode](**common))
+        ctx = PhaseContext(epoch=0, batch_idx=0, optimizer=opt, net=net)
+        lrs = []
+
+        def fire(phase):
+            for cb in cbs:
+                if getattr(cb, "phase", None) == phase:
+                    cb(ctx)
+
+        for epoch in range(tp.max_epochs):
+            ctx.update_context(epoch=epoch, batch_idx=0)
+            fire(Phase.TRAIN_EPOCH_START)
+            for b in range(loader_len):
+                ctx.update_context(batch_idx=b)
+                for cb in cbs:
+                    if hasattr(cb, "on_train_batch_start") and not hasattr(cb, "phase"):
+                        cb.on_train_batch_start(ctx)
+                lrs.append(float(opt.param_groups[0]["lr"]))
+                fire(Phase.TRAIN_BATCH_STEP)
+                fire(Phase.TRAIN_BATCH_END)
+            fire(Phase.TRAIN_EPOCH_END)
+        out[name] = dict(params={**base, **kw}, loader_len=loader_len, lrs=lrs)
+    torch.save(out, os.path.join(HERE, "lr_schedules.pt"))
+
+
 def golden_tiny_yolo_nas():
     from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
     from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNAS
@@ -550,7 +603,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "lr_schedules", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

@@ -336,9 +336,12 @@ def test_trainer_train_end_to_end(golden, monkeypatch, tmp_path):
     hist = trainer.train(model, tp, loader, valid_loader=loader[:1])
     assert len(hist["train_loss"]) == 2 and len(hist["valid_loss"]) == 2 and len(hist["lr"]) == 6
     assert all(np.isfinite(v) for v in hist["train_loss"] + hist["valid_loss"])
-    # the schedule: 2 linear warm-up steps from lr0 / 3, then cosine over the remaining 4 of 6 steps down to 0.1 * lr0
-    want = [2e-3 / 3 + (2e-3 - 2e-3 / 3) * s / 2 for s in range(2)] + [cosine_lr(s, 4, 2e-3, 0.1) for s in range(4)]
+    # the schedule the reference's callbacks would leave in the optimizer (tests/test_host_logic.py pins lr_schedule against
+    # traces of those callbacks): batch warm-up linspace(lr0 / 3, lr0, 2), then the cosine value computed after each step
+    want = sg_trainer.lr_schedule({**sg_trainer.DEFAULT_TRAINING_PARAMS, **tp}, 3)
     np.testing.assert_allclose([lr for lr, _ in seen_lr], want, rtol=1e-12)
+    np.testing.assert_allclose(want[:3], [2e-3 / 3, 2e-3, cosine_lr(0, 4, 2e-3, 0.1)], rtol=1e-12)
+    assert want[-1] < 0.75 * 2e-3 and want[1:] == sorted(want[1:], reverse=True)  # decreasing after the warm-up
     np.testing.assert_allclose([d for _, d in seen_lr], [min(0.99, (1 + t) / (10 + t)) for t in range(1, 7)], rtol=1e-12)
     assert trainer.step.opt_steps == 6 and not np.allclose(hist["train_loss"][0], hist["train_loss"][1])
     ck = torch.load(tmp_path / "glue" / "ckpt_latest.pth", weights_only=False)
@@ -684,5 +687,5 @@ def test_trainer_accepts_the_shipped_yolo_nas_recipe_dict(golden, monkeypatch, t
     tr = Trainer("recipe", ckpt_root_dir=str(tmp_path))
     hist = tr.train(m, recipe, [(g["x"], g["targets"])] * 2, valid_loader=[(g["x"], g["targets"])])
     assert len(hist["train_loss"]) == 2 and all(np.isfinite(hist["train_loss"])) and len(hist["valid_loss"]) == 2
-    np.testing.assert_allclose(hist["lr"][:3], [1e-6 + (2e-4 - 1e-6) * s / 3 for s in range(3)], rtol=1e-12)  # linear batch warm-up from warmup_initial_lr
-    assert hist["lr"][3] <= 2e-4 and tr.step.opt_name == "AdamW" and tr.step.ema_on
+    np.testing.assert_allclose(hist["lr"][:2], [1e-6, 2e-4], rtol=1e-12)  # LinearBatchLRWarmup capped at the loader length (2 steps here)
+    assert max(hist["lr"]) <= 2e-4 and tr.step.opt_name == "AdamW" and tr.step.ema_on

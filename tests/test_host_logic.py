@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -188,3 +189,18 @@ def test_no_undefined_names_in_any_python_file():
             files += [os.path.join(d, n) for n in names if n.endswith(".py")]
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "undefined_names.py"), *files], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
+
+
+@pytest.mark.parametrize("case", ["yolo_nas_recipe", "pose_recipe_like", "resnet50_like", "cifar_like", "epoch_warmup_given_start_step", "cosine_cooldown"])
+def test_lr_schedule_reproduces_the_reference_callbacks(golden, case):
+    """The LR in the optimizer at every step == traces recorded by driving the reference's LinearBatchLRWarmup / LinearEpochLRWarmup /
+    CosineLRScheduler / StepLRScheduler in the order of its training loop (tests/golden/make_goldens.py::golden_lr_schedules),
+    including their quirks (cosine values apply from the next step, step milestones from the next epoch, lr_warmup_steps capped
+    at the loader length for the warm-up but not for the scheduler's start)."""
+    from super_gradients_b200.training.sg_trainer import DEFAULT_TRAINING_PARAMS, lr_schedule
+
+    g = golden("lr_schedules")[case]
+    tp = {**DEFAULT_TRAINING_PARAMS, **{k: v for k, v in g["params"].items() if k in DEFAULT_TRAINING_PARAMS}}
+    mine = lr_schedule(tp, g["loader_len"])
+    assert len(mine) == len(g["lrs"])
+    np.testing.assert_allclose(mine, g["lrs"], rtol=1e-12, atol=0)
