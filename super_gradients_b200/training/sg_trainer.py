@@ -454,7 +454,7 @@ class Trainer:
                 gstep = epoch * steps_per_epoch + batch_idx
                 lr = self._lr_at(tp, gstep, steps_per_epoch)
                 do_step = (batch_idx + 1 + steps_per_epoch * epoch) % acc == 0
-                self.step.set_hyper_params(lr, ema_decay(ema_p["decay_type"], float(ema_p["decay"]), self.step.opt_steps + 1, total_steps, float(ema_p.get("beta", 15))) if tp["ema"] else None)
+                self.step.set_hyper_params(lr, ema_decay(ema_p["decay_type"], float(ema_p["decay"]), gstep + 1, total_steps, float(ema_p.get("beta", 15))) if tp["ema"] else None)
                 if tp["cuda_graph"] and self.step.graph is None and torch.is_tensor(targets) and targets.is_cuda:
                     self.step.capture(inputs, targets)
                 loss, _items = self.step.run(inputs, targets, do_step)
