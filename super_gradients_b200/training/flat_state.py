@@ -14,8 +14,10 @@ from torch import nn
 
 
 def _is_no_decay(name: str, p: torch.Tensor, bn_param_ids) -> bool:
-    """zero_weight_decay_on_bias_and_bn grouping (reference: training/utils/optimizer_utils.py:32-85)."""
-    return id(p) in bn_param_ids or name.endswith(".bias") or name.endswith("alpha")
+    """zero_weight_decay_on_bias_and_bn grouping (reference: training/utils/optimizer_utils.py:32-85): normalisation weights and
+    biases, and every module's `bias` parameter; everything else decays -- including the scalar `alpha` parameters of QARepVGG
+    blocks and YOLO-NAS bottlenecks (pinned against the reference's grouping in tests/test_host_logic.py)."""
+    return id(p) in bn_param_ids or name.endswith(".bias")
 
 
 class FlatState:

@@ -434,6 +434,26 @@ def golden_lr_schedules():
     torch.save(out, os.path.join(HERE, "lr_schedules.pt"))
 
 
+def golden_param_groups():
+    """zero_weight_decay_on_bias_and_bn: which parameters the reference puts in the weight_decay = 0 group
+    (training/utils/optimizer_utils.py:32-85), for the tiny YOLO-NAS, the tiny YOLO-NAS-POSE and resnet18_cifar."""
+    from super_gradients.training import models
+    from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNAS
+    from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_variants import YoloNASPose
+    from super_gradients.training.utils.optimizer_utils import _get_no_decay_param_ids
+
+    out = {}
+    ap = copy.deepcopy(TINY_YOLO_NAS)
+    nets = {"tiny_yolo_nas": YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)}
+    ap = copy.deepcopy(tiny_pose_arch())
+    nets["tiny_yolo_nas_pose"] = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    nets["resnet18_cifar"] = models.get("resnet18_cifar", num_classes=10)
+    for name, net in nets.items():
+        ids = set(_get_no_decay_param_ids(net))
+        out[name] = dict(no_decay=[k for k, p in net.named_parameters() if id(p) in ids], decay=[k for k, p in net.named_parameters() if id(p) not in ids])
+    torch.save(out, os.path.join(HERE, "param_groups.pt"))
+
+
 def golden_tiny_yolo_nas():
     from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
     from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNAS
@@ -603,7 +623,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "lr_schedules", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

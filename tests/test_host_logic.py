@@ -204,3 +204,31 @@ def test_lr_schedule_reproduces_the_reference_callbacks(golden, case):
     mine = lr_schedule(tp, g["loader_len"])
     assert len(mine) == len(g["lrs"])
     np.testing.assert_allclose(mine, g["lrs"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", ["tiny_yolo_nas", "tiny_yolo_nas_pose", "resnet18_cifar"])
+def test_zero_weight_decay_groups_match_reference(golden, name):
+    """FlatState's decay / no-decay split == the reference's separate_zero_wd_params_groups_for_optimizer on the same architecture
+    (the never-used rbr_reparam placeholders aside: they receive no gradient, so no optimizer ever touches them)."""
+    import copy
+
+    from super_gradients_b200.training import models
+    from super_gradients_b200.training.flat_state import FlatState
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.models.pose_estimation_models import YoloNASPose
+
+    g = golden("param_groups")[name]
+    if name == "resnet18_cifar":
+        m = models.get("resnet18_cifar", num_classes=10)
+    elif name == "tiny_yolo_nas":
+        ap = copy.deepcopy(golden("tiny_yolo_nas")["arch"])
+        m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    else:
+        ap = copy.deepcopy(golden("tiny_yolo_nas_pose")["arch"])
+        m = YoloNASPose(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=5, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    fs = FlatState(m, zero_wd_on_bias_and_bn=True)
+    decay = [n for n, _ in fs.order if fs.offsets[n][0] < fs.n_decay]
+    no_decay = [n for n, _ in fs.order if fs.offsets[n][0] >= fs.n_decay]
+    live = lambda names: [n for n in names if "rbr_reparam" not in n]  # noqa: E731
+    assert decay == live(g["decay"]) and no_decay == live(g["no_decay"])
+    assert any(n.endswith("alpha") for n in decay) or name == "resnet18_cifar"
