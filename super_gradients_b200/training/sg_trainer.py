@@ -23,6 +23,7 @@ from .. import functional as SF
 from .. import kernels as K
 from ..common.factories import LossesFactory
 from .flat_state import FlatState
+from .utils.callbacks import CallbackHandler, PhaseContext
 
 DEFAULT_TRAINING_PARAMS = {
     "max_epochs": 1,
@@ -428,6 +429,9 @@ class Trainer:
             criterion = criterion.to(self.device)
         self.criterion = criterion
         self.step = TrainStep(self.net, criterion, tp["optimizer"], tp["optimizer_params"], bool(tp["zero_weight_decay_on_bias_and_bn"]), ema=bool(tp["ema"]), batch_accumulate=int(tp["batch_accumulate"]))
+        handler = CallbackHandler(tp["phase_callbacks"])
+        context = PhaseContext(net=self.net, criterion=criterion, device=self.device, experiment_name=self.experiment_name, ckpt_dir=self.checkpoints_dir_path,
+                               train_loader=train_loader, valid_loader=valid_loader, training_params=tp, optimizer=None, context_methods=self)  # fmt: skip
         steps_per_epoch = len(train_loader) if tp["max_train_batches"] is None else min(len(train_loader), int(tp["max_train_batches"]))
         total_steps = steps_per_epoch * int(tp["max_epochs"])
         ema_p = {**DEFAULT_TRAINING_PARAMS["ema_params"], **dict(tp["ema_params"] or {})}
@@ -439,8 +443,13 @@ class Trainer:
             best = ckpt.get("acc")
             self._restore_training_state(ckpt)
         t0 = time.time()
+        handler.fire("on_training_start", context)
         for epoch in range(start_epoch, int(tp["max_epochs"])):
+            if context.stop_training:
+                break
             self.net.train()
+            context.update_context(epoch=epoch, batch_idx=None)
+            handler.fire("on_train_loader_start", context)
             if hasattr(getattr(train_loader, "sampler", None), "set_epoch"):
                 train_loader.sampler.set_epoch(epoch)
             running, nb = None, 0
@@ -457,29 +466,48 @@ class Trainer:
                 self.step.set_hyper_params(lr, ema_decay(ema_p["decay_type"], float(ema_p["decay"]), gstep + 1, total_steps, float(ema_p.get("beta", 15))) if tp["ema"] else None)
                 if tp["cuda_graph"] and self.step.graph is None and torch.is_tensor(targets) and targets.is_cuda:
                     self.step.capture(inputs, targets)
+                if handler.callbacks:
+                    context.update_context(batch_idx=batch_idx, inputs=inputs, target=targets, lr=lr)
+                    handler.fire("on_train_batch_start", context)
                 loss, _items = self.step.run(inputs, targets, do_step)
                 running = loss.clone() if running is None else running + loss  # clone: with a captured graph `loss` is the static output buffer
                 nb += 1
                 self.history["lr"].append(lr)
+                if handler.callbacks:  # the fused step is over: the reference's per-batch events, in its order
+                    context.update_context(loss_log_items=_items, preds=None)
+                    handler.fire("on_train_batch_loss_end", context)
+                    handler.fire("on_train_batch_backward_end", context)
+                    if do_step:
+                        handler.fire("on_train_batch_gradient_step_start", context)
+                        handler.fire("on_train_batch_gradient_step_end", context)
+                    handler.fire("on_train_batch_end", context)
             train_loss = float(running / max(nb, 1)) if running is not None else float("nan")
             self.history["train_loss"].append(train_loss)
             metrics = {"train_loss": train_loss}
+            context.update_context(metrics_dict=metrics)
+            handler.fire("on_train_loader_end", context)
             if valid_loader is not None and (epoch + 1) % int(tp["run_validation_freq"]) == 0:
                 self.step.swap_ema()  # validate / checkpoint the EMA weights (sg_trainer.py:1566-1569)
-                metrics["valid_loss"] = self._validate(valid_loader, tp)
+                handler.fire("on_validation_loader_start", context)
+                metrics["valid_loss"] = self._validate(valid_loader, tp, handler, context)
                 self.history["valid_loss"].append(metrics["valid_loss"])
+                context.update_context(metrics_dict=metrics)
+                handler.fire("on_validation_loader_end", context)
                 self.step.swap_ema()
             if tp["save_model"] and not self.ddp_silent_mode:
                 watch = metrics.get("valid_loss", train_loss)
                 is_best = best is None or watch < best
                 best = watch if is_best else best
                 self._save_checkpoint(epoch, metrics, tp, is_best)
+                if is_best and "valid_loss" in metrics:
+                    handler.fire("on_validation_end_best_epoch", context)
             if not tp["silent_mode"] and not self.ddp_silent_mode:
                 print(f"[{self.experiment_name}] epoch {epoch} " + " ".join(f"{k}={v:.5f}" for k, v in metrics.items()) + f" ({time.time() - t0:.1f}s)")
+        handler.fire("on_training_end", context)
         return self.history
 
     @torch.no_grad()
-    def _validate(self, loader, tp) -> float:
+    def _validate(self, loader, tp, handler=None, context=None) -> float:
         self.net.eval()
         tot, n = 0.0, 0
         for i, batch in enumerate(loader):
@@ -488,7 +516,14 @@ class Trainer:
             inputs, targets = batch[0].to(self.device), batch[1]
             if torch.is_tensor(targets) and type(self.criterion).__name__ != "PPYoloELoss":
                 targets = targets.to(self.device)
-            out = self.criterion(self.net(inputs), targets)
+            if handler is not None and handler.callbacks:
+                context.update_context(batch_idx=i, inputs=inputs, target=targets)
+                handler.fire("on_validation_batch_start", context)
+            preds = self.net(inputs)
+            out = self.criterion(preds, targets)
+            if handler is not None and handler.callbacks:
+                context.update_context(preds=preds, loss_log_items=out[1] if isinstance(out, tuple) else None)
+                handler.fire("on_validation_batch_end", context)
             loss = out[0] if isinstance(out, tuple) else out
             tot += float(loss)
             n += 1

@@ -689,3 +689,47 @@ def test_trainer_accepts_the_shipped_yolo_nas_recipe_dict(golden, monkeypatch, t
     assert len(hist["train_loss"]) == 2 and all(np.isfinite(hist["train_loss"])) and len(hist["valid_loss"]) == 2
     np.testing.assert_allclose(hist["lr"][:2], [1e-6, 2e-4], rtol=1e-12)  # LinearBatchLRWarmup capped at the loader length (2 steps here)
     assert max(hist["lr"]) <= 2e-4 and tr.step.opt_name == "AdamW" and tr.step.ema_on
+
+
+def test_phase_callbacks_fire_in_the_reference_order(golden, monkeypatch, tmp_path):
+    """training_params.phase_callbacks: Callback subclasses get every on_<event>, PhaseCallbacks are called at their phase; the
+    order is the reference training loop's (per batch: start, [fused step], loss_end, backward_end, gradient_step_start / _end,
+    batch_end), validation runs on the EMA weights between loader_start / loader_end, and a callback can stop the run."""
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.losses import PPYoloELoss
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.sg_trainer import Trainer
+    from super_gradients_b200.training.utils.callbacks import Callback, Phase, PhaseCallback
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("tiny_yolo_nas")
+    ap = copy.deepcopy(g["arch"])
+    m = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    m.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+    events = []
+
+    class Recorder(Callback):
+        pass
+
+    for name in [n for n in dir(Callback) if n.startswith("on_")]:
+        setattr(Recorder, name, (lambda n: lambda self, ctx: events.append((n, ctx.epoch, ctx.batch_idx)))(name))
+
+    class StopAfterFirstEpoch(PhaseCallback):
+        def __init__(self):
+            super().__init__(Phase.VALIDATION_EPOCH_END)
+
+        def __call__(self, ctx):
+            events.append(("PHASE_VALIDATION_EPOCH_END", ctx.epoch, float(ctx.metrics_dict["valid_loss"])))
+            ctx.stop_training = True
+
+    tp = dict(max_epochs=3, initial_lr=1e-3, lr_mode="constant", optimizer="SGD", optimizer_params={}, ema=True, ema_params={"decay": 0.9, "decay_type": "constant"},
+              loss=PPYoloELoss(num_classes=4, use_static_assigner=False), save_model=False, phase_callbacks=[Recorder(), StopAfterFirstEpoch()])  # fmt: skip
+    hist = Trainer("cb", ckpt_root_dir=str(tmp_path)).train(m, tp, [(g["x"], g["targets"])] * 2, valid_loader=[(g["x"], g["targets"])])
+    assert len(hist["train_loss"]) == 1  # stopped after the first epoch
+    names = [e[0] for e in events]
+    per_batch = ["on_train_batch_start", "on_train_batch_loss_end", "on_train_batch_backward_end", "on_train_batch_gradient_step_start", "on_train_batch_gradient_step_end",
+                 "on_train_batch_end"]  # fmt: skip
+    assert names == (["on_training_start", "on_train_loader_start"] + per_batch * 2 + ["on_train_loader_end", "on_validation_loader_start", "on_validation_batch_start",
+                     "on_validation_batch_end", "on_validation_loader_end", "PHASE_VALIDATION_EPOCH_END", "on_training_end"])  # fmt: skip
+    assert [e[2] for e in events if e[0] == "on_train_batch_start"] == [0, 1] and np.isfinite(events[-2][2])
