@@ -306,6 +306,27 @@ int64_t sgb_nms_workspace_bytes(const SgbNmsDesc* d);
 int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const float* scores, float* out, int32_t* out_idx,
                     int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- DetectionMetrics matching (training/utils/detection_utils.py:1120-1281, IoUMatching :880-1003) ---- */
+#define SGB_MATCH_MAX_THRESHOLDS 32
+typedef struct SgbMatchDesc {
+  int32_t B;                     /* images of the batch */
+  int32_t max_preds;             /* row pitch of the prediction tensor (the NMS kernel's max_out) */
+  int32_t max_targets;           /* row pitch of the padded target tensor (>= 1) */
+  int32_t max_crowd;             /* row pitch of the padded crowd-target tensor (0: none) */
+  int32_t n_thresholds;          /* IoU thresholds, ascending, <= SGB_MATCH_MAX_THRESHOLDS */
+  int32_t top_k;                 /* predictions kept per class and image (DetectionMetrics top_k_predictions) */
+  int32_t denormalize_targets;   /* targets are normalised (cx, cy, w, h): scale by width / height */
+  float height, width;           /* image size the predictions are clipped to */
+} SgbMatchDesc;
+/* preds [B, max_preds, 6] f32 rows (x1, y1, x2, y2, score, class) as sgb_batched_nms writes them, pred_count [B];
+ * targets [B, max_targets, 5] f32 rows (class, cx, cy, w, h), target_count [B]; crowd likewise (NULL when max_crowd == 0);
+ * thresholds [n_thresholds] f32.  matched / ignore [B, max_preds, n_thresholds] uint8 (rows >= pred_count[b] are zeroed) =
+ * compute_img_detection_matching's preds_matched / preds_to_ignore for every image, bit-exact.  One CTA per image, one warp
+ * per threshold. */
+int sgb_detection_matching(const SgbMatchDesc* d, const float* preds, const int32_t* pred_count, const float* targets,
+                           const int32_t* target_count, const float* crowd, const int32_t* crowd_count, const float* thresholds,
+                           uint8_t* matched, uint8_t* ignore, void* stream);
+
 /* ---- fused predict() pre-processing (training/processing/processing.py:205-590, pipelines.py:192-216) ---- */
 typedef struct SgbPreprocDesc {
   int32_t src_h, src_w, src_c; /* uint8 H x W x C source image (C <= 4) */

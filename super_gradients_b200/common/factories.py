@@ -5,7 +5,7 @@ from typing import Any, Dict, Union
 
 from torch import nn
 
-from .registry import ALL_DETECTION_MODULES, LOSSES
+from .registry import ALL_DETECTION_MODULES, LOSSES, METRICS
 
 
 class UnknownTypeException(Exception):
@@ -60,6 +60,13 @@ class DetectionModulesFactory(BaseFactory):
 class LossesFactory(BaseFactory):
     def __init__(self):
         super().__init__(LOSSES)
+
+
+class MetricsFactory(BaseFactory):
+    """`valid_metrics_list` entries (reference: common/factories/metrics_factory.py): a name, `{name: {kwargs}}` or an object."""
+
+    def __init__(self):
+        super().__init__(METRICS)
 
 
 ACTIVATIONS = {"relu": nn.ReLU, "silu": nn.SiLU, "swish": nn.SiLU, "identity": nn.Identity, None: None}

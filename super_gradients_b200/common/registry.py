@@ -27,3 +27,5 @@ LOSSES: Dict[str, Callable] = {}
 register_loss = create_register_decorator(LOSSES)
 CALLBACKS: Dict[str, Callable] = {}
 register_callback = create_register_decorator(CALLBACKS)
+METRICS: Dict[str, Callable] = {}
+register_metric = create_register_decorator(METRICS)

@@ -353,6 +353,40 @@ def preprocess_u8(src, out_slot, dst_hw, pad_tl, pad_value=114.0, max_value=255.
     return out_slot
 
 
+# ------------------------------------------------------------------------------------------------ validation metrics
+def match_desc(preds, targets, crowd, n_thresholds, height, width, top_k, denormalize_targets) -> L.MatchDesc:
+    d = L.MatchDesc()
+    d.B, d.max_preds = preds.shape[0], preds.shape[1]
+    d.max_targets = targets.shape[1]
+    d.max_crowd = 0 if crowd is None else crowd.shape[1]
+    d.n_thresholds, d.top_k = int(n_thresholds), int(top_k)
+    d.denormalize_targets = 1 if denormalize_targets else 0
+    d.height, d.width = float(height), float(width)
+    return d
+
+
+def detection_matching(preds, pred_count, targets, target_count, crowd, crowd_count, thresholds, height, width, top_k=100, denormalize_targets=True):
+    """DetectionMetrics matching of one batch.  preds [B, P, 6] f32 + pred_count [B] int32 (batched_nms' outputs), targets
+    [B, M, 5] f32 rows (class, cx, cy, w, h) + target_count [B], crowd likewise or None, thresholds [T] f32 ascending.
+    Returns (matched, ignore) uint8 [B, P, T]."""
+    require_cuda(preds, "preds")
+    for name, t, dt in (("preds", preds, torch.float32), ("targets", targets, torch.float32), ("thresholds", thresholds, torch.float32), ("pred_count", pred_count, torch.int32), ("target_count", target_count, torch.int32)):
+        if t.dtype != dt or not t.is_contiguous() or t.device != preds.device:
+            raise L.SgbError(f"{name} must be a contiguous {dt} tensor on {preds.device}")
+    if preds.dim() != 3 or preds.shape[2] != 6 or targets.dim() != 3 or targets.shape[2] != 5 or targets.shape[0] != preds.shape[0]:
+        raise L.SgbError("preds must be [B, P, 6] and targets [B, M, 5]")
+    if crowd is not None and (crowd.dtype != torch.float32 or not crowd.is_contiguous() or crowd.dim() != 3 or crowd.shape[2] != 5 or crowd.shape[0] != preds.shape[0] or crowd_count.dtype != torch.int32):
+        raise L.SgbError("crowd targets must be a contiguous float32 [B, C, 5] tensor with int32 counts")
+    if crowd is not None and crowd.shape[1] == 0:
+        crowd = crowd_count = None
+    d = match_desc(preds, targets, crowd, thresholds.numel(), height, width, top_k, denormalize_targets)
+    matched = torch.empty((d.B, d.max_preds, d.n_thresholds), dtype=torch.uint8, device=preds.device)
+    ignore = torch.empty_like(matched)
+    _timed("sgb_detection_matching", ctypes.byref(d), _ptr(preds), _ptr(pred_count), _ptr(targets), _ptr(target_count), _ptr(crowd) if crowd is not None else None,
+           _ptr(crowd_count) if crowd is not None else None, _ptr(thresholds), _ptr(matched), _ptr(ignore), _stream())  # fmt: skip
+    return matched, ignore
+
+
 # ------------------------------------------------------------------------------------------------ batch norm
 def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL) -> L.BnDesc:
     n, c, h, w = x.shape

@@ -91,6 +91,10 @@ class PreprocDesc(Structure):  # SgbPreprocDesc
     )
 
 
+class MatchDesc(Structure):  # SgbMatchDesc
+    _fields_ = [(n, c_int32) for n in ("B", "max_preds", "max_targets", "max_crowd", "n_thresholds", "top_k", "denormalize_targets")] + [("height", c_float), ("width", c_float)]
+
+
 class LossDesc(Structure):
     _fields_ = [
         ("B", c_int32),
@@ -168,6 +172,7 @@ _SIGNATURES = {
     "sgb_dfl_iou_loss_fwd_bwd": (c_int, [POINTER(LossDesc)] + [P] * 8 + [_F, P, P, P]),
     "sgb_loss_finalize": (c_int, [POINTER(LossDesc), P, P, P]),
     "sgb_preprocess_u8": (c_int, [POINTER(PreprocDesc), P, P, P]),
+    "sgb_detection_matching": (c_int, [POINTER(MatchDesc), P, P, P, P, P, P, P, P, P, P]),
     "sgb_pose_tal_workspace_bytes": (c_int64, [POINTER(PoseLossDesc)]),
     "sgb_pose_tal_assign": (c_int, [POINTER(PoseLossDesc)] + [P] * 14 + [_L, P]),
     "sgb_pose_loss_fwd_bwd": (c_int, [POINTER(PoseLossDesc)] + [P] * 12 + [_F] + [P] * 5),

@@ -11,6 +11,7 @@ torchrun, and (optionally) the whole step captured in a CUDA graph.
 Out of scope: hydra recipes, dataset classes, loggers, metrics bookkeeping, QAT/PTQ, KD.
 """
 import datetime
+import inspect
 import math
 import os
 import time
@@ -21,7 +22,7 @@ from torch import nn
 
 from .. import functional as SF
 from .. import kernels as K
-from ..common.factories import LossesFactory
+from ..common.factories import LossesFactory, MetricsFactory, _fuzzy
 from .flat_state import FlatState
 from .utils.callbacks import CallbackHandler, PhaseContext
 
@@ -56,6 +57,9 @@ DEFAULT_TRAINING_PARAMS = {
     "silent_mode": True,
     "sync_bn": False,
     "phase_callbacks": [],
+    "valid_metrics_list": [],  # metric objects with update(...) / compute() / reset(), e.g. training.metrics.DetectionMetrics_050
+    "metric_to_watch": None,  # None: the validation loss; else a key of the metrics' compute() dictionaries (fuzzy-matched like the reference)
+    "greater_metric_to_watch_is_better": False,
     "resume": False,  # continue from <ckpt_root_dir>/<experiment_name>/<ckpt_name> (reference: sg_trainer.py:1877-1935)
     "resume_path": None,  # ... or from an explicit checkpoint file
     "ckpt_name": "ckpt_latest.pth",
@@ -64,6 +68,17 @@ DEFAULT_TRAINING_PARAMS = {
 
 # defaults merged under user optimizer_params (reference: training/params.py:84-90)
 OPTIMIZER_DEFAULTS = {"SGD": {"weight_decay": 1e-4, "momentum": 0.9}, "Adam": {"weight_decay": 1e-4}, "AdamW": {"weight_decay": 1e-2}}
+
+
+def _match_metric_name(wanted: str, available: list) -> str:
+    """metric_to_watch resolution (reference: sg_trainer.py:588-601, fuzzy_idx_in_list): exact name, else the unique name that
+    is equal after dropping case, underscores and punctuation."""
+    if wanted in available:
+        return wanted
+    hits = [a for a in available if _fuzzy(a) == _fuzzy(wanted)]
+    if len(hits) != 1:
+        raise ValueError(f"No match found for `metric_to_watch={wanted}`. Available metrics to monitor are: `{available}`.")
+    return hits[0]
 
 
 def cosine_lr(step: float, total_steps: float, initial_lr: float, final_lr_ratio: float) -> float:
@@ -490,13 +505,16 @@ class Trainer:
                 self.step.swap_ema()  # validate / checkpoint the EMA weights (sg_trainer.py:1566-1569)
                 handler.fire("on_validation_loader_start", context)
                 metrics["valid_loss"] = self._validate(valid_loader, tp, handler, context)
+                metrics.update(self.valid_metric_values)
                 self.history["valid_loss"].append(metrics["valid_loss"])
                 context.update_context(metrics_dict=metrics)
                 handler.fire("on_validation_loader_end", context)
                 self.step.swap_ema()
             if tp["save_model"] and not self.ddp_silent_mode:
-                watch = metrics.get("valid_loss", train_loss)
-                is_best = best is None or watch < best
+                watch, greater = metrics.get("valid_loss", train_loss), False
+                if tp["metric_to_watch"] and "valid_loss" in metrics:
+                    watch, greater = metrics[_match_metric_name(tp["metric_to_watch"], list(metrics))], bool(tp["greater_metric_to_watch_is_better"])
+                is_best = best is None or (watch > best if greater else watch < best)
                 best = watch if is_best else best
                 self._save_checkpoint(epoch, metrics, tp, is_best)
                 if is_best and "valid_loss" in metrics:
@@ -508,8 +526,17 @@ class Trainer:
 
     @torch.no_grad()
     def _validate(self, loader, tp, handler=None, context=None) -> float:
+        """One pass over `loader` in eval mode: mean loss (returned) and the `valid_metrics_list` objects' results
+        (self.valid_metric_values).  As the reference's MetricsUpdateCallback does (callbacks.py:590-597), every metric's update()
+        receives the batch context -- preds, target, inputs, device and the data set's additional batch items such as
+        crowd_targets -- filtered to the arguments it declares."""
         self.net.eval()
         tot, n = 0.0, 0
+        from . import metrics as _registered_metrics  # noqa: F401  (fills the METRICS registry)
+
+        valid_metrics = [MetricsFactory().get(m) for m in (tp.get("valid_metrics_list") or [])]
+        for m in valid_metrics:
+            m.reset()
         for i, batch in enumerate(loader):
             if tp["max_valid_batches"] is not None and i >= int(tp["max_valid_batches"]):
                 break
@@ -527,6 +554,16 @@ class Trainer:
             loss = out[0] if isinstance(out, tuple) else out
             tot += float(loss)
             n += 1
+            if valid_metrics:
+                extra = batch[2] if len(batch) > 2 and isinstance(batch[2], Mapping) else {}
+                fields = {"preds": preds, "target": targets, "inputs": inputs, "device": self.device, **extra}
+                for m in valid_metrics:
+                    accepted = inspect.signature(m.update).parameters
+                    m.update(**{k: v for k, v in fields.items() if k in accepted})
+        self.valid_metric_values = {}
+        for m in valid_metrics:
+            res = m.compute()
+            self.valid_metric_values.update({k: float(v) for k, v in res.items()} if isinstance(res, Mapping) else {type(m).__name__: float(res)})
         self.net.train()
         return tot / max(n, 1)
 

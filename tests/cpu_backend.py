@@ -519,9 +519,16 @@ def preprocess_u8(*args, **kwargs):
     return host_preprocess.preprocess_u8(*args, **kwargs)
 
 
+def detection_matching(*args, **kwargs):
+    """The product header's arithmetic behind a serial host driver (tests/host_detection_match.py)."""
+    import host_detection_match
+
+    return host_detection_match.detection_matching(*args, **kwargs)
+
+
 _SUBSET = dict(conv_fprop=conv_fprop, weight_prepare=weight_prepare, convt2x2_fprop=convt2x2_fprop, nchw_f32_to_nhwc_bf16=nchw_f32_to_nhwc_bf16,
                nhwc_bf16_to_nchw_f32=nhwc_bf16_to_nchw_f32, bn_act_infer=bn_act_infer, maxpool_fwd=maxpool_fwd, axpby=axpby, scale_add=scale_add,
-               dfl_decode=dfl_decode, pose_keypoint_decode=pose_keypoint_decode, batched_nms=batched_nms, preprocess_u8=preprocess_u8)  # fmt: skip
+               dfl_decode=dfl_decode, pose_keypoint_decode=pose_keypoint_decode, batched_nms=batched_nms, preprocess_u8=preprocess_u8, detection_matching=detection_matching)  # fmt: skip
 
 
 def install(monkeypatch):

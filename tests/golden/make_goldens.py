@@ -381,6 +381,81 @@ def golden_processing():
     torch.save(out, os.path.join(HERE, "processing.pt"))
 
 
+def _metric_scene(gen, n_img, n_cls, hw, max_t, max_p, crowd, normalized):
+    """Synthetic NMS output / ground truth of one validation batch: predictions are jittered copies of targets plus clutter."""
+    H, W = hw
+    targets, crowds, output = [], [], []
+    for i in range(n_img):
+        nt = int(torch.randint(0, max_t + 1, (1,), generator=gen))
+        cxcy = torch.rand(nt, 2, generator=gen) * torch.tensor([W, H]) * 0.8 + torch.tensor([W, H]) * 0.1
+        wh = torch.rand(nt, 2, generator=gen) * torch.tensor([W, H]) * 0.3 + 8
+        cls = torch.randint(0, n_cls, (nt, 1), generator=gen).float()
+        t = torch.cat([torch.full((nt, 1), float(i)), cls, cxcy, wh], 1)
+        is_crowd = (torch.rand(nt, generator=gen) < 0.2) if crowd else torch.zeros(nt, dtype=torch.bool)
+        boxes = []
+        for k in range(nt):
+            for _ in range(int(torch.randint(0, 5, (1,), generator=gen))):
+                jit = (torch.rand(4, generator=gen) - 0.5) * torch.tensor([0.3, 0.3, 0.4, 0.4])
+                cx, cy = (t[k, 2:4] + jit[:2] * t[k, 4:6]).tolist()
+                w, h = (t[k, 4:6] * (1 + jit[2:])).tolist()
+                c = t[k, 1].item() if torch.rand(1, generator=gen) < 0.85 else float(torch.randint(0, n_cls, (1,), generator=gen))
+                boxes.append([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2, 0.0, c])
+        n_clutter = int(torch.randint(0, max_p + 1, (1,), generator=gen))
+        for _ in range(n_clutter):
+            x1, y1 = (torch.rand(2, generator=gen) * torch.tensor([W, H]) * 1.1 - 10).tolist()
+            w, h = (torch.rand(2, generator=gen) * 120 + 4).tolist()
+            boxes.append([x1, y1, x1 + w, y1 + h, 0.0, float(torch.randint(0, n_cls, (1,), generator=gen))])
+        p = torch.tensor(boxes, dtype=torch.float32).reshape(-1, 6)
+        if len(p):
+            sc = torch.rand(len(p), generator=gen)
+            p[:, 4] = sc[torch.argsort(sc, descending=True)]  # NMS output is sorted by confidence
+            if len(p) > 3:
+                p[-1, 4] = 0.0  # a zero score is dropped by the top-k selection (nonzero())
+            assert len(torch.unique(p[:, 4])) == len(p)
+        if normalized:
+            t[:, [2, 4]] /= W
+            t[:, [3, 5]] /= H
+        targets.append(t[~is_crowd])
+        crowds.append(t[is_crowd])
+        output.append(p if len(p) and i != 1 else None)  # image 1: "no prediction"
+    return output, torch.cat(targets), torch.cat(crowds)
+
+
+def golden_detection_metrics():
+    """Row (f)-N4: compute_detection_matching (IoUMatching) and compute_detection_metrics on synthetic batches."""
+    from super_gradients.training.utils.detection_utils import IoUMatching, IouThreshold, compute_detection_matching, compute_detection_metrics
+
+    gen = torch.Generator().manual_seed(77)
+    cases = {}
+    specs = {
+        "coco_range_crowd": dict(n_img=6, n_cls=5, hw=(320, 416), max_t=9, max_p=40, crowd=True, normalized=True, top_k=12, thr=IouThreshold.MAP_05_TO_095.to_tensor(), score_thres=0.1),
+        "single_thr_pixels": dict(n_img=4, n_cls=3, hw=(256, 256), max_t=6, max_p=10, crowd=False, normalized=False, top_k=100, thr=torch.tensor([0.5]), score_thres=0.3),
+        "dense": dict(n_img=3, n_cls=2, hw=(640, 640), max_t=30, max_p=150, crowd=True, normalized=True, top_k=100, thr=IouThreshold.MAP_05_TO_095.to_tensor(), score_thres=0.05),
+    }
+    for name, sp in specs.items():
+        batches = []
+        info = []
+        for b in range(2):
+            output, targets, crowds = _metric_scene(gen, sp["n_img"], sp["n_cls"], sp["hw"], sp["max_t"], sp["max_p"], sp["crowd"], sp["normalized"])
+            res = compute_detection_matching(
+                [None if o is None else o.clone() for o in output], targets.clone(), sp["hw"][0], sp["hw"][1], denormalize_targets=sp["normalized"], device="cpu",
+                iou_thresholds=sp["thr"], crowd_targets=crowds.clone() if sp["crowd"] else None, top_k=sp["top_k"], matching_strategy=IoUMatching(sp["thr"]),
+            )
+            info += res
+            batches.append({"output": output, "targets": targets, "crowd_targets": crowds if sp["crowd"] else None, "matching": [tuple(t.clone() for t in r) for r in res]})
+        cat = [torch.cat(x, 0) for x in zip(*info)]
+        # the recall grid is an input of the golden: torch.linspace's last bit depends on the CPU's SIMD width, and a recall of
+        # exactly k / n_targets can sit on a grid point
+        recall_thresholds = torch.linspace(0, 1, 101)
+        ap, prec, rec, f1, classes, best, best_cls = compute_detection_metrics(*cat, device="cpu", score_threshold=sp["score_thres"], recall_thresholds=recall_thresholds)
+        cases[name] = {
+            "hw": sp["hw"], "top_k": sp["top_k"], "iou_thresholds": sp["thr"], "normalized": sp["normalized"], "score_thres": sp["score_thres"], "n_cls": sp["n_cls"], "recall_thresholds": recall_thresholds,
+            "batches": batches, "metrics": {"ap": ap, "precision": prec, "recall": rec, "f1": f1, "classes": classes, "best_score_threshold": best, "best_per_cls": best_cls},
+        }
+        print(name, "preds", len(cat[0]), "matched@thr0", int(cat[0][:, 0].sum()), "ignored", int(cat[1][:, 0].sum()), "mAP", float(ap.mean()))
+    torch.save(cases, os.path.join(HERE, "detection_metrics.pt"))
+
+
 def golden_lr_schedules():
     """LR actually in the optimizer at every optimisation step, produced by the reference's own warm-up / scheduler callbacks driven in
     the order of Trainer._train_epoch (epoch-start callbacks, per batch: batch-start callbacks -> optimizer step -> TRAIN_BATCH_STEP
@@ -623,7 +698,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

@@ -733,3 +733,46 @@ def test_phase_callbacks_fire_in_the_reference_order(golden, monkeypatch, tmp_pa
     assert names == (["on_training_start", "on_train_loader_start"] + per_batch * 2 + ["on_train_loader_end", "on_validation_loader_start", "on_validation_batch_start",
                      "on_validation_batch_end", "on_validation_loader_end", "PHASE_VALIDATION_EPOCH_END", "on_training_end"])  # fmt: skip
     assert [e[2] for e in events if e[0] == "on_train_batch_start"] == [0, 1] and np.isfinite(events[-2][2])
+
+
+def test_trainer_validation_metrics_and_metric_to_watch(golden, monkeypatch, tmp_path):
+    """valid_metrics_list / metric_to_watch / greater_metric_to_watch_is_better (row (f)-N4): the Trainer feeds each validation
+    batch to DetectionMetrics (NMS callback's batched output -> matching kernel stand-in), reports compute()'s keys next to the
+    loss, selects ckpt_best by the watched metric, and the numbers equal the oracle's matching + summary on the same predictions."""
+    from oracle import sg_oracle as O
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.losses import PPYoloELoss
+    from super_gradients_b200.training.models.detection_models.pp_yolo_e.post_prediction_callback import PPYoloEPostPredictionCallback
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.sg_trainer import Trainer
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("tiny_yolo_nas")
+    ap = copy.deepcopy(g["arch"])
+    model = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    model.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+    callback = PPYoloEPostPredictionCallback(score_threshold=0.01, nms_threshold=0.7, nms_top_k=200, max_predictions=50)
+    loader = [(g["x"], g["targets"]), (g["x"].flip(0), g["targets"])]
+    tp = dict(max_epochs=2, initial_lr=1e-3, lr_mode="constant", optimizer="SGD", loss=PPYoloELoss(num_classes=4, use_static_assigner=False), save_model=True,
+              valid_metrics_list=[{"DetectionMetrics_050": {"num_cls": 4, "post_prediction_callback": callback, "normalize_targets": True, "score_thres": 0.01}}],
+              metric_to_watch="map@0.50", greater_metric_to_watch_is_better=True)  # fmt: skip
+    trainer = Trainer("metrics", ckpt_root_dir=str(tmp_path))
+    trainer.train(model, tp, loader[:1], valid_loader=loader)
+    ck = torch.load(tmp_path / "metrics" / "ckpt_latest.pth", weights_only=False)
+    assert {"valid_loss", "mAP@0.50", "Precision@0.50", "Recall@0.50", "F1@0.50", "Best_score_threshold"} <= set(ck["metrics"])
+    # the same predictions through the oracle
+    model.eval()
+    info = []
+    with torch.no_grad():
+        for x, t in loader:
+            rows = callback(model(x))
+            info += O.detection_matching([r.numpy() for r in rows], t.numpy(), x.shape[2], x.shape[3], np.array([0.5], np.float32), None, 100, False)
+    assert sum(len(i[0]) for i in info) > 0
+    cat = [np.concatenate(c, 0) for c in zip(*info)]
+    ap_, prec, rec, f1, classes, best, _ = O.detection_metrics(*cat, score_threshold=0.01)
+    m = ck["metrics"]
+    assert m["mAP@0.50"] == pytest.approx(float(ap_.mean()), abs=1e-6) and m["Recall@0.50"] == pytest.approx(float(rec.mean()), abs=1e-6)
+    assert m["Precision@0.50"] == pytest.approx(float(prec.mean()), abs=1e-6) and m["F1@0.50"] == pytest.approx(float(f1.mean()), abs=1e-6)
+    with pytest.raises(ValueError, match="metric_to_watch"):
+        sg_trainer._match_metric_name("accuracy", list(m))

@@ -263,3 +263,58 @@ def test_split_graph_replay_matches_eager(golden, monkeypatch):
         lb, _ = sb.run(x, t)
         assert abs(float(la) - float(lb)) <= 2e-2 * abs(float(la)), (i, float(la), float(lb))
     assert rel(sb.flat.params, sa.flat.params) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ row (f)-N4: DetectionMetrics matching
+@pytest.mark.parametrize("case", ["coco_range_crowd", "single_thr_pixels", "dense"])
+def test_detection_matching_kernel_vs_reference_golden(golden, case):
+    """sgb_detection_matching through the C-ABI against compute_detection_matching's outputs, bit for bit."""
+    from super_gradients_b200 import kernels as K
+    from super_gradients_b200.training.utils import detection_utils as DU
+
+    c = golden("detection_metrics")[case]
+    for batch in c["batches"]:
+        rows, counts = DU.pad_predictions(batch["output"], DEV)
+        matched, ignore = DU.compute_detection_matching(rows, counts, batch["targets"], c["hw"][0], c["hw"][1], c["iou_thresholds"], c["normalized"], batch["crowd_targets"], c["top_k"])
+        for b, ref in enumerate(batch["matching"]):
+            n = int(counts[b])
+            assert torch.equal(matched[b, :n].bool().cpu(), ref[0]) and torch.equal(ignore[b, :n].bool().cpu(), ref[1]), (case, b)
+            assert not matched[b, n:].any() and not ignore[b, n:].any()
+    assert K is not None
+
+
+def test_detection_matching_kernel_validation_batch_size():
+    """A COCO-sized validation batch (64 images x 300 predictions x up to 90 targets, 80 classes, 10 thresholds) against the
+    oracle, and the whole DetectionMetrics object on the device against the oracle's summary."""
+    import numpy as np
+
+    from super_gradients_b200.training.metrics import DetectionMetrics
+    from super_gradients_b200.training.utils import detection_utils as DU
+
+    gen = torch.Generator().manual_seed(3)
+    B, Hh, Ww, n_cls = 64, 640, 640, 80
+    out, tg = [], []
+    for b in range(B):
+        nt = int(torch.randint(1, 90, (1,), generator=gen))
+        c = torch.rand(nt, 2, generator=gen) * 600 + 20
+        wh = torch.rand(nt, 2, generator=gen) * 150 + 10
+        t = torch.cat([torch.full((nt, 1), float(b)), torch.randint(0, n_cls, (nt, 1), generator=gen).float(), c, wh], 1)
+        tg.append(t)
+        rep = t[torch.randint(0, nt, (300,), generator=gen)]
+        jit = (torch.rand(300, 4, generator=gen) - 0.5) * 0.3
+        cx, cy = rep[:, 2] + jit[:, 0] * rep[:, 4], rep[:, 3] + jit[:, 1] * rep[:, 5]
+        w, h = rep[:, 4] * (1 + jit[:, 2]), rep[:, 5] * (1 + jit[:, 3])
+        p = torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2, torch.rand(300, generator=gen), rep[:, 1]], 1)
+        out.append(p[torch.argsort(p[:, 4], descending=True)])
+    targets = torch.cat(tg)
+    metric = DetectionMetrics(num_cls=n_cls, post_prediction_callback=None, normalize_targets=True, top_k_predictions=100)
+    metric.update([o.to(DEV) for o in out], targets, device=DEV, inputs=torch.zeros(1, 1, 1, 1, device=DEV).expand(B, 3, Hh, Ww))
+    res = metric.compute()
+    thr = np.linspace(0.5, 0.95, 10, dtype=np.float32)
+    ref = O.detection_matching([o.numpy() for o in out], targets.numpy(), Hh, Ww, metric.iou_thresholds.numpy(), None, 100, False)
+    _rows, _counts, matched, ignore, _t = metric._batches[0]
+    for b in range(B):
+        assert np.array_equal(matched[b].bool().cpu().numpy(), ref[b][0]) and np.array_equal(ignore[b].bool().cpu().numpy(), ref[b][1]), b
+    cat = [np.concatenate(x, 0) for x in zip(*ref)]
+    ap = O.detection_metrics(*cat, score_threshold=0.1)[0]
+    assert abs(res["mAP@0.50:0.95"] - float(ap.mean())) < 1e-6 and res["mAP@0.50:0.95"] > 0.05 and len(thr) == 10
