@@ -668,8 +668,10 @@ def test_resnet_imagenet_variants_wire_up(monkeypatch, name, shape):
 def test_trainer_accepts_the_shipped_yolo_nas_recipe_dict(golden, monkeypatch, tmp_path):
     """The training hyper-parameters of the reference's coco2017_yolo_nas_train_params.yaml (recipes/training_hyperparams), as the
     dict hydra would hand to Trainer.train(): registry-built loss with criterion_params, LinearBatchLRWarmup + CosineLRScheduler, AdamW,
-    threshold EMA, sync_bn: True (a no-op on one device), metric bookkeeping keys that this mirror ignores."""
+    threshold EMA, sync_bn: True (a no-op on one device), the DetectionMetrics_050_095 entry of valid_metrics_list with its
+    PPYoloEPostPredictionCallback and metric_to_watch on its mAP key."""
     from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.models.detection_models.pp_yolo_e import PPYoloEPostPredictionCallback
     from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
     from super_gradients_b200.training.sg_trainer import Trainer
 
@@ -682,13 +684,18 @@ def test_trainer_accepts_the_shipped_yolo_nas_recipe_dict(golden, monkeypatch, t
     recipe = dict(max_epochs=2, warmup_mode="LinearBatchLRWarmup", warmup_initial_lr=1e-6, lr_warmup_steps=3, lr_warmup_epochs=0, initial_lr=2e-4, lr_mode="CosineLRScheduler",
                   cosine_final_lr_ratio=0.1, zero_weight_decay_on_bias_and_bn=True, batch_accumulate=1, save_ckpt_epoch_list=[100, 200, 250], loss="PPYoloELoss",
                   criterion_params={"use_static_assigner": False, "num_classes": 4}, optimizer="AdamW", optimizer_params={"weight_decay": 0.00001}, ema=True,
-                  ema_params={"decay": 0.9997, "decay_type": "threshold"}, mixed_precision=False, sync_bn=True, valid_metrics_list=[], pre_prediction_callback=None,
+                  ema_params={"decay": 0.9997, "decay_type": "threshold"}, mixed_precision=False, sync_bn=True, pre_prediction_callback=None,
+                  valid_metrics_list=[{"DetectionMetrics_050_095": {"score_thres": 0.1, "top_k_predictions": 300, "num_cls": 4, "normalize_targets": True,
+                                                                   "post_prediction_callback": PPYoloEPostPredictionCallback(score_threshold=0.01, nms_top_k=1000, max_predictions=300, nms_threshold=0.7)}}],
                   metric_to_watch="mAP@0.50:0.95", greater_metric_to_watch_is_better=True)  # fmt: skip
     tr = Trainer("recipe", ckpt_root_dir=str(tmp_path))
     hist = tr.train(m, recipe, [(g["x"], g["targets"])] * 2, valid_loader=[(g["x"], g["targets"])])
     assert len(hist["train_loss"]) == 2 and all(np.isfinite(hist["train_loss"])) and len(hist["valid_loss"]) == 2
     np.testing.assert_allclose(hist["lr"][:2], [1e-6, 2e-4], rtol=1e-12)  # LinearBatchLRWarmup capped at the loader length (2 steps here)
     assert max(hist["lr"]) <= 2e-4 and tr.step.opt_name == "AdamW" and tr.step.ema_on
+    assert {"mAP@0.50:0.95", "Recall@0.50:0.95", "valid_loss"} <= set(tr.valid_metric_values) | {"valid_loss"}
+    with pytest.raises(ValueError, match="metric_to_watch"):  # the reference raises too when the watched metric is not produced (sg_trainer.py:588-593)
+        Trainer("recipe2", ckpt_root_dir=str(tmp_path)).train(m, {**recipe, "valid_metrics_list": []}, [(g["x"], g["targets"])], valid_loader=[(g["x"], g["targets"])])
 
 
 def test_phase_callbacks_fire_in_the_reference_order(golden, monkeypatch, tmp_path):
