@@ -241,6 +241,16 @@ int sgb_tal_assign(const SgbLossDesc* d, const float* cls_logits, const float* r
                    int32_t* assigned_label, float* assigned_box, float* assigned_score, double* sums, void* workspace,
                    int64_t workspace_bytes, void* stream);
 int64_t sgb_tal_workspace_bytes(const SgbLossDesc* d);
+/* ATSS assigner (ppyolo_loss.py:301-434 the way PPYoloELoss calls it, :810-820: topk = d->topk (9) per pyramid level,
+ * force_gt_matching = False, scores = IoU(gt, predicted box)).  anchors [L, 4] xyxy pixels (the head's anchor boxes);
+ * level_sizes: HOST array [n_levels <= 8] (num_anchors_list; sums to L, each >= topk <= 16).  d->alpha / beta are unused.
+ * Outputs exactly as sgb_tal_assign, including sum(assigned_score) added into sums[3].  Equal centre distances are ordered
+ * by anchor index. */
+int sgb_atss_assign(const SgbLossDesc* d, const float* reg_distri, const float* anchors, const float* anchor_points,
+                    const float* stride_tensor, const int32_t* level_sizes, int32_t n_levels, const float* gt_boxes,
+                    const int32_t* gt_labels, const uint8_t* gt_valid, int32_t* assigned_label, float* assigned_box,
+                    float* assigned_score, double* sums, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t sgb_atss_workspace_bytes(const SgbLossDesc* d);
 /* Varifocal + GIoU/CIoU + DFL loss, forward and backward in one launch (ppyolo_loss.py:944-1084).
  * sums [4] doubles: sgb_tal_assign has already added sum(assigned_score) into sums[3] (the normaliser, clipped at 1);
  * this call adds {cls_sum, iou_sum, dfl_sum} into sums[0..2] and writes the FINAL gradients of

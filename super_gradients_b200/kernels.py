@@ -610,6 +610,24 @@ def tal_assign(d, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes
     return al, ab, asc
 
 
+def atss_assign(d, reg_distri, anchors, anchor_points, stride_tensor, level_sizes, gt_boxes, gt_labels, gt_valid, sums):
+    """ATSS assignment with tal_assign's outputs.  anchors [L, 4] f32 anchor boxes, level_sizes = the head's num_anchors_list
+    (host ints); d.topk = candidates per level (9)."""
+    dev = reg_distri.device
+    require_cuda(reg_distri, "reg_distri")
+    if anchors.dtype != torch.float32 or not anchors.is_contiguous() or anchors.shape != (d.L, 4):
+        raise L.SgbError("anchors must be a contiguous float32 [L, 4] tensor")
+    al = torch.empty((d.B, d.L), dtype=torch.int32, device=dev)
+    ab = torch.empty((d.B, d.L, 4), dtype=torch.float32, device=dev)
+    asc = torch.empty((d.B, d.L), dtype=torch.float32, device=dev)
+    nbytes = L.load().sgb_atss_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    lv = (ctypes.c_int32 * len(level_sizes))(*[int(v) for v in level_sizes])
+    _timed("sgb_atss_assign", ctypes.byref(d), _ptr(reg_distri), _ptr(anchors), _ptr(anchor_points), _ptr(stride_tensor), lv, len(level_sizes), _ptr(gt_boxes), _ptr(gt_labels),
+           _ptr(gt_valid), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), _ptr(ws), nbytes, _stream())  # fmt: skip
+    return al, ab, asc
+
+
 def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
     gc = torch.empty_like(cls_logits) if want_grad else None
     gr = torch.empty_like(reg_distri) if want_grad else None

@@ -169,6 +169,8 @@ _SIGNATURES = {
     "sgb_pose_keypoint_decode": (c_int, [P, _I, P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, P, P, P, P]),
     "sgb_tal_assign": (c_int, [POINTER(LossDesc)] + [P] * 12 + [_L, P]),
     "sgb_tal_workspace_bytes": (c_int64, [POINTER(LossDesc)]),
+    "sgb_atss_assign": (c_int, [POINTER(LossDesc)] + [P] * 5 + [c_int32] + [P] * 7 + [P, _L, P]),
+    "sgb_atss_workspace_bytes": (c_int64, [POINTER(LossDesc)]),
     "sgb_dfl_iou_loss_fwd_bwd": (c_int, [POINTER(LossDesc)] + [P] * 8 + [_F, P, P, P]),
     "sgb_loss_finalize": (c_int, [POINTER(LossDesc), P, P, P]),
     "sgb_preprocess_u8": (c_int, [POINTER(PreprocDesc), P, P, P]),
@@ -188,7 +190,7 @@ _SIGNATURES = {
 _lib = None
 
 # kernels launched by one call of each entry point (default 1); LAUNCHES[0] accumulates them (bench.py: gpu_launches)
-LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_pose_tal_assign": 4, "sgb_sm100_launches": 0, "sgb_sm100_halo_launches": 0, "sgb_debug_read_trace": 0, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
+LAUNCH_COUNT = {"sgb_tal_assign": 4, "sgb_atss_assign": 3, "sgb_pose_tal_assign": 4, "sgb_sm100_launches": 0, "sgb_sm100_halo_launches": 0, "sgb_debug_read_trace": 0, "sgb_last_error": 0, "sgb_version": 0, "sgb_check_device": 0}
 LAUNCHES = [0]
 
 

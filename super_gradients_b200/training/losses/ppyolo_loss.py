@@ -42,10 +42,14 @@ def pad_targets_host(targets: Tensor, batch_size: int, n_max: int) -> Tuple[Tens
 
 class _FusedDetectionLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, desc, sync):
+    def forward(ctx, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, desc, sync, static=None):
+        """static: None (task-aligned assigner) or (anchor boxes [L, 4], num_anchors_list) for the ATSS assigner."""
         cls_logits, reg_distri = cls_logits.contiguous().float(), reg_distri.contiguous().float()
         sums = torch.zeros(4, dtype=torch.float64, device=cls_logits.device)
-        al, ab, asc = K.tal_assign(desc, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, sums)
+        if static is None:
+            al, ab, asc = K.tal_assign(desc, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, sums)
+        else:
+            al, ab, asc = K.atss_assign(desc, reg_distri, static[0], anchor_points, stride_tensor, static[1], gt_boxes, gt_labels, gt_valid, sums)
         if sync:
             import torch.distributed as dist
 
@@ -59,7 +63,7 @@ class _FusedDetectionLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gitems):
         gc, gr = ctx.saved_tensors
-        return gc * gloss, gr * gloss, None, None, None, None, None, None, None
+        return gc * gloss, gr * gloss, None, None, None, None, None, None, None, None
 
 
 @register_loss(name="PPYoloELoss", deprecated_name="ppyoloe_loss")
@@ -81,8 +85,7 @@ class PPYoloELoss(nn.Module):
         super().__init__()
         if not use_varifocal_loss:
             raise NotImplementedError("focal classification loss is not implemented (YOLO-NAS recipes use varifocal)")
-        self.use_static_assigner = use_static_assigner
-        self._warned_static = False
+        self.use_static_assigner = use_static_assigner  # ATSS (topk 9 per level) instead of the task-aligned assigner (:681-683)
         self.num_classes = num_classes
         self.classification_loss_weight = classification_loss_weight
         self.iou_loss_weight = iou_loss_weight
@@ -97,13 +100,11 @@ class PPYoloELoss(nn.Module):
         return ["loss_cls", "loss_iou", "loss_dfl", "loss"]
 
     def forward(self, outputs: Union[Tuple, Tuple[Tuple[Tensor, Tensor], Tuple]], targets: Tensor) -> Tuple[Tensor, Tensor]:
-        if self.use_static_assigner:
-            raise NotImplementedError("ATSS (use_static_assigner=True) has no sm_100a kernel; YOLO-NAS trains with use_static_assigner=False")
         if isinstance(outputs, tuple) and len(outputs) == 2:
             _, predictions = outputs
         else:
             predictions = outputs
-        cls_logits, reg_distri, _anchors, anchor_points, _num_anchors_list, stride_tensor = predictions
+        cls_logits, reg_distri, anchors, anchor_points, num_anchors_list, stride_tensor = predictions
         K.require_cuda(cls_logits, "predictions")
         B, L, C = cls_logits.shape
         reg_max = reg_distri.shape[-1] // 4 - 1
@@ -120,7 +121,9 @@ class PPYoloELoss(nn.Module):
             n_max = self._n_max
             gt_boxes, gt_labels, gt_valid = pad_targets_host(t, B, max(n_max, 1))
             gt_boxes, gt_labels, gt_valid = gt_boxes.to(dev, non_blocking=True), gt_labels.to(dev, non_blocking=True), gt_valid.to(dev, non_blocking=True)
-        desc = K.loss_desc(B, L, C, reg_max, n_max, w_cls=self.classification_loss_weight, w_iou=self.iou_loss_weight, w_dfl=self.dfl_loss_weight, iou_type=self.iou_type)
+        desc = K.loss_desc(B, L, C, reg_max, n_max, topk=9 if self.use_static_assigner else 13, w_cls=self.classification_loss_weight, w_iou=self.iou_loss_weight,
+                           w_dfl=self.dfl_loss_weight, iou_type=self.iou_type)  # fmt: skip
         sync = self.sync_normaliser and torch.distributed.is_available() and torch.distributed.is_initialized()
-        loss, items = _FusedDetectionLoss.apply(cls_logits, reg_distri, anchor_points, stride_tensor.reshape(-1).contiguous(), gt_boxes, gt_labels, gt_valid, desc, sync)
+        static = (anchors.detach().float().contiguous(), [int(v) for v in num_anchors_list]) if self.use_static_assigner else None
+        loss, items = _FusedDetectionLoss.apply(cls_logits, reg_distri, anchor_points, stride_tensor.reshape(-1).contiguous(), gt_boxes, gt_labels, gt_valid, desc, sync, static)
         return loss, items.detach()

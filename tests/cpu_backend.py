@@ -401,6 +401,13 @@ def tal_assign(d, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes
     return lab.int(), box, score.sum(-1)
 
 
+def atss_assign(*args, **kwargs):
+    """The product header's arithmetic behind a serial host driver (tests/host_atss.py)."""
+    import host_atss
+
+    return host_atss.atss_assign(*args, **kwargs)
+
+
 def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
     C, reg_max = d.ncls, d.reg_max
     st = stride_tensor.view(-1, 1)
@@ -508,7 +515,7 @@ def pose_loss(d, cls_logits, reg_distri, pose_coords, pose_logits, anchor_points
 _TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgrad_to_oihw, weight_prepare_batch=weight_prepare_batch,
                  run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch,
                  bn_act_fwd=bn_act_fwd, bn_act_bwd=bn_act_bwd, channel_stats=channel_stats, channel_dot=channel_dot, qarep_fwd=qarep_fwd, qarep_bwd=qarep_bwd,
-                 maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,
+                 maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, atss_assign=atss_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,
                  adamw_step=adamw_step, ema_update=ema_update, pose_tal_assign=pose_tal_assign, pose_loss=pose_loss, avgpool_fwd=avgpool_fwd, avgpool_bwd=avgpool_bwd)  # fmt: skip
 
 

@@ -191,6 +191,51 @@ def golden_loss():
     torch.save(out, os.path.join(HERE, "loss.pt"))
 
 
+def golden_atss():
+    """Rows L2 (alt) : ATSSAssigner and PPYoloELoss(use_static_assigner=True) on a 128 x 128 input (levels of 256 / 64 / 16 anchors:
+    every level holds at least topk = 9 anchors, which torch.topk needs)."""
+    from super_gradients.training.losses.ppyolo_loss import ATSSAssigner, PPYoloELoss
+    from super_gradients.training.models.detection_models.pp_yolo_e.pp_yolo_head import generate_anchors_for_grid_cell
+
+    gen = torch.Generator().manual_seed(9)
+    B, C, reg_max = 3, 5, 16
+    feats = [torch.zeros(B, 1, 16, 16), torch.zeros(B, 1, 8, 8), torch.zeros(B, 1, 4, 4)]
+    anchors, anchor_points, nums, stride_tensor = generate_anchors_for_grid_cell(feats, (8, 16, 32), 5.0, 0.5)
+    L = sum(nums)
+    out = {"anchors": anchors, "anchor_points": anchor_points, "nums": nums, "stride_tensor": stride_tensor}
+    for case, n_per_img in [("regular", [4, 2, 6]), ("ragged_with_empty", [7, 0, 1]), ("no_targets", [0, 0, 0]), ("crowded", [12, 9, 10])]:
+        cls_logits = (torch.randn(B, L, C, generator=gen) * 2.0).requires_grad_(True)
+        # predicted distances concentrated around 2.5 strides (the anchor box half-size) so that IoU(gt, prediction) is not negligible
+        reg_distri = (torch.randn(B, L, 4 * (reg_max + 1), generator=gen) * 1.0)
+        reg_distri[..., 2::17] += 2.0
+        reg_distri[..., 3::17] += 2.0
+        reg_distri.requires_grad_(True)
+        rows = []
+        for b, n in enumerate(n_per_img):
+            for _ in range(n):
+                cx, cy = (torch.rand(2, generator=gen) * 96 + 16).tolist()
+                w, h = (torch.rand(2, generator=gen) * (70 if case != "crowded" else 40) + 10).tolist()
+                rows.append([b, int(torch.randint(0, C, (1,), generator=gen)), cx, cy, w, h])
+        targets = torch.tensor(rows, dtype=torch.float32).reshape(-1, 6)
+        crit = PPYoloELoss(num_classes=C, use_static_assigner=True)
+        raw = (cls_logits, reg_distri, anchors, anchor_points, nums, stride_tensor)
+        loss, items = crit(raw, targets)
+        loss.backward()
+        with torch.no_grad():
+            t = crit._get_targets_for_batched_assigner(targets, batch_size=B)
+            pred_bboxes, _, _ = crit._bbox_decode(anchor_points / stride_tensor, reg_distri)
+            al, ab, asc = ATSSAssigner(topk=9, num_classes=C)(
+                anchor_bboxes=anchors, num_anchors_list=nums, gt_labels=t["gt_class"], gt_bboxes=t["gt_bbox"], pad_gt_mask=t["pad_gt_mask"], bg_index=C,
+                pred_bboxes=pred_bboxes * stride_tensor,
+            )  # fmt: skip
+        out[case] = dict(
+            cls_logits=cls_logits.detach(), reg_distri=reg_distri.detach(), targets=targets, loss=loss.detach(), items=items.detach(), g_cls=cls_logits.grad.clone(),
+            g_reg=reg_distri.grad.clone(), assigned_labels=al, assigned_bboxes=ab, assigned_scores=asc, gt_class=t["gt_class"], gt_bbox=t["gt_bbox"], pad_gt_mask=t["pad_gt_mask"].float(),
+        )  # fmt: skip
+        print(case, "positives", int((al != C).sum()), "loss", float(loss), "score sum", float(asc.sum()))
+    torch.save(out, os.path.join(HERE, "atss.pt"))
+
+
 def golden_pose_nms():
     """YoloNASPosePostPredictionCallback of the unmodified reference on seeded decoded pose outputs."""
     from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_post_prediction_callback import YoloNASPosePostPredictionCallback
@@ -698,7 +743,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "atss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

@@ -318,3 +318,63 @@ def test_detection_matching_kernel_validation_batch_size():
     cat = [np.concatenate(x, 0) for x in zip(*ref)]
     ap = O.detection_metrics(*cat, score_threshold=0.1)[0]
     assert abs(res["mAP@0.50:0.95"] - float(ap.mean())) < 1e-6 and res["mAP@0.50:0.95"] > 0.05 and len(thr) == 10
+
+
+# ------------------------------------------------------------------------------------------------ row L2 (static assigner): ATSS
+@pytest.mark.parametrize("case", ["regular", "ragged_with_empty", "no_targets", "crowded"])
+def test_atss_assigner_and_static_ppyoloe_loss_vs_reference_golden(golden, case):
+    """sgb_atss_assign + the fused loss kernel behind PPYoloELoss(use_static_assigner=True) against the reference's recorded
+    assignment, loss, components and gradients."""
+    from super_gradients_b200 import kernels as K
+    from super_gradients_b200.training.losses.ppyolo_loss import PPYoloELoss, pad_targets_host
+
+    g = golden("atss")
+    c, C = g[case], 5
+    B, L, _ = c["cls_logits"].shape
+    n_max = c["gt_bbox"].shape[1]
+    if n_max:
+        gt_boxes, gt_labels, gt_valid = (t.to(DEV) for t in pad_targets_host(c["targets"], B, n_max))
+        sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+        al, ab, asc = K.atss_assign(K.loss_desc(B, L, C, 16, n_max, topk=9), c["reg_distri"].to(DEV), g["anchors"].to(DEV).contiguous(), g["anchor_points"].to(DEV),
+                                    g["stride_tensor"].reshape(-1).to(DEV), g["nums"], gt_boxes, gt_labels, gt_valid, sums)  # fmt: skip
+        assert torch.equal(al.long().cpu(), c["assigned_labels"])
+        torch.testing.assert_close(asc.cpu(), c["assigned_scores"].sum(-1), rtol=1e-4, atol=1e-5)
+        assert float(sums[3]) == pytest.approx(float(c["assigned_scores"].sum()), rel=1e-4)
+    cls_logits, reg_distri = c["cls_logits"].to(DEV).requires_grad_(True), c["reg_distri"].to(DEV).requires_grad_(True)
+    crit = PPYoloELoss(num_classes=C, use_static_assigner=True)
+    loss, items = crit((cls_logits, reg_distri, g["anchors"].to(DEV), g["anchor_points"].to(DEV), g["nums"], g["stride_tensor"].to(DEV)), c["targets"])
+    loss.backward()
+    torch.testing.assert_close(loss.detach().cpu(), c["loss"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(items.cpu(), c["items"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(cls_logits.grad.cpu(), c["g_cls"], rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(reg_distri.grad.cpu(), c["g_reg"], rtol=1e-3, atol=1e-5)
+
+
+def test_atss_assigner_at_training_size():
+    """YOLO-NAS geometry (640 x 640: 6400 + 1600 + 400 anchors), 32 images x up to 20 boxes, against the oracle."""
+    from super_gradients_b200 import kernels as K
+    from super_gradients_b200.training.losses.ppyolo_loss import pad_targets_host
+
+    gen = torch.Generator().manual_seed(4)
+    B, C = 32, 80
+    anchors, anchor_points, nums, stride_tensor = O.anchors_for_levels([(80, 80), (40, 40), (20, 20)], (8, 16, 32))
+    L = sum(nums)
+    rows = []
+    for b in range(B):
+        for _ in range(int(torch.randint(0, 21, (1,), generator=gen))):
+            cx, cy = (torch.rand(2, generator=gen) * 540 + 50).tolist()
+            w, h = (torch.rand(2, generator=gen) * 250 + 12).tolist()
+            rows.append([b, int(torch.randint(0, C, (1,), generator=gen)), cx, cy, w, h])
+    targets = torch.tensor(rows, dtype=torch.float32)
+    reg = torch.randn(B, L, 68, generator=gen)
+    gt_boxes, gt_labels, gt_valid = pad_targets_host(targets, B, 20)
+    sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+    al, ab, asc = K.atss_assign(K.loss_desc(B, L, C, 16, 20, topk=9), reg.to(DEV), anchors.to(DEV).contiguous(), anchor_points.to(DEV), stride_tensor.reshape(-1).to(DEV), nums,
+                                gt_boxes.to(DEV), gt_labels.to(DEV), gt_valid.to(DEV), sums)  # fmt: skip
+    pred = O.bbox_decode(anchor_points / stride_tensor, reg) * stride_tensor
+    rl, rb, rs = O.atss_assign(anchors, nums, gt_labels.long(), gt_boxes, gt_valid.float().unsqueeze(-1), C, pred)
+    assert torch.equal(al.long().cpu(), rl) and (rl != C).sum() > 1000
+    torch.testing.assert_close(asc.cpu(), rs.sum(-1), rtol=1e-4, atol=1e-5)
+    pos = rl != C
+    torch.testing.assert_close(ab.cpu()[pos], rb[pos], rtol=0, atol=1e-4)
+
