@@ -259,6 +259,12 @@ int sgb_dfl_iou_loss_fwd_bwd(const SgbLossDesc* d, const float* cls_logits, cons
                              const float* anchor_points, const float* stride_tensor, const int32_t* assigned_label,
                              const float* assigned_box, const float* assigned_score, double* sums, float grad_scale,
                              float* grad_cls, float* grad_reg, void* stream);
+/* Focal classification term (PPYoloELoss use_varifocal_loss=False: ppyolo_loss.py:1069-1077; alpha = 0.25 behind the ATSS
+ * assigner, <= 0 (no alpha_t) behind the task-aligned one, :821/:833).  Call AFTER sgb_dfl_iou_loss_fwd_bwd and before
+ * sgb_loss_finalize: replaces sums[0] by the focal sum and grad_cls by the focal term's final gradient. */
+int sgb_focal_cls_fwd_bwd(const SgbLossDesc* d, const float* cls_logits, const int32_t* assigned_label,
+                          const float* assigned_score, double* sums, float grad_scale, float alpha, float* grad_cls,
+                          void* stream);
 /* loss_out [4] = {cls, iou, dfl, total} (weighted, normalised) -- the reference's log_losses. */
 int sgb_loss_finalize(const SgbLossDesc* d, const double* sums, float* loss_out, void* stream);
 /* d(raw fp32 logits [N, L, gC]) -> bf16 NHWC head-output gradient of one level (rows anchor_base..+HW). */

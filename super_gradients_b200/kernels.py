@@ -628,10 +628,14 @@ def atss_assign(d, reg_distri, anchors, anchor_points, stride_tensor, level_size
     return al, ab, asc
 
 
-def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
+def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True, focal_alpha=None):
+    """focal_alpha: None = varifocal classification term (the fused kernel's); a float = focal term with that alpha (<= 0: no
+    alpha_t), computed by a replacement pass after the fused kernel."""
     gc = torch.empty_like(cls_logits) if want_grad else None
     gr = torch.empty_like(reg_distri) if want_grad else None
     _timed("sgb_dfl_iou_loss_fwd_bwd", ctypes.byref(d), _ptr(cls_logits), _ptr(reg_distri), _ptr(anchor_points), _ptr(stride_tensor), _ptr(al), _ptr(ab), _ptr(asc), _ptr(sums), float(grad_scale), _ptr(gc), _ptr(gr), _stream())
+    if focal_alpha is not None:
+        _timed("sgb_focal_cls_fwd_bwd", ctypes.byref(d), _ptr(cls_logits), _ptr(al), _ptr(asc), _ptr(sums), float(grad_scale), float(focal_alpha), _ptr(gc), _stream())
     out = torch.empty(4, dtype=torch.float32, device=cls_logits.device)
     L.call("sgb_loss_finalize", ctypes.byref(d), _ptr(sums), _ptr(out), _stream())
     return out, gc, gr

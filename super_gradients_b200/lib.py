@@ -172,6 +172,7 @@ _SIGNATURES = {
     "sgb_atss_assign": (c_int, [POINTER(LossDesc)] + [P] * 5 + [c_int32] + [P] * 7 + [P, _L, P]),
     "sgb_atss_workspace_bytes": (c_int64, [POINTER(LossDesc)]),
     "sgb_dfl_iou_loss_fwd_bwd": (c_int, [POINTER(LossDesc)] + [P] * 8 + [_F, P, P, P]),
+    "sgb_focal_cls_fwd_bwd": (c_int, [POINTER(LossDesc), P, P, P, P, c_float, c_float, P, P]),
     "sgb_loss_finalize": (c_int, [POINTER(LossDesc), P, P, P]),
     "sgb_preprocess_u8": (c_int, [POINTER(PreprocDesc), P, P, P]),
     "sgb_detection_matching": (c_int, [POINTER(MatchDesc), P, P, P, P, P, P, P, P, P, P]),

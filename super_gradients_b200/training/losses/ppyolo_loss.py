@@ -42,8 +42,9 @@ def pad_targets_host(targets: Tensor, batch_size: int, n_max: int) -> Tuple[Tens
 
 class _FusedDetectionLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, desc, sync, static=None):
-        """static: None (task-aligned assigner) or (anchor boxes [L, 4], num_anchors_list) for the ATSS assigner."""
+    def forward(ctx, cls_logits, reg_distri, anchor_points, stride_tensor, gt_boxes, gt_labels, gt_valid, desc, sync, static=None, focal_alpha=None):
+        """static: None (task-aligned assigner) or (anchor boxes [L, 4], num_anchors_list) for the ATSS assigner;
+        focal_alpha: None (varifocal classification term) or the focal term's alpha."""
         cls_logits, reg_distri = cls_logits.contiguous().float(), reg_distri.contiguous().float()
         sums = torch.zeros(4, dtype=torch.float64, device=cls_logits.device)
         if static is None:
@@ -55,7 +56,7 @@ class _FusedDetectionLoss(torch.autograd.Function):
 
             dist.all_reduce(sums[3:4])
             sums[3:4] /= dist.get_world_size()
-        items, gc, gr = K.dfl_iou_loss(desc, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums)
+        items, gc, gr = K.dfl_iou_loss(desc, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, focal_alpha=focal_alpha)
         ctx.save_for_backward(gc, gr)
         ctx.mark_non_differentiable(items)
         return items[3].clone(), items
@@ -63,7 +64,7 @@ class _FusedDetectionLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gitems):
         gc, gr = ctx.saved_tensors
-        return gc * gloss, gr * gloss, None, None, None, None, None, None, None, None
+        return gc * gloss, gr * gloss, None, None, None, None, None, None, None, None, None
 
 
 @register_loss(name="PPYoloELoss", deprecated_name="ppyoloe_loss")
@@ -83,8 +84,7 @@ class PPYoloELoss(nn.Module):
         iou_type: str = "giou",
     ):
         super().__init__()
-        if not use_varifocal_loss:
-            raise NotImplementedError("focal classification loss is not implemented (YOLO-NAS recipes use varifocal)")
+        self.use_varifocal_loss = use_varifocal_loss  # False: focal term, alpha 0.25 behind ATSS / none behind TAL (:821, :833-838)
         self.use_static_assigner = use_static_assigner  # ATSS (topk 9 per level) instead of the task-aligned assigner (:681-683)
         self.num_classes = num_classes
         self.classification_loss_weight = classification_loss_weight
@@ -125,5 +125,6 @@ class PPYoloELoss(nn.Module):
                            w_dfl=self.dfl_loss_weight, iou_type=self.iou_type)  # fmt: skip
         sync = self.sync_normaliser and torch.distributed.is_available() and torch.distributed.is_initialized()
         static = (anchors.detach().float().contiguous(), [int(v) for v in num_anchors_list]) if self.use_static_assigner else None
-        loss, items = _FusedDetectionLoss.apply(cls_logits, reg_distri, anchor_points, stride_tensor.reshape(-1).contiguous(), gt_boxes, gt_labels, gt_valid, desc, sync, static)
+        loss, items = _FusedDetectionLoss.apply(cls_logits, reg_distri, anchor_points, stride_tensor.reshape(-1).contiguous(), gt_boxes, gt_labels, gt_valid, desc, sync, static,
+                                                None if self.use_varifocal_loss else (0.25 if self.use_static_assigner else -1.0))  # fmt: skip
         return loss, items.detach()

@@ -408,14 +408,14 @@ def atss_assign(*args, **kwargs):
     return host_atss.atss_assign(*args, **kwargs)
 
 
-def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True):
+def dfl_iou_loss(d, cls_logits, reg_distri, anchor_points, stride_tensor, al, ab, asc, sums, grad_scale=1.0, want_grad=True, focal_alpha=None):
     C, reg_max = d.ncls, d.reg_max
     st = stride_tensor.view(-1, 1)
     cl, rd = cls_logits.detach().clone().requires_grad_(True), reg_distri.detach().clone().requires_grad_(True)
     with torch.enable_grad():
         lab = al.long()
         onehot = F.one_hot(lab, C + 1)[..., :C].float()
-        cls_sum = O.varifocal_loss(cl, onehot * asc.unsqueeze(-1), onehot)
+        cls_sum = O.varifocal_loss(cl, onehot * asc.unsqueeze(-1), onehot) if focal_alpha is None else O.focal_loss(cl, onehot * asc.unsqueeze(-1), alpha=focal_alpha)
         pts_s = anchor_points / st
         pred = O.bbox_decode(pts_s, rd)
         pos = lab != C

@@ -232,7 +232,17 @@ def golden_atss():
             cls_logits=cls_logits.detach(), reg_distri=reg_distri.detach(), targets=targets, loss=loss.detach(), items=items.detach(), g_cls=cls_logits.grad.clone(),
             g_reg=reg_distri.grad.clone(), assigned_labels=al, assigned_bboxes=ab, assigned_scores=asc, gt_class=t["gt_class"], gt_bbox=t["gt_bbox"], pad_gt_mask=t["pad_gt_mask"].float(),
         )  # fmt: skip
-        print(case, "positives", int((al != C).sum()), "loss", float(loss), "score sum", float(asc.sum()))
+        # the focal classification term (use_varifocal_loss=False) behind either assigner, on the same inputs
+        for key, static in (("focal_static", True), ("focal_tal", False)):
+            cl, rd = cls_logits.detach().clone().requires_grad_(True), reg_distri.detach().clone().requires_grad_(True)
+            f_loss, f_items = PPYoloELoss(num_classes=C, use_static_assigner=static, use_varifocal_loss=False)((cl, rd, anchors, anchor_points, nums, stride_tensor), targets)
+            f_loss.backward()
+            out[case][key] = dict(loss=f_loss.detach(), items=f_items.detach(), g_cls=cl.grad.clone())
+            if static:  # same assignment and box terms as the varifocal run: the regression gradient is the one stored above
+                assert torch.equal(rd.grad, reg_distri.grad)
+            else:
+                out[case][key]["g_reg"] = rd.grad.clone()
+        print(case, "positives", int((al != C).sum()), "loss", float(loss.detach()), "score sum", float(asc.sum()), "focal", float(out[case]["focal_static"]["loss"]), float(out[case]["focal_tal"]["loss"]))
     torch.save(out, os.path.join(HERE, "atss.pt"))
 
 

@@ -97,3 +97,9 @@ extern "C" int pose_loss_host(const SgbPoseLossDesc* dp, const float* cls, const
   finalize(d, sums, items);
   return 0;
 }
+
+// the classification term alone (also the focal replacement pass of PPYoloELoss, csrc/focal_cls.cu), elementwise over n logits
+extern "C" int cls_term_host(int focal, float alpha, const float* x, const float* q, int n, float* loss, float* grad) {
+  for (int i = 0; i < n; ++i) sgb_pose::cls_term(focal, alpha, x[i], q[i], loss + i, grad + i);
+  return 0;
+}

@@ -340,7 +340,7 @@ def test_atss_assigner_and_static_ppyoloe_loss_vs_reference_golden(golden, case)
         assert torch.equal(al.long().cpu(), c["assigned_labels"])
         torch.testing.assert_close(asc.cpu(), c["assigned_scores"].sum(-1), rtol=1e-4, atol=1e-5)
         assert float(sums[3]) == pytest.approx(float(c["assigned_scores"].sum()), rel=1e-4)
-    cls_logits, reg_distri = c["cls_logits"].to(DEV).requires_grad_(True), c["reg_distri"].to(DEV).requires_grad_(True)
+    cls_logits, reg_distri = c["cls_logits"].clone().to(DEV).requires_grad_(True), c["reg_distri"].clone().to(DEV).requires_grad_(True)
     crit = PPYoloELoss(num_classes=C, use_static_assigner=True)
     loss, items = crit((cls_logits, reg_distri, g["anchors"].to(DEV), g["anchor_points"].to(DEV), g["nums"], g["stride_tensor"].to(DEV)), c["targets"])
     loss.backward()
@@ -378,3 +378,23 @@ def test_atss_assigner_at_training_size():
     pos = rl != C
     torch.testing.assert_close(ab.cpu()[pos], rb[pos], rtol=0, atol=1e-4)
 
+
+
+@pytest.mark.parametrize("static", [True, False])
+@pytest.mark.parametrize("case", ["regular", "no_targets", "crowded"])
+def test_focal_classification_pass_vs_reference_golden(golden, case, static):
+    """PPYoloELoss(use_varifocal_loss=False): the focal replacement pass (csrc/focal_cls.cu) behind either assigner."""
+    from super_gradients_b200.training.losses.ppyolo_loss import PPYoloELoss
+
+    g = golden("atss")
+    c = g[case]
+    ref = c["focal_static" if static else "focal_tal"]
+    g_reg = c["g_reg"] if static else ref["g_reg"]
+    cls_logits, reg_distri = c["cls_logits"].clone().to(DEV).requires_grad_(True), c["reg_distri"].clone().to(DEV).requires_grad_(True)
+    crit = PPYoloELoss(num_classes=5, use_static_assigner=static, use_varifocal_loss=False)
+    loss, items = crit((cls_logits, reg_distri, g["anchors"].to(DEV), g["anchor_points"].to(DEV), g["nums"], g["stride_tensor"].to(DEV)), c["targets"])
+    loss.backward()
+    torch.testing.assert_close(loss.detach().cpu(), ref["loss"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(items.cpu(), ref["items"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(cls_logits.grad.cpu(), ref["g_cls"], rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(reg_distri.grad.cpu(), g_reg, rtol=1e-3, atol=1e-5)
