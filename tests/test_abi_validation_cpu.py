@@ -1,0 +1,129 @@
+"""Every kernel call the OTHER benchmark configurations make (BASELINE.json configs 3-5: YOLO-NAS-M / -L training, ResNet-50 training,
+YOLO-NAS-POSE-L predict) is accepted by the C-ABI's host-side argument validation.
+
+Only YOLO-NAS-S, the tiny fixtures and resnet18_cifar have run on a B200 so far.  Here the models run on the CPU stand-in backend,
+and every kernel wrapper call is ALSO forwarded to the real wrapper and the real libsgb200.so entry point with the host tensors'
+addresses: without a GPU the entry point either rejects the descriptor (SGB_E_INVALID / SGB_E_UNSUPPORTED -- a shape this
+library cannot serve, which would be the first thing to fail on hardware) or gets as far as the first CUDA call and returns
+SGB_E_CUDA.  No kernel runs, nothing is read through the pointers on the host."""
+import collections
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import cpu_backend  # noqa: E402
+from super_gradients_b200 import kernels as K  # noqa: E402
+from super_gradients_b200 import lib as L  # noqa: E402
+
+# the batched filter-refresh / gradient-layout tables are device-resident work lists whose stand-in representation is a Python
+# list: nothing to validate through the C entry point
+TABLES = {"weight_prepare_batch", "run_weight_prepare_batch", "wgrad_to_oihw_batch_table", "run_wgrad_to_oihw_batch"}
+REAL = {name: getattr(K, name) for name in list(cpu_backend._SUBSET) + list(cpu_backend._TRAINING) if hasattr(K, name) and name not in TABLES}
+
+
+@pytest.fixture
+def validating_backend(monkeypatch):
+    """Stand-in backend whose every call first goes through the product wrapper + C entry point (validation only)."""
+    cpu_backend.install_training(monkeypatch)
+    seen, rejected = collections.Counter(), []
+    lib = L.load()
+
+    def call(name, *args):
+        rc = getattr(lib, name)(*args)
+        seen[name] += 1
+        if rc in (-1, -2):
+            msg = lib.sgb_last_error()
+            rejected.append((name, rc, msg.decode() if msg else ""))
+        return rc
+
+    monkeypatch.setattr(L, "call", call)
+    monkeypatch.setattr(K, "_stream", lambda: None)
+    for name, real in REAL.items():
+        standin = getattr(K, name)
+
+        def both(*a, _real=real, _standin=standin, _name=name, **k):
+            try:
+                _real(*a, **k)
+            except L.SgbError as e:  # raised by a wrapper's own argument check
+                rejected.append((_name, "wrapper", str(e)))
+            return _standin(*a, **k)
+
+        monkeypatch.setattr(K, name, both)
+    return seen, rejected
+
+
+def _targets(batch, size, n_cls, per_image=3, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    rows = []
+    for b in range(batch):
+        for _ in range(per_image):
+            cx, cy = (torch.rand(2, generator=gen) * size * 0.6 + size * 0.2).tolist()
+            w, h = (torch.rand(2, generator=gen) * size * 0.3 + 8).tolist()
+            rows.append([b, int(torch.randint(0, n_cls, (1,), generator=gen)), cx, cy, w, h])
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+@pytest.mark.parametrize("name", ["yolo_nas_m", "yolo_nas_l"])
+def test_yolo_nas_m_l_train_step_shapes_are_served(validating_backend, name):
+    from super_gradients_b200.training import models
+    from super_gradients_b200.training.losses import PPYoloELoss
+    from super_gradients_b200.training.sg_trainer import TrainStep
+
+    seen, rejected = validating_backend
+    torch.manual_seed(0)
+    m = models.get(name, num_classes=80).train()
+    st = TrainStep(m, PPYoloELoss(num_classes=80, use_static_assigner=False), "AdamW", {"weight_decay": 1e-5}, zero_wd_on_bias_and_bn=True, ema=True)
+    x = torch.randn(2, 3, 128, 128)
+    st.set_hyper_params(2e-4, 0.999)
+    loss, _items = st.forward_backward(x, _targets(2, 128, 80))
+    st.optimizer_step()
+    assert torch.isfinite(loss)
+    assert not rejected, rejected[:5]
+    assert seen["sgb_conv_fprop"] > 100 and seen["sgb_conv_dgrad"] > 100 and seen["sgb_conv_wgrad"] > 100 and seen["sgb_tal_assign"] == 1 and seen["sgb_adamw_step"] >= 1
+
+
+def test_resnet50_train_step_shapes_are_served(validating_backend):
+    from super_gradients_b200.training import models
+
+    seen, rejected = validating_backend
+    torch.manual_seed(0)
+    m = models.get("resnet50", num_classes=1000).train()
+    logits = m(torch.randn(2, 3, 224, 224))
+    torch.nn.functional.cross_entropy(logits, torch.tensor([1, 4])).backward()
+    assert not rejected, rejected[:5]
+    assert seen["sgb_conv_fprop"] >= 53 and seen["sgb_conv_wgrad"] >= 53 and seen["sgb_maxpool_fwd"] == 1 and seen["sgb_avgpool_fwd"] == 1
+
+
+def test_yolo_nas_pose_l_predict_shapes_are_served(validating_backend):
+    from super_gradients_b200.training import models
+
+    seen, rejected = validating_backend
+    torch.manual_seed(0)
+    m = models.get("yolo_nas_pose_l", num_classes=17).eval()
+    with torch.no_grad():
+        res = m.predict(torch.rand(2, 3, 128, 128), conf=0.01)
+    assert len(res) == 2
+    assert not rejected, rejected[:5]
+    assert seen["sgb_conv_fprop"] > 100 and seen["sgb_batched_nms"] == 1 and seen["sgb_pose_keypoint_decode"] == 3
+
+
+def test_the_validation_hook_sees_rejections(validating_backend):
+    """Negative control: a descriptor the library must refuse is reported, an acceptable one is not."""
+    import ctypes
+
+    seen, rejected = validating_backend
+    x = torch.zeros(1, 16, 8, 8, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.zeros(32, 3, 3, 16, dtype=torch.bfloat16)
+    K.conv_fprop(x, w, 32, 3, 3, 1, 1)
+    assert not rejected and seen["sgb_conv_fprop"] == 1
+    d = REAL["conv_fprop"].__globals__["conv_desc"](x, 32, 3, 3, 1, 1)
+    d.K = 0
+    ep = L.Epilogue()
+    L.call("sgb_conv_fprop", ctypes.byref(d), x.data_ptr(), w.data_ptr(), x.data_ptr(), ctypes.byref(ep), None)
+    assert len(rejected) == 1 and rejected[0][1] == -1
