@@ -511,6 +511,71 @@ def golden_detection_metrics():
     torch.save(cases, os.path.join(HERE, "detection_metrics.pt"))
 
 
+def golden_other_configs():
+    """BASELINE.json configs 3-5 (YOLO-NAS-M training, ResNet-50 training, YOLO-NAS-POSE-L inference) at reduced resolution: the
+    reference's fp32 outputs for its own seeded initialisation (torch.manual_seed(0) before models.get -- the product's
+    constructors consume the RNG identically, see tests/test_abi_validation_cpu.py), so only inputs / outputs are stored."""
+    from super_gradients.training import models
+    from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
+
+    gen = torch.Generator().manual_seed(21)
+    out = {}
+    # ---- ResNet-50
+    torch.manual_seed(0)
+    m = models.get("resnet50", num_classes=1000).train()
+    x = torch.randn(4, 3, 128, 128, generator=gen).bfloat16().float()  # exactly representable in the product's bf16 input layout
+    y = torch.tensor([3, 17, 256, 999])
+    logits = m(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    names = ["conv1.weight", "layer1.0.conv1.weight", "layer2.0.shortcut.0.weight", "layer3.5.conv2.weight", "layer4.2.conv3.weight", "linear.weight", "linear.bias", "layer4.2.bn3.weight"]
+    params = dict(m.named_parameters())
+    grads = {k: params[k].grad.clone() if params[k].grad.numel() < 20000 else params[k].grad.flatten()[:: params[k].grad.numel() // 10000].clone() for k in names}
+    grad_norms = {k: float(p.grad.norm()) for k, p in params.items() if p.grad is not None}
+    m.eval()
+    with torch.no_grad():
+        eval_logits = m(x)
+    out["resnet50"] = dict(x=x.to(torch.bfloat16), y=y, train_logits=logits.detach(), loss=loss.detach(), grads=grads, grad_norms=grad_norms, eval_logits=eval_logits)
+    # NOTE on tolerances: at random initialisation, batch 4 and 4 x 4 final maps the train-mode network is chaotic.  The reference
+    # itself, re-run with every Conv2d / BatchNorm2d / ReLU output rounded to bf16 (straight-through forward hooks), moves its
+    # logits by 0.16 (relative L2) and leaves the early layers' gradients ~uncorrelated with the fp32 ones (relative L2 1.2-1.3)
+    # while the gradient NORMS stay within a few percent.  Hence logits / loss / gradient norms / eval-mode logits are compared,
+    # gradient directions only at the classifier.
+    print("resnet50 loss", float(loss))
+    # ---- YOLO-NAS-M
+    torch.manual_seed(0)
+    m = models.get("yolo_nas_m", num_classes=80).train()
+    x = torch.randn(2, 3, 128, 128, generator=gen).bfloat16().float()
+    rows = []
+    for b in range(2):
+        for _ in range(3):
+            cx, cy = (torch.rand(2, generator=gen) * 76 + 26).tolist()
+            w, h = (torch.rand(2, generator=gen) * 40 + 10).tolist()
+            rows.append([b, int(torch.randint(0, 80, (1,), generator=gen)), cx, cy, w, h])
+    targets = torch.tensor(rows, dtype=torch.float32)
+    outputs = m(x)
+    raw = outputs[1] if isinstance(outputs, tuple) and len(outputs) == 2 else outputs
+    loss, items = PPYoloELoss(num_classes=80, use_static_assigner=False)(outputs, targets)
+    loss.backward()
+    params = dict(m.named_parameters())
+    grad_norms = {k: float(p.grad.norm()) for k, p in params.items() if p.grad is not None}
+    m.eval()
+    with torch.no_grad():
+        (eb, es), _ = m(x)
+    out["yolo_nas_m"] = dict(x=x.to(torch.bfloat16), targets=targets, cls_logits=raw[0].detach(), reg_distri=raw[1].detach(), loss=loss.detach(), items=items.detach(), grad_norms=grad_norms,
+                             eval_boxes=eb, eval_scores=es)  # fmt: skip
+    print("yolo_nas_m loss", float(loss.detach()), items)
+    # ---- YOLO-NAS-POSE-L
+    torch.manual_seed(0)
+    m = models.get("yolo_nas_pose_l", num_classes=17).eval()
+    x = torch.rand(2, 3, 128, 128, generator=gen).bfloat16().float()
+    with torch.no_grad():
+        decoded, _raw = m(x)
+    out["yolo_nas_pose_l"] = dict(x=x.to(torch.bfloat16), boxes=decoded[0], scores=decoded[1], poses=decoded[2], joint_scores=decoded[3])
+    print("pose_l", [tuple(t.shape) for t in decoded])
+    torch.save(out, os.path.join(HERE, "other_configs.pt"))
+
+
 def golden_lr_schedules():
     """LR actually in the optimizer at every optimisation step, produced by the reference's own warm-up / scheduler callbacks driven in
     the order of Trainer._train_epoch (epoch-start callbacks, per batch: batch-start callbacks -> optimizer step -> TRAIN_BATCH_STEP
@@ -753,7 +818,7 @@ def golden_resnet_cifar_train():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "atss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "atss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train", "other_configs"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()
