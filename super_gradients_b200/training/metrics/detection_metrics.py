@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from ...common.registry import register_metric
-from ..utils.detection_utils import IouThreshold, compute_detection_matching, compute_detection_metrics, pad_predictions
+from ..utils.detection_utils import IouThreshold, compute_detection_matching_batched, compute_detection_metrics, pad_predictions
 
 
 @register_metric("DetectionMetrics")
@@ -84,7 +84,7 @@ class DetectionMetrics:
             rows, counts = pad_predictions(out, dev)
         if self._thr_dev is None or self._thr_dev.device != rows.device:
             self._thr_dev = self.iou_thresholds.to(rows.device)
-        matched, ignore = compute_detection_matching(rows, counts, target, height, width, self._thr_dev, self.denormalize_targets, crowd_targets, self.top_k_predictions)
+        matched, ignore = compute_detection_matching_batched(rows, counts, target, height, width, self._thr_dev, self.denormalize_targets, crowd_targets, self.top_k_predictions)
         self._batches.append((rows[..., 4:6], counts, matched, ignore, target.detach()[:, 1].float().cpu().clone()))
 
     def _matching_info(self):

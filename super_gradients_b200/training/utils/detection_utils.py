@@ -93,9 +93,46 @@ def pad_predictions(output: List[Optional[Tensor]], device) -> Tuple[Tensor, Ten
     return rows, torch.tensor(counts, dtype=torch.int32, device=device)
 
 
+class IoUMatching:
+    """IoUMatching (detection_utils.py:880-904): the matching strategy object of the reference's API; here it only carries the IoU
+    thresholds -- compute_targets / compute_crowd_targets are the matching kernel."""
+
+    def __init__(self, iou_thresholds: Tensor):
+        self.iou_thresholds = iou_thresholds
+
+    def get_thresholds(self) -> Tensor:
+        return self.iou_thresholds
+
+
 @torch.no_grad()
-def compute_detection_matching(rows: Tensor, counts: Tensor, targets: Tensor, height: int, width: int, iou_thresholds: Tensor, denormalize_targets: bool,
-                               crowd_targets: Optional[Tensor] = None, top_k: int = 100) -> Tuple[Tensor, Tensor]:  # fmt: skip
+def compute_detection_matching(output: List[Optional[Tensor]], targets: Tensor, height: int, width: int, denormalize_targets: bool, device: str = None,
+                               iou_thresholds: Tensor = None, crowd_targets: Optional[Tensor] = None, top_k: int = 100, return_on_cpu: bool = True,
+                               matching_strategy: IoUMatching = None) -> List[Tuple]:  # fmt: skip
+    """The reference's signature and return value (detection_utils.py:1120-1179): per image (preds_matched [n, T] bool,
+    preds_to_ignore [n, T] bool, scores [n], classes [n], target classes).  One kernel launch for the batch
+    (compute_detection_matching_batched), then one device->host copy to split the flags per image."""
+    if matching_strategy is None:
+        raise ValueError("matching_strategy must not be None")
+    if not isinstance(matching_strategy, IoUMatching):
+        raise NotImplementedError("only IoUMatching has a kernel (DistanceMatching is not on the YOLO-NAS validation path)")
+    thr = matching_strategy.get_thresholds()
+    output = list(output)
+    dev = next((o.device for o in output if o is not None), torch.device(device) if device is not None else targets.device)
+    rows, counts = pad_predictions(output, dev)
+    matched, ignore = compute_detection_matching_batched(rows, counts, targets, height, width, thr, denormalize_targets, crowd_targets, top_k)
+    if return_on_cpu:
+        rows, matched, ignore = rows.cpu(), matched.cpu(), ignore.cpu()
+    t = targets.detach().float().to(rows.device)
+    res = []
+    for b, o in enumerate(output):
+        n = 0 if o is None else int(o.shape[0])
+        res.append((matched[b, :n].bool(), ignore[b, :n].bool(), rows[b, :n, 4], rows[b, :n, 5], t[t[:, 0] == b, 1]))
+    return res
+
+
+@torch.no_grad()
+def compute_detection_matching_batched(rows: Tensor, counts: Tensor, targets: Tensor, height: int, width: int, iou_thresholds: Tensor, denormalize_targets: bool,
+                                       crowd_targets: Optional[Tensor] = None, top_k: int = 100) -> Tuple[Tensor, Tensor]:  # fmt: skip
     """compute_detection_matching + IoUMatching (detection_utils.py:1120-1281, :880-1003) for a whole batch in one kernel launch.
     rows / counts: the padded NMS output ([B, P, 6], [B]) on the device; targets / crowd_targets: the reference's flat [N, 6]
     (image, class, cx, cy, w, h) tensors (read on the host, where the data loader left them).  Returns uint8 [B, P, T] tensors

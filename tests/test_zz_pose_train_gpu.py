@@ -275,7 +275,7 @@ def test_detection_matching_kernel_vs_reference_golden(golden, case):
     c = golden("detection_metrics")[case]
     for batch in c["batches"]:
         rows, counts = DU.pad_predictions(batch["output"], DEV)
-        matched, ignore = DU.compute_detection_matching(rows, counts, batch["targets"], c["hw"][0], c["hw"][1], c["iou_thresholds"], c["normalized"], batch["crowd_targets"], c["top_k"])
+        matched, ignore = DU.compute_detection_matching_batched(rows, counts, batch["targets"], c["hw"][0], c["hw"][1], c["iou_thresholds"], c["normalized"], batch["crowd_targets"], c["top_k"])
         for b, ref in enumerate(batch["matching"]):
             n = int(counts[b])
             assert torch.equal(matched[b, :n].bool().cpu(), ref[0]) and torch.equal(ignore[b, :n].bool().cpu(), ref[1]), (case, b)
