@@ -172,3 +172,34 @@ def test_the_validation_hook_sees_rejections(validating_backend):
     ep = L.Epilogue()
     L.call("sgb_conv_fprop", ctypes.byref(d), x.data_ptr(), w.data_ptr(), x.data_ptr(), ctypes.byref(ep), None)
     assert len(rejected) == 1 and rejected[0][1] == -1
+
+
+def test_new_entry_points_validate_their_descriptors(monkeypatch):
+    """sgb_atss_assign / sgb_detection_matching / sgb_focal_cls_fwd_bwd through the product wrappers with host tensors: a valid call
+    reaches the first CUDA call (SGB_E_CUDA here), an invalid one is refused with SGB_E_INVALID and the reason."""
+    from super_gradients_b200.training.losses.ppyolo_loss import pad_targets_host
+
+    monkeypatch.setattr(K, "require_cuda", lambda t, name="tensor": None)
+    monkeypatch.setattr(K, "_stream", lambda: None)
+    g = torch.load(os.path.join(HERE, "golden", "atss.pt"))
+    c = g["regular"]
+    B, Lc, _ = c["cls_logits"].shape
+    gb, gl, gv = pad_targets_host(c["targets"], B, 6)
+    st = g["stride_tensor"].reshape(-1).contiguous()
+
+    def code(fn):
+        with pytest.raises(L.SgbError) as e:
+            fn()
+        return str(e.value)
+
+    atss = lambda nums, topk=9: K.atss_assign(K.loss_desc(B, Lc, 5, 16, 6, topk=topk), c["reg_distri"], g["anchors"].contiguous(), g["anchor_points"], st, nums, gb, gl, gv, torch.zeros(4, dtype=torch.float64))  # noqa: E731
+    assert "code -3" in code(lambda: atss(g["nums"]))
+    assert "code -1" in code(lambda: atss([320, 12, 4])) and "at least topk" in code(lambda: atss([320, 12, 4]))
+    assert "code -1" in code(lambda: atss([256, 64])) and "code -1" in code(lambda: atss(g["nums"], topk=17))
+    match = lambda thr: K.detection_matching(torch.zeros(2, 5, 6), torch.zeros(2, dtype=torch.int32), torch.zeros(2, 3, 5), torch.zeros(2, dtype=torch.int32), None, None, thr, 64, 64)  # noqa: E731
+    assert "code -3" in code(lambda: match(torch.tensor([0.5]))) and "code -1" in code(lambda: match(torch.linspace(0.1, 0.9, 33)))
+    with pytest.raises(L.SgbError, match="contiguous"):
+        K.detection_matching(torch.zeros(2, 5, 6).double(), torch.zeros(2, dtype=torch.int32), torch.zeros(2, 3, 5), torch.zeros(2, dtype=torch.int32), None, None, torch.tensor([0.5]), 64, 64)
+    d = K.loss_desc(B, Lc, 5, 16, 6)
+    focal = lambda: L.call("sgb_focal_cls_fwd_bwd", __import__("ctypes").byref(d), c["cls_logits"].data_ptr(), gl.data_ptr(), c["cls_logits"].data_ptr(), torch.zeros(4, dtype=torch.float64).data_ptr(), 1.0, 0.25, None, None)  # noqa: E731
+    assert "code -3" in code(focal)
