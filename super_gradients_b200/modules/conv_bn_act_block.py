@@ -79,6 +79,12 @@ class ConvBNAct(nn.Module, _FusedConvBN):
     def forward(self, x, residual=None):
         return self._fused(x, self.seq.conv, getattr(self.seq, "bn", None), self._act_code, self._cache, residual)
 
+    def replace_input_channels(self, in_channels: int, compute_new_weights_fn=None):
+        from .weight_replacement_utils import replace_conv2d_input_channels
+
+        self.seq[0] = replace_conv2d_input_channels(conv=self.seq[0], in_channels=in_channels, fn=compute_new_weights_fn)
+        check_conv_supported(self.seq[0])
+
     def get_input_channels(self) -> int:
         return self.seq[0].in_channels
 
@@ -95,6 +101,12 @@ class Conv(nn.Module, _FusedConvBN):
 
     def forward(self, x):
         return self._fused(x, self.conv, self.bn, self._act_code, self._cache)
+
+    def replace_input_channels(self, in_channels: int, compute_new_weights_fn=None):
+        from .weight_replacement_utils import replace_conv2d_input_channels
+
+        self.conv = replace_conv2d_input_channels(conv=self.conv, in_channels=in_channels, fn=compute_new_weights_fn)
+        check_conv_supported(self.conv)
 
     def get_input_channels(self) -> int:
         return self.conv.in_channels

@@ -40,5 +40,10 @@ class NStageBackbone(BaseDetectionModule):
                 outputs.append(x)
         return outputs
 
+    def replace_input_channels(self, in_channels: int, compute_new_weights_fn=None):
+        if not hasattr(self.stem, "replace_input_channels"):
+            raise NotImplementedError(f"`{self.stem.__class__.__name__}` does not support `replace_input_channels`")
+        self.stem.replace_input_channels(in_channels=in_channels, compute_new_weights_fn=compute_new_weights_fn)
+
     def get_input_channels(self) -> int:
         return self.stem.get_input_channels()

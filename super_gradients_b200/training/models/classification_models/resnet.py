@@ -90,6 +90,12 @@ class _Classifier(SgModule, _FusedConvBN):
             self.in_planes = planes * self.expansion
         return nn.Sequential(*layers)
 
+    def replace_input_channels(self, in_channels: int, compute_new_weights_fn=None):
+        """resnet.py:249-255."""
+        from ....modules.weight_replacement_utils import replace_conv2d_input_channels
+
+        self.conv1 = replace_conv2d_input_channels(conv=self.conv1, in_channels=in_channels, fn=compute_new_weights_fn)
+
     def get_input_channels(self) -> int:
         return self.conv1.in_channels
 

@@ -61,6 +61,13 @@ class CustomizableDetector(SgModule):
         else:
             self.heads.replace_num_classes(new_num_classes, None)
 
+    def replace_input_channels(self, in_channels: int, compute_new_weights_fn=None):
+        """customizable_detector.py:124-129."""
+        if not hasattr(self.backbone, "replace_input_channels"):
+            raise NotImplementedError(f"`{self.backbone.__class__.__name__}` does not support `replace_input_channels`")
+        self.backbone.replace_input_channels(in_channels=in_channels, compute_new_weights_fn=compute_new_weights_fn)
+        self.in_channels = self.get_input_channels()
+
     def get_input_channels(self) -> int:
         return self.backbone.get_input_channels()
 

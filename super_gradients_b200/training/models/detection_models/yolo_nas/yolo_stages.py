@@ -130,6 +130,12 @@ class YoloNASStem(BaseDetectionModule):
     def forward(self, x: Tensor) -> Tensor:
         return self.conv(x)
 
+    def replace_input_channels(self, in_channels: int, compute_new_weights_fn=None):
+        """A fresh QARepVGG block, as the reference does (yolo_stages.py:176-177): a three-branch block has no single filter to cut."""
+        old = self.conv
+        self.conv = QARepVGGBlock(in_channels, self._out_channels, stride=2, use_residual_connection=False)
+        self.conv.to(next(old.parameters()).device)
+
     def get_input_channels(self) -> int:
         return self.conv.in_channels
 

@@ -203,3 +203,20 @@ def test_new_entry_points_validate_their_descriptors(monkeypatch):
     d = K.loss_desc(B, Lc, 5, 16, 6)
     focal = lambda: L.call("sgb_focal_cls_fwd_bwd", __import__("ctypes").byref(d), c["cls_logits"].data_ptr(), gl.data_ptr(), c["cls_logits"].data_ptr(), torch.zeros(4, dtype=torch.float64).data_ptr(), 1.0, 0.25, None, None)  # noqa: E731
     assert "code -3" in code(focal)
+
+
+def test_replaced_input_channels_are_served(validating_backend):
+    """models.get(..., num_input_channels=N): 1-channel ResNet-18 and 4-channel YOLO-NAS-S forward + backward run, and the first
+    layers' (channel-padded) shapes pass the C-ABI validation."""
+    from super_gradients_b200.training import models
+
+    seen, rejected = validating_backend
+    torch.manual_seed(0)
+    r = models.get("resnet18", num_classes=5, num_input_channels=1).train()
+    r(torch.randn(2, 1, 64, 64)).sum().backward()
+    assert r.conv1.weight.grad is not None and r.conv1.weight.grad.shape[1] == 1 and torch.isfinite(r.conv1.weight.grad).all()
+    y = models.get("yolo_nas_s", num_classes=3, num_input_channels=4).eval()
+    with torch.no_grad():
+        (boxes, scores), _raw = y(torch.randn(1, 4, 64, 64))
+    assert tuple(scores.shape) == (1, 84, 3) and torch.isfinite(boxes).all()
+    assert not rejected, rejected[:5]

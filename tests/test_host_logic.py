@@ -232,3 +232,32 @@ def test_zero_weight_decay_groups_match_reference(golden, name):
     live = lambda names: [n for n in names if "rbr_reparam" not in n]  # noqa: E731
     assert decay == live(g["decay"]) and no_decay == live(g["no_decay"])
     assert any(n.endswith("alpha") for n in decay) or name == "resnet18_cifar"
+
+
+def test_replace_input_channels_and_checkpoint_num_classes(tmp_path):
+    """models.get(..., checkpoint_path, checkpoint_num_classes, num_input_channels) (model_factory.py:227-254): the checkpoint's head
+    is built and loaded first, then replace_head / replace_input_channels; the filter surgery keeps the old channels
+    (weight_replacement_utils.py:27-68)."""
+    from super_gradients_b200.modules.weight_replacement_utils import replace_conv2d_input_channels
+    from super_gradients_b200.training import models
+
+    conv = torch.nn.Conv2d(3, 8, 3, padding=1, bias=True)
+    wide, narrow = replace_conv2d_input_channels(conv, 5), replace_conv2d_input_channels(conv, 2)
+    assert wide.weight.shape == (8, 5, 3, 3) and torch.equal(wide.weight[:, :3], conv.weight) and wide.weight[:, 3:].abs().sum() > 0
+    assert torch.equal(narrow.weight, conv.weight[:, :2]) and narrow.padding == conv.padding and narrow.bias is not None
+    assert replace_conv2d_input_channels(conv, 4, fn=lambda c, n: torch.nn.Conv2d(n, c.out_channels, 1)).kernel_size == (1, 1)
+    with pytest.raises(ValueError):
+        replace_conv2d_input_channels(torch.nn.Conv2d(4, 8, 3, groups=2), 3)
+
+    torch.manual_seed(0)
+    r = models.get("resnet18", num_classes=10)
+    w0 = r.conv1.weight.detach().clone()
+    torch.save({"net": r.state_dict()}, tmp_path / "r18.pth")
+    r2 = models.get("resnet18", num_classes=4, checkpoint_path=str(tmp_path / "r18.pth"), checkpoint_num_classes=10, num_input_channels=1)
+    assert r2.get_input_channels() == 1 and torch.equal(r2.conv1.weight, w0[:, :1]) and r2.linear.out_features == 4
+    assert torch.equal(r2.layer1[0].conv1.weight, r.layer1[0].conv1.weight)  # the rest of the checkpoint is in place
+
+    torch.manual_seed(0)
+    y = models.get("yolo_nas_s", num_classes=80, num_input_channels=4)
+    assert y.get_input_channels() == 4 == y.in_channels and y.backbone.stem.conv.in_channels == 4
+    assert {k: tuple(v.shape) for k, v in y.state_dict().items() if "stem" in k and "3x3.conv.weight" in k}.popitem()[1][1] == 4
