@@ -530,29 +530,37 @@ class Trainer:
         (self.valid_metric_values).  As the reference's MetricsUpdateCallback does (callbacks.py:590-597), every metric's update()
         receives the batch context -- preds, target, inputs, device and the data set's additional batch items such as
         crowd_targets -- filtered to the arguments it declares."""
-        self.net.eval()
-        tot, n = 0.0, 0
+        loss, _items, self.valid_metric_values = self._evaluate(loader, tp.get("valid_metrics_list") or [], tp["max_valid_batches"], handler, context)
+        return loss
+
+    @torch.no_grad()
+    def _evaluate(self, loader, metrics_list, max_batches=None, handler=None, context=None, phase="validation"):
+        """-> (mean loss, mean loss-items tensor or None, {metric name: value}); fires on_<phase>_batch_start / _end."""
         from . import metrics as _registered_metrics  # noqa: F401  (fills the METRICS registry)
 
-        valid_metrics = [MetricsFactory().get(m) for m in (tp.get("valid_metrics_list") or [])]
+        self.net.eval()
+        tot, items_tot, n = 0.0, None, 0
+        valid_metrics = [MetricsFactory().get(m) for m in metrics_list]
         for m in valid_metrics:
             m.reset()
         for i, batch in enumerate(loader):
-            if tp["max_valid_batches"] is not None and i >= int(tp["max_valid_batches"]):
+            if max_batches is not None and i >= int(max_batches):
                 break
             inputs, targets = batch[0].to(self.device), batch[1]
             if torch.is_tensor(targets) and type(self.criterion).__name__ != "PPYoloELoss":
                 targets = targets.to(self.device)
             if handler is not None and handler.callbacks:
                 context.update_context(batch_idx=i, inputs=inputs, target=targets)
-                handler.fire("on_validation_batch_start", context)
+                handler.fire(f"on_{phase}_batch_start", context)
             preds = self.net(inputs)
-            out = self.criterion(preds, targets)
+            out = self.criterion(preds, targets) if self.criterion is not None else None
             if handler is not None and handler.callbacks:
                 context.update_context(preds=preds, loss_log_items=out[1] if isinstance(out, tuple) else None)
-                handler.fire("on_validation_batch_end", context)
-            loss = out[0] if isinstance(out, tuple) else out
-            tot += float(loss)
+                handler.fire(f"on_{phase}_batch_end", context)
+            if out is not None:
+                tot += float(out[0] if isinstance(out, tuple) else out)
+                if isinstance(out, tuple):
+                    items_tot = out[1].detach().double().cpu() if items_tot is None else items_tot + out[1].detach().double().cpu()
             n += 1
             if valid_metrics:
                 extra = batch[2] if len(batch) > 2 and isinstance(batch[2], Mapping) else {}
@@ -560,14 +568,52 @@ class Trainer:
                 for m in valid_metrics:
                     accepted = inspect.signature(m.update).parameters
                     m.update(**{k: v for k, v in fields.items() if k in accepted})
-        self.valid_metric_values = {}
+        values = {}
         for m in valid_metrics:
             res = m.compute()
-            self.valid_metric_values.update({k: float(v) for k, v in res.items()} if isinstance(res, Mapping) else {type(m).__name__: float(res)})
+            values.update({k: float(v) for k, v in res.items()} if isinstance(res, Mapping) else {type(m).__name__: float(res)})
         self.net.train()
-        return tot / max(n, 1)
+        return tot / max(n, 1), (items_tot / max(n, 1) if items_tot is not None else None), values
 
-    test = _validate
+    def test(self, model: nn.Module = None, test_loader=None, loss=None, silent_mode: bool = False, test_metrics_list=None, loss_logging_items_names=None,
+             metrics_progress_verbose=False, test_phase_callbacks=None, use_ema_net=True) -> Dict[str, float]:  # fmt: skip
+        """Trainer.test (reference: sg_trainer.py:2096-2192): evaluates `model` (or the trained network -- its EMA weights when
+        use_ema_net and EMA was on) on `test_loader` and returns {loss component name: mean, ..., metric name: value, ...}."""
+        if test_loader is None:
+            raise ValueError("test_loader is required")
+        keep_net, keep_criterion = getattr(self, "net", None), getattr(self, "criterion", None)
+        swapped = False
+        try:
+            if model is not None:
+                self.net = model.to(self.device)
+            elif keep_net is None:
+                raise ValueError("Model is not defined. You should either train some model using trainer.train(...) or pass `model` to trainer.test(...)")
+            elif use_ema_net and getattr(self, "step", None) is not None and self.step.ema_on:
+                self.step.swap_ema()
+                swapped = True
+            if loss is not None:
+                self.criterion = LossesFactory().get(loss) if isinstance(loss, (str, Mapping)) else loss
+            handler = CallbackHandler(list(test_phase_callbacks or []))
+            context = PhaseContext(net=self.net, criterion=self.criterion, device=self.device, experiment_name=self.experiment_name)
+            handler.fire("on_test_loader_start", context)
+            mean_loss, items, values = self._evaluate(test_loader, test_metrics_list or [], None, handler, context, phase="test")
+            out = {}
+            if self.criterion is not None:
+                names = loss_logging_items_names or getattr(self.criterion, "component_names", None)
+                if items is not None and names is not None and len(names) == len(items):
+                    out.update({n_: float(v) for n_, v in zip(names, items)})
+                else:
+                    out[type(self.criterion).__name__] = mean_loss
+            out.update(values)
+            context.update_context(metrics_dict=out)
+            handler.fire("on_test_loader_end", context)
+            if not silent_mode and not self.ddp_silent_mode:
+                print(f"[{self.experiment_name}] test " + " ".join(f"{k}={v:.5f}" for k, v in out.items()))
+            return out
+        finally:
+            if swapped:
+                self.step.swap_ema()
+            self.net, self.criterion = keep_net, keep_criterion
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     def _state_dict(self, use_ema=False):

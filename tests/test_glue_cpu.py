@@ -783,3 +783,53 @@ def test_trainer_validation_metrics_and_metric_to_watch(golden, monkeypatch, tmp
     assert m["Precision@0.50"] == pytest.approx(float(prec.mean()), abs=1e-6) and m["F1@0.50"] == pytest.approx(float(f1.mean()), abs=1e-6)
     with pytest.raises(ValueError, match="metric_to_watch"):
         sg_trainer._match_metric_name("accuracy", list(m))
+
+
+def test_trainer_test_returns_loss_items_and_metrics(golden, monkeypatch, tmp_path):
+    """Trainer.test(model, test_loader, loss, test_metrics_list, test_phase_callbacks) with the reference's signature: a standalone
+    evaluation (no train() before it) returns the loss components under the criterion's component_names plus the metrics' keys,
+    fires the test-phase events, and leaves the trainer's own state untouched; after train() it evaluates the EMA weights."""
+    from super_gradients_b200.training import sg_trainer
+    from super_gradients_b200.training.losses import PPYoloELoss
+    from super_gradients_b200.training.metrics import DetectionMetrics_050
+    from super_gradients_b200.training.models.detection_models.pp_yolo_e.post_prediction_callback import PPYoloEPostPredictionCallback
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNAS
+    from super_gradients_b200.training.sg_trainer import Trainer
+    from super_gradients_b200.training.utils.callbacks import Callback
+
+    cpu_backend.install_training(monkeypatch)
+    monkeypatch.setattr(sg_trainer, "setup_device", lambda device=None: torch.device("cpu"))
+    g = golden("tiny_yolo_nas")
+    ap = copy.deepcopy(g["arch"])
+    model = YoloNAS(backbone=ap["backbone"], neck=ap["neck"], heads=ap["heads"], num_classes=4, bn_eps=1e-3, bn_momentum=0.03, inplace_act=True, in_channels=3)
+    model.load_state_dict({k: v.clone() for k, v in g["sd0"].items()}, strict=False)
+    events = []
+
+    class Rec(Callback):
+        def on_test_loader_start(self, context):
+            events.append("start")
+
+        def on_test_batch_end(self, context):
+            events.append(("batch", context.batch_idx, context.preds is not None))
+
+        def on_test_loader_end(self, context):
+            events.append(("end", sorted(context.metrics_dict)))
+
+    metric = DetectionMetrics_050(num_cls=4, normalize_targets=True, score_thres=0.01, post_prediction_callback=PPYoloEPostPredictionCallback(score_threshold=0.01, nms_threshold=0.7, nms_top_k=200, max_predictions=50))
+    trainer = Trainer("test_api", ckpt_root_dir=str(tmp_path))
+    loader = [(g["x"], g["targets"]), (g["x"].flip(0), g["targets"])]
+    res = trainer.test(model=model, test_loader=loader, loss=PPYoloELoss(num_classes=4, use_static_assigner=False), test_metrics_list=[metric], test_phase_callbacks=[Rec()], silent_mode=True)
+    assert list(res)[:4] == ["loss_cls", "loss_iou", "loss_dfl", "loss"] and {"mAP@0.50", "Recall@0.50", "Best_score_threshold"} <= set(res)
+    assert res["loss"] == pytest.approx(res["loss_cls"] + res["loss_iou"] + res["loss_dfl"], rel=1e-5) and np.isfinite(list(res.values())).all()
+    assert events[0] == "start" and events[1:3] == [("batch", 0, True), ("batch", 1, True)] and events[3][0] == "end" and "mAP@0.50" in events[3][1]
+    assert getattr(trainer, "net", None) is None and model.training  # nothing sticks to the trainer; the model is back in train mode
+    with pytest.raises(ValueError):
+        Trainer("no_model", ckpt_root_dir=str(tmp_path)).test(test_loader=loader)
+    # after training: test() without a model evaluates the EMA weights (use_ema_net=True) or the raw ones
+    tp = dict(max_epochs=1, initial_lr=5e-3, lr_mode="constant", optimizer="SGD", loss=PPYoloELoss(num_classes=4, use_static_assigner=False), ema=True,
+              ema_params={"decay": 0.5, "decay_type": "constant"}, save_model=False)  # fmt: skip
+    trainer.train(model, tp, loader)
+    ema, raw = trainer.test(test_loader=loader[:1], silent_mode=True), trainer.test(test_loader=loader[:1], silent_mode=True, use_ema_net=False)
+    assert ema["loss"] != raw["loss"] and trainer.net is model
+    again = trainer.test(test_loader=loader[:1], silent_mode=True, use_ema_net=False)
+    assert again["loss"] == raw["loss"]  # the EMA swap was undone
