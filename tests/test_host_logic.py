@@ -261,3 +261,72 @@ def test_replace_input_channels_and_checkpoint_num_classes(tmp_path):
     y = models.get("yolo_nas_s", num_classes=80, num_input_channels=4)
     assert y.get_input_channels() == 4 == y.in_channels and y.backbone.stem.conv.in_channels == 4
     assert {k: tuple(v.shape) for k, v in y.state_dict().items() if "stem" in k and "3x3.conv.weight" in k}.popitem()[1][1] == 4
+
+
+def _pose_samples(seed):
+    import types
+
+    gen = np.random.RandomState(seed)
+    samples = []
+    for n in (2, 0, 3):
+        samples.append(types.SimpleNamespace(image=gen.randint(0, 255, (32, 48, 3)).astype(np.uint8), mask=np.ones((32, 48), np.float32), bboxes_xywh=gen.rand(n, 4).astype(np.float32) * 20,
+                                             joints=gen.rand(n, 5, 3).astype(np.float32) * 30, is_crowd=(gen.rand(n) < 0.5) if n != 3 else None, additional_samples=[1]))  # fmt: skip
+    return samples
+
+
+def test_collate_functions_produce_the_reference_target_formats():
+    """DetectionCollateFN (detection_collate_fn.py:10-49) and YoloNASPoseCollateFN / flat_collate_tensors_with_batch_index
+    (yolo_nas_pose_collate_fn.py:14-125): the producers of the flat target tensors rows L1 / L7 consume -- equal to the reference's
+    outputs when /root/reference is present, and accepted by the product's target padding either way."""
+    from super_gradients_b200.common.registry import COLLATE_FUNCTIONS
+    from super_gradients_b200.training.datasets.pose_estimation_datasets import YoloNASPoseCollateFN, flat_collate_tensors_with_batch_index, undo_flat_collate_tensors_with_batch_index
+    from super_gradients_b200.training.losses.ppyolo_loss import pad_targets_host
+    from super_gradients_b200.training.losses.yolo_nas_pose_loss import pad_pose_targets_host
+    from super_gradients_b200.training.utils.collate_fn import DatasetItemsException, DetectionCollateFN
+
+    gen = np.random.RandomState(0)
+    data = [(gen.rand(16, 24, 3).astype(np.float32), gen.rand(n, 5).astype(np.float32) * 10) for n in (3, 0, 2)]
+    images, targets = DetectionCollateFN()(data)
+    assert images.shape == (3, 3, 16, 24) and images.dtype == torch.float32 and targets.shape == (5, 6) and targets[:, 0].tolist() == [0, 0, 0, 2, 2]
+    assert torch.equal(targets[3:, 1:], torch.from_numpy(data[2][1])) and COLLATE_FUNCTIONS["DetectionCollateFN"] is DetectionCollateFN
+    boxes, labels, valid = pad_targets_host(targets, 3, 4)
+    assert valid.sum(1).tolist() == [3, 0, 2]
+    with pytest.raises(DatasetItemsException):
+        DetectionCollateFN()([(1, 2, 3)])
+    chw = DetectionCollateFN._format_images([np.zeros((3, 8, 8), np.float32)] * 2)
+    assert chw.shape == (2, 3, 8, 8)
+
+    flat = flat_collate_tensors_with_batch_index([torch.ones(2, 4, 3), torch.zeros(0, 4, 3), torch.ones(1, 4, 3) * 5])
+    assert flat.shape == (3, 4, 4) and flat[:, 0, 0].tolist() == [0, 0, 2]
+    parts = undo_flat_collate_tensors_with_batch_index(flat, 3)
+    assert [p.shape[0] for p in parts] == [2, 0, 1] and torch.equal(parts[2], torch.ones(1, 4, 3) * 5)
+    imgs, (b, j, c), extras = YoloNASPoseCollateFN()(_pose_samples(1))
+    assert imgs.shape == (3, 3, 32, 48) and b.shape == (5, 5) and j.shape == (5, 5, 4) and c.shape == (5, 2) and c.dtype == torch.int64
+    assert extras["gt_samples"][0].image is None and extras["gt_samples"][0].additional_samples is None
+    ref_in = _pose_samples(1)
+    assert np.allclose(b[0, 1:].numpy(), np.r_[ref_in[0].bboxes_xywh[0, :2], ref_in[0].bboxes_xywh[0, :2] + ref_in[0].bboxes_xywh[0, 2:]])
+    padded = pad_pose_targets_host((b.float(), j.float(), c), 3, 4)
+    assert padded[-1].sum(1).tolist() == [2, 0, 3]
+
+    # against the reference itself, in a child process (the import shim installs module stubs that must not leak into this one)
+    if not os.path.isdir("/root/reference/src/super_gradients"):
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = (
+        "import sys, torch, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import test_host_logic as T\n"
+        "from oracle import ref_shim; ref_shim.install()\n"
+        "from super_gradients.training.datasets.pose_estimation_datasets.yolo_nas_pose_collate_fn import YoloNASPoseCollateFN as RefPose\n"
+        "from super_gradients.training.utils.collate_fn.detection_collate_fn import DetectionCollateFN as RefDet\n"
+        "from super_gradients_b200.training.datasets.pose_estimation_datasets import YoloNASPoseCollateFN\n"
+        "from super_gradients_b200.training.utils.collate_fn import DetectionCollateFN\n"
+        "gen = np.random.RandomState(0)\n"
+        "data = [(gen.rand(16, 24, 3).astype(np.float32), gen.rand(n, 5).astype(np.float32) * 10) for n in (3, 0, 2)]\n"
+        "(ri, rt), (pi, pt) = RefDet()(data), DetectionCollateFN()(data)\n"
+        "assert torch.equal(ri, pi) and torch.equal(rt, pt) and rt.dtype == pt.dtype\n"
+        "ra, (rb, rj, rc), _ = RefPose()(T._pose_samples(1)); pa, (pb, pj, pc), _ = YoloNASPoseCollateFN()(T._pose_samples(1))\n"
+        "assert torch.equal(ra, pa) and torch.equal(rb, pb) and torch.equal(rj, pj) and torch.equal(rc, pc) and rb.dtype == pb.dtype and rc.dtype == pc.dtype\n"
+        "print('same as the reference')\n"
+    ) % (root, os.path.join(root, "tests"))
+    out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "same as the reference" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
