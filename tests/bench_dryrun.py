@@ -1,6 +1,6 @@
 """Test infrastructure: runs bench.py's `run_ours` control flow on CPU ranks (gloo) -- the CUDA runtime objects it touches are
 replaced by inert fakes, the kernel wrappers by tests/cpu_backend.py, the CUDA graph by a replay of the eager step, and the
-workload by a 64x64 image batch.  It exists to catch what cost round 1 its GPU budget: a collective that only some ranks
+workload by a 32x32 image batch.  It exists to catch what cost round 1 its GPU budget: a collective that only some ranks
 reach (a hang at N > 1), or an exception on a path that only runs at N > 1.  Launched by tests/test_bench_dryrun.py under
 torchrun; usage: bench_dryrun.py REPO_ROOT [bench.py flags]."""
 import contextlib
@@ -79,7 +79,7 @@ def fake_capture_region(self, fn, pool=None):
     return FakeGraph(), template
 
 
-def synth_batch(batch, seed, img=64):
+def synth_batch(batch, seed, img=32):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(batch, 3, img, img, generator=g)
     rows = []
