@@ -2,9 +2,14 @@
 objectness x class score, multi- or single-label candidates, class-aware or class-agnostic NMS -- on the same one-CTA-per-image
 kernel as the PP-YOLOE / YOLO-NAS callback (csrc/nms.cu), i.e. for the whole batch in one launch instead of a Python loop over
 images around torchvision.  The kernel keeps its IoU bit-matrix in shared memory, so an image may have at most 1024 candidates
-above the confidence threshold; more raise (the reference has no such limit)."""
-from typing import List, Optional
+above the confidence threshold; more raise (the reference has no such limit).
 
+Second half (row (f)-N4): the DetectionMetrics helpers -- IouThreshold, target / prediction padding, the batched matching kernel's
+wrapper with the reference's `compute_detection_matching` signature on top, and the precision / recall / AP summary."""
+import enum
+from typing import List, Optional, Tuple
+
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -43,11 +48,6 @@ def non_max_suppression(prediction: Tensor, conf_thres: float = 0.1, iou_thres: 
 
 
 # ------------------------------------------------------------------------------------------------ validation metrics (row (f)-N4)
-import enum  # noqa: E402
-from typing import Tuple  # noqa: E402
-
-import numpy as np  # noqa: E402
-
 
 class IouThreshold(tuple, enum.Enum):
     """detection_utils.py:231-254."""
