@@ -13,6 +13,27 @@ from ...detection_models.customizable_detector import CustomizableDetector
 from .yolo_nas_pose_post_prediction_callback import YoloNASPosePostPredictionCallback
 
 
+class YoloNASPoseDecodingModule(torch.nn.Module):
+    """Export-time pre-NMS selection (reference: yolo_nas_pose_variants.py:27-90): the `num_pre_nms_predictions` most
+    confident poses per image, in descending confidence -> (boxes [B, k, 4], scores [B, k, 1], joints [B, k, J, 3] = (x, y,
+    joint confidence)).  Plain torch ops: this module exists for the ONNX / TensorRT export graph, not for the predict() path
+    (which runs the batched NMS kernel on all anchors)."""
+
+    def __init__(self, num_pre_nms_predictions: int = 1000):
+        super().__init__()
+        self.num_pre_nms_predictions = num_pre_nms_predictions
+
+    def get_num_pre_nms_predictions(self) -> int:
+        return self.num_pre_nms_predictions
+
+    def forward(self, inputs):
+        boxes, conf, coords, joint_scores = inputs if torch.jit.is_tracing() else inputs[0]
+        idx = torch.topk(conf, dim=1, k=self.num_pre_nms_predictions, largest=True, sorted=True).indices  # [B, k, 1]
+        joints = torch.cat([coords, joint_scores.unsqueeze(3)], dim=3)
+        take = lambda t: torch.gather(t, 1, idx.reshape(idx.shape[0], -1, *([1] * (t.dim() - 2))).expand(-1, -1, *t.shape[2:]))  # noqa: E731
+        return take(boxes), take(conf), take(joints)
+
+
 class YoloNASPose(CustomizableDetector):
     def __init__(self, backbone, heads, neck=None, num_classes: int = None, bn_eps: Optional[float] = None, bn_momentum: Optional[float] = None, inplace_act: Optional[bool] = True, in_channels: int = 3):
         super().__init__(backbone, heads, neck, num_classes, bn_eps, bn_momentum, inplace_act, in_channels)
@@ -23,6 +44,9 @@ class YoloNASPose(CustomizableDetector):
         self._default_nms_iou = None
         self._default_pre_nms_max_predictions = None
         self._default_post_nms_max_predictions = None
+
+    def get_decoding_module(self, num_pre_nms_predictions: int, **kwargs) -> torch.nn.Module:
+        return YoloNASPoseDecodingModule(num_pre_nms_predictions)
 
     def get_post_prediction_callback(self, conf: float, iou: float, pre_nms_max_predictions=1000, post_nms_max_predictions=300) -> YoloNASPosePostPredictionCallback:
         return YoloNASPosePostPredictionCallback(pose_confidence_threshold=conf, nms_iou_threshold=iou, pre_nms_max_predictions=pre_nms_max_predictions, post_nms_max_predictions=post_nms_max_predictions)

@@ -330,3 +330,39 @@ def test_collate_functions_produce_the_reference_target_formats():
     ) % (root, os.path.join(root, "tests"))
     out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "same as the reference" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_export_decoding_modules_match_the_reference():
+    """Row N4: YoloNASDecodingModule (yolo_nas_variants.py:53-72) and YoloNASPoseDecodingModule (yolo_nas_pose_variants.py:54-90),
+    the pre-NMS top-k of the export graph, against the reference's modules on the same random head outputs (child process)."""
+    from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNASDecodingModule
+    from super_gradients_b200.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_variants import YoloNASPoseDecodingModule
+
+    gen = torch.Generator().manual_seed(0)
+    boxes, scores = torch.rand(2, 50, 4, generator=gen), torch.rand(2, 50, 7, generator=gen)
+    b, s = YoloNASDecodingModule(10)(((boxes, scores), None))
+    assert b.shape == (2, 10, 4) and s.shape == (2, 10, 7) and (s.max(-1).values.diff(dim=1) <= 0).all()
+    conf, coords, js = torch.rand(2, 50, 1, generator=gen), torch.rand(2, 50, 5, 2, generator=gen), torch.rand(2, 50, 5, generator=gen)
+    pb, pc, pj = YoloNASPoseDecodingModule(8)(((boxes, conf, coords, js), None))
+    assert pb.shape == (2, 8, 4) and pc.shape == (2, 8, 1) and pj.shape == (2, 8, 5, 3) and (pc[:, :, 0].diff(dim=1) <= 0).all()
+    k = int(conf[0, :, 0].argmax())
+    assert torch.equal(pb[0, 0], boxes[0, k]) and torch.equal(pj[0, 0, :, :2], coords[0, k]) and torch.equal(pj[0, 0, :, 2], js[0, k])
+    if not os.path.isdir("/root/reference/src/super_gradients"):
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = (
+        "import sys, torch; sys.path[:0] = [%r]\n"
+        "from oracle import ref_shim; ref_shim.install()\n"
+        "from super_gradients.training.models.detection_models.yolo_nas.yolo_nas_variants import YoloNASDecodingModule as RD\n"
+        "from super_gradients.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_variants import YoloNASPoseDecodingModule as RP\n"
+        "from super_gradients_b200.training.models.detection_models.yolo_nas import YoloNASDecodingModule as PD\n"
+        "from super_gradients_b200.training.models.pose_estimation_models.yolo_nas_pose.yolo_nas_pose_variants import YoloNASPoseDecodingModule as PP\n"
+        "gen = torch.Generator().manual_seed(0)\n"
+        "boxes, scores = torch.rand(3, 400, 4, generator=gen), torch.rand(3, 400, 80, generator=gen)\n"
+        "for a, b in zip(RD(100)(((boxes, scores), None)), PD(100)(((boxes, scores), None))): assert torch.equal(a, b)\n"
+        "conf, coords, js = torch.rand(3, 400, 1, generator=gen), torch.rand(3, 400, 17, 2, generator=gen), torch.rand(3, 400, 17, generator=gen)\n"
+        "for a, b in zip(RP(64)(((boxes, conf, coords, js), None)), PP(64)(((boxes, conf, coords, js), None))): assert torch.equal(a, b)\n"
+        "print('same as the reference')\n"
+    ) % (root,)
+    out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "same as the reference" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
