@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # First GPU calls of the next round, cheapest / most informative first (each line is one `gpurun` payload; wrap in `timeout`).
 #   1. bash tools/next_round_gpu_plan.sh verify      -> every GPU test incl. the ones written after round 1's budget ran out
+#   1b. bash tools/next_round_gpu_plan.sh sanitize   -> compute-sanitizer memcheck over the small fixtures of the never-run kernels
 #   2. bash tools/next_round_gpu_plan.sh repro       -> the interleaved-model anomaly under compute-sanitizer
 #   2b. bash tools/next_round_gpu_plan.sh determinism -> same scenario on the -DSGB_DETERMINISTIC_STATS build (prebuilt HERE by
 #       `SGB_OUT=$PWD/super_gradients_b200/libsgb200_det.so SGB_OBJ=$PWD/super_gradients_b200/csrc/obj_det bash super_gradients_b200/csrc/build.sh -DSGB_DETERMINISTIC_STATS`)
@@ -29,6 +30,12 @@ case "${1:-verify}" in
     timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
     timeout 300 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_verify.json 2> gpurun_out/bench_verify.err
     tail -2 gpurun_out/bench_verify.err; cut -c1-400 gpurun_out/bench_verify.json ;;
+  sanitize)  # memcheck over the kernels that have never run (small fixtures only: ~40x slowdown)
+    for grp in "detection_matching_kernel_vs" "atss_assigner_and_static" "focal" "preprocessing" "pose_loss_kernels_match_the_reference" "yolox"; do
+      echo "== memcheck -k '$grp'"
+      timeout 600 compute-sanitizer --tool memcheck --print-limit 10 python -m pytest tests/test_zz_pose_train_gpu.py -m gpu -q --tb=line --runxfail -k "$grp" > gpurun_out/sanitize_${grp// /_}.log 2>&1
+      grep -E "ERROR SUMMARY|Invalid|passed|failed" gpurun_out/sanitize_${grp// /_}.log | tail -4
+    done ;;
   repro)
     STEPS=4 timeout 120 python tools/repro_interleaved.py 2>&1 | tail -6
     for tool in memcheck initcheck; do
