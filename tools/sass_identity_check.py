@@ -7,6 +7,7 @@ Usage: python tools/sass_identity_check.py [commit]      (exit code 1 if a commo
 import hashlib
 import os
 import re
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -50,6 +51,7 @@ def main(commit):
         for k in diff + gone:
             print("    !", k[-90:])
         bad += len(diff) + len(gone)
+    shutil.rmtree(scratch, ignore_errors=True)
     return 1 if bad else 0
 
 
