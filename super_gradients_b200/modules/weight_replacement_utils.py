@@ -1,4 +1,4 @@
-"""Input-channel surgery on a convolution (reference: modules/weight_replacement_utils.py:9-68), the leaf of every
+"""Input-channel surgery on a convolution (reference: modules/weight_replacement_utils.py:9-65), the leaf of every
 `replace_input_channels` (ConvBNAct / Conv, ResNet.conv1, the detectors' backbones; `models.get(..., num_input_channels=...)` after
 loading a checkpoint trained on 3 channels)."""
 from typing import Callable, Optional

@@ -1,5 +1,5 @@
 """The producer of YoloNASPoseLoss's target triple (reference:
-training/datasets/pose_estimation_datasets/yolo_nas_pose_collate_fn.py:14-125): samples -> (images [B, 3, H, W],
+training/datasets/pose_estimation_datasets/yolo_nas_pose_collate_fn.py:14-123): samples -> (images [B, 3, H, W],
 (boxes [N, 1+4] xyxy, joints [N, J, 1+3], is_crowd [N, 1+1]) each with the sample index prepended, extras)."""
 from typing import Dict, List, Tuple
 

@@ -237,7 +237,7 @@ def test_zero_weight_decay_groups_match_reference(golden, name):
 def test_replace_input_channels_and_checkpoint_num_classes(tmp_path):
     """models.get(..., checkpoint_path, checkpoint_num_classes, num_input_channels) (model_factory.py:227-254): the checkpoint's head
     is built and loaded first, then replace_head / replace_input_channels; the filter surgery keeps the old channels
-    (weight_replacement_utils.py:27-68)."""
+    (weight_replacement_utils.py:27-65)."""
     from super_gradients_b200.modules.weight_replacement_utils import replace_conv2d_input_channels
     from super_gradients_b200.training import models
 
@@ -276,7 +276,7 @@ def _pose_samples(seed):
 
 def test_collate_functions_produce_the_reference_target_formats():
     """DetectionCollateFN (detection_collate_fn.py:10-49) and YoloNASPoseCollateFN / flat_collate_tensors_with_batch_index
-    (yolo_nas_pose_collate_fn.py:14-125): the producers of the flat target tensors rows L1 / L7 consume -- equal to the reference's
+    (yolo_nas_pose_collate_fn.py:14-123): the producers of the flat target tensors rows L1 / L7 consume -- equal to the reference's
     outputs when /root/reference is present, and accepted by the product's target padding either way."""
     from super_gradients_b200.common.registry import COLLATE_FUNCTIONS
     from super_gradients_b200.training.datasets.pose_estimation_datasets import YoloNASPoseCollateFN, flat_collate_tensors_with_batch_index, undo_flat_collate_tensors_with_batch_index
