@@ -260,7 +260,7 @@ int sgb_dfl_iou_loss_fwd_bwd(const SgbLossDesc* d, const float* cls_logits, cons
                              const float* assigned_box, const float* assigned_score, double* sums, float grad_scale,
                              float* grad_cls, float* grad_reg, void* stream);
 /* Focal classification term (PPYoloELoss use_varifocal_loss=False: ppyolo_loss.py:1069-1077; alpha = 0.25 behind the ATSS
- * assigner, <= 0 (no alpha_t) behind the task-aligned one, :821/:833).  Call AFTER sgb_dfl_iou_loss_fwd_bwd and before
+ * assigner, <= 0 (no alpha_t) behind the task-aligned one, :820 / :832).  Call AFTER sgb_dfl_iou_loss_fwd_bwd and before
  * sgb_loss_finalize: replaces sums[0] by the focal sum and grad_cls by the focal term's final gradient. */
 int sgb_focal_cls_fwd_bwd(const SgbLossDesc* d, const float* cls_logits, const int32_t* assigned_label,
                           const float* assigned_score, double* sums, float grad_scale, float alpha, float* grad_cls,

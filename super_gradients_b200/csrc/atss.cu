@@ -148,7 +148,7 @@ extern "C" int sgb_atss_assign(const SgbLossDesc* d, const float* reg_distri, co
   lv.n = n_levels;
   int acc = 0, widest = 0;
   for (int i = 0; i < n_levels; ++i) {
-    // torch.topk raises when a level holds fewer than topk anchors (ppyolo_loss.py:290)
+    // torch.topk raises when a level holds fewer than topk anchors (ppyolo_loss.py:291)
     SGB_REQUIRE(level_sizes[i] >= d->topk, "every pyramid level needs at least topk anchors");
     lv.start[i] = acc;
     acc += level_sizes[i];

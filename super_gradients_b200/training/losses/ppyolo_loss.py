@@ -84,7 +84,7 @@ class PPYoloELoss(nn.Module):
         iou_type: str = "giou",
     ):
         super().__init__()
-        self.use_varifocal_loss = use_varifocal_loss  # False: focal term, alpha 0.25 behind ATSS / none behind TAL (:821, :833-838)
+        self.use_varifocal_loss = use_varifocal_loss  # False: focal term, alpha 0.25 behind ATSS / none behind TAL (:820, :832-838)
         self.use_static_assigner = use_static_assigner  # ATSS (topk 9 per level) instead of the task-aligned assigner (:681-683)
         self.num_classes = num_classes
         self.classification_loss_weight = classification_loss_weight
