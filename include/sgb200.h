@@ -322,7 +322,7 @@ int64_t sgb_nms_workspace_bytes(const SgbNmsDesc* d);
 int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const float* scores, float* out, int32_t* out_idx,
                     int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* ---- DetectionMetrics matching (training/utils/detection_utils.py:1120-1281, IoUMatching :880-1003) ---- */
+/* ---- DetectionMetrics matching (training/utils/detection_utils.py:1120-1290, IoUMatching :880-1005) ---- */
 #define SGB_MATCH_MAX_THRESHOLDS 32
 typedef struct SgbMatchDesc {
   int32_t B;                     /* images of the batch */

@@ -1,6 +1,6 @@
 // DetectionMetrics matching (row (f)-N4): which NMS outputs are true positives / ignored, for every IoU threshold, one launch per
 // validation batch instead of the reference's per-image Python loop over (prediction, target) pairs with a dozen small tensor ops
-// per pair (detection_utils.py:942-961).  One CTA per image; its predictions, targets and crowd targets live in shared memory;
+// per pair (detection_utils.py:937-958).  One CTA per image; its predictions, targets and crowd targets live in shared memory;
 // warp j runs threshold j's greedy assignment (the thresholds never interact), lanes stride over the targets.
 // Latency-bound integer / compare work on a few KB per image -- no roofline to speak of; the point is removing ~1e4 launches and a
 // device->host sync per validation batch.  The arithmetic is in detection_match_math.cuh (shared with the CPU test build).

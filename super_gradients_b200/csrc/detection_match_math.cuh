@@ -4,11 +4,11 @@
 //
 // Reference (src/super_gradients/training/utils/detection_utils.py):
 //   change_bbox_bounds_for_image_size_inplace :174-185   predictions clipped to the image
-//   cxcywh2xyxy :725-735 (+ denormalisation :1255-1259)   targets -> pixel XYXY, in exactly this operation order
+//   cxcywh2xyxy :725-735 (+ denormalisation :1269-1273)   targets -> pixel XYXY, in exactly this operation order
 //   box_iou :257-276, crowd_ioa :797-812                  float32, (area1 + area2) - inter
 //   get_top_k_idx_per_cls :1342-1359                      predictions used: non-zero score, rank < top_k inside their class
-//   IoUMatching.compute_targets :906-963                  greedy loop over predictions (confidence order) x targets (IoU order)
-//   IoUMatching.compute_crowd_targets :965-1003           crowd targets only switch predictions to "ignore"
+//   IoUMatching.compute_targets :902-960                  greedy loop over predictions (confidence order) x targets (IoU order)
+//   IoUMatching.compute_crowd_targets :962-1005           crowd targets only switch predictions to "ignore"
 //
 // The greedy loop is restated per threshold j: a prediction takes the still-free same-class target of highest IoU (first one on
 // ties, the order of the reference's stable descending sort) if that IoU is > thr[j]; thresholds never interact, so each one can

@@ -108,7 +108,7 @@ class IoUMatching:
 def compute_detection_matching(output: List[Optional[Tensor]], targets: Tensor, height: int, width: int, denormalize_targets: bool, device: str = None,
                                iou_thresholds: Tensor = None, crowd_targets: Optional[Tensor] = None, top_k: int = 100, return_on_cpu: bool = True,
                                matching_strategy: IoUMatching = None) -> List[Tuple]:  # fmt: skip
-    """The reference's signature and return value (detection_utils.py:1120-1179): per image (preds_matched [n, T] bool,
+    """The reference's signature and return value (detection_utils.py:1120-1193): per image (preds_matched [n, T] bool,
     preds_to_ignore [n, T] bool, scores [n], classes [n], target classes).  One kernel launch for the batch
     (compute_detection_matching_batched), then one device->host copy to split the flags per image."""
     if matching_strategy is None:
@@ -133,7 +133,7 @@ def compute_detection_matching(output: List[Optional[Tensor]], targets: Tensor, 
 @torch.no_grad()
 def compute_detection_matching_batched(rows: Tensor, counts: Tensor, targets: Tensor, height: int, width: int, iou_thresholds: Tensor, denormalize_targets: bool,
                                        crowd_targets: Optional[Tensor] = None, top_k: int = 100) -> Tuple[Tensor, Tensor]:  # fmt: skip
-    """compute_detection_matching + IoUMatching (detection_utils.py:1120-1281, :880-1003) for a whole batch in one kernel launch.
+    """compute_detection_matching + IoUMatching (detection_utils.py:1120-1290, :880-1005) for a whole batch in one kernel launch.
     rows / counts: the padded NMS output ([B, P, 6], [B]) on the device; targets / crowd_targets: the reference's flat [N, 6]
     (image, class, cx, cy, w, h) tensors (read on the host, where the data loader left them).  Returns uint8 [B, P, T] tensors
     (preds_matched, preds_to_ignore); prediction rows past counts[b] are zero."""
@@ -150,7 +150,7 @@ def compute_detection_matching_batched(rows: Tensor, counts: Tensor, targets: Te
 
 def compute_detection_metrics_per_cls(preds_matched: Tensor, preds_to_ignore: Tensor, preds_scores: Tensor, n_targets, recall_thresholds: Tensor, score_threshold: float, device="cpu"):
     """Precision / recall at `score_threshold`, the F1-optimal confidence and the 101-point interpolated AP of one class for
-    every IoU threshold (detection_utils.py:1442-1580).  Host-side summary arithmetic on the accumulated matching flags, once per
+    every IoU threshold (detection_utils.py:1449-1580).  Host-side summary arithmetic on the accumulated matching flags, once per
     validation run; same torch operations, in the same order, as the reference."""
     nb_iou, nb_score = preds_matched.shape[-1], len(recall_thresholds)
     zeros = torch.zeros(nb_iou, device=device)
@@ -185,7 +185,7 @@ def compute_detection_metrics_per_cls(preds_matched: Tensor, preds_to_ignore: Te
 
 def compute_detection_metrics(preds_matched: Tensor, preds_to_ignore: Tensor, preds_scores: Tensor, preds_cls: Tensor, targets_cls: Tensor, device="cpu",
                               recall_thresholds: Optional[Tensor] = None, score_threshold: float = 0.1):  # fmt: skip
-    """detection_utils.py:1361-1439: (ap, precision, recall, f1) [n_present_classes, T], the present classes, the overall best
+    """detection_utils.py:1361-1446: (ap, precision, recall, f1) [n_present_classes, T], the present classes, the overall best
     confidence threshold and the per-class ones."""
     preds_matched, preds_to_ignore = preds_matched.to(device).bool(), preds_to_ignore.to(device).bool()
     preds_scores, preds_cls, targets_cls = preds_scores.to(device), preds_cls.to(device), targets_cls.to(device)
