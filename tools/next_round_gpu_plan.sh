@@ -13,6 +13,7 @@
 #       `SGB200_LIB=.../libsgb200_1x1.so pytest tests/test_kernels_gpu.py tests/test_zz_pose_train_gpu.py -m gpu --runxfail -k conv` first)
 #   3. bash tools/next_round_gpu_plan.sh twogpu      -> 2-GPU bench, hard 150 s limit (run with `gpurun --gpus 2`)
 #   4. bash tools/next_round_gpu_plan.sh profile     -> ncu launch list of one graph step + layer profile
+# `bash tools/build_variants.sh` (here, no GPU needed) builds all experiment libraries; rerun it after any change to include/sgb200.h.
 # NOTE: the experiment libraries (libsgb200_{det,pdl,wide,exp}.so) are listed in .gpurunignore so that routine calls stay small:
 # comment those lines out before `determinism`, `pdl` or `variants`.
 set -uo pipefail
