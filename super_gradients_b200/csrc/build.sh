@@ -6,7 +6,14 @@ ROOT="$(cd "$HERE/../.." && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="${SGB_OUT:-$HERE/../libsgb200.so}"   # SGB_OUT / SGB_OBJ: build a variant (e.g. -DSGB_DETERMINISTIC_STATS) next to the default library
 OBJ="${SGB_OBJ:-$HERE/obj}"
-FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE" --expt-relaxed-constexpr)
+# Default feature set (each measured on B200 in round 2, tools/next_round_gpu_plan.sh variants / determinism):
+#   SGB_DETERMINISTIC_STATS  per-warp BatchNorm-statistics slots summed in a fixed order: removes the run-to-run last-bit
+#                            differences of interleaved models at < 1 % cost
+#   SGB_UMMA_WIDE_STORE      256-bit stores in the im2col kernels' fast epilogue (+2 %)
+#   SGB_HALO_1X1             1x1 stride-1 convolutions on the halo-tile pipeline (+1 %)
+# -DSGB_PDL (programmatic dependent launch) measured 2 % SLOWER on the graph step and stays off.
+DEFS=(${SGB_DEFS:--DSGB_DETERMINISTIC_STATS -DSGB_UMMA_WIDE_STORE -DSGB_HALO_1X1})
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I"$ROOT/include" -I"$HERE" --expt-relaxed-constexpr "${DEFS[@]}")
 mkdir -p "$OBJ"
 pids=()
 for f in "$HERE"/*.cu; do

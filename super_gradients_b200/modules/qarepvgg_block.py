@@ -108,7 +108,16 @@ class QARepVGGBlock(nn.Module):
         # eval with branches: fold them on the fly (numerically the reference's partial fusion, max abs err ~5e-6)
         with torch.no_grad():
             k, b = self._get_equivalent_kernel_bias_for_branches()
-            return self._forward_single_conv(inputs, k, b, extra_key="eval")
+            return self._forward_single_conv(inputs, k, b, extra_key=("eval", self._eval_source_key()))
+
+    def _eval_source_key(self):
+        """Identity + version of every tensor the folded eval kernel is computed from: `k` itself is a temporary whose
+        address the caching allocator reuses, so it cannot key the bf16 filter cache (load_state_dict / in-place edits)."""
+        bn = self.branch_3x3.bn
+        srcs = [self.branch_3x3.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.branch_1x1.weight, self.branch_1x1.bias]
+        if isinstance(self.alpha, torch.Tensor):
+            srcs.append(self.alpha)
+        return tuple((t.data_ptr(), t._version) for t in srcs if t is not None)
 
     def _forward_single_conv(self, x, weight, bias, extra_key=None):
         """act(post_bn_eval(conv3x3(x, weight) + bias)) in one GEMM launch."""

@@ -220,7 +220,9 @@ class TrainStep:
     def set_hyper_params(self, lr: float, ema_decay_value: Optional[float] = None):
         """Writes this step's LR (and Adam bias corrections) to the device; must precede run()."""
         t = self.opt_steps + 1
-        gs = 1.0 / (self.world * self.accumulate)
+        # the reference's _backward_step (sg_trainer.py:611-644) calls loss.backward() on every micro-batch without dividing
+        # by batch_accumulate: accumulated gradients are SUMMED; only the data-parallel average (DDP) divides
+        gs = 1.0 / self.world
         wd = float(self.op.get("weight_decay", 0.0))
         # The host may run many steps ahead of the device (graph replays are enqueued without a sync): every call stages its
         # values in its own pinned slot, and a slot is only rewritten after the copy that read it has executed.
@@ -511,12 +513,20 @@ class Trainer:
                 handler.fire("on_validation_loader_end", context)
                 self.step.swap_ema()
             if tp["save_model"] and not self.ddp_silent_mode:
-                watch, greater = metrics.get("valid_loss", train_loss), False
-                if tp["metric_to_watch"] and "valid_loss" in metrics:
+                # `best` always holds ONE metric: the watched validation metric when a validation loader exists (epochs that
+                # skipped validation neither compare nor update it), else the training loss
+                validated = "valid_loss" in metrics
+                if validated and tp["metric_to_watch"]:
                     watch, greater = metrics[_match_metric_name(tp["metric_to_watch"], list(metrics))], bool(tp["greater_metric_to_watch_is_better"])
-                is_best = best is None or (watch > best if greater else watch < best)
+                elif validated:
+                    watch, greater = metrics["valid_loss"], False
+                elif valid_loader is None:
+                    watch, greater = train_loss, False
+                else:
+                    watch, greater = None, False
+                is_best = watch is not None and (best is None or (watch > best if greater else watch < best))
                 best = watch if is_best else best
-                self._save_checkpoint(epoch, metrics, tp, is_best)
+                self._save_checkpoint(epoch, metrics, tp, is_best, acc=best if best is not None else watch)
                 if is_best and "valid_loss" in metrics:
                     handler.fire("on_validation_end_best_epoch", context)
             if not tp["silent_mode"] and not self.ddp_silent_mode:
@@ -646,13 +656,13 @@ class Trainer:
                     st.ema_buffers[off : off + k].copy_(ema[name].reshape(-1).to(st.ema_buffers.device))
                     off += k
 
-    def _save_checkpoint(self, epoch: int, metrics: dict, tp, is_best: bool):
+    def _save_checkpoint(self, epoch: int, metrics: dict, tp, is_best: bool, acc=None):
         """Same dictionary keys as the reference (sg_trainer.py:649-739): net, acc, epoch, metrics, optimizer_state_dict,
         ema_net, ..."""
         os.makedirs(self.checkpoints_dir_path, exist_ok=True)
         state = {
             "net": self._state_dict(False),
-            "acc": metrics.get("valid_loss", metrics.get("train_loss")),
+            "acc": acc if acc is not None else metrics.get("valid_loss", metrics.get("train_loss")),  # the watched metric, as the reference stores it
             "epoch": epoch,
             "metrics": metrics,
             "packages": {"torch": torch.__version__},

@@ -239,7 +239,9 @@ for step in range(3):
     ema = [torch.zeros_like(st.ema_params) for _ in range(world)]
     dist.all_gather(ema, st.ema_params)
     assert torch.equal(ema[0], ema[1])
-print("rank", rank, "ok", float(loss))
+print("rank", rank, "ok", float(loss), flush=True)
+dist.barrier()
+dist.destroy_process_group()  # an orderly shutdown: a rank that exits while gloo's threads are alive can abort at interpreter exit
 """
 
 

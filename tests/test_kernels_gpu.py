@@ -362,7 +362,6 @@ def test_nms_bit_exact_vs_oracle_and_reference_golden(golden, case):
         np.testing.assert_array_equal(_canon(out[b, : cnt[b]]), _canon(rr))
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.5)")
 @pytest.mark.parametrize("case", ["regular", "topk", "few_joints", "nothing_passes"])
 def test_pose_post_prediction_callback_vs_oracle_and_reference_golden(golden, case):
     """Row N2: YoloNASPosePostPredictionCallback on the batched NMS kernel (single score, class-agnostic, >= threshold)."""

@@ -256,6 +256,60 @@ def test_yolo_nas_s_full_train_step_runs_and_predicts():
     assert len(preds) == 2 and preds[0].shape[1] == 6
 
 
+def test_yolo_nas_s_config2_size_loss_parity():
+    """Whole-graph parity at CONFIG-2 size (YOLO-NAS-S, 640 x 640, COCO-shape targets; 4 of the 32 images so the CPU oracle stays
+    in seconds): raw head outputs, decoded boxes / scores, loss and its three components against
+      (1) the whole-graph oracle in bf16-emulation mode (same rounding points as the kernels): the kernels' own error;
+      (2) the same oracle in plain fp32 (= the reference's CPU arithmetic): adds the gap bf16 activation STORAGE cannot avoid.
+    Unlike the 4 x 4-map tiny fixture the BatchNorms here average >= 1600 positions, so single-ulp flips are not amplified.
+    The achieved errors are written to gpurun_out/config2_parity.json (profiles/ keeps the committed copy)."""
+    import json
+    import os
+
+    import yaml
+
+    import bench
+    from oracle import sg_oracle as O
+    from oracle.yolo_nas_oracle import YoloNASOracle
+    from super_gradients_b200.training import models
+    from super_gradients_b200.training.losses import PPYoloELoss
+
+    torch.manual_seed(0)
+    m = models.get("yolo_nas_s", num_classes=80).to(DEV).train()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x, t = bench.synth_batch(4, 7)
+    (pb, ps), raw = m(x.to(DEV))
+    loss, items = PPYoloELoss(num_classes=80, use_static_assigner=False)(((pb, ps), raw), t)
+    torch.cuda.synchronize()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    arch = yaml.safe_load(open(os.path.join(root, "super_gradients_b200", "recipes", "arch_params", "yolo_nas_s_arch_params.yaml")))
+    arch["bn_eps"], arch["bn_momentum"] = float(arch["bn_eps"]), float(arch["bn_momentum"])
+    rep = {}
+    for mode in ("bf16_emulation", "fp32"):
+        with torch.no_grad():
+            if mode == "bf16_emulation":
+                with O.bf16_emulation():
+                    (pbe, pse), rawe = YoloNASOracle(arch, {k: v.clone() for k, v in sd.items()}, training=True).forward(x)
+                    losse, itemse = O.ppyoloe_loss(rawe, t, 80)
+            else:
+                (pbe, pse), rawe = YoloNASOracle(arch, {k: v.clone() for k, v in sd.items()}, training=True).forward(x)
+                losse, itemse = O.ppyoloe_loss(rawe, t, 80)
+        rep[mode] = {
+            "cls_logits": l2rel(raw[0], rawe[0]), "reg_distri": l2rel(raw[1], rawe[1]), "boxes": l2rel(pb, pbe), "scores": l2rel(ps, pse),
+            "loss": abs(float(loss) - float(losse)) / abs(float(losse)),
+            "items": [abs(float(a) - float(b)) / max(abs(float(b)), 1e-12) for a, b in zip(items.detach().cpu().reshape(-1), itemse.detach().reshape(-1))],
+            "loss_value": float(loss), "oracle_loss_value": float(losse),
+        }  # fmt: skip
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(root, "gpurun_out", "config2_parity.json"), "w"), indent=1)
+    print("config-2-size parity:", json.dumps(rep))
+    e, f = rep["bf16_emulation"], rep["fp32"]
+    # north_star: loss within 1e-3 relative.  Against the emulation (the kernels' own error) and against fp32 (bf16 storage gap included).
+    assert e["loss"] < 1e-3 and max(e["items"][:3]) < 2e-3, e
+    assert e["cls_logits"] < 5e-3 and e["reg_distri"] < 2e-2 and e["boxes"] < 5e-3 and e["scores"] < 1e-2, e
+    assert f["loss"] < 5e-3 and f["cls_logits"] < 2e-2, f
+
+
 def test_resnet18_cifar_training_matches_reference_trajectory(golden):
     """config 1: same seeded init (identical RNG consumption as the reference constructor), same synthetic batches,
     SGD(lr 0.1, m 0.9, wd 1e-4 on conv/linear weights) + CE: per-step losses follow the reference's."""
@@ -284,7 +338,6 @@ def test_resnet18_cifar_training_matches_reference_trajectory(golden):
     assert abs(losses[1] - g["losses"][1]) < 0.1 * g["losses"][1]
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.5)")
 def test_tiny_yolo_nas_pose_eval_and_predict(golden):
     """Row L8 end to end on the GPU: eval-mode YoloNASPose (reference arch + state dict) -> decoded boxes / person scores /
     keypoints / joint scores and raw head outputs against the whole-graph oracle in bf16-emulation mode (tight) and the fp32

@@ -10,7 +10,7 @@ import torch
 
 from oracle import sg_oracle as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was exhausted: first hardware run pending (DESIGN.md 8.5)")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda"
 
 
@@ -104,11 +104,36 @@ def test_tiny_yolo_nas_pose_train_step(golden):
     assert l2rel(items, items_e) < 0.15, (items, items_e)  # iou^6 * oks scores of a random model: see tests/test_glue_cpu.py
     params = dict(m.named_parameters())
     zero_ref = {k for k, v in g["grad_sums"].items() if tuple(v) == (0.0, 0.0)}
+    # d(bn3.bias) and d(branch_1x1.bias) of a QARepVGG block are identically zero (post_bn removes per-channel constants): the
+    # reference's autograd leaves fp32 round-off there (|sum| < 1e-5 against 1e0..1e2 for the block's weights), the fused kernels
+    # the exact 0.  First hardware run (round 2) failed on exactly this: the test had demanded a non-zero value.
+    math_zero = {k for k in g["grad_sums"] if k.endswith("branch_3x3.bn.bias") or k.endswith("branch_1x1.bias")}
     for k in g["grad_sums"]:
         assert params[k].grad is not None, k
+        if k in math_zero:
+            assert abs(g["grad_sums"][k][1]) < 1e-4, (k, g["grad_sums"][k])
+            assert float(params[k].grad.abs().sum()) < 1e-4, k
+            continue
         assert (float(params[k].grad.abs().sum()) == 0.0) == (k in zero_ref), k
+    # Backward, tight: the loss restatement evaluated on the PRODUCT's own raw head outputs gives d(loss)/d(raw); the gradient of a
+    # prediction conv's bias is that summed over the batch and the level's anchors -- this pins the loss kernels' gradients, the
+    # `_PoseDecode` backward scatter into the head maps and the bias reductions on the real graph without comparing two forwards.
+    from test_pose_loss_host import _oracle
+
+    raw_cpu = [t.detach().float().cpu() if torch.is_tensor(t) else t for t in outs[1]]
+    _le, _ie, graw = _oracle(raw_cpu, g["targets"], g["sigmas"], g["kw"])
+    nums, a0 = list(raw_cpu[6]), 0
+    for lvl, n in enumerate(nums):
+        for name, gr in (("cls_pred", graw[0]), ("reg_pred", graw[1])):
+            ref = gr[:, a0 : a0 + n].reshape(-1, gr.shape[-1]).sum(0)
+            mine = params[f"heads.head{lvl + 1}.{name}.bias"].grad.detach().float().cpu()
+            assert float((mine - ref).abs().max()) <= 2e-2 * float(ref.abs().max()) + 1e-6, (lvl, name, mine, ref)
+        a0 += n
+    # Backward, loose: against the whole-graph oracle's own forward.  On this 4 x 4-map fixture two bf16 emulations that differ only
+    # in accumulation precision already disagree on which anchors are positive (tests/test_glue_cpu.py), so this is a direction check.
     for k in ("heads.head1.cls_pred.bias", "heads.head1.pose_pred.bias", "heads.head1.reg_pred.bias"):
-        assert l2rel(params[k].grad, pe[k].grad) < 0.3, (k, l2rel(params[k].grad, pe[k].grad))
+        a, b = params[k].grad.detach().float().cpu().reshape(-1), pe[k].grad.detach().float().reshape(-1)
+        assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.9, (k, l2rel(params[k].grad, pe[k].grad))
 
 
 @pytest.mark.parametrize("case", ["multi_conf", "multi_raw", "single", "agnostic", "one_empty_image", "nothing_passes"])
