@@ -110,6 +110,20 @@ typedef struct SgbWgradItem {
   int64_t start;
 } SgbWgradItem;
 int sgb_weight_prepare_batch(const SgbWeightItem* items_dev, int n_items, int64_t total, void* stream);
+typedef struct SgbAlphaItem {
+  const float* dw1;   /* fp32 KRSC [K][1][1][c_pad]: gradient of the FOLDED 1x1 filter (alpha * K1 + I) */
+  const float* w1;    /* fp32 OIHW [K][C][1][1]: branch_1x1.weight */
+  const float* alpha; /* fp32 [1] */
+  const float* dab;   /* fp32 [K]: gradient of (alpha * b1), or NULL */
+  const float* bias1; /* fp32 [K]: branch_1x1.bias, or NULL */
+  float* g_w1;        /* += alpha * dw1 */
+  float* g_bias;      /* += alpha * dab (NULL: skipped) */
+  float* g_alpha;     /* += <dw1, w1> + <dab, bias1> */
+  int32_t K, C, c_pad, pad_;
+} SgbAlphaItem;
+/* QARepVGG `alpha` chain rule for every block of a step in ONE launch (one CTA per block, fixed-order reduction): replaces
+ * mul / sum / add / addcmul_ launches per block (modules/qarepvgg_block.py:196-198: x_1x1 = alpha * branch_1x1(inputs)). */
+int sgb_qarep_alpha_finish_batch(const SgbAlphaItem* items_dev, int n_items, void* stream);
 int sgb_wgrad_to_oihw_batch(const SgbWgradItem* items_dev, int n_items, int64_t total, void* stream);
 /* ConvTranspose2d(kernel=2, stride=2) (modules/sampling.py:72-73): desc describes the EQUIVALENT 2x2/s2 convolution
  * from the upsampled tensor (N,H,W,C) to the small tensor (N,P,Q,K); w is [K_small][2][2][C_up] bf16. */
@@ -134,6 +148,12 @@ typedef struct SgbBnDesc {
   float eps, momentum;
   int32_t act;
   int32_t stats_repl;
+  int32_t dy_pitch, dy_off;      /* backward passes: layout of dy when it is a channel slice of a wider buffer (a concat's
+                                    gradient); dy_pitch == 0: dy is laid out like y */
+  /* drop-path (stochastic depth, training/utils/regularization_utils.py:4-15): y = act(bn(x) * sample_scale[n] + residual) with
+   * n = pixel / hw; sample_scale holds 0 or 1/keep_prob per image.  NULL: no drop-path. */
+  int64_t hw;
+  const float* sample_scale;
 } SgbBnDesc;
 /* Reduces stats -> mean / rstd (saved for backward), updates running stats, writes y = act(bn(x) + residual). */
 int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, const float* gamma, const float* beta,
@@ -166,6 +186,7 @@ typedef struct SgbQarepDesc {
   float eps3, eps_post, momentum;
   int32_t act;
   int32_t use_post_bn;
+  int32_t pitchd, offd; /* backward passes: layout of dout when it is a channel slice; pitchd == 0: laid out like out */
 } SgbQarepDesc;
 int sgb_qarep_moments(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments, void* stream);
 /* coef out: [9][C] floats = mu3, rstd3, mu_u, rstd_z, a3 (coefficient of y3), au (of u), c0 (constant),

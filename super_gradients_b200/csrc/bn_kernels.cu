@@ -174,7 +174,11 @@ struct BnFwdOp {
   }
   __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[2][8], float (&)[1][8]) const {
     V8 a = in.a;
-    if (res) {
+    if (d.sample_scale) {  // drop-path: the normalised branch of image n is scaled by 0 or 1 / keep_prob before the residual joins
+      const float ss = d.sample_scale[pix / d.hw];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) * ss + (res ? in.rr.v[e] : 0.f), d.act);
+    } else if (res) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + in.rr.v[e], d.act);
     } else {
@@ -250,13 +254,14 @@ struct BnBwdRedOp {
   };
   __device__ In load(int64_t pix, int c0) const {
     In in;
-    in.g = ld8(dy + pix * d.y_pitch + d.y_off + c0);
+    in.g = ld8(dy + pix * (d.dy_pitch ? d.dy_pitch : d.y_pitch) + (d.dy_pitch ? d.dy_off : d.y_off) + c0);
     in.xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
     if (y) in.yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
     return in;
   }
-  __device__ void finish(int64_t, int, const In& in, const float (&r)[4][8], float (&acc)[2][8]) const {
+  __device__ void finish(int64_t pix, int, const In& in, const float (&r)[4][8], float (&acc)[2][8]) const {
     const V8 &g = in.g, &xv = in.xv, &yv = in.yv;
+    const float ss = d.sample_scale ? d.sample_scale[pix / d.hw] : 1.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = g.v[e];
@@ -264,6 +269,7 @@ struct BnBwdRedOp {
         const float pre = y ? yv.v[e] : fmaf(xv.v[e], r[2][e], r[3][e]);  // same FMA as the forward pass
         dz = pre > 0.f ? dz : 0.f;
       }
+      dz *= ss;  // gradient reaching the normalised branch (drop-path)
       acc[0][e] += dz;
       acc[1][e] = fmaf(dz, (xv.v[e] - r[0][e]) * r[1][e], acc[1][e]);
     }
@@ -303,13 +309,14 @@ struct BnBwdApplyOp {
   };
   __device__ In load(int64_t pix, int c0) const {
     In in;
-    in.g = ld8(dy + pix * d.y_pitch + d.y_off + c0);
+    in.g = ld8(dy + pix * (d.dy_pitch ? d.dy_pitch : d.y_pitch) + (d.dy_pitch ? d.dy_off : d.y_off) + c0);
     in.xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
     if (y) in.yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
     return in;
   }
   __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[6][8], float (&)[1][8]) const {
     const V8 &g = in.g, &xv = in.xv, &yv = in.yv;
+    const float ss = d.sample_scale ? d.sample_scale[pix / d.hw] : 1.f;
     V8 o, dr;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -318,9 +325,10 @@ struct BnBwdApplyOp {
         const float pre = y ? yv.v[e] : fmaf(xv.v[e], r[2][e], r[3][e]);
         dz = pre > 0.f ? dz : 0.f;
       }
+      dr.v[e] = dz;  // the residual sees the unscaled gradient
+      dz *= ss;
       const float xh = (xv.v[e] - r[0][e]) * r[1][e];
       o.v[e] = r[2][e] * (dz - r[4][e] - xh * r[5][e]);
-      dr.v[e] = dz;
     }
     st8(dx + pix * d.x_pitch + d.x_off + c0, o);
     if (dres) st8(dres + pix * d.r_pitch + d.r_off + c0, dr);
@@ -442,7 +450,7 @@ struct QarepBwdRedOp {
   };
   __device__ In load(int64_t pix, int c0) const {
     In in;
-    in.g = ld8(dout + pix * d.pitcho + d.offo + c0);
+    in.g = ld8(dout + pix * (d.pitchd ? d.pitchd : d.pitcho) + (d.pitchd ? d.offd : d.offo) + c0);
     in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
     in.b = ld8(u + pix * d.pitchu + d.offu + c0);
     return in;
@@ -521,7 +529,7 @@ struct QarepBwdApplyOp {
   };
   __device__ In load(int64_t pix, int c0) const {
     In in;
-    in.g = ld8(dout + pix * d.pitcho + d.offo + c0);
+    in.g = ld8(dout + pix * (d.pitchd ? d.pitchd : d.pitcho) + (d.pitchd ? d.offd : d.offo) + c0);
     in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
     in.b = ld8(u + pix * d.pitchu + d.offu + c0);
     return in;
@@ -557,13 +565,16 @@ int check_bn(const SgbBnDesc* d) {
   SGB_REQUIRE(d->x_pitch % 8 == 0 && d->x_off % 8 == 0 && d->y_pitch % 8 == 0 && d->y_off % 8 == 0,
               "pitch/offset multiples of 8");
   SGB_REQUIRE(d->C <= 4096, "C too large for the shared-memory coefficient cache");
+  SGB_REQUIRE(!d->sample_scale || (d->hw > 0 && d->M % d->hw == 0), "drop-path: hw must divide M");
+  SGB_REQUIRE(d->dy_pitch % 8 == 0 && d->dy_off % 8 == 0 && (d->dy_pitch == 0 || d->dy_pitch >= d->dy_off + d->C), "dy slice layout");
   return SGB_OK;
 }
 int check_qarep(const SgbQarepDesc* d) {
   SGB_REQUIRE(d && d->M > 0 && d->C > 0 && d->C % 8 == 0 && d->C <= 2048, "bad desc");
   SGB_REQUIRE(d->pitch3 % 8 == 0 && d->off3 % 8 == 0 && d->pitchu % 8 == 0 && d->offu % 8 == 0 &&
-                  d->pitcho % 8 == 0 && d->offo % 8 == 0,
+                  d->pitcho % 8 == 0 && d->offo % 8 == 0 && d->pitchd % 8 == 0 && d->offd % 8 == 0,
               "pitch/offset multiples of 8");
+  SGB_REQUIRE(d->pitchd == 0 || d->pitchd >= d->offd + d->C, "dout slice layout");
   return SGB_OK;
 }
 
@@ -593,6 +604,7 @@ extern "C" int sgb_bn_act_bwd_reduce(const SgbBnDesc* d, const sgb_bf16* dy, con
                                      const float* save_rstd, double* sums, void* stream) {
   if (int rc = check_bn(d)) return rc;
   SGB_REQUIRE(dy && x && save_mean && save_rstd && sums, "null pointer");
+  SGB_REQUIRE(!d->sample_scale || y, "drop-path backward needs the forward output (the mask cannot be recomputed from x alone)");
   BnBwdRedOp op{*d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean, save_rstd, gamma, beta, sums, d->C};
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_bwd_reduce");
 }
@@ -603,6 +615,7 @@ extern "C" int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, cons
                                     float* dgamma, float* dbeta, void* stream) {
   if (int rc = check_bn(d)) return rc;
   SGB_REQUIRE(dy && x && save_mean && save_rstd && sums && dx, "null pointer");
+  SGB_REQUIRE(!d->sample_scale || y, "drop-path backward needs the forward output (the mask cannot be recomputed from x alone)");
   BnBwdApplyOp op{*d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, beta, save_mean, save_rstd, sums, (bf16*)dx, (bf16*)dresidual, dgamma, dbeta};
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_bwd_apply");
 }

@@ -134,6 +134,36 @@ __global__ void wgrad_to_oihw_batch_kernel(const SgbWgradItem* __restrict__ item
   }
 }
 
+__global__ void __launch_bounds__(256) qarep_alpha_finish_kernel(const SgbAlphaItem* __restrict__ items) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
+  const SgbAlphaItem it = items[blockIdx.x];
+  const float alpha = *it.alpha;
+  float acc = 0.f;
+  const int total = it.K * it.C;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int k = i / it.C, c = i - k * it.C;
+    const float g = it.dw1[(int64_t)k * it.c_pad + c];
+    acc = fmaf(g, it.w1[i], acc);
+    it.g_w1[i] += alpha * g;
+  }
+  if (it.dab) {
+    for (int k = threadIdx.x; k < it.K; k += blockDim.x) {
+      const float g = it.dab[k];
+      if (it.bias1) acc = fmaf(g, it.bias1[k], acc);
+      if (it.g_bias) it.g_bias[k] += alpha * g;
+    }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {  // fixed order: reproducible
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && it.g_alpha) *it.g_alpha += red[0];
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W, bf16* y, int pitch,
                                     int off, int cpad) {
   SGB_GRID_DEP_LAUNCH();
@@ -483,6 +513,13 @@ extern "C" int sgb_wgrad_to_oihw_batch(const SgbWgradItem* items_dev, int n_item
   SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
   SGB_LAUNCH(wgrad_to_oihw_batch_kernel, grid_for(total), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
   SGB_LAUNCH_CHECK("wgrad_to_oihw_batch_kernel");
+  return SGB_OK;
+}
+
+extern "C" int sgb_qarep_alpha_finish_batch(const SgbAlphaItem* items_dev, int n_items, void* stream) {
+  SGB_REQUIRE(items_dev && n_items > 0, "bad args");
+  SGB_LAUNCH(qarep_alpha_finish_kernel, n_items, 256, 0, (cudaStream_t)stream, items_dev);
+  SGB_LAUNCH_CHECK("qarep_alpha_finish_kernel");
   return SGB_OK;
 }
 

@@ -38,6 +38,10 @@ def bump_weight_epoch():
     _WEIGHT_EPOCH[0] += 1
 
 
+def weight_epoch() -> int:
+    return _WEIGHT_EPOCH[0]
+
+
 class StepContext:
     """Per-TrainStep state of the batched plumbing: the filter caches its model touched, the device work tables of the
     batched filter re-layout / gradient layout change (kept alive here because a captured CUDA graph reads them) and the
@@ -50,6 +54,15 @@ class StepContext:
         self.pending = []         # (dw fp32 KRSC, C, slot)
         self.wgrad_table = None
         self.wgrad_key = None
+        self.alpha_pending = []   # QARepVGG alpha chain rule of every block, finished by one batched launch (flush_wgrads)
+        self.alpha_table = None
+        self.alpha_key = None
+        # Weight gradients are off the critical path of backward (nothing consumes them before the optimizer): with a side
+        # stream they run concurrently with the dgrad / BatchNorm-backward chain (fork per wgrad, ONE join in flush_wgrads);
+        # under stream capture the fork / join become parallel branches of the CUDA graph.
+        self.side_stream = None   # torch.cuda.Stream or None (set by TrainStep)
+        self.side_used = False
+        self.keep = []            # operands of side-stream launches, referenced until the join
 
 
 _CTX = [None]  # the StepContext of the TrainStep that is executing (None: per-layer launches everywhere)
@@ -59,6 +72,9 @@ def set_step_context(ctx: Optional["StepContext"]):
     _CTX[0] = ctx
     if ctx is not None:
         ctx.pending.clear()
+        ctx.alpha_pending.clear()
+        ctx.keep.clear()
+        ctx.side_used = False
 
 
 class WeightCache:
@@ -109,6 +125,19 @@ def refresh_weight_caches(ctx: StepContext, device) -> int:
 
 def flush_wgrads(ctx: StepContext, device) -> int:
     """Converts every deferred fp32 KRSC weight gradient of this step into its OIHW gradient slot with one launch."""
+    if ctx.side_used:  # join: every side-stream weight gradient is complete before the layout pass / optimizer read it
+        ev = torch.cuda.Event()
+        ev.record(ctx.side_stream)
+        torch.cuda.current_stream().wait_event(ev)
+        ctx.side_used = False
+    ctx.keep.clear()
+    if ctx.alpha_pending:
+        ident = tuple(tuple(None if t is None else (t.data_ptr() if torch.is_tensor(t) else t) for t in e) for e in ctx.alpha_pending)
+        if ctx.alpha_key != ident:
+            ctx.alpha_table = K.qarep_alpha_finish_table(ctx.alpha_pending, device)
+            ctx.alpha_key = ident
+        K.run_qarep_alpha_finish(*ctx.alpha_table)
+        ctx.alpha_pending.clear()
     pend = ctx.pending
     if not pend:
         return 0
@@ -182,11 +211,28 @@ def _deliver(slot, grad):
     return None
 
 
+def _side_wgrad(ctx, x, dy, r, s, stride, pad):
+    """conv_wgrad on the context's side stream (after everything queued so far on the current stream); the result may only
+    be read after flush_wgrads() joined the streams."""
+    dw = K.zeros((dy.shape[1], r, s, x.shape[1]), torch.float32, x.device)  # arena (host-side) or a fill on the current stream
+    main, side = torch.cuda.current_stream(), ctx.side_stream
+    ev = torch.cuda.Event()
+    ev.record(main)
+    with torch.cuda.stream(side):
+        side.wait_event(ev)
+        K.conv_wgrad(x, dy, r, s, stride, pad, dw_krsc=dw)
+    ctx.keep.append((x, dy, dw))
+    ctx.side_used = True
+    return dw
+
+
 def _wgrad(x, dy, r, s, stride, pad, cin, slot):
-    dw = K.conv_wgrad(x, dy, r, s, stride, pad)
-    if slot is not None and _CTX[0] is not None:
-        _CTX[0].pending.append((dw, cin, slot))  # dw (step arena or a plain tensor) stays referenced until flush_wgrads()
+    ctx = _CTX[0]
+    if slot is not None and ctx is not None:
+        dw = _side_wgrad(ctx, x, dy, r, s, stride, pad) if ctx.side_stream is not None else K.conv_wgrad(x, dy, r, s, stride, pad)
+        ctx.pending.append((dw, cin, slot))  # dw (step arena or a plain tensor) stays referenced until flush_wgrads()
         return None
+    dw = K.conv_wgrad(x, dy, r, s, stride, pad)
     if slot is not None:
         K.wgrad_to_oihw(dw, cin, out=slot, accumulate=True)
         return None
@@ -238,7 +284,8 @@ class _ConvBnAct(torch.autograd.Function):
         stats = K.new_stats(kout, x.device)
         y_raw = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, stats=stats)
         res = K.as_nhwc(residual) if residual is not None else None
-        out, mean, rstd = K.bn_act_fwd(y_raw, stats, gamma, beta, cfg.running_mean, cfg.running_var, cfg.eps, cfg.momentum, cfg.act, res)
+        ss = getattr(cfg, "sample_scale", None)
+        out, mean, rstd = K.bn_act_fwd(y_raw, stats, gamma, beta, cfg.running_mean, cfg.running_var, cfg.eps, cfg.momentum, cfg.act, res, **({"sample_scale": ss} if ss is not None else {}))
         if cfg.num_batches_tracked is not None and not _NBT_DEFERRED[0]:
             cfg.num_batches_tracked += 1
         ctx.save_for_backward(x, y_raw, out, gamma, mean, rstd, beta)
@@ -252,7 +299,8 @@ class _ConvBnAct(torch.autograd.Function):
         cfg = ctx.cfg
         kout, cin, r, s = ctx.wshape
         sw, sg, sb = ctx.slots
-        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res, dgamma=sg, dbeta=sb, beta=beta)
+        ss = getattr(cfg, "sample_scale", None)
+        dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res, dgamma=sg, dbeta=sb, beta=beta, **({"sample_scale": ss} if ss is not None else {}))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad)
@@ -260,12 +308,13 @@ class _ConvBnAct(torch.autograd.Function):
         return dx, dw, (None if sg is not None else dgamma), (None if sb is not None else dbeta), dres, None
 
 
-def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracked, *, stride, pad, eps, momentum, act, training, cache: WeightCache, residual=None):
-    """Conv2d(bias=False) -> BatchNorm2d -> (+ residual) -> activation.   reference: modules/conv_bn_act_block.py:92-93,
-    training/models/classification_models/resnet.py:53-84 (the residual form)."""
+def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracked, *, stride, pad, eps, momentum, act, training, cache: WeightCache, residual=None, sample_scale=None):
+    """Conv2d(bias=False) -> BatchNorm2d -> (* drop-path scale per image) -> (+ residual) -> activation.   reference:
+    modules/conv_bn_act_block.py:92-93, training/models/classification_models/resnet.py:53-84 (the residual form),
+    training/utils/regularization_utils.py:4-15 (drop_path; `sample_scale` = bernoulli(keep) / keep per image, training only)."""
     K.require_cuda(x, "x")
     if training:
-        cfg = SimpleNamespace(stride=stride, pad=pad, eps=eps, momentum=momentum, act=act, cache=cache, running_mean=running_mean, running_var=running_var, num_batches_tracked=num_batches_tracked)
+        cfg = SimpleNamespace(stride=stride, pad=pad, eps=eps, momentum=momentum, act=act, cache=cache, running_mean=running_mean, running_var=running_var, num_batches_tracked=num_batches_tracked, sample_scale=sample_scale)
         return _ConvBnAct.apply(x, w, gamma, beta, residual, cfg)
     # inference: BN folded into the GEMM epilogue (one kernel)
     with torch.no_grad():
@@ -389,6 +438,13 @@ class _QARepVGG(torch.autograd.Function):
                 sbias.addcmul_(dab, alpha)
             sw1.addcmul_(dw1f, alpha)
             salpha.add_(dalpha_v)
+            dw1 = dbias1 = dalpha = None
+        elif has_alpha and dw1f is None and _CTX[0] is not None and sw1 is not None and salpha is not None and (sbias is not None or not has_bias):
+            # batched plumbing: the 1x1 weight gradient goes to the side stream (when there is one) and the alpha chain rule of
+            # every block is finished by ONE launch in flush_wgrads() instead of ~7 small launches per block
+            c = _CTX[0]
+            dw1k = _side_wgrad(c, x, du, 1, 1, cfg.stride, 0) if c.side_stream is not None else K.conv_wgrad(x, du, 1, 1, cfg.stride, 0)
+            c.alpha_pending.append((dw1k, cin, w1, alpha, dab if has_bias else None, bias1 if has_bias else None, sw1, sbias if has_bias else None, salpha))
             dw1 = dbias1 = dalpha = None
         elif has_alpha:
             if dw1f is None:

@@ -292,6 +292,22 @@ def run_wgrad_to_oihw_batch(table, n, total):
     _timed("sgb_wgrad_to_oihw_batch", _ptr(table), n, total, _stream())
 
 
+def qarep_alpha_finish_table(entries, device):
+    """entries: (dw1 fp32 KRSC [K,1,1,c_pad], C, w1, alpha, dab or None, bias1 or None, g_w1, g_bias or None, g_alpha)."""
+    items = []
+    for dw1, C, w1, alpha, dab, bias1, g_w1, g_bias, g_alpha in entries:
+        it = L.AlphaItem()
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        it.dw1, it.w1, it.alpha, it.dab, it.bias1, it.g_w1, it.g_bias, it.g_alpha = p(dw1), p(w1), p(alpha), p(dab), p(bias1), p(g_w1), p(g_bias), p(g_alpha)
+        it.K, it.C, it.c_pad, it.pad_ = dw1.shape[0], C, dw1.shape[3], 0
+        items.append(it)
+    return _item_table(items).to(device), len(items)
+
+
+def run_qarep_alpha_finish(table, n):
+    _timed("sgb_qarep_alpha_finish_batch", _ptr(table), n, _stream())
+
+
 def convt2x2_fprop(x_small, w_up, bias, C_up):
     """ConvTranspose2d(k=2, s=2): x_small [N,K,P,Q] -> [N,C_up,2P,2Q]; w_up bf16 [(dh,dw,c_up)][K]."""
     n, K, P, Q = x_small.shape
@@ -388,9 +404,14 @@ def detection_matching(preds, pred_count, targets, target_count, crowd, crowd_co
 
 
 # ------------------------------------------------------------------------------------------------ batch norm
-def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL) -> L.BnDesc:
+def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL, sample_scale=None) -> L.BnDesc:
     n, c, h, w = x.shape
     d = L.BnDesc()
+    if sample_scale is not None:  # drop-path: fp32 [N], 0 or 1 / keep_prob per image
+        if sample_scale.dtype != torch.float32 or sample_scale.numel() != n or not sample_scale.is_contiguous():
+            raise L.SgbError("sample_scale must be a contiguous fp32 tensor with one entry per image")
+        require_cuda(sample_scale, "sample_scale")
+        d.hw, d.sample_scale = h * w, sample_scale.data_ptr()
     d.M, d.C = n * h * w, c
     d.x_pitch, d.x_off = nhwc_pitch(x), 0
     d.y_pitch, d.y_off = nhwc_pitch(y), 0
@@ -401,12 +422,12 @@ def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL) -> L
     return d
 
 
-def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None):
+def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None, sample_scale=None):
     n, c, h, w = x.shape
     y = empty_nhwc(n, c, h, w, x.device)
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     rstd = torch.empty(c, dtype=torch.float32, device=x.device)
-    d = bn_desc(x, y, eps, momentum, act, residual, stats.shape[0])
+    d = bn_desc(x, y, eps, momentum, act, residual, stats.shape[0], sample_scale=sample_scale)
     _timed("sgb_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _ptr(mean), _ptr(rstd), _stream())
     return y, mean, rstd
 
@@ -419,18 +440,22 @@ def bn_act_infer(x, gamma, beta, running_mean, running_var, eps, act, residual=N
     return y
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None):
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None, sample_scale=None):
     """Returns (dx, dresidual or None, dgamma, dbeta); dgamma / dbeta are accumulated into when given."""
     n, c, h, w = x.shape
     dy = as_nhwc(dy)
-    d = bn_desc(x, y, eps, 0.0, act, None, 1)
+    d = bn_desc(x, y, eps, 0.0, act, None, 1, sample_scale=sample_scale)
     if nhwc_pitch(dy) != d.y_pitch:
-        dy = dy.contiguous(memory_format=torch.channels_last)
-        if nhwc_pitch(dy) != d.y_pitch:
-            raise L.SgbError("dy pitch mismatch")
+        # dy is a channel slice of a wider gradient buffer (the layer's output went into a concat): the kernels read it in place
+        if nhwc_pitch(dy) % 8 == 0 and dy.data_ptr() % 16 == 0:
+            d.dy_pitch, d.dy_off = nhwc_pitch(dy), 0
+        else:
+            dy = dy.contiguous(memory_format=torch.channels_last)
+            if nhwc_pitch(dy) != d.y_pitch:
+                raise L.SgbError("dy pitch mismatch")
     sums = zeros((2, c), torch.float64, x.device)
     # the forward output is only read when a residual entered the activation; otherwise the mask is recomputed from x
-    y_arg = y if (want_residual_grad or beta is None) else None
+    y_arg = y if (want_residual_grad or beta is None or sample_scale is not None) else None
     _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
     dx = torch.empty_like(x, memory_format=torch.channels_last) if nhwc_pitch(x) == c else torch.zeros_like(x)
     d.x_pitch = nhwc_pitch(dx)
@@ -488,9 +513,12 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
     y3 / u are slices); by default dense tensors are allocated, which requires dense y3 / u."""
     n, c, h, w = y3.shape
     dout = as_nhwc(dout)
-    if nhwc_pitch(dout) != nhwc_pitch(out):
-        dout = dout.contiguous(memory_format=torch.channels_last)
     d = qarep_desc(y3, u, out, eps3, eps_post, 0.0, act, use_post_bn)
+    if nhwc_pitch(dout) != nhwc_pitch(out):
+        if nhwc_pitch(dout) % 8 == 0 and dout.data_ptr() % 16 == 0:  # a concat's gradient slice: read in place
+            d.pitchd, d.offd = nhwc_pitch(dout), 0
+        else:
+            dout = dout.contiguous(memory_format=torch.channels_last)
     sums = zeros((3, c), torch.float64, y3.device)
     _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
     if out_grads is not None:
@@ -692,7 +720,7 @@ def batched_nms(boxes, scores, score_thr, iou_thr, top_k, max_out, multi_label=T
     cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
     nbytes = L.load().sgb_nms_workspace_bytes(ctypes.byref(d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
-    L.call("sgb_batched_nms", ctypes.byref(d), _ptr(boxes), _ptr(scores), _ptr(out), _ptr(oidx), _ptr(cnt), _ptr(ws), nbytes, _stream())
+    _timed("sgb_batched_nms", ctypes.byref(d), _ptr(boxes), _ptr(scores), _ptr(out), _ptr(oidx), _ptr(cnt), _ptr(ws), nbytes, _stream())
     return out, oidx, cnt
 
 

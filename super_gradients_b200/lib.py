@@ -41,6 +41,10 @@ class WgradItem(Structure):  # SgbWgradItem
     _fields_ = [("dw", c_void_p), ("g", c_void_p)] + [(n, c_int32) for n in ("K", "C", "R", "S", "c_pad", "accumulate")] + [("start", c_int64)]
 
 
+class AlphaItem(Structure):  # SgbAlphaItem
+    _fields_ = [(n, c_void_p) for n in ("dw1", "w1", "alpha", "dab", "bias1", "g_w1", "g_bias", "g_alpha")] + [(n, c_int32) for n in ("K", "C", "c_pad", "pad_")]
+
+
 class BnDesc(Structure):
     _fields_ = [
         ("M", c_int64),
@@ -55,6 +59,10 @@ class BnDesc(Structure):
         ("momentum", c_float),
         ("act", c_int32),
         ("stats_repl", c_int32),
+        ("dy_pitch", c_int32),
+        ("dy_off", c_int32),
+        ("hw", c_int64),
+        ("sample_scale", c_void_p),
     ]
 
 
@@ -73,6 +81,8 @@ class QarepDesc(Structure):
         ("momentum", c_float),
         ("act", c_int32),
         ("use_post_bn", c_int32),
+        ("pitchd", c_int32),
+        ("offd", c_int32),
     ]
 
 
@@ -145,6 +155,7 @@ _SIGNATURES = {
     "sgb_wgrad_to_oihw": (c_int, [P, _I, _I, _I, _I, _I, P, _I, P]),
     "sgb_weight_prepare_batch": (c_int, [P, _I, c_int64, P]),
     "sgb_wgrad_to_oihw_batch": (c_int, [P, _I, c_int64, P]),
+    "sgb_qarep_alpha_finish_batch": (c_int, [P, _I, P]),
     "sgb_convt2x2_fprop": (c_int, [POINTER(ConvDesc), P, P, P, P, P]),
     "sgb_nchw_f32_to_nhwc_bf16": (c_int, [P, _I, _I, _I, _I, P, _I, _I, _I, P]),
     "sgb_nhwc_bf16_to_nchw_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, P, P]),

@@ -29,7 +29,7 @@ def check_conv_supported(conv: nn.Conv2d):
 class _FusedConvBN:
     """Mixin: runs conv -> bn -> act of sibling nn.Conv2d / nn.BatchNorm2d parameter containers through the fused path."""
 
-    def _fused(self, x, conv: nn.Conv2d, bn, act_code: str, cache, residual=None):
+    def _fused(self, x, conv: nn.Conv2d, bn, act_code: str, cache, residual=None, sample_scale=None):
         stride, pad = _single(conv.stride), _single(conv.padding)
         if bn is None:
             return SF.conv_bias(x, conv.weight, conv.bias, stride=stride, pad=pad, cache=cache, act=act_code)
@@ -38,7 +38,7 @@ class _FusedConvBN:
         momentum = 0.1 if bn.momentum is None else bn.momentum
         return SF.conv_bn_act(
             x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-            stride=stride, pad=pad, eps=bn.eps, momentum=momentum, act=act_code, training=self.training and bn.training, cache=cache, residual=residual,
+            stride=stride, pad=pad, eps=bn.eps, momentum=momentum, act=act_code, training=self.training and bn.training, cache=cache, residual=residual, sample_scale=sample_scale,
         )  # fmt: skip
 
 

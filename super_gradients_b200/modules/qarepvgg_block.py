@@ -79,6 +79,7 @@ class QARepVGGBlock(nn.Module):
         self._cache3, self._cache1, self._cache_eq = SF.WeightCache(), SF.WeightCache(), SF.WeightCache()
         self._cache_fold = SF.FoldedWeightCache()
         self._eq = None
+        self._eval_fold = None  # (key, bf16 KRSC filter, scale, shift) of the on-the-fly eval fold
         if not build_residual_branches:
             self.fuse_block_residual_branches()
 
@@ -105,18 +106,35 @@ class QARepVGGBlock(nn.Module):
                 inputs, self.branch_3x3.conv.weight, bn3.weight, bn3.bias, self.branch_1x1.weight, self.branch_1x1.bias, alpha,
                 pbn.weight if pbn is not None else None, pbn.bias if pbn is not None else None, cfg,
             )  # fmt: skip
-        # eval with branches: fold them on the fly (numerically the reference's partial fusion, max abs err ~5e-6)
+        # eval with branches: fold them (numerically the reference's partial fusion, max abs err ~5e-6).  The folded bf16 filter
+        # and the post_bn scale / shift are kept until one of their SOURCE tensors changes, so a steady-state inference forward of
+        # the block is exactly one GEMM launch (predict() on an unfused model costs what the reference's fused model costs).
         with torch.no_grad():
-            k, b = self._get_equivalent_kernel_bias_for_branches()
-            return self._forward_single_conv(inputs, k, b, extra_key=("eval", self._eval_source_key()))
+            x = K.as_nhwc(inputs)
+            key = (self._eval_source_key(), x.shape[1], SF.weight_epoch())
+            if self._eval_fold is None or self._eval_fold[0] != key:
+                k, b = self._get_equivalent_kernel_bias_for_branches()
+                krsc, _ = K.weight_prepare(k, c_pad=x.shape[1], want_crsk=False)
+                if self.use_post_bn:
+                    pbn = self.post_bn
+                    scale = pbn.weight * torch.rsqrt(pbn.running_var + pbn.eps)
+                    shift = pbn.bias - pbn.running_mean * scale + b * scale
+                else:
+                    scale, shift = None, b
+                self._eval_fold = (key, krsc, scale, shift)
+            _, krsc, scale, shift = self._eval_fold
+            return K.conv_fprop(x, krsc, self.out_channels, 3, 3, self.stride, 1, scale=scale, shift=shift, act=self._act_code)
 
     def _eval_source_key(self):
-        """Identity + version of every tensor the folded eval kernel is computed from: `k` itself is a temporary whose
-        address the caching allocator reuses, so it cannot key the bf16 filter cache (load_state_dict / in-place edits)."""
+        """Identity + version of every tensor the folded eval kernel is computed from.  The folded kernel itself is a temporary
+        whose address the caching allocator reuses, so it cannot key a cache (load_state_dict / in-place edits would go unnoticed);
+        optimizer steps that write parameters through raw pointers are covered by functional.weight_epoch()."""
         bn = self.branch_3x3.bn
         srcs = [self.branch_3x3.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, self.branch_1x1.weight, self.branch_1x1.bias]
         if isinstance(self.alpha, torch.Tensor):
             srcs.append(self.alpha)
+        if self.use_post_bn:
+            srcs += [self.post_bn.weight, self.post_bn.bias, self.post_bn.running_mean, self.post_bn.running_var]
         return tuple((t.data_ptr(), t._version) for t in srcs if t is not None)
 
     def _forward_single_conv(self, x, weight, bias, extra_key=None):

@@ -11,6 +11,7 @@ from ....common.registry import register_model
 from ....modules.conv_bn_act_block import _FusedConvBN
 from ....modules.utils import width_multiplier
 from ...utils import get_param
+from ...utils.regularization_utils import DropPath
 from ..sg_module import SgModule
 
 
@@ -27,15 +28,13 @@ class _Block(nn.Module, _FusedConvBN):
 class BasicResNetBlock(_Block):
     def __init__(self, in_planes, planes, stride=1, expansion=1, final_relu=True, droppath_prob=0.0):
         super().__init__()
-        if droppath_prob:
-            raise NotImplementedError("drop-path is not implemented on the fused path (use droppath_prob=0)")
         self.expansion = expansion
         self.conv1 = nn.Conv2d(in_planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
         self.final_relu = final_relu
-        self.drop_path = nn.Identity()
+        self.drop_path = DropPath(drop_prob=droppath_prob)  # draws the per-image mask; the multiply runs inside the fused bn + add kernel
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != self.expansion * planes:
             self.shortcut = nn.Sequential(nn.Conv2d(in_planes, self.expansion * planes, kernel_size=1, stride=stride, bias=False), nn.BatchNorm2d(self.expansion * planes))
@@ -43,14 +42,12 @@ class BasicResNetBlock(_Block):
 
     def forward(self, x):
         out = self._fused(x, self.conv1, self.bn1, "relu", self._caches[0])
-        return self._fused(out, self.conv2, self.bn2, "relu" if self.final_relu else "none", self._caches[1], residual=self._shortcut(x))
+        return self._fused(out, self.conv2, self.bn2, "relu" if self.final_relu else "none", self._caches[1], residual=self._shortcut(x), sample_scale=self.drop_path.sample_scale(x))
 
 
 class Bottleneck(_Block):
     def __init__(self, in_planes, planes, stride=1, expansion=4, final_relu=True, droppath_prob=0.0):
         super().__init__()
-        if droppath_prob:
-            raise NotImplementedError("drop-path is not implemented on the fused path (use droppath_prob=0)")
         self.expansion = expansion
         self.conv1 = nn.Conv2d(in_planes, planes, kernel_size=1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
@@ -59,7 +56,7 @@ class Bottleneck(_Block):
         self.conv3 = nn.Conv2d(planes, self.expansion * planes, kernel_size=1, bias=False)
         self.bn3 = nn.BatchNorm2d(self.expansion * planes)
         self.final_relu = final_relu
-        self.drop_path = nn.Identity()
+        self.drop_path = DropPath(drop_prob=droppath_prob)  # draws the per-image mask; the multiply runs inside the fused bn + add kernel
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != self.expansion * planes:
             self.shortcut = nn.Sequential(nn.Conv2d(in_planes, self.expansion * planes, kernel_size=1, stride=stride, bias=False), nn.BatchNorm2d(self.expansion * planes))
@@ -68,7 +65,7 @@ class Bottleneck(_Block):
     def forward(self, x):
         out = self._fused(x, self.conv1, self.bn1, "relu", self._caches[0])
         out = self._fused(out, self.conv2, self.bn2, "relu", self._caches[1])
-        return self._fused(out, self.conv3, self.bn3, "relu" if self.final_relu else "none", self._caches[2], residual=self._shortcut(x))
+        return self._fused(out, self.conv3, self.bn3, "relu" if self.final_relu else "none", self._caches[2], residual=self._shortcut(x), sample_scale=self.drop_path.sample_scale(x))
 
 
 class _Classifier(SgModule, _FusedConvBN):

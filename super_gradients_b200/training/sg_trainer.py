@@ -214,6 +214,8 @@ class TrainStep:
         self.batched_plumbing = True
         self.arena = K.StepArena()   # zero-initialised scratch of one step (owned here: a captured graph replays its addresses)
         self.ctx = SF.StepContext()  # filter caches + batched work tables of this model
+        if self.device.type == "cuda" and os.environ.get("SGB_SIDE_WGRAD", "1") != "0":
+            self.ctx.side_stream = torch.cuda.Stream(device=self.device)  # weight gradients overlap the dgrad / BN-backward chain
         self._nbt = [b for n, b in model.named_buffers() if n.endswith("num_batches_tracked")]
 
     # -------------------------------------------------------------------------------------------- host-side schedule
@@ -358,6 +360,10 @@ class TrainStep:
         clone = lambda t: t.clone() if torch.is_tensor(t) else type(t)(clone(u) for u in t)  # noqa: E731
         warmup = max(warmup, 2)  # step 1 sizes the zero arena, step 2 builds the batched work tables the graph replays
         self.static_in = (clone(inputs), clone(targets))
+        # The warm-up steps exist to size the arena / build the work tables, not to train: parameters, optimizer moments, EMA,
+        # BatchNorm buffers and the step counter are restored afterwards, so a captured run follows the eager trajectory.
+        live = [t for t in (self.flat.params, *self.state, getattr(self, "ema_params", None), getattr(self, "ema_buffers", None), self.flat.buffers, *self._nbt) if torch.is_tensor(t) and t.numel()]
+        saved, steps0 = [t.clone() for t in live], self.opt_steps
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -365,6 +371,10 @@ class TrainStep:
                 self._step_eager(*self.static_in)
                 self.opt_steps += 1
         torch.cuda.current_stream().wait_stream(s)
+        with torch.no_grad():
+            for t, v in zip(live, saved):
+                t.copy_(v)
+        self.opt_steps = steps0
         torch.cuda.synchronize()
         SF.bump_weight_epoch()
         split = (self.world > 1 and os.environ.get("SGB_NCCL_IN_GRAPH") != "1") or os.environ.get("SGB_SPLIT_GRAPH") == "1"

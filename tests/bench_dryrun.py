@@ -112,6 +112,7 @@ for n in ("conv_fprop", "conv_dgrad", "conv_wgrad"):
 mp.setattr(sg_trainer, "setup_device", setup_device)
 mp.setattr(sg_trainer.TrainStep, "_capture_region", fake_capture_region)
 mp.setattr(bench, "synth_batch", synth_batch)
+mp.setitem(bench.CONFIGS[2], "img", 32)  # the stand-in runs the graph of a 32 x 32 input
 mp.setattr(torch.cuda, "Event", FakeEvent)
 mp.setattr(torch.cuda, "Stream", FakeStream)
 mp.setattr(torch.cuda, "current_stream", lambda *a: FakeStream())
@@ -127,13 +128,19 @@ if os.environ.get("SGB_DRYRUN_THROTTLE") == "1":
 
         calls = 0
 
-        def __init__(self, index):
+        def __init__(self, index, enabled=True):
             pass
 
         def start(self):
             pass
 
+        def mark(self):
+            pass
+
         def stop(self):
+            pass
+
+        def snapshot(self):
             ThrottledOnce.calls += 1
             hot = ThrottledOnce.calls == 1 and os.environ.get("RANK", "0") == "0"
             return {"sm_mhz": 1500.0, "sm_max_mhz": 1965.0, "reasons": ["hw_slowdown"] if hot else [], "samples": 3}

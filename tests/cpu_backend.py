@@ -247,6 +247,25 @@ def run_wgrad_to_oihw_batch(table, n, total):
         wgrad_to_oihw(dw, C, out=g, accumulate=accumulate)
 
 
+def qarep_alpha_finish_table(entries, device):
+    return list(entries), len(entries)
+
+
+def run_qarep_alpha_finish(table, n):
+    assert len(table) == n
+    for dw1, C, w1, alpha, dab, bias1, g_w1, g_bias, g_alpha in table:
+        g = dw1[:, 0, 0, :C]
+        acc = (g * w1[:, :, 0, 0]).sum()
+        g_w1.add_((alpha * g).reshape(g_w1.shape))
+        if dab is not None:
+            if bias1 is not None:
+                acc = acc + (dab * bias1).sum()
+            if g_bias is not None:
+                g_bias.add_(alpha * dab)
+        if g_alpha is not None:
+            g_alpha.add_(acc.reshape(g_alpha.shape))
+
+
 def _cv(t):
     return t.float().view(1, -1, 1, 1)
 
@@ -257,7 +276,7 @@ def _update_running(rm, rv, mean, var_biased, M, momentum):
         rv.mul_(1 - momentum).add_(momentum * var_biased * (M / max(M - 1, 1)))
 
 
-def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None):
+def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None, sample_scale=None):
     n, c, h, w = x.shape
     M = n * h * w
     tot = stats.sum(0)  # [2, C] fp64
@@ -265,6 +284,8 @@ def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, 
     var = (tot[1] / M - mean * mean).clamp_min(0)
     rstd = torch.rsqrt(var + eps)
     y = (x.float() - _cv(mean)) * _cv(rstd) * _cv(gamma) + _cv(beta)
+    if sample_scale is not None:
+        y = y * sample_scale.float().view(-1, 1, 1, 1)
     if residual is not None:
         y = y + residual.float()
     out = K.empty_nhwc(n, c, h, w, x.device)
@@ -282,10 +303,11 @@ def _mask(dout, out, act):
     raise NotImplementedError("CPU stand-in: only relu / identity activations have a backward")
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None):
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None, sample_scale=None):
     n, c, h, w = x.shape
     M = n * h * w
-    dz = _mask(dy, y, act)
+    dz_res = _mask(dy, y, act)
+    dz = dz_res if sample_scale is None else dz_res * sample_scale.float().view(-1, 1, 1, 1)
     xh = (x.float() - _cv(mean)) * _cv(rstd)
     sb = dz.sum((0, 2, 3))
     sg = (dz * xh).sum((0, 2, 3))
@@ -295,7 +317,7 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
     dres = None
     if want_residual_grad:
         dres = K.empty_nhwc(n, c, h, w, x.device)
-        dres.copy_(_bf16(dz))
+        dres.copy_(_bf16(dz_res))
     dgamma = K.zeros((c,), torch.float32, x.device) if dgamma is None else dgamma
     dbeta = K.zeros((c,), torch.float32, x.device) if dbeta is None else dbeta
     dgamma += sg
@@ -513,7 +535,7 @@ def pose_loss(d, cls_logits, reg_distri, pose_coords, pose_logits, anchor_points
 
 
 _TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgrad_to_oihw, weight_prepare_batch=weight_prepare_batch,
-                 run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch,
+                 run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch, qarep_alpha_finish_table=qarep_alpha_finish_table, run_qarep_alpha_finish=run_qarep_alpha_finish,
                  bn_act_fwd=bn_act_fwd, bn_act_bwd=bn_act_bwd, channel_stats=channel_stats, channel_dot=channel_dot, qarep_fwd=qarep_fwd, qarep_bwd=qarep_bwd,
                  maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, atss_assign=atss_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,
                  adamw_step=adamw_step, ema_update=ema_update, pose_tal_assign=pose_tal_assign, pose_loss=pose_loss, avgpool_fwd=avgpool_fwd, avgpool_bwd=avgpool_bwd)  # fmt: skip

@@ -816,6 +816,41 @@ def golden_resnet_cifar_train():
     torch.save(dict(losses=losses, data_seed=6), os.path.join(HERE, "resnet18_cifar_train.pt"))
 
 
+def golden_droppath():
+    """Bottleneck / BasicResNetBlock with drop-path (config 4 is specified with droppath_prob 0.05): the reference draws its mask
+    inside forward (`x.new_empty((N,1,1,1)).bernoulli_(keep)`); re-seeding and drawing a tensor of the same shape afterwards
+    reproduces exactly that mask, which the fixture records as the per-image scale (mask / keep)."""
+    from super_gradients.training.models.classification_models.resnet import BasicResNetBlock, Bottleneck
+
+    out = {}
+    gen = torch.Generator().manual_seed(12)
+    for name, mk, cin, prob in [
+        ("bottleneck_s2", lambda p: Bottleneck(16, 8, stride=2, expansion=4, droppath_prob=p), 16, 0.4),
+        ("bottleneck_id", lambda p: Bottleneck(32, 8, stride=1, expansion=4, droppath_prob=p), 32, 0.4),
+        ("basic_s2", lambda p: BasicResNetBlock(16, 24, stride=2, droppath_prob=p), 16, 0.5),
+    ]:
+        torch.manual_seed(3)
+        mod = mk(prob)
+        randomize_bn(mod, gen)
+        sd0 = sd_clone(mod)
+        x = torch.randn(8, cin, 16, 16, generator=gen, requires_grad=True)
+        mod.train()
+        torch.manual_seed(77)
+        y = mod(x)
+        torch.manual_seed(77)
+        scale = torch.empty((8, 1, 1, 1)).bernoulli_(1 - prob).div_(1 - prob).reshape(8)
+        assert 0 < int((scale == 0).sum()) < 8, "the fixture needs dropped and kept images"
+        gy = torch.randn(y.shape, generator=gen)
+        y.backward(gy)
+        grads = {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+        sd1 = sd_clone(mod)
+        mod.eval()
+        with torch.no_grad():
+            y_eval = mod(x)
+        out[name] = dict(sd0=sd0, sd1=sd1, x=x.detach(), y=y.detach(), gy=gy, gx=x.grad.clone(), grads=grads, y_eval=y_eval, scale=scale, prob=prob)
+    torch.save(out, os.path.join(HERE, "droppath.pt"))
+
+
 if __name__ == "__main__":
     ref_shim.install()
     which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "atss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train", "other_configs"]

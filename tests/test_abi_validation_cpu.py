@@ -23,7 +23,7 @@ from super_gradients_b200 import lib as L  # noqa: E402
 
 # the batched filter-refresh / gradient-layout tables are device-resident work lists whose stand-in representation is a Python
 # list: nothing to validate through the C entry point
-TABLES = {"weight_prepare_batch", "run_weight_prepare_batch", "wgrad_to_oihw_batch_table", "run_wgrad_to_oihw_batch"}
+TABLES = {"weight_prepare_batch", "run_weight_prepare_batch", "wgrad_to_oihw_batch_table", "run_wgrad_to_oihw_batch", "qarep_alpha_finish_table", "run_qarep_alpha_finish"}
 REAL = {name: getattr(K, name) for name in list(cpu_backend._SUBSET) + list(cpu_backend._TRAINING) if hasattr(K, name) and name not in TABLES}
 
 

@@ -67,7 +67,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
 
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
-    pairs = {"SgbConvDesc": L.ConvDesc, "SgbEpilogue": L.Epilogue, "SgbWeightItem": L.WeightItem, "SgbWgradItem": L.WgradItem,
+    pairs = {"SgbConvDesc": L.ConvDesc, "SgbEpilogue": L.Epilogue, "SgbWeightItem": L.WeightItem, "SgbWgradItem": L.WgradItem, "SgbAlphaItem": L.AlphaItem,
              "SgbBnDesc": L.BnDesc, "SgbQarepDesc": L.QarepDesc, "SgbLossDesc": L.LossDesc, "SgbPoseLossDesc": L.PoseLossDesc, "SgbNmsDesc": L.NmsDesc, "SgbPreprocDesc": L.PreprocDesc, "SgbMatchDesc": L.MatchDesc}  # fmt: skip
     header = open(os.path.join(ROOT, "include", "sgb200.h")).read()
     assert set(re.findall(r"typedef struct (Sgb\w+)", header)) == set(pairs), "a header struct has no ctypes mirror (or vice versa)"

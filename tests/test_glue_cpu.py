@@ -646,6 +646,43 @@ def test_folded_qarepvgg_path_is_the_same_block(golden, monkeypatch):
     assert l2rel(res[True][1][3], res[False][1][3]) < 1e-3  # parameters after two steps
 
 
+def test_resnet_blocks_with_drop_path_glue(golden, monkeypatch):
+    """Drop-path wiring above the C ABI (the GPU twin is tests/test_modules_gpu.py::test_resnet_blocks_with_drop_path): the blocks
+    hand the per-image scale to the fused bn + add + relu call and its backward; against the unmodified reference's fixture."""
+    from super_gradients_b200.training.models.classification_models.resnet import BasicResNetBlock, Bottleneck
+
+    cpu_backend.install_training(monkeypatch)
+    G = golden("droppath")
+    for name, mod in (("bottleneck_s2", Bottleneck(16, 8, stride=2, expansion=4, droppath_prob=0.4)), ("bottleneck_id", Bottleneck(32, 8, stride=1, expansion=4, droppath_prob=0.4)),
+                      ("basic_s2", BasicResNetBlock(16, 24, stride=2, droppath_prob=0.5))):  # fmt: skip
+        g = G[name]
+        mod.load_state_dict(g["sd0"])
+        mod.train()
+        mod.drop_path.sample_scale = lambda x, g=g, mod=mod: g["scale"] if mod.training else None
+        x = g["x"].bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = mod(x)
+        y.backward(g["gy"].bfloat16())
+        # tight: the oracle with the same rounding points; loose: the reference's fp32 fixture (as tests/test_modules_gpu.py::_run_block)
+        fn, args = {"bottleneck_s2": (O.resnet_bottleneck, (2, True)), "bottleneck_id": (O.resnet_bottleneck, (1, False)), "basic_s2": (O.resnet_basic_block, (2, True))}[name]
+        with O.bf16_emulation():
+            pe = {k: v.clone() for k, v in g["sd0"].items()}
+            for k in g["grads"]:
+                pe[k].requires_grad_(True)
+            xe = g["x"].clone().requires_grad_(True)
+            ye = fn(O.q(xe), pe, "", args[0], args[1], True, sample_scale=g["scale"])
+            ye.backward(g["gy"].bfloat16().float())
+        assert l2rel(y, ye) < 5e-3 and l2rel(x.grad, xe.grad) < 2e-2, (name, l2rel(y, ye), l2rel(x.grad, xe.grad))
+        for k in g["grads"]:
+            assert l2rel(dict(mod.named_parameters())[k].grad, pe[k].grad) < 3e-2, (name, k)
+        assert l2rel(y, g["y"]) < 1.5e-2 and l2rel(x.grad, g["gx"]) < 0.2, (name, l2rel(y, g["y"]), l2rel(x.grad, g["gx"]))
+        assert int((g["scale"] == 0).sum()) > 0
+        mod.eval()
+        with torch.no_grad():
+            assert l2rel(mod(x.detach()), g["y_eval"]) < 2e-2  # eval: no drop-path
+    # the default stays exactly the plain block
+    assert Bottleneck(16, 8).drop_path.sample_scale(torch.zeros(2, 1)) is None
+
+
 @pytest.mark.parametrize("name,shape", [("resnet50", (2, 3, 64, 64)), ("resnet18", (2, 3, 64, 64))])
 def test_resnet_imagenet_variants_wire_up(monkeypatch, name, shape):
     """configs[3] family (Bottleneck / BasicBlock ImageNet ResNets) through models.get(): forward + backward run on the stand-in,

@@ -59,6 +59,50 @@ def test_conv_blocks(golden):
     torch.testing.assert_close(O.spp(g["x"], _clone(g["sd0"]), "", (5, 9, 13), "relu", True, 1e-5, 0.1), g["y"], rtol=1e-5, atol=1e-5)
 
 
+def test_resnet50_oracle_matches_reference(golden):
+    """oracle/resnet_oracle.py (the CPU arm of bench.py --config 4) == the unmodified reference's ResNet-50 for its own seeded
+    initialisation: train-mode logits, loss, the recorded gradients and every parameter's gradient norm; eval-mode logits.  The state
+    dict is the product constructor's (it consumes the RNG exactly as the reference's does -- the init fingerprints are pinned in
+    test_host_logic.py); only nn.Module construction runs here, no kernel."""
+    from oracle import resnet_oracle as R
+    from super_gradients_b200.training import models
+
+    g = golden("other_configs")["resnet50"]
+    torch.manual_seed(0)
+    m = models.get("resnet50", num_classes=1000)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    live = [k for k, _ in m.named_parameters()]
+    x = g["x"].float()
+    torch.testing.assert_close(R.resnet_forward("resnet50", {k: v.clone() for k, v in sd.items()}, x, True), g["train_logits"], rtol=2e-3, atol=2e-3)
+    loss, grads = R.train_step("resnet50", sd, x, g["y"], live)  # updates the BatchNorm running statistics held in `sd` (once)
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-4, atol=1e-5)
+    for k, ref in g["grads"].items():
+        mine = grads[k] if grads[k].numel() < 20000 else grads[k].flatten()[:: grads[k].numel() // 10000]
+        assert float((mine - ref).norm() / ref.norm()) < 2e-2, k
+    worst = max(abs(float(grads[k].norm()) / v - 1) for k, v in g["grad_norms"].items() if v > 1e-6)
+    assert worst < 2e-2, worst
+    # eval: with the running statistics of that one training forward
+    torch.testing.assert_close(R.resnet_forward("resnet50", sd, x, False), g["eval_logits"], rtol=2e-3, atol=2e-3)
+
+
+def test_resnet_blocks_with_drop_path(golden):
+    """Config 4 runs with droppath_prob 0.05: the oracle's blocks with the recorded per-image scale == the unmodified reference
+    (outputs and, through autograd, input / parameter gradients)."""
+    G = golden("droppath")
+    for name, fn, args in (("bottleneck_s2", O.resnet_bottleneck, (2, True)), ("bottleneck_id", O.resnet_bottleneck, (1, False)), ("basic_s2", O.resnet_basic_block, (2, True))):
+        g = G[name]
+        p = _clone(g["sd0"])
+        for k in g["grads"]:
+            p[k].requires_grad_(True)
+        x = g["x"].clone().requires_grad_(True)
+        y = fn(x, p, "", args[0], args[1], True, sample_scale=g["scale"])
+        torch.testing.assert_close(y, g["y"], rtol=1e-5, atol=1e-5)
+        y.backward(g["gy"])
+        torch.testing.assert_close(x.grad, g["gx"], rtol=1e-4, atol=1e-5)
+        for k, v in g["grads"].items():
+            torch.testing.assert_close(p[k].grad, v, rtol=1e-4, atol=1e-5)
+
+
 @pytest.mark.parametrize("case", ["regular", "ragged_with_empty", "no_targets"])
 def test_loss_and_assigner(golden, case):
     G = golden("loss")

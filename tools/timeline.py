@@ -24,8 +24,8 @@ from super_gradients_b200.training.sg_trainer import TrainStep, setup_device  # 
 
 
 def short(name):
-    name = re.sub(r"\(.*$", "", name)
     name = name.replace("void ", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+    name = re.sub(r"\(.*$", "", name)
     return name[:70]
 
 
@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--model", default="yolo_nas_s")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--aten", action="store_true", help="eager step with Python stacks: which call sites launch the remaining ATen kernels")
     args = ap.parse_args()
     import torch.distributed as dist
 
@@ -63,6 +64,17 @@ def main():
         dist.barrier()
     from torch.profiler import ProfilerActivity, profile
 
+    if args.aten:
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+            step.set_hyper_params(2e-4, 0.9997)
+            step._step_eager(xs[0], ts[0])
+            torch.cuda.synchronize()
+        rows = [e for e in prof.key_averages(group_by_stack_n=8) if e.key.startswith("aten::") and e.self_device_time_total > 0]
+        rows.sort(key=lambda e: -e.self_device_time_total)
+        for e in rows[: args.top]:
+            stack = [fr for fr in e.stack if "super_gradients_b200" in fr or "bench.py" in fr][:3]
+            print(f"{e.key:28s} n={e.count:4d} cuda {e.self_device_time_total / 1e3:8.3f} ms   " + " <- ".join(fr.split("/")[-1] for fr in stack))
+        return
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for i in range(args.steps):
             step.set_hyper_params(2e-4, 0.9997)
