@@ -134,6 +134,14 @@ int sgb_convt2x2_fprop(const SgbConvDesc* d, const sgb_bf16* x_small, const sgb_
 /* fp32 NCHW -> bf16 NHWC; channels [C, c_out) of the destination are written as zeros (c_out % 8 == 0). */
 int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, sgb_bf16* y, int y_pitch, int y_off, int c_out,
                               void* stream);
+/* Patch gather for a first-layer R x R / stride / pad convolution over a FEW input channels (C * R * R <= c_out, e.g. the
+ * YOLO-NAS stem: 3 channels, 3 x 3, stride 2): fp32 NCHW image -> bf16 NHWC [N, P, Q, c_out] with channel (r * R + s) * C + c
+ * of output pixel (p, q) = x[n, c, p * stride - pad + r, q * stride - pad + s] (0 outside the image; channels >= C * R * R zero).
+ * The stem convolution then is a 1 x 1 GEMM over this tensor: its input is fetched once instead of once per tap, and the
+ * QARepVGG 1 x 1 branch (which samples exactly the centre tap) shares the GEMM (training/models/.../yolo_stages.py:61-63,
+ * modules/qarepvgg_block.py:184-204). */
+int sgb_stem_patches_f32(const float* x, int N, int C, int H, int W, int R, int stride, int pad, sgb_bf16* y, int P, int Q, int c_out,
+                         void* stream);
 int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H, int W, int x_pitch, int x_off, float* y,
                               void* stream);
 
@@ -204,6 +212,15 @@ int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_b
                         const sgb_bf16* u, const float* coef, const double* sums, const float* gamma3,
                         const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du, float* dgamma3, float* dbeta3,
                         float* dbias1a, float* dgamma_p, float* dbeta_p, void* stream);
+/* The two backward passes above as ONE cooperative launch (reduction, grid-wide barrier, apply): one launch less per layer and, for
+ * operands that fit L2, one HBM read of them instead of two.  `sums` must be zero on entry, as for the two-pass form. */
+int sgb_bn_act_bwd_fused(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y, const float* gamma,
+                         const float* beta, const float* save_mean, const float* save_rstd, double* sums, sgb_bf16* dx,
+                         sgb_bf16* dresidual, float* dgamma, float* dbeta, void* stream);
+int sgb_qarep_bwd_fused(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* y3, const sgb_bf16* u, const float* coef,
+                        double* sums, const float* gamma3, const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du, float* dgamma3,
+                        float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p, void* stream);
+
 
 /* ---- pooling / elementwise (rows C6, C7, C8) --------------------------------------------------------------- */
 /* stride-`stride` max-pool k x k, pad k/2 (csp_darknet53.py:135-157 SPP; resnet.py maxpool 3/2/1). idx (int8,

@@ -12,6 +12,8 @@
 // training/models/classification_models/resnet.py:53-84 and its autograd backward.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace {
 
 constexpr int TPB = 256;
@@ -47,11 +49,9 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
 //   (all loads of a batch are issued before the first store, so UNROLL pixels x |In| vectors are in flight per thread)
 //   double* out; int out_stride;                (only when NACC > 0)
 template <class Op>
-__global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M, const int C) {
-  SGB_GRID_DEP_LAUNCH();
-  SGB_GRID_DEP_WAIT();
+__device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const int C, float* sc) {
   constexpr int NCOEF = Op::NCOEF, NACC = Op::NACC;
-  extern __shared__ float sc[];  // [NCOEF][C] (+ [NACC][cvb*8] reduction scratch)
+  // sc: [NCOEF][C] (+ [NACC][cvb*8] reduction scratch)
   op.prologue(sc);
   __syncthreads();
   const int cvs = C / 8;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M,
       }
       for (; pix < p1; pix += lanes) op.finish(pix, cv * 8, op.load(pix, cv * 8), r, acc);
     }
-    if (NACC > 0) {
+    if constexpr (NACC > 0) {
       // thread t = pl * cvb + cvi stores its NACC*8 sums at [pl][cvi][a][e]; output j = (cvi, a, e) then sums over pl
       __syncthreads();
       if (pl < lanes) {
@@ -107,6 +107,55 @@ __global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M,
       }
     }
   }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M, const int C) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
+  extern __shared__ float sc[];
+  chan_body(op, M, C, sc);
+}
+
+// A reduction pass and the apply pass that consumes its sums as ONE cooperative launch: grid-wide barrier in between.  Saves a
+// launch (ramp-up, tail) per pair and, for the layers whose operands fit the 126 MB L2 (every 80 x 80 and smaller map of YOLO-NAS-S
+// at batch 32), the apply pass's re-read of the same tensors hits L2 instead of HBM.  The sums are fp64 global atomics in both forms.
+template <class OpA, class OpB>
+__global__ void __launch_bounds__(TPB) chan_fused_kernel(const OpA a, const OpB b, const int64_t M, const int C) {
+  extern __shared__ float sc[];
+  chan_body(a, M, C, sc);
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  chan_body(b, M, C, sc);
+}
+
+template <class OpA, class OpB>
+int launch_chan_fused(const OpA& a, const OpB& b, int64_t M, int C, cudaStream_t st, const char* what) {
+  auto bytes = [&](int ncoef, int nacc) { return ((size_t)ncoef * C + (size_t)(nacc * 8 + 1) * TPB) * sizeof(float); };
+  const size_t sa = bytes(OpA::NCOEF, OpA::NACC), sb = bytes(OpB::NCOEF, OpB::NACC);
+  const size_t smem = sa > sb ? sa : sb;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(chan_fused_kernel<OpA, OpB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chan_fused_kernel<OpA, OpB>, TPB, smem) != cudaSuccess || per_sm < 1)
+    return sgb_cuda_check(cudaErrorCooperativeLaunchTooLarge, what);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int64_t want = (M + 255) / 256;
+  int64_t cap = (int64_t)sms * per_sm;
+  if (cap > sgb_chan_grid_cap()) cap = sgb_chan_grid_cap();
+  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  int64_t Mv = M;
+  int Cv = C;
+  void* args[] = {(void*)&a, (void*)&b, (void*)&Mv, (void*)&Cv};
+  return sgb_cuda_check(cudaLaunchCooperativeKernel((const void*)chan_fused_kernel<OpA, OpB>, dim3(grid), dim3(TPB), args, smem, st), what);
 }
 
 template <class Op>
@@ -295,11 +344,12 @@ struct BnBwdApplyOp {
       sc[C + c] = rstd[c];
       sc[2 * C + c] = g * rstd[c];
       sc[3 * C + c] = b - mean[c] * g * rstd[c];
-      sc[4 * C + c] = (float)(sums[c] / (double)d.M);
-      sc[5 * C + c] = (float)(sums[C + c] / (double)d.M);
+      const double S0 = __ldcg(sums + c), S1 = __ldcg(sums + C + c);  // L2 reads: in the fused launch other CTAs just wrote them
+      sc[4 * C + c] = (float)(S0 / (double)d.M);
+      sc[5 * C + c] = (float)(S1 / (double)d.M);
       if (blockIdx.x == 0) {
-        if (dgamma) dgamma[c] += (float)sums[C + c];
-        if (dbeta) dbeta[c] += (float)sums[c];
+        if (dgamma) dgamma[c] += (float)S1;
+        if (dbeta) dbeta[c] += (float)S0;
       }
     }
   }
@@ -486,7 +536,7 @@ struct QarepBwdApplyOp {
     const double M = (double)d.M;
     for (int c = threadIdx.x; c < C; c += TPB) {
       const float rstdz = coef[3 * C + c], czy = coef[7 * C + c];
-      const double T0 = sums[c], T1 = sums[C + c], T2 = sums[2 * C + c];
+      const double T0 = __ldcg(sums + c), T1 = __ldcg(sums + C + c), T2 = __ldcg(sums + 2 * C + c);  // L2 reads (fused launch)
       const float m0 = (float)(T0 / M), m2 = (float)(T2 / M);
       float m1 = (float)(T1 / M), g, q;
       if (d.use_post_bn) {
@@ -620,6 +670,17 @@ extern "C" int sgb_bn_act_bwd_apply(const SgbBnDesc* d, const sgb_bf16* dy, cons
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_bwd_apply");
 }
 
+extern "C" int sgb_bn_act_bwd_fused(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y, const float* gamma,
+                                    const float* beta, const float* save_mean, const float* save_rstd, double* sums, sgb_bf16* dx,
+                                    sgb_bf16* dresidual, float* dgamma, float* dbeta, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(dy && x && save_mean && save_rstd && sums && dx, "null pointer");
+  SGB_REQUIRE(!d->sample_scale || y, "drop-path backward needs the forward output (the mask cannot be recomputed from x alone)");
+  BnBwdRedOp ra{*d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, save_mean, save_rstd, gamma, beta, sums, d->C};
+  BnBwdApplyOp ap{*d, (const bf16*)dy, (const bf16*)x, (const bf16*)y, gamma, beta, save_mean, save_rstd, sums, (bf16*)dx, (bf16*)dresidual, dgamma, dbeta};
+  return launch_chan_fused(ra, ap, d->M, d->C, (cudaStream_t)stream, "bn_act_bwd_fused");
+}
+
 extern "C" int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, const double* moments,
                              const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
                              const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out,
@@ -652,4 +713,15 @@ extern "C" int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, 
   SGB_REQUIRE(!d->use_post_bn || gamma_p, "gamma_p missing");
   QarepBwdApplyOp op{*d, (const bf16*)dout, (const bf16*)y3, (const bf16*)u, coef, sums, gamma3, gamma_p, (bf16*)dy3, (bf16*)du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p};
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_bwd_apply");
+}
+
+extern "C" int sgb_qarep_bwd_fused(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* y3, const sgb_bf16* u, const float* coef,
+                                   double* sums, const float* gamma3, const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du, float* dgamma3,
+                                   float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p, void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(dout && y3 && u && coef && sums && gamma3 && dy3 && du, "null pointer");
+  SGB_REQUIRE(!d->use_post_bn || gamma_p, "gamma_p missing");
+  QarepBwdRedOp ra{*d, (const bf16*)dout, (const bf16*)y3, (const bf16*)u, coef, sums, d->C};
+  QarepBwdApplyOp ap{*d, (const bf16*)dout, (const bf16*)y3, (const bf16*)u, coef, sums, gamma3, gamma_p, (bf16*)dy3, (bf16*)du, dgamma3, dbeta3, dbias1a, dgamma_p, dbeta_p};
+  return launch_chan_fused(ra, ap, d->M, d->C, (cudaStream_t)stream, "qarep_bwd_fused");
 }

@@ -187,6 +187,48 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int N, int C, i
   }
 }
 
+// Patch gather.  One CTA = one output row segment (STEM_QT output pixels of one (image, output row)): the R input rows x C channels
+// that feed it are staged in shared memory with coalesced fp32 reads (each input row segment is read once per output row that uses
+// it: R / stride times in total), then every thread assembles 8-channel vectors from shared memory and stores them so that a warp
+// writes contiguous 16-byte pieces.  (The first version gathered straight from global memory with 4-byte scattered reads: 0.9 TB/s.)
+constexpr int STEM_QT = 128;
+__global__ void __launch_bounds__(256) stem_patches_kernel(const float* __restrict__ x, int N, int C, int H, int W, int R, int stride, int pad,
+                                                           bf16* __restrict__ y, int P, int Q, int cout) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
+  extern __shared__ float srow[];  // [C][R][span]
+  const int qtiles = (Q + STEM_QT - 1) / STEM_QT;
+  const int qt = blockIdx.x % qtiles;
+  const int p = (blockIdx.x / qtiles) % P;
+  const int n = blockIdx.x / (qtiles * P);
+  const int q0 = qt * STEM_QT, nq = min(STEM_QT, Q - q0);
+  const int w0 = q0 * stride - pad, span = (STEM_QT - 1) * stride + R;
+  const int64_t hw = (int64_t)H * W;
+  for (int i = threadIdx.x; i < C * R * span; i += blockDim.x) {
+    const int j = i % span, cr = i / span, r = cr % R, c = cr / R;
+    const int h = p * stride - pad + r, w = w0 + j;
+    srow[i] = (h >= 0 && h < H && w >= 0 && w < W) ? x[((int64_t)n * C + c) * hw + (int64_t)h * W + w] : 0.f;
+  }
+  __syncthreads();
+  const int cv = cout / 8, taps = C * R * R;
+  bf16* yrow = y + (((int64_t)n * P + p) * Q + q0) * cout;
+  for (int i = threadIdx.x; i < nq * cv; i += blockDim.x) {
+    const int v = i % cv, q = i / cv;
+    V8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = v * 8 + e;
+      float val = 0.f;
+      if (ch < taps) {
+        const int c = ch % C, rs = ch / C, r = rs / R, s2 = rs - r * R;
+        val = srow[(c * R + r) * span + q * stride + s2];
+      }
+      o.v[e] = val;
+    }
+    st8(yrow + (int64_t)q * cout + v * 8, o);
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, int H, int W, int pitch, int off,
                                     float* y) {
   SGB_GRID_DEP_LAUNCH();
@@ -328,6 +370,76 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int N, int H, int
     for (int e = 0; e < 8; ++e) o.v[e] = best[e];
     int64_t opix = ((int64_t)n * P + p) * Q + q;
     st8(y + opix * yp + yo + cv * 8, o);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + opix * C + cv * 8) = pk;
+    }
+  }
+}
+
+// Stride-1 max-pool (the SPP pools, k = 5 / 9 / 13 over 20 x 20 maps) as two separable passes through shared memory: one CTA owns
+// the H x W plane of one image and one 8-channel vector.  Pass 1: per (row, output column) the maximum over the window's columns and
+// the FIRST column offset that attains it; pass 2: per output pixel the first window row whose row-maximum is the window maximum.
+// That is the same element as the direct scan's (row-major order, strict >: the first maximum), which the backward routes to, at
+// 2k instead of k^2 comparisons per output and with the plane read from HBM once (the direct kernel ran at 73 GB/s).
+__global__ void __launch_bounds__(256) maxpool_s1_smem_kernel(const bf16* __restrict__ x, int H, int W, int C, int xp, int xo, int k, int pad, bf16* y,
+                                                              int P, int Q, int yp, int yo, uint8_t* idx) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
+  extern __shared__ __align__(16) unsigned char smem_mp[];
+  uint4* plane = reinterpret_cast<uint4*>(smem_mp);                     // [H][W] 8 x bf16
+  float* rmax = reinterpret_cast<float*>(plane + (size_t)H * W);        // [H][Q][8]
+  uint8_t* rarg = reinterpret_cast<uint8_t*>(rmax + (size_t)H * Q * 8);  // [H][Q][8]
+  const int cvs = C / 8, n = blockIdx.x / cvs, cv = blockIdx.x % cvs;
+  const bf16* xin = x + (int64_t)n * H * W * xp + xo + cv * 8;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) plane[i] = *reinterpret_cast<const uint4*>(xin + (int64_t)i * xp);
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * Q; i += blockDim.x) {
+    const int h = i / Q, q = i - h * Q;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+    for (int s2 = 0; s2 < k; ++s2) {
+      const int w = q - pad + s2;
+      if ((unsigned)w >= (unsigned)W) continue;
+      const uint4 r = plane[h * W + w];
+      const uint32_t ww[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(ww[e] << 16), hi = __uint_as_float(ww[e] & 0xffff0000u);
+        if (lo > best[2 * e]) { best[2 * e] = lo; bi[2 * e] = s2; }
+        if (hi > best[2 * e + 1]) { best[2 * e + 1] = hi; bi[2 * e + 1] = s2; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      rmax[(size_t)i * 8 + e] = best[e];
+      rarg[(size_t)i * 8 + e] = (uint8_t)bi[e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P * Q; i += blockDim.x) {
+    const int p = i / Q, q = i - p * Q;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+    for (int r = 0; r < k; ++r) {
+      const int h = p - pad + r;
+      if ((unsigned)h >= (unsigned)H) continue;
+      const size_t o = ((size_t)h * Q + q) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (rmax[o + e] > best[e]) { best[e] = rmax[o + e]; bi[e] = r * k + rarg[o + e]; }
+    }
+    V8 ov;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ov.v[e] = best[e];
+    const int64_t opix = ((int64_t)n * P + p) * Q + q;
+    st8(y + opix * yp + yo + cv * 8, ov);
     if (idx) {
       uint2 pk;
       pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
@@ -535,6 +647,20 @@ extern "C" int sgb_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, in
   return SGB_OK;
 }
 
+extern "C" int sgb_stem_patches_f32(const float* x, int N, int C, int H, int W, int R, int stride, int pad, sgb_bf16* y, int P, int Q,
+                                    int c_out, void* stream) {
+  SGB_REQUIRE(x && y && N > 0 && C > 0 && R > 0 && stride > 0 && pad >= 0, "bad args");
+  SGB_REQUIRE(c_out % 8 == 0 && c_out >= C * R * R, "c_out must be a multiple of 8 and hold C * R * R patch entries");
+  SGB_REQUIRE(P == (H + 2 * pad - R) / stride + 1 && Q == (W + 2 * pad - R) / stride + 1, "P/Q inconsistent");
+  const size_t smem = (size_t)C * R * ((STEM_QT - 1) * stride + R) * sizeof(float);
+  SGB_REQUIRE(smem <= 48 * 1024, "patch rows do not fit shared memory");
+  const int64_t ctas = (int64_t)N * P * ((Q + STEM_QT - 1) / STEM_QT);
+  SGB_REQUIRE(ctas < (1ll << 31), "too many tiles");
+  SGB_LAUNCH(stem_patches_kernel, (int)ctas, 256, smem, (cudaStream_t)stream, x, N, C, H, W, R, stride, pad, (bf16*)y, P, Q, c_out);
+  SGB_LAUNCH_CHECK("stem_patches_kernel");
+  return SGB_OK;
+}
+
 extern "C" int sgb_nhwc_bf16_to_nchw_f32(const sgb_bf16* x, int N, int C, int H, int W, int x_pitch, int x_off,
                                          float* y, void* stream) {
   SGB_REQUIRE(x && y, "null pointer");
@@ -565,6 +691,17 @@ extern "C" int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, in
               "bad args");
   SGB_REQUIRE(k * k <= 255, "kernel too large for uint8 arg-max");
   SGB_REQUIRE(P == (H + 2 * pad - k) / stride + 1 && Q == (W + 2 * pad - k) / stride + 1, "P/Q inconsistent");
+  const size_t smem = (size_t)H * W * 16 + (size_t)H * Q * 8 * (sizeof(float) + 1);
+  if (stride == 1 && smem <= 96 * 1024 && (int64_t)N * (C / 8) <= 1 << 20) {  // the SPP pools: separable pass through shared memory
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(maxpool_s1_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    SGB_LAUNCH(maxpool_s1_smem_kernel, N * (C / 8), 256, smem, (cudaStream_t)stream, (const bf16*)x, H, W, C, x_pitch, x_off, k, pad, (bf16*)y, P, Q, y_pitch, y_off, idx);
+    SGB_LAUNCH_CHECK("maxpool_s1_smem_kernel");
+    return SGB_OK;
+  }
   SGB_LAUNCH(maxpool_fwd_kernel, grid_for((int64_t)N * P * Q * (C / 8)), TPB, 0, (cudaStream_t)stream,  (const bf16*)x, N, H, W, C, x_pitch, x_off, k, stride, pad, (bf16*)y, P, Q, y_pitch, y_off, idx);
   SGB_LAUNCH_CHECK("maxpool_fwd_kernel");
   return SGB_OK;

@@ -55,6 +55,7 @@ class StepContext:
         self.wgrad_table = None
         self.wgrad_key = None
         self.alpha_pending = []   # QARepVGG alpha chain rule of every block, finished by one batched launch (flush_wgrads)
+        self.stem_pending = []    # patch-stem weight gradients, unpacked into the two filters' slots after the join
         self.alpha_table = None
         self.alpha_key = None
         # Weight gradients are off the critical path of backward (nothing consumes them before the optimizer): with a side
@@ -73,6 +74,7 @@ def set_step_context(ctx: Optional["StepContext"]):
     if ctx is not None:
         ctx.pending.clear()
         ctx.alpha_pending.clear()
+        ctx.stem_pending.clear()
         ctx.keep.clear()
         ctx.side_used = False
 
@@ -131,6 +133,9 @@ def flush_wgrads(ctx: StepContext, device) -> int:
         torch.cuda.current_stream().wait_event(ev)
         ctx.side_used = False
     ctx.keep.clear()
+    for dwf, kout, cin, r, s, sw3, sw1 in ctx.stem_pending:
+        _unpack_stem_wgrad(dwf, kout, cin, r, s, sw3, sw1)
+    ctx.stem_pending.clear()
     if ctx.alpha_pending:
         ident = tuple(tuple(None if t is None else (t.data_ptr() if torch.is_tensor(t) else t) for t in e) for e in ctx.alpha_pending)
         if ctx.alpha_key != ident:
@@ -331,11 +336,16 @@ class _ConvBias(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, cfg):
         x = K.as_nhwc(x)
-        krsc, crsk = cfg.cache.get(w, c_pad=x.shape[1])
-        kout, _, r, s = w.shape
+        # an nn.Linear weight [K, C] is the OIHW filter [K, C, 1, 1] of a 1 x 1 convolution: the PARAMETER itself is passed in (not a
+        # reshaped view), so its weight gradient goes to the flat gradient slot like every filter's instead of through an autograd
+        # AccumulateGrad node (whose stream bookkeeping invalidates a CUDA-graph capture of the step)
+        ctx.w_orig_shape = tuple(w.shape)
+        w4 = w if w.dim() == 4 else w.detach().view(w.shape[0], w.shape[1], 1, 1)
+        krsc, crsk = cfg.cache.get(w4, c_pad=x.shape[1])
+        kout, _, r, s = w4.shape
         y = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, shift=b, act=cfg.act)
         ctx.save_for_backward(x)
-        ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_bias = cfg, crsk, tuple(w.shape), b is not None
+        ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_bias = cfg, crsk, tuple(w4.shape), b is not None
         ctx.slots = (_mg(w), _mg(b))
         return y
 
@@ -347,6 +357,8 @@ class _ConvBias(torch.autograd.Function):
         dy = K.as_nhwc(dy)
         dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad) if ctx.needs_input_grad[0] else None
         dw = _wgrad(x, dy, r, s, cfg.stride, cfg.pad, cin, ctx.slots[0])
+        if dw is not None:
+            dw = dw.reshape(ctx.w_orig_shape)
         db = _deliver(ctx.slots[1], _chan_sum(dy)) if ctx.has_bias else None
         return dx, dw, db, None
 
@@ -465,6 +477,111 @@ class _QARepVGG(torch.autograd.Function):
 def qarepvgg_block(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
     K.require_cuda(x, "x")
     return _QARepVGG.apply(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------ QARepVGG stem on patches
+STEM_PATCHES = [__import__("os").environ.get("SGB_STEM_PATCHES", "1") != "0"]
+
+
+def stem_patch_channels(cin: int, r: int) -> int:
+    return ((cin * r * r + 15) // 16) * 16
+
+
+def stem_patches_supported(block, x) -> bool:
+    """A train-mode, unfused QARepVGG first layer (3 x 3, stride 2, no identity, no learnable alpha) over a raw fp32 NCHW image
+    with so few channels that all nine taps fit 32 patch channels: the YOLO-NAS / YOLO-NAS-POSE stem (yolo_stages.py:61-63)."""
+    return bool(
+        STEM_PATCHES[0] and block.training and not block.partially_fused and not block.fully_fused and torch.is_tensor(x) and x.dim() == 4
+        and x.dtype == torch.float32 and not x.requires_grad and x.shape[1] == block.in_channels and block.in_channels * 9 <= 32 and block.stride == 2
+        and block.identity is None and not isinstance(block.alpha, torch.Tensor) and float(block.alpha) == 1.0 and block.use_post_bn
+    )  # fmt: skip
+
+
+class StemPatchWeightCache:
+    """fp32 [2K, c_out, 1, 1] staging of the two stem filters in patch-channel order -- rows [0, K): K3 as (r, s, c); rows [K, 2K):
+    K1 at the centre tap's channels -- plus its bf16 KRSC copy, refreshed when a source changes."""
+
+    def __init__(self):
+        self.key = None
+        self.stage = None
+        self.inner = WeightCache(batched=False)
+
+    def get(self, w3, w1, c_out):
+        key = (WeightCache._key(w3, None, False, None, c_out), WeightCache._key(w1, None, False, None, c_out))
+        if key != self.key:
+            kout, cin, r, s = w3.shape
+            with torch.no_grad():
+                if self.stage is None or tuple(self.stage.shape) != (2 * kout, c_out, 1, 1) or self.stage.device != w3.device:
+                    self.stage = torch.zeros((2 * kout, c_out, 1, 1), dtype=torch.float32, device=w3.device)
+                st = self.stage.view(2 * kout, c_out)
+                st[:kout, : cin * r * s].copy_(w3.detach().permute(0, 2, 3, 1).reshape(kout, r * s * cin))
+                ctr = ((r // 2) * s + s // 2) * cin
+                st[kout:, ctr : ctr + cin].copy_(w1.detach()[:, :, 0, 0])
+            self.key = key
+        return self.inner.get(self.stage, c_pad=c_out, extra_key=key)
+
+
+def _unpack_stem_wgrad(dwf, kout, cin, r, s, sw3, sw1):
+    """dwf fp32 [2K, 1, 1, c_out] (gradient of the staged patch filter) -> += into the two OIHW gradient slots."""
+    g = dwf.reshape(dwf.shape[0], dwf.shape[3])
+    sw3.add_(g[:kout, : cin * r * s].reshape(kout, r, s, cin).permute(0, 3, 1, 2))
+    ctr = ((r // 2) * s + s // 2) * cin
+    sw1.add_(g[kout:, ctr : ctr + cin].reshape(kout, cin, 1, 1))
+
+
+class _QARepVGGStem(torch.autograd.Function):
+    """The train-mode QARepVGG stem as ONE 1 x 1 GEMM over gathered patches: y3 = conv3x3_s2(x) and u = conv1x1_s2(x) are the
+    first / second K output channels of `patches(x) @ [K3 ; centre(K1)]`.  The im2col engine fetched the 16-channel-padded image
+    once per tap (9 x 419 MB through L2 per pass at batch 32) for each of the four stem launches; here the image is read once by the
+    gather and the two GEMMs (forward, weight gradient) read a 32-channel tensor.  Same arithmetic per output: products of the
+    same bf16 operands accumulated in fp32.  The image needs no gradient, so there is no dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w3, g3, b3, w1, bias1, gp, bp, cfg):
+        kout, cin, r, s = w3.shape
+        c_out = stem_patch_channels(cin, r)
+        xp = K.stem_patches(x, r, cfg.stride, 1, c_out)
+        kf, _ = cfg.cache_stem.get(w3, w1, c_out)
+        ycat = K.conv_fprop(xp, kf, 2 * kout, 1, 1, 1, 0)
+        y3, u = ycat[:, :kout], ycat[:, kout:]
+        out, coef = K.qarep_fwd(y3, u, g3, b3, bias1, gp, bp, cfg.rm3, cfg.rv3, cfg.rmp, cfg.rvp, cfg.eps, cfg.eps, cfg.momentum, cfg.act, True)
+        if not _NBT_DEFERRED[0]:
+            for nbt in cfg.nbt:
+                if nbt is not None:
+                    nbt += 1
+        ctx.save_for_backward(xp, y3, u, out, coef, g3, gp)
+        ctx.cfg, ctx.geom, ctx.has_bias = cfg, (kout, cin, r, s), bias1 is not None
+        ctx.slots = (_mg(w3), _mg(g3), _mg(b3), _mg(w1), _mg(bias1), _mg(gp), _mg(bp))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xp, y3, u, out, coef, g3, gp = ctx.saved_tensors
+        cfg = ctx.cfg
+        kout, cin, r, s = ctx.geom
+        sw3, sg3, sb3, sw1, sbias, sgp, sbp = ctx.slots
+        n, _, h, w = y3.shape
+        dcat = K.empty_nhwc(n, 2 * kout, h, w, y3.device)
+        _dy3, _du, dg3, db3, dab, dgp, dbp = K.qarep_bwd(dout, out, y3, u, coef, g3, gp, cfg.eps, cfg.eps, cfg.act, True, acc=(sg3, sb3, sbias, sgp, sbp),
+                                                         out_grads=(dcat[:, :kout], dcat[:, kout:]))  # fmt: skip
+        c = _CTX[0]
+        dw3 = dw1 = None
+        if c is not None and sw3 is not None and sw1 is not None:
+            dwf = _side_wgrad(c, xp, dcat, 1, 1, 1, 0) if c.side_stream is not None else K.conv_wgrad(xp, dcat, 1, 1, 1, 0)
+            c.stem_pending.append((dwf, kout, cin, r, s, sw3, sw1))  # unpacked in flush_wgrads(), after the side stream joined
+        else:
+            dwf = K.conv_wgrad(xp, dcat, 1, 1, 1, 0)
+            g = dwf.reshape(2 * kout, dwf.shape[3])
+            dw3 = _deliver(sw3, g[:kout, : cin * r * s].reshape(kout, r, s, cin).permute(0, 3, 1, 2).contiguous())
+            ctr = ((r // 2) * s + s // 2) * cin
+            dw1 = _deliver(sw1, g[kout:, ctr : ctr + cin].reshape(kout, cin, 1, 1).contiguous())
+        ret = lambda slot, v: None if slot is not None else v  # noqa: E731
+        return None, dw3, ret(sg3, dg3), ret(sb3, db3), dw1, (ret(sbias, dab) if ctx.has_bias else None), ret(sgp, dgp), ret(sbp, dbp), None
+
+
+def qarepvgg_stem_block(x, w3, g3, b3, w1, bias1, gp, bp, cfg):
+    K.require_cuda(x, "x")
+    return _QARepVGGStem.apply(x, w3, g3, b3, w1, bias1, gp, bp, cfg)
 
 
 # ------------------------------------------------------------------------------------------------------------ ConvTranspose 2x2/s2

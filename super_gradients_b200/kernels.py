@@ -5,6 +5,7 @@ Activation tensors are NCHW-shaped torch tensors in channels_last memory format 
 slice ``buf[:, a:b]`` of such a tensor is a valid operand: its channel pitch is ``buf.shape[1]``.
 """
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -85,6 +86,9 @@ ARENA = NO_ARENA        # the arena of the TrainStep that is executing (training
 def zeros(shape, dtype, device):
     return ARENA.zeros(tuple(shape) if not isinstance(shape, int) else (shape,), dtype, device)
 
+
+# BatchNorm / QARepVGG backward as one cooperative launch per layer instead of a reduction launch + an apply launch (SGB_FUSED_BWD=0: two passes)
+FUSED_BWD = [os.environ.get("SGB_FUSED_BWD", "1") != "0"]
 
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU}
 
@@ -334,6 +338,17 @@ def nchw_f32_to_nhwc_bf16(x: torch.Tensor, c_align: int = 8) -> torch.Tensor:
     return out
 
 
+def stem_patches(x: torch.Tensor, R: int, stride: int, pad: int, c_out: int) -> torch.Tensor:
+    """fp32 NCHW image -> bf16 NHWC [N, c_out, P, Q] patch tensor (channel (r * R + s) * C + c; see include/sgb200.h)."""
+    require_cuda(x, "x")
+    n, c, h, w = x.shape
+    x = x.contiguous().float()
+    P, Q = (h + 2 * pad - R) // stride + 1, (w + 2 * pad - R) // stride + 1
+    out = torch.empty((n, c_out, P, Q), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    _timed("sgb_stem_patches_f32", _ptr(x), n, c, h, w, R, stride, pad, _ptr(out), P, Q, c_out, _stream())
+    return out
+
+
 def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     n, c, h, w = x.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
@@ -456,7 +471,9 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
     sums = zeros((2, c), torch.float64, x.device)
     # the forward output is only read when a residual entered the activation; otherwise the mask is recomputed from x
     y_arg = y if (want_residual_grad or beta is None or sample_scale is not None) else None
-    _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
+    fused = FUSED_BWD[0] and nhwc_pitch(x) == c
+    if not fused:
+        _timed("sgb_bn_act_bwd_reduce", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _stream())
     dx = torch.empty_like(x, memory_format=torch.channels_last) if nhwc_pitch(x) == c else torch.zeros_like(x)
     d.x_pitch = nhwc_pitch(dx)
     # x and dx must share a pitch for the kernel: re-describe x if it is a slice
@@ -470,7 +487,8 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
         dgamma = zeros((c,), torch.float32, x.device)
     if dbeta is None:
         dbeta = zeros((c,), torch.float32, x.device)
-    _timed("sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
+    # one cooperative launch (reduction, grid barrier, apply) when every operand is dense; else the two passes
+    _timed("sgb_bn_act_bwd_fused" if fused else "sgb_bn_act_bwd_apply", ctypes.byref(d), _ptr(dy), _ptr(x), _ptr(y_arg), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(sums), _ptr(dx), _ptr(dres), _ptr(dgamma), _ptr(dbeta), _stream())
     return dx, dres, dgamma, dbeta
 
 
@@ -520,7 +538,8 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
         else:
             dout = dout.contiguous(memory_format=torch.channels_last)
     sums = zeros((3, c), torch.float64, y3.device)
-    _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
+    if not FUSED_BWD[0]:
+        _timed("sgb_qarep_bwd_reduce", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _stream())
     if out_grads is not None:
         dy3, du = out_grads
         if nhwc_pitch(dy3) != nhwc_pitch(y3) or nhwc_pitch(du) != nhwc_pitch(u):
@@ -530,7 +549,10 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
     z = lambda: zeros((c,), torch.float32, y3.device)  # noqa: E731
     acc = acc or (None,) * 5
     dg3, db3, dab, dgp, dbp = [a if a is not None else z() for a in acc]
-    _timed("sgb_qarep_bwd_apply", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
+    if FUSED_BWD[0]:  # one cooperative launch: reduction, grid barrier, apply
+        _timed("sgb_qarep_bwd_fused", ctypes.byref(d), _ptr(dout), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
+    else:
+        _timed("sgb_qarep_bwd_apply", ctypes.byref(d), _ptr(dout), _ptr(out), _ptr(y3), _ptr(u), _ptr(coef), _ptr(sums), _ptr(gamma3), _ptr(gamma_p), _ptr(dy3), _ptr(du), _ptr(dg3), _ptr(db3), _ptr(dab), _ptr(dgp), _ptr(dbp), _stream())
     return dy3, du, dg3, db3, dab, dgp, dbp
 
 

@@ -158,16 +158,19 @@ _SIGNATURES = {
     "sgb_qarep_alpha_finish_batch": (c_int, [P, _I, P]),
     "sgb_convt2x2_fprop": (c_int, [POINTER(ConvDesc), P, P, P, P, P]),
     "sgb_nchw_f32_to_nhwc_bf16": (c_int, [P, _I, _I, _I, _I, P, _I, _I, _I, P]),
+    "sgb_stem_patches_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, P, _I, _I, _I, P]),
     "sgb_nhwc_bf16_to_nchw_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, P, P]),
     "sgb_bn_act_fwd": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P]),
     "sgb_bn_act_infer": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P]),
     "sgb_bn_act_bwd_reduce": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P]),
     "sgb_bn_act_bwd_apply": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "sgb_bn_act_bwd_fused": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "sgb_channel_stats": (c_int, [P, _L, _I, _I, _I, P, P]),
     "sgb_qarep_moments": (c_int, [POINTER(QarepDesc), P, P, P, P]),
     "sgb_qarep_fwd": (c_int, [POINTER(QarepDesc)] + [P] * 15),
     "sgb_qarep_bwd_reduce": (c_int, [POINTER(QarepDesc), P, P, P, P, P, P, P]),
     "sgb_qarep_bwd_apply": (c_int, [POINTER(QarepDesc)] + [P] * 16),
+    "sgb_qarep_bwd_fused": (c_int, [POINTER(QarepDesc)] + [P] * 15),
     "sgb_maxpool_fwd": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, _I, _I, _I, _I, P, P]),
     "sgb_maxpool_bwd": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, P, P]),
     "sgb_axpby": (c_int, [P, _I, _I, _F, P, _I, _I, _F, P, _I, _I, _L, _I, P]),

@@ -78,6 +78,7 @@ class QARepVGGBlock(nn.Module):
         self.fully_fused = False
         self._cache3, self._cache1, self._cache_eq = SF.WeightCache(), SF.WeightCache(), SF.WeightCache()
         self._cache_fold = SF.FoldedWeightCache()
+        self._cache_stem = SF.StemPatchWeightCache()
         self._eq = None
         self._eval_fold = None  # (key, bf16 KRSC filter, scale, shift) of the on-the-fly eval fold
         if not build_residual_branches:
@@ -93,6 +94,16 @@ class QARepVGGBlock(nn.Module):
         if self.training:
             bn3 = self.branch_3x3.bn
             pbn = self.post_bn if self.use_post_bn else None
+            if SF.stem_patches_supported(self, inputs):  # a raw fp32 image entering a first layer (the detector passes it through)
+                cfg = SimpleNamespace(
+                    stride=self.stride, act=self._act_code, eps=bn3.eps, momentum=0.1 if bn3.momentum is None else bn3.momentum, cache_stem=self._cache_stem,
+                    rm3=bn3.running_mean, rv3=bn3.running_var, rmp=pbn.running_mean, rvp=pbn.running_var, nbt=(bn3.num_batches_tracked, pbn.num_batches_tracked),
+                )  # fmt: skip
+                if pbn.eps != bn3.eps:
+                    raise NotImplementedError("branch and post BatchNorm must share eps")
+                return SF.qarepvgg_stem_block(inputs, self.branch_3x3.conv.weight, bn3.weight, bn3.bias, self.branch_1x1.weight, self.branch_1x1.bias, pbn.weight, pbn.bias, cfg)
+            if inputs.dtype == torch.float32 and inputs.shape[1] == self.in_channels and self.in_channels % 8 != 0:
+                inputs = SF.to_nhwc(inputs)  # a raw image the patch path does not serve
             cfg = SimpleNamespace(
                 stride=self.stride, residual=self.identity is not None, act=self._act_code, eps=bn3.eps, momentum=0.1 if bn3.momentum is None else bn3.momentum,
                 use_post_bn=self.use_post_bn, cache3=self._cache3, cache1=self._cache1, cache_fold=self._cache_fold, rm3=bn3.running_mean, rv3=bn3.running_var,

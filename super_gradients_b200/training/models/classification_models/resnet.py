@@ -72,8 +72,7 @@ class _Classifier(SgModule, _FusedConvBN):
     def _head(self, out):
         """avgpool -> Linear (as a 1x1 GEMM) -> fp32 logits [N, num_classes]."""
         out = SF.global_avg_pool(out)
-        w = self.linear.weight
-        logits = SF.conv_bias(out, w.reshape(w.shape[0], w.shape[1], 1, 1), self.linear.bias, stride=1, pad=0, cache=self._fc_cache)
+        logits = SF.conv_bias(out, self.linear.weight, self.linear.bias, stride=1, pad=0, cache=self._fc_cache)  # [K, C] == OIHW [K, C, 1, 1]
         return SF.from_nhwc(logits).flatten(1)
 
     def _make_layer(self, block, planes, num_blocks, stride, droppath_prob=0.0):

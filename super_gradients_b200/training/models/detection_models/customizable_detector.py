@@ -37,7 +37,9 @@ class CustomizableDetector(SgModule):
 
     def forward(self, x):
         """x: [B, C, H, W] fp32 or bf16 CUDA tensor (NCHW semantics).  Same return structure as the reference."""
-        x = SF.to_nhwc(x)
+        stem = getattr(getattr(self.backbone, "stem", None), "conv", None)
+        if stem is None or not hasattr(stem, "partially_fused") or not SF.stem_patches_supported(stem, x):
+            x = SF.to_nhwc(x)  # else: the raw image goes to the stem, which gathers its patches itself (functional._QARepVGGStem)
         x = self.backbone(x)
         x = self.neck(x)
         return self.heads(x)
@@ -126,9 +128,20 @@ class CustomizableDetector(SgModule):
         images = [images] if isinstance(images, np.ndarray) else list(images)
         processor = self._image_processor or default_yolo_nas_coco_processing_params()["image_processor"]
         device = next(self.parameters()).device
+        dflt = dict(conf=self._default_nms_conf, iou=self._default_nms_iou, nms_top_k=self._default_nms_top_k, max_predictions=self._default_max_predictions,
+                    multi_label_per_box=self._default_multi_label_per_box, class_agnostic_nms=self._default_class_agnostic_nms)  # fmt: skip
+        cb = self.get_post_prediction_callback(**{k: dflt[k] if kw.get(k) is None else kw[k] for k in dflt})
+        was_training = self.training
+        self.eval()
         out = []
         for i in range(0, len(images), batch_size):
+            # one fused pre-processing launch per image, ONE model / decode / NMS pass per batch, padding / rescaling undone for the whole
+            # batch at once, ONE device -> host copy; the per-image results are host views (the reference's pipeline returns host arrays)
             batch, geos = processor.preprocess_batch(images[i : i + batch_size], device)
-            rows = self.predict(batch, batch_size=batch_size, **kw)
-            out += [processor.postprocess_boxes(r, g) for r, g in zip(rows, geos)]
+            rows, _idx, count = cb.forward_batched(self(batch))
+            shift, scale = processor.batch_shift_scale(geos, device)
+            rows = torch.cat([(rows[..., :4] + shift.repeat(1, 2)[:, None, :]) * scale.repeat(1, 2)[:, None, :], rows[..., 4:]], dim=-1)
+            rows_h, counts = rows.cpu(), count.tolist()
+            out += [rows_h[b, :n] for b, n in enumerate(counts)]
+        self.train(was_training)
         return out

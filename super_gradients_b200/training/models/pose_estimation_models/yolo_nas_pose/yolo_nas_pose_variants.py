@@ -77,13 +77,27 @@ class YoloNASPose(CustomizableDetector):
             processor = self._image_processor or default_yolo_nas_pose_coco_processing_params()["image_processor"]
             device = next(self.parameters()).device
             out: List[PoseEstimationPredictions] = []
+            cb = self.get_post_prediction_callback(
+                conf=conf or self._default_nms_conf or 0.5, iou=iou or self._default_nms_iou or 0.7,
+                pre_nms_max_predictions=pre_nms_max_predictions or self._default_pre_nms_max_predictions or 300,
+                post_nms_max_predictions=post_nms_max_predictions or self._default_post_nms_max_predictions or 100,
+            )  # fmt: skip
+            was_training = self.training
+            self.eval()
             for i in range(0, len(raw), batch_size):
+                # one fused pre-processing launch per image, ONE model / decode / NMS pass per batch, the padding / rescaling of every
+                # image undone by batched launches, ONE device -> host copy per result tensor; the per-image objects are host views
+                # (the reference's pipeline returns host arrays as well: pipelines.py:445-452)
                 batch, geos = processor.preprocess_batch(raw[i : i + batch_size], device)
-                preds = self.predict(batch, iou=iou, conf=conf, pre_nms_max_predictions=pre_nms_max_predictions, post_nms_max_predictions=post_nms_max_predictions, batch_size=batch_size)
-                for pr, g in zip(preds, geos):
-                    poses = pr.poses.clone()
-                    poses[..., :2] = processor.postprocess_keypoints(pr.poses[..., :2], g)
-                    out.append(PoseEstimationPredictions(poses=poses, scores=pr.scores, bboxes_xyxy=processor.postprocess_boxes(pr.bboxes_xyxy, g)))
+                with torch.no_grad():
+                    res = self(batch)
+                    rows, poses, _idx, count = cb.forward_batched(res if self.heads.inference_mode is False else (res, None))
+                    shift, scale = processor.batch_shift_scale(geos, device)
+                    boxes = (rows[..., :4] + shift.repeat(1, 2)[:, None, :]) * scale.repeat(1, 2)[:, None, :]
+                    poses = torch.cat([(poses[..., :2] + shift[:, None, None, :]) * scale[:, None, None, :], poses[..., 2:]], dim=-1)
+                    boxes_h, poses_h, scores_h, counts = boxes.cpu(), poses.cpu(), rows[..., 4].cpu(), count.tolist()
+                out += [PoseEstimationPredictions(poses=poses_h[b, :n], scores=scores_h[b, :n], bboxes_xyxy=boxes_h[b, :n]) for b, n in enumerate(counts)]
+            self.train(was_training)
             return out
         cb = self.get_post_prediction_callback(
             conf=conf or self._default_nms_conf or 0.5, iou=iou or self._default_nms_iou or 0.7,

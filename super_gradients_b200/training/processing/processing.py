@@ -158,6 +158,15 @@ class ComposeProcessing(Processing):
         return batch, list(geos)
 
     @staticmethod
+    def batch_shift_scale(geos: Sequence[ImageGeometry], device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-image (shift [B, 2] = (-pad_left, -pad_top), scale [B, 2] = float32(1 / scale_w), float32(1 / scale_h)): the operands
+        of postprocess_boxes / postprocess_keypoints for a whole batch, so that undoing the padding / rescaling of every image is
+        a handful of batched launches ((v + shift) * scale in float32: the same two roundings per coordinate as the per-image form)."""
+        shift = torch.tensor([[-g.pad_left, -g.pad_top] for g in geos], dtype=torch.float32)
+        scale = torch.tensor([[float(np.float32(1 / g.scale_factor_w)), float(np.float32(1 / g.scale_factor_h))] for g in geos], dtype=torch.float32)
+        return shift.to(device, non_blocking=True), scale.to(device, non_blocking=True)
+
+    @staticmethod
     def postprocess_boxes(boxes_xyxy: torch.Tensor, g: ImageGeometry) -> torch.Tensor:
         """[n, >= 4] rows whose first four columns are xyxy in model-input pixels -> original-image pixels: shift by the padding,
         then multiply by float32(1 / scale) (_shift_bboxes_xyxy, _rescale_bboxes: transforms/utils.py:47-62, 155-166)."""

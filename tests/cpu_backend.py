@@ -88,6 +88,15 @@ def nchw_f32_to_nhwc_bf16(x, c_align=8):
     return out
 
 
+def stem_patches(x, R, stride, pad, c_out):
+    n, c, h, w = x.shape
+    P, Q = (h + 2 * pad - R) // stride + 1, (w + 2 * pad - R) // stride + 1
+    cols = torch.nn.functional.unfold(x.float(), R, padding=pad, stride=stride).reshape(n, c, R * R, P, Q)  # [n, c, (r, s), P, Q]
+    out = torch.zeros((n, c_out, P, Q), dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    out[:, : c * R * R] = _bf16(cols.permute(0, 2, 1, 3, 4).reshape(n, R * R * c, P, Q))  # channel = (r * R + s) * C + c
+    return out
+
+
 def nhwc_bf16_to_nchw_f32(x):
     return x.float().contiguous()
 
@@ -220,6 +229,7 @@ def wgrad_to_oihw(dw_krsc, C, out=None, accumulate=False):
     g = dw_krsc[..., :C].permute(0, 3, 1, 2)
     if out is None:
         return g.contiguous()
+    g = g.reshape(out.shape)  # an nn.Linear slot is [K, C]: the same memory as OIHW [K, C, 1, 1] (the kernel writes through a pointer)
     out.copy_(out + g if accumulate else g)
     return out
 
@@ -534,7 +544,7 @@ def pose_loss(d, cls_logits, reg_distri, pose_coords, pose_logits, anchor_points
     return r["items"], gc.reshape(cls_logits.shape), gr, gp, gl
 
 
-_TRAINING = dict(conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgrad_to_oihw, weight_prepare_batch=weight_prepare_batch,
+_TRAINING = dict(stem_patches=stem_patches, conv_dgrad=conv_dgrad, conv_wgrad=conv_wgrad, wgrad_to_oihw=wgrad_to_oihw, weight_prepare_batch=weight_prepare_batch,
                  run_weight_prepare_batch=run_weight_prepare_batch, wgrad_to_oihw_batch_table=wgrad_to_oihw_batch_table, run_wgrad_to_oihw_batch=run_wgrad_to_oihw_batch, qarep_alpha_finish_table=qarep_alpha_finish_table, run_qarep_alpha_finish=run_qarep_alpha_finish,
                  bn_act_fwd=bn_act_fwd, bn_act_bwd=bn_act_bwd, channel_stats=channel_stats, channel_dot=channel_dot, qarep_fwd=qarep_fwd, qarep_bwd=qarep_bwd,
                  maxpool_bwd=maxpool_bwd, head_grad_scatter=head_grad_scatter, tal_assign=tal_assign, atss_assign=atss_assign, dfl_iou_loss=dfl_iou_loss, sgd_step=sgd_step,

@@ -646,6 +646,47 @@ def test_folded_qarepvgg_path_is_the_same_block(golden, monkeypatch):
     assert l2rel(res[True][1][3], res[False][1][3]) < 1e-3  # parameters after two steps
 
 
+def test_patch_stem_is_the_same_block(golden, monkeypatch):
+    """functional._QARepVGGStem (the stem as one 1 x 1 GEMM over gathered patches, both branches in one launch) against the
+    two-convolution path of the same block: output, every parameter gradient, running statistics; then a whole TrainStep of the tiny
+    model with and without it.  (GPU twin: tests/test_modules_gpu.py::test_patch_stem_matches_the_two_convolution_path.)"""
+    from super_gradients_b200 import functional as SF
+    from super_gradients_b200.modules import QARepVGGBlock
+
+    cpu_backend.install_training(monkeypatch)
+
+    def run(patches, seed=0):
+        monkeypatch.setattr(SF, "STEM_PATCHES", [patches])
+        torch.manual_seed(seed)
+        blk = QARepVGGBlock(3, 16, stride=2, use_residual_connection=False).train()
+        with torch.no_grad():
+            for p in blk.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        x = torch.randn(2, 3, 22, 26).bfloat16().float()
+        assert SF.stem_patches_supported(blk, x) == patches
+        y = blk(x)
+        (y.float() * torch.linspace(-1, 1, y.numel()).reshape(y.shape)).sum().backward()
+        return y.detach().float(), {k: p.grad.clone() for k, p in blk.named_parameters() if p.grad is not None}, {k: v.clone() for k, v in blk.state_dict().items() if "running" in k}
+
+    y0, g0, r0 = run(False)
+    y1, g1, r1 = run(True)
+    assert y0.shape == y1.shape == (2, 16, 11, 13) and l2rel(y1, y0) < 4e-3, l2rel(y1, y0)
+    assert set(g0) == set(g1)
+    for k in g0:
+        assert l2rel(g1[k], g0[k]) < 2e-2 or float(g0[k].abs().max()) < 1e-4, (k, l2rel(g1[k], g0[k]))
+    for k in r0:
+        assert l2rel(r1[k], r0[k]) < 1e-3, k
+    g = golden("tiny_yolo_nas")
+    x, t = g["x"], _padded_targets(g)
+    res = {}
+    for patches in (False, True):
+        monkeypatch.setattr(SF, "STEM_PATCHES", [patches])
+        _, st = _train_step(g, monkeypatch)
+        res[patches] = _run(st, x, t, 2)
+    assert abs(res[True][0][0] - res[False][0][0]) < 2e-2 * abs(res[False][0][0])
+    assert l2rel(res[True][1][3], res[False][1][3]) < 1e-3  # parameters after two steps
+
+
 def test_resnet_blocks_with_drop_path_glue(golden, monkeypatch):
     """Drop-path wiring above the C ABI (the GPU twin is tests/test_modules_gpu.py::test_resnet_blocks_with_drop_path): the blocks
     hand the per-image scale to the fused bn + add + relu call and its backward; against the unmodified reference's fixture."""

@@ -210,11 +210,15 @@ def test_bn_act_fwd_bwd(act, with_res):
     # dy as a channel slice of a wider buffer (the gradient of a concat): read in place (SgbBnDesc.dy_pitch), identical results
     wide = torch.randn(n, c + 24, h, w, generator=g).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
     wide[:, 16 : 16 + c].copy_(to_nhwc_bf16(dy))
-    n0 = torch.cuda.memory_stats()["allocation.all.allocated"]
+    count = lambda: torch.cuda.memory_stats()["allocation.all.allocated"]  # noqa: E731
+    dyg = to_nhwc_bf16(dy)
+    n0 = count()
+    k.bn_act_bwd(dyg, xg, y, gamma.detach().to(DEV), mean, rstd, eps, act, want_residual_grad=with_res, beta=beta.detach().to(DEV))
+    n1 = count()
     dx2, dres2, dgamma2, dbeta2 = k.bn_act_bwd(wide[:, 16 : 16 + c], xg, y, gamma.detach().to(DEV), mean, rstd, eps, act, want_residual_grad=with_res, beta=beta.detach().to(DEV))
+    assert count() - n1 == n1 - n0, "the sliced dy was copied instead of being read in place"
     assert torch.equal(dx2, dx) and torch.equal(dgamma2, dgamma) and torch.equal(dbeta2, dbeta)
     assert not with_res or torch.equal(dres2, dres)
-    assert torch.cuda.memory_stats()["allocation.all.allocated"] - n0 <= 5, "the sliced dy was copied instead of being read in place"
 
 
 def test_maxpool_axpby_avgpool():

@@ -19,4 +19,26 @@ case "${1}" in
   fourth)  # dy-slice backward, drop-path, eval fold cache, bench --config 2..5
     timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 > gpurun_out/r2_pytest4.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_pytest4.log
     for c in 2 3 4 5; do printf "config %d: " $c; timeout 400 python bench.py --config $c --steps 10 --warmup 3 --skip-cpu-baseline 2>gpurun_out/r2_bench_c$c.err | tee gpurun_out/r2_bench_c$c.json | bench_line; tail -2 gpurun_out/r2_bench_c$c.err; done ;;
+  fifth)  # patch stem, smem max-pool, linear-slot fix (config 4 capture), batched predict post-processing; memory-kernel table + ncu
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 > gpurun_out/r2_pytest5.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_pytest5.log
+    for c in 2 4 5; do printf "config %d: " $c; timeout 400 python bench.py --config $c --steps 10 --warmup 3 --skip-cpu-baseline 2>gpurun_out/r2_bench5_c$c.err | tee gpurun_out/r2_bench5_c$c.json | bench_line; tail -2 gpurun_out/r2_bench5_c$c.err; done
+    printf "config 2, SGB_STEM_PATCHES=0: "; SGB_STEM_PATCHES=0 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline 2>/dev/null | bench_line
+    timeout 300 python tools/mem_kernels.py > gpurun_out/r2_mem_kernels.txt 2>gpurun_out/r2_mem_kernels.err; cat gpurun_out/r2_mem_kernels.txt; tail -3 gpurun_out/r2_mem_kernels.err
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"nms_kernel|loss_kernel|tal_topk_kernel|tal_decode_kernel" -c 8 -o gpurun_out/r2_full_mem -f python tools/mem_kernels.py --reps 1 > gpurun_out/r2_ncu_full_mem.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/r2_ncu_full_mem.log
+    timeout 300 python tools/timeline.py > gpurun_out/r2_timeline5.txt 2>gpurun_out/r2_timeline5.err; head -30 gpurun_out/r2_timeline5.txt ;;
+  sixth)  # cooperative fused backward passes (A/B), smem-staged stem gather, ncu: nms + graph-step launch list + conv kernels
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 > gpurun_out/r2_pytest6.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_pytest6.log
+    for fb in 1 0; do printf "SGB_FUSED_BWD=%d: " $fb; SGB_FUSED_BWD=$fb timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench6_fb$fb.err | tee gpurun_out/r2_bench6_fb$fb.json | bench_line; tail -2 gpurun_out/r2_bench6_fb$fb.err; done
+    timeout 300 python tools/timeline.py > gpurun_out/r2_timeline6.txt 2>gpurun_out/r2_timeline6.err; head -24 gpurun_out/r2_timeline6.txt
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:"nms_kernel" -c 4 -o gpurun_out/r2_full_nms -f python tools/mem_kernels.py --reps 1 > gpurun_out/r2_ncu_full_nms.log 2>&1; echo "ncu nms rc=$?"
+    SGB_PROFILER_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv       --log-file gpurun_out/r2_launches_graph_step.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/r2_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+    for kn in conv_umma_kernel wgrad_umma_kernel; do
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kn --launch-skip 20 --launch-count 3 -o gpurun_out/r2_full_$kn -f         python bench.py --steps 1 --warmup 1 --no-graph --skip-cpu-baseline > gpurun_out/r2_ncu_full_$kn.log 2>&1; echo "ncu $kn rc=$?"
+    done ;;
+  multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
+    N=${2:-2}
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \
+      > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench rc=$?"; tail -3 gpurun_out/r2_bench_n$N.err; bench_line < gpurun_out/r2_bench_n$N.json
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 tools/timeline.py --steps 4 --top 12 > gpurun_out/r2_timeline_n$N.txt 2> gpurun_out/r2_timeline_n$N.err
+    echo "timeline rc=$?"; head -16 gpurun_out/r2_timeline_n$N.txt; grep -h "nccl\|wall" gpurun_out/timeline_rank*.txt | head -40 ;;
 esac
