@@ -11,6 +11,7 @@
 // Reference: nn.BatchNorm2d as used by modules/conv_bn_act_block.py:92-93, modules/qarepvgg_block.py:190-204,
 // training/models/classification_models/resnet.py:53-84 and its autograd backward.
 #include "common.cuh"
+#include "stream_ring.cuh"
 
 #include <cooperative_groups.h>
 
@@ -21,17 +22,6 @@ constexpr int TPB = 256;
 struct V8 {
   float v[8];
 };
-__device__ __forceinline__ V8 ld8(const bf16* p) {
-  uint4 r = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-  V8 o;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    o.v[2 * i] = __uint_as_float(w[i] << 16);
-    o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-  return o;
-}
 __device__ __forceinline__ void st8(bf16* p, const V8& a) {
   uint4 r;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
@@ -42,15 +32,43 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
 
 // Op interface:
 //   static constexpr int NCOEF, NACC;           (NACC == 0: pure map)
+//   static constexpr int NIN, UNROLL, DEPTH;    16-byte input vectors per pixel / pixels per ring slot / ring slots per thread
 //   __device__ void prologue(float* sc) const;  all threads of the CTA; fills sc[NCOEF][C]
-//   struct In;  static constexpr int UNROLL;    the 16-byte vectors of one pixel / pixels batched per thread
-//   __device__ In load(int64_t pix, int c0) const;
-//   __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[NCOEF][8], float (&acc)[NACC or 1][8]) const;
-//   (all loads of a batch are issued before the first store, so UNROLL pixels x |In| vectors are in flight per thread)
+//   __device__ const bf16* base(int j, int c0) const;  address of input j at pixel 0, channel c0 (nullptr: input absent)
+//   __device__ int pitch(int j) const;                 its pixel pitch in elements
+//   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[NIN], const float (&r)[NCOEF][8], float (&acc)[NACC or 1][8]) const;
 //   double* out; int out_stride;                (only when NACC > 0)
+//
+// Memory pipeline.  These passes are pure HBM streams, and with the per-channel coefficients in registers (up to 12 x 8 floats) a
+// thread has no registers left to keep many loads in flight: at 170-190 registers one 256-thread CTA is resident per SM, and with
+// 2-4 pixels x 3 vectors of plain loads per thread that is 24-49 KB in flight per SM -- the passes ran at 1.5-3 TB/s.  Every thread
+// now owns a private ring of DEPTH slots in shared memory that it fills with cp.async (16 bytes, L1 bypassed) DEPTH iterations
+// ahead and reads back itself: no barrier is involved (a thread only ever reads what it copied), the bytes in flight per SM are
+// DEPTH x UNROLL x NIN x 4 KB (96-128 KB) whatever the register count, and channel slices of wider buffers cost nothing extra
+// because every thread still forms its own addresses.  One CTA per SM (the ring is the SM's shared memory), grid <= SM count x
+// resident CTAs, each CTA walks one contiguous range of pixels.
+__device__ __forceinline__ V8 unpack8(const uint4& r) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  V8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o.v[2 * i] = __uint_as_float(w[i] << 16);
+    o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return o;
+}
 template <class Op>
-__device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const int C, float* sc) {
-  constexpr int NCOEF = Op::NCOEF, NACC = Op::NACC;
+constexpr size_t chan_ring_bytes() {
+  return sgb_ring::bytes<Op::NIN, Op::UNROLL, Op::DEPTH, TPB>();
+}
+template <class Op>
+size_t chan_smem_bytes(int C) {
+  return chan_ring_bytes<Op>() + ((size_t)Op::NCOEF * C + (size_t)(Op::NACC * 8 + 1) * TPB) * sizeof(float);
+}
+
+template <class Op>
+__device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const int C, float* sc, const uint32_t ring) {
+  constexpr int NCOEF = Op::NCOEF, NACC = Op::NACC, NIN = Op::NIN, U = Op::UNROLL, D = Op::DEPTH;
   // sc: [NCOEF][C] (+ [NACC][cvb*8] reduction scratch)
   op.prologue(sc);
   __syncthreads();
@@ -62,6 +80,7 @@ __device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const i
   const int64_t p0 = blockIdx.x * per;
   const int64_t p1 = (p0 + per < M) ? p0 + per : M;
   float* sred = sc + NCOEF * C;  // [TPB][NACC * 8]: every thread's partial sums, tree-summed without atomics
+  const uint32_t my_ring = ring + (uint32_t)t * 16u;  // slot (d, k, j) of this thread: + ((d * U + k) * NIN + j) * TPB * 16
   for (int cv0 = 0; cv0 < cvs; cv0 += cvb) {
     const int cv = cv0 + cvi;
     const bool active = pl < lanes && cv < cvs;
@@ -76,16 +95,18 @@ __device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const i
       for (int k = 0; k < NCOEF; ++k)
 #pragma unroll
         for (int e = 0; e < 8; ++e) r[k][e] = sc[k * C + cv * 8 + e];
-      constexpr int U = Op::UNROLL;
-      int64_t pix = p0 + pl;
-      for (; pix + (int64_t)(U - 1) * lanes < p1; pix += (int64_t)U * lanes) {
-        typename Op::In in[U];
+      const int c0 = cv * 8;
+      const int64_t first = p0 + pl;
+      const int64_t mine = first < p1 ? (p1 - first + lanes - 1) / lanes : 0;  // pixels first, first + lanes, ... of this thread
+      const bf16* ptr[NIN];  // this thread's pixel `first` of every input
+      int64_t kstep[NIN];    // elements between two consecutive pixels of this thread
 #pragma unroll
-        for (int k = 0; k < U; ++k) in[k] = op.load(pix + (int64_t)k * lanes, cv * 8);
-#pragma unroll
-        for (int k = 0; k < U; ++k) op.finish(pix + (int64_t)k * lanes, cv * 8, in[k], r, acc);
+      for (int j = 0; j < NIN; ++j) {
+        const bf16* b = op.base(j, c0);
+        kstep[j] = (int64_t)lanes * op.pitch(j);
+        ptr[j] = b ? b + first * op.pitch(j) : nullptr;
       }
-      for (; pix < p1; pix += lanes) op.finish(pix, cv * 8, op.load(pix, cv * 8), r, acc);
+      sgb_ring::walk<NIN, U, D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t q, const uint4(&raw)[NIN]) { op.finish(first + q * lanes, c0, raw, r, acc); });
     }
     if constexpr (NACC > 0) {
       // thread t = pl * cvb + cvi stores its NACC*8 sums at [pl][cvi][a][e]; output j = (cvi, a, e) then sums over pl
@@ -109,47 +130,58 @@ __device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const i
   }
 }
 
+// dynamic shared memory: [ring][coefficients + reduction scratch]
 template <class Op>
 __global__ void __launch_bounds__(TPB) chan_kernel(const Op op, const int64_t M, const int C) {
   SGB_GRID_DEP_LAUNCH();
   SGB_GRID_DEP_WAIT();
-  extern __shared__ float sc[];
-  chan_body(op, M, C, sc);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  chan_body(op, M, C, reinterpret_cast<float*>(smem_raw + chan_ring_bytes<Op>()), smem_u32(smem_raw));
 }
 
 // A reduction pass and the apply pass that consumes its sums as ONE cooperative launch: grid-wide barrier in between.  Saves a
 // launch (ramp-up, tail) per pair and, for the layers whose operands fit the 126 MB L2 (every 80 x 80 and smaller map of YOLO-NAS-S
 // at batch 32), the apply pass's re-read of the same tensors hits L2 instead of HBM.  The sums are fp64 global atomics in both forms.
 template <class OpA, class OpB>
+constexpr size_t chan_ring_bytes2() {
+  return chan_ring_bytes<OpA>() > chan_ring_bytes<OpB>() ? chan_ring_bytes<OpA>() : chan_ring_bytes<OpB>();
+}
+template <class OpA, class OpB>
 __global__ void __launch_bounds__(TPB) chan_fused_kernel(const OpA a, const OpB b, const int64_t M, const int C) {
-  extern __shared__ float sc[];
-  chan_body(a, M, C, sc);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sc = reinterpret_cast<float*>(smem_raw + chan_ring_bytes2<OpA, OpB>());
+  chan_body(a, M, C, sc, smem_u32(smem_raw));
   __threadfence();
   cooperative_groups::this_grid().sync();
-  chan_body(b, M, C, sc);
+  chan_body(b, M, C, sc, smem_u32(smem_raw));
 }
 
-template <class OpA, class OpB>
-int launch_chan_fused(const OpA& a, const OpB& b, int64_t M, int C, cudaStream_t st, const char* what) {
-  auto bytes = [&](int ncoef, int nacc) { return ((size_t)ncoef * C + (size_t)(nacc * 8 + 1) * TPB) * sizeof(float); };
-  const size_t sa = bytes(OpA::NCOEF, OpA::NACC), sb = bytes(OpB::NCOEF, OpB::NACC);
-  const size_t smem = sa > sb ? sa : sb;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(chan_fused_kernel<OpA, OpB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr = true;
-  }
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chan_fused_kernel<OpA, OpB>, TPB, smem) != cudaSuccess || per_sm < 1)
-    return sgb_cuda_check(cudaErrorCooperativeLaunchTooLarge, what);
+static int sgb_sm_count() {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
   }
+  return sms;
+}
+
+template <class OpA, class OpB>
+int launch_chan_fused(const OpA& a, const OpB& b, int64_t M, int C, cudaStream_t st, const char* what) {
+  auto tail = [&](int ncoef, int nacc) { return ((size_t)ncoef * C + (size_t)(nacc * 8 + 1) * TPB) * sizeof(float); };
+  const size_t ta = tail(OpA::NCOEF, OpA::NACC), tb = tail(OpB::NCOEF, OpB::NACC);
+  const size_t smem = chan_ring_bytes2<OpA, OpB>() + (ta > tb ? ta : tb);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(chan_fused_kernel<OpA, OpB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chan_fused_kernel<OpA, OpB>, TPB, smem) != cudaSuccess || per_sm < 1)
+    return sgb_cuda_check(cudaErrorCooperativeLaunchTooLarge, what);
   int64_t want = (M + 255) / 256;
-  int64_t cap = (int64_t)sms * per_sm;
+  int64_t cap = (int64_t)sgb_sm_count() * per_sm;
   if (cap > sgb_chan_grid_cap()) cap = sgb_chan_grid_cap();
   const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   int64_t Mv = M;
@@ -160,16 +192,20 @@ int launch_chan_fused(const OpA& a, const OpB& b, int64_t M, int C, cudaStream_t
 
 template <class Op>
 int launch_chan(const Op& op, int64_t M, int C, cudaStream_t st, const char* what) {
-  const int cvs = C / 8;
-  const int cvb = cvs < TPB ? cvs : TPB;
-  const size_t smem = ((size_t)Op::NCOEF * C + (size_t)(Op::NACC * 8 + 1) * TPB) * sizeof(float);
-  int64_t want = (M + 255) / 256;
-  const int grid = (int)(want < 1 ? 1 : (want > sgb_chan_grid_cap() ? sgb_chan_grid_cap() : want));
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    cudaFuncSetAttribute(chan_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr = true;
+  const size_t smem = chan_smem_bytes<Op>(C);
+  static int per_sm = 0;  // resident CTAs per SM of this instantiation at its largest shared-memory footprint seen so far
+  static size_t attr_smem = 0;
+  if (per_sm == 0 || smem > attr_smem) {
+    cudaFuncSetAttribute(chan_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chan_kernel<Op>, TPB, smem) != cudaSuccess || n < 1) n = 1;
+    per_sm = n;
+    attr_smem = smem;
   }
+  int64_t want = (M + 255) / 256;
+  int64_t cap = (int64_t)sgb_sm_count() * per_sm;
+  if (cap > sgb_chan_grid_cap()) cap = sgb_chan_grid_cap();
+  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   SGB_LAUNCH(chan_kernel<Op>, grid, TPB, smem, st, op, M, C);
   return sgb_cuda_check(cudaGetLastError(), what);
 }
@@ -211,18 +247,15 @@ struct BnFwdOp {
       }
     }
   }
-  static constexpr int UNROLL = 4;
-  struct In {
-    V8 a, rr;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.a = ld8(x + pix * d.x_pitch + d.x_off + c0);
-    if (res) in.rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
-    return in;
-  }
-  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[2][8], float (&)[1][8]) const {
-    V8 a = in.a;
+  static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? x + d.x_off + c0 : (res ? res + d.r_off + c0 : nullptr); }
+  __device__ int pitch(int j) const { return j == 0 ? d.x_pitch : d.r_pitch; }
+  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[2][8], float (&)[1][8]) const {
+    V8 a = unpack8(raw[0]);
+    struct {
+      V8 rr;
+    } in;
+    if (res) in.rr = unpack8(raw[1]);
     if (d.sample_scale) {  // drop-path: the normalised branch of image n is scaled by 0 or 1 / keep_prob before the residual joins
       const float ss = d.sample_scale[pix / d.hw];
 #pragma unroll
@@ -255,18 +288,15 @@ struct BnInferOp {
       sc[C + c] = b - rmean[c] * g * rstd;
     }
   }
-  static constexpr int UNROLL = 4;
-  struct In {
-    V8 a, rr;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.a = ld8(x + pix * d.x_pitch + d.x_off + c0);
-    if (res) in.rr = ld8(res + pix * d.r_pitch + d.r_off + c0);
-    return in;
-  }
-  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[2][8], float (&)[1][8]) const {
-    V8 a = in.a;
+  static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? x + d.x_off + c0 : (res ? res + d.r_off + c0 : nullptr); }
+  __device__ int pitch(int j) const { return j == 0 ? d.x_pitch : d.r_pitch; }
+  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[2][8], float (&)[1][8]) const {
+    V8 a = unpack8(raw[0]);
+    struct {
+      V8 rr;
+    } in;
+    if (res) in.rr = unpack8(raw[1]);
     if (res) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(a.v[e], r[0][e], r[1][e]) + in.rr.v[e], d.act);
@@ -297,19 +327,17 @@ struct BnBwdRedOp {
       sc[3 * C + c] = b - mean[c] * g * rstd[c];
     }
   }
-  static constexpr int UNROLL = 4;
-  struct In {
-    V8 g, xv, yv;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.g = ld8(dy + pix * (d.dy_pitch ? d.dy_pitch : d.y_pitch) + (d.dy_pitch ? d.dy_off : d.y_off) + c0);
-    in.xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
-    if (y) in.yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
-    return in;
+  static constexpr int NIN = 3, UNROLL = 2, DEPTH = 5;
+  __device__ const bf16* base(int j, int c0) const {
+    if (j == 0) return dy + (d.dy_pitch ? d.dy_off : d.y_off) + c0;
+    if (j == 1) return x + d.x_off + c0;
+    return y ? y + d.y_off + c0 : nullptr;
   }
-  __device__ void finish(int64_t pix, int, const In& in, const float (&r)[4][8], float (&acc)[2][8]) const {
-    const V8 &g = in.g, &xv = in.xv, &yv = in.yv;
+  __device__ int pitch(int j) const { return j == 0 ? (d.dy_pitch ? d.dy_pitch : d.y_pitch) : (j == 1 ? d.x_pitch : d.y_pitch); }
+  __device__ void finish(int64_t pix, int, const uint4 (&raw)[3], const float (&r)[4][8], float (&acc)[2][8]) const {
+    const V8 g = unpack8(raw[0]), xv = unpack8(raw[1]);
+    V8 yv;
+    if (y) yv = unpack8(raw[2]);
     const float ss = d.sample_scale ? d.sample_scale[pix / d.hw] : 1.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -353,19 +381,17 @@ struct BnBwdApplyOp {
       }
     }
   }
-  static constexpr int UNROLL = 2;
-  struct In {
-    V8 g, xv, yv;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.g = ld8(dy + pix * (d.dy_pitch ? d.dy_pitch : d.y_pitch) + (d.dy_pitch ? d.dy_off : d.y_off) + c0);
-    in.xv = ld8(x + pix * d.x_pitch + d.x_off + c0);
-    if (y) in.yv = ld8(y + pix * d.y_pitch + d.y_off + c0);
-    return in;
+  static constexpr int NIN = 3, UNROLL = 2, DEPTH = 5;
+  __device__ const bf16* base(int j, int c0) const {
+    if (j == 0) return dy + (d.dy_pitch ? d.dy_off : d.y_off) + c0;
+    if (j == 1) return x + d.x_off + c0;
+    return y ? y + d.y_off + c0 : nullptr;
   }
-  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[6][8], float (&)[1][8]) const {
-    const V8 &g = in.g, &xv = in.xv, &yv = in.yv;
+  __device__ int pitch(int j) const { return j == 0 ? (d.dy_pitch ? d.dy_pitch : d.y_pitch) : (j == 1 ? d.x_pitch : d.y_pitch); }
+  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[3], const float (&r)[6][8], float (&)[1][8]) const {
+    const V8 g = unpack8(raw[0]), xv = unpack8(raw[1]);
+    V8 yv;
+    if (y) yv = unpack8(raw[2]);
     const float ss = d.sample_scale ? d.sample_scale[pix / d.hw] : 1.f;
     V8 o, dr;
 #pragma unroll
@@ -454,19 +480,12 @@ struct QarepFwdOp {
       }
     }
   }
-  static constexpr int UNROLL = 4;
-  struct In {
-    V8 a, b;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
-    in.b = ld8(u + pix * d.pitchu + d.offu + c0);
-    return in;
-  }
-  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[3][8], float (&)[1][8]) const {
-    V8 a = in.a;
-    const V8& b = in.b;
+  static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + d.off3 + c0 : u + d.offu + c0; }
+  __device__ int pitch(int j) const { return j == 0 ? d.pitch3 : d.pitchu; }
+  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[3][8], float (&)[1][8]) const {
+    V8 a = unpack8(raw[0]);
+    const V8 b = unpack8(raw[1]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(r[0][e], a.v[e], fmaf(r[1][e], b.v[e], r[2][e])), d.act);
     st8(outp + pix * d.pitcho + d.offo + c0, a);
@@ -494,19 +513,14 @@ struct QarepBwdRedOp {
       sc[7 * C + c] = coef[8 * C + c];
     }
   }
-  static constexpr int UNROLL = 4;
-  struct In {
-    V8 g, a, b;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.g = ld8(dout + pix * (d.pitchd ? d.pitchd : d.pitcho) + (d.pitchd ? d.offd : d.offo) + c0);
-    in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
-    in.b = ld8(u + pix * d.pitchu + d.offu + c0);
-    return in;
+  static constexpr int NIN = 3, UNROLL = 2, DEPTH = 5;
+  __device__ const bf16* base(int j, int c0) const {
+    if (j == 0) return dout + (d.pitchd ? d.offd : d.offo) + c0;
+    return j == 1 ? y3 + d.off3 + c0 : u + d.offu + c0;
   }
-  __device__ void finish(int64_t, int, const In& in, const float (&r)[8][8], float (&acc)[3][8]) const {
-    const V8 &g = in.g, &a = in.a, &b = in.b;
+  __device__ int pitch(int j) const { return j == 0 ? (d.pitchd ? d.pitchd : d.pitcho) : (j == 1 ? d.pitch3 : d.pitchu); }
+  __device__ void finish(int64_t, int, const uint4 (&raw)[3], const float (&r)[8][8], float (&acc)[3][8]) const {
+    const V8 g = unpack8(raw[0]), a = unpack8(raw[1]), b = unpack8(raw[2]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float dz = g.v[e];
@@ -573,19 +587,14 @@ struct QarepBwdApplyOp {
       }
     }
   }
-  static constexpr int UNROLL = 2;
-  struct In {
-    V8 g, a, b;
-  };
-  __device__ In load(int64_t pix, int c0) const {
-    In in;
-    in.g = ld8(dout + pix * (d.pitchd ? d.pitchd : d.pitcho) + (d.pitchd ? d.offd : d.offo) + c0);
-    in.a = ld8(y3 + pix * d.pitch3 + d.off3 + c0);
-    in.b = ld8(u + pix * d.pitchu + d.offu + c0);
-    return in;
+  static constexpr int NIN = 3, UNROLL = 2, DEPTH = 5;
+  __device__ const bf16* base(int j, int c0) const {
+    if (j == 0) return dout + (d.pitchd ? d.offd : d.offo) + c0;
+    return j == 1 ? y3 + d.off3 + c0 : u + d.offu + c0;
   }
-  __device__ void finish(int64_t pix, int c0, const In& in, const float (&r)[12][8], float (&)[1][8]) const {
-    const V8 &g = in.g, &a = in.a, &b = in.b;
+  __device__ int pitch(int j) const { return j == 0 ? (d.pitchd ? d.pitchd : d.pitcho) : (j == 1 ? d.pitch3 : d.pitchu); }
+  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[3], const float (&r)[12][8], float (&)[1][8]) const {
+    const V8 g = unpack8(raw[0]), a = unpack8(raw[1]), b = unpack8(raw[2]);
     V8 o3, ou;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {

@@ -4,6 +4,7 @@
 // vectors (8 channels) per thread with consecutive threads on consecutive channel vectors (coalesced), per-channel
 // reductions go registers -> shared atomics -> one fp64 global atomic per channel per CTA.
 #include "common.cuh"
+#include "stream_ring.cuh"
 
 namespace {
 
@@ -14,6 +15,17 @@ struct V8 {
 };
 __device__ __forceinline__ V8 ld8(const bf16* p) {
   uint4 r = *reinterpret_cast<const uint4*>(p);
+  V8 o;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o.v[2 * i] = f.x;
+    o.v[2 * i + 1] = f.y;
+  }
+  return o;
+}
+__device__ __forceinline__ V8 unpack8(const uint4& r) {
   V8 o;
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
@@ -42,32 +54,40 @@ inline int grid_for(int64_t work, int per_cta = TPB, int max_ctas = 148 * 8) {
 // ---------------------------------------------------------------------------------------------- weights / layout
 // element i of the concatenated [K][R][S][cp] (KRSC) ++ [C][R][S][Kp] (CRSK) bf16 copies of one fp32 OIHW filter
 __device__ __forceinline__ void weight_prepare_elem(const float* __restrict__ w, int K, int C, int R, int S, int cp, bf16* krsc,
-                                                    bf16* crsk, float sc, int add_identity, int64_t i) {
-  const int Kp = ((K + 7) / 8) * 8;
-  const int64_t n1 = (int64_t)K * R * S * cp;
+                                                    bf16* crsk, float sc, int add_identity, int64_t i64) {
+  // one filter has far fewer than 2^31 elements: 32-bit unsigned index arithmetic (a 64-bit division costs ~10x a 32-bit one)
+  const uint32_t Kp = (uint32_t)((K + 7) / 8) * 8, uC = (uint32_t)C, uR = (uint32_t)R, uS = (uint32_t)S, ucp = (uint32_t)cp;
+  const uint32_t n1 = (uint32_t)K * uR * uS * ucp;
+  const uint32_t i = (uint32_t)i64;
   if (i < n1) {
-    int c = i % cp;
-    int64_t t = i / cp;
-    int s = t % S; t /= S;
-    int r = t % R;
-    int k = t / R;
+    const uint32_t c = i % ucp;
+    uint32_t t = i / ucp;
+    uint32_t s = 0, r = 0;
+    if (uR * uS != 1) {
+      s = t % uS; t /= uS;
+      r = t % uR; t /= uR;
+    }
+    const uint32_t k = t;
     float v = 0.f;
-    if (c < C) {
-      v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
-      if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
+    if (c < uC) {
+      v = w[((k * uC + c) * uR + r) * uS + s] * sc;
+      if (add_identity && k == c && r == uR / 2 && s == uS / 2) v += 1.f;
     }
     krsc[i] = __float2bfloat16_rn(v);
   } else {
-    int64_t j = i - n1;
-    int k = j % Kp;
-    int64_t t = j / Kp;
-    int s = t % S; t /= S;
-    int r = t % R;
-    int c = t / R;
+    const uint32_t j = i - n1;
+    const uint32_t k = j % Kp;
+    uint32_t t = j / Kp;
+    uint32_t s = 0, r = 0;
+    if (uR * uS != 1) {
+      s = t % uS; t /= uS;
+      r = t % uR; t /= uR;
+    }
+    const uint32_t c = t;
     float v = 0.f;
-    if (k < K) {
-      v = w[(((int64_t)k * C + c) * R + r) * S + s] * sc;
-      if (add_identity && k == c && r == R / 2 && s == S / 2) v += 1.f;
+    if (k < (uint32_t)K) {
+      v = w[((k * uC + c) * uR + r) * uS + s] * sc;
+      if (add_identity && k == c && r == uR / 2 && s == uS / 2) v += 1.f;
     }
     crsk[j] = __float2bfloat16_rn(v);
   }
@@ -85,13 +105,15 @@ __global__ void weight_prepare_kernel(const float* __restrict__ w, int K, int C,
 
 // element i of the fp32 OIHW gradient gathered from the fp32 KRSC accumulation buffer
 __device__ __forceinline__ void wgrad_to_oihw_elem(const float* __restrict__ dw, int C, int R, int S, int cp, float* g,
-                                                   int accumulate, int64_t i) {
-  int s = i % S;
-  int64_t t = i / S;
-  int r = t % R; t /= R;
-  int c = t % C;
-  int k = t / C;
-  float v = dw[(((int64_t)k * R + r) * S + s) * cp + c];
+                                                   int accumulate, int64_t i64) {
+  const uint32_t i = (uint32_t)i64, uC = (uint32_t)C, uR = (uint32_t)R, uS = (uint32_t)S;
+  uint32_t t = i, s = 0, r = 0;
+  if (uR * uS != 1) {
+    s = t % uS; t /= uS;
+    r = t % uR; t /= uR;
+  }
+  const uint32_t c = t % uC, k = t / uC;
+  const float v = dw[(((size_t)k * uR + r) * uS + s) * (uint32_t)cp + c];
   g[i] = accumulate ? g[i] + v : v;
 }
 
@@ -115,23 +137,43 @@ __device__ __forceinline__ int find_item(const Item* items, int n, int64_t i) {
   return lo;
 }
 
-__global__ void weight_prepare_batch_kernel(const SgbWeightItem* __restrict__ items, int n, int64_t total) {
-  SGB_GRID_DEP_LAUNCH();
-  SGB_GRID_DEP_WAIT();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const SgbWeightItem it = items[find_item(items, n, i)];
-    weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f,
-                        it.add_identity, i - it.start);
+// A CTA walks chunks of BATCH_CHUNK consecutive elements; one search per chunk (thread 0, broadcast through shared memory) finds
+// the item of the chunk's first element, and a thread re-searches only when its element lies past that item's end (a chunk
+// straddling two filters).  The first version searched per element (8 dependent loads for ~200 items): 295 us for 19 M weights.
+constexpr int BATCH_CHUNK = 2048;
+template <class Item, class Fn>
+__device__ __forceinline__ void batch_walk(const Item* __restrict__ items, int n, int64_t total, Fn&& fn) {
+  __shared__ int s_first;
+  for (int64_t c0 = (int64_t)blockIdx.x * BATCH_CHUNK; c0 < total; c0 += (int64_t)gridDim.x * BATCH_CHUNK) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_first = find_item(items, n, c0);
+    __syncthreads();
+    int idx = s_first;
+    Item it = items[idx];
+    int64_t end = idx + 1 < n ? items[idx + 1].start : total;
+    for (int64_t i = c0 + threadIdx.x; i < c0 + BATCH_CHUNK && i < total; i += blockDim.x) {
+      while (i >= end) {  // next filter (filters are much longer than a chunk is wide, so this runs at most a few times)
+        ++idx;
+        it = items[idx];
+        end = idx + 1 < n ? items[idx + 1].start : total;
+      }
+      fn(it, i - it.start);
+    }
   }
 }
 
-__global__ void wgrad_to_oihw_batch_kernel(const SgbWgradItem* __restrict__ items, int n, int64_t total) {
+__global__ void __launch_bounds__(TPB) weight_prepare_batch_kernel(const SgbWeightItem* __restrict__ items, int n, int64_t total) {
   SGB_GRID_DEP_LAUNCH();
   SGB_GRID_DEP_WAIT();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const SgbWgradItem it = items[find_item(items, n, i)];
-    wgrad_to_oihw_elem(it.dw, it.C, it.R, it.S, it.c_pad, it.g, it.accumulate, i - it.start);
-  }
+  batch_walk(items, n, total, [](const SgbWeightItem& it, int64_t local) {
+    weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f, it.add_identity, local);
+  });
+}
+
+__global__ void __launch_bounds__(TPB) wgrad_to_oihw_batch_kernel(const SgbWgradItem* __restrict__ items, int n, int64_t total) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
+  batch_walk(items, n, total, [](const SgbWgradItem& it, int64_t local) { wgrad_to_oihw_elem(it.dw, it.C, it.R, it.S, it.c_pad, it.g, it.accumulate, local); });
 }
 
 __global__ void __launch_bounds__(256) qarep_alpha_finish_kernel(const SgbAlphaItem* __restrict__ items) {
@@ -229,6 +271,49 @@ __global__ void __launch_bounds__(256) stem_patches_kernel(const float* __restri
   }
 }
 
+// The YOLO-NAS stem shape (3 channels, 3 x 3, stride 2, pad 1, 32 patch channels) with every index a compile-time constant: no
+// integer division anywhere, one CTA per (image, output row), the 3 x 3 input rows staged with coalesced fp32 reads, each thread
+// assembles whole 64-byte pixels (4 vectors) from shared memory.  The generic kernel above spent its time in div / mod chains
+// (480 us for 32 x 3 x 640 x 640; the data is 157 MB in + 210 MB out = 56 us at the HBM peak).
+__global__ void __launch_bounds__(256) stem_patches_c3r3s2_kernel(const float* __restrict__ x, int H, int W, bf16* __restrict__ y, int P, int Q) {
+  SGB_GRID_DEP_LAUNCH();
+  SGB_GRID_DEP_WAIT();
+  extern __shared__ float srow[];  // [9 = (c, r)][span], span = 2 * Q + 1 (input columns -1 .. 2Q - 1)
+  const int p = blockIdx.x % P, n = blockIdx.x / P;
+  const int span = 2 * Q + 1;
+  const int64_t hw = (int64_t)H * W;
+#pragma unroll
+  for (int cr = 0; cr < 9; ++cr) {
+    const int c = cr / 3, r = cr % 3;
+    const int h = 2 * p - 1 + r;
+    const bool hin = h >= 0 && h < H;
+    const float* src = x + ((int64_t)n * 3 + c) * hw + (int64_t)(hin ? h : 0) * W - 1;
+    for (int j = threadIdx.x; j < span; j += 256) srow[cr * span + j] = (hin && j >= 1 && j <= W) ? src[j] : 0.f;
+  }
+  __syncthreads();
+  bf16* yrow = y + ((int64_t)n * P + p) * Q * 32;
+  // thread -> (pixel q, vector v): consecutive threads write consecutive 16-byte pieces
+  for (int i = threadIdx.x; i < Q * 4; i += 256) {
+    const int v = i & 3, q = i >> 2;
+    V8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      // patch channel ch = (r * 3 + s) * 3 + c for ch < 27; v is runtime (0..3), so select among the four constant patterns
+      float val = 0.f;
+#pragma unroll
+      for (int vv = 0; vv < 4; ++vv) {
+        const int ch = vv * 8 + e;
+        if (ch < 27 && v == vv) {
+          const int c = ch % 3, rs = ch / 3, r = rs / 3, s2 = rs % 3;
+          val = srow[(c * 3 + r) * span + 2 * q + s2];
+        }
+      }
+      o.v[e] = val;
+    }
+    st8(yrow + (int64_t)q * 32 + v * 8, o);
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, int H, int W, int pitch, int off,
                                     float* y) {
   SGB_GRID_DEP_LAUNCH();
@@ -245,14 +330,22 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, in
 }
 
 // ---------------------------------------------------------------------------------------------- channel reductions
-// Generic per-channel reduction skeleton.  F::NACC sums per channel;  F::eval(pix, c0, acc[NACC][8]) accumulates the
-// contribution of 8 consecutive channels of one pixel.
+// Generic per-channel reduction skeleton.  F::NACC sums per channel over F::NIN input tensors; F::base(j, c0) / F::pitch(j) locate
+// input j; F::eval(raw[NIN], acc[NACC][8]) accumulates the contribution of 8 consecutive channels of one pixel.  The inputs stream
+// through the per-thread shared-memory ring of stream_ring.cuh (64 KB per CTA, two or three CTAs per SM).
+constexpr int RED_U = 2;
+template <class F>
+constexpr int red_depth() {
+  return 16 / (RED_U * F::NIN);  // 64 KB of ring per 256-thread CTA: two or three CTAs per SM
+}
 template <class F>
 __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C, double* out, int out_stride) {
   SGB_GRID_DEP_LAUNCH();
   SGB_GRID_DEP_WAIT();
-  constexpr int NACC = F::NACC;
-  extern __shared__ float sred[];  // [TPB][NACC*8]
+  constexpr int NACC = F::NACC, NIN = F::NIN, D = red_depth<F>();
+  extern __shared__ __align__(16) unsigned char smem_red[];
+  float* sred = reinterpret_cast<float*>(smem_red + sgb_ring::bytes<NIN, RED_U, D, TPB>());  // [TPB][NACC*8]
+  const uint32_t my_ring = smem_u32(smem_red) + (uint32_t)threadIdx.x * 16u;
   const int cvs = C / 8;
   const int cvb = cvs < TPB ? cvs : TPB;  // channel vectors per CTA pass
   const int lanes = TPB / cvb;
@@ -270,8 +363,16 @@ __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C,
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
     if (pl < lanes && cv < cvs) {
-#pragma unroll 4
-      for (int64_t pix = p0 + pl; pix < p1; pix += lanes) f.eval(pix, cv * 8, acc);
+      const int64_t first = p0 + pl;
+      const int64_t mine = first < p1 ? (p1 - first + lanes - 1) / lanes : 0;
+      const bf16* ptr[NIN];
+      int64_t kstep[NIN];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        kstep[j] = (int64_t)lanes * f.pitch(j);
+        ptr[j] = f.base(j, cv * 8) + first * f.pitch(j);
+      }
+      sgb_ring::walk<NIN, RED_U, D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t, const uint4(&raw)[NIN]) { f.eval(raw, acc); });
     }
     // every thread parks its NACC*8 partial sums at [pl][cvi][a][e]; output j = (cvi, a, e) sums over pl (no atomics)
     __syncthreads();
@@ -297,20 +398,32 @@ template <class F>
 int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaStream_t st) {
   int cvs = C / 8;
   int cvb = cvs < TPB ? cvs : TPB;
-  size_t smem = (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
+  size_t smem = sgb_ring::bytes<F::NIN, RED_U, red_depth<F>(), TPB>() + (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaFuncSetAttribute(chan_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chan_reduce_kernel<F>, TPB, smem) != cudaSuccess || n < 1) n = 1;
+    per_sm = n;
+  }
   int64_t want = (M + 255) / 256;  // >= 256 pixels per CTA
-  int grid = (int)(want < 1 ? 1 : (want > sgb_chan_grid_cap() ? sgb_chan_grid_cap() : want));
+  int64_t cap = (int64_t)148 * per_sm;
+  if (cap > sgb_chan_grid_cap()) cap = sgb_chan_grid_cap();
+  int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  (void)cvb;
   SGB_LAUNCH(chan_reduce_kernel<F>, grid, TPB, smem, st, f, M, C, out, out_stride);
   SGB_LAUNCH_CHECK("chan_reduce_kernel");
   return SGB_OK;
 }
 
 struct StatsF {
-  static constexpr int NACC = 2;
+  static constexpr int NACC = 2, NIN = 1;
   const bf16* x;
-  int pitch, off;
-  __device__ void eval(int64_t pix, int c0, float (&acc)[2][8]) const {
-    V8 a = ld8(x + pix * pitch + off + c0);
+  int pitch_, off;
+  __device__ const bf16* base(int, int c0) const { return x + off + c0; }
+  __device__ int pitch(int) const { return pitch_; }
+  __device__ void eval(const uint4 (&raw)[1], float (&acc)[2][8]) const {
+    V8 a = unpack8(raw[0]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       acc[0][e] += a.v[e];
@@ -320,11 +433,13 @@ struct StatsF {
 };
 
 struct QarepMomF {
-  static constexpr int NACC = 5;
+  static constexpr int NACC = 5, NIN = 2;
   const bf16 *y3, *u;
   int p3, o3, pu, ou;
-  __device__ void eval(int64_t pix, int c0, float (&acc)[5][8]) const {
-    V8 a = ld8(y3 + pix * p3 + o3 + c0), b = ld8(u + pix * pu + ou + c0);
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + o3 + c0 : u + ou + c0; }
+  __device__ int pitch(int j) const { return j == 0 ? p3 : pu; }
+  __device__ void eval(const uint4 (&raw)[2], float (&acc)[5][8]) const {
+    V8 a = unpack8(raw[0]), b = unpack8(raw[1]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       acc[0][e] += a.v[e];
@@ -515,11 +630,13 @@ __global__ void scale_add_kernel(const bf16* __restrict__ x1, int p1, int o1, co
 }
 
 struct DotF {
-  static constexpr int NACC = 1;
+  static constexpr int NACC = 1, NIN = 2;
   const bf16 *a, *b;
   int pa, oa, pb, ob;
-  __device__ void eval(int64_t pix, int c0, float (&acc)[1][8]) const {
-    V8 u = ld8(a + pix * pa + oa + c0), v = ld8(b + pix * pb + ob + c0);
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? a + oa + c0 : b + ob + c0; }
+  __device__ int pitch(int j) const { return j == 0 ? pa : pb; }
+  __device__ void eval(const uint4 (&raw)[2], float (&acc)[1][8]) const {
+    V8 u = unpack8(raw[0]), v = unpack8(raw[1]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] += u.v[e] * v.v[e];
   }
@@ -616,14 +733,14 @@ extern "C" int sgb_wgrad_to_oihw(const float* dw, int K, int C, int R, int S, in
 
 extern "C" int sgb_weight_prepare_batch(const SgbWeightItem* items_dev, int n_items, int64_t total, void* stream) {
   SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
-  SGB_LAUNCH(weight_prepare_batch_kernel, grid_for(total), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
+  SGB_LAUNCH(weight_prepare_batch_kernel, grid_for(total, BATCH_CHUNK), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
   SGB_LAUNCH_CHECK("weight_prepare_batch_kernel");
   return SGB_OK;
 }
 
 extern "C" int sgb_wgrad_to_oihw_batch(const SgbWgradItem* items_dev, int n_items, int64_t total, void* stream) {
   SGB_REQUIRE(items_dev && n_items > 0 && total > 0, "bad args");
-  SGB_LAUNCH(wgrad_to_oihw_batch_kernel, grid_for(total), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
+  SGB_LAUNCH(wgrad_to_oihw_batch_kernel, grid_for(total, BATCH_CHUNK), TPB, 0, (cudaStream_t)stream, items_dev, n_items, total);
   SGB_LAUNCH_CHECK("wgrad_to_oihw_batch_kernel");
   return SGB_OK;
 }
@@ -652,6 +769,11 @@ extern "C" int sgb_stem_patches_f32(const float* x, int N, int C, int H, int W, 
   SGB_REQUIRE(x && y && N > 0 && C > 0 && R > 0 && stride > 0 && pad >= 0, "bad args");
   SGB_REQUIRE(c_out % 8 == 0 && c_out >= C * R * R, "c_out must be a multiple of 8 and hold C * R * R patch entries");
   SGB_REQUIRE(P == (H + 2 * pad - R) / stride + 1 && Q == (W + 2 * pad - R) / stride + 1, "P/Q inconsistent");
+  if (C == 3 && R == 3 && stride == 2 && pad == 1 && c_out == 32 && H % 2 == 0 && W % 2 == 0 && (size_t)9 * (2 * Q + 1) * sizeof(float) <= 48 * 1024) {
+    SGB_LAUNCH(stem_patches_c3r3s2_kernel, N * P, 256, (size_t)9 * (2 * Q + 1) * sizeof(float), (cudaStream_t)stream, x, H, W, (bf16*)y, P, Q);
+    SGB_LAUNCH_CHECK("stem_patches_c3r3s2_kernel");
+    return SGB_OK;
+  }
   const size_t smem = (size_t)C * R * ((STEM_QT - 1) * stride + R) * sizeof(float);
   SGB_REQUIRE(smem <= 48 * 1024, "patch rows do not fit shared memory");
   const int64_t ctas = (int64_t)N * P * ((Q + STEM_QT - 1) / STEM_QT);

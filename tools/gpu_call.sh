@@ -35,6 +35,14 @@ case "${1}" in
     for kn in conv_umma_kernel wgrad_umma_kernel; do
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kn --launch-skip 20 --launch-count 3 -o gpurun_out/r2_full_$kn -f         python bench.py --steps 1 --warmup 1 --no-graph --skip-cpu-baseline > gpurun_out/r2_ncu_full_$kn.log 2>&1; echo "ncu $kn rc=$?"
     done ;;
+  seventh)  # state of HEAD after the container was re-created: suite, fused-backward A/B, timeline with the per-launch dump
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 > gpurun_out/r2_pytest7.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_pytest7.log
+    for fb in 1 0; do printf "SGB_FUSED_BWD=%d: " $fb; SGB_FUSED_BWD=$fb timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench7_fb$fb.err | tee gpurun_out/r2_bench7_fb$fb.json | bench_line; tail -2 gpurun_out/r2_bench7_fb$fb.err; done
+    timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline7_launches.txt > gpurun_out/r2_timeline7.txt 2>gpurun_out/r2_timeline7.err; head -40 gpurun_out/r2_timeline7.txt; tail -3 gpurun_out/r2_timeline7.err ;;
+  eighth)  # cp.async ring in the per-channel passes, constant-folded stem gather, chunked layout kernels: suite, bench, timeline
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest8.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_pytest8.log
+    for fb in 1 0; do printf "SGB_FUSED_BWD=%d: " $fb; SGB_FUSED_BWD=$fb timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench8_fb$fb.err | tee gpurun_out/r2_bench8_fb$fb.json | bench_line; tail -2 gpurun_out/r2_bench8_fb$fb.err; done
+    timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline8_launches.txt > gpurun_out/r2_timeline8.txt 2>gpurun_out/r2_timeline8.err; head -40 gpurun_out/r2_timeline8.txt; tail -3 gpurun_out/r2_timeline8.err ;;
   multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
     N=${2:-2}
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \

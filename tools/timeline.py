@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("--aten", action="store_true", help="eager step with Python stacks: which call sites launch the remaining ATen kernels")
+    ap.add_argument("--dump", default=None, help="also write every launch of the LAST timed step in start order (start us, duration us, name) to this file")
     args = ap.parse_args()
     import torch.distributed as dist
 
@@ -113,6 +114,12 @@ def main():
     for n, (c, dur, gap) in sorted(per.items(), key=lambda kv: -kv[1][1])[: args.top]:
         out.append(f"{n:70s} {c / args.steps:7.1f} {dur / args.steps / 1e3:8.3f} {dur / args.steps / wall * 100:5.1f}% {dur / c:7.1f} {gap / c:13.2f}")
     text = "\n".join(out)
+    if args.dump and rank == 0:
+        cut = t0 + (t1 - t0) * (args.steps - 1) / args.steps
+        last = [k for k in ks if k[0] >= cut]
+        with open(args.dump, "w") as f:
+            for s, e, n in last:
+                f.write(f"{(s - last[0][0]):10.1f} {(e - s):8.1f} {short(n)}\n")
     if world > 1:
         os.makedirs("gpurun_out", exist_ok=True)
         open(f"gpurun_out/timeline_rank{rank}.txt", "w").write(text + "\n")
