@@ -43,6 +43,8 @@ case "${1}" in
     timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest8.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_pytest8.log
     for fb in 1 0; do printf "SGB_FUSED_BWD=%d: " $fb; SGB_FUSED_BWD=$fb timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench8_fb$fb.err | tee gpurun_out/r2_bench8_fb$fb.json | bench_line; tail -2 gpurun_out/r2_bench8_fb$fb.err; done
     timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline8_launches.txt > gpurun_out/r2_timeline8.txt 2>gpurun_out/r2_timeline8.err; head -40 gpurun_out/r2_timeline8.txt; tail -3 gpurun_out/r2_timeline8.err ;;
+  table)  # per-shape convolution table (eager, no overlap)
+    timeout 300 python tools/conv_table.py > gpurun_out/r2_conv_table.txt 2>gpurun_out/r2_conv_table.err; cat gpurun_out/r2_conv_table.txt; tail -3 gpurun_out/r2_conv_table.err ;;
   multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
     N=${2:-2}
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \
