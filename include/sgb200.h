@@ -203,6 +203,10 @@ int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, 
                   const float* gamma3, const float* beta3, const float* bias1_alpha, const float* gamma_p,
                   const float* beta_p, float* rm3, float* rv3, float* rm_p, float* rv_p, sgb_bf16* out, float* coef,
                   void* stream);
+/* sgb_qarep_moments + sgb_qarep_fwd as ONE cooperative launch (moments, grid-wide barrier, apply); `moments` must be zero on entry. */
+int sgb_qarep_fwd_fused(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments, const float* gamma3,
+                        const float* beta3, const float* bias1_alpha, const float* gamma_p, const float* beta_p, float* rm3, float* rv3,
+                        float* rm_p, float* rv_p, sgb_bf16* out, float* coef, void* stream);
 /* pass 1: sums [3][C] = sum dzp, sum dzp*zhat, sum dzp*y3hat, dzp = dout*act'(pre).  `out` is unused (may be NULL):
  * the activation mask is recomputed from y3, u and the saved coefficients. */
 int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out, const sgb_bf16* y3,
@@ -236,6 +240,10 @@ int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_bf16* x2, i
  * out[c] += sum_pixels a*b (fp64), used for d(alpha). */
 int sgb_scale_add(const sgb_bf16* x1, int p1, int o1, const float* a_dev, const sgb_bf16* x2, int p2, int o2, sgb_bf16* y,
                   int py, int oy, int64_t M, int C, void* stream);
+/* y = (*a_dev)*x1 + x2 (x2 optional) and out_dot[c] += sum_pixels x1*xd (fp64) in one pass over x1: backward of the learnable-alpha
+ * shortcut (alpha * dy for the shortcut input, sum(dy * x) for alpha).  y may alias x2 (in-place accumulation). */
+int sgb_scale_add_dot(const sgb_bf16* x1, int p1, int o1, const float* a_dev, const sgb_bf16* x2, int p2, int o2, const sgb_bf16* xd, int pd,
+                      int od, sgb_bf16* y, int py, int oy, int64_t M, int C, double* out_dot, void* stream);
 int sgb_channel_dot(const sgb_bf16* a, int pa, int oa, const sgb_bf16* b, int pb, int ob, int64_t M, int C, double* out,
                     void* stream);
 int sgb_f32_to_bf16(const float* x, sgb_bf16* y, int64_t n, void* stream);

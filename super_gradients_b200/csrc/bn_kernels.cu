@@ -414,6 +414,30 @@ struct BnBwdApplyOp {
 // ============================================================================================== QARepVGG algebra
 // y3 = conv3x3(x) (raw), u = conv1x1_{alpha*K1 + I}(x) (raw);  z = s3*(y3 - mu3) + beta3 + u + alpha*b1;
 // out = act(post_bn(z)) = act(a3*y3 + au*u + c0).  See include/sgb200.h for the coefficient / moment layout.
+// the five moments of (y3, u) as a pass of the same skeleton: first half of the fused forward launch (sgb_qarep_fwd_fused)
+struct QarepMomOp {
+  static constexpr int NCOEF = 0, NACC = 5;
+  SgbQarepDesc d;
+  const bf16 *y3, *u;
+  double* out;
+  int out_stride;
+  __device__ void prologue(float*) const {}
+  static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + d.off3 + c0 : u + d.offu + c0; }
+  __device__ int pitch(int j) const { return j == 0 ? d.pitch3 : d.pitchu; }
+  __device__ void finish(int64_t, int, const uint4 (&raw)[2], const float (&)[1][8], float (&acc)[5][8]) const {
+    const V8 a = unpack8(raw[0]), b = unpack8(raw[1]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += a.v[e];
+      acc[1][e] = fmaf(a.v[e], a.v[e], acc[1][e]);
+      acc[2][e] += b.v[e];
+      acc[3][e] = fmaf(b.v[e], b.v[e], acc[3][e]);
+      acc[4][e] = fmaf(a.v[e], b.v[e], acc[4][e]);
+    }
+  }
+};
+
 struct QarepFwdOp {
   static constexpr int NCOEF = 3, NACC = 0;
   SgbQarepDesc d;
@@ -428,7 +452,8 @@ struct QarepFwdOp {
     const int C = d.C;
     const double M = (double)d.M;
     for (int c = threadIdx.x; c < C; c += TPB) {
-      const double S3 = mom[c], S33 = mom[C + c], Su = mom[2 * C + c], Suu = mom[3 * C + c], S3u = mom[4 * C + c];
+      // L2 reads: in the fused launch other CTAs produced the sums just before the grid barrier
+      const double S3 = __ldcg(mom + c), S33 = __ldcg(mom + C + c), Su = __ldcg(mom + 2 * C + c), Suu = __ldcg(mom + 3 * C + c), S3u = __ldcg(mom + 4 * C + c);
       const double mu3 = S3 / M;
       double var3 = S33 / M - mu3 * mu3;
       if (var3 < 0) var3 = 0;
@@ -699,6 +724,17 @@ extern "C" int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sg
   SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
   QarepFwdOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd");
+}
+
+extern "C" int sgb_qarep_fwd_fused(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments, const float* gamma3,
+                                   const float* beta3, const float* bias1_alpha, const float* gamma_p, const float* beta_p, float* rm3, float* rv3,
+                                   float* rm_p, float* rv_p, sgb_bf16* out, float* coef, void* stream) {
+  if (int rc = check_qarep(d)) return rc;
+  SGB_REQUIRE(y3 && u && moments && gamma3 && beta3 && out && coef, "null pointer");
+  SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
+  QarepMomOp mo{*d, (const bf16*)y3, (const bf16*)u, moments, d->C};
+  QarepFwdOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
+  return launch_chan_fused(mo, op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd_fused");
 }
 
 extern "C" int sgb_qarep_bwd_reduce(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* out,

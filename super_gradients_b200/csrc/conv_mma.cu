@@ -555,6 +555,25 @@ extern "C" int sgb_convt2x2_fprop(const SgbConvDesc* d, const sgb_bf16* x_small,
   if (int rc = check_desc(d)) return rc;
   SGB_REQUIRE(d->R == 2 && d->S == 2 && d->stride == 2 && d->pad == 0, "convt2x2 needs R=S=2, stride 2, pad 0");
   SGB_REQUIRE(d->K % 8 == 0 && d->y_pitch % 8 == 0 && d->y_off % 8 == 0, "small-side channels must be multiples of 8");
+  if (d->K % 16 == 0 && d->C % 16 == 0 && sm100::enabled()) {
+    // tcgen05 path: the transposed convolution is four 1x1 GEMMs, one per output parity (dh, dw), each writing the output pixels
+    // (2h + dh, 2w + dw) through the strided-row epilogue the stride-2 input gradients use.  w_up rows are ordered (dh, dw, co).
+    bool all_ok = true;
+    for (int cls = 0; cls < 4 && all_ok; ++cls) {
+      sm100::Problem q{};
+      q.a = x_small + d->y_off; q.N = d->N; q.H = d->P; q.W = d->Q; q.C = d->K; q.a_pitch = d->y_pitch;
+      q.b = w_up + (size_t)cls * d->C * d->K; q.b_rows = d->C; q.b_cols = d->K; q.b_cols_per_tap = d->K;
+      q.R = 1; q.S = 1; q.stride = 1; q.pad = 0; q.P = d->P; q.Q = d->Q; q.flip = 0;
+      q.y = y_up; q.y_pitch = d->x_pitch; q.y_off = d->x_off;
+      q.shift = bias;
+      q.stats_repl = 1;
+      q.out_mode = 1; q.o_mul = 2; q.oh_add = cls >> 1; q.ow_add = cls & 1; q.outH = d->H; q.outW = d->W;
+      q.ntaps = 1; q.tap_dh[0] = 0; q.tap_dw[0] = 0; q.tap_b[0] = 0;
+      if (!sm100::supported(q)) { all_ok = false; break; }  // identical for the four classes: fails before any launch
+      if (int rc = sm100::launch(q, (cudaStream_t)stream)) return rc;
+    }
+    if (all_ok) return SGB_OK;
+  }
   IGemmParams p{};
   p.A = reinterpret_cast<const bf16*>(x_small);
   p.B = reinterpret_cast<const bf16*>(w_up);

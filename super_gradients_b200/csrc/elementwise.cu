@@ -369,10 +369,14 @@ __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C,
       int64_t kstep[NIN];
 #pragma unroll
       for (int j = 0; j < NIN; ++j) {
+        const bf16* b = f.base(j, cv * 8);
         kstep[j] = (int64_t)lanes * f.pitch(j);
-        ptr[j] = f.base(j, cv * 8) + first * f.pitch(j);
+        ptr[j] = b ? b + first * f.pitch(j) : nullptr;
       }
-      sgb_ring::walk<NIN, RED_U, D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t, const uint4(&raw)[NIN]) { f.eval(raw, acc); });
+      sgb_ring::walk<NIN, RED_U, D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t q, const uint4(&raw)[NIN]) {
+        if constexpr (F::WRITES) f.evalw(first + q * lanes, cv * 8, raw, acc);  // a pass that also writes an output tensor
+        else f.eval(raw, acc);
+      });
     }
     // every thread parks its NACC*8 partial sums at [pl][cvi][a][e]; output j = (cvi, a, e) sums over pl (no atomics)
     __syncthreads();
@@ -418,6 +422,7 @@ int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaS
 
 struct StatsF {
   static constexpr int NACC = 2, NIN = 1;
+  static constexpr bool WRITES = false;
   const bf16* x;
   int pitch_, off;
   __device__ const bf16* base(int, int c0) const { return x + off + c0; }
@@ -434,6 +439,7 @@ struct StatsF {
 
 struct QarepMomF {
   static constexpr int NACC = 5, NIN = 2;
+  static constexpr bool WRITES = false;
   const bf16 *y3, *u;
   int p3, o3, pu, ou;
   __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + o3 + c0 : u + ou + c0; }
@@ -631,6 +637,7 @@ __global__ void scale_add_kernel(const bf16* __restrict__ x1, int p1, int o1, co
 
 struct DotF {
   static constexpr int NACC = 1, NIN = 2;
+  static constexpr bool WRITES = false;
   const bf16 *a, *b;
   int pa, oa, pb, ob;
   __device__ const bf16* base(int j, int c0) const { return j == 0 ? a + oa + c0 : b + ob + c0; }
@@ -640,6 +647,38 @@ struct DotF {
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] += u.v[e] * v.v[e];
   }
+};
+
+// y = a * x1 (+ x2) and out[c] += sum over pixels of x1 * xd in ONE pass: the backward of the learnable-alpha shortcut
+// (yolo_stages.py:61-63) needs alpha * dy for the shortcut's input and sum(dy * x) for alpha; separately that was a scale pass and
+// a dot pass, each reading dy.
+struct ScaleAddDotF {
+  static constexpr int NACC = 1, NIN = 3;
+  static constexpr bool WRITES = true;
+  const bf16 *x1, *xd, *x2;  // x2 may be null
+  int p1, o1, pd, od, p2, o2;
+  const float* a_dev;
+  bf16* y;
+  int py, oy;
+  __device__ const bf16* base(int j, int c0) const { return j == 0 ? x1 + o1 + c0 : (j == 1 ? xd + od + c0 : (x2 ? x2 + o2 + c0 : nullptr)); }
+  __device__ int pitch(int j) const { return j == 0 ? p1 : (j == 1 ? pd : p2); }
+  __device__ void evalw(int64_t pix, int c0, const uint4 (&raw)[3], float (&acc)[1][8]) const {
+    const float a = __ldg(a_dev);
+    V8 u = unpack8(raw[0]);
+    const V8 v = unpack8(raw[1]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[0][e] = fmaf(u.v[e], v.v[e], acc[0][e]);
+    if (x2) {
+      const V8 w = unpack8(raw[2]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u.v[e] = a * u.v[e] + w.v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u.v[e] = a * u.v[e];
+    }
+    st8(y + pix * py + oy + c0, u);
+  }
+  __device__ void eval(const uint4 (&)[3], float (&)[1][8]) const {}
 };
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* y, int64_t n) {
@@ -860,6 +899,14 @@ extern "C" int sgb_channel_dot(const sgb_bf16* a, int pa, int oa, const sgb_bf16
   SGB_REQUIRE(a && b && out && C % 8 == 0 && pa % 8 == 0 && oa % 8 == 0 && pb % 8 == 0 && ob % 8 == 0, "bad args");
   DotF f{(const bf16*)a, (const bf16*)b, pa, oa, pb, ob};
   return launch_chan_reduce(f, M, C, out, C, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_scale_add_dot(const sgb_bf16* x1, int p1, int o1, const float* a_dev, const sgb_bf16* x2, int p2, int o2, const sgb_bf16* xd,
+                                 int pd, int od, sgb_bf16* y, int py, int oy, int64_t M, int C, double* out_dot, void* stream) {
+  SGB_REQUIRE(x1 && xd && y && a_dev && out_dot && M > 0 && C > 0 && C % 8 == 0, "bad args");
+  SGB_REQUIRE(p1 % 8 == 0 && o1 % 8 == 0 && pd % 8 == 0 && od % 8 == 0 && py % 8 == 0 && oy % 8 == 0 && (!x2 || (p2 % 8 == 0 && o2 % 8 == 0)), "pitch/offset multiples of 8");
+  ScaleAddDotF f{(const bf16*)x1, (const bf16*)xd, (const bf16*)x2, p1, o1, pd, od, p2, o2, a_dev, (bf16*)y, py, oy};
+  return launch_chan_reduce(f, M, C, out_dot, C, (cudaStream_t)stream);
 }
 
 extern "C" int sgb_f32_to_bf16(const float* x, sgb_bf16* y, int64_t n, void* stream) {

@@ -172,6 +172,7 @@ def flush_wgrads(ctx: StepContext, device) -> int:
 # both gradients in one launch (for K <= 64 inside the M = 128 padding the 3x3 weight gradient already pays for).  Only verified
 # kernels are involved; tools/next_round_gpu_plan.sh benches it.
 QAREP_FOLD = [__import__("os").environ.get("SGB_QAREP_FOLD") == "1"]
+QAREP_FOLD_MAXPIX = [int(__import__("os").environ.get("SGB_QAREP_FOLD_MAXPIX", "0"))]  # > 0: fold only maps of at most this many pixels (N*H*W)
 _FOLD_CHANNELS = (32, 48, 64, 96, 128, 192)  # channel counts the halo-tile kernels are instantiated for
 
 
@@ -203,6 +204,73 @@ class FoldedWeightCache:
         return self.inner.get(self.stage, c_pad=c_pad, extra_key=key)
 
 
+# ------------------------------------------------------------------------------------------------ shared input gradients
+# An activation consumed by several fused blocks (the two 1 x 1 convolutions of a CSP layer, a bottleneck's first block and its
+# shortcut, a backbone feature feeding the next stage and the neck, a head stem feeding the cls / reg branches) receives one
+# gradient per consumer, which autograd sums with an ATen add per extra consumer: 39 full-tensor read-read-write passes per
+# YOLO-NAS-S step (0.78 ms at batch 32).  Every input-gradient kernel here can instead ACCUMULATE into an existing tensor in its
+# epilogue (sgb_conv_dgrad's `accumulate`, sgb_scale_add's in-place form), so the consumers of one tensor object share a token:
+# the first to run backward produces the gradient buffer, the others add into it and return None to autograd, the last returns
+# the buffer.  Autograd's sum is unchanged whatever else consumes the tensor (non-participating consumers are added by autograd
+# as before).  It relies on every registered consumer running in the same backward pass; a pass that reaches only some of them
+# (part of the outputs unused) is detected by a callback at the end of the pass and raises instead of returning wrong gradients
+# (SGB_SHARE_GRADS=0 turns the mechanism off).
+SHARE_GRADS = [__import__("os").environ.get("SGB_SHARE_GRADS", "1") != "0"]
+
+
+class _GradShare:
+    __slots__ = ("n", "arrived", "buf", "queued")
+
+    def __init__(self):
+        self.n = 0          # consumers registered by the forward pass
+        self.arrived = 0    # consumers whose backward ran in the current backward pass
+        self.buf = None     # the gradient accumulated so far
+        self.queued = False
+
+
+def _share_pickup(x):
+    """Called by a block's wrapper with the tensor object the caller passed in; returns the tensor's token (or None)."""
+    if not SHARE_GRADS[0] or not torch.is_tensor(x) or not torch.is_grad_enabled() or not x.requires_grad or x.grad_fn is None:
+        return None
+    tok = x.__dict__.get("_sgb_share") if hasattr(x, "__dict__") else None
+    if tok is None:
+        tok = _GradShare()
+        x._sgb_share = tok
+    tok.n += 1
+    return tok
+
+
+def _share_check(tok):
+    n, a = tok.n, tok.arrived
+    tok.arrived, tok.buf, tok.queued = 0, None, False
+    if a != n:
+        raise RuntimeError(
+            f"shared input gradient: {a} of the {n} fused blocks consuming one activation ran in this backward pass; the gradient of that "
+            "activation would be incomplete.  Backward passes that reach only part of a model's outputs need SGB_SHARE_GRADS=0."
+        )
+
+
+def _share_dx(tok, fresh, accumulate):
+    """The input gradient a backward returns to autograd.  fresh() -> new tensor; accumulate(buf) adds this consumer's gradient
+    into buf in place."""
+    if tok is None or tok.n <= 1:
+        return fresh()
+    if not tok.queued:
+        tok.queued = True
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _share_check(tok))
+    tok.arrived += 1
+    if tok.buf is None:
+        buf = fresh()
+    else:
+        buf = tok.buf
+        accumulate(buf)
+    if tok.arrived == tok.n:
+        tok.buf = None
+        return buf
+    tok.buf = buf
+    return None
+
+
 def _mg(p):
     """Flat-buffer gradient slot of a parameter (training/flat_state.py) or None under plain autograd."""
     return getattr(p, "main_grad", None) if p is not None else None
@@ -229,6 +297,28 @@ def _side_wgrad(ctx, x, dy, r, s, stride, pad):
     ctx.keep.append((x, dy, dw))
     ctx.side_used = True
     return dw
+
+
+def _wgrad_raw(x, dy, r, s, stride, pad):
+    """fp32 KRSC weight gradient; on the step's side stream when there is one (readable after flush_wgrads() joined)."""
+    ctx = _CTX[0]
+    if ctx is not None and ctx.side_stream is not None:
+        return _side_wgrad(ctx, x, dy, r, s, stride, pad)
+    return K.conv_wgrad(x, dy, r, s, stride, pad)
+
+
+def _wgrad_finish(dw, cin, slot):
+    """fp32 KRSC gradient (rows of dw) -> the parameter's flat gradient slot (deferred to the batched pass inside a step) or OIHW."""
+    ctx = _CTX[0]
+    if slot is not None and ctx is not None:
+        ctx.pending.append((dw, cin, slot))  # dw (step arena or a plain tensor) stays referenced until flush_wgrads()
+        return None
+    if ctx is not None and ctx.side_used:  # no slot: the caller reads the result now
+        torch.cuda.current_stream().wait_stream(ctx.side_stream)
+    if slot is not None:
+        K.wgrad_to_oihw(dw, cin, out=slot, accumulate=True)
+        return None
+    return K.wgrad_to_oihw(dw, cin)
 
 
 def _wgrad(x, dy, r, s, stride, pad, cin, slot):
@@ -308,7 +398,11 @@ class _ConvBnAct(torch.autograd.Function):
         dy, dres, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, out, gamma, mean, rstd, cfg.eps, cfg.act, want_residual_grad=ctx.has_res, dgamma=sg, dbeta=sb, beta=beta, **({"sample_scale": ss} if ss is not None else {}))
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad)
+            dx = _share_dx(
+                getattr(cfg, "share", None),
+                lambda: K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad),
+                lambda buf: K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad, out=buf, accumulate=True),
+            )
         dw = _wgrad(x, dy, r, s, cfg.stride, cfg.pad, cin, sw)
         return dx, dw, (None if sg is not None else dgamma), (None if sb is not None else dbeta), dres, None
 
@@ -319,7 +413,8 @@ def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracke
     training/utils/regularization_utils.py:4-15 (drop_path; `sample_scale` = bernoulli(keep) / keep per image, training only)."""
     K.require_cuda(x, "x")
     if training:
-        cfg = SimpleNamespace(stride=stride, pad=pad, eps=eps, momentum=momentum, act=act, cache=cache, running_mean=running_mean, running_var=running_var, num_batches_tracked=num_batches_tracked, sample_scale=sample_scale)
+        cfg = SimpleNamespace(stride=stride, pad=pad, eps=eps, momentum=momentum, act=act, cache=cache, running_mean=running_mean, running_var=running_var, num_batches_tracked=num_batches_tracked, sample_scale=sample_scale,
+                              share=_share_pickup(x))  # fmt: skip
         return _ConvBnAct.apply(x, w, gamma, beta, residual, cfg)
     # inference: BN folded into the GEMM epilogue (one kernel)
     with torch.no_grad():
@@ -332,6 +427,44 @@ def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracke
         return K.conv_fprop(x, krsc, kout, r, s, stride, pad, scale=scale, shift=shift, residual=res, act=act)
 
 
+# Output channels that are not a multiple of 16 (the 68-channel DFL regression convolution, yolo_nas/dfl_heads.py:66) do not fit the
+# tcgen05 kernels' N granularity and used to fall back to the mma.sync kernels for forward, input gradient and weight gradient.
+# They now run as a convolution with K rounded up to 16: zero filter rows / bias entries for the padding channels (staged fp32 copy,
+# refreshed when the parameter changes), the output allocated with that pitch and handed on as its first K channels, and in the
+# backward the incoming gradient re-described with the padded channel count when its producer marked the padding as zero
+# (`_sgb_zero_pad`, set by the head-decode backward), else copied into a zeroed buffer.
+KPAD = [__import__("os").environ.get("SGB_KPAD", "1") != "0"]
+
+
+class PaddedOutCache:
+    def __init__(self):
+        self.key = None
+        self.stage = None
+        self.bias = None
+        self.inner = WeightCache(batched=False)
+
+    def get(self, w4, b, kp, c_pad):
+        key = (WeightCache._key(w4, None, False, None, c_pad), None if b is None else (b.data_ptr(), b._version), kp)
+        if key != self.key:
+            kout = w4.shape[0]
+            with torch.no_grad():
+                if self.stage is None or tuple(self.stage.shape) != (kp,) + tuple(w4.shape[1:]) or self.stage.device != w4.device:
+                    self.stage = torch.zeros((kp,) + tuple(w4.shape[1:]), dtype=torch.float32, device=w4.device)
+                    self.bias = torch.zeros((kp,), dtype=torch.float32, device=w4.device)
+                self.stage[:kout].copy_(w4.detach())
+                if b is not None:
+                    self.bias[:kout].copy_(b.detach())
+            self.key = key
+        krsc, crsk = self.inner.get(self.stage, c_pad=c_pad, extra_key=key)
+        return krsc, crsk, (self.bias if b is not None else None)
+
+
+def _padded_view(t, kp):
+    """The kp-channel tensor behind a channel-slice view whose buffer has pitch kp."""
+    n, _c, h, w = t.shape
+    return torch.as_strided(t, (n, kp, h, w), t.stride(), t.storage_offset())
+
+
 class _ConvBias(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, cfg):
@@ -341,9 +474,23 @@ class _ConvBias(torch.autograd.Function):
         # AccumulateGrad node (whose stream bookkeeping invalidates a CUDA-graph capture of the step)
         ctx.w_orig_shape = tuple(w.shape)
         w4 = w if w.dim() == 4 else w.detach().view(w.shape[0], w.shape[1], 1, 1)
-        krsc, crsk = cfg.cache.get(w4, c_pad=x.shape[1])
         kout, _, r, s = w4.shape
-        y = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, shift=b, act=cfg.act)
+        ctx.kp = 0
+        if KPAD[0] and w.dim() == 4 and kout % 16 != 0 and kout >= 32 and x.shape[1] % 16 == 0:
+            kp = ((kout + 15) // 16) * 16
+            pc = cfg.cache.__dict__.get("_kpad")
+            if pc is None:
+                pc = cfg.cache._kpad = PaddedOutCache()
+            krsc, crsk, bpad = pc.get(w4, b, kp, x.shape[1])
+            n, _, h, wd = x.shape
+            P, Q = (h + 2 * cfg.pad - r) // cfg.stride + 1, (wd + 2 * cfg.pad - s) // cfg.stride + 1
+            ybuf = K.empty_nhwc(n, kp, P, Q, x.device)
+            K.conv_fprop(x, krsc, kp, r, s, cfg.stride, cfg.pad, shift=bpad, act=cfg.act, out=ybuf)
+            y = ybuf[:, :kout].detach()  # a plain alias: autograd must not treat the output as a view of a tensor made inside forward
+            ctx.kp = kp
+        else:
+            krsc, crsk = cfg.cache.get(w4, c_pad=x.shape[1])
+            y = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, shift=b, act=cfg.act)
         ctx.save_for_backward(x)
         ctx.cfg, ctx.crsk, ctx.wshape, ctx.has_bias = cfg, crsk, tuple(w4.shape), b is not None
         ctx.slots = (_mg(w), _mg(b))
@@ -354,9 +501,29 @@ class _ConvBias(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         cfg = ctx.cfg
         kout, cin, r, s = ctx.wshape
+        zero_pad = getattr(dy, "_sgb_zero_pad", 0)
         dy = K.as_nhwc(dy)
-        dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad) if ctx.needs_input_grad[0] else None
-        dw = _wgrad(x, dy, r, s, cfg.stride, cfg.pad, cin, ctx.slots[0])
+        dyk = dy  # the gradient with the channel count the kernels see
+        if ctx.kp:
+            kp = ctx.kp
+            if zero_pad == kp and K.nhwc_pitch(dy) == kp:
+                dyk = _padded_view(dy, kp)
+            else:
+                n, _, h, wd = dy.shape
+                dyk = _padded_view(K.empty_nhwc(n, kout, h, wd, dy.device, c_alloc=kp), kp)  # zero-initialised
+                K.axpby(dy, 1.0, out=dyk[:, :kout])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _share_dx(
+                getattr(cfg, "share", None),
+                lambda: K.conv_dgrad(dyk, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad),
+                lambda buf: K.conv_dgrad(dyk, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad, out=buf, accumulate=True),
+            )
+        if ctx.kp:
+            dwf = _wgrad_raw(x, dyk, r, s, cfg.stride, cfg.pad)  # fp32 [kp, r, s, c]; rows [0, kout) are the filter's gradient
+            dw = _wgrad_finish(dwf[:kout], cin, ctx.slots[0])
+        else:
+            dw = _wgrad(x, dyk, r, s, cfg.stride, cfg.pad, cin, ctx.slots[0])
         if dw is not None:
             dw = dw.reshape(ctx.w_orig_shape)
         db = _deliver(ctx.slots[1], _chan_sum(dy)) if ctx.has_bias else None
@@ -366,7 +533,7 @@ class _ConvBias(torch.autograd.Function):
 def conv_bias(x, w, b, *, stride, pad, cache: WeightCache, act=None):
     """Plain Conv2d (+ bias), e.g. the cls/reg prediction convs (yolo_nas/dfl_heads.py:65-66) and nn.Linear as 1x1."""
     K.require_cuda(x, "x")
-    cfg = SimpleNamespace(stride=stride, pad=pad, cache=cache, act=act)
+    cfg = SimpleNamespace(stride=stride, pad=pad, cache=cache, act=act, share=_share_pickup(x))
     return _ConvBias.apply(x, w, b, cfg)
 
 
@@ -383,6 +550,8 @@ class _QARepVGG(torch.autograd.Function):
         x = K.as_nhwc(x)
         kout = w3.shape[0]
         fold = QAREP_FOLD[0] and getattr(cfg, "cache_fold", None) is not None and qarep_fold_supported(w3.shape[1], x.shape[1], kout, cfg.stride)
+        if fold and QAREP_FOLD_MAXPIX[0] > 0 and x.shape[0] * x.shape[2] * x.shape[3] > QAREP_FOLD_MAXPIX[0]:
+            fold = False
         if fold:
             kf, cf = cfg.cache_fold.get(w3, w1, alpha, cfg.residual, x.shape[1])
             ycat = K.conv_fprop(x, kf, 2 * kout, 3, 3, 1, 1)
@@ -402,6 +571,7 @@ class _QARepVGG(torch.autograd.Function):
                     nbt += 1
         ctx.save_for_backward(x, y3, u, out, coef, g3, gp if gp is not None else g3, w1, bias1 if bias1 is not None else g3, alpha if alpha is not None else g3)
         ctx.cfg, ctx.c3, ctx.c1, ctx.fold = cfg, c3, c1, fold
+        ctx.share = getattr(cfg, "share_tok", None)
         ctx.flags = (bias1 is not None, alpha is not None, gp is not None, w3.shape[1])
         ctx.slots = (_mg(w3), _mg(g3), _mg(b3), _mg(w1), _mg(bias1), _mg(alpha), _mg(gp), _mg(bp))
         return out
@@ -423,9 +593,10 @@ class _QARepVGG(torch.autograd.Function):
         )  # fmt: skip
         dx = None
         dw1f = None
+        tok = ctx.share
         if dcat is not None:
             if ctx.needs_input_grad[0]:
-                dx = K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1)
+                dx = _share_dx(tok, lambda: K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1), lambda buf: K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1, out=buf, accumulate=True))
             dwf = K.conv_wgrad(x, dcat, 3, 3, 1, 1)  # fp32 [2K, 3, 3, C]: rows [0, K) = dW3, rows [K, 2K) centre tap = d(alpha * K1 + I)
             if sw3 is not None and _CTX[0] is not None:
                 _CTX[0].pending.append((dwf[:kout], cin, sw3))
@@ -438,8 +609,16 @@ class _QARepVGG(torch.autograd.Function):
             dw1f = dwf[kout:, 1, 1, :cin].reshape(kout, cin, 1, 1).contiguous()
         else:
             if ctx.needs_input_grad[0]:
-                dx = K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1)
-                K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=dx, accumulate=True)
+
+                def _fresh():
+                    d = K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1)
+                    return K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=d, accumulate=True)
+
+                def _acc(buf):
+                    K.conv_dgrad(dy3, ctx.c3, x.shape, 3, 3, cfg.stride, 1, out=buf, accumulate=True)
+                    K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=buf, accumulate=True)
+
+                dx = _share_dx(tok, _fresh, _acc)
             dw3 = _wgrad(x, dy3, 3, 3, cfg.stride, 1, cin, sw3)
         dalpha = None
         if has_alpha and dcat is not None and sw1 is not None and salpha is not None and (sbias is not None or not has_bias):
@@ -476,6 +655,7 @@ class _QARepVGG(torch.autograd.Function):
 
 def qarepvgg_block(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
     K.require_cuda(x, "x")
+    cfg.share_tok = _share_pickup(x)  # cfg is built per call by the module
     return _QARepVGG.apply(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg)
 
 
@@ -672,23 +852,27 @@ def concat(xs):
 
 class _Add(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x1, x2, a, b):
+    def forward(ctx, x1, x2, a, b, tok1, tok2):
         x1, x2 = K.as_nhwc(x1), K.as_nhwc(x2)
         ctx.ab = (a, b)
+        ctx.toks = (tok1, tok2)
         return K.axpby(x1, a, x2, b)
 
     @staticmethod
     def backward(ctx, dy):
         a, b = ctx.ab
         dy = K.as_nhwc(dy)
-        d1 = dy if a == 1.0 else K.axpby(dy, a)
-        d2 = dy if b == 1.0 else K.axpby(dy, b)
-        return d1, d2, None, None
+        # a scaled branch writes a new tensor anyway, so it can take part in the shared-gradient accumulation; an unscaled branch
+        # hands dy itself to autograd (no kernel) and stays out of it
+        d1 = dy if a == 1.0 else _share_dx(ctx.toks[0], lambda: K.axpby(dy, a), lambda buf: K.axpby(dy, a, buf, 1.0, out=buf))
+        d2 = dy if b == 1.0 else _share_dx(ctx.toks[1], lambda: K.axpby(dy, b), lambda buf: K.axpby(dy, b, buf, 1.0, out=buf))
+        return d1, d2, None, None, None, None
 
 
 def add(x1, x2, a=1.0, b=1.0):
     """a*x1 + b*x2 (residual connections)."""
-    return _Add.apply(x1, x2, float(a), float(b))
+    a, b = float(a), float(b)
+    return _Add.apply(x1, x2, a, b, _share_pickup(x1) if a != 1.0 else None, _share_pickup(x2) if b != 1.0 else None)
 
 
 class _GlobalAvgPool(torch.autograd.Function):
@@ -708,6 +892,16 @@ def global_avg_pool(x):
 
 
 # ------------------------------------------------------------------------------------------------------------ head decode
+def _grad_map(shape, pitch, device):
+    """Gradient buffer of a head map laid out like the forward map (same channel pitch); channels beyond the logical count are
+    zero and the tensor says so (`_sgb_zero_pad`), so a K-padded prediction convolution can read it without a copy."""
+    n, c, h, w = shape
+    g = K.empty_nhwc(n, c, h, w, device, c_alloc=pitch if pitch > c else None)
+    if pitch > c:
+        g._sgb_zero_pad = pitch
+    return g
+
+
 class _DflDecode(torch.autograd.Function):
     """NDFLHeads decode (yolo_nas/dfl_heads.py:199-245): per-level bf16 NHWC reg/cls maps -> fp32 [B, L, *] tensors."""
 
@@ -730,6 +924,7 @@ class _DflDecode(torch.autograd.Function):
             K.dfl_decode(r, c, Ltot, base, cfg.num_classes, cfg.reg_max, s, cfg.cell_offset, pb, ps, cl, rd)
             base += hw
         ctx.geom = (B, hws, Ltot, [tuple(r.shape) for r in regs], [tuple(c.shape) for c in clss])
+        ctx.pitches = ([K.nhwc_pitch(r) for r in regs], [K.nhwc_pitch(c) for c in clss])
         ctx.mark_non_differentiable(pb, ps)
         return pb, ps, cl, rd
 
@@ -738,13 +933,13 @@ class _DflDecode(torch.autograd.Function):
         B, hws, Ltot, rshapes, cshapes = ctx.geom
         outs = [None]
         base = 0
-        for hw, rs, cs in zip(hws, rshapes, cshapes):
+        for hw, rs, cs, rp, cp in zip(hws, rshapes, cshapes, ctx.pitches[0], ctx.pitches[1]):
             dr = dc = None
             if grd is not None:
-                dr = K.empty_nhwc(rs[0], rs[1], rs[2], rs[3], grd.device)
+                dr = _grad_map(rs, rp, grd.device)
                 K.head_grad_scatter(grd.contiguous(), B, hw, Ltot, base, dr)
             if gcl is not None:
-                dc = K.empty_nhwc(cs[0], cs[1], cs[2], cs[3], gcl.device)
+                dc = _grad_map(cs, cp, gcl.device)
                 K.head_grad_scatter(gcl.contiguous(), B, hw, Ltot, base, dc)
             outs += [dr, dc]
             base += hw

@@ -89,6 +89,7 @@ def zeros(shape, dtype, device):
 
 # BatchNorm / QARepVGG backward as one cooperative launch per layer instead of a reduction launch + an apply launch (SGB_FUSED_BWD=0: two passes)
 FUSED_BWD = [os.environ.get("SGB_FUSED_BWD", "1") != "0"]
+FUSED_FWD = [os.environ.get("SGB_FUSED_FWD", "1") != "0"]  # QARepVGG forward: moments + apply as one cooperative launch
 
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU}
 
@@ -155,8 +156,8 @@ def empty_nhwc(n, c, h, w, device, c_alloc=None) -> torch.Tensor:
     ca = c_alloc or ((c + 7) // 8) * 8
     if ca == c:
         return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=torch.channels_last)
-    buf = torch.zeros((n, ca, h, w), dtype=torch.bfloat16, device=device).contiguous(memory_format=torch.channels_last)
-    return buf[:, :c]
+    buf = zeros((n, h, w, ca), torch.bfloat16, device).permute(0, 3, 1, 2)  # NHWC storage; inside a train step: the step arena (no fill launch)
+    return buf[:, :c].detach()  # a plain alias of the storage (not an autograd view: outputs of custom Functions are written in place)
 
 
 def conv_desc(x: torch.Tensor, K: int, R: int, S: int, stride: int, pad: int, y: Optional[torch.Tensor] = None, P=None, Q=None) -> L.ConvDesc:
@@ -518,8 +519,11 @@ def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp,
     out = empty_nhwc(n, c, h, w, y3.device)
     d = qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn)
     mom = zeros((5, c), torch.float64, y3.device)
-    _timed("sgb_qarep_moments", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _stream())
     coef = torch.empty((9, c), dtype=torch.float32, device=y3.device)
+    if FUSED_FWD[0]:  # moments, grid barrier, apply in one cooperative launch
+        _timed("sgb_qarep_fwd_fused", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _ptr(gamma3), _ptr(beta3), _ptr(bias1a), _ptr(gamma_p), _ptr(beta_p), _ptr(rm3), _ptr(rv3), _ptr(rmp), _ptr(rvp), _ptr(out), _ptr(coef), _stream())
+        return out, coef
+    _timed("sgb_qarep_moments", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _stream())
     _timed("sgb_qarep_fwd", ctypes.byref(d), _ptr(y3), _ptr(u), _ptr(mom), _ptr(gamma3), _ptr(beta3), _ptr(bias1a), _ptr(gamma_p), _ptr(beta_p), _ptr(rm3), _ptr(rv3), _ptr(rmp), _ptr(rvp), _ptr(out), _ptr(coef), _stream())
     return out, coef
 
@@ -590,6 +594,17 @@ def scale_add(x1, a_dev, x2=None, out=None):
         out = empty_nhwc(n, c, h, w, x1.device)
     _timed("sgb_scale_add", _ptr(x1), nhwc_pitch(x1), 0, _ptr(a_dev), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _stream())
     return out
+
+
+def scale_add_dot(x1, a_dev, xd, x2=None, out=None):
+    """((*a_dev) * x1 + x2, fp64 [C] = sum over pixels of x1 * xd) in one pass over x1; `out` may be x2 (in place)."""
+    n, c, h, w = x1.shape
+    if out is None:
+        out = empty_nhwc(n, c, h, w, x1.device)
+    dot = zeros((c,), torch.float64, x1.device)
+    _timed("sgb_scale_add_dot", _ptr(x1), nhwc_pitch(x1), 0, _ptr(a_dev), _ptr(x2), nhwc_pitch(x2) if x2 is not None else 0, 0, _ptr(xd), nhwc_pitch(xd), 0,
+           _ptr(out), nhwc_pitch(out), 0, n * h * w, c, _ptr(dot), _stream())  # fmt: skip
+    return out, dot
 
 
 def channel_dot(a, b) -> torch.Tensor:

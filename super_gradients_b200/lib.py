@@ -168,6 +168,7 @@ _SIGNATURES = {
     "sgb_channel_stats": (c_int, [P, _L, _I, _I, _I, P, P]),
     "sgb_qarep_moments": (c_int, [POINTER(QarepDesc), P, P, P, P]),
     "sgb_qarep_fwd": (c_int, [POINTER(QarepDesc)] + [P] * 15),
+    "sgb_qarep_fwd_fused": (c_int, [POINTER(QarepDesc)] + [P] * 15),
     "sgb_qarep_bwd_reduce": (c_int, [POINTER(QarepDesc), P, P, P, P, P, P, P]),
     "sgb_qarep_bwd_apply": (c_int, [POINTER(QarepDesc)] + [P] * 16),
     "sgb_qarep_bwd_fused": (c_int, [POINTER(QarepDesc)] + [P] * 15),
@@ -176,6 +177,7 @@ _SIGNATURES = {
     "sgb_axpby": (c_int, [P, _I, _I, _F, P, _I, _I, _F, P, _I, _I, _L, _I, P]),
     "sgb_scale_add": (c_int, [P, _I, _I, P, P, _I, _I, P, _I, _I, _L, _I, P]),
     "sgb_channel_dot": (c_int, [P, _I, _I, P, _I, _I, _L, _I, P, P]),
+    "sgb_scale_add_dot": (c_int, [P, _I, _I, P, P, _I, _I, P, _I, _I, P, _I, _I, _L, _I, P, P]),
     "sgb_f32_to_bf16": (c_int, [P, P, _L, P]),
     "sgb_avgpool_fwd": (c_int, [P, _I, _I, _I, P, P]),
     "sgb_avgpool_bwd": (c_int, [P, _I, _I, _I, P, P]),

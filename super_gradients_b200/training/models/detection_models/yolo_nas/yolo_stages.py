@@ -36,7 +36,7 @@ class YoloNASBottleneck(nn.Module):
         if not self.add:
             return y
         if isinstance(self.alpha, torch.Tensor):
-            return _ScaledAdd.apply(x, y, self.alpha)
+            return _ScaledAdd.apply(x, y, self.alpha, SF._share_pickup(x))
         return SF.add(x, y, self.alpha, 1.0)
 
 
@@ -44,12 +44,13 @@ class _ScaledAdd(torch.autograd.Function):
     """alpha * x + y with a learnable scalar alpha read on the device (yolo_stages.py:61-63)."""
 
     @staticmethod
-    def forward(ctx, x, y, alpha):
+    def forward(ctx, x, y, alpha, share=None):
         from ..... import kernels as K
 
         x, y = K.as_nhwc(x), K.as_nhwc(y)
         ctx.save_for_backward(x, alpha)
         ctx.slot = getattr(alpha, "main_grad", None)
+        ctx.share = share  # x also feeds the block's first convolution: both input gradients land in one buffer (functional._share_dx)
         return K.scale_add(x, alpha, y)
 
     @staticmethod
@@ -58,11 +59,22 @@ class _ScaledAdd(torch.autograd.Function):
 
         x, alpha = ctx.saved_tensors
         dy = K.as_nhwc(dy)
-        dalpha = K.channel_dot(dy, x).sum().float().reshape(1)
+        dots = []  # alpha * dy (into the shared input-gradient buffer when there is one) and sum(dy * x) in one pass over dy
+
+        def fresh():
+            out, dot = K.scale_add_dot(dy, alpha, x)
+            dots.append(dot)
+            return out
+
+        def acc(buf):
+            dots.append(K.scale_add_dot(dy, alpha, x, buf, out=buf)[1])
+
+        dx = SF._share_dx(ctx.share, fresh, acc)
+        dalpha = dots[0].sum().float().reshape(1)
         if ctx.slot is not None:
             ctx.slot.add_(dalpha)
             dalpha = None
-        return K.scale_add(dy, alpha), dy, dalpha
+        return dx, dy, dalpha, None
 
 
 class SequentialWithIntermediates(nn.Sequential):

@@ -137,6 +137,12 @@ def scale_add(x1, a_dev, x2=None, out=None):
     return out
 
 
+def scale_add_dot(x1, a_dev, xd, x2=None, out=None):
+    dot = K.zeros((x1.shape[1],), torch.float64, x1.device)
+    dot += (x1.double() * xd.double()).sum((0, 2, 3))
+    return scale_add(x1, a_dev, x2, out), dot
+
+
 def dfl_decode(reg, cls, L_total, anchor_base, ncls, reg_max, stride, cell_offset, pred_bboxes, pred_scores, cls_logits=None, reg_distri=None):
     n, _, hf, wf = reg.shape
     hw, nb = hf * wf, reg_max + 1
@@ -566,7 +572,7 @@ def detection_matching(*args, **kwargs):
 
 
 _SUBSET = dict(conv_fprop=conv_fprop, weight_prepare=weight_prepare, convt2x2_fprop=convt2x2_fprop, nchw_f32_to_nhwc_bf16=nchw_f32_to_nhwc_bf16,
-               nhwc_bf16_to_nchw_f32=nhwc_bf16_to_nchw_f32, bn_act_infer=bn_act_infer, maxpool_fwd=maxpool_fwd, axpby=axpby, scale_add=scale_add,
+               nhwc_bf16_to_nchw_f32=nhwc_bf16_to_nchw_f32, bn_act_infer=bn_act_infer, maxpool_fwd=maxpool_fwd, axpby=axpby, scale_add=scale_add, scale_add_dot=scale_add_dot,
                dfl_decode=dfl_decode, pose_keypoint_decode=pose_keypoint_decode, batched_nms=batched_nms, preprocess_u8=preprocess_u8, detection_matching=detection_matching)  # fmt: skip
 
 

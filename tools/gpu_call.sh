@@ -45,6 +45,11 @@ case "${1}" in
     timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline8_launches.txt > gpurun_out/r2_timeline8.txt 2>gpurun_out/r2_timeline8.err; head -40 gpurun_out/r2_timeline8.txt; tail -3 gpurun_out/r2_timeline8.err ;;
   table)  # per-shape convolution table (eager, no overlap)
     timeout 300 python tools/conv_table.py > gpurun_out/r2_conv_table.txt 2>gpurun_out/r2_conv_table.err; cat gpurun_out/r2_conv_table.txt; tail -3 gpurun_out/r2_conv_table.err ;;
+  ninth)  # shared input gradients (A/B), QARepVGG fold by map size
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest9.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest9.log
+    for sg in 1 0; do printf "SGB_SHARE_GRADS=%d: " $sg; SGB_SHARE_GRADS=$sg timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench9_sg$sg.err | tee gpurun_out/r2_bench9_sg$sg.json | bench_line; tail -2 gpurun_out/r2_bench9_sg$sg.err; done
+    for mp in 12800 51200 204800 0; do printf "SGB_QAREP_FOLD=1 MAXPIX=%d: " $mp; SGB_QAREP_FOLD=1 SGB_QAREP_FOLD_MAXPIX=$mp timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench9_fold$mp.err | tee gpurun_out/r2_bench9_fold$mp.json | bench_line; tail -2 gpurun_out/r2_bench9_fold$mp.err; done
+    timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline9_launches.txt > gpurun_out/r2_timeline9.txt 2>gpurun_out/r2_timeline9.err; head -30 gpurun_out/r2_timeline9.txt; tail -3 gpurun_out/r2_timeline9.err ;;
   multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
     N=${2:-2}
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \
