@@ -333,10 +333,13 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int N, int C, in
 // Generic per-channel reduction skeleton.  F::NACC sums per channel over F::NIN input tensors; F::base(j, c0) / F::pitch(j) locate
 // input j; F::eval(raw[NIN], acc[NACC][8]) accumulates the contribution of 8 consecutive channels of one pixel.  The inputs stream
 // through the per-thread shared-memory ring of stream_ring.cuh (64 KB per CTA, two or three CTAs per SM).
-constexpr int RED_U = 2;
+template <class F>
+constexpr int red_unroll() {
+  return F::NIN >= 3 ? 1 : 2;
+}
 template <class F>
 constexpr int red_depth() {
-  return 16 / (RED_U * F::NIN);  // 64 KB of ring per 256-thread CTA: two or three CTAs per SM
+  return 16 / (red_unroll<F>() * F::NIN);  // <= 64 KB of ring per 256-thread CTA: two or three CTAs per SM
 }
 template <class F>
 __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C, double* out, int out_stride) {
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C,
   SGB_GRID_DEP_WAIT();
   constexpr int NACC = F::NACC, NIN = F::NIN, D = red_depth<F>();
   extern __shared__ __align__(16) unsigned char smem_red[];
-  float* sred = reinterpret_cast<float*>(smem_red + sgb_ring::bytes<NIN, RED_U, D, TPB>());  // [TPB][NACC*8]
+  float* sred = reinterpret_cast<float*>(smem_red + sgb_ring::bytes<NIN, red_unroll<F>(), D, TPB>());  // [TPB][NACC*8]
   const uint32_t my_ring = smem_u32(smem_red) + (uint32_t)threadIdx.x * 16u;
   const int cvs = C / 8;
   const int cvb = cvs < TPB ? cvs : TPB;  // channel vectors per CTA pass
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(TPB) chan_reduce_kernel(F f, int64_t M, int C,
         kstep[j] = (int64_t)lanes * f.pitch(j);
         ptr[j] = b ? b + first * f.pitch(j) : nullptr;
       }
-      sgb_ring::walk<NIN, RED_U, D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t q, const uint4(&raw)[NIN]) {
+      sgb_ring::walk<NIN, red_unroll<F>(), D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t q, const uint4(&raw)[NIN]) {
         if constexpr (F::WRITES) f.evalw(first + q * lanes, cv * 8, raw, acc);  // a pass that also writes an output tensor
         else f.eval(raw, acc);
       });
@@ -402,7 +405,7 @@ template <class F>
 int launch_chan_reduce(F f, int64_t M, int C, double* out, int out_stride, cudaStream_t st) {
   int cvs = C / 8;
   int cvb = cvs < TPB ? cvs : TPB;
-  size_t smem = sgb_ring::bytes<F::NIN, RED_U, red_depth<F>(), TPB>() + (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
+  size_t smem = sgb_ring::bytes<F::NIN, red_unroll<F>(), red_depth<F>(), TPB>() + (size_t)(F::NACC * 8 + 1) * TPB * sizeof(float);
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaFuncSetAttribute(chan_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -13,6 +13,8 @@
 //   * IoU arithmetic is fp32 with no fused multiply-add, and `ovr > iou_threshold` is evaluated in double.
 #include "common.cuh"
 
+#include <math.h>
+
 namespace {
 
 constexpr int NT = 1024;      // threads per CTA
@@ -115,40 +117,42 @@ __device__ int find_bin(const int* hist, int nbins, int need, int lane, int* nee
   return bin;
 }
 
-__global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* __restrict__ boxes,
-                                                    const float* __restrict__ scores, const float* __restrict__ conf,
-                                                    const int* __restrict__ lab, float* out, int* out_idx,
-                                                    int* out_count) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
-  const int b = blockIdx.x;
+// Scratch of the selection phase (shared memory of the calling kernel)
+struct SelScratch {
+  int* hist;  // [NBIN]
+  int* wcnt;  // [32]
+  int* wtie;  // [32]
+  int* misc;  // [16]
+};
+
+// Selection phase shared by the NMS kernel and its pre-filter: among sc[0, n_items) the entries passing the threshold, or -- when
+// more than top_k pass -- the top_k largest (3-level radix select; equal scores: lowest index first), visited in INDEX order.
+// emit(p, idx, key) is called once per selected entry with its output position p (0 .. nsel-1, increasing with idx).  All NT
+// threads of the CTA call it; returns the number selected.  `sc` may point to global or shared memory.
+template <class Emit>
+__device__ int select_ordered(const float* __restrict__ sc, const int n_items, const float thr, const int incl, const int top_k, const SelScratch sh,
+                              Emit&& emit) {
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const bool multi = d.multi_label != 0;
-  const int n_items = multi ? d.L * d.ncls : d.L;
-  const float* sc = multi ? scores + (int64_t)b * n_items : conf + (int64_t)b * d.L;
-  const float thr = d.score_thr;
-  const int incl = d.thr_inclusive;
   // contiguous segment per warp (multiple of 128 items so that the unrolled loop stays in order)
   int seg_len = (n_items + 31) / 32;
   seg_len = ((seg_len + 127) / 128) * 128;
   const int seg0 = min(warp * seg_len, n_items), seg1 = min(seg0 + seg_len, n_items);
 
   // ---- pass 1: level-1 histogram (top 11 key bits) + per-warp candidate counts
-  for (int i = t; i < NBIN; i += NT) S.hist[i] = 0;
+  for (int i = t; i < NBIN; i += NT) sh.hist[i] = 0;
   __syncthreads();
-  hist_pass<11>(sc, seg0, seg1, thr, incl, 0u, 0u, 21, S.hist, lane);
+  hist_pass<11>(sc, seg0, seg1, thr, incl, 0u, 0u, 21, sh.hist, lane);
   __syncthreads();
   if (warp == 0) {
     int s = 0;
-    for (int j = 0; j < NBIN / 32; ++j) s += S.hist[lane * (NBIN / 32) + j];
+    for (int j = 0; j < NBIN / 32; ++j) s += sh.hist[lane * (NBIN / 32) + j];
     int tot = s;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) S.misc[0] = tot;
+    if (lane == 0) sh.misc[0] = tot;
   }
   __syncthreads();
-  const int total = S.misc[0];
-  const int top_k = d.top_k < KMAX ? d.top_k : KMAX;
+  const int total = sh.misc[0];
   unsigned Tkey = 0;  // select keys > Tkey, plus `tie_need` keys == Tkey (lowest index first)
   int tie_need = 0;
   bool select_all = total <= top_k;
@@ -156,45 +160,45 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
     // 3-level radix select of the top_k-th largest key
     if (warp == 0) {
       int need;
-      int b1 = find_bin(S.hist, NBIN, top_k, lane, &need);
+      int b1 = find_bin(sh.hist, NBIN, top_k, lane, &need);
       if (lane == 0) {
-        S.misc[1] = b1;
-        S.misc[2] = need;
+        sh.misc[1] = b1;
+        sh.misc[2] = need;
       }
     }
     __syncthreads();
-    unsigned prefix = (unsigned)S.misc[1] << 21;
-    int need = S.misc[2];
-    for (int i = t; i < NBIN; i += NT) S.hist[i] = 0;
+    unsigned prefix = (unsigned)sh.misc[1] << 21;
+    int need = sh.misc[2];
+    for (int i = t; i < NBIN; i += NT) sh.hist[i] = 0;
     __syncthreads();
-    hist_pass<11>(sc, seg0, seg1, thr, incl, 0xffe00000u, prefix, 10, S.hist, lane);
+    hist_pass<11>(sc, seg0, seg1, thr, incl, 0xffe00000u, prefix, 10, sh.hist, lane);
     __syncthreads();
     if (warp == 0) {
       int need2;
-      int b2 = find_bin(S.hist, NBIN, need, lane, &need2);
+      int b2 = find_bin(sh.hist, NBIN, need, lane, &need2);
       if (lane == 0) {
-        S.misc[1] = b2;
-        S.misc[2] = need2;
+        sh.misc[1] = b2;
+        sh.misc[2] = need2;
       }
     }
     __syncthreads();
-    prefix |= (unsigned)S.misc[1] << 10;
-    need = S.misc[2];
-    for (int i = t; i < NBIN; i += NT) S.hist[i] = 0;
+    prefix |= (unsigned)sh.misc[1] << 10;
+    need = sh.misc[2];
+    for (int i = t; i < NBIN; i += NT) sh.hist[i] = 0;
     __syncthreads();
-    hist_pass<10>(sc, seg0, seg1, thr, incl, 0xfffffc00u, prefix, 0, S.hist, lane);
+    hist_pass<10>(sc, seg0, seg1, thr, incl, 0xfffffc00u, prefix, 0, sh.hist, lane);
     __syncthreads();
     if (warp == 0) {
       int need3;
-      int b3 = find_bin(S.hist, 1024, need, lane, &need3);
+      int b3 = find_bin(sh.hist, 1024, need, lane, &need3);
       if (lane == 0) {
-        S.misc[1] = b3;
-        S.misc[2] = need3;
+        sh.misc[1] = b3;
+        sh.misc[2] = need3;
       }
     }
     __syncthreads();
-    Tkey = prefix | (unsigned)S.misc[1];
-    tie_need = S.misc[2];
+    Tkey = prefix | (unsigned)sh.misc[1];
+    tie_need = sh.misc[2];
   }
 
   // ---- count pass: per-warp (# selected strictly above, # ties) in index order
@@ -220,8 +224,8 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
       ct += __shfl_xor_sync(0xffffffffu, ct, o);
     }
     if (lane == 0) {
-      S.wcnt[warp] = cg;
-      S.wtie[warp] = ct;
+      sh.wcnt[warp] = cg;
+      sh.wtie[warp] = ct;
     }
   }
   __syncthreads();
@@ -229,26 +233,26 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
     // exclusive scan over warps; ties are granted in index order until tie_need is exhausted
     int pos = 0, ties_before = 0;
     for (int w = 0; w < 32; ++w) {
-      int cg = S.wcnt[w], ct = S.wtie[w];
+      int cg = sh.wcnt[w], ct = sh.wtie[w];
       int grant = 0;
       if (!select_all) {
         int left = tie_need - ties_before;
         grant = left > 0 ? (ct < left ? ct : left) : 0;
       }
-      S.wcnt[w] = pos;           // output base of this warp
-      S.wtie[w] = ties_before;   // ties preceding this warp
+      sh.wcnt[w] = pos;           // output base of this warp
+      sh.wtie[w] = ties_before;   // ties preceding this warp
       pos += cg + grant;
       ties_before += ct;
     }
-    S.misc[3] = pos;  // number of selected candidates
+    sh.misc[3] = pos;  // number of selected candidates
   }
   __syncthreads();
-  const int nsel = S.misc[3];
+  const int nsel = sh.misc[3];
 
   // ---- write pass: ordered compaction into S.flat / S.keys
   {
-    int pos = S.wcnt[warp];
-    int ties_seen = S.wtie[warp];
+    int pos = sh.wcnt[warp];
+    int ties_seen = sh.wtie[warp];
     for (int base = seg0; base < seg1; base += 128) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -272,10 +276,7 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
         unsigned vb = __ballot_sync(0xffffffffu, valid);
         if (valid) {
           int p = pos + __popc(vb & ((1u << lane) - 1));
-          if (p < KMAX) {
-            S.flat[p] = idx;
-            S.keys[p] = ((unsigned long long)(~k) << 32) | (unsigned)p;
-          }
+          if (p < top_k) emit(p, idx, k);
         }
         pos += __popc(vb);
       }
@@ -283,6 +284,155 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
   }
   __syncthreads();
 
+  __syncthreads();
+  return nsel;
+}
+
+// Pre-filter of the multi-label path.  One CTA per (slice, image): the slice of the score row (<= PF_SLICE floats) is read from
+// HBM ONCE with 16-byte loads into shared memory; the selection phase then runs on the shared-memory copy and writes the slice's
+// candidates -- everything passing the threshold, or the slice's own top_k -- in index order to cand_sc / cand_flat[b][slice][0..top_k),
+// padding the segment with -inf.  The union of the per-slice top_k contains the image's top_k (an entry beaten by fewer than
+// top_k entries of the image is beaten by fewer than top_k entries of its slice; ties keep the lowest index in both rules), and the
+// concatenated segments keep the row-major candidate order, so nms_kernel run on the candidate lists selects, orders and suppresses
+// exactly what it would on the full row.  The full row is L * ncls floats per image (2.7 MB for 8400 x 80): scanned by one CTA per
+// image with up to five passes of 4-byte loads it was the whole cost of the launch (1.77 ms for 32 images: 51 GB/s); here every SM
+// streams slices.
+constexpr int PF_SLICE = 24576;  // floats per slice: 96 KB + scratch, two CTAs per SM
+__global__ void __launch_bounds__(NT, 2) nms_prefilter_kernel(SgbNmsDesc d, const float* __restrict__ scores, int n_items, int slice_len, int nslices,
+                                                              float* __restrict__ cand_sc, int* __restrict__ cand_flat) {
+  extern __shared__ __align__(16) unsigned char pf_raw[];
+  float* v = reinterpret_cast<float*>(pf_raw);             // [slice_len]
+  int* scratch = reinterpret_cast<int*>(v + PF_SLICE);      // hist[NBIN], wcnt[32], wtie[32], misc[16]
+  const int s = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int i0 = s * slice_len;
+  const int n = max(0, min(slice_len, n_items - i0));
+  const float* src = scores + (int64_t)b * n_items + i0;
+  if (((uintptr_t)src & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i = t; i < n4; i += NT) reinterpret_cast<float4*>(v)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int i = (n4 << 2) + t; i < n; i += NT) v[i] = src[i];
+  } else {
+    for (int i = t; i < n; i += NT) v[i] = src[i];
+  }
+  __syncthreads();
+  const int top_k = d.top_k < KMAX ? d.top_k : KMAX;
+  float* osc = cand_sc + ((int64_t)b * nslices + s) * top_k;
+  int* ofl = cand_flat + ((int64_t)b * nslices + s) * top_k;
+  SelScratch sh{scratch, scratch + NBIN, scratch + NBIN + 32, scratch + NBIN + 64};
+  const int nsel = select_ordered(v, n, d.score_thr, d.thr_inclusive, top_k, sh, [&](int p, int idx, unsigned) {
+    osc[p] = v[idx];
+    ofl[p] = i0 + idx;
+  });
+  for (int j = nsel + t; j < top_k; j += NT) {
+    osc[j] = -INFINITY;  // never passes a (finite) threshold
+    ofl[j] = 0;
+  }
+}
+
+// Split form of the per-image work for large candidate counts.  With ~1000 candidates the IoU bit-matrix is 500 k IoU evaluations
+// (fp32 division each) and dominated the one-CTA-per-image kernel (32 CTAs on 148 SMs); it is the only part with no sequential
+// dependence, so it runs as its own launch over (row block, image) CTAs between a "front" launch (selection, sort, gather, offsets,
+// areas -> NmsStage in global memory) and a "back" launch (greedy sweep over the matrix + output rows).  Same arithmetic, same
+// order of operations per IoU.
+struct NmsStage {
+  float bx[4][KMAX];
+  float area[KMAX];
+  int label[KMAX];
+  int sflat[KMAX];
+  int nsel, trick, pad_[2];
+};
+constexpr int MASK_ROWS = 64;  // rows of the bit-matrix per CTA of nms_mask_kernel
+
+__global__ void __launch_bounds__(NT, 1) nms_mask_kernel(SgbNmsDesc d, const NmsStage* __restrict__ stages, unsigned long long* __restrict__ masks) {
+  __shared__ float bx[4][KMAX];
+  __shared__ float area[KMAX];
+  __shared__ int label[KMAX];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const NmsStage& st = stages[b];
+  const int nsel = st.nsel;
+  const int i0 = blockIdx.x * MASK_ROWS;
+  if (i0 >= nsel) return;
+  for (int i = t; i < nsel; i += NT) {
+    bx[0][i] = st.bx[0][i];
+    bx[1][i] = st.bx[1][i];
+    bx[2][i] = st.bx[2][i];
+    bx[3][i] = st.bx[3][i];
+    area[i] = st.area[i];
+    label[i] = st.label[i];
+  }
+  __syncthreads();
+  const int nw = (nsel + 63) / 64;
+  const bool same_class_only = !d.class_agnostic && !st.trick;
+  unsigned long long* mrow = masks + (int64_t)b * KMAX * (KMAX / 64);
+  const int rows = min(MASK_ROWS, nsel - i0);
+  for (int pair = t; pair < rows * nw; pair += NT) {
+    const int i = i0 + pair / nw, w = pair % nw;
+    unsigned long long bits = 0ull;
+    if (w * 64 + 63 > i) {
+      const float ix1 = bx[0][i], iy1 = bx[1][i], ix2 = bx[2][i], iy2 = bx[3][i], ia = area[i];
+      const int li = label[i];
+      const int j0 = w * 64;
+      const int jend = min(j0 + 64, nsel);
+      for (int j = max(j0, i + 1); j < jend; ++j) {
+        if (same_class_only && label[j] != li) continue;
+        float xx1 = fmaxf(ix1, bx[0][j]), yy1 = fmaxf(iy1, bx[1][j]);
+        float xx2 = fminf(ix2, bx[2][j]), yy2 = fminf(iy2, bx[3][j]);
+        float ww = fmaxf(0.f, __fsub_rn(xx2, xx1)), hh = fmaxf(0.f, __fsub_rn(yy2, yy1));
+        float inter = __fmul_rn(ww, hh);
+        float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ia, area[j]), inter));
+        if ((double)ovr > d.iou_thr) bits |= 1ull << (j - j0);
+      }
+    }
+    mrow[i * (KMAX / 64) + w] = bits;
+  }
+}
+
+// cand_sc / cand_flat (optional): per image `cand_items` pre-filtered candidates in row-major order (nms_prefilter_kernel); the
+// selection phase then scans those instead of the full score row.
+__global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* __restrict__ boxes,
+                                                    const float* __restrict__ scores, const float* __restrict__ conf,
+                                                    const int* __restrict__ lab, float* out, int* out_idx,
+                                                    int* out_count, const float* __restrict__ cand_sc, const int* __restrict__ cand_flat,
+                                                    int cand_items, int mode, NmsStage* __restrict__ stages,
+                                                    const unsigned long long* __restrict__ masks) {
+  // mode 0: everything in this launch; 1: front (up to the areas, staged to `stages`); 2: back (sweep over `masks` + output)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
+  const int b = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool multi = d.multi_label != 0;
+  const int n_items = multi ? d.L * d.ncls : d.L;
+  const float* orig = multi ? scores + (int64_t)b * n_items : conf + (int64_t)b * d.L;  // score of a flat candidate index
+  const float* sc = cand_sc ? cand_sc + (int64_t)b * cand_items : orig;
+  const int n_scan = cand_sc ? cand_items : n_items;
+  const float thr = d.score_thr;
+  const int incl = d.thr_inclusive;
+  SelScratch sh{S.hist, S.wcnt, S.wtie, S.misc};
+  const int top_k = d.top_k < KMAX ? d.top_k : KMAX;
+  const int* fmap = cand_flat ? cand_flat + (int64_t)b * cand_items : nullptr;
+  if (mode == 2) {  // back half: restore what the sweep and the output rows need
+    const NmsStage& st = stages[b];
+    const int ns = st.nsel;
+    for (int i = t; i < ns; i += NT) {
+      S.label[i] = st.label[i];
+      S.sflat[i] = st.sflat[i];
+    }
+    const int nwb = (ns + 63) / 64;
+    const unsigned long long* mrow = masks + (int64_t)b * KMAX * (KMAX / 64);
+    for (int i = t; i < ns * nwb; i += NT) {
+      const int r = i / nwb, w = i - r * nwb;
+      S.mask[r * (KMAX / 64) + w] = mrow[r * (KMAX / 64) + w];
+    }
+    if (t == 0) S.misc[5] = ns;
+    __syncthreads();
+  }
+  const int nsel = mode == 2 ? S.misc[5] : select_ordered(sc, n_scan, thr, incl, top_k, sh, [&](int p, int idx, unsigned k) {
+    S.flat[p] = fmap ? fmap[idx] : idx;
+    S.keys[p] = ((unsigned long long)(~k) << 32) | (unsigned)p;
+  });
+
+  bool trick_flag = false;
+  if (mode != 2) {
   // ---- bitonic sort of (score desc, position asc)
   int np2 = 1;
   while (np2 < nsel) np2 <<= 1;
@@ -324,6 +474,7 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
   }
   // batched_nms path selection exactly as torchvision (CPU): coordinate trick iff boxes.numel() <= 4000
   const bool trick = !d.class_agnostic && (4 * nsel <= 4000);
+  trick_flag = trick;
   if (trick) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -350,9 +501,28 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
     S.area[i] = __fmul_rn(__fsub_rn(S.bx[2][i], S.bx[0][i]), __fsub_rn(S.bx[3][i], S.bx[1][i]));
   __syncthreads();
 
-  // ---- IoU bit matrix: mask[i][w] bit j: j > i, suppressed by i
+  }
+  if (mode == 1) {  // front half done: stage what the matrix and the back half need
+    NmsStage& st = stages[b];
+    for (int i = t; i < nsel; i += NT) {
+      st.bx[0][i] = S.bx[0][i];
+      st.bx[1][i] = S.bx[1][i];
+      st.bx[2][i] = S.bx[2][i];
+      st.bx[3][i] = S.bx[3][i];
+      st.area[i] = S.area[i];
+      st.label[i] = S.label[i];
+      st.sflat[i] = S.sflat[i];
+    }
+    if (t == 0) {
+      st.nsel = nsel;
+      st.trick = trick_flag ? 1 : 0;
+    }
+    return;
+  }
   const int nw = (nsel + 63) / 64;
-  const bool same_class_only = !d.class_agnostic && !trick;
+  if (mode == 0) {
+  // ---- IoU bit matrix: mask[i][w] bit j: j > i, suppressed by i
+  const bool same_class_only = !d.class_agnostic && !trick_flag;
   for (int pair = t; pair < nsel * nw; pair += NT) {
     int i = pair / nw, w = pair - i * nw;
     unsigned long long bits = 0ull;
@@ -375,6 +545,7 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
   }
   __syncthreads();
 
+  }
   // ---- greedy sweep by warp 0: lane w owns word w of the "removed" bitset
   if (warp == 0) {
     unsigned long long remv = 0ull;  // lanes 0..15
@@ -404,7 +575,7 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
       o[1] = bp[1];
       o[2] = bp[2];
       o[3] = bp[3];
-      o[4] = sc[f];
+      o[4] = orig[f];
       o[5] = (float)S.label[i];
       out_idx[(int64_t)b * d.max_out + r] = multi ? f : f * d.ncls + S.label[i];
     } else {
@@ -416,9 +587,51 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
 
 }  // namespace
 
+// multi-label rows longer than this go through the pre-filter (SGB_NMS_PREFILTER=0 disables it: a tuning / A-B hook)
+static bool prefilter_wanted(const SgbNmsDesc* d) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SGB_NMS_PREFILTER");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && d->multi_label && (int64_t)d->L * d->ncls > 4 * PF_SLICE && (int64_t)d->L * d->ncls < (1ll << 30) && isfinite(d->score_thr);
+}
+static int prefilter_slices(const SgbNmsDesc* d, int* slice_len) {
+  const int64_t n = (int64_t)d->L * d->ncls;
+  const int ns = (int)((n + PF_SLICE - 1) / PF_SLICE);
+  int sl = (int)((n + ns - 1) / ns);
+  sl = ((sl + 3) / 4) * 4;  // slice starts stay 16-byte aligned when the row is
+  *slice_len = sl;
+  return (int)((n + sl - 1) / sl);
+}
+
+// more than this many candidates per image: front / IoU-matrix / back as three launches (SGB_NMS_SPLIT=0 disables it)
+static bool split_wanted(const SgbNmsDesc* d) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SGB_NMS_SPLIT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && d->top_k > 512;
+}
+static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+// workspace layout: [single-label conf / labels  |  pre-filter candidates] [stages] [masks]
+static int64_t ws_head_bytes(const SgbNmsDesc* d) {
+  int64_t bytes = (int64_t)d->B * d->L * 8;
+  if (prefilter_wanted(d)) {
+    int sl;
+    const int ns = prefilter_slices(d, &sl);
+    const int64_t cand = (int64_t)d->B * ns * (d->top_k < KMAX ? d->top_k : KMAX) * 8;
+    if (cand > bytes) bytes = cand;
+  }
+  return align256(bytes);
+}
+
 extern "C" int64_t sgb_nms_workspace_bytes(const SgbNmsDesc* d) {
   if (!d) return 0;
-  return (int64_t)d->B * d->L * 8 + 256;
+  int64_t bytes = ws_head_bytes(d) + 256;
+  if (split_wanted(d)) bytes += align256((int64_t)d->B * sizeof(NmsStage)) + (int64_t)d->B * KMAX * (KMAX / 64) * 8;
+  return bytes;
 }
 
 extern "C" int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const float* scores, float* out,
@@ -452,7 +665,42 @@ extern "C" int sgb_batched_nms(const SgbNmsDesc* d, const float* boxes, const fl
       return rc;
     attr = true;
   }
-  nms_kernel<<<d->B, NT, sizeof(NmsSmem), st>>>(*d, boxes, scores, conf, lab, out, out_idx, out_count);
+  const float* cand_sc = nullptr;
+  const int* cand_flat = nullptr;
+  int cand_items = 0;
+  if (prefilter_wanted(d) && workspace && workspace_bytes >= sgb_nms_workspace_bytes(d)) {
+    int sl;
+    const int ns = prefilter_slices(d, &sl);
+    const int tk = d->top_k < KMAX ? d->top_k : KMAX;
+    float* csc = reinterpret_cast<float*>(workspace);
+    int* cfl = reinterpret_cast<int*>(csc + (int64_t)d->B * ns * tk);
+    const size_t pf_smem = (size_t)PF_SLICE * 4 + (NBIN + 32 + 32 + 16) * 4;
+    static bool pf_attr = false;
+    if (!pf_attr) {
+      if (int rc = sgb_cuda_check(cudaFuncSetAttribute(nms_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_smem),
+                                  "cudaFuncSetAttribute(nms_prefilter_kernel)"))
+        return rc;
+      pf_attr = true;
+    }
+    nms_prefilter_kernel<<<dim3(ns, d->B), NT, pf_smem, st>>>(*d, scores, d->L * d->ncls, sl, ns, csc, cfl);
+    SGB_LAUNCH_CHECK("nms_prefilter_kernel");
+    cand_sc = csc;
+    cand_flat = cfl;
+    cand_items = ns * tk;
+  }
+  if (split_wanted(d) && workspace && workspace_bytes >= sgb_nms_workspace_bytes(d)) {
+    unsigned char* base = reinterpret_cast<unsigned char*>(workspace) + ws_head_bytes(d);
+    NmsStage* stages = reinterpret_cast<NmsStage*>(base);
+    unsigned long long* masks = reinterpret_cast<unsigned long long*>(base + align256((int64_t)d->B * sizeof(NmsStage)));
+    nms_kernel<<<d->B, NT, sizeof(NmsSmem), st>>>(*d, boxes, scores, conf, lab, out, out_idx, out_count, cand_sc, cand_flat, cand_items, 1, stages, masks);
+    SGB_LAUNCH_CHECK("nms_kernel (front)");
+    nms_mask_kernel<<<dim3(KMAX / MASK_ROWS, d->B), NT, 0, st>>>(*d, stages, masks);
+    SGB_LAUNCH_CHECK("nms_mask_kernel");
+    nms_kernel<<<d->B, NT, sizeof(NmsSmem), st>>>(*d, boxes, scores, conf, lab, out, out_idx, out_count, cand_sc, cand_flat, cand_items, 2, stages, masks);
+    SGB_LAUNCH_CHECK("nms_kernel (back)");
+    return SGB_OK;
+  }
+  nms_kernel<<<d->B, NT, sizeof(NmsSmem), st>>>(*d, boxes, scores, conf, lab, out, out_idx, out_count, cand_sc, cand_flat, cand_items, 0, nullptr, nullptr);
   SGB_LAUNCH_CHECK("nms_kernel");
   return SGB_OK;
 }

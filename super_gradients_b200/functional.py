@@ -214,8 +214,11 @@ class FoldedWeightCache:
 # the buffer.  Autograd's sum is unchanged whatever else consumes the tensor (non-participating consumers are added by autograd
 # as before).  It relies on every registered consumer running in the same backward pass; a pass that reaches only some of them
 # (part of the outputs unused) is detected by a callback at the end of the pass and raises instead of returning wrong gradients
-# (SGB_SHARE_GRADS=0 turns the mechanism off).
-SHARE_GRADS = [__import__("os").environ.get("SGB_SHARE_GRADS", "1") != "0"]
+# Measured on B200 (YOLO-NAS-S, batch 32): the 39 ATen adds disappear (-0.78 ms) but the accumulating epilogues of the halo / 1x1
+# tile kernels read the residual row with one dependent 16-byte load per thread and cost more than that (+1.3 ms): 1627 img/s
+# with the mechanism against 1673 without, so it is OFF by default (SGB_SHARE_GRADS=1 turns it on) until those epilogues prefetch
+# the residual through TMA.
+SHARE_GRADS = [__import__("os").environ.get("SGB_SHARE_GRADS", "0") == "1"]
 
 
 class _GradShare:
@@ -511,7 +514,10 @@ class _ConvBias(torch.autograd.Function):
             else:
                 n, _, h, wd = dy.shape
                 dyk = _padded_view(K.empty_nhwc(n, kout, h, wd, dy.device, c_alloc=kp), kp)  # zero-initialised
-                K.axpby(dy, 1.0, out=dyk[:, :kout])
+                if kout % 8 == 0:
+                    K.axpby(dy, 1.0, out=dyk[:, :kout])
+                else:
+                    dyk[:, :kout].copy_(dy)  # ragged channel count from a producer that did not mark its padding: plain strided copy
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _share_dx(
@@ -597,7 +603,24 @@ class _QARepVGG(torch.autograd.Function):
         if dcat is not None:
             if ctx.needs_input_grad[0]:
                 dx = _share_dx(tok, lambda: K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1), lambda buf: K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1, out=buf, accumulate=True))
-            dwf = K.conv_wgrad(x, dcat, 3, 3, 1, 1)  # fp32 [2K, 3, 3, C]: rows [0, K) = dW3, rows [K, 2K) centre tap = d(alpha * K1 + I)
+            c = _CTX[0]
+            batched = c is not None and sw3 is not None and sw1 is not None and (not has_alpha or (salpha is not None and (sbias is not None or not has_bias)))
+            # fp32 [2K, 3, 3, C]: rows [0, K) = dW3, rows [K, 2K) centre tap = d(alpha * K1 + I)
+            dwf = _wgrad_raw(x, dcat, 3, 3, 1, 1) if batched else K.conv_wgrad(x, dcat, 3, 3, 1, 1)
+            if batched:
+                # inside a train step nothing reads the gradient before flush_wgrads(): the launch goes to the side stream and both
+                # filters' gradients are delivered by the batched passes (the 1x1 filter's is the centre-tap view of the buffer)
+                c.pending.append((dwf[:kout], cin, sw3))
+                dw1v = dwf[kout:, 1:2, 1:2, :]  # [K, 1, 1, c] view, row pitch 9 * c
+                if has_alpha:
+                    c.alpha_pending.append((dw1v, cin, w1, alpha, dab if has_bias else None, bias1 if has_bias else None, sw1, sbias if has_bias else None, salpha))
+                else:
+                    c.pending.append((dw1v, cin, sw1))
+                dw3 = dw1 = dbias1 = dalpha = None
+                if has_bias and not has_alpha and sbias is None:
+                    dbias1 = dab
+                ret = lambda slot, v: None if slot is not None else v  # noqa: E731
+                return dx, dw3, ret(sg3, dg3), ret(sb3, db3), dw1, dbias1, dalpha, (ret(sgp, dgp) if has_post else None), (ret(sbp, dbp) if has_post else None), None
             if sw3 is not None and _CTX[0] is not None:
                 _CTX[0].pending.append((dwf[:kout], cin, sw3))
                 dw3 = None
@@ -973,6 +996,7 @@ class _PoseDecode(torch.autograd.Function):
             base += hw
         ctx.cfg = cfg
         ctx.geom = (B, hws, Ltot, [tuple(t.shape) for t in regs], [tuple(t.shape) for t in clss], [tuple(t.shape) for t in poses])
+        ctx.pitches = [[K.nhwc_pitch(t) for t in ts] for ts in (regs, clss, poses)]
         ctx.mark_non_differentiable(pb, ps, pj)
         return pb, ps, pc, pj, cl, rd, pl
 
@@ -995,16 +1019,16 @@ class _PoseDecode(torch.autograd.Function):
                 base += hw
         outs = [None]
         base = 0
-        for hw, rs, cs, psh in zip(hws, rshapes, cshapes, pshapes):
+        for lvl, (hw, rs, cs, psh) in enumerate(zip(hws, rshapes, cshapes, pshapes)):
             dr = dc = dp = None
             if grd is not None:
-                dr = K.empty_nhwc(rs[0], rs[1], rs[2], rs[3], some.device)
+                dr = _grad_map(rs, ctx.pitches[0][lvl], some.device)
                 K.head_grad_scatter(grd.contiguous(), B, hw, Ltot, base, dr)
             if g_cls is not None:
-                dc = K.empty_nhwc(cs[0], cs[1], cs[2], cs[3], some.device)
+                dc = _grad_map(cs, ctx.pitches[1][lvl], some.device)
                 K.head_grad_scatter(g_cls, B, hw, Ltot, base, dc)
             if g_pose is not None:
-                dp = K.empty_nhwc(psh[0], psh[1], psh[2], psh[3], some.device)
+                dp = _grad_map(psh, ctx.pitches[2][lvl], some.device)
                 K.head_grad_scatter(g_pose, B, hw, Ltot, base, dp)
             outs += [dr, dc, dp]
             base += hw

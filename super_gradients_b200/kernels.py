@@ -285,6 +285,10 @@ def wgrad_to_oihw_batch_table(entries, device):
     items, start = [], 0
     for dw, C, g, accumulate in entries:
         Kk, R, S, cp = dw.shape
+        if R == 1 and S == 1:
+            cp = dw.stride(0)  # a [K, 1, 1, c] view of one tap of a wider gradient buffer (the folded QARepVGG filter): rows are further apart
+        elif not dw.is_contiguous():
+            raise L.SgbError("wgrad_to_oihw_batch: a multi-tap gradient must be contiguous KRSC")
         it = L.WgradItem()
         it.dw, it.g = dw.data_ptr(), g.data_ptr()
         it.K, it.C, it.R, it.S, it.c_pad, it.accumulate, it.start = Kk, C, R, S, cp, 1 if accumulate else 0, start
@@ -304,7 +308,7 @@ def qarep_alpha_finish_table(entries, device):
         it = L.AlphaItem()
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         it.dw1, it.w1, it.alpha, it.dab, it.bias1, it.g_w1, it.g_bias, it.g_alpha = p(dw1), p(w1), p(alpha), p(dab), p(bias1), p(g_w1), p(g_bias), p(g_alpha)
-        it.K, it.C, it.c_pad, it.pad_ = dw1.shape[0], C, dw1.shape[3], 0
+        it.K, it.C, it.c_pad, it.pad_ = dw1.shape[0], C, dw1.stride(0), 0  # stride(0): the row pitch (a one-tap view of a wider buffer has a larger one)
         items.append(it)
     return _item_table(items).to(device), len(items)
 

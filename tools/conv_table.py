@@ -39,6 +39,21 @@ def main():
         step.set_hyper_params(2e-4, 0.9997)
         step._step_eager(x, t)
     torch.cuda.synchronize()
+    # which engine served each convolution call: the library counts launches of the im2col (umma) and halo-tile kernels
+    lib = K.L.load()
+    engines = []
+    orig_call = K.L.call
+
+    def call(name, *a):
+        if not name.startswith("sgb_conv_"):
+            return orig_call(name, *a)
+        u0, h0 = lib.sgb_sm100_launches(), lib.sgb_sm100_halo_launches()
+        rc = orig_call(name, *a)
+        u1, h1 = lib.sgb_sm100_launches(), lib.sgb_sm100_halo_launches()
+        engines.append("halo" if h1 > h0 else ("umma" if u1 > u0 else "mma.sync"))
+        return rc
+
+    K.L.call = call
     K.PROFILE.clear()
     K.PROFILE_ON[0] = True
     n = 3
@@ -47,9 +62,13 @@ def main():
         step._step_eager(x, t)
     torch.cuda.synchronize()
     K.PROFILE_ON[0] = False
+    K.L.call = orig_call
     agg = {}
+    eng = iter(engines)
     for name, a, b, tag in K.PROFILE:
-        if not args.all and not name.startswith("sgb_conv_"):
+        if name.startswith("sgb_conv_"):
+            name = name + ":" + next(eng)
+        elif not args.all:
             continue
         d = agg.setdefault((name, tag), [0, 0.0])
         d[0] += 1
@@ -69,10 +88,18 @@ def main():
         rows.append((ms / n, cnt // n, us, name, desc, gbs, tfs))
     rows.sort(reverse=True)
     tot = sum(r[0] for r in rows)
+    by_engine = {}
+    for ms, cnt, us, name, desc, gbs, tfs in rows:
+        if ":" in name:
+            e = by_engine.setdefault(name.split("_", 1)[1], [0, 0.0])
+            e[0] += cnt
+            e[1] += ms
+    for k, (cnt, ms) in sorted(by_engine.items(), key=lambda kv: -kv[1][1]):
+        print(f"  {k:24s} {cnt:4d} calls  {ms:7.3f} ms/step")
     print(f"{args.model} batch {args.batch}: {tot:.3f} ms/step in the listed calls (eager, events per call, no side stream)")
-    print(f"{'ms/step':>8s} {'n':>3s} {'avg us':>8s}  {'call':16s} {'shape':32s} {'GB/s':>7s} {'TF/s':>7s}")
+    print(f"{'ms/step':>8s} {'n':>3s} {'avg us':>8s}  {'call':24s} {'shape':32s} {'GB/s':>7s} {'TF/s':>7s}")
     for ms, cnt, us, name, desc, gbs, tfs in rows[: args.top]:
-        print(f"{ms:8.3f} {cnt:3d} {us:8.1f}  {name[4:]:16s} {desc:32s} {gbs:7.0f} {tfs:7.1f}")
+        print(f"{ms:8.3f} {cnt:3d} {us:8.1f}  {name[4:]:24s} {desc:32s} {gbs:7.0f} {tfs:7.1f}")
 
 
 if __name__ == "__main__":

@@ -49,7 +49,29 @@ case "${1}" in
     timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest9.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest9.log
     for sg in 1 0; do printf "SGB_SHARE_GRADS=%d: " $sg; SGB_SHARE_GRADS=$sg timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench9_sg$sg.err | tee gpurun_out/r2_bench9_sg$sg.json | bench_line; tail -2 gpurun_out/r2_bench9_sg$sg.err; done
     for mp in 12800 51200 204800 0; do printf "SGB_QAREP_FOLD=1 MAXPIX=%d: " $mp; SGB_QAREP_FOLD=1 SGB_QAREP_FOLD_MAXPIX=$mp timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench9_fold$mp.err | tee gpurun_out/r2_bench9_fold$mp.json | bench_line; tail -2 gpurun_out/r2_bench9_fold$mp.err; done
-    timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline9_launches.txt > gpurun_out/r2_timeline9.txt 2>gpurun_out/r2_timeline9.err; head -30 gpurun_out/r2_timeline9.txt; tail -3 gpurun_out/r2_timeline9.err ;;
+    timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline9_launches.txt > gpurun_out/r2_timeline9.txt 2>gpurun_out/r2_timeline9.err; head -30 gpurun_out/r2_timeline9.txt; tail -3 gpurun_out/r2_timeline9.err
+    timeout 300 python tools/mem_kernels.py > gpurun_out/r2_mem_kernels9.txt 2>gpurun_out/r2_mem_kernels9.err; cat gpurun_out/r2_mem_kernels9.txt; tail -3 gpurun_out/r2_mem_kernels9.err ;;
+  dp)  # N GPUs (gpurun --gpus N): split graphs around an eager all-reduce vs NCCL captured inside one graph
+    N=${2:-2}
+    for ig in 0 1; do
+      printf "N=%d SGB_NCCL_IN_GRAPH=%d: " $N $ig
+      SGB_NCCL_IN_GRAPH=$ig timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29520 + ig)) bench.py --gpus $N --steps 30 --warmup 5 --skip-cpu-baseline \
+        > gpurun_out/r2_bench_dp${N}_ig$ig.json 2> gpurun_out/r2_bench_dp${N}_ig$ig.err; echo "rc=$?"; tail -2 gpurun_out/r2_bench_dp${N}_ig$ig.err; bench_line < gpurun_out/r2_bench_dp${N}_ig$ig.json
+    done ;;
+  tenth)  # shared grads off by default; fold / fused-forward A/B; timeline of the folded step
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest10.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest10.log
+    for v in "SGB_QAREP_FOLD=0 SGB_FUSED_FWD=1" "SGB_QAREP_FOLD=1 SGB_FUSED_FWD=1" "SGB_QAREP_FOLD=0 SGB_FUSED_FWD=0" "SGB_QAREP_FOLD=1 SGB_FUSED_FWD=0"; do
+      printf "%s: " "$v"; env $v timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench10.err | tee "gpurun_out/r2_bench10_$(echo $v | tr ' =' '__').json" | bench_line; tail -2 gpurun_out/r2_bench10.err
+    done
+    SGB_QAREP_FOLD=1 timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline10_launches.txt > gpurun_out/r2_timeline10.txt 2>gpurun_out/r2_timeline10.err; head -36 gpurun_out/r2_timeline10.txt; tail -3 gpurun_out/r2_timeline10.err
+    SGB_QAREP_FOLD=1 timeout 300 python tools/conv_table.py --all --top 60 > gpurun_out/r2_conv_table10.txt 2>gpurun_out/r2_conv_table10.err; tail -3 gpurun_out/r2_conv_table10.err ;;
+  eleventh)  # split NMS (front / IoU matrix / back), batched folded plumbing; engine-attributed conv table
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest11.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest11.log
+    for v in "SGB_QAREP_FOLD=0" "SGB_QAREP_FOLD=1"; do
+      printf "%s: " "$v"; env $v timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench11.err | tee "gpurun_out/r2_bench11_$(echo $v | tr ' =' '__').json" | bench_line; tail -2 gpurun_out/r2_bench11.err
+    done
+    timeout 300 python tools/mem_kernels.py > gpurun_out/r2_mem_kernels11.txt 2>gpurun_out/r2_mem_kernels11.err; cat gpurun_out/r2_mem_kernels11.txt; tail -3 gpurun_out/r2_mem_kernels11.err
+    timeout 300 python tools/conv_table.py --top 300 > gpurun_out/r2_conv_table11.txt 2>gpurun_out/r2_conv_table11.err; head -8 gpurun_out/r2_conv_table11.txt; tail -3 gpurun_out/r2_conv_table11.err ;;
   multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
     N=${2:-2}
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \
