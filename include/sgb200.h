@@ -101,6 +101,12 @@ typedef struct SgbWeightItem {
   sgb_bf16* krsc;
   sgb_bf16* crsk;     /* or NULL */
   int32_t K, C, R, S, c_pad, add_identity;
+  /* Destination inside a WIDER filter (the folded QARepVGG filter [K3 ; centre(alpha*K1 + I)] with 2K output channels):
+   * kp > 0: the CRSK rows have kp entries and this filter's K outputs start at column koff (only k < K is written);
+   * etaps > 0: the (1 x 1) source is the tap `etap` of an etaps-tap destination filter (KRSC row = etaps * c_pad entries,
+   * CRSK row index = c * etaps + etap); krsc already points at this filter's first destination row.  The destination's
+   * other entries are never written: allocate it zeroed. */
+  int32_t kp, koff, etaps, etap;
   int64_t start;
 } SgbWeightItem;
 typedef struct SgbWgradItem {

@@ -54,7 +54,8 @@ inline int grid_for(int64_t work, int per_cta = TPB, int max_ctas = 148 * 8) {
 // ---------------------------------------------------------------------------------------------- weights / layout
 // element i of the concatenated [K][R][S][cp] (KRSC) ++ [C][R][S][Kp] (CRSK) bf16 copies of one fp32 OIHW filter
 __device__ __forceinline__ void weight_prepare_elem(const float* __restrict__ w, int K, int C, int R, int S, int cp, bf16* krsc,
-                                                    bf16* crsk, float sc, int add_identity, int64_t i64) {
+                                                    bf16* crsk, float sc, int add_identity, int64_t i64, int kp = 0, int koff = 0, int etaps = 0,
+                                                    int etap = 0) {
   // one filter has far fewer than 2^31 elements: 32-bit unsigned index arithmetic (a 64-bit division costs ~10x a 32-bit one)
   const uint32_t Kp = (uint32_t)((K + 7) / 8) * 8, uC = (uint32_t)C, uR = (uint32_t)R, uS = (uint32_t)S, ucp = (uint32_t)cp;
   const uint32_t n1 = (uint32_t)K * uR * uS * ucp;
@@ -73,7 +74,8 @@ __device__ __forceinline__ void weight_prepare_elem(const float* __restrict__ w,
       v = w[((k * uC + c) * uR + r) * uS + s] * sc;
       if (add_identity && k == c && r == uR / 2 && s == uS / 2) v += 1.f;
     }
-    krsc[i] = __float2bfloat16_rn(v);
+    // destination inside a wider filter: the 1 x 1 source is one tap of an etaps-tap filter
+    krsc[etaps > 0 ? (k * (uint32_t)etaps + (uint32_t)etap) * ucp + c : i] = __float2bfloat16_rn(v);
   } else {
     const uint32_t j = i - n1;
     const uint32_t k = j % Kp;
@@ -89,7 +91,12 @@ __device__ __forceinline__ void weight_prepare_elem(const float* __restrict__ w,
       v = w[((k * uC + c) * uR + r) * uS + s] * sc;
       if (add_identity && k == c && r == uR / 2 && s == uS / 2) v += 1.f;
     }
-    crsk[j] = __float2bfloat16_rn(v);
+    if (kp > 0 || etaps > 0) {
+      const uint32_t row = etaps > 0 ? c * (uint32_t)etaps + (uint32_t)etap : (c * uR + r) * uS + s;
+      if (k < (uint32_t)K) crsk[(size_t)row * (uint32_t)(kp > 0 ? kp : (int)Kp) + (uint32_t)koff + k] = __float2bfloat16_rn(v);
+    } else {
+      crsk[j] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -166,7 +173,8 @@ __global__ void __launch_bounds__(TPB) weight_prepare_batch_kernel(const SgbWeig
   SGB_GRID_DEP_LAUNCH();
   SGB_GRID_DEP_WAIT();
   batch_walk(items, n, total, [](const SgbWeightItem& it, int64_t local) {
-    weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f, it.add_identity, local);
+    weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f, it.add_identity, local, it.kp,
+                        it.koff, it.etaps, it.etap);
   });
 }
 

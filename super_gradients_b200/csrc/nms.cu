@@ -74,10 +74,16 @@ __device__ void hist_pass(const float* __restrict__ sc, int seg0, int seg1, floa
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       int idx = base + u * 32 + lane;
+      // Detector scores crowd a few exponents (sigmoid of logits around the -4.6 prior), so most lanes of a warp hit the same
+      // handful of bins: lanes with equal bins elect one to add their count (one shared-memory atomic per distinct bin per warp
+      // instead of one per lane -- the same-address atomics were the whole cost of the histogram passes).
+      unsigned bin = 0xffffffffu;
       if (idx < seg1 && passes(v[u], thr, incl)) {
         unsigned k = okey(v[u]);
-        if ((k & prefix_mask) == prefix) atomicAdd(&hist[(k >> shift) & ((1u << BITS) - 1)], 1);
+        if ((k & prefix_mask) == prefix) bin = (k >> shift) & ((1u << BITS) - 1);
       }
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
     }
   }
 }
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(NT, 1) nms_mask_kernel(SgbNmsDesc d, const Nms
   unsigned long long* mrow = masks + (int64_t)b * KMAX * (KMAX / 64);
   const int rows = min(MASK_ROWS, nsel - i0);
   for (int pair = t; pair < rows * nw; pair += NT) {
-    const int i = i0 + pair / nw, w = pair % nw;
+    const int w = pair / rows, i = i0 + pair % rows;  // consecutive lanes: consecutive rows of ONE word -> box j is a broadcast read
     unsigned long long bits = 0ull;
     if (w * 64 + 63 > i) {
       const float ix1 = bx[0][i], iy1 = bx[1][i], ix2 = bx[2][i], iy2 = bx[3][i], ia = area[i];
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(NT, 1) nms_kernel(SgbNmsDesc d, const float* _
   // ---- IoU bit matrix: mask[i][w] bit j: j > i, suppressed by i
   const bool same_class_only = !d.class_agnostic && !trick_flag;
   for (int pair = t; pair < nsel * nw; pair += NT) {
-    int i = pair / nw, w = pair - i * nw;
+    int w = pair / nsel, i = pair - w * nsel;  // consecutive lanes: consecutive rows of ONE word -> box j is a broadcast read
     unsigned long long bits = 0ull;
     if (w * 64 + 63 > i) {
       float ix1 = S.bx[0][i], iy1 = S.bx[1][i], ix2 = S.bx[2][i], iy2 = S.bx[3][i], ia = S.area[i];

@@ -104,24 +104,37 @@ class WeightCache:
             _CTX[0].caches.setdefault(id(self), self)
         return self.krsc, self.crsk
 
+    # -- the train step's batched refresh (refresh_weight_caches): one work-table entry per filter
+    def batch_ready(self, dev) -> bool:
+        return self.args is not None and self.krsc is not None and self.args[0].device == dev and self.args[0].dtype == torch.float32 and self.args[0].is_contiguous()
+
+    def batch_ident(self):
+        a = self.args
+        return (a[0].data_ptr(), self.krsc.data_ptr(), None if self.crsk is None else self.crsk.data_ptr(), None if a[1] is None else a[1].data_ptr(), a[2], a[4])
+
+    def batch_entries(self):
+        return [(self.args[0], self.args[1], self.krsc, self.crsk, self.krsc.shape[3], self.args[2])]
+
+    def mark_current(self):
+        self.key = WeightCache._key(*self.args)
+
 
 def refresh_weight_caches(ctx: StepContext, device) -> int:
     """Re-prepares every filter the context's model uses with ONE batched launch (instead of one launch per layer on
     first use) and marks those caches current.  Called by the train step after the optimizer moved the weights."""
-    live = [c for c in ctx.caches.values() if c.args is not None and c.krsc is not None]
     dev = torch.device(device)
-    live = [c for c in live if c.args[0].device == dev and c.args[0].dtype == torch.float32 and c.args[0].is_contiguous()]
+    live = [c for c in ctx.caches.values() if c.batch_ready(dev)]
     if not live:
         return 0
-    ident = tuple((c.args[0].data_ptr(), c.krsc.data_ptr(), None if c.crsk is None else c.crsk.data_ptr(), None if c.args[1] is None else c.args[1].data_ptr(), c.args[2], c.args[4]) for c in live)
+    ident = tuple(c.batch_ident() for c in live)
     if ctx.weight_key != ident:
-        entries = [(c.args[0], c.args[1], c.krsc, c.crsk, c.krsc.shape[3], c.args[2]) for c in live]
+        entries = [e for c in live for e in c.batch_entries()]
         ctx.weight_table = K.weight_prepare_batch(entries, device)
         ctx.weight_key = ident
     table, n, total = ctx.weight_table
     K.run_weight_prepare_batch(table, n, total)
     for c in live:
-        c.key = WeightCache._key(*c.args)
+        c.mark_current()
     return n
 
 
@@ -166,12 +179,13 @@ def flush_wgrads(ctx: StepContext, device) -> int:
     return n + len(rest)
 
 
-# Experiment (off unless SGB_QAREP_FOLD=1): a stride-1 QARepVGG block runs its 1x1 branch as the centre tap of ONE 3x3 convolution
-# with 2K output channels (rows [0, K) = the 3x3 filters, rows [K, 2K) = alpha * K1 + I embedded at the centre), so y3 and u come
-# out of one halo-kernel launch that reads x once, dgrad consumes [dy3 | du] in one launch (no accumulate pass) and wgrad produces
-# both gradients in one launch (for K <= 64 inside the M = 128 padding the 3x3 weight gradient already pays for).  Only verified
-# kernels are involved; tools/next_round_gpu_plan.sh benches it.
-QAREP_FOLD = [__import__("os").environ.get("SGB_QAREP_FOLD") == "1"]
+# Folded QARepVGG (default; SGB_QAREP_FOLD=0 restores the two-convolution form): a stride-1 block runs its 1x1 branch as the centre tap
+# of ONE 3x3 convolution with 2K output channels (rows [0, K) = the 3x3 filters, rows [K, 2K) = alpha * K1 + I embedded at the centre),
+# so y3 and u come out of one halo-kernel launch that reads x once, dgrad consumes [dy3 | du] in one launch (no accumulating
+# epilogue) and wgrad produces both gradients in one launch (for K <= 64 inside the M = 128 padding the 3x3 weight gradient pays
+# for anyway).  Measured on B200 (YOLO-NAS-S, batch 32): 1679 -> 1722 img/s, 830 -> 718 launches per step, once the folded filters
+# are written in place by the step's batched re-layout launch (FoldedWeightCache) and the weight gradient goes to the side stream.
+QAREP_FOLD = [__import__("os").environ.get("SGB_QAREP_FOLD", "1") != "0"]
 QAREP_FOLD_MAXPIX = [int(__import__("os").environ.get("SGB_QAREP_FOLD_MAXPIX", "0"))]  # > 0: fold only maps of at most this many pixels (N*H*W)
 _FOLD_CHANNELS = (32, 48, 64, 96, 128, 192)  # channel counts the halo-tile kernels are instantiated for
 
@@ -181,27 +195,65 @@ def qarep_fold_supported(cin: int, x_channels: int, kout: int, stride: int) -> b
 
 
 class FoldedWeightCache:
-    """fp32 OIHW [2K, C, 3, 3] staging of (K3 ; centre(alpha * K1 + I)) + its bf16 KRSC / CRSK copies, refreshed when a source changes."""
+    """bf16 KRSC [2K, 3, 3, C] / CRSK [C, 3, 3, 2K] of the folded filter (K3 ; centre(alpha * K1 + I)), written in place from the two
+    fp32 parameters by two work-table entries of the batched filter re-layout (SgbWeightItem kp / koff / etaps / etap): inside a
+    train step they ride in the step's ONE sgb_weight_prepare_batch launch, outside one the cache launches its own two-entry
+    table.  The destination's never-written entries (the eight outer taps of rows [K, 2K)) stay zero from the allocation."""
 
     def __init__(self):
         self.key = None
-        self.stage = None
-        self.inner = WeightCache(batched=False)
+        self.krsc = None
+        self.crsk = None
+        self.src = None    # (w3, w1, alpha, add_identity, c_pad)
+        self.table = None  # own two-entry table (and the identity it was built for)
+        self.table_ident = None
+
+    def _key(self):
+        w3, w1, alpha, add_identity, c_pad = self.src
+        return (WeightCache._key(w3, None, False, None, c_pad), WeightCache._key(w1, alpha, add_identity, None, c_pad))
 
     def get(self, w3, w1, alpha, add_identity, c_pad):
-        key = (WeightCache._key(w3, None, False, None, c_pad), WeightCache._key(w1, alpha, add_identity, None, c_pad))
+        self.src = (w3, w1, alpha, add_identity, c_pad)
+        kout, cin = w3.shape[0], w3.shape[1]
+        if c_pad != cin:
+            raise K.L.SgbError("folded QARepVGG filter: the input tensor must have exactly the filter's channel count")
+        if self.krsc is None or tuple(self.krsc.shape) != (2 * kout, 3, 3, c_pad) or self.krsc.device != w3.device:
+            self.krsc = torch.zeros((2 * kout, 3, 3, c_pad), dtype=torch.bfloat16, device=w3.device)
+            self.crsk = torch.zeros((cin, 3, 3, 2 * kout), dtype=torch.bfloat16, device=w3.device)
+            self.key = None
+        key = self._key()
         if key != self.key:
-            kout, cin = w3.shape[0], w3.shape[1]
-            with torch.no_grad():
-                if self.stage is None or tuple(self.stage.shape) != (2 * kout, cin, 3, 3) or self.stage.device != w3.device:
-                    self.stage = torch.zeros((2 * kout, cin, 3, 3), dtype=torch.float32, device=w3.device)
-                self.stage[:kout].copy_(w3.detach())
-                centre = w1.detach()[:, :, 0, 0] * alpha.detach() if alpha is not None else w1.detach()[:, :, 0, 0].clone()
-                if add_identity:
-                    centre.diagonal().add_(1.0)
-                self.stage[kout:, :, 1, 1].copy_(centre)
+            ident = self.batch_ident()
+            if self.table_ident != ident:
+                self.table = K.weight_prepare_batch(self.batch_entries(), w3.device)
+                self.table_ident = ident
+            K.run_weight_prepare_batch(*self.table)
             self.key = key
-        return self.inner.get(self.stage, c_pad=c_pad, extra_key=key)
+        if _CTX[0] is not None:
+            _CTX[0].caches.setdefault(id(self), self)
+        return self.krsc, self.crsk
+
+    def batch_ready(self, dev) -> bool:
+        if self.src is None or self.krsc is None:
+            return False
+        w3, w1 = self.src[0], self.src[1]
+        return all(t.device == dev and t.dtype == torch.float32 and t.is_contiguous() for t in (w3, w1))
+
+    def batch_ident(self):
+        w3, w1, alpha, add_identity, c_pad = self.src
+        return (w3.data_ptr(), w1.data_ptr(), None if alpha is None else alpha.data_ptr(), add_identity, self.krsc.data_ptr(), self.crsk.data_ptr())
+
+    def batch_entries(self):
+        w3, w1, alpha, add_identity, c_pad = self.src
+        kout = w3.shape[0]
+        w1_4d = w1 if w1.dim() == 4 else w1.view(w1.shape[0], w1.shape[1], 1, 1)
+        return [
+            (w3, None, self.krsc[:kout], self.crsk, c_pad, False, (2 * kout, 0, 0, 0)),                # rows [0, K): the 3x3 filter
+            (w1_4d, alpha, self.krsc[kout:], self.crsk, c_pad, bool(add_identity), (2 * kout, kout, 9, 4)),  # rows [K, 2K): centre tap
+        ]
+
+    def mark_current(self):
+        self.key = self._key()
 
 
 # ------------------------------------------------------------------------------------------------ shared input gradients

@@ -266,12 +266,14 @@ def weight_prepare_batch(entries, device) -> torch.Tensor:
     """entries: (w fp32 OIHW, scale or None, krsc, crsk or None, c_pad, add_identity).  Returns the device item table
     to pass to run_weight_prepare_batch (build once, replay every step)."""
     items, start = [], 0
-    for w, scale, krsc, crsk, c_pad, add_identity in entries:
+    for w, scale, krsc, crsk, c_pad, add_identity, *extra in entries:
         Kk, C, R, S = w.shape
         it = L.WeightItem()
         it.w, it.scale, it.krsc, it.crsk = w.data_ptr(), (scale.data_ptr() if scale is not None else None), krsc.data_ptr(), (crsk.data_ptr() if crsk is not None else None)
         it.K, it.C, it.R, it.S, it.c_pad, it.add_identity, it.start = Kk, C, R, S, c_pad, 1 if add_identity else 0, start
-        start += krsc.numel() + (crsk.numel() if crsk is not None else 0)
+        # optional 7th element: placement inside a wider destination filter (SgbWeightItem: kp, koff, etaps, etap)
+        it.kp, it.koff, it.etaps, it.etap = extra[0] if extra else (0, 0, 0, 0)
+        start += Kk * R * S * c_pad + (C * R * S * (((Kk + 7) // 8) * 8) if crsk is not None else 0)  # the kernel walks the SOURCE-shaped index space
         items.append(it)
     return _item_table(items).to(device), len(items), start
 

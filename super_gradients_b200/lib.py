@@ -34,7 +34,7 @@ class Epilogue(Structure):
 
 
 class WeightItem(Structure):  # SgbWeightItem
-    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("krsc", c_void_p), ("crsk", c_void_p)] + [(n, c_int32) for n in ("K", "C", "R", "S", "c_pad", "add_identity")] + [("start", c_int64)]
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("krsc", c_void_p), ("crsk", c_void_p)] + [(n, c_int32) for n in ("K", "C", "R", "S", "c_pad", "add_identity", "kp", "koff", "etaps", "etap")] + [("start", c_int64)]
 
 
 class WgradItem(Structure):  # SgbWgradItem

@@ -246,11 +246,23 @@ def weight_prepare_batch(entries, device):
 
 def run_weight_prepare_batch(table, n, total):
     assert len(table) == n
-    for w, scale, krsc, crsk, c_pad, add_identity in table:
+    for w, scale, krsc, crsk, c_pad, add_identity, *extra in table:
         k2, c2 = weight_prepare(w, c_pad=c_pad, want_crsk=crsk is not None, scale=scale, add_identity=add_identity)
-        krsc.copy_(k2)
-        if crsk is not None:
-            crsk.copy_(c2)
+        kp, koff, etaps, etap = extra[0] if extra else (0, 0, 0, 0)
+        Kk = w.shape[0]
+        if etaps:  # 1x1 source = tap `etap` of an etaps-tap destination (krsc: this filter's rows of the wider KRSC, crsk: the wider CRSK)
+            r, s = divmod(etap, int(round(etaps**0.5)))
+            krsc[:, r, s, :].copy_(k2[:, 0, 0, :])
+            if crsk is not None:
+                crsk[:, r, s, koff : koff + Kk].copy_(c2[:, 0, 0, :Kk])
+        elif kp:
+            krsc.copy_(k2)
+            if crsk is not None:
+                crsk[..., koff : koff + Kk].copy_(c2[..., :Kk])
+        else:
+            krsc.copy_(k2)
+            if crsk is not None:
+                crsk.copy_(c2)
 
 
 def wgrad_to_oihw_batch_table(entries, device):

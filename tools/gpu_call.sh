@@ -72,6 +72,13 @@ case "${1}" in
     done
     timeout 300 python tools/mem_kernels.py > gpurun_out/r2_mem_kernels11.txt 2>gpurun_out/r2_mem_kernels11.err; cat gpurun_out/r2_mem_kernels11.txt; tail -3 gpurun_out/r2_mem_kernels11.err
     timeout 300 python tools/conv_table.py --top 300 > gpurun_out/r2_conv_table11.txt 2>gpurun_out/r2_conv_table11.err; head -8 gpurun_out/r2_conv_table11.txt; tail -3 gpurun_out/r2_conv_table11.err ;;
+  twelfth)  # in-place batched folded filters; NMS kernel breakdown
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest12.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest12.log
+    for v in "SGB_QAREP_FOLD=0" "SGB_QAREP_FOLD=1"; do
+      printf "%s: " "$v"; env $v timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench12.err | tee "gpurun_out/r2_bench12_$(echo $v | tr ' =' '__').json" | bench_line; tail -2 gpurun_out/r2_bench12.err
+    done
+    timeout 300 python tools/mem_kernels.py --breakdown > gpurun_out/r2_mem_kernels12.txt 2>gpurun_out/r2_mem_kernels12.err; cat gpurun_out/r2_mem_kernels12.txt; tail -3 gpurun_out/r2_mem_kernels12.err
+    SGB_QAREP_FOLD=1 timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline12_launches.txt > gpurun_out/r2_timeline12.txt 2>gpurun_out/r2_timeline12.err; head -40 gpurun_out/r2_timeline12.txt; tail -3 gpurun_out/r2_timeline12.err ;;
   multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
     N=${2:-2}
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \

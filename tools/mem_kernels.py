@@ -35,6 +35,7 @@ def anchors(img=640, strides=(8, 16, 32)):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--breakdown", action="store_true", help="also list the kernels of one NMS call with their durations")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -90,6 +91,18 @@ def main():
             K.PROFILE_ON[0] = False
             if on:
                 record(tag)
+    if args.breakdown:  # kernels of one detection / pose NMS call (CUPTI records through torch.profiler)
+        from torch.profiler import ProfilerActivity, profile
+
+        for tag, fn in (("det nms B=32", lambda: det_cb.forward_batched((pb, ps))), ("pose nms B=64", lambda: pose_cb.forward_batched((pose_in, None)))):
+            flush.zero_()
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fn()
+                torch.cuda.synchronize()
+            print(f"-- kernels of one `{tag}` call")
+            for e in sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start):
+                print(f"   {e.time_range.end - e.time_range.start:9.1f} us  {e.name[:90]}")
     kept_det = float(det_cb.forward_batched((pb, ps))[2].float().mean())
     kept_pose = float(pose_cb.forward_batched((pose_in, None))[3].float().mean())
     hbm = bench.peaks()[1]
