@@ -79,6 +79,14 @@ case "${1}" in
     done
     timeout 300 python tools/mem_kernels.py --breakdown > gpurun_out/r2_mem_kernels12.txt 2>gpurun_out/r2_mem_kernels12.err; cat gpurun_out/r2_mem_kernels12.txt; tail -3 gpurun_out/r2_mem_kernels12.err
     SGB_QAREP_FOLD=1 timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline12_launches.txt > gpurun_out/r2_timeline12.txt 2>gpurun_out/r2_timeline12.err; head -40 gpurun_out/r2_timeline12.txt; tail -3 gpurun_out/r2_timeline12.err ;;
+  thirteenth)  # fold default; NMS atomics / mapping fixes
+    timeout 700 python -m pytest tests -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest13.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest13.log
+    printf "default: "; timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench13.err | tee gpurun_out/r2_bench13.json | bench_line; tail -2 gpurun_out/r2_bench13.err
+    timeout 300 python tools/mem_kernels.py --breakdown > gpurun_out/r2_mem_kernels13.txt 2>gpurun_out/r2_mem_kernels13.err; cat gpurun_out/r2_mem_kernels13.txt; tail -3 gpurun_out/r2_mem_kernels13.err
+    for c in 3 4 5; do printf "config %d: " $c; timeout 400 python bench.py --config $c --steps 10 --warmup 3 --skip-cpu-baseline 2>gpurun_out/r2_bench13_c$c.err | tee gpurun_out/r2_bench13_c$c.json | bench_line; tail -2 gpurun_out/r2_bench13_c$c.err; done ;;
+  ncu_nms)  # ncu --set full of the NMS kernels (detection callback at benchmark size)
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"nms_" -c 6 -o gpurun_out/r2_full_nms -f python tools/mem_kernels.py --reps 1 > gpurun_out/r2_ncu_full_nms.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/r2_ncu_full_nms.log
+    ls -la gpurun_out/*.ncu-rep ;;
   multi)  # N GPUs (gpurun --gpus N): the BASELINE bench + the in-situ timeline of every rank (all-reduce duration, skew)
     N=${2:-2}
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --skip-cpu-baseline \
