@@ -168,6 +168,10 @@ typedef struct SgbBnDesc {
    * n = pixel / hw; sample_scale holds 0 or 1/keep_prob per image.  NULL: no drop-path. */
   int64_t hw;
   const float* sample_scale;
+  /* backward passes of two layers that share one GEMM (functional._DualConvBnAct: the two 1x1 convolutions of a CSP layer run as one
+   * GEMM with concatenated output channels): channels [dy2_split, C) of dy come from a second tensor.  dy2 == NULL: one source. */
+  int32_t dy2_split, dy2_pitch, dy2_off, dy2_reserved;
+  const void* dy2;
 } SgbBnDesc;
 /* Reduces stats -> mean / rstd (saved for backward), updates running stats, writes y = act(bn(x) + residual). */
 int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const double* stats, const float* gamma, const float* beta,
@@ -227,6 +231,11 @@ int sgb_qarep_bwd_apply(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_b
 int sgb_bn_act_bwd_fused(const SgbBnDesc* d, const sgb_bf16* dy, const sgb_bf16* x, const sgb_bf16* y, const float* gamma,
                          const float* beta, const float* save_mean, const float* save_rstd, double* sums, sgb_bf16* dx,
                          sgb_bf16* dresidual, float* dgamma, float* dbeta, void* stream);
+/* Per-channel sums of x + sgb_bn_act_fwd as ONE cooperative launch, for convolutions whose epilogue produced no statistics (more than
+ * 96 output channels); `stats` ([stats_repl][2][C]) must be zero on entry.  Same reference lines as sgb_bn_act_fwd. */
+int sgb_bn_act_fwd_fused(const SgbBnDesc* d, const sgb_bf16* x, double* stats, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, const sgb_bf16* residual, sgb_bf16* y, float* save_mean,
+                         float* save_rstd, void* stream);
 int sgb_qarep_bwd_fused(const SgbQarepDesc* d, const sgb_bf16* dout, const sgb_bf16* y3, const sgb_bf16* u, const float* coef,
                         double* sums, const float* gamma3, const float* gamma_p, sgb_bf16* dy3, sgb_bf16* du, float* dgamma3,
                         float* dbeta3, float* dbias1a, float* dgamma_p, float* dbeta_p, void* stream);

@@ -35,7 +35,7 @@ __device__ __forceinline__ void st8(bf16* p, const V8& a) {
 //   static constexpr int NIN, UNROLL, DEPTH;    16-byte input vectors per pixel / pixels per ring slot / ring slots per thread
 //   __device__ void prologue(float* sc) const;  all threads of the CTA; fills sc[NCOEF][C]
 //   __device__ const bf16* base(int j, int c0) const;  address of input j at pixel 0, channel c0 (nullptr: input absent)
-//   __device__ int pitch(int j) const;                 its pixel pitch in elements
+//   __device__ int pitch(int j, int c0) const;         its pixel pitch in elements (may depend on the channel: two-source dy)
 //   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[NIN], const float (&r)[NCOEF][8], float (&acc)[NACC or 1][8]) const;
 //   double* out; int out_stride;                (only when NACC > 0)
 //
@@ -103,8 +103,8 @@ __device__ __forceinline__ void chan_body(const Op& op, const int64_t M, const i
 #pragma unroll
       for (int j = 0; j < NIN; ++j) {
         const bf16* b = op.base(j, c0);
-        kstep[j] = (int64_t)lanes * op.pitch(j);
-        ptr[j] = b ? b + first * op.pitch(j) : nullptr;
+        kstep[j] = (int64_t)lanes * op.pitch(j, c0);
+        ptr[j] = b ? b + first * op.pitch(j, c0) : nullptr;
       }
       sgb_ring::walk<NIN, U, D, TPB>(my_ring, ptr, kstep, mine, [&](int64_t q, const uint4(&raw)[NIN]) { op.finish(first + q * lanes, c0, raw, r, acc); });
     }
@@ -211,6 +211,29 @@ int launch_chan(const Op& op, int64_t M, int C, cudaStream_t st, const char* wha
 }
 
 // ============================================================================================== BatchNorm forward
+// Per-channel sum / sum of squares of the stored bf16 values as a pass of the same skeleton: first half of sgb_bn_act_fwd_fused, for
+// the layers whose GEMM epilogue has no register-held statistics (more than 96 output channels) -- all of them small enough at
+// YOLO-NAS sizes for the apply pass's re-read to hit L2.
+struct BnStatsOp {
+  static constexpr int NCOEF = 0, NACC = 2;
+  SgbBnDesc d;
+  const bf16* x;
+  double* out;
+  int out_stride;
+  __device__ void prologue(float*) const {}
+  static constexpr int NIN = 1, UNROLL = 4, DEPTH = 4;
+  __device__ const bf16* base(int, int c0) const { return x + d.x_off + c0; }
+  __device__ int pitch(int, int) const { return d.x_pitch; }
+  __device__ void finish(int64_t, int, const uint4 (&raw)[1], const float (&)[1][8], float (&acc)[2][8]) const {
+    const V8 a = unpack8(raw[0]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] += a.v[e];
+      acc[1][e] = fmaf(a.v[e], a.v[e], acc[1][e]);
+    }
+  }
+};
+
 struct BnFwdOp {
   static constexpr int NCOEF = 2, NACC = 0;
   SgbBnDesc d;
@@ -225,9 +248,9 @@ struct BnFwdOp {
     const int C = d.C;
     for (int c = threadIdx.x; c < C; c += TPB) {
       double s1 = 0, s2 = 0;
-      for (int r = 0; r < d.stats_repl; ++r) {
-        s1 += stats[(int64_t)r * 2 * C + c];
-        s2 += stats[(int64_t)r * 2 * C + C + c];
+      for (int r = 0; r < d.stats_repl; ++r) {  // L2 reads: in the fused launch other CTAs produced the sums just before the grid barrier
+        s1 += __ldcg(stats + (int64_t)r * 2 * C + c);
+        s2 += __ldcg(stats + (int64_t)r * 2 * C + C + c);
       }
       const double mean = s1 / (double)d.M;
       double var = s2 / (double)d.M - mean * mean;
@@ -249,7 +272,7 @@ struct BnFwdOp {
   }
   static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
   __device__ const bf16* base(int j, int c0) const { return j == 0 ? x + d.x_off + c0 : (res ? res + d.r_off + c0 : nullptr); }
-  __device__ int pitch(int j) const { return j == 0 ? d.x_pitch : d.r_pitch; }
+  __device__ int pitch(int j, int) const { return j == 0 ? d.x_pitch : d.r_pitch; }
   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[2][8], float (&)[1][8]) const {
     V8 a = unpack8(raw[0]);
     struct {
@@ -290,7 +313,7 @@ struct BnInferOp {
   }
   static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
   __device__ const bf16* base(int j, int c0) const { return j == 0 ? x + d.x_off + c0 : (res ? res + d.r_off + c0 : nullptr); }
-  __device__ int pitch(int j) const { return j == 0 ? d.x_pitch : d.r_pitch; }
+  __device__ int pitch(int j, int) const { return j == 0 ? d.x_pitch : d.r_pitch; }
   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[2][8], float (&)[1][8]) const {
     V8 a = unpack8(raw[0]);
     struct {
@@ -329,11 +352,17 @@ struct BnBwdRedOp {
   }
   static constexpr int NIN = 3, UNROLL = 2, DEPTH = 5;
   __device__ const bf16* base(int j, int c0) const {
-    if (j == 0) return dy + (d.dy_pitch ? d.dy_off : d.y_off) + c0;
+    if (j == 0) {
+      if (d.dy2 && c0 >= d.dy2_split) return reinterpret_cast<const bf16*>(d.dy2) + d.dy2_off + (c0 - d.dy2_split);
+      return dy + (d.dy_pitch ? d.dy_off : d.y_off) + c0;
+    }
     if (j == 1) return x + d.x_off + c0;
     return y ? y + d.y_off + c0 : nullptr;
   }
-  __device__ int pitch(int j) const { return j == 0 ? (d.dy_pitch ? d.dy_pitch : d.y_pitch) : (j == 1 ? d.x_pitch : d.y_pitch); }
+  __device__ int pitch(int j, int c0) const {
+    if (j == 0) return (d.dy2 && c0 >= d.dy2_split) ? d.dy2_pitch : (d.dy_pitch ? d.dy_pitch : d.y_pitch);
+    return j == 1 ? d.x_pitch : d.y_pitch;
+  }
   __device__ void finish(int64_t pix, int, const uint4 (&raw)[3], const float (&r)[4][8], float (&acc)[2][8]) const {
     const V8 g = unpack8(raw[0]), xv = unpack8(raw[1]);
     V8 yv;
@@ -383,11 +412,17 @@ struct BnBwdApplyOp {
   }
   static constexpr int NIN = 3, UNROLL = 2, DEPTH = 5;
   __device__ const bf16* base(int j, int c0) const {
-    if (j == 0) return dy + (d.dy_pitch ? d.dy_off : d.y_off) + c0;
+    if (j == 0) {
+      if (d.dy2 && c0 >= d.dy2_split) return reinterpret_cast<const bf16*>(d.dy2) + d.dy2_off + (c0 - d.dy2_split);
+      return dy + (d.dy_pitch ? d.dy_off : d.y_off) + c0;
+    }
     if (j == 1) return x + d.x_off + c0;
     return y ? y + d.y_off + c0 : nullptr;
   }
-  __device__ int pitch(int j) const { return j == 0 ? (d.dy_pitch ? d.dy_pitch : d.y_pitch) : (j == 1 ? d.x_pitch : d.y_pitch); }
+  __device__ int pitch(int j, int c0) const {
+    if (j == 0) return (d.dy2 && c0 >= d.dy2_split) ? d.dy2_pitch : (d.dy_pitch ? d.dy_pitch : d.y_pitch);
+    return j == 1 ? d.x_pitch : d.y_pitch;
+  }
   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[3], const float (&r)[6][8], float (&)[1][8]) const {
     const V8 g = unpack8(raw[0]), xv = unpack8(raw[1]);
     V8 yv;
@@ -424,7 +459,7 @@ struct QarepMomOp {
   __device__ void prologue(float*) const {}
   static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;
   __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + d.off3 + c0 : u + d.offu + c0; }
-  __device__ int pitch(int j) const { return j == 0 ? d.pitch3 : d.pitchu; }
+  __device__ int pitch(int j, int) const { return j == 0 ? d.pitch3 : d.pitchu; }
   __device__ void finish(int64_t, int, const uint4 (&raw)[2], const float (&)[1][8], float (&acc)[5][8]) const {
     const V8 a = unpack8(raw[0]), b = unpack8(raw[1]);
 #pragma unroll
@@ -507,7 +542,7 @@ struct QarepFwdOp {
   }
   static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
   __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + d.off3 + c0 : u + d.offu + c0; }
-  __device__ int pitch(int j) const { return j == 0 ? d.pitch3 : d.pitchu; }
+  __device__ int pitch(int j, int) const { return j == 0 ? d.pitch3 : d.pitchu; }
   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[3][8], float (&)[1][8]) const {
     V8 a = unpack8(raw[0]);
     const V8 b = unpack8(raw[1]);
@@ -543,7 +578,7 @@ struct QarepBwdRedOp {
     if (j == 0) return dout + (d.pitchd ? d.offd : d.offo) + c0;
     return j == 1 ? y3 + d.off3 + c0 : u + d.offu + c0;
   }
-  __device__ int pitch(int j) const { return j == 0 ? (d.pitchd ? d.pitchd : d.pitcho) : (j == 1 ? d.pitch3 : d.pitchu); }
+  __device__ int pitch(int j, int) const { return j == 0 ? (d.pitchd ? d.pitchd : d.pitcho) : (j == 1 ? d.pitch3 : d.pitchu); }
   __device__ void finish(int64_t, int, const uint4 (&raw)[3], const float (&r)[8][8], float (&acc)[3][8]) const {
     const V8 g = unpack8(raw[0]), a = unpack8(raw[1]), b = unpack8(raw[2]);
 #pragma unroll
@@ -617,7 +652,7 @@ struct QarepBwdApplyOp {
     if (j == 0) return dout + (d.pitchd ? d.offd : d.offo) + c0;
     return j == 1 ? y3 + d.off3 + c0 : u + d.offu + c0;
   }
-  __device__ int pitch(int j) const { return j == 0 ? (d.pitchd ? d.pitchd : d.pitcho) : (j == 1 ? d.pitch3 : d.pitchu); }
+  __device__ int pitch(int j, int) const { return j == 0 ? (d.pitchd ? d.pitchd : d.pitcho) : (j == 1 ? d.pitch3 : d.pitchu); }
   __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[3], const float (&r)[12][8], float (&)[1][8]) const {
     const V8 g = unpack8(raw[0]), a = unpack8(raw[1]), b = unpack8(raw[2]);
     V8 o3, ou;
@@ -650,7 +685,10 @@ int check_bn(const SgbBnDesc* d) {
               "pitch/offset multiples of 8");
   SGB_REQUIRE(d->C <= 4096, "C too large for the shared-memory coefficient cache");
   SGB_REQUIRE(!d->sample_scale || (d->hw > 0 && d->M % d->hw == 0), "drop-path: hw must divide M");
-  SGB_REQUIRE(d->dy_pitch % 8 == 0 && d->dy_off % 8 == 0 && (d->dy_pitch == 0 || d->dy_pitch >= d->dy_off + d->C), "dy slice layout");
+  SGB_REQUIRE(d->dy_pitch % 8 == 0 && d->dy_off % 8 == 0 && (d->dy_pitch == 0 || d->dy_pitch >= d->dy_off + (d->dy2 ? d->dy2_split : d->C)), "dy slice layout");
+  SGB_REQUIRE(!d->dy2 || (d->dy2_split > 0 && d->dy2_split < d->C && d->dy2_split % 8 == 0 && d->dy2_pitch % 8 == 0 && d->dy2_off % 8 == 0 &&
+                          d->dy2_pitch >= d->dy2_off + d->C - d->dy2_split && ((uintptr_t)d->dy2 & 15) == 0),
+              "second dy source layout");
   return SGB_OK;
 }
 int check_qarep(const SgbQarepDesc* d) {
@@ -672,6 +710,19 @@ extern "C" int sgb_bn_act_fwd(const SgbBnDesc* d, const sgb_bf16* x, const doubl
   SGB_REQUIRE(d->stats_repl >= 1, "stats_repl");
   BnFwdOp op{*d, (const bf16*)x, (const bf16*)residual, (bf16*)y, stats, gamma, beta, running_mean, running_var, save_mean, save_rstd};
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "bn_act_fwd");
+}
+
+// sgb_channel-statistics + sgb_bn_act_fwd as ONE cooperative launch (sums, grid-wide barrier, apply): `stats` ([stats_repl][2][C]) must be
+// zero on entry; the sums land in replica 0.
+extern "C" int sgb_bn_act_fwd_fused(const SgbBnDesc* d, const sgb_bf16* x, double* stats, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, const sgb_bf16* residual, sgb_bf16* y, float* save_mean,
+                                    float* save_rstd, void* stream) {
+  if (int rc = check_bn(d)) return rc;
+  SGB_REQUIRE(x && stats && y && save_mean && save_rstd, "null pointer");
+  SGB_REQUIRE(d->stats_repl >= 1, "stats_repl");
+  BnStatsOp so{*d, (const bf16*)x, stats, d->C};
+  BnFwdOp op{*d, (const bf16*)x, (const bf16*)residual, (bf16*)y, stats, gamma, beta, running_mean, running_var, save_mean, save_rstd};
+  return launch_chan_fused(so, op, d->M, d->C, (cudaStream_t)stream, "bn_act_fwd_fused");
 }
 
 extern "C" int sgb_bn_act_infer(const SgbBnDesc* d, const sgb_bf16* x, const float* gamma, const float* beta,

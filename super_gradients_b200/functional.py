@@ -256,6 +256,66 @@ class FoldedWeightCache:
         self.key = self._key()
 
 
+class ConcatWeightCache:
+    """bf16 KRSC [K1 + K2, R, S, C] / CRSK [C, R, S, K1 + K2] of two filters applied to the same input (the two 1x1 convolutions of a
+    CSP layer as ONE GEMM), written in place from the two fp32 parameters by two entries of the batched filter re-layout, exactly like
+    FoldedWeightCache (SgbWeightItem kp / koff)."""
+
+    def __init__(self):
+        self.key = None
+        self.krsc = None
+        self.crsk = None
+        self.src = None    # (w1, w2, c_pad)
+        self.table = None
+        self.table_ident = None
+
+    def _key(self):
+        w1, w2, c_pad = self.src
+        return (WeightCache._key(w1, None, False, None, c_pad), WeightCache._key(w2, None, False, None, c_pad))
+
+    def get(self, w1, w2, c_pad):
+        self.src = (w1, w2, c_pad)
+        k1, cin, r, s_ = w1.shape
+        k2 = w2.shape[0]
+        if tuple(w2.shape[1:]) != (cin, r, s_) or k1 % 8 != 0 or k2 % 8 != 0:
+            raise K.L.SgbError("concatenated filters need equal input channels / taps and multiples of 8 output channels")
+        if self.krsc is None or tuple(self.krsc.shape) != (k1 + k2, r, s_, c_pad) or self.krsc.device != w1.device:
+            self.krsc = torch.zeros((k1 + k2, r, s_, c_pad), dtype=torch.bfloat16, device=w1.device)
+            self.crsk = torch.zeros((c_pad, r, s_, k1 + k2), dtype=torch.bfloat16, device=w1.device)
+            self.key = None
+        key = self._key()
+        if key != self.key:
+            ident = self.batch_ident()
+            if self.table_ident != ident:
+                self.table = K.weight_prepare_batch(self.batch_entries(), w1.device)
+                self.table_ident = ident
+            K.run_weight_prepare_batch(*self.table)
+            self.key = key
+        if _CTX[0] is not None:
+            _CTX[0].caches.setdefault(id(self), self)
+        return self.krsc, self.crsk
+
+    def batch_ready(self, dev) -> bool:
+        if self.src is None or self.krsc is None:
+            return False
+        return all(t.device == dev and t.dtype == torch.float32 and t.is_contiguous() for t in self.src[:2])
+
+    def batch_ident(self):
+        w1, w2, c_pad = self.src
+        return (w1.data_ptr(), w2.data_ptr(), c_pad, self.krsc.data_ptr(), self.crsk.data_ptr())
+
+    def batch_entries(self):
+        w1, w2, c_pad = self.src
+        k1, k2 = w1.shape[0], w2.shape[0]
+        return [
+            (w1, None, self.krsc[:k1], self.crsk, c_pad, False, (k1 + k2, 0, 0, 0)),
+            (w2, None, self.krsc[k1:], self.crsk, c_pad, False, (k1 + k2, k1, 0, 0)),
+        ]
+
+    def mark_current(self):
+        self.key = self._key()
+
+
 # ------------------------------------------------------------------------------------------------ shared input gradients
 # An activation consumed by several fused blocks (the two 1 x 1 convolutions of a CSP layer, a bottleneck's first block and its
 # shortcut, a backbone feature feeding the next stage and the neck, a head stem feeding the cls / reg branches) receives one
@@ -324,6 +384,64 @@ def _share_dx(tok, fresh, accumulate):
         return buf
     tok.buf = buf
     return None
+
+
+# ------------------------------------------------------------------------------------------------ deferred shortcut gradient
+# A YOLO-NAS bottleneck computes alpha * x + cv2(cv1(x)).  Its backward used to be: scale_add_dot (reads dout, x; writes alpha * dout),
+# ... cv1's dgrad (writes the main-path gradient), then autograd's ATen add of the two (reads both, writes dx): 6 tensor passes and two
+# launches per bottleneck around the dgrad.  With a token the shortcut's backward only parks (dout, alpha, x); cv1's backward runs its
+# dgrad as before and then ONE pass dx = alpha * dout + dx, dot = sum(dout * x) in place (reads dout, x, dx; writes dx): 4 passes, one
+# launch, no ATen add (20 bottlenecks per YOLO-NAS-S step).  Unlike SGB_SHARE_GRADS nothing accumulates inside a GEMM epilogue.
+DEFER_SHORTCUT = [__import__("os").environ.get("SGB_DEFER_SHORTCUT", "1") != "0"]
+
+
+class _DeferTok:
+    __slots__ = ("host", "pending")
+
+    def __init__(self):
+        self.host = False    # a fused block picked the token up in its forward and will finish the gradient in its backward
+        self.pending = None  # (dout, alpha, x, alpha's gradient slot) parked by the shortcut's backward
+
+
+def defer_shortcut_offer(x, alpha):
+    """Called by the bottleneck before cv1(x): attaches a token to x for the block that consumes x next (or returns None)."""
+    if not DEFER_SHORTCUT[0] or SHARE_GRADS[0] or not torch.is_grad_enabled() or not torch.is_tensor(x) or not x.requires_grad:
+        return None
+    if not torch.is_tensor(alpha) or getattr(alpha, "main_grad", None) is None:
+        return None
+    tok = _DeferTok()
+    x._sgb_defer = tok
+    return tok
+
+
+def _defer_pickup(x):
+    tok = x.__dict__.pop("_sgb_defer", None) if torch.is_tensor(x) and hasattr(x, "__dict__") else None
+    if tok is not None:
+        tok.host = True
+    return tok
+
+
+def defer_shortcut_withdraw(x, tok):
+    """After cv1(x): drops an offer nobody picked up; returns the token only if a block hosts it."""
+    if tok is None:
+        return None
+    if hasattr(x, "__dict__"):
+        x.__dict__.pop("_sgb_defer", None)
+    return tok if tok.host else None
+
+
+def _defer_finish(tok, dx):
+    """In the hosting block's backward, after its own input gradient dx exists: adds the parked shortcut gradient in place."""
+    if tok is None or tok.pending is None:
+        return dx
+    dout, alpha, xs, slot = tok.pending
+    tok.pending = None
+    if dx is None:
+        dx, dot = K.scale_add_dot(dout, alpha, xs)
+    else:
+        _, dot = K.scale_add_dot(dout, alpha, xs, dx, out=dx)
+    slot.add_(dot.sum().float().reshape(slot.shape))
+    return dx
 
 
 def _mg(p):
@@ -431,7 +549,9 @@ class _ConvBnAct(torch.autograd.Function):
         x = K.as_nhwc(x)
         krsc, crsk = cfg.cache.get(w, c_pad=x.shape[1])
         kout, _, r, s = w.shape
-        stats = K.new_stats(kout, x.device)
+        p_out = (x.shape[2] + 2 * cfg.pad - r) // cfg.stride + 1, (x.shape[3] + 2 * cfg.pad - s) // cfg.stride + 1
+        # wide layers: no statistics in the GEMM epilogue, the BatchNorm launch computes them (kernels.stats_in_bn)
+        stats = None if K.stats_in_bn(kout, x.shape[0] * p_out[0] * p_out[1]) else K.new_stats(kout, x.device)
         y_raw = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, stats=stats)
         res = K.as_nhwc(residual) if residual is not None else None
         ss = getattr(cfg, "sample_scale", None)
@@ -489,6 +609,94 @@ def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracke
 # backward the incoming gradient re-described with the padded channel count when its producer marked the padding as zero
 # (`_sgb_zero_pad`, set by the head-decode backward), else copied into a zeroed buffer.
 KPAD = [__import__("os").environ.get("SGB_KPAD", "1") != "0"]
+
+
+# ------------------------------------------------------------------------------------------------------------ two conv + BN on one input
+# A CSP layer applies two 1x1 ConvBNAct layers to the same tensor (yolo_stages.py:104-106 of the reference: conv1, conv2).  Separately
+# that is 2 GEMMs reading x twice, 2 BatchNorm passes, and in backward 2 BatchNorm passes, 2 dgrads whose results autograd adds with an
+# ATen kernel (3 more tensor passes over dx), 2 wgrads.  As ONE layer with concatenated output channels: 1 GEMM (x read once), 1
+# BatchNorm launch over K1 + K2 channels (per-channel, so identical arithmetic), backward 1 BatchNorm launch reading the two incoming
+# gradients in place (SgbBnDesc.dy2), 1 dgrad (no add), 1 wgrad whose rows are the two filters' gradients.  The two layers keep their
+# own parameters / state-dict keys; the BatchNorm parameters, statistics and gradient slots of the pair must be adjacent in memory
+# (training/flat_state.py lays them out so on request: YoloNASCSPLayer.sgb_adjacent_tensors) -- dual_conv_bn_act_ready() checks.
+DUAL_CONV = [__import__("os").environ.get("SGB_DUAL_CONV", "1") != "0"]
+
+
+def _follows(a, b) -> bool:
+    """b starts exactly where a ends (same dtype, both contiguous)."""
+    return a is not None and b is not None and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous() and b.data_ptr() == a.data_ptr() + a.numel() * a.element_size()
+
+
+def dual_conv_bn_act_ready(conv1, bn1, conv2, bn2) -> bool:
+    if not DUAL_CONV[0] or not torch.is_grad_enabled():
+        return False
+    w1, w2 = conv1.weight, conv2.weight
+    if tuple(w1.shape[1:]) != tuple(w2.shape[1:]) or w1.shape[0] % 8 or w2.shape[0] % 8 or conv1.stride != conv2.stride or conv1.padding != conv2.padding:
+        return False
+    if bn1.eps != bn2.eps or bn1.momentum != bn2.momentum or bn1.running_mean is None or bn2.running_mean is None:
+        return False
+    pairs = [(bn1.weight, bn2.weight), (bn1.bias, bn2.bias), (bn1.running_mean, bn2.running_mean), (bn1.running_var, bn2.running_var)]
+    if not all(_follows(a, b) for a, b in pairs):
+        return False
+    slots = [(_mg(bn1.weight), _mg(bn2.weight)), (_mg(bn1.bias), _mg(bn2.bias))]
+    return all(_follows(a, b) for a, b in slots) and _mg(w1) is not None and _mg(w2) is not None
+
+
+class _DualConvBnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, cfg):
+        x = K.as_nhwc(x)
+        k1, cin, r, s = w1.shape
+        k2 = w2.shape[0]
+        krsc, crsk = cfg.cache.get(w1, w2, x.shape[1])
+        kout = k1 + k2
+        p_out = (x.shape[2] + 2 * cfg.pad - r) // cfg.stride + 1, (x.shape[3] + 2 * cfg.pad - s) // cfg.stride + 1
+        stats = None if K.stats_in_bn(kout, x.shape[0] * p_out[0] * p_out[1]) else K.new_stats(kout, x.device)
+        y_raw = K.conv_fprop(x, krsc, kout, r, s, cfg.stride, cfg.pad, stats=stats)
+        # gamma / beta / running statistics of the second layer follow the first's in memory: the pointers of the first serve K1 + K2 channels
+        out, mean, rstd = K.bn_act_fwd(y_raw, stats, g1, b1, cfg.rm1, cfg.rv1, cfg.eps, cfg.momentum, cfg.act)
+        if not _NBT_DEFERRED[0]:
+            for nbt in cfg.nbt:
+                if nbt is not None:
+                    nbt += 1
+        ctx.save_for_backward(x, y_raw, g1, b1, mean, rstd)
+        ctx.cfg, ctx.crsk, ctx.shape = cfg, crsk, (k1, k2, cin, r, s)
+        ctx.slots = (_mg(w1), _mg(w2), _mg(g1), _mg(b1))
+        return out[:, :k1], out[:, k1:]
+
+    @staticmethod
+    def backward(ctx, d1, d2):
+        x, y_raw, g1, b1, mean, rstd = ctx.saved_tensors
+        cfg = ctx.cfg
+        k1, k2, cin, r, s = ctx.shape
+        sw1, sw2, sg, sb = ctx.slots
+        if d1 is None or d2 is None:  # one of the two outputs unused: its gradient is zero
+            n, _, h, w = y_raw.shape
+            d1 = d1 if d1 is not None else torch.zeros((n, k1, h, w), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
+            d2 = d2 if d2 is not None else torch.zeros((n, k2, h, w), dtype=torch.bfloat16, device=x.device).contiguous(memory_format=torch.channels_last)
+        dy, _, _, _ = K.bn_act_bwd(d1, y_raw, None, g1, mean, rstd, cfg.eps, cfg.act, dgamma=sg, dbeta=sb, beta=b1, dy2=d2)
+        dx = K.conv_dgrad(dy, ctx.crsk, x.shape, r, s, cfg.stride, cfg.pad) if ctx.needs_input_grad[0] else None
+        c = _CTX[0]
+        if c is not None:
+            dwf = _wgrad_raw(x, dy, r, s, cfg.stride, cfg.pad)  # fp32 [K1 + K2, R, S, C]: rows of the two filters
+            c.pending.append((dwf[:k1], cin, sw1))
+            c.pending.append((dwf[k1:], cin, sw2))
+        else:
+            dwf = K.conv_wgrad(x, dy, r, s, cfg.stride, cfg.pad)
+            K.wgrad_to_oihw(dwf[:k1], cin, out=sw1, accumulate=True)
+            K.wgrad_to_oihw(dwf[k1:], cin, out=sw2, accumulate=True)
+        return dx, None, None, None, None, None, None, None
+
+
+def dual_conv_bn_act(x, conv1, bn1, conv2, bn2, *, act, cache: ConcatWeightCache):
+    """(act(bn1(conv1(x))), act(bn2(conv2(x)))) in training mode as one GEMM + one BatchNorm launch; the caller checked
+    dual_conv_bn_act_ready().  Reference: modules/conv_bn_act_block.py:92-93 applied twice (yolo_stages.py:104-106)."""
+    K.require_cuda(x, "x")
+    stride = conv1.stride[0] if isinstance(conv1.stride, (tuple, list)) else conv1.stride
+    pad = conv1.padding[0] if isinstance(conv1.padding, (tuple, list)) else conv1.padding
+    cfg = SimpleNamespace(stride=int(stride), pad=int(pad), eps=bn1.eps, momentum=0.1 if bn1.momentum is None else bn1.momentum, act=act, cache=cache,
+                          rm1=bn1.running_mean, rv1=bn1.running_var, nbt=(bn1.num_batches_tracked, bn2.num_batches_tracked))  # fmt: skip
+    return _DualConvBnAct.apply(x, conv1.weight, bn1.weight, bn1.bias, conv2.weight, bn2.weight, bn2.bias, cfg)
 
 
 class PaddedOutCache:
@@ -630,6 +838,7 @@ class _QARepVGG(torch.autograd.Function):
         ctx.save_for_backward(x, y3, u, out, coef, g3, gp if gp is not None else g3, w1, bias1 if bias1 is not None else g3, alpha if alpha is not None else g3)
         ctx.cfg, ctx.c3, ctx.c1, ctx.fold = cfg, c3, c1, fold
         ctx.share = getattr(cfg, "share_tok", None)
+        ctx.defer = getattr(cfg, "defer_tok", None)
         ctx.flags = (bias1 is not None, alpha is not None, gp is not None, w3.shape[1])
         ctx.slots = (_mg(w3), _mg(g3), _mg(b3), _mg(w1), _mg(bias1), _mg(alpha), _mg(gp), _mg(bp))
         return out
@@ -655,6 +864,7 @@ class _QARepVGG(torch.autograd.Function):
         if dcat is not None:
             if ctx.needs_input_grad[0]:
                 dx = _share_dx(tok, lambda: K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1), lambda buf: K.conv_dgrad(dcat, ctx.c3, x.shape, 3, 3, 1, 1, out=buf, accumulate=True))
+            dx = _defer_finish(ctx.defer, dx)
             c = _CTX[0]
             batched = c is not None and sw3 is not None and sw1 is not None and (not has_alpha or (salpha is not None and (sbias is not None or not has_bias)))
             # fp32 [2K, 3, 3, C]: rows [0, K) = dW3, rows [K, 2K) centre tap = d(alpha * K1 + I)
@@ -694,6 +904,7 @@ class _QARepVGG(torch.autograd.Function):
                     K.conv_dgrad(du, ctx.c1, x.shape, 1, 1, cfg.stride, 0, out=buf, accumulate=True)
 
                 dx = _share_dx(tok, _fresh, _acc)
+            dx = _defer_finish(ctx.defer, dx)
             dw3 = _wgrad(x, dy3, 3, 3, cfg.stride, 1, cin, sw3)
         dalpha = None
         if has_alpha and dcat is not None and sw1 is not None and salpha is not None and (sbias is not None or not has_bias):
@@ -731,6 +942,7 @@ class _QARepVGG(torch.autograd.Function):
 def qarepvgg_block(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):
     K.require_cuda(x, "x")
     cfg.share_tok = _share_pickup(x)  # cfg is built per call by the module
+    cfg.defer_tok = _defer_pickup(x)
     return _QARepVGG.apply(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg)
 
 

@@ -444,11 +444,33 @@ def bn_desc(x, y, eps, momentum, act, residual=None, stats_repl=STATS_REPL, samp
     return d
 
 
+# Convolutions whose epilogue keeps per-channel statistics in registers exist for 32 / 48 / 64 / 96 output channels (halo-tile, 1x1-tile
+# and im2col fast paths); wider layers ran the im2col kernel's general epilogue (a 32-lane butterfly per 16 columns: 1.2-1.5 TB/s on
+# 1x1 layers that move the same bytes as 4.4 TB/s ones).  Those layers now run WITHOUT epilogue statistics and their BatchNorm forward
+# is one cooperative launch (sums, grid barrier, apply) -- at most STATS_IN_BN_MAX_BYTES of activation, so the apply pass's re-read
+# hits L2 (every such layer of YOLO-NAS at batch 32 is below 40 MB).  SGB_STATS_IN_BN=0 restores the epilogue statistics everywhere.
+STATS_IN_BN = [os.environ.get("SGB_STATS_IN_BN", "1") != "0"]
+STATS_IN_BN_MAX_BYTES = [int(os.environ.get("SGB_STATS_IN_BN_MAX_BYTES", str(96 << 20)))]
+_EPILOGUE_STATS_CHANNELS = (32, 48, 64, 96)
+
+
+def stats_in_bn(kout: int, pixels: int) -> bool:
+    """True: the layer's convolution runs without epilogue statistics and bn_act_fwd(stats=None) computes them itself."""
+    return STATS_IN_BN[0] and kout not in _EPILOGUE_STATS_CHANNELS and kout % 8 == 0 and 2 * kout * pixels <= STATS_IN_BN_MAX_BYTES[0]
+
+
 def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None, sample_scale=None):
+    """stats: [repl, 2, C] fp64 sums from the producing GEMM's epilogue, or None: the launch computes them itself (cooperative:
+    sums, grid-wide barrier, apply)."""
     n, c, h, w = x.shape
     y = empty_nhwc(n, c, h, w, x.device)
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    if stats is None:
+        stats = zeros((1, 2, c), torch.float64, x.device)
+        d = bn_desc(x, y, eps, momentum, act, residual, 1, sample_scale=sample_scale)
+        _timed("sgb_bn_act_fwd_fused", ctypes.byref(d), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _ptr(mean), _ptr(rstd), _stream())
+        return y, mean, rstd
     d = bn_desc(x, y, eps, momentum, act, residual, stats.shape[0], sample_scale=sample_scale)
     _timed("sgb_bn_act_fwd", ctypes.byref(d), _ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(residual), _ptr(y), _ptr(mean), _ptr(rstd), _stream())
     return y, mean, rstd
@@ -462,12 +484,24 @@ def bn_act_infer(x, gamma, beta, running_mean, running_var, eps, act, residual=N
     return y
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None, sample_scale=None):
-    """Returns (dx, dresidual or None, dgamma, dbeta); dgamma / dbeta are accumulated into when given."""
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None, sample_scale=None, dy2=None):
+    """Returns (dx, dresidual or None, dgamma, dbeta); dgamma / dbeta are accumulated into when given.
+    dy2: the gradient arrives as TWO tensors, dy for channels [0, dy.shape[1]) and dy2 for the rest (two layers that shared one GEMM,
+    functional._DualConvBnAct); both are read in place (SgbBnDesc.dy2).  y may be None when the mask is recomputed from x."""
     n, c, h, w = x.shape
     dy = as_nhwc(dy)
-    d = bn_desc(x, y, eps, 0.0, act, None, 1, sample_scale=sample_scale)
-    if nhwc_pitch(dy) != d.y_pitch:
+    d = bn_desc(x, y if y is not None else x, eps, 0.0, act, None, 1, sample_scale=sample_scale)
+    if dy2 is not None:
+        dy2 = as_nhwc(dy2)
+        if dy.shape[1] + dy2.shape[1] != c or dy.shape[1] % 8 != 0:
+            raise L.SgbError("bn_act_bwd: dy and dy2 must split the layer's channels at a multiple of 8")
+        if nhwc_pitch(dy) % 8 != 0 or dy.data_ptr() % 16 != 0:
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        if nhwc_pitch(dy2) % 8 != 0 or dy2.data_ptr() % 16 != 0:
+            dy2 = dy2.contiguous(memory_format=torch.channels_last)
+        d.dy_pitch, d.dy_off = nhwc_pitch(dy), 0
+        d.dy2_split, d.dy2_pitch, d.dy2_off, d.dy2 = dy.shape[1], nhwc_pitch(dy2), 0, dy2.data_ptr()
+    elif nhwc_pitch(dy) != d.y_pitch:
         # dy is a channel slice of a wider gradient buffer (the layer's output went into a concat): the kernels read it in place
         if nhwc_pitch(dy) % 8 == 0 and dy.data_ptr() % 16 == 0:
             d.dy_pitch, d.dy_off = nhwc_pitch(dy), 0

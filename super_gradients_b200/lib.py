@@ -63,6 +63,11 @@ class BnDesc(Structure):
         ("dy_off", c_int32),
         ("hw", c_int64),
         ("sample_scale", c_void_p),
+        ("dy2_split", c_int32),
+        ("dy2_pitch", c_int32),
+        ("dy2_off", c_int32),
+        ("dy2_reserved", c_int32),
+        ("dy2", c_void_p),
     ]
 
 
@@ -161,6 +166,7 @@ _SIGNATURES = {
     "sgb_stem_patches_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, P, _I, _I, _I, P]),
     "sgb_nhwc_bf16_to_nchw_f32": (c_int, [P, _I, _I, _I, _I, _I, _I, P, P]),
     "sgb_bn_act_fwd": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P]),
+    "sgb_bn_act_fwd_fused": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P]),
     "sgb_bn_act_infer": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P]),
     "sgb_bn_act_bwd_reduce": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P]),
     "sgb_bn_act_bwd_apply": (c_int, [POINTER(BnDesc), P, P, P, P, P, P, P, P, P, P, P, P, P]),

@@ -20,6 +20,38 @@ def _is_no_decay(name: str, p: torch.Tensor, bn_param_ids) -> bool:
     return id(p) in bn_param_ids or name.endswith(".bias")
 
 
+def _adjacency_groups(model: nn.Module):
+    """Tensors that modules ask to be laid out back to back (`sgb_adjacent_tensors()` -> iterable of tensor lists): layers that share
+    one GEMM (the two 1x1 convolutions of a CSP layer) then run their BatchNorm over the concatenated channels with ONE pointer per
+    parameter / statistic, no gather."""
+    groups = []
+    for m in model.modules():
+        fn = getattr(m, "sgb_adjacent_tensors", None)
+        if callable(fn):
+            groups.extend([t for t in g] for g in fn())
+    return groups
+
+
+def _apply_adjacency(items, groups):
+    """items: [(name, tensor)] in layout order.  Every group whose members are ALL in `items` is moved so that its members follow its
+    first member directly, in group order; everything else keeps its relative order."""
+    pos = {id(t): i for i, (_, t) in enumerate(items)}
+    followers = {}
+    skip = set()
+    for g in groups:
+        if len(g) < 2 or any(id(t) not in pos for t in g) or any(id(t) in skip or id(t) in followers for t in g):
+            continue
+        followers[id(g[0])] = [items[pos[id(t)]] for t in g[1:]]
+        skip.update(id(t) for t in g[1:])
+    out = []
+    for n, t in items:
+        if id(t) in skip:
+            continue
+        out.append((n, t))
+        out.extend(followers.get(id(t), ()))
+    return out
+
+
 class FlatState:
     def __init__(self, model: nn.Module, zero_wd_on_bias_and_bn: bool = True, dead_param_filter=lambda n: "rbr_reparam" in n):
         dev = next(model.parameters()).device
@@ -32,6 +64,8 @@ class FlatState:
         live = [(n, p) for n, p in named if not dead_param_filter(n)]
         decay = [(n, p) for n, p in live if not (zero_wd_on_bias_and_bn and _is_no_decay(n, p, bn_ids))]
         no_decay = [(n, p) for n, p in live if zero_wd_on_bias_and_bn and _is_no_decay(n, p, bn_ids)]
+        groups = _adjacency_groups(model)
+        decay, no_decay = _apply_adjacency(decay, groups), _apply_adjacency(no_decay, groups)
         self.order: List[Tuple[str, nn.Parameter]] = decay + no_decay
         self.n_decay = sum(p.numel() for _, p in decay)
         self.n_live = sum(p.numel() for _, p in self.order)
@@ -49,6 +83,7 @@ class FlatState:
                 off += k
         # floating-point buffers (BN running statistics) -> one flat tensor so EMA covers them in one launch
         bufs = [(n, b) for n, b in model.named_buffers() if b is not None and b.dtype == torch.float32 and n.split(".")[-1] in ("running_mean", "running_var")]
+        bufs = _apply_adjacency(bufs, groups)
         self.n_buf = sum(b.numel() for _, b in bufs)
         self.buffers = torch.empty(self.n_buf, dtype=torch.float32, device=dev)
         off = 0

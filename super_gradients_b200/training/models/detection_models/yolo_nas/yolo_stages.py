@@ -32,11 +32,15 @@ class YoloNASBottleneck(nn.Module):
             self.alpha = 1.0
 
     def forward(self, x):
-        y = self.cv2(self.cv1(x))
+        learnable = self.add and isinstance(self.alpha, torch.Tensor)
+        tok = SF.defer_shortcut_offer(x, self.alpha) if learnable and self.training else None
+        h = self.cv1(x)
+        tok = SF.defer_shortcut_withdraw(x, tok)  # not None: cv1's backward finishes the shortcut's input gradient (functional._defer_finish)
+        y = self.cv2(h)
         if not self.add:
             return y
-        if isinstance(self.alpha, torch.Tensor):
-            return _ScaledAdd.apply(x, y, self.alpha, SF._share_pickup(x))
+        if learnable:
+            return _ScaledAdd.apply(x, y, self.alpha, SF._share_pickup(x), tok)
         return SF.add(x, y, self.alpha, 1.0)
 
 
@@ -44,13 +48,14 @@ class _ScaledAdd(torch.autograd.Function):
     """alpha * x + y with a learnable scalar alpha read on the device (yolo_stages.py:61-63)."""
 
     @staticmethod
-    def forward(ctx, x, y, alpha, share=None):
+    def forward(ctx, x, y, alpha, share=None, defer=None):
         from ..... import kernels as K
 
         x, y = K.as_nhwc(x), K.as_nhwc(y)
         ctx.save_for_backward(x, alpha)
         ctx.slot = getattr(alpha, "main_grad", None)
         ctx.share = share  # x also feeds the block's first convolution: both input gradients land in one buffer (functional._share_dx)
+        ctx.defer = defer if ctx.slot is not None else None
         return K.scale_add(x, alpha, y)
 
     @staticmethod
@@ -59,6 +64,11 @@ class _ScaledAdd(torch.autograd.Function):
 
         x, alpha = ctx.saved_tensors
         dy = K.as_nhwc(dy)
+        if ctx.defer is not None:
+            # the block that consumes x (cv1) adds alpha * dy into its own input gradient and accumulates d(alpha) in ONE pass after its
+            # dgrad: no gradient tensor for x from here, no ATen add afterwards
+            ctx.defer.pending = (dy, alpha, x, ctx.slot)
+            return None, dy, None, None, None
         dots = []  # alpha * dy (into the shared input-gradient buffer when there is one) and sum(dy * x) in one pass over dy
 
         def fresh():
@@ -74,7 +84,7 @@ class _ScaledAdd(torch.autograd.Function):
         if ctx.slot is not None:
             ctx.slot.add_(dalpha)
             dalpha = None
-        return dx, dy, dalpha, None
+        return dx, dy, dalpha, None, None
 
 
 class SequentialWithIntermediates(nn.Sequential):
@@ -121,10 +131,21 @@ class YoloNASCSPLayer(nn.Module):
         module_list = [YoloNASBottleneck(hidden_channels, hidden_channels, block_type, activation_type, shortcut, use_alpha, drop_path_rate=drop_path_rates[i]) for i in range(num_bottlenecks)]
         self.bottlenecks = SequentialWithIntermediates(concat_intermediates, *module_list)
         self.dropout = nn.Identity()
+        self._cache12 = SF.ConcatWeightCache()
+
+    def sgb_adjacent_tensors(self):
+        """conv1 and conv2 read the same tensor: in training they run as ONE GEMM + ONE BatchNorm launch over the concatenated channels
+        (functional.dual_conv_bn_act), which needs the pair's BatchNorm parameters / statistics back to back in the flat buffers."""
+        b1, b2 = self.conv1.bn, self.conv2.bn
+        return [[b1.weight, b2.weight], [b1.bias, b2.bias], [b1.running_mean, b2.running_mean], [b1.running_var, b2.running_var]]
 
     def forward(self, x: Tensor) -> Tensor:
-        x_1 = self.bottlenecks(self.conv1(x))
-        x_2 = self.conv2(x)
+        if self.training and SF.dual_conv_bn_act_ready(self.conv1.conv, self.conv1.bn, self.conv2.conv, self.conv2.bn):
+            h1, x_2 = SF.dual_conv_bn_act(x, self.conv1.conv, self.conv1.bn, self.conv2.conv, self.conv2.bn, act=self.conv1._act_code, cache=self._cache12)
+            x_1 = self.bottlenecks(h1)
+        else:
+            x_1 = self.bottlenecks(self.conv1(x))
+            x_2 = self.conv2(x)
         return self.conv3(SF.concat([*x_1, x_2]))
 
 

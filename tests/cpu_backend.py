@@ -304,9 +304,22 @@ def _update_running(rm, rv, mean, var_biased, M, momentum):
         rv.mul_(1 - momentum).add_(momentum * var_biased * (M / max(M - 1, 1)))
 
 
+def _span(t, c):
+    """The kernels read / write C entries from a pointer: two layers that share one GEMM pass the FIRST layer's tensor and rely on the
+    second's following it in memory (functional.dual_conv_bn_act_ready checked that).  Same view here."""
+    if t is None or t.numel() == c:
+        return t
+    t = t.detach()
+    return torch.as_strided(t, (c,), (1,), t.storage_offset())
+
+
 def bn_act_fwd(x, stats, gamma, beta, running_mean, running_var, eps, momentum, act, residual=None, sample_scale=None):
     n, c, h, w = x.shape
     M = n * h * w
+    gamma, beta, running_mean, running_var = _span(gamma, c), _span(beta, c), _span(running_mean, c), _span(running_var, c)
+    if stats is None:  # wide layers: the BatchNorm launch computes the sums of the stored bf16 values itself
+        xd = x.double()
+        stats = torch.stack([xd.sum((0, 2, 3)), (xd * xd).sum((0, 2, 3))])[None]
     tot = stats.sum(0)  # [2, C] fp64
     mean = tot[0] / M
     var = (tot[1] / M - mean * mean).clamp_min(0)
@@ -331,9 +344,15 @@ def _mask(dout, out, act):
     raise NotImplementedError("CPU stand-in: only relu / identity activations have a backward")
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None, sample_scale=None):
+def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, dgamma=None, dbeta=None, beta=None, sample_scale=None, dy2=None):
     n, c, h, w = x.shape
     M = n * h * w
+    gamma, beta, dgamma, dbeta = _span(gamma, c), _span(beta, c), _span(dgamma, c), _span(dbeta, c)
+    if dy2 is not None:  # the gradient arrives as two channel ranges (two layers that shared one GEMM)
+        dy = torch.cat([dy.float(), dy2.float()], 1)
+    if y is None:  # the mask is recomputed from x with the forward pass's FMA
+        scale = gamma.float() * rstd
+        y = x.float() * _cv(scale) + _cv(beta.float() - mean * scale)
     dz_res = _mask(dy, y, act)
     dz = dz_res if sample_scale is None else dz_res * sample_scale.float().view(-1, 1, 1, 1)
     xh = (x.float() - _cv(mean)) * _cv(rstd)

@@ -1007,3 +1007,87 @@ def test_k_padded_prediction_conv_is_the_same_conv(monkeypatch):
         y1, dx1, dw1, db1 = run(True, through_decode)
         assert torch.equal(y0, y1)
         assert l2rel(dx1, dx0) < 1e-6 and l2rel(dw1, dw0) < 1e-6 and l2rel(db1, db0) < 1e-6, (through_decode, l2rel(dx1, dx0), l2rel(dw1, dw0), l2rel(db1, db0))
+
+
+def test_dual_conv_and_deferred_shortcut_are_the_same_csp_layer(golden, monkeypatch):
+    """functional._DualConvBnAct (conv1 / conv2 of a CSP layer as one GEMM + one BatchNorm launch over adjacent parameters, the two
+    incoming gradients read in place) and functional._defer_finish (a bottleneck's shortcut gradient added by ONE pass after cv1's dgrad
+    instead of scale_add_dot + an ATen add): output, input gradient, every parameter gradient and the running statistics of a CSP layer
+    laid out by FlatState equal the separate-layer path's; the merged path really ran; a whole train step of the tiny model stays on
+    the same trajectory."""
+    from super_gradients_b200 import functional as SF
+    from super_gradients_b200 import kernels as Kmod
+    from super_gradients_b200.modules import Conv, QARepVGGBlock
+    from super_gradients_b200.training.flat_state import FlatState
+    from super_gradients_b200.training.models.detection_models.yolo_nas.yolo_stages import YoloNASCSPLayer
+
+    cpu_backend.install_training(monkeypatch)
+    calls = {"fwd": 0, "bwd2": 0, "sad_acc": 0}
+    bn_fwd, bn_bwd, sad = Kmod.bn_act_fwd, Kmod.bn_act_bwd, Kmod.scale_add_dot
+
+    def count_fwd(x, *a, **k):
+        calls["fwd"] += 1
+        return bn_fwd(x, *a, **k)
+
+    def count_bwd(*a, **k):
+        calls["bwd2"] += k.get("dy2") is not None
+        return bn_bwd(*a, **k)
+
+    def count_sad(x1, a_dev, xd, x2=None, out=None):
+        calls["sad_acc"] += x2 is not None
+        return sad(x1, a_dev, xd, x2, out=out)
+
+    monkeypatch.setattr(Kmod, "bn_act_fwd", count_fwd)
+    monkeypatch.setattr(Kmod, "bn_act_bwd", count_bwd)
+    monkeypatch.setattr(Kmod, "scale_add_dot", count_sad)
+
+    def run(dual, defer):
+        monkeypatch.setattr(SF, "DUAL_CONV", [dual])
+        monkeypatch.setattr(SF, "DEFER_SHORTCUT", [defer])
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(Conv(16, 32, 1, stride=1, activation_type=torch.nn.ReLU), YoloNASCSPLayer(32, 32, 2, QARepVGGBlock, torch.nn.ReLU, True, True, hidden_channels=16)).train()
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        flat = FlatState(net)
+        csp = net[1]
+        assert SF._follows(csp.conv1.bn.weight, csp.conv2.bn.weight) and SF._follows(csp.conv1.bn.running_var, csp.conv2.bn.running_var)
+        assert SF._follows(csp.conv1.bn.bias.main_grad, csp.conv2.bn.bias.main_grad)
+        x = torch.randn(2, 16, 12, 12).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        for k in calls:
+            calls[k] = 0
+        y = net(x)
+        (y.float() * torch.linspace(-1, 1, y.numel()).reshape(y.shape)).sum().backward()
+        grads = {n: flat.grad_of(n).clone() for n, _ in flat.order}
+        return y.detach().float(), x.grad.float(), grads, flat.buffers.clone(), dict(calls)
+
+    y0, dx0, g0, b0, c0 = run(False, False)
+    y1, dx1, g1, b1, c1 = run(True, True)
+    # separate layers: pre, conv1, conv2, conv3 = 4 BatchNorm forwards; merged: 3, one two-source backward, one in-place shortcut pass per bottleneck
+    assert (c0["fwd"], c0["bwd2"], c0["sad_acc"]) == (4, 0, 0) and (c1["fwd"], c1["bwd2"], c1["sad_acc"]) == (3, 1, 2), (c0, c1)
+    assert torch.equal(y0, y1)  # per-channel arithmetic: the merged forward is the same computation
+    torch.testing.assert_close(b1, b0, rtol=1e-6, atol=1e-7)
+    assert l2rel(dx1, dx0) < 8e-3, l2rel(dx1, dx0)  # one bf16 rounding of the merged dgrad's sum instead of two + an add
+    scale = max(float(v.norm()) for v in g0.values())
+    for k in g0:
+        if float(g0[k].norm()) < 1e-4 * scale:
+            assert float(g1[k].norm()) < 1e-4 * scale, k
+            continue
+        assert l2rel(g1[k], g0[k]) < 2e-2, (k, l2rel(g1[k], g0[k]))
+    # each switch alone
+    for dual, defer in ((True, False), (False, True)):
+        y2, dx2, g2, _, _ = run(dual, defer)
+        assert torch.equal(y2, y0) and l2rel(dx2, dx0) < 8e-3
+        for k in g0:
+            assert float(g0[k].norm()) < 1e-4 * scale or l2rel(g2[k], g0[k]) < 2e-2, (dual, defer, k)
+
+    g = golden("tiny_yolo_nas")
+    x, t = g["x"], _padded_targets(g)
+    res = {}
+    for on in (False, True):
+        monkeypatch.setattr(SF, "DUAL_CONV", [on])
+        monkeypatch.setattr(SF, "DEFER_SHORTCUT", [on])
+        _, st = _train_step(g, monkeypatch)
+        res[on] = _run(st, x, t, 2)
+    assert abs(res[True][0][0] - res[False][0][0]) < 2e-2 * abs(res[False][0][0])
+    assert l2rel(res[True][1][3], res[False][1][3]) < 1e-3  # parameters after two steps

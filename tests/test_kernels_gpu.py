@@ -200,6 +200,14 @@ def test_bn_act_fwd_bwd(act, with_res):
     assert ((y.float().cpu() - ref.detach()).abs() <= ref.detach().abs() * 2**-7 + 2e-3).all()
     torch.testing.assert_close(rmg.cpu(), rm, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rvg.cpu(), rv, rtol=1e-4, atol=1e-5)
+    # stats=None: ONE cooperative launch computes the sums itself (wide layers whose GEMM epilogue keeps no statistics): same results
+    rmf, rvf = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    yf, meanf, rstdf = k.bn_act_fwd(xg, None, gamma.detach().to(DEV), beta.detach().to(DEV), rmf, rvf, eps, mom, act, resg)
+    torch.testing.assert_close(meanf, mean, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(rstdf, rstd, rtol=1e-6, atol=1e-6)
+    assert ((yf.float() - y.float()).abs() <= y.float().abs() * 2**-7 + 1e-6).all()
+    torch.testing.assert_close(rmf, rmg, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(rvf, rvg, rtol=1e-6, atol=1e-7)
     # without a residual the activation mask is recomputed from x / gamma / beta instead of reading y
     dx, dres, dgamma, dbeta = k.bn_act_bwd(to_nhwc_bf16(dy), xg, y, gamma.detach().to(DEV), mean, rstd, eps, act, want_residual_grad=with_res, beta=beta.detach().to(DEV))
     assert rel_err(dx.float().cpu(), x.grad) < 2e-2
@@ -219,6 +227,28 @@ def test_bn_act_fwd_bwd(act, with_res):
     assert count() - n1 == n1 - n0, "the sliced dy was copied instead of being read in place"
     assert torch.equal(dx2, dx) and torch.equal(dgamma2, dgamma) and torch.equal(dbeta2, dbeta)
     assert not with_res or torch.equal(dres2, dres)
+
+
+@pytest.mark.parametrize("shape", [(8, 192, 40, 40), (3, 384, 20, 20), (2, 128, 80, 80)])
+def test_bn_act_fwd_fused_statistics_many_ctas(shape):
+    """sgb_bn_act_fwd_fused (sums, grid-wide barrier, apply) on shapes that span the whole grid: equal to channel_stats + bn_act_fwd."""
+    k = K()
+    g = torch.Generator().manual_seed(131)
+    n, c, h, w = shape
+    xg = to_nhwc_bf16(torch.randn(n, c, h, w, generator=g) * 1.5 + 0.25)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.2).to(DEV)
+    rm0, rv0, rm1, rv1 = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    y0, m0, r0 = k.bn_act_fwd(xg, k.channel_stats(xg), gamma, beta, rm0, rv0, 1e-3, 0.03, "relu")
+    for _ in range(3):  # repeated launches: the grid barrier's state is reusable
+        rm1.zero_(), rv1.fill_(1.0)
+        y1, m1, r1 = k.bn_act_fwd(xg, None, gamma, beta, rm1, rv1, 1e-3, 0.03, "relu")
+        torch.testing.assert_close(m1, m0, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(r1, r0, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(rv1, rv0, rtol=1e-6, atol=1e-7)
+        assert ((y1.float() - y0.float()).abs() <= y0.float().abs() * 2**-7 + 1e-6).all()
+    xr = xg.float()
+    ref = F.relu(F.batch_norm(xr, None, None, gamma, beta, True, 0.0, 1e-3))
+    assert ((y1.float() - ref).abs() <= ref.abs() * 2**-7 + 2e-3).all()
 
 
 def test_maxpool_axpby_avgpool():

@@ -51,6 +51,11 @@ case "${1}" in
     for mp in 12800 51200 204800 0; do printf "SGB_QAREP_FOLD=1 MAXPIX=%d: " $mp; SGB_QAREP_FOLD=1 SGB_QAREP_FOLD_MAXPIX=$mp timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench9_fold$mp.err | tee gpurun_out/r2_bench9_fold$mp.json | bench_line; tail -2 gpurun_out/r2_bench9_fold$mp.err; done
     timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline9_launches.txt > gpurun_out/r2_timeline9.txt 2>gpurun_out/r2_timeline9.err; head -30 gpurun_out/r2_timeline9.txt; tail -3 gpurun_out/r2_timeline9.err
     timeout 300 python tools/mem_kernels.py > gpurun_out/r2_mem_kernels9.txt 2>gpurun_out/r2_mem_kernels9.err; cat gpurun_out/r2_mem_kernels9.txt; tail -3 gpurun_out/r2_mem_kernels9.err ;;
+  tenth)  # statistics inside the BatchNorm launch for wide layers, CSP conv1+conv2 as one GEMM, deferred shortcut gradients: suite subset, A/B, timeline
+    timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py tests/test_trainer_gpu.py -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest10.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/r2_pytest10.log
+    for cfg in "1 1 1" "0 1 1" "1 0 1" "1 1 0" "0 0 0"; do set -- $cfg; printf "STATS_IN_BN=%s DUAL_CONV=%s DEFER_SHORTCUT=%s: " $1 $2 $3
+      SGB_STATS_IN_BN=$1 SGB_DUAL_CONV=$2 SGB_DEFER_SHORTCUT=$3 timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench10_$1$2$3.err | tee gpurun_out/r2_bench10_$1$2$3.json | bench_line; tail -2 gpurun_out/r2_bench10_$1$2$3.err; done
+    timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline11_launches.txt > gpurun_out/r2_timeline11.txt 2>gpurun_out/r2_timeline11.err; head -45 gpurun_out/r2_timeline11.txt; tail -3 gpurun_out/r2_timeline11.err ;;
   dp)  # N GPUs (gpurun --gpus N): split graphs around an eager all-reduce vs NCCL captured inside one graph
     N=${2:-2}
     for ig in 0 1; do
