@@ -96,7 +96,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.BN - 1) / p.BN;
   const int total_tiles = m_tiles * n_tiles;
-  const int chunks = p.C / p.KC;
+  const int chunks = (p.C + p.KC - 1) / p.KC;  // a last chunk reaching past C is zero-filled by TMA (out-of-bounds channels)
   const int k_iters = p.ntaps * chunks;
 
   if (threadIdx.x == 0) {
@@ -411,6 +411,7 @@ struct WParams {
   int cpad;            // channel count of the KRSC output rows (x channels incl. padding)
   float* dw;
   int tmem_cols;
+  int wide_n;  // 1: ONE MMA per (tap, 16 pixels) with N = c_tile spanning the tap's boxes (LBO = box size) instead of one per box
   int dbg;  // SGB_DEBUG_SKIP (perf experiments): 1 no atomics, 4 no x loads, 8 no dy loads
 };
 constexpr int WPIX = 64;  // pixels (GEMM K) per pipeline stage
@@ -514,10 +515,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     } else if (warp == 1) {
       // A and B are MN-major: a_major (bit 15) and b_major (bit 16) set; M = 128, N = CB
       const uint32_t leader = elect_one() ? 1u : 0u;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.CB >> 3) << 17) |
+      // wide_n: the tap's boxes are consecutive N atoms of ONE operand (leading-dimension byte offset = box size), so a tap costs
+      // WPIX / 16 MMAs of N = c_tile instead of boxes_per_tap times as many of N = CB (N = 16 / 32 MMAs are issue-bound)
+      const int mma_n = p.wide_n ? p.c_tile : p.CB;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(mma_n >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const int b_row_bytes = p.CB * 2;
-      const uint64_t a_hi = make_smem_desc_mn(0, 128, WPIX * 128), b_hi = make_smem_desc_mn(0, b_row_bytes, 0);
+      const uint64_t a_hi = make_smem_desc_mn(0, 128, WPIX * 128), b_hi = make_smem_desc_mn(0, b_row_bytes, p.wide_n ? b_box : 0u);
+      const int mma_boxes = p.wide_n ? 1 : boxes_per_tap;
       int stg = 0;
       uint32_t par = 0;
       for (int it = 0; it < n_iters; ++it) {
@@ -525,7 +530,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         tcgen05_fence_after();
         const uint32_t sa = (smem_base + stg * stage_bytes) >> 4, sb = sa + (a_bytes >> 4);
         for (int t = 0; t < ntaps; ++t)
-          for (int bx = 0; bx < boxes_per_tap; ++bx) {
+          for (int bx = 0; bx < mma_boxes; ++bx) {
             const uint32_t sbox = sb + (((uint32_t)(t * boxes_per_tap + bx) * b_box) >> 4);
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.c_tile + bx * p.CB);
 #pragma unroll
@@ -649,6 +654,18 @@ int launch(const Problem& q, cudaStream_t st) {
   p.R = q.R;
   p.S = q.S;
   p.KC = q.C % 64 == 0 ? 64 : (q.C % 32 == 0 ? 32 : 16);
+  {
+    // Few channels per k-iteration make the pipeline latency-bound (one mbarrier round trip per 4-8 KB of A): with 48 / 96 / 288
+    // channels use 64-channel boxes anyway -- the channels past C are zero-filled by TMA's bounds check (the matching B columns
+    // belong to the next tap or are out of bounds: finite x 0), so C = 48 runs 1 k-iteration per tap instead of 3 and C = 96 runs 2
+    // instead of 3, at the price of some zero MMA work.  SGB_UMMA_KC_PAD=0 restores exact chunks.
+    static int kc_pad = -1;
+    if (kc_pad < 0) {
+      const char* e = getenv("SGB_UMMA_KC_PAD");
+      kc_pad = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (kc_pad && p.KC < 64 && q.C > 32) p.KC = 64;
+  }
   // N tile: whole N when it fits one accumulator, else the divisor-friendly size with least padding
   int bn;
   if (p.N <= 256) {
@@ -815,6 +832,14 @@ int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
   int tc = 32;
   while (tc < p.tpg * p.c_tile) tc <<= 1;
   p.tmem_cols = tc;
+  {
+    static int wide = -1;
+    if (wide < 0) {
+      const char* e = getenv("SGB_WGRAD_WIDE_N");
+      wide = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.wide_n = (wide && p.c_tile > p.CB && p.c_tile <= 256 && p.c_tile % 16 == 0) ? 1 : 0;
+  }
   const uint32_t a_bytes = 2 * WPIX * 128;
   const uint32_t b_bytes = (uint32_t)p.tpg * (p.c_tile / p.CB) * WPIX * p.CB * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;

@@ -76,6 +76,15 @@ CONV_CASES = [
     (3, 32, 13, 37, 32, 3, 1, 1),
     (2, 128, 19, 16, 128, 3, 1, 1),
     (40, 32, 64, 64, 32, 3, 1, 1),
+    # im2col kernels with channel counts that are not multiples of 64: 64-channel boxes with TMA-zero-filled tails (fprop / dgrad),
+    # weight-gradient MMAs whose N spans several boxes (48 = 3 x 16, 96 = 3 x 32, 192 = 3 x 64, 288 = 9 x 32)
+    (4, 96, 20, 20, 192, 3, 2, 1),
+    (4, 96, 20, 20, 96, 3, 2, 1),
+    (4, 96, 20, 20, 64, 1, 1, 0),
+    (4, 192, 20, 20, 64, 1, 1, 0),
+    (2, 288, 20, 20, 96, 1, 1, 0),
+    (2, 48, 40, 40, 96, 1, 2, 0),
+    (2, 80, 12, 12, 80, 1, 1, 0),
 ]
 
 

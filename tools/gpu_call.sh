@@ -56,6 +56,11 @@ case "${1}" in
     for cfg in "1 1 1" "0 1 1" "1 0 1" "1 1 0" "0 0 0"; do set -- $cfg; printf "STATS_IN_BN=%s DUAL_CONV=%s DEFER_SHORTCUT=%s: " $1 $2 $3
       SGB_STATS_IN_BN=$1 SGB_DUAL_CONV=$2 SGB_DEFER_SHORTCUT=$3 timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench10_$1$2$3.err | tee gpurun_out/r2_bench10_$1$2$3.json | bench_line; tail -2 gpurun_out/r2_bench10_$1$2$3.err; done
     timeout 300 python tools/timeline.py --dump gpurun_out/r2_timeline11_launches.txt > gpurun_out/r2_timeline11.txt 2>gpurun_out/r2_timeline11.err; head -45 gpurun_out/r2_timeline11.txt; tail -3 gpurun_out/r2_timeline11.err ;;
+  eleventh)  # im2col kernels: 64-channel boxes with zero-filled tails, wide-N weight-gradient MMAs: kernel suite, A/B, conv table
+    timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest11.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/r2_pytest11.log
+    for cfg in "1 1" "0 1" "1 0"; do set -- $cfg; printf "UMMA_KC_PAD=%s WGRAD_WIDE_N=%s: " $1 $2
+      SGB_UMMA_KC_PAD=$1 SGB_WGRAD_WIDE_N=$2 timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench11_$1$2.err | tee gpurun_out/r2_bench11_$1$2.json | bench_line; tail -2 gpurun_out/r2_bench11_$1$2.err; done
+    timeout 300 python tools/conv_table.py --top 150 > gpurun_out/r2_conv_table11.txt 2>gpurun_out/r2_conv_table11.err; grep -E "umma" gpurun_out/r2_conv_table11.txt | head -70; tail -3 gpurun_out/r2_conv_table11.err ;;
   dp)  # N GPUs (gpurun --gpus N): split graphs around an eager all-reduce vs NCCL captured inside one graph
     N=${2:-2}
     for ig in 0 1; do
