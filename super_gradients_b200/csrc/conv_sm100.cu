@@ -517,29 +517,47 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       const uint32_t leader = elect_one() ? 1u : 0u;
       // wide_n: the tap's boxes are consecutive N atoms of ONE operand (leading-dimension byte offset = box size), so a tap costs
       // WPIX / 16 MMAs of N = c_tile instead of boxes_per_tap times as many of N = CB (N = 16 / 32 MMAs are issue-bound)
-      const int mma_n = p.wide_n ? p.c_tile : p.CB;
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(mma_n >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
+      // An M = 128, K = 16 MMA reads 4 KB of A from shared memory whatever its N: with N = 16 .. 48 the tensor pipe waits on the operand
+      // port (measured: 62 clocks per N = 48 MMA).  So one MMA covers as many boxes as 256 columns hold -- across TAPS too: box a of
+      // the stage (a = tap * boxes_per_tap + box) sits at a * b_box in shared memory and owns TMEM columns [a * CB, (a + 1) * CB).
+      const int n_atoms = p.wide_n ? ntaps * boxes_per_tap : 0;
+      const int apm = 256 / p.CB;  // boxes per MMA
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = idesc_base | ((uint32_t)(p.CB >> 3) << 17);
       const int b_row_bytes = p.CB * 2;
       const uint64_t a_hi = make_smem_desc_mn(0, 128, WPIX * 128), b_hi = make_smem_desc_mn(0, b_row_bytes, p.wide_n ? b_box : 0u);
-      const int mma_boxes = p.wide_n ? 1 : boxes_per_tap;
       int stg = 0;
       uint32_t par = 0;
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(full_bar(stg), par);
         tcgen05_fence_after();
         const uint32_t sa = (smem_base + stg * stage_bytes) >> 4, sb = sa + (a_bytes >> 4);
-        for (int t = 0; t < ntaps; ++t)
-          for (int bx = 0; bx < mma_boxes; ++bx) {
-            const uint32_t sbox = sb + (((uint32_t)(t * boxes_per_tap + bx) * b_box) >> 4);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.c_tile + bx * p.CB);
+        if (p.wide_n) {
+          for (int a0 = 0; a0 < n_atoms; a0 += apm) {
+            const int na = min(apm, n_atoms - a0);
+            const uint32_t idesc_w = idesc_base | ((uint32_t)((na * p.CB) >> 3) << 17);
+            const uint32_t sbox = sb + (((uint32_t)a0 * b_box) >> 4);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a0 * p.CB);
 #pragma unroll
             for (int j = 0; j < WPIX / 16; ++j) {
               const uint64_t da = a_hi | (uint64_t)((sa + ((j * 16 * 128) >> 4)) & 0x3fff);
               const uint64_t db = b_hi | (uint64_t)((sbox + (uint32_t)((j * 16 * b_row_bytes) >> 4)) & 0x3fff);
-              umma_bf16_if(leader, d_tmem, da, db, idesc, (it | j) != 0);
+              umma_bf16_if(leader, d_tmem, da, db, idesc_w, (it | j) != 0);
             }
           }
+        } else {
+          for (int t = 0; t < ntaps; ++t)
+            for (int bx = 0; bx < boxes_per_tap; ++bx) {
+              const uint32_t sbox = sb + (((uint32_t)(t * boxes_per_tap + bx) * b_box) >> 4);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.c_tile + bx * p.CB);
+#pragma unroll
+              for (int j = 0; j < WPIX / 16; ++j) {
+                const uint64_t da = a_hi | (uint64_t)((sa + ((j * 16 * 128) >> 4)) & 0x3fff);
+                const uint64_t db = b_hi | (uint64_t)((sbox + (uint32_t)((j * 16 * b_row_bytes) >> 4)) & 0x3fff);
+                umma_bf16_if(leader, d_tmem, da, db, idesc, (it | j) != 0);
+              }
+            }
+        }
         umma_commit_if(leader, empty_bar(stg));
         if (it == n_iters - 1) umma_commit_if(leader, done_bar);
         if (++stg == p.stages) {
@@ -838,7 +856,7 @@ int wgrad_launch(const WgradProblem& q, cudaStream_t st) {
       const char* e = getenv("SGB_WGRAD_WIDE_N");
       wide = (e && e[0] == '0') ? 0 : 1;
     }
-    p.wide_n = (wide && p.c_tile > p.CB && p.c_tile <= 256 && p.c_tile % 16 == 0) ? 1 : 0;
+    p.wide_n = (wide && p.tpg * (p.c_tile / p.CB) > 1) ? 1 : 0;  // more than one box per stage
   }
   const uint32_t a_bytes = 2 * WPIX * 128;
   const uint32_t b_bytes = (uint32_t)p.tpg * (p.c_tile / p.CB) * WPIX * p.CB * 2;

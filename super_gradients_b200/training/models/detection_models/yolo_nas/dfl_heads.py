@@ -42,6 +42,20 @@ class YoloNASDFLHead(BaseDetectionModule):
         self.prior_prob = 1e-2
         self._initialize_biases()
         self._cls_cache, self._reg_cache = SF.WeightCache(), SF.WeightCache()
+        self._cache_pair = SF.ConcatWeightCache()
+
+    def _first_pair(self):
+        """The first cls / reg convolutions read the same tensor (the stem's output): candidates for ONE GEMM (functional.dual_conv_bn_act)."""
+        a, b = self.cls_convs[0], self.reg_convs[0]
+        ok = all(hasattr(m.seq, "bn") and m.seq.conv.bias is None and m.seq.conv.groups == 1 and m._act_code == a._act_code for m in (a, b))
+        return (a, b) if ok else None
+
+    def sgb_adjacent_tensors(self):
+        pair = self._first_pair()
+        if pair is None:
+            return []
+        b1, b2 = pair[0].seq.bn, pair[1].seq.bn
+        return [[b1.weight, b2.weight], [b1.bias, b2.bias], [b1.running_mean, b2.running_mean], [b1.running_var, b2.running_var]]
 
     def replace_num_classes(self, num_classes: int, compute_new_weights_fn=None):
         old = self.cls_pred
@@ -57,9 +71,18 @@ class YoloNASDFLHead(BaseDetectionModule):
     def forward(self, x):
         """Returns (reg_output, cls_output) as bf16 NHWC maps [B, 4*(reg_max+1), H, W], [B, num_classes, H, W]."""
         x = self.stem(x)
-        cls_feat = self.cls_convs(x)
+        pair = self._first_pair() if self.training else None
+        if pair is not None and SF.dual_conv_bn_act_ready(pair[0].seq.conv, pair[0].seq.bn, pair[1].seq.conv, pair[1].seq.bn):
+            cls_feat, reg_feat = SF.dual_conv_bn_act(x, pair[0].seq.conv, pair[0].seq.bn, pair[1].seq.conv, pair[1].seq.bn, act=pair[0]._act_code, cache=self._cache_pair)
+            for m in list(self.cls_convs)[1:]:
+                cls_feat = m(cls_feat)
+            for m in list(self.reg_convs)[1:]:
+                reg_feat = m(reg_feat)
+        else:
+            cls_feat, reg_feat = self.cls_convs(x), None
         cls_output = SF.conv_bias(cls_feat, self.cls_pred.weight, self.cls_pred.bias, stride=1, pad=0, cache=self._cls_cache)
-        reg_feat = self.reg_convs(x)
+        if reg_feat is None:
+            reg_feat = self.reg_convs(x)
         reg_output = SF.conv_bias(reg_feat, self.reg_pred.weight, self.reg_pred.bias, stride=1, pad=0, cache=self._reg_cache)
         return reg_output, cls_output
 

@@ -61,6 +61,12 @@ case "${1}" in
     for cfg in "1 1" "0 1" "1 0"; do set -- $cfg; printf "UMMA_KC_PAD=%s WGRAD_WIDE_N=%s: " $1 $2
       SGB_UMMA_KC_PAD=$1 SGB_WGRAD_WIDE_N=$2 timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench11_$1$2.err | tee gpurun_out/r2_bench11_$1$2.json | bench_line; tail -2 gpurun_out/r2_bench11_$1$2.err; done
     timeout 300 python tools/conv_table.py --top 150 > gpurun_out/r2_conv_table11.txt 2>gpurun_out/r2_conv_table11.err; grep -E "umma" gpurun_out/r2_conv_table11.txt | head -70; tail -3 gpurun_out/r2_conv_table11.err ;;
+  twelfth)  # weight-gradient MMAs spanning taps, head cls/reg first convs as one GEMM
+    timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py tests/test_trainer_gpu.py -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest12.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2_pytest12.log
+    for wn in 1 0; do printf "WGRAD_WIDE_N=%s: " $wn
+      SGB_WGRAD_WIDE_N=$wn timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench12_$wn.err | tee gpurun_out/r2_bench12_$wn.json | bench_line; tail -2 gpurun_out/r2_bench12_$wn.err; done
+    SHAPES="32,48,320,320,96,3,2;32,96,160,160,192,3,2;32,96,160,160,96,3,2;32,192,80,80,384,3,2;32,96,160,160,64,1,1" timeout 120 python tools/conv_microbench.py wgrad
+    timeout 300 python tools/timeline.py > gpurun_out/r2_timeline12.txt 2>gpurun_out/r2_timeline12.err; head -30 gpurun_out/r2_timeline12.txt; tail -3 gpurun_out/r2_timeline12.err ;;
   dp)  # N GPUs (gpurun --gpus N): split graphs around an eager all-reduce vs NCCL captured inside one graph
     N=${2:-2}
     for ig in 0 1; do
