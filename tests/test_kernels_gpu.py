@@ -85,6 +85,11 @@ CONV_CASES = [
     (2, 288, 20, 20, 96, 1, 1, 0),
     (2, 48, 40, 40, 96, 1, 2, 0),
     (2, 80, 12, 12, 80, 1, 1, 0),
+    # im2col kernel with more tiles than co-resident CTAs (persistent loops, both TMEM accumulators): even / odd tile counts, fast and
+    # general epilogues, the stride-2 dgrad parity classes
+    (9, 48, 192, 192, 96, 3, 2, 1),
+    (8, 96, 200, 200, 64, 1, 2, 0),
+    (9, 64, 96, 96, 80, 1, 1, 0),
 ]
 
 
