@@ -40,7 +40,7 @@ METRIC, WORKLOAD, IMG, BATCH = CONFIGS[2]["metric"], CONFIGS[2]["workload"], 640
 TRAIN_GFLOP_PER_IMG = CONFIGS[2]["gflop"]
 # dram__bytes_read.sum + dram__bytes_write.sum of the conv family over ONE step from a committed ncu launch list of this command
 # (None: not captured for that configuration); the JSON line names the file
-NCU_CONV_DRAM = {(2, 32): (20.988e9, "profiles/r1_launches_graph_step.txt")}
+NCU_CONV_DRAM = {(2, 32): (17.99e9, "profiles/r2_launches_graph_step.txt")}
 
 
 def synth_batch(batch, seed, img=640):

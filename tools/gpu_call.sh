@@ -76,6 +76,17 @@ case "${1}" in
     timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short --timeout 300 -x -k "conv_fprop" > gpurun_out/r2_pytest14.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest14.log
     for cfg in 1 0 1 0; do printf "OVERLAP_PREPARE=%s: " $cfg
       SGB_OVERLAP_PREPARE=$cfg timeout 400 python bench.py --steps 30 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench14_$cfg.err | tee gpurun_out/r2_bench14_$cfg.json | bench_line; tail -2 gpurun_out/r2_bench14_$cfg.err; done ;;
+  evidence_a)  # whole GPU suite + the four configuration bench lines
+    timeout 900 python -m pytest tests -m gpu -q --tb=short --timeout 300 > gpurun_out/r2_pytest_final.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2_pytest_final.log
+    printf "config 2 (default command): "; timeout 500 python bench.py 2>gpurun_out/r2_final_c2.err | tee gpurun_out/r2_final_c2.json | bench_line; tail -2 gpurun_out/r2_final_c2.err
+    for c in 3 4 5; do printf "config %d: " $c; timeout 400 python bench.py --config $c --steps 10 --warmup 3 --skip-cpu-baseline 2>gpurun_out/r2_final_c$c.err | tee gpurun_out/r2_final_c$c.json | bench_line; tail -2 gpurun_out/r2_final_c$c.err; done ;;
+  evidence_b)  # ncu: launch list of ONE graph step with DRAM traffic, --set full of the top kernels (eager step)
+    SGB_PROFILER_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv       --log-file gpurun_out/r2_launches_graph_step.csv python bench.py --steps 1 --warmup 3 --skip-cpu-baseline > gpurun_out/r2_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+    python tools/ncu_summary.py gpurun_out/r2_launches_graph_step.csv 60 > gpurun_out/r2_launches_graph_step.txt 2>&1; head -30 gpurun_out/r2_launches_graph_step.txt
+    for kn in wgrad_umma_kernel conv_umma_kernel chan_fused_kernel conv3x3_halo_kernel wgrad3x3_halo_kernel; do
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kn --launch-skip 12 --launch-count 4 -o gpurun_out/r2_full_$kn -f         python bench.py --steps 1 --warmup 1 --no-graph --skip-cpu-baseline > gpurun_out/r2_ncu_full_$kn.log 2>&1; echo "ncu $kn rc=$?"
+      ncu -i gpurun_out/r2_full_$kn.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py > gpurun_out/r2_full_$kn.txt 2>&1; head -20 gpurun_out/r2_full_$kn.txt
+    done ;;
   dp)  # N GPUs (gpurun --gpus N): split graphs around an eager all-reduce vs NCCL captured inside one graph
     N=${2:-2}
     for ig in 0 1; do
