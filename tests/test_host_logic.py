@@ -230,7 +230,14 @@ def test_zero_weight_decay_groups_match_reference(golden, name):
     decay = [n for n, _ in fs.order if fs.offsets[n][0] < fs.n_decay]
     no_decay = [n for n, _ in fs.order if fs.offsets[n][0] >= fs.n_decay]
     live = lambda names: [n for n in names if "rbr_reparam" not in n]  # noqa: E731
-    assert decay == live(g["decay"]) and no_decay == live(g["no_decay"])
+    # membership is the contract (which parameters decay); the ORDER inside the flat buffer is a layout choice -- FlatState moves the
+    # BatchNorm parameters of layers that share one GEMM next to each other (sgb_adjacent_tensors), everything else keeps the
+    # reference's order
+    assert sorted(decay) == sorted(live(g["decay"])) and sorted(no_decay) == sorted(live(g["no_decay"]))
+    assert decay == live(g["decay"])  # no adjacency request touches a decaying parameter
+    moved = [n for n in no_decay if ".conv2.bn." in n or ".reg_convs.0.seq.bn." in n]
+    rest = [n for n in no_decay if n not in moved]
+    assert rest == [n for n in live(g["no_decay"]) if n not in moved]
     assert any(n.endswith("alpha") for n in decay) or name == "resnet18_cifar"
 
 

@@ -26,15 +26,22 @@ def main():
     ap.add_argument("--model", default="yolo_nas_s")
     ap.add_argument("--top", type=int, default=70)
     ap.add_argument("--all", action="store_true", help="every C-ABI call, not only the convolutions")
+    ap.add_argument("--config", type=int, default=0, help="a bench.py training configuration (3: YOLO-NAS-M, 4: ResNet-50) instead of --model / --batch")
     args = ap.parse_args()
     dev = setup_device()
     torch.manual_seed(0)
-    model = models.get(args.model, num_classes=bench.NCLS).to(dev).train()
-    crit = PPYoloELoss(num_classes=bench.NCLS, use_static_assigner=False)
-    step = TrainStep(model, crit, "AdamW", {"weight_decay": 1e-5}, zero_wd_on_bias_and_bn=True, ema=True)
-    x, t = bench.synth_batch(args.batch, 0)
-    x = x.to(dev)
-    t = tuple(a.to(dev) for a in pad_targets_host(t, args.batch, bench.NBOX))
+    if args.config:
+        cfg = bench.CONFIGS[args.config]
+        args.model, args.batch = cfg["model"], cfg["batch"]
+        model, step, host = bench.build_train_workload(cfg, dev, 0, args.batch)
+        x, t = bench._to_dev(host[0], dev)
+    else:
+        model = models.get(args.model, num_classes=bench.NCLS).to(dev).train()
+        crit = PPYoloELoss(num_classes=bench.NCLS, use_static_assigner=False)
+        step = TrainStep(model, crit, "AdamW", {"weight_decay": 1e-5}, zero_wd_on_bias_and_bn=True, ema=True)
+        x, t = bench.synth_batch(args.batch, 0)
+        x = x.to(dev)
+        t = tuple(a.to(dev) for a in pad_targets_host(t, args.batch, bench.NBOX))
     for _ in range(3):
         step.set_hyper_params(2e-4, 0.9997)
         step._step_eager(x, t)
