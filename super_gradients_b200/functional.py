@@ -611,6 +611,90 @@ def conv_bn_act(x, w, gamma, beta, running_mean, running_var, num_batches_tracke
 KPAD = [__import__("os").environ.get("SGB_KPAD", "1") != "0"]
 
 
+# ------------------------------------------------------------------------------------------------------------ conv + BN stem on patches
+# ResNet's first layer (7 x 7, stride 2, 3 input channels; classification_models/resnet.py:199-200 of the reference) has no tcgen05
+# kernel of its own: padded to 16 channels it ran on the mma.sync implicit GEMM at 130-145 TF/s -- 2.2 ms forward + 2.5 ms weight
+# gradient of a 30 ms ResNet-50 step at batch 256.  Like the YOLO-NAS stem it becomes ONE 1 x 1 GEMM over gathered patches
+# (3 * 7 * 7 = 147 patch channels padded to 160): the gather reads the image once, forward and weight gradient are im2col-free
+# tcgen05 GEMMs, and there is no dgrad (the image needs no gradient).  Same products of the same bf16 operands, fp32 accumulation.
+STEM_PATCH_MAX_CHANNELS = 256
+
+
+def conv_stem_patches_supported(conv, bn, x, training) -> bool:
+    if not (STEM_PATCHES[0] and training and bn is not None and torch.is_tensor(x) and x.dim() == 4 and x.dtype == torch.float32 and not x.requires_grad):
+        return False
+    w = conv.weight
+    r, s = w.shape[2], w.shape[3]
+    return bool(conv.bias is None and conv.groups == 1 and r == s and r > 1 and x.shape[1] == w.shape[1] and w.shape[1] % 8 != 0
+                and w.shape[1] * r * s <= STEM_PATCH_MAX_CHANNELS and w.shape[0] % 8 == 0)  # fmt: skip
+
+
+class PatchWeightCache:
+    """fp32 [K, c_out, 1, 1] staging of a first-layer filter in patch-channel order (r, s, c) plus its bf16 KRSC copy."""
+
+    def __init__(self):
+        self.key = None
+        self.stage = None
+        self.inner = WeightCache(batched=False)
+
+    def get(self, w, c_out):
+        key = WeightCache._key(w, None, False, None, c_out)
+        if key != self.key:
+            kout, cin, r, s = w.shape
+            with torch.no_grad():
+                if self.stage is None or tuple(self.stage.shape) != (kout, c_out, 1, 1) or self.stage.device != w.device:
+                    self.stage = torch.zeros((kout, c_out, 1, 1), dtype=torch.float32, device=w.device)
+                self.stage.view(kout, c_out)[:, : cin * r * s].copy_(w.detach().permute(0, 2, 3, 1).reshape(kout, r * s * cin))
+            self.key = key
+        return self.inner.get(self.stage, c_pad=c_out, extra_key=key)
+
+
+class _ConvBnActStem(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, cfg):
+        kout, cin, r, s = w.shape
+        c_out = ((cin * r * s + 31) // 32) * 32
+        xp = K.stem_patches(x, r, cfg.stride, cfg.pad, c_out)
+        kf, _ = cfg.cache.get(w, c_out)
+        stats = None if K.stats_in_bn(kout, xp.shape[0] * xp.shape[2] * xp.shape[3]) else K.new_stats(kout, x.device)
+        y_raw = K.conv_fprop(xp, kf, kout, 1, 1, 1, 0, stats=stats)
+        out, mean, rstd = K.bn_act_fwd(y_raw, stats, gamma, beta, cfg.running_mean, cfg.running_var, cfg.eps, cfg.momentum, cfg.act)
+        if cfg.num_batches_tracked is not None and not _NBT_DEFERRED[0]:
+            cfg.num_batches_tracked += 1
+        ctx.save_for_backward(xp, y_raw, gamma, mean, rstd, beta)
+        ctx.cfg, ctx.geom = cfg, (kout, cin, r, s)
+        ctx.slots = (_mg(w), _mg(gamma), _mg(beta))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xp, y_raw, gamma, mean, rstd, beta = ctx.saved_tensors
+        cfg = ctx.cfg
+        kout, cin, r, s = ctx.geom
+        sw, sg, sb = ctx.slots
+        dy, _, dgamma, dbeta = K.bn_act_bwd(dout, y_raw, None, gamma, mean, rstd, cfg.eps, cfg.act, dgamma=sg, dbeta=sb, beta=beta)
+        c = _CTX[0]
+        if c is not None and c.side_stream is not None and sw is not None:
+            dwf = _side_wgrad(c, xp, dy, 1, 1, 1, 0)
+            c.stem_pending.append((dwf, kout, cin, r, s, sw, None))  # unpacked in flush_wgrads(), after the side stream joined
+            dw = None
+        else:
+            dwf = K.conv_wgrad(xp, dy, 1, 1, 1, 0)
+            dw = _deliver(sw, dwf.reshape(kout, dwf.shape[3])[:, : cin * r * s].reshape(kout, r, s, cin).permute(0, 3, 1, 2).contiguous())
+        return None, dw, (None if sg is not None else dgamma), (None if sb is not None else dbeta), None
+
+
+def conv_bn_act_stem(x, conv, bn, *, act, cache: PatchWeightCache):
+    """act(bn_train(conv(x))) of a first layer over a raw fp32 NCHW image as a 1 x 1 GEMM over gathered patches; the caller checked
+    conv_stem_patches_supported()."""
+    K.require_cuda(x, "x")
+    stride = conv.stride[0] if isinstance(conv.stride, (tuple, list)) else conv.stride
+    pad = conv.padding[0] if isinstance(conv.padding, (tuple, list)) else conv.padding
+    cfg = SimpleNamespace(stride=int(stride), pad=int(pad), eps=bn.eps, momentum=0.1 if bn.momentum is None else bn.momentum, act=act, cache=cache,
+                          running_mean=bn.running_mean, running_var=bn.running_var, num_batches_tracked=bn.num_batches_tracked)  # fmt: skip
+    return _ConvBnActStem.apply(x, conv.weight, bn.weight, bn.bias, cfg)
+
+
 # ------------------------------------------------------------------------------------------------------------ two conv + BN on one input
 # A CSP layer applies two 1x1 ConvBNAct layers to the same tensor (yolo_stages.py:104-106 of the reference: conv1, conv2).  Separately
 # that is 2 GEMMs reading x twice, 2 BatchNorm passes, and in backward 2 BatchNorm passes, 2 dgrads whose results autograd adds with an
@@ -992,6 +1076,8 @@ def _unpack_stem_wgrad(dwf, kout, cin, r, s, sw3, sw1):
     """dwf fp32 [2K, 1, 1, c_out] (gradient of the staged patch filter) -> += into the two OIHW gradient slots."""
     g = dwf.reshape(dwf.shape[0], dwf.shape[3])
     sw3.add_(g[:kout, : cin * r * s].reshape(kout, r, s, cin).permute(0, 3, 1, 2))
+    if sw1 is None:  # a plain conv + BN stem (functional._ConvBnActStem): one filter
+        return
     ctr = ((r // 2) * s + s // 2) * cin
     sw1.add_(g[kout:, ctr : ctr + cin].reshape(kout, cin, 1, 1))
 

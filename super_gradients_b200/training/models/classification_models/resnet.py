@@ -143,10 +143,14 @@ class ResNet(_Classifier):
         self.avgpool = nn.AdaptiveAvgPool2d(1)
         self.width_mult = width_mult
         self._stem_cache, self._fc_cache = SF.WeightCache(), SF.WeightCache()
+        self._stem_patch_cache = SF.PatchWeightCache()
 
     def forward(self, x):
-        x = SF.to_nhwc(x)
-        out = self._fused(x, self.conv1, self.bn1, "relu", self._stem_cache)
+        if SF.conv_stem_patches_supported(self.conv1, self.bn1, x, self.training and self.bn1.training):
+            out = SF.conv_bn_act_stem(x, self.conv1, self.bn1, act="relu", cache=self._stem_patch_cache)  # 7x7 / s2 as a 1x1 GEMM over patches
+        else:
+            x = SF.to_nhwc(x)
+            out = self._fused(x, self.conv1, self.bn1, "relu", self._stem_cache)
         out = SF.max_pool(out, 3, 2, 1)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         return self._head(out)

@@ -145,6 +145,57 @@ def test_patch_stem_matches_the_two_convolution_path(monkeypatch):
     assert lib.load() is not None
 
 
+def test_resnet_stem_on_patches_matches_the_direct_convolution(monkeypatch):
+    """ResNet's 7 x 7 / stride-2 first layer as ONE 1 x 1 GEMM over gathered patches (functional._ConvBnActStem; 147 patch channels
+    padded to 160): same output, weight / BatchNorm gradients and running statistics as the direct convolution over the 16-channel-
+    padded image (the mma.sync path it replaces), and as fp32 torch on the same bf16-rounded operands; the 7 x 7 gather against unfold."""
+    import torch.nn.functional as F
+
+    from super_gradients_b200 import functional as SF
+    from super_gradients_b200 import kernels as K
+    from super_gradients_b200.training import models
+
+    def run(patches, shape):
+        monkeypatch.setattr(SF, "STEM_PATCHES", [patches])
+        torch.manual_seed(5)
+        net = models.get("resnet18", num_classes=10)
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        net = net.to(DEV).train()
+        x = torch.randn(*shape).bfloat16().float()
+        assert SF.conv_stem_patches_supported(net.conv1, net.bn1, x.to(DEV), True) == patches
+        xg = x.to(DEV)
+        if patches:
+            out = SF.conv_bn_act_stem(xg, net.conv1, net.bn1, act="relu", cache=net._stem_patch_cache)
+        else:
+            out = net._fused(SF.to_nhwc(xg), net.conv1, net.bn1, "relu", net._stem_cache)
+        gy = torch.linspace(-1, 1, out.numel()).reshape(out.shape).bfloat16()
+        out.backward(gy.to(DEV))
+        torch.cuda.synchronize()
+        grads = {k: p.grad.cpu().clone() for k, p in net.named_parameters() if p.grad is not None}
+        return x, sd0, gy, out.detach().float().cpu(), grads, {k: v.cpu().clone() for k, v in net.state_dict().items() if k.startswith("bn1.running")}
+
+    for shape in ((2, 3, 64, 96), (3, 3, 70, 54)):
+        x, sd0, gy, y0, g0, r0 = run(False, shape)
+        _, _, _, y1, g1, r1 = run(True, shape)
+        assert ((y1 - y0).abs() <= y0.abs() * 2**-7 + 1e-3).all(), float((y1 - y0).abs().max())
+        assert set(g0) == set(g1) == {"conv1.weight", "bn1.weight", "bn1.bias"}
+        for k in g0:
+            assert l2rel(g1[k], g0[k]) < 1e-2, (k, l2rel(g1[k], g0[k]))
+        for k in r0:
+            assert l2rel(r1[k], r0[k]) < 1e-4, k
+        # fp32 torch on the same bf16 operands
+        w = sd0["conv1.weight"].bfloat16().float().requires_grad_(True)
+        gam, bet = sd0["bn1.weight"].clone().requires_grad_(True), sd0["bn1.bias"].clone().requires_grad_(True)
+        ref = F.relu(F.batch_norm(F.conv2d(x, w, stride=2, padding=3), None, None, gam, bet, True, 0.1, 1e-5))
+        ref.backward(gy.float())
+        assert l2rel(y1, ref.detach()) < 5e-3, l2rel(y1, ref.detach())
+        assert l2rel(g1["conv1.weight"], w.grad) < 2e-2 and l2rel(g1["bn1.weight"], gam.grad) < 1e-2
+    xs = torch.randn(2, 3, 37, 41, device=DEV)
+    got = K.stem_patches(xs, 7, 2, 3, 160).float()
+    cols = F.unfold(xs, 7, padding=3, stride=2).reshape(2, 3, 49, 19, 21).permute(0, 2, 1, 3, 4).reshape(2, 147, 19, 21)
+    assert torch.equal(got[:, :147], cols.bfloat16().float()) and float(got[:, 147:].abs().max()) == 0.0
+
+
 def test_backward_reads_a_concat_gradient_slice_in_place():
     """A block whose output feeds a channel concat receives its gradient as a channel SLICE of the concat's gradient buffer.  The
     BatchNorm / QARepVGG backward kernels read that slice in place (SgbBnDesc.dy_pitch, SgbQarepDesc.pitchd) -- round 1 made a

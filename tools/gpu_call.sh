@@ -87,6 +87,11 @@ case "${1}" in
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kn --launch-skip 12 --launch-count 4 -o gpurun_out/r2_full_$kn -f         python bench.py --steps 1 --warmup 1 --no-graph --skip-cpu-baseline > gpurun_out/r2_ncu_full_$kn.log 2>&1; echo "ncu $kn rc=$?"
       ncu -i gpurun_out/r2_full_$kn.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py > gpurun_out/r2_full_$kn.txt 2>&1; head -20 gpurun_out/r2_full_$kn.txt
     done ;;
+  fifteenth)  # ResNet 7x7 stem as a 1x1 GEMM over gathered patches
+    timeout 600 python -m pytest tests/test_modules_gpu.py tests/test_kernels_gpu.py -m gpu -q --tb=short --timeout 300 -x -k "stem or resnet or patch" > gpurun_out/r2_pytest15.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2_pytest15.log
+    timeout 600 python -m pytest tests/test_zz_pose_train_gpu.py -m gpu -q --tb=short --timeout 300 -x -k "resnet" > gpurun_out/r2_pytest15b.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest15b.log
+    for sp in 1 0; do printf "config 4 STEM_PATCHES=%s: " $sp; SGB_STEM_PATCHES=$sp timeout 400 python bench.py --config 4 --steps 10 --warmup 3 --skip-cpu-baseline 2>gpurun_out/r2_bench15_$sp.err | tee gpurun_out/r2_bench15_$sp.json | bench_line; tail -2 gpurun_out/r2_bench15_$sp.err; done
+    timeout 400 python tools/conv_table.py --config 4 --all --top 24 > gpurun_out/r2_conv_table_resnet50_b.txt 2>gpurun_out/r2_conv_table_resnet50_b.err; tail -3 gpurun_out/r2_conv_table_resnet50_b.err; cat gpurun_out/r2_conv_table_resnet50_b.txt ;;
   dp)  # N GPUs (gpurun --gpus N): split graphs around an eager all-reduce vs NCCL captured inside one graph
     N=${2:-2}
     for ig in 0 1; do
