@@ -501,6 +501,22 @@ extern "C" int sgb_conv_fprop(const SgbConvDesc* d, const sgb_bf16* x, const sgb
       q.stats_repl = 1;
     }
     if (d->pad == d->R / 2 && sm100::supported(q)) return sm100::launch(q, (cudaStream_t)stream);
+    // 2 x 2 / stride 2 / no padding over a dense tensor (the backward of ConvTranspose2d(2, 2), modules/sampling.py:72-73): the
+    // patches do not overlap, so the tensor viewed as an image [N * H/2][2][W/2][2C] -- row pair, row parity, column pair, (column
+    // parity, channel) -- turns the layer into a 2-tap (rows 0 and 1), stride-1 valid convolution with 2C channels per tap whose
+    // B columns are the filter's own (dh, dw, c) order: the im2col tcgen05 kernel serves it through its explicit tap table.
+    if (sm100::enabled() && d->R == 2 && d->S == 2 && d->stride == 2 && d->pad == 0 && d->x_pitch == d->C && d->x_off == 0 && d->H % 2 == 0 &&
+        d->W % 2 == 0 && d->P == d->H / 2 && d->Q == d->W / 2 && (2 * d->C) % 16 == 0 && d->K % 8 == 0 && d->y_pitch % 8 == 0 && d->y_off % 8 == 0 &&
+        (long long)d->N * (d->H / 2) < (1ll << 31)) {
+      q.N = d->N * (d->H / 2); q.H = 2; q.W = d->W / 2; q.C = 2 * d->C; q.a_pitch = 2 * d->C;
+      q.b_cols_per_tap = 2 * d->C;
+      q.R = 1; q.S = 1; q.stride = 1; q.pad = 0; q.P = 1; q.Q = d->W / 2;
+      q.ntaps = 2;
+      q.tap_dh[0] = 0; q.tap_dw[0] = 0; q.tap_b[0] = 0;
+      q.tap_dh[1] = 1; q.tap_dw[1] = 0; q.tap_b[1] = 1;
+      if (sm100::supported(q)) return sm100::launch(q, (cudaStream_t)stream);
+      return SGB_E_UNSUPPORTED;
+    }
   }
   IGemmParams p{};
   p.A = reinterpret_cast<const bf16*>(x);
@@ -739,6 +755,14 @@ extern "C" int sgb_conv_wgrad(const SgbConvDesc* d, const sgb_bf16* x, const sgb
     q.R = d->R; q.S = d->S; q.stride = d->stride; q.pad = d->pad; q.P = d->P; q.Q = d->Q;
     q.dw = dw;
     if (sm100::wgrad_supported(q)) return sm100::wgrad_launch(q, (cudaStream_t)stream);
+    // 2 x 2 / stride 2 / no padding over a dense x: the same re-description as in sgb_conv_fprop -- a (2 x 1)-tap stride-1 valid
+    // convolution over the image [N * H/2][2][W/2][2C]; dW rows [K][dh][(dw, c)] are the KRSC rows of the 2 x 2 filter.
+    if (sm100::enabled() && d->R == 2 && d->S == 2 && d->stride == 2 && d->pad == 0 && d->x_pitch == d->C && d->x_off == 0 && d->H % 2 == 0 &&
+        d->W % 2 == 0 && d->P == d->H / 2 && d->Q == d->W / 2 && (2 * d->C) % 16 == 0 && d->K % 8 == 0 && (long long)d->N * (d->H / 2) < (1ll << 31)) {
+      q.N = d->N * (d->H / 2); q.H = 2; q.W = d->W / 2; q.C = 2 * d->C; q.x_pitch = 2 * d->C;
+      q.R = 2; q.S = 1; q.stride = 1; q.pad = 0; q.P = 1; q.Q = d->W / 2;
+      return sm100::wgrad_launch(q, (cudaStream_t)stream);
+    }
   }
   WgradParams p{};
   p.X = reinterpret_cast<const bf16*>(x);

@@ -90,6 +90,10 @@ CONV_CASES = [
     (9, 48, 192, 192, 96, 3, 2, 1),
     (8, 96, 200, 200, 64, 1, 2, 0),
     (9, 64, 96, 96, 80, 1, 1, 0),
+    # 2 x 2 / stride 2 (ConvTranspose backward) re-described as a 2-tap valid convolution over [N * H/2][2][W/2][2C] on the tcgen05 kernels
+    (4, 96, 40, 40, 96, 2, 2, 0),
+    (2, 192, 20, 20, 192, 2, 2, 0),
+    (3, 32, 18, 22, 48, 2, 2, 0),
 ]
 
 
@@ -113,7 +117,7 @@ def test_conv_fprop_dgrad_wgrad(case):
 
     n_sm100 = lib.load().sgb_sm100_launches()
     y = k.conv_fprop(xg, krsc, kk, r, r, stride, pad, stats=stats)
-    if c % 16 == 0 and kk % 8 == 0 and r in (1, 3) and pad == r // 2:
+    if c % 16 == 0 and kk % 8 == 0 and ((r in (1, 3) and pad == r // 2) or (r == 2 and stride == 2 and pad == 0 and h % 2 == 0 and w % 2 == 0)):
         assert lib.load().sgb_sm100_launches() == n_sm100 + 1, "the tcgen05/TMA kernel should have served this shape"
     yc = y.float().cpu()
     # absolute floor: fp32 accumulation noise of a c*r*r-term sum whose result cancels to ~0
