@@ -205,6 +205,11 @@ typedef struct SgbQarepDesc {
   int32_t act;
   int32_t use_post_bn;
   int32_t pitchd, offd; /* backward passes: layout of dout when it is a channel slice; pitchd == 0: laid out like out */
+  /* forward passes: out = act(...) + (*res_alpha) * res -- the learnable shortcut of a YOLO-NAS bottleneck
+   * (training/models/detection_models/yolo_nas/yolo_stages.py:61-63) fused into its second block.  res == NULL: none. */
+  int32_t pitchr, offr;
+  const void* res;
+  const float* res_alpha;
 } SgbQarepDesc;
 int sgb_qarep_moments(const SgbQarepDesc* d, const sgb_bf16* y3, const sgb_bf16* u, double* moments, void* stream);
 /* coef out: [9][C] floats = mu3, rstd3, mu_u, rstd_z, a3 (coefficient of y3), au (of u), c0 (constant),

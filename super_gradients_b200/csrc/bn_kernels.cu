@@ -473,7 +473,10 @@ struct QarepMomOp {
   }
 };
 
-struct QarepFwdOp {
+// RES: out = act(a3*y3 + au*u + c0) + (*res_alpha) * res -- a YOLO-NAS bottleneck's learnable shortcut (yolo_stages.py:61-63 of the
+// reference: alpha * x + cv2(cv1(x))) fused into its second block's apply pass instead of a scale_add pass of its own.
+template <bool RES>
+struct QarepFwdOpT {
   static constexpr int NCOEF = 3, NACC = 0;
   SgbQarepDesc d;
   const bf16 *y3, *u;
@@ -540,17 +543,31 @@ struct QarepFwdOp {
       }
     }
   }
-  static constexpr int NIN = 2, UNROLL = 2, DEPTH = 4;  // 64 KB ring: two CTAs per SM
-  __device__ const bf16* base(int j, int c0) const { return j == 0 ? y3 + d.off3 + c0 : u + d.offu + c0; }
-  __device__ int pitch(int j, int) const { return j == 0 ? d.pitch3 : d.pitchu; }
-  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[2], const float (&r)[3][8], float (&)[1][8]) const {
+  static constexpr int NIN = RES ? 3 : 2, UNROLL = 2, DEPTH = RES ? 3 : 4;  // 64 KB ring (72 KB with the shortcut): two CTAs per SM
+  __device__ const bf16* base(int j, int c0) const {
+    if (j == 0) return y3 + d.off3 + c0;
+    if (j == 1) return u + d.offu + c0;
+    return reinterpret_cast<const bf16*>(d.res) + d.offr + c0;
+  }
+  __device__ int pitch(int j, int) const { return j == 0 ? d.pitch3 : (j == 1 ? d.pitchu : d.pitchr); }
+  __device__ void finish(int64_t pix, int c0, const uint4 (&raw)[NIN], const float (&r)[3][8], float (&)[1][8]) const {
     V8 a = unpack8(raw[0]);
     const V8 b = unpack8(raw[1]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) a.v[e] = apply_act(fmaf(r[0][e], a.v[e], fmaf(r[1][e], b.v[e], r[2][e])), d.act);
+    if constexpr (RES) {
+      // the block's own output is rounded to bf16 first, exactly as when it was stored and re-read by a separate scale_add pass:
+      // the fused form is bit-identical to the two-pass form
+      const V8 x = unpack8(raw[NIN - 1]);
+      const float al = __ldg(d.res_alpha);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = fmaf(al, x.v[e], __bfloat162float(__float2bfloat16_rn(a.v[e])));
+    }
     st8(outp + pix * d.pitcho + d.offo + c0, a);
   }
 };
+using QarepFwdOp = QarepFwdOpT<false>;
+using QarepFwdResOp = QarepFwdOpT<true>;
 
 // coefficient rows: 0 mu3, 1 rstd3, 2 mu_u, 3 rstd_z, 4 a3, 5 au, 6 c0, 7 s3
 struct QarepBwdRedOp {
@@ -697,6 +714,8 @@ int check_qarep(const SgbQarepDesc* d) {
                   d->pitcho % 8 == 0 && d->offo % 8 == 0 && d->pitchd % 8 == 0 && d->offd % 8 == 0,
               "pitch/offset multiples of 8");
   SGB_REQUIRE(d->pitchd == 0 || d->pitchd >= d->offd + d->C, "dout slice layout");
+  SGB_REQUIRE(!d->res || (d->res_alpha && d->pitchr % 8 == 0 && d->offr % 8 == 0 && d->pitchr >= d->offr + d->C && ((uintptr_t)d->res & 15) == 0),
+              "shortcut tensor layout");
   return SGB_OK;
 }
 
@@ -773,6 +792,10 @@ extern "C" int sgb_qarep_fwd(const SgbQarepDesc* d, const sgb_bf16* y3, const sg
   if (int rc = check_qarep(d)) return rc;
   SGB_REQUIRE(y3 && u && moments && gamma3 && beta3 && out && coef, "null pointer");
   SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
+  if (d->res) {
+    QarepFwdResOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
+    return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd (shortcut)");
+  }
   QarepFwdOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
   return launch_chan(op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd");
 }
@@ -784,6 +807,10 @@ extern "C" int sgb_qarep_fwd_fused(const SgbQarepDesc* d, const sgb_bf16* y3, co
   SGB_REQUIRE(y3 && u && moments && gamma3 && beta3 && out && coef, "null pointer");
   SGB_REQUIRE(!d->use_post_bn || (gamma_p && beta_p), "post_bn parameters missing");
   QarepMomOp mo{*d, (const bf16*)y3, (const bf16*)u, moments, d->C};
+  if (d->res) {
+    QarepFwdResOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
+    return launch_chan_fused(mo, op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd_fused (shortcut)");
+  }
   QarepFwdOp op{*d, (const bf16*)y3, (const bf16*)u, (bf16*)out, moments, gamma3, beta3, bias1_alpha, gamma_p, beta_p, rm3, rv3, rm_p, rv_p, coef};
   return launch_chan_fused(mo, op, d->M, d->C, (cudaStream_t)stream, "qarep_fwd_fused");
 }

@@ -914,7 +914,10 @@ class _QARepVGG(torch.autograd.Function):
         ab = None
         if bias1 is not None:
             ab = bias1 * alpha if alpha is not None else bias1
-        out, coef = K.qarep_fwd(y3, u, g3, b3, ab, gp, bp, cfg.rm3, cfg.rv3, cfg.rmp, cfg.rvp, cfg.eps, cfg.eps, cfg.momentum, cfg.act, cfg.use_post_bn)
+        sc = getattr(cfg, "shortcut", None)  # (x_s, alpha_s, token): out += alpha_s * x_s in the apply pass (a bottleneck's shortcut)
+        skw = {"residual": sc[0], "res_alpha": sc[1]} if sc is not None else {}
+        out, coef = K.qarep_fwd(y3, u, g3, b3, ab, gp, bp, cfg.rm3, cfg.rv3, cfg.rmp, cfg.rvp, cfg.eps, cfg.eps, cfg.momentum, cfg.act, cfg.use_post_bn, **skw)
+        ctx.shortcut = sc
         if not _NBT_DEFERRED[0]:
             for nbt in cfg.nbt:
                 if nbt is not None:
@@ -933,6 +936,11 @@ class _QARepVGG(torch.autograd.Function):
         cfg = ctx.cfg
         has_bias, has_alpha, has_post, cin = ctx.flags
         sw3, sg3, sb3, sw1, sbias, salpha, sgp, sbp = ctx.slots
+        if ctx.shortcut is not None:
+            # out = act(...) + alpha_s * x_s: the shortcut's gradient (alpha_s * dout into x_s's gradient, sum(dout * x_s) into alpha_s's)
+            # is finished by the block that consumes x_s, after its own dgrad (_defer_finish); nothing is launched here
+            xs, alpha_s, tok_s = ctx.shortcut
+            tok_s.pending = (K.as_nhwc(dout), alpha_s, K.as_nhwc(xs), alpha_s.main_grad)
         direct_bias = sbias if not has_alpha else None  # d(alpha*b1) == d(b1) when alpha is the constant 1
         dcat = None
         if ctx.fold:  # [dy3 | du] in one buffer: one dgrad and one wgrad launch consume it
@@ -1021,6 +1029,9 @@ class _QARepVGG(torch.autograd.Function):
             dbias1 = (None if sbias is not None else dab) if has_bias else None
         ret = lambda slot, v: None if slot is not None else v  # noqa: E731
         return dx, dw3, ret(sg3, dg3), ret(sb3, db3), dw1, dbias1, dalpha, (ret(sgp, dgp) if has_post else None), (ret(sbp, dbp) if has_post else None), None
+
+
+FUSE_SHORTCUT = [__import__("os").environ.get("SGB_FUSE_SHORTCUT", "1") != "0"]
 
 
 def qarepvgg_block(x, w3, g3, b3, w1, bias1, alpha, gp, bp, cfg):

@@ -555,10 +555,17 @@ def qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn) -> L.Qare
     return d
 
 
-def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp, eps3, eps_post, momentum, act, use_post_bn=True):
+def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp, eps3, eps_post, momentum, act, use_post_bn=True, residual=None, res_alpha=None):
+    """residual / res_alpha: out = act(...) + res_alpha * residual (device scalar): a bottleneck's learnable shortcut in the same pass."""
     n, c, h, w = y3.shape
     out = empty_nhwc(n, c, h, w, y3.device)
     d = qarep_desc(y3, u, out, eps3, eps_post, momentum, act, use_post_bn)
+    if residual is not None:
+        residual = as_nhwc(residual)
+        if tuple(residual.shape) != tuple(y3.shape) or res_alpha is None or res_alpha.dtype != torch.float32 or res_alpha.numel() != 1:
+            raise L.SgbError("qarep_fwd: the shortcut must have the output's shape and a one-element fp32 device scale")
+        require_cuda(res_alpha, "res_alpha")
+        d.pitchr, d.offr, d.res, d.res_alpha = nhwc_pitch(residual), 0, residual.data_ptr(), res_alpha.data_ptr()
     mom = zeros((5, c), torch.float64, y3.device)
     coef = torch.empty((9, c), dtype=torch.float32, device=y3.device)
     if FUSED_FWD[0]:  # moments, grid barrier, apply in one cooperative launch

@@ -88,6 +88,10 @@ class QarepDesc(Structure):
         ("use_post_bn", c_int32),
         ("pitchd", c_int32),
         ("offd", c_int32),
+        ("pitchr", c_int32),
+        ("offr", c_int32),
+        ("res", c_void_p),
+        ("res_alpha", c_void_p),
     ]
 
 

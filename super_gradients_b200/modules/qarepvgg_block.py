@@ -85,8 +85,14 @@ class QARepVGGBlock(nn.Module):
             self.fuse_block_residual_branches()
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, inputs):
+    def takes_shortcut(self) -> bool:
+        """True when forward(inputs, shortcut=...) can add a caller's `alpha * x` in its own apply pass (the unfused train-mode path)."""
+        return self.training and not self.fully_fused and not self.partially_fused and self.in_channels % 8 == 0
+
+    def forward(self, inputs, shortcut=None):
         K.require_cuda(inputs, "inputs")
+        if shortcut is not None and not self.takes_shortcut():
+            raise RuntimeError("QARepVGGBlock: a fused shortcut needs the train-mode branch path (takes_shortcut())")
         if self.fully_fused:
             return SF.conv_bias(inputs, self.rbr_reparam.weight, self.rbr_reparam.bias, stride=self.stride, pad=1, cache=self._cache_eq, act=self._act_code)
         if self.partially_fused:
@@ -112,6 +118,8 @@ class QARepVGGBlock(nn.Module):
             )  # fmt: skip
             if pbn is not None and pbn.eps != bn3.eps:
                 raise NotImplementedError("branch and post BatchNorm must share eps")
+            if shortcut is not None:
+                cfg.shortcut = shortcut
             alpha = self.alpha if isinstance(self.alpha, torch.Tensor) else None
             return SF.qarepvgg_block(
                 inputs, self.branch_3x3.conv.weight, bn3.weight, bn3.bias, self.branch_1x1.weight, self.branch_1x1.bias, alpha,

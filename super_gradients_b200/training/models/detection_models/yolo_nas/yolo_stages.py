@@ -36,6 +36,10 @@ class YoloNASBottleneck(nn.Module):
         tok = SF.defer_shortcut_offer(x, self.alpha) if learnable and self.training else None
         h = self.cv1(x)
         tok = SF.defer_shortcut_withdraw(x, tok)  # not None: cv1's backward finishes the shortcut's input gradient (functional._defer_finish)
+        if tok is not None and SF.FUSE_SHORTCUT[0] and getattr(self.cv2, "takes_shortcut", lambda: False)():
+            # alpha * x joins cv2's own apply pass (one launch and two tensor passes fewer than a scale_add after it); cv2's backward
+            # parks the shortcut's gradient for cv1's backward exactly as _ScaledAdd would
+            return self.cv2(h, shortcut=(x, self.alpha, tok))
         y = self.cv2(h)
         if not self.add:
             return y

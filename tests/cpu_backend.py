@@ -409,22 +409,34 @@ def _qarep_pre(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, eps3, eps_post, us
     return zp, (m3, v3, mz, vz)
 
 
-def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp, eps3, eps_post, momentum, act, use_post_bn=True):
+def qarep_fwd(y3, u, gamma3, beta3, bias1a, gamma_p, beta_p, rm3, rv3, rmp, rvp, eps3, eps_post, momentum, act, use_post_bn=True, residual=None, res_alpha=None):
     n, c, h, w = y3.shape
     M = n * h * w
     f = lambda t: None if t is None else t.detach().float()  # noqa: E731
     pre, (m3, v3, mz, vz) = _qarep_pre(y3.float(), u.float(), f(gamma3), f(beta3), f(bias1a), f(gamma_p), f(beta_p), eps3, eps_post, use_post_bn)
     out = K.empty_nhwc(n, c, h, w, y3.device)
-    out.copy_(_bf16(_act(pre, act)))
+    res = _act(pre, act)
+    if residual is not None:  # the bottleneck's learnable shortcut in the same pass; the block's own output is rounded first, like the kernel
+        res = res_alpha.detach().float() * residual.float() + _bf16(res).float()
+    out.copy_(_bf16(res))
     _update_running(rm3, rv3, m3, v3, M, momentum)
     if use_post_bn:
         _update_running(rmp, rvp, mz, vz, M, momentum)
-    return out, torch.zeros((9, c), dtype=torch.float32)  # the coefficient table is private to the CUDA kernels
+    coef = torch.zeros((9, c), dtype=torch.float32)  # the coefficient table is private to the CUDA kernels
+    if residual is not None:
+        # the kernels recompute the activation mask from y3, u and the coefficient table (they never read `out`); with a shortcut added
+        # `out` no longer carries the mask, so the stand-in keeps it next to its (otherwise empty) coefficient table
+        _QAREP_MASK[coef.data_ptr()] = (coef, pre > 0)
+    return out, coef
+
+
+_QAREP_MASK = {}
 
 
 def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_post_bn=True, acc=None, out_grads=None):
     n, c, h, w = y3.shape
-    dpre = _mask(dout, out, act)
+    kept = _QAREP_MASK.pop(coef.data_ptr(), None)
+    dpre = dout.float() * kept[1] if kept is not None and K.act_code(act) == K.ACT_RELU else _mask(dout, out, act)
     leaf = lambda t: t.detach().float().clone().requires_grad_(True)  # noqa: E731
     y3l, ul, g3l = leaf(y3), leaf(u), leaf(gamma3)
     b3l, abl = torch.zeros(c, requires_grad=True), torch.zeros(c, requires_grad=True)  # additive constants: only their gradients matter

@@ -1022,8 +1022,19 @@ def test_dual_conv_and_deferred_shortcut_are_the_same_csp_layer(golden, monkeypa
     from super_gradients_b200.training.models.detection_models.yolo_nas.yolo_stages import YoloNASCSPLayer
 
     cpu_backend.install_training(monkeypatch)
-    calls = {"fwd": 0, "bwd2": 0, "sad_acc": 0}
-    bn_fwd, bn_bwd, sad = Kmod.bn_act_fwd, Kmod.bn_act_bwd, Kmod.scale_add_dot
+    calls = {"fwd": 0, "bwd2": 0, "sad_acc": 0, "scale_add": 0, "qfwd_res": 0}
+    bn_fwd, bn_bwd, sad, sadd, qfwd = Kmod.bn_act_fwd, Kmod.bn_act_bwd, Kmod.scale_add_dot, Kmod.scale_add, Kmod.qarep_fwd
+
+    def count_sadd(*a, **k):
+        calls["scale_add"] += 1
+        return sadd(*a, **k)
+
+    def count_qfwd(*a, **k):
+        calls["qfwd_res"] += k.get("residual") is not None
+        return qfwd(*a, **k)
+
+    monkeypatch.setattr(Kmod, "scale_add", count_sadd)
+    monkeypatch.setattr(Kmod, "qarep_fwd", count_qfwd)
 
     def count_fwd(x, *a, **k):
         calls["fwd"] += 1
@@ -1065,6 +1076,8 @@ def test_dual_conv_and_deferred_shortcut_are_the_same_csp_layer(golden, monkeypa
     y1, dx1, g1, b1, c1 = run(True, True)
     # separate layers: pre, conv1, conv2, conv3 = 4 BatchNorm forwards; merged: 3, one two-source backward, one in-place shortcut pass per bottleneck
     assert (c0["fwd"], c0["bwd2"], c0["sad_acc"]) == (4, 0, 0) and (c1["fwd"], c1["bwd2"], c1["sad_acc"]) == (3, 1, 2), (c0, c1)
+    # the shortcut alpha * x + cv2(...) joins cv2's apply pass (bit-identical: the block's output is rounded before the add): no scale_add launch
+    assert (c0["scale_add"], c0["qfwd_res"]) == (2, 0) and (c1["scale_add"], c1["qfwd_res"]) == (0, 2), (c0, c1)
     assert torch.equal(y0, y1)  # per-channel arithmetic: the merged forward is the same computation
     torch.testing.assert_close(b1, b0, rtol=1e-6, atol=1e-7)
     assert l2rel(dx1, dx0) < 8e-3, l2rel(dx1, dx0)  # one bf16 rounding of the merged dgrad's sum instead of two + an add

@@ -196,6 +196,49 @@ def test_resnet_stem_on_patches_matches_the_direct_convolution(monkeypatch):
     assert torch.equal(got[:, :147], cols.bfloat16().float()) and float(got[:, 147:].abs().max()) == 0.0
 
 
+def test_csp_layer_merged_launches_match_the_separate_layers(monkeypatch):
+    """On the device: conv1 / conv2 of a CSP layer as ONE GEMM + ONE BatchNorm launch over adjacent parameters with a two-source
+    backward (functional._DualConvBnAct, SgbBnDesc.dy2), the bottleneck shortcut's gradient finished in place after cv1's dgrad
+    (functional._defer_finish) and the shortcut itself fused into cv2's apply pass (SgbQarepDesc.res) against the same layer with
+    every switch off: identical output (per-channel arithmetic, the fused shortcut rounds like the two-pass form), input and parameter
+    gradients equal up to the bf16 rounding of one merged dgrad sum; statistics-in-BatchNorm layers included (96 + 96 channels)."""
+    from super_gradients_b200 import functional as SF
+    from super_gradients_b200.modules import Conv, QARepVGGBlock
+    from super_gradients_b200.training.flat_state import FlatState
+    from super_gradients_b200.training.models.detection_models.yolo_nas.yolo_stages import YoloNASCSPLayer
+
+    def run(on, cin, hid, shape):
+        for name in ("DUAL_CONV", "DEFER_SHORTCUT", "FUSE_SHORTCUT"):
+            monkeypatch.setattr(SF, name, [on])
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(Conv(16, cin, 1, stride=1, activation_type=torch.nn.ReLU), YoloNASCSPLayer(cin, cin, 2, QARepVGGBlock, torch.nn.ReLU, True, True, hidden_channels=hid))
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        net = net.to(DEV).train()
+        flat = FlatState(net)
+        assert SF.dual_conv_bn_act_ready(net[1].conv1.conv, net[1].conv1.bn, net[1].conv2.conv, net[1].conv2.bn) == on
+        x = torch.randn(*shape).bfloat16().to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = net(x)
+        gy = torch.linspace(-1, 1, y.numel()).reshape(y.shape).bfloat16().to(DEV)
+        y.backward(gy)
+        torch.cuda.synchronize()
+        return y.detach().float().cpu(), x.grad.float().cpu(), {n: flat.grad_of(n).cpu().clone() for n, _ in flat.order}, flat.buffers.cpu().clone()
+
+    for cin, hid, shape in ((32, 16, (2, 16, 24, 20)), (64, 96, (3, 16, 17, 13))):
+        y0, dx0, g0, b0 = run(False, cin, hid, shape)
+        y1, dx1, g1, b1 = run(True, cin, hid, shape)
+        assert torch.equal(y0, y1), float((y0 - y1).abs().max())
+        torch.testing.assert_close(b1, b0, rtol=1e-5, atol=1e-6)
+        assert l2rel(dx1, dx0) < 8e-3, l2rel(dx1, dx0)
+        scale = max(float(v.norm()) for v in g0.values())
+        for k in g0:
+            if float(g0[k].norm()) < 1e-4 * scale:
+                assert float(g1[k].norm()) < 1e-3 * scale, k
+                continue
+            assert l2rel(g1[k], g0[k]) < 2e-2, (k, l2rel(g1[k], g0[k]))
+
+
 def test_backward_reads_a_concat_gradient_slice_in_place():
     """A block whose output feeds a channel concat receives its gradient as a channel SLICE of the concat's gradient buffer.  The
     BatchNorm / QARepVGG backward kernels read that slice in place (SgbBnDesc.dy_pitch, SgbQarepDesc.pitchd) -- round 1 made a
