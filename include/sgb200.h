@@ -253,6 +253,10 @@ int sgb_maxpool_fwd(const sgb_bf16* x, int N, int H, int W, int C, int x_pitch, 
                     sgb_bf16* y, int P, int Q, int y_pitch, int y_off, uint8_t* idx, void* stream);
 int sgb_maxpool_bwd(const sgb_bf16* dy, int N, int H, int W, int C, int k, int stride, int pad, int P, int Q,
                     int dy_pitch, int dy_off, const uint8_t* idx, float* dx_f32, void* stream);
+/* The same gradient written as bf16 by a gather (every input pixel sums the dy of the <= ceil(k/stride)^2 windows whose arg-max is that
+ * pixel): no zeroed fp32 tensor, no atomics, no conversion pass.  Meant for stride >= 2 (ResNet's 3 x 3 / 2 after the stem). */
+int sgb_maxpool_bwd_bf16(const sgb_bf16* dy, int N, int H, int W, int C, int k, int stride, int pad, int P, int Q,
+                         int dy_pitch, int dy_off, const uint8_t* idx, sgb_bf16* dx, int dx_pitch, void* stream);
 /* y[slice] = a*x1 + b*x2 (x2 optional) over NHWC bf16 slices: concat copies, residual adds, grad accumulation */
 int sgb_axpby(const sgb_bf16* x1, int p1, int o1, float a, const sgb_bf16* x2, int p2, int o2, float b, sgb_bf16* y,
               int py, int oy, int64_t M, int C, void* stream);

@@ -622,6 +622,10 @@ def maxpool_fwd(x, k, stride, pad, want_idx=True, out=None):
 def maxpool_bwd(dy, idx, x_shape, k, stride, pad):
     n, c, h, w = x_shape
     dy = as_nhwc(dy)
+    if stride >= 2 and c % 8 == 0:  # few windows per input pixel: gather, bf16 out (no memset / atomics / conversion pass)
+        dxb = empty_nhwc(n, c, h, w, dy.device)
+        _timed("sgb_maxpool_bwd_bf16", _ptr(dy), n, h, w, c, k, stride, pad, dy.shape[2], dy.shape[3], nhwc_pitch(dy), 0, _ptr(idx), _ptr(dxb), nhwc_pitch(dxb), _stream())
+        return dxb
     dx = torch.zeros((n, h, w, c), dtype=torch.float32, device=dy.device)
     _timed("sgb_maxpool_bwd", _ptr(dy), n, h, w, c, k, stride, pad, dy.shape[2], dy.shape[3], nhwc_pitch(dy), 0, _ptr(idx), _ptr(dx), _stream())
     return dx.permute(0, 3, 1, 2)  # NCHW-shaped view of NHWC fp32 storage

@@ -184,6 +184,7 @@ _SIGNATURES = {
     "sgb_qarep_bwd_fused": (c_int, [POINTER(QarepDesc)] + [P] * 15),
     "sgb_maxpool_fwd": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, _I, _I, _I, _I, P, P]),
     "sgb_maxpool_bwd": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, P, P]),
+    "sgb_maxpool_bwd_bf16": (c_int, [P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, P, P, _I, P]),
     "sgb_axpby": (c_int, [P, _I, _I, _F, P, _I, _I, _F, P, _I, _I, _L, _I, P]),
     "sgb_scale_add": (c_int, [P, _I, _I, P, P, _I, _I, P, _I, _I, _L, _I, P]),
     "sgb_channel_dot": (c_int, [P, _I, _I, P, _I, _I, _L, _I, P, P]),

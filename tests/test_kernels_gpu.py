@@ -281,7 +281,11 @@ def test_maxpool_axpby_avgpool():
         dy = torch.randn(ref.shape, generator=g).bfloat16().float()
         (gx,) = torch.autograd.grad(ref, x, dy)
         dx = k.maxpool_bwd(to_nhwc_bf16(dy), idx, x.shape, ks, stride, pad)
-        torch.testing.assert_close(dx.cpu(), gx, rtol=1e-5, atol=1e-5)
+        if stride >= 2:  # gather form: bf16 output, one rounding of the (<= 4 term) fp32 sum
+            assert dx.dtype == torch.bfloat16
+            torch.testing.assert_close(dx.float().cpu(), gx, rtol=2**-8, atol=1e-6)
+        else:
+            torch.testing.assert_close(dx.cpu(), gx, rtol=1e-5, atol=1e-5)
     a = torch.randn(2, 16, 5, 5, generator=g).bfloat16().float()
     b = torch.randn(2, 16, 5, 5, generator=g).bfloat16().float()
     out = k.axpby(to_nhwc_bf16(a), 1.5, to_nhwc_bf16(b), -0.5)
