@@ -650,10 +650,20 @@ class Trainer:
         st = self.step
         osd = ckpt.get("optimizer_state_dict") or {}
         if osd:
-            if osd.get("name") != st.opt_name or list(osd.get("flat_order", [])) != [n for n, _ in st.flat.order]:
+            saved_order, mine_order = list(osd.get("flat_order", [])), [n for n, _ in st.flat.order]
+            if osd.get("name") != st.opt_name or sorted(saved_order) != sorted(mine_order):
                 raise ValueError("the checkpoint's optimizer state does not belong to this model / optimizer")
-            for mine, saved in zip(st.state, osd["state"]):
-                mine.copy_(saved.to(mine.device))
+            if saved_order == mine_order:
+                for mine, saved in zip(st.state, osd["state"]):
+                    mine.copy_(saved.to(mine.device))
+            else:
+                # same parameters, another layout of the flat buffer (FlatState moves parameters that asked to be adjacent): by name
+                off = 0
+                for name in saved_order:
+                    o, k = st.flat.offsets[name]
+                    for mine, saved in zip(st.state, osd["state"]):
+                        mine[o : o + k].copy_(saved[off : off + k].to(mine.device))
+                    off += k
             st.opt_steps = int(osd.get("opt_steps", 0))
         if st.ema_on and ckpt.get("ema_net") is not None:
             ema = ckpt["ema_net"]
