@@ -6,7 +6,7 @@ ROOT="$(cd "$HERE/../.." && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="${SGB_OUT:-$HERE/../libsgb200.so}"   # SGB_OUT / SGB_OBJ: build a variant (e.g. -DSGB_DETERMINISTIC_STATS) next to the default library
 OBJ="${SGB_OBJ:-$HERE/obj}"
-# Default feature set (each measured on B200 in round 2, tools/next_round_gpu_plan.sh variants / determinism):
+# Default feature set (each measured on B200 in round 2, tools/gpu_call.sh; profiles/r2_variants_bench.txt, r2_determinism_repro.txt):
 #   SGB_DETERMINISTIC_STATS  per-warp BatchNorm-statistics slots summed in a fixed order: removes the run-to-run last-bit
 #                            differences of interleaved models at < 1 % cost
 #   SGB_UMMA_WIDE_STORE      256-bit stores in the im2col kernels' fast epilogue (+2 %)
