@@ -612,7 +612,7 @@ KPAD = [__import__("os").environ.get("SGB_KPAD", "1") != "0"]
 
 
 # ------------------------------------------------------------------------------------------------------------ conv + BN stem on patches
-# ResNet's first layer (7 x 7, stride 2, 3 input channels; classification_models/resnet.py:199-200 of the reference) has no tcgen05
+# ResNet's first layer (7 x 7, stride 2, 3 input channels; training/models/classification_models/resnet.py:162 of the reference) has no tcgen05
 # kernel of its own: padded to 16 channels it ran on the mma.sync implicit GEMM at 130-145 TF/s -- 2.2 ms forward + 2.5 ms weight
 # gradient of a 30 ms ResNet-50 step at batch 256.  Like the YOLO-NAS stem it becomes ONE 1 x 1 GEMM over gathered patches
 # (3 * 7 * 7 = 147 patch channels padded to 160): the gather reads the image once, forward and weight gradient are im2col-free
@@ -696,7 +696,7 @@ def conv_bn_act_stem(x, conv, bn, *, act, cache: PatchWeightCache):
 
 
 # ------------------------------------------------------------------------------------------------------------ two conv + BN on one input
-# A CSP layer applies two 1x1 ConvBNAct layers to the same tensor (yolo_stages.py:104-106 of the reference: conv1, conv2).  Separately
+# A CSP layer applies two 1x1 ConvBNAct layers to the same tensor (training/models/detection_models/yolo_nas/yolo_stages.py:134-135, 144-147 of the reference: conv1, conv2).  Separately
 # that is 2 GEMMs reading x twice, 2 BatchNorm passes, and in backward 2 BatchNorm passes, 2 dgrads whose results autograd adds with an
 # ATen kernel (3 more tensor passes over dx), 2 wgrads.  As ONE layer with concatenated output channels: 1 GEMM (x read once), 1
 # BatchNorm launch over K1 + K2 channels (per-channel, so identical arithmetic), backward 1 BatchNorm launch reading the two incoming
@@ -774,7 +774,7 @@ class _DualConvBnAct(torch.autograd.Function):
 
 def dual_conv_bn_act(x, conv1, bn1, conv2, bn2, *, act, cache: ConcatWeightCache):
     """(act(bn1(conv1(x))), act(bn2(conv2(x)))) in training mode as one GEMM + one BatchNorm launch; the caller checked
-    dual_conv_bn_act_ready().  Reference: modules/conv_bn_act_block.py:92-93 applied twice (yolo_stages.py:104-106)."""
+    dual_conv_bn_act_ready().  Reference: modules/conv_bn_act_block.py:92-93 applied twice (training/models/detection_models/yolo_nas/yolo_stages.py:134-135, 144-147)."""
     K.require_cuda(x, "x")
     stride = conv1.stride[0] if isinstance(conv1.stride, (tuple, list)) else conv1.stride
     pad = conv1.padding[0] if isinstance(conv1.padding, (tuple, list)) else conv1.padding

@@ -45,7 +45,8 @@ class YoloNASDFLHead(BaseDetectionModule):
         self._cache_pair = SF.ConcatWeightCache()
 
     def _first_pair(self):
-        """The first cls / reg convolutions read the same tensor (the stem's output): candidates for ONE GEMM (functional.dual_conv_bn_act)."""
+        """The first cls / reg convolutions read the same tensor (the stem's output; training/models/detection_models/yolo_nas/dfl_heads.py:86-92
+        of the reference): candidates for ONE GEMM (functional.dual_conv_bn_act)."""
         a, b = self.cls_convs[0], self.reg_convs[0]
         ok = all(hasattr(m.seq, "bn") and m.seq.conv.bias is None and m.seq.conv.groups == 1 and m._act_code == a._act_code for m in (a, b))
         return (a, b) if ok else None
