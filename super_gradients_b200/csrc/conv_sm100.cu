@@ -59,6 +59,10 @@ struct Params {
   int stats_repl;
   int act;
   int tmem_cols;
+  // b_resident: the whole filter (ntaps x chunks tiles of BN x KC) is loaded ONCE per CTA into its own shared-memory region instead of
+  // being re-streamed from L2 with every k-iteration of every 128-pixel tile (the floor of the stride-2 layers: DESIGN.md section 3).
+  int b_resident;
+  uint32_t b_tile_bytes;
   int dbg;  // SGB_DEBUG_SKIP bit mask (perf experiments only): 1 no stores, 2 no stats, 4 no A loads
 };
 
@@ -83,14 +87,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = p.BN * p.KC * 2;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
-  // control block after the stages
-  const uint32_t ctrl = smem_base + p.stages * stage_bytes;
+  const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : ((b_bytes + 1023u) & ~1023u));
+  // resident filter tiles after the stages, then the control block
+  const uint32_t bres_base = smem_base + p.stages * stage_bytes;
+  const uint32_t ctrl = bres_base + (p.b_resident ? (uint32_t)(p.ntaps * ((p.C + p.KC - 1) / p.KC)) * p.b_tile_bytes : 0u);
   auto full_bar = [&](int s) { return ctrl + 8u * s; };
   auto empty_bar = [&](int s) { return ctrl + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int b) { return ctrl + 8u * (2 * MAX_STAGES + b); };
   auto tempty_bar = [&](int b) { return ctrl + 8u * (2 * MAX_STAGES + 2 + b); };
   const uint32_t tmem_slot = ctrl + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t bres_bar = tmem_slot + 8u;  // second half of the 16-byte slot
   float* s_stats = reinterpret_cast<float*>(smem_raw + (ctrl - smem_u32(smem_raw)) + 8u * (2 * MAX_STAGES + 4) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,6 +114,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 4);
     }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -127,6 +134,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int it = 0, stg = 0;
       uint32_t par = 1;  // parity awaited on the empty barriers: the first pass through the ring is free
       const int pq = p.P * p.Q;
+      if (p.b_resident && (int)blockIdx.x < total_tiles) {  // the whole filter, once (n_tiles == 1)
+        mbar_expect_tx(bres_bar, (uint32_t)k_iters * b_bytes);
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int ck = 0; ck < chunks; ++ck)
+            tma_load_2d(bres_base + (uint32_t)(tap * chunks + ck) * p.b_tile_bytes, &map_b, bres_bar, p.tap_b[tap] * p.b_cols_per_tap + ck * p.KC, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
         const int m0 = mt * BLOCK_M;
@@ -142,11 +155,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const bool tr = (p.dbg & 16) && blockIdx.x == 0 && it < 512;
             if (tr) g_trace[0][it] = clock64();
             const uint32_t sa = smem_base + stg * stage_bytes, sb = sa + a_bytes;
-            mbar_expect_tx(full_bar(stg), ((p.dbg & 4) ? 0u : a_bytes) + b_bytes);
+            mbar_expect_tx(full_bar(stg), ((p.dbg & 4) ? 0u : a_bytes) + (p.b_resident ? 0u : b_bytes));
             if (tr) g_trace[4][it] = clock64();
             if (!(p.dbg & 4)) tma_load_im2col_4d(sa, &map_a, full_bar(stg), ck * p.KC, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             if (tr) g_trace[5][it] = clock64();
-            tma_load_2d(sb, &map_b, full_bar(stg), btap * p.b_cols_per_tap + ck * p.KC, nt * p.BN);
+            if (!p.b_resident) tma_load_2d(sb, &map_b, full_bar(stg), btap * p.b_cols_per_tap + ck * p.KC, nt * p.BN);
             if (tr) g_trace[1][it] = clock64();
             if (++stg == p.stages) {
               stg = 0;
@@ -165,6 +178,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t ksteps = (uint32_t)p.KC / 16;
     int it = 0, tcount = 0, stg = 0;
     uint32_t par = 0;
+    if (p.b_resident && (int)blockIdx.x < total_tiles) {
+      mbar_wait(bres_bar, 0);
+      tcgen05_fence_after();
+    }
+    const uint32_t bres16 = bres_base >> 4, btile16 = p.b_tile_bytes >> 4;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
       const uint32_t apar = ((tcount >> 1) & 1) ^ 1;
@@ -176,7 +194,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(full_bar(stg), par);
         if (tr0) g_trace[2][it] = clock64();
         tcgen05_fence_after();
-        const uint32_t sa = (smem_base + stg * stage_bytes) >> 4, sb = sa + (a_bytes >> 4);
+        const uint32_t sa = (smem_base + stg * stage_bytes) >> 4, sb = p.b_resident ? bres16 + (uint32_t)k * btile16 : sa + (a_bytes >> 4);
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
           // advance 16 bf16 (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -751,8 +769,19 @@ int launch(const Problem& q, cudaStream_t st) {
   // A CTA's pipeline is latency-bound when its k-iterations are small (few channels per tap): co-resident CTAs overlap
   // each other's TMA / MMA / epilogue chains.  Limits: TMEM columns (512 per SM), registers (64K per SM), shared memory.
   const uint32_t a_bytes = BLOCK_M * p.KC * 2, b_bytes = bn * p.KC * 2;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + SGB_STATS_SLOTS * 2 * p.N * 4 + 64;
+  p.b_tile_bytes = (b_bytes + 1023u) & ~1023u;
+  const uint32_t bres_all = (uint32_t)(p.ntaps * ((p.C + p.KC - 1) / p.KC)) * p.b_tile_bytes;
+  {
+    static int bres_on = -1;
+    if (bres_on < 0) {
+      const char* e = getenv("SGB_UMMA_B_RESIDENT");
+      bres_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    // worth it when every CTA walks many tiles (the filter load is amortised) and the filter leaves room for a deep A ring
+    p.b_resident = (bres_on && n_tiles == 1 && bres_all <= 112u * 1024u && m_tiles >= 4 * g_num_sms && 2 * b_bytes >= a_bytes) ? 1 : 0;  // BN >= 64: narrow filters gain nothing (measured)
+  }
+  const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : p.b_tile_bytes);
+  const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + SGB_STATS_SLOTS * 2 * p.N * 4 + 64 + (p.b_resident ? bres_all : 0u);
   int ctas_per_sm = 3;
   {
     const char* e = getenv("SGB_CTAS_PER_SM");
