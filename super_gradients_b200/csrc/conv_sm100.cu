@@ -772,13 +772,15 @@ int launch(const Problem& q, cudaStream_t st) {
   p.b_tile_bytes = (b_bytes + 1023u) & ~1023u;
   const uint32_t bres_all = (uint32_t)(p.ntaps * ((p.C + p.KC - 1) / p.KC)) * p.b_tile_bytes;
   {
-    static int bres_on = -1;
+    static int bres_on = -1, bres_min = 4;
     if (bres_on < 0) {
       const char* e = getenv("SGB_UMMA_B_RESIDENT");
       bres_on = (e && e[0] == '0') ? 0 : 1;
+      const char* m = getenv("SGB_UMMA_B_RESIDENT_MINTILES");  // tiles per SM from which the one-off filter load pays
+      if (m && atoi(m) > 0) bres_min = atoi(m);
     }
     // worth it when every CTA walks many tiles (the filter load is amortised) and the filter leaves room for a deep A ring
-    p.b_resident = (bres_on && n_tiles == 1 && bres_all <= 112u * 1024u && m_tiles >= 4 * g_num_sms && 2 * b_bytes >= a_bytes) ? 1 : 0;  // BN >= 64: narrow filters gain nothing (measured)
+    p.b_resident = (bres_on && n_tiles == 1 && bres_all <= 112u * 1024u && m_tiles >= bres_min * g_num_sms && 2 * b_bytes >= a_bytes) ? 1 : 0;  // BN >= 64: narrow filters gain nothing (measured)
   }
   const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : p.b_tile_bytes);
   const uint32_t ctrl_bytes = 8 * (2 * MAX_STAGES + 4) + 16 + SGB_STATS_SLOTS * 2 * p.N * 4 + 64 + (p.b_resident ? bres_all : 0u);
