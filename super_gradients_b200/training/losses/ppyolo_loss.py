@@ -5,8 +5,11 @@ GIoU + DFL, normalisation by max(sum(assigned_scores), 1), weights 1.0 / 2.5 / 0
 host with a FIXED n_max (static shapes, CUDA-graph friendly) instead of the reference's per-image Python loop; the
 assigner (3 small kernels) and the fused loss forward+backward (1 kernel) replace ~60 eager kernels and 3 host syncs.
 
-Deviations (documented in DESIGN.md): ATSS static assigner and focal loss are not implemented (the YOLO-NAS recipe uses
-TAL + varifocal); under DDP the normaliser is per-rank unless `sync_normaliser=True`.
+Both assigners of the reference are served: the task-aligned one (`use_static_assigner=False`, the YOLO-NAS recipes) by
+`sgb_tal_assign`, the ATSS static one (`use_static_assigner=True`, the constructor default as in the reference) by `sgb_atss_assign`;
+`use_varifocal_loss=False` swaps the classification term for the focal pass (`sgb_focal_cls_fwd_bwd`).  All of them are parity-tested on
+B200 against the reference's recorded values (tests/test_zz_pose_train_gpu.py).  Deviation: under DDP the
+normaliser is per rank unless `sync_normaliser=True`.
 """
 from typing import Optional, Tuple, Union
 

@@ -491,8 +491,16 @@ class Trainer:
                 lr = self._lr_at(tp, gstep, steps_per_epoch)
                 do_step = (batch_idx + 1 + steps_per_epoch * epoch) % acc == 0
                 self.step.set_hyper_params(lr, ema_decay(ema_p["decay_type"], float(ema_p["decay"]), gstep + 1, total_steps, float(ema_p.get("beta", 15))) if tp["ema"] else None)
-                if tp["cuda_graph"] and self.step.graph is None and torch.is_tensor(targets) and targets.is_cuda:
-                    self.step.capture(inputs, targets)
+                if tp["cuda_graph"] and self.step.graph is None:
+                    if torch.is_tensor(targets) and targets.is_cuda:
+                        self.step.capture(inputs, targets)
+                    elif not getattr(self, "_warned_no_graph", False):
+                        # detection / pose targets stay on the host (ragged per-image lists padded by the loss): the step runs eagerly
+                        import warnings
+
+                        warnings.warn("training_params['cuda_graph'] is set but the targets are not a device tensor (detection / pose losses pad them on the "
+                                      "host): the train step runs without a CUDA graph; TrainStep.capture() with device-resident padded targets (bench.py) captures it")
+                        self._warned_no_graph = True
                 if handler.callbacks:
                     context.update_context(batch_idx=batch_idx, inputs=inputs, target=targets, lr=lr)
                     handler.fire("on_train_batch_start", context)
