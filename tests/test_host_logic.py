@@ -373,3 +373,58 @@ def test_export_decoding_modules_match_the_reference():
     ) % (root,)
     out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "same as the reference" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_flat_state_adjacency_requests_and_checkpoint_remap(tmp_path):
+    """FlatState lays tensors that a module asks for (`sgb_adjacent_tensors`) back to back -- parameters, their gradient slots and the
+    BatchNorm statistics -- without changing the decay / no-decay membership or anything else's relative order, ignores requests it
+    cannot honour (members of different groups), and an optimizer state saved under another layout is restored by name."""
+    import torch
+    from torch import nn
+
+    from super_gradients_b200.training.flat_state import FlatState, _apply_adjacency
+
+    class Pair(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.mid, self.b = nn.BatchNorm2d(8), nn.Conv2d(8, 8, 1), nn.BatchNorm2d(8)
+
+        def sgb_adjacent_tensors(self):
+            return [[self.a.weight, self.b.weight], [self.a.bias, self.b.bias], [self.a.running_mean, self.b.running_mean],
+                    [self.a.running_var, self.b.running_var], [self.mid.weight, self.a.weight]]  # the last one mixes decay groups: ignored
+
+    def follows(x, y):
+        return y.data_ptr() == x.data_ptr() + x.numel() * x.element_size()
+
+    torch.manual_seed(0)
+    m = Pair()
+    ref = {k: v.clone() for k, v in m.state_dict().items()}
+    fs = FlatState(m)
+    assert follows(m.a.weight, m.b.weight) and follows(m.a.bias, m.b.bias) and follows(m.a.running_mean, m.b.running_mean) and follows(m.a.running_var, m.b.running_var)
+    assert follows(m.a.weight.main_grad, m.b.weight.main_grad) and follows(m.a.bias.main_grad, m.b.bias.main_grad)
+    for k, v in m.state_dict().items():  # values untouched by the re-pointing
+        assert torch.equal(v, ref[k]), k
+    names = [n for n, _ in fs.order]
+    assert names[: names.index("a.weight")] == ["mid.weight"]  # the decaying filter first, the no-decay group after it
+    assert names.index("b.weight") == names.index("a.weight") + 1 and names.index("b.bias") == names.index("a.bias") + 1
+    assert sorted(names) == sorted(n for n, _ in m.named_parameters())
+    # the helper alone: groups with a missing member are skipped, followers keep group order
+    t = [torch.zeros(1) for _ in range(5)]
+    items = list(zip("abcde", t))
+    assert [n for n, _ in _apply_adjacency(items, [[t[1], t[4], t[3]], [t[0], torch.zeros(1)]])] == ["a", "b", "e", "d", "c"]
+    # optimizer state saved under another flat layout (e.g. a checkpoint written before an adjacency request existed): restored by name
+    from types import SimpleNamespace
+
+    from super_gradients_b200.training.sg_trainer import Trainer
+
+    saved_order = sorted(names)  # some other order of the same parameters
+    sizes = {n: p.numel() for n, p in m.named_parameters()}
+    saved_state = torch.cat([torch.full((sizes[n],), float(i)) for i, n in enumerate(saved_order)])
+    step = SimpleNamespace(opt_name="SGD", flat=fs, state=[torch.zeros(fs.n_live)], opt_steps=0, ema_on=False)
+    Trainer._restore_training_state(SimpleNamespace(step=step), {"optimizer_state_dict": {"name": "SGD", "flat_order": saved_order, "state": [saved_state], "opt_steps": 7}})
+    assert step.opt_steps == 7
+    for i, n in enumerate(saved_order):
+        off, k = fs.offsets[n]
+        assert bool((step.state[0][off : off + k] == float(i)).all()), n
+    with pytest.raises(ValueError, match="optimizer"):
+        Trainer._restore_training_state(SimpleNamespace(step=step), {"optimizer_state_dict": {"name": "SGD", "flat_order": saved_order[:-1], "state": [saved_state], "opt_steps": 7}})
