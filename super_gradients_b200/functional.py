@@ -719,6 +719,8 @@ def dual_conv_bn_act_ready(conv1, bn1, conv2, bn2) -> bool:
         return False
     if bn1.eps != bn2.eps or bn1.momentum != bn2.momentum or bn1.running_mean is None or bn2.running_mean is None:
         return False
+    if not (bn1.training and bn2.training):  # a frozen BatchNorm (eval() on the sub-module) normalises with its running statistics
+        return False
     pairs = [(bn1.weight, bn2.weight), (bn1.bias, bn2.bias), (bn1.running_mean, bn2.running_mean), (bn1.running_var, bn2.running_var)]
     if not all(_follows(a, b) for a, b in pairs):
         return False
