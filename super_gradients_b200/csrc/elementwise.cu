@@ -110,6 +110,56 @@ __global__ void weight_prepare_kernel(const float* __restrict__ w, int K, int C,
     weight_prepare_elem(w, K, C, R, S, cp, krsc, crsk, sc, add_identity, i);
 }
 
+// Elements i and i + 1 (i even) of the same index space: they share (k, r, s) in the KRSC part and (c, r, s) in the CRSK part (c_pad
+// and Kp are multiples of 8), so the index arithmetic is done once and the two bf16 values leave as one 32-bit store.
+__device__ __forceinline__ void weight_prepare_pair(const float* __restrict__ w, int K, int C, int R, int S, int cp, bf16* krsc, bf16* crsk, float sc,
+                                                    int add_identity, int64_t i64, int kp, int koff, int etaps, int etap) {
+  const uint32_t Kp = (uint32_t)((K + 7) / 8) * 8, uC = (uint32_t)C, uR = (uint32_t)R, uS = (uint32_t)S, ucp = (uint32_t)cp;
+  const uint32_t n1 = (uint32_t)K * uR * uS * ucp;
+  const uint32_t i = (uint32_t)i64;
+  const uint32_t rs = uR * uS;
+  if (i < n1) {
+    const uint32_t c = i % ucp;
+    uint32_t t = i / ucp;
+    uint32_t s = 0, r = 0;
+    if (rs != 1) {
+      s = t % uS; t /= uS;
+      r = t % uR; t /= uR;
+    }
+    const uint32_t k = t;
+    const float* src = w + ((k * uC + c) * uR + r) * uS + s;  // element (k, c, r, s); (k, c + 1, r, s) is rs floats further
+    float v0 = 0.f, v1 = 0.f;
+    const bool centre = add_identity && r == uR / 2 && s == uS / 2;
+    if (c < uC) v0 = src[0] * sc + ((centre && k == c) ? 1.f : 0.f);
+    if (c + 1 < uC) v1 = src[rs] * sc + ((centre && k == c + 1) ? 1.f : 0.f);
+    const uint32_t dst = etaps > 0 ? (k * (uint32_t)etaps + (uint32_t)etap) * ucp + c : i;
+    *reinterpret_cast<__nv_bfloat162*>(krsc + dst) = __floats2bfloat162_rn(v0, v1);
+  } else {
+    const uint32_t j = i - n1;
+    const uint32_t k = j % Kp;
+    uint32_t t = j / Kp;
+    uint32_t s = 0, r = 0;
+    if (rs != 1) {
+      s = t % uS; t /= uS;
+      r = t % uR; t /= uR;
+    }
+    const uint32_t c = t;
+    const float* src = w + ((k * uC + c) * uR + r) * uS + s;  // (k + 1, c, r, s) is C * rs floats further
+    const bool ok0 = k < (uint32_t)K, ok1 = k + 1 < (uint32_t)K;
+    const bool centre = add_identity && r == uR / 2 && s == uS / 2;
+    const float v0 = ok0 ? src[0] * sc + ((centre && k == c) ? 1.f : 0.f) : 0.f;
+    const float v1 = ok1 ? src[uC * rs] * sc + ((centre && k + 1 == c) ? 1.f : 0.f) : 0.f;
+    if (kp > 0 || etaps > 0) {
+      const uint32_t row = etaps > 0 ? c * (uint32_t)etaps + (uint32_t)etap : (c * uR + r) * uS + s;
+      bf16* d = crsk + (size_t)row * (uint32_t)(kp > 0 ? kp : (int)Kp) + (uint32_t)koff + k;
+      if (ok1) *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(v0, v1);  // koff and k are even: 4-byte aligned
+      else if (ok0) d[0] = __float2bfloat16_rn(v0);
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(crsk + j) = __floats2bfloat162_rn(v0, v1);
+    }
+  }
+}
+
 // element i of the fp32 OIHW gradient gathered from the fp32 KRSC accumulation buffer
 __device__ __forceinline__ void wgrad_to_oihw_elem(const float* __restrict__ dw, int C, int R, int S, int cp, float* g,
                                                    int accumulate, int64_t i64) {
@@ -148,7 +198,9 @@ __device__ __forceinline__ int find_item(const Item* items, int n, int64_t i) {
 // the item of the chunk's first element, and a thread re-searches only when its element lies past that item's end (a chunk
 // straddling two filters).  The first version searched per element (8 dependent loads for ~200 items): 295 us for 19 M weights.
 constexpr int BATCH_CHUNK = 2048;
-template <class Item, class Fn>
+// UNIT: elements per call of fn (1, or 2 when every item starts at an even offset and has an even length): fn(it, local) gets the
+// offset of its first element inside the item.
+template <int UNIT = 1, class Item, class Fn>
 __device__ __forceinline__ void batch_walk(const Item* __restrict__ items, int n, int64_t total, Fn&& fn) {
   __shared__ int s_first;
   for (int64_t c0 = (int64_t)blockIdx.x * BATCH_CHUNK; c0 < total; c0 += (int64_t)gridDim.x * BATCH_CHUNK) {
@@ -158,7 +210,7 @@ __device__ __forceinline__ void batch_walk(const Item* __restrict__ items, int n
     int idx = s_first;
     Item it = items[idx];
     int64_t end = idx + 1 < n ? items[idx + 1].start : total;
-    for (int64_t i = c0 + threadIdx.x; i < c0 + BATCH_CHUNK && i < total; i += blockDim.x) {
+    for (int64_t i = c0 + (int64_t)threadIdx.x * UNIT; i < c0 + BATCH_CHUNK && i < total; i += (int64_t)blockDim.x * UNIT) {
       while (i >= end) {  // next filter (filters are much longer than a chunk is wide, so this runs at most a few times)
         ++idx;
         it = items[idx];
@@ -172,8 +224,10 @@ __device__ __forceinline__ void batch_walk(const Item* __restrict__ items, int n
 __global__ void __launch_bounds__(TPB) weight_prepare_batch_kernel(const SgbWeightItem* __restrict__ items, int n, int64_t total) {
   SGB_GRID_DEP_LAUNCH();
   SGB_GRID_DEP_WAIT();
-  batch_walk(items, n, total, [](const SgbWeightItem& it, int64_t local) {
-    weight_prepare_elem(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f, it.add_identity, local, it.kp,
+  // every filter's index space has an even number of elements starting at an even offset: the walk runs over PAIRS (half the index
+  // arithmetic, 32-bit stores)
+  batch_walk<2>(items, n, total, [](const SgbWeightItem& it, int64_t local) {
+    weight_prepare_pair(it.w, it.K, it.C, it.R, it.S, it.c_pad, (bf16*)it.krsc, (bf16*)it.crsk, it.scale ? *it.scale : 1.f, it.add_identity, local, it.kp,
                         it.koff, it.etaps, it.etap);
   });
 }
