@@ -625,8 +625,13 @@ def conv_stem_patches_supported(conv, bn, x, training) -> bool:
         return False
     w = conv.weight
     r, s = w.shape[2], w.shape[3]
+    stride = conv.stride[0] if isinstance(conv.stride, (tuple, list)) else conv.stride
+    if isinstance(conv.stride, (tuple, list)) and len(set(conv.stride)) != 1:
+        return False
+    # the gather stages C * R input rows of (128 - 1) * stride + R pixels in shared memory (sgb_stem_patches_f32: 48 KB)
+    staged = w.shape[1] * r * ((128 - 1) * int(stride) + r) * 4 + (((w.shape[1] * r * s + 31) // 32) * 32) * 4
     return bool(conv.bias is None and conv.groups == 1 and r == s and r > 1 and x.shape[1] == w.shape[1] and w.shape[1] % 8 != 0
-                and w.shape[1] * r * s <= STEM_PATCH_MAX_CHANNELS and w.shape[0] % 8 == 0)  # fmt: skip
+                and w.shape[1] * r * s <= STEM_PATCH_MAX_CHANNELS and w.shape[0] % 8 == 0 and staged + 64 <= 48 * 1024)  # fmt: skip
 
 
 class PatchWeightCache:
