@@ -491,6 +491,9 @@ def bn_act_bwd(dy, x, y, gamma, mean, rstd, eps, act, want_residual_grad=False, 
     functional._DualConvBnAct); both are read in place (SgbBnDesc.dy2).  y may be None when the mask is recomputed from x."""
     n, c, h, w = x.shape
     dy = as_nhwc(dy)
+    if act_code(act) not in (ACT_NONE, ACT_RELU):
+        # the backward passes apply the ReLU mask only; SiLU exists as a forward / inference epilogue (PP-YOLOE-style heads)
+        raise L.SgbError("bn_act_bwd: only identity / ReLU activations have a backward pass in super_gradients_b200")
     d = bn_desc(x, y if y is not None else x, eps, 0.0, act, None, 1, sample_scale=sample_scale)
     if dy2 is not None:
         dy2 = as_nhwc(dy2)
@@ -583,6 +586,8 @@ def qarep_bwd(dout, out, y3, u, coef, gamma3, gamma_p, eps3, eps_post, act, use_
     y3 / u are slices); by default dense tensors are allocated, which requires dense y3 / u."""
     n, c, h, w = y3.shape
     dout = as_nhwc(dout)
+    if act_code(act) not in (ACT_NONE, ACT_RELU):
+        raise L.SgbError("qarep_bwd: only identity / ReLU activations have a backward pass in super_gradients_b200")
     d = qarep_desc(y3, u, out, eps3, eps_post, 0.0, act, use_post_bn)
     if nhwc_pitch(dout) != nhwc_pitch(out):
         if nhwc_pitch(dout) % 8 == 0 and dout.data_ptr() % 16 == 0:  # a concat's gradient slice: read in place
