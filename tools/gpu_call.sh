@@ -67,12 +67,12 @@ case "${1}" in
       SGB_WGRAD_WIDE_N=$wn timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench12_$wn.err | tee gpurun_out/r2_bench12_$wn.json | bench_line; tail -2 gpurun_out/r2_bench12_$wn.err; done
     SHAPES="32,48,320,320,96,3,2;32,96,160,160,192,3,2;32,96,160,160,96,3,2;32,192,80,80,384,3,2;32,96,160,160,64,1,1" timeout 120 python tools/conv_microbench.py wgrad
     timeout 300 python tools/timeline.py > gpurun_out/r2_timeline12.txt 2>gpurun_out/r2_timeline12.err; head -30 gpurun_out/r2_timeline12.txt; tail -3 gpurun_out/r2_timeline12.err ;;
-  thirteenth)  # two M tiles per filter tile in the im2col kernel, filter re-layout next to the stem gather
+  thirteenth)  # (historical: both experiments measured slower / neutral and were reverted -- SGB_UMMA_MSUB and SGB_OVERLAP_PREPARE no longer exist) two M tiles per filter tile in the im2col kernel, filter re-layout next to the stem gather
     timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py tests/test_trainer_gpu.py -m gpu -q --tb=short --timeout 300 -x > gpurun_out/r2_pytest13.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2_pytest13.log
     for cfg in "1 1" "0 1" "1 0"; do set -- $cfg; printf "UMMA_MSUB=%s OVERLAP_PREPARE=%s: " $1 $2
       SGB_UMMA_MSUB=$1 SGB_OVERLAP_PREPARE=$2 timeout 400 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench13_$1$2.err | tee gpurun_out/r2_bench13_$1$2.json | bench_line; tail -2 gpurun_out/r2_bench13_$1$2.err; done
     for mode in fprop dgrad; do SHAPES="32,48,320,320,96,3,2;32,96,160,160,192,3,2;32,96,160,160,96,3,2;32,192,80,80,384,3,2;32,48,320,320,96,1,2" timeout 120 python tools/conv_microbench.py $mode; done ;;
-  fourteenth)  # filter re-layout next to the stem gather (A/B) after reverting the two-M-tile experiment (slower: 1840 -> 1748 img/s)
+  fourteenth)  # (historical: SGB_OVERLAP_PREPARE no longer exists) filter re-layout next to the stem gather (A/B) after reverting the two-M-tile experiment (slower: 1840 -> 1748 img/s)
     timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short --timeout 300 -x -k "conv_fprop" > gpurun_out/r2_pytest14.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest14.log
     for cfg in 1 0 1 0; do printf "OVERLAP_PREPARE=%s: " $cfg
       SGB_OVERLAP_PREPARE=$cfg timeout 400 python bench.py --steps 30 --warmup 5 --skip-cpu-baseline 2>gpurun_out/r2_bench14_$cfg.err | tee gpurun_out/r2_bench14_$cfg.json | bench_line; tail -2 gpurun_out/r2_bench14_$cfg.err; done ;;
