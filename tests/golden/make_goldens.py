@@ -576,6 +576,36 @@ def golden_other_configs():
     torch.save(out, os.path.join(HERE, "other_configs.pt"))
 
 
+def golden_port_fidelity():
+    """The workload of `bench.py --impl reference` / `cpu_baseline` (BASELINE config 2 on a 2-image sample): the UNMODIFIED reference's
+    YOLO-NAS-S, loaded with exactly the state the oracle port starts from (oracle.yolo_nas_oracle.random_state(seed 0)) and fed the
+    bench's own synthetic batch (bench.synth_batch(2, 123, 640)), one fp32 train-mode forward + PPYoloELoss(TAL) + backward on CPU.
+    Only scalars are stored (loss, its components, a checksum of the raw head outputs, per-parameter gradient norms): the test that
+    reads this file (tests/test_oracle_golden.py::test_bench_cpu_port_is_the_reference_train_step) times nothing."""
+    import bench
+    from oracle.yolo_nas_oracle import random_state
+    from super_gradients.training import models
+    from super_gradients.training.losses.ppyolo_loss import PPYoloELoss
+
+    table = torch.load(os.path.join(HERE, "state_keys.pt"), weights_only=False)
+    state = random_state(table["yolo_nas_s"], seed=0)
+    m = models.get("yolo_nas_s", num_classes=bench.NCLS)
+    missing, unexpected = m.load_state_dict({k: v.clone() for k, v in state.items()}, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k or "id_tensor" in k for k in missing), (missing, unexpected)
+    m.train()
+    x, t = bench.synth_batch(2, 123, 640)
+    outputs = m(x)
+    raw = outputs[1] if isinstance(outputs, tuple) and len(outputs) == 2 else outputs
+    loss, items = PPYoloELoss(num_classes=bench.NCLS, use_static_assigner=False)(outputs, t)
+    loss.backward()
+    grad_norms = {k: float(p.grad.norm()) for k, p in m.named_parameters() if p.grad is not None}
+    out = dict(loss=float(loss.detach()), items=[float(v) for v in items.detach().reshape(-1)], cls_logits_sum=float(raw[0].detach().double().sum()),
+               cls_logits_abs=float(raw[0].detach().double().abs().sum()), reg_distri_abs=float(raw[1].detach().double().abs().sum()), grad_norms=grad_norms,
+               n_targets=int(t.shape[0]) if torch.is_tensor(t) else len(t))  # fmt: skip
+    print("port fidelity: reference loss", out["loss"], out["items"], "params with gradients", len(grad_norms))
+    torch.save(out, os.path.join(HERE, "port_fidelity_2x640.pt"))
+
+
 def golden_lr_schedules():
     """LR actually in the optimizer at every optimisation step, produced by the reference's own warm-up / scheduler callbacks driven in
     the order of Trainer._train_epoch (epoch-start callbacks, per batch: batch-start callbacks -> optimizer step -> TRAIN_BATCH_STEP
@@ -853,7 +883,7 @@ def golden_droppath():
 
 if __name__ == "__main__":
     ref_shim.install()
-    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "atss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train", "other_configs"]
+    which = sys.argv[1:] or ["qarepvgg", "conv_blocks", "loss", "atss", "nms", "yolox_nms", "processing", "detection_metrics", "lr_schedules", "param_groups", "pose_nms", "pose", "tiny_yolo_nas", "tiny_yolo_nas_pose", "tiny_yolo_nas_pose_train", "state_keys", "resnet_cifar_train", "other_configs", "port_fidelity"]
     for w in which:
         print("generating", w, flush=True)
         globals()["golden_" + w]()

@@ -381,3 +381,33 @@ def test_yolox_nms_oracle_matches_reference(golden, case):
         assert (mine is None) == (ref is None)
         if ref is not None:
             np.testing.assert_array_equal(mine, ref.numpy())
+
+
+def test_bench_cpu_port_is_the_reference_train_step(golden):
+    """`bench.py --impl reference` and the `cpu_baseline` leg time the oracle PORT of the train step (the reference tree does not exist
+    on the GPU box).  This pins that port at the benchmarked workload itself -- YOLO-NAS-S, the bench's synthetic batch, a 2-image
+    640 x 640 sample, the state `bench.cpu_step_fn` starts from -- against the UNMODIFIED reference run once in the build container
+    (tests/golden/make_goldens.py::golden_port_fidelity, via oracle/ref_shim.py): loss, its three components, checksums of the raw
+    head outputs and every parameter's gradient norm.  Nothing is timed here."""
+    import bench
+    from oracle.yolo_nas_oracle import random_state, train_step
+
+    g = golden("port_fidelity_2x640")
+    table = golden("state_keys")
+    state = random_state(table["yolo_nas_s"], seed=0)
+    live = [k for k in table["yolo_nas_s/param_names"] if "rbr_reparam" not in k]
+    x, t = bench.synth_batch(2, 123, 640)
+    assert int(t.shape[0]) == g["n_targets"]
+    loss, items, grads = train_step(bench._arch_yaml("yolo_nas_s"), state, x, t, bench.NCLS, live)
+    assert abs(float(loss) - g["loss"]) <= 1e-4 * abs(g["loss"]), (float(loss), g["loss"])
+    for mine, ref in zip(items.reshape(-1).tolist(), g["items"]):
+        assert abs(mine - ref) <= 1e-4 * abs(ref) + 1e-6, (mine, ref)
+    assert set(grads) == set(g["grad_norms"]), set(grads) ^ set(g["grad_norms"])
+    # Parameters whose gradient is identically zero -- biases in front of a BatchNorm (branch_3x3.bn.bias / branch_1x1.bias of a
+    # QARepVGG block behind post_bn, the up-sampling ConvTranspose's bias) and the regression branches of pyramid levels without a
+    # positive anchor in this sample -- hold fp32 round-off (< 2e-4 against norms up to 3.6e3) or an exact 0 on both sides.
+    scale = max(g["grad_norms"].values())
+    noise = [k for k in grads if g["grad_norms"][k] < 1e-7 * scale]
+    assert any(k.endswith("branch_1x1.bias") for k in noise) and all(float(grads[k].norm()) < 1e-6 * scale for k in noise)
+    worst = max(abs(float(v.norm()) - g["grad_norms"][k]) / g["grad_norms"][k] for k, v in grads.items() if k not in noise)
+    assert worst < 5e-4, worst  # measured 5.4e-5
