@@ -407,7 +407,8 @@ def test_bench_cpu_port_is_the_reference_train_step(golden):
     # QARepVGG block behind post_bn, the up-sampling ConvTranspose's bias) and the regression branches of pyramid levels without a
     # positive anchor in this sample -- hold fp32 round-off (< 2e-4 against norms up to 3.6e3) or an exact 0 on both sides.
     scale = max(g["grad_norms"].values())
-    noise = [k for k in grads if g["grad_norms"][k] < 1e-7 * scale]
+    noise = [k for k in grads if g["grad_norms"][k] < 1e-6 * scale]  # 3.6e-3; the largest round-off norm is 1.1e-3 (stem, 204 800 pixels per image)
     assert any(k.endswith("branch_1x1.bias") for k in noise) and all(float(grads[k].norm()) < 1e-6 * scale for k in noise)
+    assert not any(k.endswith(".weight") and "bn" not in k for k in noise if g["grad_norms"][k] > 0)  # no filter is treated as noise
     worst = max(abs(float(v.norm()) - g["grad_norms"][k]) / g["grad_norms"][k] for k, v in grads.items() if k not in noise)
     assert worst < 5e-4, worst  # measured 5.4e-5
