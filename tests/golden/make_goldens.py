@@ -603,6 +603,22 @@ def golden_port_fidelity():
                cls_logits_abs=float(raw[0].detach().double().abs().sum()), reg_distri_abs=float(raw[1].detach().double().abs().sum()), grad_norms=grad_norms,
                n_targets=int(t.shape[0]) if torch.is_tensor(t) else len(t))  # fmt: skip
     print("port fidelity: reference loss", out["loss"], out["items"], "params with gradients", len(grad_norms))
+    # config 4's CPU arm: ResNet-50 at 224 x 224 on a 4-image sample of the bench's classification batch, the port's own initial state,
+    # drop-path off on both sides (the reference draws its masks from the global RNG inside forward; the port's masks are pinned
+    # separately by droppath.pt)
+    table = torch.load(os.path.join(HERE, "state_keys.pt"), weights_only=False)
+    state = random_state(table["resnet50"], seed=0)
+    m = models.get("resnet50", num_classes=1000)
+    missing, unexpected = torch.nn.Module.load_state_dict(m, {k: v.clone() for k, v in state.items()}, strict=False)  # the reference's override returns None
+    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+    m.train()
+    x, y = bench.synth_cls_batch(4, 123, 224)
+    logits = m(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    out["resnet50"] = dict(loss=float(loss.detach()), logits_abs=float(logits.detach().double().abs().sum()),
+                           grad_norms={k: float(p.grad.norm()) for k, p in m.named_parameters() if p.grad is not None})
+    print("port fidelity: reference resnet50 loss", out["resnet50"]["loss"])
     torch.save(out, os.path.join(HERE, "port_fidelity_2x640.pt"))
 
 

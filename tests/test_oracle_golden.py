@@ -412,3 +412,26 @@ def test_bench_cpu_port_is_the_reference_train_step(golden):
     assert not any(k.endswith(".weight") and "bn" not in k for k in noise if g["grad_norms"][k] > 0)  # no filter is treated as noise
     worst = max(abs(float(v.norm()) - g["grad_norms"][k]) / g["grad_norms"][k] for k, v in grads.items() if k not in noise)
     assert worst < 5e-4, worst  # measured 5.4e-5
+
+
+def test_bench_cpu_port_is_the_reference_resnet50_train_step(golden):
+    """The same pin for config 4's CPU arm (`bench.cpu_step_fn`, kind train_cls): ResNet-50 at 224 x 224 on a 4-image sample of the
+    bench's classification batch, from the port's own initial state, drop-path off on both sides (its masks are pinned by droppath.pt):
+    loss, a checksum of the logits and every parameter's gradient norm against the unmodified reference."""
+    import bench
+    from oracle import resnet_oracle as R
+    from oracle.yolo_nas_oracle import random_state
+
+    g = golden("port_fidelity_2x640")["resnet50"]
+    table = golden("state_keys")
+    state = random_state(table["resnet50"], seed=0)
+    live = list(table["resnet50/param_names"])
+    x, y = bench.synth_cls_batch(4, 123, 224)
+    loss, grads = R.train_step("resnet50", state, x, y, live, droppath_prob=0.0)
+    assert abs(float(loss) - g["loss"]) <= 1e-4 * abs(g["loss"]), (float(loss), g["loss"])
+    assert set(grads) == set(g["grad_norms"])
+    scale = max(g["grad_norms"].values())
+    noise = [k for k in grads if g["grad_norms"][k] < 1e-6 * scale]
+    assert all(float(grads[k].norm()) < 1e-5 * scale for k in noise)
+    worst = max(abs(float(v.norm()) - g["grad_norms"][k]) / g["grad_norms"][k] for k, v in grads.items() if k not in noise)
+    assert worst < 2e-3, worst
